@@ -1,0 +1,593 @@
+// tcgen05 implicit-GEMM convolution kernel + host-side plan (geometry, TMA descriptors, launch).
+// See conv_tc.cuh for the formulation.  Reference semantics: Keras Conv2D(padding='same'),
+// models.py:1177-1199, 1231-1270 (cross-correlation, HWIO kernels, bias, optional ReLU) and the
+// residual algebra of _residual_block_light / _residual_block_light53 (0.1 / 0.9 scalar_mul,
+// models.py:977-986), which is fused here as out = act(alpha*(acc+bias) + beta*res).
+#include "conv_tc.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sr {
+
+namespace {
+
+constexpr int kMaxWStages = 16;
+
+struct __align__(8) ConvBarriers {
+  uint64_t w_full[kMaxWStages];
+  uint64_t w_empty[kMaxWStages];
+  uint64_t a_full[2];
+  uint64_t a_empty[2];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct TileCoord {
+  int n, seg_x0, f0, r_lo, off0;
+};
+
+template <int T>
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& P, int t) {
+  const int per_img = P.nseg * P.tiles_per_seg;
+  TileCoord c;
+  c.n = t / per_img;
+  const int r = t - c.n * per_img;
+  const int seg = r / P.tiles_per_seg;
+  const int ti = r - seg * P.tiles_per_seg;
+  c.seg_x0 = seg * P.BW;
+  c.f0 = P.p * P.PWs + P.p + ti * T;
+  c.r_lo = (ti * T) / P.PWs;  // first strip row, in padded-row units (row 0 = image row -p)
+  c.off0 = c.f0 - c.r_lo * P.PWs;
+  return c;
+}
+
+template <int AMODE>
+__device__ __forceinline__ uint64_t make_a_desc(uint32_t abase, int pix, int k16, uint32_t lbo) {
+  if constexpr (AMODE == kAModeSwizzle64) {
+    // rows of 64 B (32 ch), 8-row groups 512 B apart, 64B swizzle; K advance = 32 B inside the row
+    return umma_smem_desc(abase + (uint32_t)pix * 64u + (uint32_t)k16 * 32u, 16u, 512u,
+                          SR_LAYOUT_SW64);
+  } else {
+    // [8ch group][pixel][8ch]: rows 16 B apart (SBO = 128 B per 8 rows), K core matrices LBO apart
+    return umma_smem_desc(abase + (uint32_t)pix * 16u + (uint32_t)k16 * 2u * lbo, lbo, 128u,
+                          SR_LAYOUT_NONE);
+  }
+}
+
+}  // namespace
+
+template <int N_, int AMODE, int NACC, int NBUF>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
+               const ConvKernelParams P) {
+  constexpr int T = NACC * 128;
+  constexpr int WSTAGE = N_ * kChunk * 2;
+  constexpr uint32_t TM_COLS_RAW = NACC * NBUF * N_;
+  constexpr uint32_t TM_COLS = TM_COLS_RAW <= 32    ? 32
+                               : TM_COLS_RAW <= 64  ? 64
+                               : TM_COLS_RAW <= 128 ? 128
+                               : TM_COLS_RAW <= 256 ? 256
+                                                    : 512;
+  static_assert(TM_COLS_RAW <= 512, "TMEM overflow");
+  constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 128u, (uint32_t)N_);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + 2 * P.a_bytes;
+  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(w_buf + P.num_wstages * WSTAGE);
+  float* s_bias = reinterpret_cast<float*>(bars + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NS = P.num_wstages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bars->w_full[i], 1);
+      mbar_init(&bars->w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 1);
+      mbar_init(&bars->a_empty[i], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmW0);
+    if (P.nsrc > 1) prefetch_tmap(&tmW1);
+  }
+  if (warp == 3 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    if (P.nsrc > 1) prefetch_tmap(&tmA1);
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_base, TM_COLS);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 128) {
+    for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight-stage TMA producer
+    if (lane == 0) {
+      uint32_t ws = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        for (int s = 0; s < P.nsrc; ++s) {
+          const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
+          const int ntaps = P.ksize[s] * P.ksize[s];
+          for (int st = 0; st < kNumChunks * ntaps; ++st) {
+            const uint32_t slot = ws % NS, ph = (ws / NS) & 1;
+            mbar_wait(&bars->w_empty[slot], ph ^ 1);
+            mbar_expect_tx(&bars->w_full[slot], WSTAGE);
+            tma_load_2d(w_buf + slot * WSTAGE, tmW, &bars->w_full[slot], 0, st * N_);
+            ++ws;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------ activation strip TMA producer
+    if (lane == 0) {
+      uint32_t ac = 0;
+      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kChunk * 2;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile<T>(P, t);
+        for (int s = 0; s < P.nsrc; ++s) {
+          const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
+            mbar_wait(&bars->a_empty[slot], ph ^ 1);
+            mbar_expect_tx(&bars->a_full[slot], strip_bytes);
+            if constexpr (AMODE == kAModeSwizzle64) {
+              tma_load_4d(a_buf + slot * P.a_bytes, tmA, &bars->a_full[slot], ch * kChunk,
+                          c.seg_x0 - P.p, c.r_lo - P.p, c.n);
+            } else {
+              tma_load_5d(a_buf + slot * P.a_bytes, tmA, &bars->a_full[slot], 0, c.seg_x0 - P.p,
+                          c.r_lo - P.p, ch * (kChunk / 8), c.n);
+            }
+            ++ac;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      uint32_t ws = 0, ac = 0, it = 0;
+      const uint32_t lbo = (uint32_t)P.NR * P.PWs * 16u;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+        const TileCoord c = decode_tile<T>(P, t);
+        const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+        mbar_wait(&bars->tmem_empty[buf], bph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + buf * (NACC * N_);
+        bool first = true;
+        for (int s = 0; s < P.nsrc; ++s) {
+          const int k = P.ksize[s];
+          const int pk = (k - 1) / 2;
+          const int ntaps = k * k;
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
+            mbar_wait(&bars->a_full[aslot], aph);
+            tc_fence_after();
+            const uint32_t abase = smem_u32(a_buf + aslot * P.a_bytes);
+            int ky = 0, kx = 0;
+            for (int tap = 0; tap < ntaps; ++tap) {
+              const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
+              mbar_wait(&bars->w_full[wslot], wph);
+              tc_fence_after();
+              const uint32_t wbase = smem_u32(w_buf + wslot * WSTAGE);
+              const int shift = c.off0 + (ky - pk) * P.PWs + (kx - pk);
+#pragma unroll
+              for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {
+                  const uint64_t adesc = make_a_desc<AMODE>(abase, shift + acc * 128, k16, lbo);
+                  const uint64_t bdesc =
+                      umma_smem_desc(wbase + (uint32_t)k16 * 32u, 16u, 512u, SR_LAYOUT_SW64);
+                  umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, (first && k16 == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(&bars->w_empty[wslot]);
+              ++ws;
+              if (++kx == k) { kx = 0; ++ky; }
+            }
+            umma_commit(&bars->a_empty[aslot]);
+            ++ac;
+          }
+        }
+        umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile<T>(P, t);
+      const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+      mbar_wait(&bars->tmem_full[buf], bph);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc) {
+        const int f = c.f0 + acc * 128 + ew * 32 + lane;
+        const int fr = f / P.PWs;
+        const int yy = fr - P.p;
+        const int xx = f - fr * P.PWs - P.p;
+        const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                           xx < P.BW && (c.seg_x0 + xx) < P.W;
+        const size_t pix = ((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx;
+        if constexpr (N_ == 128) {
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(t_base + acc * N_ + cb * 32, v);
+            tmem_ld_wait();
+            if (valid) {
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                o[j] = P.alpha * (__uint_as_float(v[j]) + s_bias[cb * 32 + j]);
+              if (P.res_f32) {
+                const float4* rp = reinterpret_cast<const float4*>(P.res_f32 + pix * 128 + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 r = rp[j];
+                  o[4 * j + 0] = fmaf(P.beta, r.x, o[4 * j + 0]);
+                  o[4 * j + 1] = fmaf(P.beta, r.y, o[4 * j + 1]);
+                  o[4 * j + 2] = fmaf(P.beta, r.z, o[4 * j + 2]);
+                  o[4 * j + 3] = fmaf(P.beta, r.w, o[4 * j + 3]);
+                }
+              } else if (P.res_bf16) {
+                const uint4* rp = reinterpret_cast<const uint4*>(P.res_bf16 + pix * 128 + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 r = rp[j];
+                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    o[8 * j + 2 * q] = fmaf(P.beta, __uint_as_float(w[q] << 16), o[8 * j + 2 * q]);
+                    o[8 * j + 2 * q + 1] =
+                        fmaf(P.beta, __uint_as_float(w[q] & 0xFFFF0000u), o[8 * j + 2 * q + 1]);
+                  }
+                }
+              }
+              if (P.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
+              if (P.relu_mask_bf16) {
+                const uint4* mp =
+                    reinterpret_cast<const uint4*>(P.relu_mask_bf16 + pix * 128 + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 r = mp[j];
+                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (!(__uint_as_float(w[q] << 16) > 0.f)) o[8 * j + 2 * q] = 0.f;
+                    if (!(__uint_as_float(w[q] & 0xFFFF0000u) > 0.f)) o[8 * j + 2 * q + 1] = 0.f;
+                  }
+                }
+              }
+              if (P.out_f32) {
+                float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * 128 + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
+              if (P.out_bf16) {
+                uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + pix * 128 + cb * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 h =
+                        __floats2bfloat162_rn(o[8 * j + 2 * q], o[8 * j + 2 * q + 1]);
+                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(t_base + acc * N_, v);
+          tmem_ld_wait();
+          if (valid) {
+            for (int j = 0; j < P.cout; ++j) {
+              float o = P.alpha * (__uint_as_float(v[j]) + s_bias[j]);
+              if (P.res_f32) o = fmaf(P.beta, P.res_f32[pix * P.cout + j], o);
+              if (P.relu) o = fmaxf(o, 0.f);
+              if (P.out_f32) P.out_f32[pix * P.cout + j] = o;
+              if (P.out_bf16) P.out_bf16[pix * P.cout + j] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+// =====================================================================================
+// Host side: plan
+// =====================================================================================
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+struct ConvPlan {
+  CUtensorMap tmA[2], tmW[2];
+  ConvKernelParams P;
+  int n_pad;     // 128 or 16
+  int amode;
+  int nacc;
+  int grid;
+  size_t smem_bytes;
+  double flops;  // algorithmic FLOPs (2*MAC) of one run
+};
+
+static int make_a_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, int PWs, int NR,
+                      int amode) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r;
+  if (amode == kAModeSwizzle64) {
+    cuuint64_t dims[4] = {(cuuint64_t)kCin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t strides[3] = {(cuuint64_t)kCin * 2, (cuuint64_t)W * kCin * 2,
+                             (cuuint64_t)H * W * kCin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)PWs, (cuuint32_t)NR, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)kCin / 8, (cuuint64_t)NB};
+    cuuint64_t strides[4] = {(cuuint64_t)kCin * 2, (cuuint64_t)W * kCin * 2, 16,
+                             (cuuint64_t)H * W * kCin * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)PWs, (cuuint32_t)NR, (cuuint32_t)kChunk / 8, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(A) failed: %d (W=%d H=%d PWs=%d NR=%d)",
+             (int)r, W, H, PWs, NR);
+    return set_error(SR_ERR_CUDA, msg);
+  }
+  return SR_OK;
+}
+
+static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)kChunk, (cuuint64_t)nstages * n_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)kChunk * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)n_pad};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    return set_error(SR_ERR_CUDA, msg);
+  }
+  return SR_OK;
+}
+
+static constexpr size_t kSmemBudget = 227 * 1024;
+
+// Choose the column-segment width: maximise useful MMA rows subject to the shared-memory budget.
+static bool choose_geometry(int H, int W, int p, int T, int wstage, ConvKernelParams* P) {
+  double best_eff = -1.0;
+  for (int nseg = 1; nseg <= W; ++nseg) {
+    const int BW = (W + nseg - 1) / nseg;
+    if ((BW * (nseg - 1)) >= W) continue;  // last segment would be empty
+    const int PWs = BW + 2 * p;
+    if (PWs > 256) continue;
+    const int NR = (2 * p * PWs + 2 * p + PWs + T - 2) / PWs + 1;
+    if (NR > 256) continue;
+    const size_t a_bytes = ((size_t)NR * PWs * kChunk * 2 + 1023) & ~(size_t)1023;
+    const size_t fixed = 2 * a_bytes + 1024 /*align slack*/ + sizeof(ConvBarriers) + 128 * 4 + 64;
+    if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;
+    const int f_len = (H - 1) * PWs + BW;
+    const int tps = (f_len + T - 1) / T;
+    const double eff = (double)H * W / ((double)nseg * tps * T);
+    // prefer fewer segments on ties (less halo traffic)
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      P->BW = BW;
+      P->nseg = nseg;
+      P->PWs = PWs;
+      P->NR = NR;
+      P->a_bytes = (int)a_bytes;
+      P->f_len = f_len;
+      P->tiles_per_seg = tps;
+      int ns = (int)((kSmemBudget - fixed) / wstage);
+      P->num_wstages = std::min(ns, kMaxWStages);
+    }
+    if (BW <= 16) break;
+  }
+  return best_eff > 0;
+}
+
+template <int N_, int AMODE, int NACC, int NBUF>
+static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
+  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBudget);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    attr_set = true;
+  }
+  kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
+                                                           pl->tmW[1], pl->P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
+  return SR_OK;
+}
+
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
+  if (!d || !out) return set_error(SR_ERR_INVALID, "sr_conv_plan_create: null argument");
+  if (d->nsrc < 1 || d->nsrc > 2) return set_error(SR_ERR_INVALID, "nsrc must be 1 or 2");
+  if (d->cin != kCin) return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv requires cin == 128");
+  if (!(d->cout == 128 || (d->cout >= 1 && d->cout <= 16)))
+    return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv supports cout == 128 or cout <= 16");
+  if (d->NB < 1 || d->H < 1 || d->W < 1) return set_error(SR_ERR_INVALID, "empty tensor");
+  int p = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const int k = d->ksize[s];
+    if (!(k == 1 || k == 3 || k == 5 || k == 7))
+      return set_error(SR_ERR_UNSUPPORTED, "kernel size must be 1, 3, 5 or 7");
+    if (!d->in[s] || !d->wpacked[s]) return set_error(SR_ERR_INVALID, "null source pointer");
+    p = std::max(p, (k - 1) / 2);
+  }
+  ConvPlan* pl = new (std::nothrow) ConvPlan();
+  if (!pl) return set_error(SR_ERR_NOMEM, "out of host memory");
+  memset(pl, 0, sizeof *pl);
+  pl->n_pad = d->cout == 128 ? 128 : 16;
+  pl->amode = d->a_mode == 1 ? kAModeInterleave : kAModeSwizzle64;
+  pl->nacc = (d->nacc == 2 && pl->n_pad == 128) ? 2 : 4;
+  const int T = pl->nacc * 128;
+  const int wstage = pl->n_pad * kChunk * 2;
+  ConvKernelParams& P = pl->P;
+  P.nsrc = d->nsrc;
+  P.ksize[0] = d->ksize[0];
+  P.ksize[1] = d->nsrc > 1 ? d->ksize[1] : 0;
+  P.H = d->H;
+  P.W = d->W;
+  P.NB = d->NB;
+  P.p = p;
+  if (!choose_geometry(d->H, d->W, p, T, wstage, &P)) {
+    delete pl;
+    return set_error(SR_ERR_UNSUPPORTED, "no conv geometry fits shared memory");
+  }
+  P.total_tiles = P.NB * P.nseg * P.tiles_per_seg;
+  P.bias = d->bias;
+  P.alpha = d->alpha;
+  P.beta = d->beta;
+  P.relu = d->relu;
+  P.res_f32 = d->res_f32;
+  P.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->res_bf16);
+  P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
+  P.out_f32 = d->out_f32;
+  P.cout = d->cout;
+  P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
+  double macs = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode);
+    if (rc == SR_OK)
+      rc = make_w_map(&pl->tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], pl->n_pad);
+    if (rc != SR_OK) {
+      delete pl;
+      return rc;
+    }
+    macs += (double)d->NB * d->H * d->W * d->ksize[s] * d->ksize[s] * kCin * d->cout;
+  }
+  if (d->nsrc == 1) {
+    pl->tmA[1] = pl->tmA[0];
+    pl->tmW[1] = pl->tmW[0];
+  }
+  pl->flops = 2.0 * macs;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  pl->grid = std::min(P.total_tiles, sms);
+  pl->smem_bytes = 1024 + 2 * (size_t)P.a_bytes + (size_t)P.num_wstages * wstage +
+                   sizeof(ConvBarriers) + 128 * 4 + 64;
+  *out = reinterpret_cast<sr_conv_plan*>(pl);
+  return SR_OK;
+}
+
+extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
+  if (!plan) return set_error(SR_ERR_INVALID, "sr_conv_plan_run: null plan");
+  const ConvPlan* pl = reinterpret_cast<const ConvPlan*>(plan);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pl->n_pad == 128) {
+    if (pl->amode == kAModeSwizzle64)
+      return pl->nacc == 4 ? launch_variant<128, kAModeSwizzle64, 4, 1>(pl, st)
+                           : launch_variant<128, kAModeSwizzle64, 2, 2>(pl, st);
+    return pl->nacc == 4 ? launch_variant<128, kAModeInterleave, 4, 1>(pl, st)
+                         : launch_variant<128, kAModeInterleave, 2, 2>(pl, st);
+  }
+  if (pl->amode == kAModeSwizzle64) return launch_variant<16, kAModeSwizzle64, 4, 2>(pl, st);
+  return launch_variant<16, kAModeInterleave, 4, 2>(pl, st);
+}
+
+extern "C" void sr_conv_plan_destroy(sr_conv_plan* plan) {
+  delete reinterpret_cast<ConvPlan*>(plan);
+}
+
+extern "C" int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info) {
+  if (!plan || !info) return set_error(SR_ERR_INVALID, "sr_conv_plan_info: null argument");
+  const ConvPlan* pl = reinterpret_cast<const ConvPlan*>(plan);
+  info->flops = pl->flops;
+  info->total_tiles = pl->P.total_tiles;
+  info->grid = pl->grid;
+  info->smem_bytes = (int)pl->smem_bytes;
+  info->seg_width = pl->P.BW;
+  info->nseg = pl->P.nseg;
+  info->strip_rows = pl->P.NR;
+  info->num_wstages = pl->P.num_wstages;
+  info->tile_positions = pl->nacc * 128;
+  info->mma_efficiency =
+      (double)pl->P.NB * pl->P.H * pl->P.W / ((double)pl->P.total_tiles * pl->nacc * 128);
+  return SR_OK;
+}

@@ -1,0 +1,55 @@
+// Implicit-GEMM convolution for sm_100a: TMA halo staging -> tcgen05.mma (TMEM accumulators) ->
+// fused epilogue.  Replaces every Conv2D of the DifvdsrDouble stack
+// (reference: models.py:1177-1199, 1231-1270; Keras Conv2D = cross-correlation, SAME, stride 1).
+//
+// Formulation ("flat halo"): a column segment of the image (width BW) is staged in shared memory
+// together with its zero halo as a dense strip of NR rows with pitch PWs = BW + 2p pixels (TMA box
+// load; out-of-bounds pixels are zero-filled by the TMA unit, which IS the SAME padding).  In the
+// strip every filter tap (dy,dx) is a constant pixel shift dy*PWs + dx, so the A operand of tap
+// (dy,dx) is the same shared-memory strip addressed through a UMMA descriptor whose start address
+// is shifted by that many pixel rows: the strip is loaded once per 32-channel chunk and reused
+// by all k*k taps.  One CTA tile = T = NACC*128 consecutive flat positions (NACC accumulators of
+// 128x128 fp32 in TMEM), so every weight stage (tap, 32 channels, 128 couts = 8 KB) feeds
+// NACC*2 MMAs.  Positions that fall on halo columns are computed and discarded (4 of 100).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sr {
+
+constexpr int kConvThreads = 256;  // warp0: weight TMA, warp1: MMA, warp2: TMEM alloc, warp3: A TMA, warps4-7: epilogue
+constexpr int kCin = 128;          // every tensor-core conv of the stack has 128 input channels
+constexpr int kChunk = 32;         // channels per K chunk (64-byte rows)
+constexpr int kNumChunks = kCin / kChunk;
+
+enum ConvAMode : int {
+  kAModeSwizzle64 = 0,   // A strip [pixel][32ch] with TMA/UMMA 64B swizzle, tap = start-address shift
+  kAModeInterleave = 1,  // A strip [8ch group][pixel][8ch] no swizzle (SBO=128B, LBO=strip bytes/4)
+};
+
+struct ConvKernelParams {
+  int nsrc;          // 1 or 2 K-concatenated sources (second half of a 5/3 block)
+  int ksize[2];
+  int H, W, NB;
+  int p;             // geometry halo = max (k-1)/2 over sources
+  int BW, nseg, PWs, NR;
+  int tiles_per_seg, total_tiles;
+  int a_bytes;       // bytes of one A strip buffer (1024-aligned)
+  int num_wstages;
+  int f_len;         // number of useful flat positions per segment
+  // epilogue: out = act(alpha * (acc + bias) + beta * res)
+  const float* bias;
+  float alpha, beta;
+  int relu;
+  const float* res_f32;
+  const __nv_bfloat16* res_bf16;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  int cout;          // real output channels (128; 3 for the tail conv)
+  // dgrad-time ReLU mask: if non-null, out *= (mask > 0)
+  const __nv_bfloat16* relu_mask_bf16;
+};
+
+}  // namespace sr

@@ -1,0 +1,561 @@
+// Bandwidth-bound kernels of the sr100 hot path: first layer (1x1, K=3), TF1-legacy bilinear x4 and
+// its adjoint, patch gather / stitch, depth-to-space, weight repack, casts, loss and Adam.
+// All are grid-stride, 128-bit vectorised where the layout allows, sized in multiples of 148 SMs.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "internal.h"
+
+namespace sr {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------ head 1x1 conv (3 -> 128) + ReLU
+// Reference: models.py:1177 Convolution2D(128,(1,1),activation='relu',name='level1').
+__global__ void head1x1_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                               const float* __restrict__ bias, size_t npix,
+                               uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+  __shared__ float sw[3 * 128 + 128];
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) sw[384 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const size_t total = npix * 16;  // 16 groups of 8 channels per pixel
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = idx >> 4;
+    const int c0 = (int)(idx & 15) * 8;
+    const float r = in[pix * 3 + 0], g = in[pix * 3 + 1], b = in[pix * 3 + 2];
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // accumulate in channel order like a 3-term dot product, then bias, then ReLU
+      float a = __fmul_rn(r, sw[c0 + j]);
+      a = __fmaf_rn(g, sw[128 + c0 + j], a);
+      a = __fmaf_rn(b, sw[256 + c0 + j], a);
+      a = __fadd_rn(a, sw[384 + c0 + j]);
+      o[j] = fmaxf(a, 0.f);
+    }
+    if (out_bf16)
+      out_bf16[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (out_f32) {
+      out_f32[idx * 2] = make_float4(o[0], o[1], o[2], o[3]);
+      out_f32[idx * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bilinear x4, TF1 legacy
+// Reference: tf.image.resize_bilinear(x, [4h,4w]) (models.py:1392-1399), align_corners=False,
+// legacy sampling: src = dst*0.25, lo = floor(src), hi = min(ceil(src), n-1), t = src - lo;
+// top = tl + (tr-tl)*tx ; bot = bl + (br-bl)*tx ; out = top + (bot-top)*ty  (fp32, no FMA).
+__device__ __forceinline__ float lerp_tf(float a, float b, float t) {
+  return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+}
+
+template <bool IN_BF16>
+__device__ __forceinline__ void load8(const void* base, size_t elem_off, float (&v)[8]) {
+  if constexpr (IN_BF16) {
+    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) +
+                                                    elem_off);
+    v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+    v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
+template <bool IN_BF16>
+__global__ void bilinear4_fwd_kernel(const void* __restrict__ in, int NB, int H, int W, int C,
+                                     uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+  const int C8 = C >> 3;
+  const int OH = 4 * H, OW = 4 * W;
+  const size_t total = (size_t)NB * OH * OW * C8;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    size_t r = idx / C8;
+    const int X = (int)(r % OW);
+    r /= OW;
+    const int Y = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int y0 = Y >> 2, x0 = X >> 2;
+    const float ty = (float)(Y & 3) * 0.25f, tx = (float)(X & 3) * 0.25f;
+    const int y1 = ((Y & 3) == 0) ? y0 : min(y0 + 1, H - 1);
+    const int x1 = ((X & 3) == 0) ? x0 : min(x0 + 1, W - 1);
+    const size_t rowb0 = ((size_t)n * H + y0) * W, rowb1 = ((size_t)n * H + y1) * W;
+    float tl[8], tr[8], bl[8], br[8], o[8];
+    load8<IN_BF16>(in, (rowb0 + x0) * C + c8 * 8, tl);
+    load8<IN_BF16>(in, (rowb0 + x1) * C + c8 * 8, tr);
+    load8<IN_BF16>(in, (rowb1 + x0) * C + c8 * 8, bl);
+    load8<IN_BF16>(in, (rowb1 + x1) * C + c8 * 8, br);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = lerp_tf(tl[j], tr[j], tx);
+      const float bot = lerp_tf(bl[j], br[j], tx);
+      o[j] = lerp_tf(top, bot, ty);
+    }
+    if (out_bf16)
+      out_bf16[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (out_f32) {
+      out_f32[idx * 2] = make_float4(o[0], o[1], o[2], o[3]);
+      out_f32[idx * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// weight with which HR index Q (0..4n-1) samples LR index q, along one axis
+__device__ __forceinline__ float axis_weight(int Q, int q, int n) {
+  const int lo = Q >> 2;
+  const int fr = Q & 3;
+  const int hi = fr == 0 ? lo : min(lo + 1, n - 1);
+  const float t = (float)fr * 0.25f;
+  float w = 0.f;
+  if (lo == q) w += 1.f - t;
+  if (hi == q) w += t;
+  return w;
+}
+
+// Adjoint (gather form, deterministic): gin[y,x] = sum_{Y,X} wy(Y,y) wx(X,x) gout[Y,X].
+__global__ void bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, int H, int W, int C,
+                                     float4* __restrict__ gin) {
+  const int C4 = C >> 2;
+  const int OH = 4 * H, OW = 4 * W;
+  const size_t total = (size_t)NB * H * W * C4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    size_t r = idx / C4;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int Y = max(4 * y - 3, 0); Y <= min(4 * y + 3, OH - 1); ++Y) {
+      const float wy = axis_weight(Y, y, H);
+      if (wy == 0.f) continue;
+      for (int X = max(4 * x - 3, 0); X <= min(4 * x + 3, OW - 1); ++X) {
+        const float wgt = wy * axis_weight(X, x, W);
+        if (wgt == 0.f) continue;
+        const float4 g = gout[(((size_t)n * OH + Y) * OW + X) * C4 + c4];
+        acc.x = fmaf(wgt, g.x, acc.x);
+        acc.y = fmaf(wgt, g.y, acc.y);
+        acc.z = fmaf(wgt, g.z, acc.z);
+        acc.w = fmaf(wgt, g.w, acc.w);
+      }
+    }
+    gin[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ patch gather / stitch
+// Reference: img_utils.extract_patches_Step (img_utils.py:601-676): positions
+// {x : 0 <= x < dim-p, x % step == 0}, w outer / h inner => n = wi*cnt_h + hi.
+template <bool FROM_U8>
+__global__ void patch_gather_kernel(const void* __restrict__ src, int h, int w, int canvas_w,
+                                    int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,
+                                    float* __restrict__ out) {
+  const size_t row_elems = (size_t)pw * 3;
+  const size_t total = (size_t)cnt_h * cnt_w * ph * row_elems;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % row_elems);
+    size_t r = idx / row_elems;
+    const int i = (int)(r % ph);
+    const int n = (int)(r / ph);
+    const int wi = n / cnt_h, hi = n - wi * cnt_h;
+    const int y = hi * step + i;
+    const int x = wi * step + e / 3;
+    const int c = e % 3;
+    float v = 0.f;
+    if (FROM_U8) {
+      if (y < h && x < w) v = (float)reinterpret_cast<const uint8_t*>(src)[((size_t)y * w + x) * 3 + c];
+    } else {
+      v = reinterpret_cast<const float*>(src)[((size_t)y * canvas_w + x) * 3 + c];
+    }
+    out[idx] = divisor == 1.f ? v : __fdiv_rn(v, divisor);
+  }
+}
+
+// Reference: img_utils.rebuild_from_patches_Step (img_utils.py:692-724).  Per axis the owner of
+// output coordinate Q is the LAST patch whose cropped span [S*i + c_i, S*i + P - c_i) contains Q
+// (c_0 = 0, c_i = 8), because later patches overwrite earlier ones.
+__device__ __forceinline__ int stitch_owner(int Q, int cnt, int S, int P, int crop) {
+  int i = 0;
+  if (Q >= S + crop) i = min(cnt - 1, (Q - crop) / S);
+  const int c = i == 0 ? 0 : crop;
+  if (Q < S * i + c || Q >= S * i + P - c) return -1;
+  return i;
+}
+
+__global__ void patch_stitch_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH,
+                                    int PW, int S, int crop, int out_h, int out_w, float mul,
+                                    float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
+  const size_t row_elems = (size_t)out_w * 3;
+  const size_t total = (size_t)out_h * row_elems;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % row_elems);
+    const int Y = (int)(idx / row_elems);
+    const int X = e / 3, c = e % 3;
+    const int i = stitch_owner(Y, cnt_h, S, PH, crop);
+    const int j = stitch_owner(X, cnt_w, S, PW, crop);
+    float v = 0.f;
+    if (i >= 0 && j >= 0) {
+      const size_t n = (size_t)j * cnt_h + i;
+      v = __fmul_rn(patches[((n * PH + (Y - S * i)) * PW + (X - S * j)) * 3 + c], mul);
+    }
+    if (out_f32) out_f32[idx] = v;
+    if (out_u8) {
+      // np.clip(result, 0, 255).astype('uint8'): clamp then truncate toward zero (models.py:391)
+      const float cl = fminf(fmaxf(v, 0.f), 255.f);
+      out_u8[idx] = (uint8_t)(int)cl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ depth to space
+__global__ void depth_to_space_kernel(const float* __restrict__ in, int NB, int H, int W, int C,
+                                      int r, int order, float* __restrict__ out) {
+  const int OH = H * r, OW = W * r;
+  const size_t total = (size_t)NB * OH * OW * C;
+  const int Cin = C * r * r;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    size_t q = idx / C;
+    const int X = (int)(q % OW);
+    q /= OW;
+    const int Y = (int)(q % OH);
+    const int n = (int)(q / OH);
+    const int ry = Y % r, rx = X % r;
+    int ch;
+    if (order == 0) ch = c * r * r + rx * r + ry;
+    else if (order == 1) ch = c * r * r + ry * r + rx;
+    else ch = (ry * r + rx) * C + c;
+    out[idx] = in[(((size_t)n * H + Y / r) * W + X / r) * Cin + ch];
+  }
+}
+
+// ------------------------------------------------------------------ weight repack
+// HWIO fp32 [k*k][128][cout] -> bf16 [chunk][tap][n_pad][32]
+__global__ void pack_weights_kernel(const float* __restrict__ hwio, int ntaps, int cout, int n_pad,
+                                    int transpose_flip, __nv_bfloat16* __restrict__ dst) {
+  const size_t total = (size_t)4 * ntaps * n_pad * 32;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 31);
+    size_t q = idx >> 5;
+    const int n = (int)(q % n_pad);
+    q /= n_pad;
+    const int tap = (int)(q % ntaps);
+    const int chunk = (int)(q / ntaps);
+    const int k_in = chunk * 32 + c;  // reduction (input-channel) index of the packed GEMM
+    float v = 0.f;
+    if (n < cout) {
+      if (!transpose_flip) v = hwio[((size_t)tap * 128 + k_in) * cout + n];
+      else v = hwio[((size_t)(ntaps - 1 - tap) * 128 + n) * cout + k_in];  // W'[t][co][ci] = W[T-1-t][ci][co]
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ direct conv (CUDA cores)
+__global__ void conv_direct_kernel(const void* __restrict__ in, int in_is_bf16,
+                                   const float* __restrict__ hwio, int w_round_bf16,
+                                   const float* __restrict__ bias, int NB, int H, int W, int cin,
+                                   int cout, int k, int same, int relu, int r, int order,
+                                   float* __restrict__ out) {
+  const int pad = same ? (k - 1) / 2 : 0;
+  const int OH = same ? H : H - k + 1, OW = same ? W : W - k + 1;
+  const size_t total = (size_t)NB * OH * OW * cout;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % cout);
+    size_t q = idx / cout;
+    const int x = (int)(q % OW);
+    q /= OW;
+    const int y = (int)(q % OH);
+    const int n = (int)(q / OH);
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = y + ky - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = x + kx - pad;
+        if (ix < 0 || ix >= W) continue;
+        const size_t ib = (((size_t)n * H + iy) * W + ix) * cin;
+        const float* wp = hwio + ((size_t)(ky * k + kx) * cin) * cout + co;
+        for (int ci = 0; ci < cin; ++ci) {
+          const float a = in_is_bf16
+                              ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[ib + ci])
+                              : reinterpret_cast<const float*>(in)[ib + ci];
+          float wv = wp[(size_t)ci * cout];
+          if (w_round_bf16) wv = __bfloat162float(__float2bfloat16_rn(wv));
+          acc = fmaf(a, wv, acc);
+        }
+      }
+    }
+    if (bias) acc += bias[co];
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (r > 0) {
+      const int C = cout / (r * r);
+      int c, ry, rx;
+      if (order == 0) { c = co / (r * r); rx = (co / r) % r; ry = co % r; }
+      else if (order == 1) { c = co / (r * r); ry = (co / r) % r; rx = co % r; }
+      else { c = co % C; ry = (co / C) / r; rx = (co / C) % r; }
+      out[(((size_t)n * OH * r + (y * r + ry)) * OW * r + (x * r + rx)) * C + c] = acc;
+    } else {
+      out[idx] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ casts / axpby / loss / adam
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, size_t n, __nv_bfloat16* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, size_t n, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
+                             size_t n, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = a * x[i];
+    if (y) v = fmaf(b, y[i], v);
+    if (out) out[i] = v;
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void mse_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                     size_t n, float inv_total2, float* __restrict__ grad,
+                                     double* __restrict__ loss_sum) {
+  double local = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = pred[i] - target[i];
+    local += (double)d * (double)d;
+    if (grad) grad[i] = d * inv_total2;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double sm[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = local;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && loss_sum) atomicAdd(loss_sum, v);
+  }
+}
+
+// Keras 2 Adam (keras/optimizers.py Adam.get_updates): lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_head1x1_fwd(const float* in, const float* w, const float* bias, size_t npix,
+                              void* out_bf16, float* out_f32, void* stream) {
+  if (!in || !w || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_head1x1_fwd: null pointer");
+  if (npix == 0) return SR_OK;
+  head1x1_kernel<<<grid_for(npix * 16, kBlock), kBlock, 0, as_stream(stream)>>>(
+      in, w, bias, npix, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  return check_launch("head1x1_kernel");
+}
+
+extern "C" int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C,
+                                void* out_bf16, float* out_f32, void* stream) {
+  if (!in || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: null pointer");
+  if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_fwd: C must be a multiple of 8");
+  if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: empty tensor");
+  const size_t total = (size_t)NB * H * W * 16 * (C / 8);
+  const unsigned g = grid_for(total, kBlock, 148 * 32);
+  if (in_is_bf16)
+    bilinear4_fwd_kernel<true><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, NB, H, W, C, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  else
+    bilinear4_fwd_kernel<false><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, NB, H, W, C, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  return check_launch("bilinear4_fwd_kernel");
+}
+
+extern "C" int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream) {
+  if (!gout || !gin) return set_error(SR_ERR_INVALID, "sr_bilinear4_bwd: null pointer");
+  if (C % 4 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_bwd: C must be a multiple of 4");
+  const size_t total = (size_t)NB * H * W * (C / 4);
+  bilinear4_bwd_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(gout), NB, H, W, C, reinterpret_cast<float4*>(gin));
+  return check_launch("bilinear4_bwd_kernel");
+}
+
+extern "C" int sr_patch_count(int dim, int patch, int step) {
+  if (step <= 0 || patch <= 0) return 0;
+  const int lim = dim - patch;  // positions x with 0 <= x < lim and x % step == 0
+  if (lim <= 0) return 0;
+  return (lim - 1) / step + 1;
+}
+
+extern "C" int sr_canvas_size(int h, int w, int patch, int step, int* canvas_h, int* canvas_w) {
+  if (!canvas_h || !canvas_w || h < 1 || w < 1 || patch < 1 || step < 1)
+    return set_error(SR_ERR_INVALID, "sr_canvas_size: bad argument");
+  int ch = h + patch, cw = w + patch;
+  if (cw % step != 0 || ch % step != 0) {
+    // models.py:250-252: int((x/step)+1)*step on BOTH dims
+    cw = (cw / step + 1) * step;
+    ch = (ch / step + 1) * step;
+  }
+  *canvas_h = ch;
+  *canvas_w = cw;
+  return SR_OK;
+}
+
+extern "C" int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h, int canvas_w, int ph,
+                                  int pw, int step, float divisor, float* out_f32, void* stream) {
+  if (!img || !out_f32) return set_error(SR_ERR_INVALID, "sr_patch_gather_u8: null pointer");
+  if (ph > canvas_h) return set_error(SR_ERR_INVALID, "Height of the patch should be less than the height of the image.");
+  if (pw > canvas_w) return set_error(SR_ERR_INVALID, "Width of the patch should be less than the width of the image.");
+  const int cnt_h = sr_patch_count(canvas_h, ph, step), cnt_w = sr_patch_count(canvas_w, pw, step);
+  const size_t total = (size_t)cnt_h * cnt_w * ph * pw * 3;
+  if (total == 0) return SR_OK;
+  patch_gather_kernel<true><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, out_f32);
+  return check_launch("patch_gather_kernel<u8>");
+}
+
+extern "C" int sr_patch_gather_f32(const float* canvas, int canvas_h, int canvas_w, int ph, int pw,
+                                   int step, float* out_f32, void* stream) {
+  if (!canvas || !out_f32) return set_error(SR_ERR_INVALID, "sr_patch_gather_f32: null pointer");
+  if (ph > canvas_h) return set_error(SR_ERR_INVALID, "Height of the patch should be less than the height of the image.");
+  if (pw > canvas_w) return set_error(SR_ERR_INVALID, "Width of the patch should be less than the width of the image.");
+  const int cnt_h = sr_patch_count(canvas_h, ph, step), cnt_w = sr_patch_count(canvas_w, pw, step);
+  const size_t total = (size_t)cnt_h * cnt_w * ph * pw * 3;
+  if (total == 0) return SR_OK;
+  patch_gather_kernel<false><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      canvas, canvas_h, canvas_w, canvas_w, cnt_h, cnt_w, ph, pw, step, 1.f, out_f32);
+  return check_launch("patch_gather_kernel<f32>");
+}
+
+extern "C" int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int ph, int pw, int step,
+                               int scale, int canvas_h, int canvas_w, float mul, float* out_f32,
+                               uint8_t* out_u8, void* stream) {
+  if (!patches || (!out_f32 && !out_u8)) return set_error(SR_ERR_INVALID, "sr_patch_stitch: null pointer");
+  if (cnt_h < 1 || cnt_w < 1 || scale < 1) return set_error(SR_ERR_INVALID, "sr_patch_stitch: bad counts");
+  const int out_h = canvas_h * scale, out_w = canvas_w * scale;
+  const size_t total = (size_t)out_h * out_w * 3;
+  patch_stitch_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      patches, cnt_h, cnt_w, ph * scale, pw * scale, step * scale, 8, out_h, out_w, mul, out_f32, out_u8);
+  return check_launch("patch_stitch_kernel");
+}
+
+extern "C" int sr_depth_to_space(const float* in, int NB, int H, int W, int C, int r, int order,
+                                 float* out, void* stream) {
+  if (!in || !out) return set_error(SR_ERR_INVALID, "sr_depth_to_space: null pointer");
+  if (r < 1 || C < 1 || order < 0 || order > 2) return set_error(SR_ERR_INVALID, "sr_depth_to_space: bad r/C/order");
+  const size_t total = (size_t)NB * H * r * W * r * C;
+  if (total == 0) return SR_OK;
+  depth_to_space_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      in, NB, H, W, C, r, order, out);
+  return check_launch("depth_to_space_kernel");
+}
+
+extern "C" size_t sr_packed_weight_bytes(int ksize, int cout) {
+  const int n_pad = cout == 128 ? 128 : 16;
+  return (size_t)4 * ksize * ksize * n_pad * 32 * 2;
+}
+
+extern "C" int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip,
+                                    void* dst, void* stream) {
+  if (!hwio || !dst) return set_error(SR_ERR_INVALID, "sr_pack_conv_weights: null pointer");
+  if (!(cout == 128 || (cout >= 1 && cout <= 16))) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: cout must be 128 or <= 16");
+  if (transpose_flip && cout != 128) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: transpose needs cout == 128");
+  const int n_pad = cout == 128 ? 128 : 16;
+  const size_t total = (size_t)4 * ksize * ksize * n_pad * 32;
+  pack_weights_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
+      hwio, ksize * ksize, cout, n_pad, transpose_flip, reinterpret_cast<__nv_bfloat16*>(dst));
+  return check_launch("pack_weights_kernel");
+}
+
+extern "C" int sr_conv2d_direct(const void* in, int in_is_bf16, const float* hwio, int w_round_bf16,
+                                const float* bias, int NB, int H, int W, int cin, int cout, int ksize,
+                                int same_padding, int relu, int shuffle_r, int shuffle_order, float* out,
+                                void* stream) {
+  if (!in || !hwio || !out) return set_error(SR_ERR_INVALID, "sr_conv2d_direct: null pointer");
+  if (shuffle_r > 0 && cout % (shuffle_r * shuffle_r) != 0)
+    return set_error(SR_ERR_INVALID, "sr_conv2d_direct: cout not divisible by r*r");
+  const int OH = same_padding ? H : H - ksize + 1, OW = same_padding ? W : W - ksize + 1;
+  if (OH < 1 || OW < 1) return set_error(SR_ERR_INVALID, "sr_conv2d_direct: kernel larger than image");
+  const size_t total = (size_t)NB * OH * OW * cout;
+  conv_direct_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      in, in_is_bf16, hwio, w_round_bf16, bias, NB, H, W, cin, cout, ksize, same_padding, relu,
+      shuffle_r, shuffle_order, out);
+  return check_launch("conv_direct_kernel");
+}
+
+extern "C" int sr_cast_f32_to_bf16(const float* in, size_t n, void* out_bf16, void* stream) {
+  if (!in || !out_bf16) return set_error(SR_ERR_INVALID, "sr_cast_f32_to_bf16: null pointer");
+  if (n == 0) return SR_OK;
+  cast_f32_bf16_kernel<<<grid_for(n, kBlock), kBlock, 0, as_stream(stream)>>>(in, n, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("cast_f32_bf16_kernel");
+}
+extern "C" int sr_cast_bf16_to_f32(const void* in_bf16, size_t n, float* out, void* stream) {
+  if (!in_bf16 || !out) return set_error(SR_ERR_INVALID, "sr_cast_bf16_to_f32: null pointer");
+  if (n == 0) return SR_OK;
+  cast_bf16_f32_kernel<<<grid_for(n, kBlock), kBlock, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), n, out);
+  return check_launch("cast_bf16_f32_kernel");
+}
+extern "C" int sr_axpby_f32(const float* x, const float* y, float a, float b, size_t n, float* out,
+                            void* out_bf16, void* stream) {
+  if (!x || (!out && !out_bf16)) return set_error(SR_ERR_INVALID, "sr_axpby_f32: null pointer");
+  if (n == 0) return SR_OK;
+  axpby_kernel<<<grid_for(n, kBlock), kBlock, 0, as_stream(stream)>>>(x, y, a, b, n, out, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int sr_mse_loss_grad(const float* pred, const float* target, size_t n, size_t n_total,
+                                float* grad, double* loss_sum, void* stream) {
+  if (!pred || !target) return set_error(SR_ERR_INVALID, "sr_mse_loss_grad: null pointer");
+  if (n == 0) return SR_OK;
+  const float inv2 = (float)(2.0 / (double)n_total);
+  mse_loss_grad_kernel<<<grid_for(n, kBlock, 148 * 8), kBlock, 0, as_stream(stream)>>>(pred, target, n, inv2, grad, loss_sum);
+  return check_launch("mse_loss_grad_kernel");
+}
+
+extern "C" int sr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                            float beta2, float eps, int t, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v) return set_error(SR_ERR_INVALID, "sr_adam_step: null pointer");
+  if (t < 1) return set_error(SR_ERR_INVALID, "sr_adam_step: t must be >= 1");
+  if (n == 0) return SR_OK;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t));
+  adam_kernel<<<grid_for(n, kBlock), kBlock, 0, as_stream(stream)>>>(p, g, m, v, n, (float)lr_t, beta1, beta2, eps, grad_scale);
+  return check_launch("adam_kernel");
+}

@@ -1,0 +1,27 @@
+// Internal helpers shared by the sr100 translation units (error reporting, launch checks).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/sr100.h"
+
+namespace sr {
+
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+
+inline int check_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, where);
+  return SR_OK;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline unsigned int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
+  size_t g = (work_items + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (size_t)max_blocks) g = max_blocks;
+  return (unsigned int)g;
+}
+
+}  // namespace sr

@@ -1,0 +1,137 @@
+"""ctypes binding of libsr100.so (C ABI declared in include/sr100.h).
+
+There is no CPU fallback: if the library is missing or the device is not sm_100, the engine raises.
+PyTorch is used only for device memory and streams; every compute call goes through this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsr100.so")
+
+
+class SrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sr100 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("nsrc", C.c_int),
+        ("in_", C.c_void_p * 2),
+        ("wpacked", C.c_void_p * 2),
+        ("ksize", C.c_int * 2),
+        ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("cin", C.c_int), ("cout", C.c_int),
+        ("bias", C.c_void_p),
+        ("alpha", C.c_float), ("beta", C.c_float),
+        ("relu", C.c_int),
+        ("res_f32", C.c_void_p),
+        ("res_bf16", C.c_void_p),
+        ("out_bf16", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("relu_mask_bf16", C.c_void_p),
+        ("a_mode", C.c_int),
+        ("nacc", C.c_int),
+    ]
+
+
+class ConvPlanInfo(C.Structure):
+    _fields_ = [
+        ("flops", C.c_double),
+        ("mma_efficiency", C.c_double),
+        ("total_tiles", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int),
+        ("seg_width", C.c_int), ("nseg", C.c_int), ("strip_rows", C.c_int),
+        ("num_wstages", C.c_int), ("tile_positions", C.c_int),
+    ]
+
+
+class ScoreResult(C.Structure):
+    _fields_ = [
+        ("sum_sq_y", C.c_double),
+        ("ssim_y_sum", C.c_double),
+        ("ssim_rgb_sum", C.c_double * 3),
+        ("n_pix", C.c_int64),
+        ("n_win", C.c_int64),
+    ]
+
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol declared in include/sr100.h
+SIGNATURES = {
+    "sr_last_error_string": (C.c_char_p, []),
+    "sr_version": (_i, []),
+    "sr_device_supported": (_i, []),
+    "sr_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
+    "sr_conv_plan_run": (_i, [_vp, _vp]),
+    "sr_conv_plan_destroy": (None, [_vp]),
+    "sr_conv_plan_info": (_i, [_vp, C.POINTER(ConvPlanInfo)]),
+    "sr_packed_weight_bytes": (_sz, [_i, _i]),
+    "sr_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "sr_conv2d_direct": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sr_head1x1_fwd": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "sr_bilinear4_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sr_bilinear4_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sr_patch_count": (_i, [_i, _i, _i]),
+    "sr_canvas_size": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "sr_patch_gather_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "sr_patch_gather_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sr_patch_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "sr_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sr_rgb2y_u8": (_i, [_vp, _sz, _vp, _vp]),
+    "sr_score_pair_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "sr_mse_loss_grad": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "sr_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
+    "sr_axpby_f32": (_i, [_vp, _vp, _f, _f, _sz, _vp, _vp, _vp]),
+    "sr_cast_f32_to_bf16": (_i, [_vp, _sz, _vp, _vp]),
+    "sr_cast_bf16_to_f32": (_i, [_vp, _sz, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsr100.so (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SrError(-3, "libsr100.so not built (%s); run `python __graft_entry__.py` or "
+                          "`make -C image-enhance-keras_b200/csrc`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SrError(rc, load().sr_last_error_string().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_device():
+    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SrError(-3, "no CUDA device: the sr100 engine has no CPU path")
+    lib = load()
+    if not lib.sr_device_supported():
+        raise SrError(-2, "device is not sm_100 (B200); the sr100 kernels are sm_100a-only")
+    return lib

@@ -1,0 +1,187 @@
+/* sr100 -- C ABI of the B200-native x4 super-resolution hot path.
+ *
+ * The reference (diacaf/image-enhance-keras) has no FFI layer: its hot path is Keras/TensorFlow
+ * ops reached from Python (models.py) plus numpy helpers (img_utils.py, PSNR.py, scorpath.py).
+ * This header is the boundary a binding for that path would use: every entry point names the
+ * reference operation it replaces (file:line in /root/reference).  All pointers are DEVICE
+ * pointers unless the name ends in _host; `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 (SR_OK) or a negative SR_ERR_* code; sr_last_error_string() gives the
+ * thread-local message.  Functions never allocate or free caller memory and are asynchronous on
+ * `stream` unless stated otherwise.
+ */
+#ifndef SR100_H_
+#define SR100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  SR_OK = 0,
+  SR_ERR_INVALID = -1,     /* bad argument (shape, null pointer, patch larger than image ...) */
+  SR_ERR_UNSUPPORTED = -2, /* shape/dtype outside what the sm_100a kernels implement */
+  SR_ERR_CUDA = -3,        /* CUDA runtime / driver error; message holds cudaGetErrorString */
+  SR_ERR_NOMEM = -4
+};
+
+const char* sr_last_error_string(void);
+int sr_version(void);
+/* Returns 1 when the current device is compute capability 10.x (sm_100a cubins can run). */
+int sr_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution (tensor cores).  Replaces keras Conv2D(padding='same') of the DifvdsrDouble stack:
+ * models.py:1177-1199 (stack), :1231-1245 (_residual_block_light), :1248-1270
+ * (_residual_block_light53), with the scalar_mul/Add lambdas (models.py:977-986) fused:
+ *     out = act( alpha * (sum_s conv(in[s], w[s]) + bias) + beta * res )
+ * Activations are NHWC bf16 with 128 channels; accumulation is fp32 in TMEM.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sr_conv_desc {
+  int nsrc;              /* 1, or 2 = two convolutions accumulated into one output (5/3 block tail) */
+  const void* in[2];     /* bf16 [NB,H,W,128] */
+  const void* wpacked[2];/* from sr_pack_conv_weights */
+  int ksize[2];          /* 1, 3, 5 (7) */
+  int NB, H, W;
+  int cin;               /* must be 128 */
+  int cout;              /* 128, or <= 16 (tail conv: 3) */
+  const float* bias;     /* [cout] fp32 or NULL; for nsrc == 2 the caller passes bias0 + bias1 */
+  float alpha, beta;
+  int relu;              /* 1: ReLU after the residual add */
+  const float* res_f32;  /* optional residual, fp32 [NB,H,W,cout] */
+  const void* res_bf16;  /* optional residual, bf16 (used when res_f32 is NULL) */
+  void* out_bf16;        /* optional bf16 output [NB,H,W,cout] */
+  float* out_f32;        /* optional fp32 output [NB,H,W,cout] */
+  const void* relu_mask_bf16; /* optional (backward): out = 0 where mask <= 0 */
+  int a_mode;            /* 0: 64B-swizzled strip, 1: interleaved no-swizzle strip */
+  int nacc;              /* 4 (default): 512 positions / tile; 2: 256 positions, double-buffered TMEM */
+} sr_conv_desc;
+
+typedef struct sr_conv_plan sr_conv_plan;
+
+typedef struct sr_conv_plan_info_t {
+  double flops;          /* algorithmic FLOPs (2*MAC) per run */
+  double mma_efficiency; /* useful / issued MMA rows */
+  int total_tiles, grid, smem_bytes, seg_width, nseg, strip_rows, num_wstages, tile_positions;
+} sr_conv_plan_info_t;
+
+/* Synchronous, host side only: picks tile geometry and encodes the TMA descriptors.  The plan is
+ * bound to the pointers in the descriptor. */
+int sr_conv_plan_create(const sr_conv_desc* desc, sr_conv_plan** plan);
+int sr_conv_plan_run(sr_conv_plan* plan, void* stream);
+void sr_conv_plan_destroy(sr_conv_plan* plan);
+int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info);
+
+/* Repack Keras HWIO fp32 weights [k,k,cin=128,cout] (device) into the kernel's K-chunked bf16
+ * layout [cin/32][k*k][cout_pad][32]; cout_pad = 128 or 16.  transpose_flip = 1 produces the
+ * weights of the input-gradient convolution (180-degree rotation, cin<->cout; needs cout == 128).
+ * sr_packed_weight_bytes gives the destination size. */
+size_t sr_packed_weight_bytes(int ksize, int cout);
+int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip, void* dst,
+                         void* stream);
+
+/* Plain CUDA-core convolution, fp32 accumulate, any cin/cout, SAME or VALID, NHWC.  Used for
+ * layers outside the 128-channel stack (Subpixel(Conv2D), keras_subpixel.py:28-62) and as the
+ * on-device cross-check of the tensor-core kernel.  in_is_bf16/w_round_bf16 reproduce the
+ * tensor-core kernel's operand rounding.  shuffle_r > 0 fuses the depth-to-space store, see
+ * sr_depth_to_space for the orderings. */
+int sr_conv2d_direct(const void* in, int in_is_bf16, const float* hwio, int w_round_bf16,
+                     const float* bias, int NB, int H, int W, int cin, int cout, int ksize,
+                     int same_padding, int relu, int shuffle_r, int shuffle_order, float* out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * First layer.  Replaces Convolution2D(128,(1,1),relu,name='level1') (models.py:1177) applied to
+ * the float32 /255 patch stack (models.py:336).  in: fp32 [NPIX,3] in [0,1]; w: fp32 [3,128]
+ * (HWIO of the 1x1 kernel); out: bf16 [NPIX,128] and optionally fp32 [NPIX,128].
+ * ------------------------------------------------------------------------------------------ */
+int sr_head1x1_fwd(const float* in, const float* w, const float* bias, size_t npix, void* out_bf16,
+                   float* out_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear x4, TensorFlow-1 legacy sampling (align_corners=False, no half-pixel centres).
+ * Replaces Lambda(resizeX4bil) = tf.image.resize_bilinear (models.py:1193, 1392-1399).
+ * in: [NB,H,W,C] -> out: [NB,4H,4W,C]; C % 8 == 0.  Either in/out dtype may be fp32 or bf16.
+ * ------------------------------------------------------------------------------------------ */
+int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C, void* out_bf16,
+                     float* out_f32, void* stream);
+/* Adjoint of the above: gin[NB,H,W,C] = sum over the HR samples each LR pixel contributed to. */
+int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch tiling.  Replaces img_utils.extract_patches_Step (img_utils.py:601-676) and
+ * img_utils.rebuild_from_patches_Step (img_utils.py:692-724) as used by
+ * BaseSuperResolutionModel.upscaleStepPatch (models.py:184-415).
+ * ------------------------------------------------------------------------------------------ */
+/* Number of patch positions per axis: |{x : 0 <= x < dim - patch, x % step == 0}| (img_utils.py:622,629). */
+int sr_patch_count(int dim, int patch, int step);
+/* Zero-padded canvas size of upscaleStepPatch (models.py:225-256): +patch border, then both
+ * dims bumped to int(x/step+1)*step when either is not a multiple of step. */
+int sr_canvas_size(int h, int w, int patch, int step, int* canvas_h, int* canvas_w);
+/* Gather: uint8 image [h,w,3] placed at the top-left of a zero canvas [ch,cw] -> patches
+ * [cnt_w*cnt_h, ph, pw, 3], column-major patch order n = wi*cnt_h + hi.  The pixel value is divided
+ * by `divisor` in fp32 (1 -> the reference's 0..255 patches; 255 -> the /255. of models.py:336). */
+int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h, int canvas_w, int ph, int pw,
+                       int step, float divisor, float* out_f32, void* stream);
+/* Generic gather from a float64/float32 canvas (API parity with the numpy function). */
+int sr_patch_gather_f32(const float* canvas, int canvas_h, int canvas_w, int ph, int pw, int step,
+                        float* out_f32, void* stream);
+/* Stitch: patches [N, ph*scale, pw*scale, 3] fp32 -> canvas [ch*scale, cw*scale, 3]; closed-form
+ * last-writer-wins ownership with the 8-px border crop (img_utils.py:700-722).  mul scales the
+ * value (255 for models.py:351).  out_f32 and/or out_u8 (np.clip(0,255).astype('uint8'),
+ * truncation, models.py:391) may be given. */
+int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int ph, int pw, int step, int scale,
+                    int canvas_h, int canvas_w, float mul, float* out_f32, uint8_t* out_u8,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sub-pixel shuffles.  order 0: keras_subpixel.Subpixel._phase_shift (keras_subpixel.py:64-84)
+ * and advanced.depth_to_scale_tf (advanced.py:104-129): ch = c*r*r + (X%r)*r + (Y%r);
+ * order 1: advanced.depth_to_scale_th (advanced.py:87-100): ch = c*r*r + (Y%r)*r + (X%r);
+ * order 2: tf.depth_to_space used by advanced.SubpixelConv2D (advanced.py:173-199):
+ *          ch = ((Y%r)*r + (X%r))*C + c.   in: fp32 NHWC [NB,H,W,C*r*r] -> out [NB,H*r,W*r,C].
+ * ------------------------------------------------------------------------------------------ */
+int sr_depth_to_space(const float* in, int NB, int H, int W, int C, int r, int order, float* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scoring.  Replaces scorpath.py:174-228: crop_border (scorpath.py:67-70), skimage rgb2ycbcr Y
+ * (scorpath.py:26-31), PSNR.psnrNITRE / PSNRTorch (PSNR.py:24-32, 54-84) and skimage
+ * compare_ssim (7x7 uniform window, sample covariance, data_range 255) on Y and on RGB.
+ * ------------------------------------------------------------------------------------------ */
+/* Y = 16 + (65.481 R + 128.553 G + 24.966 B)/255 in fp64, from uint8 RGB. */
+int sr_rgb2y_u8(const uint8_t* rgb, size_t npix, double* y, void* stream);
+typedef struct sr_score_result {
+  double sum_sq_y;   /* sum over cropped pixels of (Y1 - Y2)^2, Y in [16,235] */
+  double ssim_y_sum; /* sum of the SSIM map (valid 7x7 windows) on Y */
+  double ssim_rgb_sum[3];
+  int64_t n_pix;     /* cropped pixel count */
+  int64_t n_win;     /* number of valid windows */
+} sr_score_result;
+/* a, b: uint8 [h,w,3] (same shape), crop = border removed from every side first.  `result` is a
+ * device pointer to one sr_score_result which must be zeroed by the caller before the call. */
+int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w, int crop,
+                     sr_score_result* result, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training step pieces (models.py:131-157 fit, :1212-1213 compile: mse + Adam(1e-4, 0.9)).
+ * ------------------------------------------------------------------------------------------ */
+/* loss_sum += sum (pred-target)^2 (fp64 accumulator, device); grad = 2*(pred-target)/n_total. */
+int sr_mse_loss_grad(const float* pred, const float* target, size_t n, size_t n_total, float* grad,
+                     double* loss_sum, void* stream);
+/* Keras-2 Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).  grad_scale is
+ * applied to g first (1/world_size after an all-reduce sum). */
+int sr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                 float beta2, float eps, int t, float grad_scale, void* stream);
+/* ReLU backward / elementwise helpers on fp32 or bf16 NHWC tensors. */
+int sr_axpby_f32(const float* x, const float* y, float a, float b, size_t n, float* out,
+                 void* out_bf16, void* stream);
+int sr_cast_f32_to_bf16(const float* in, size_t n, void* out_bf16, void* stream);
+int sr_cast_bf16_to_f32(const void* in_bf16, size_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SR100_H_ */

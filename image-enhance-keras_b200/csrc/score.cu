@@ -120,10 +120,30 @@ __global__ void rgb2y_kernel(const uint8_t* __restrict__ rgb, size_t npix, doubl
     y[i] = y_from_rgb(rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2]);
 }
 
+__global__ void sum_sq_diff_f64_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                       size_t n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double local = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double d = a[i] - b[i];
+    local += d * d;
+  }
+  const double t = block_sum(local, red);
+  if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
 }  // namespace
 }  // namespace sr
 
 using namespace sr;
+
+extern "C" int sr_sum_sq_diff_f64(const double* a, const double* b, size_t n, double* out, void* stream) {
+  if (!a || !b || !out) return set_error(SR_ERR_INVALID, "sr_sum_sq_diff_f64: null pointer");
+  if (n == 0) return SR_OK;
+  sum_sq_diff_f64_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, as_stream(stream)>>>(a, b, n, out);
+  return check_launch("sum_sq_diff_f64_kernel");
+}
 
 extern "C" int sr_rgb2y_u8(const uint8_t* rgb, size_t npix, double* y, void* stream) {
   if (!rgb || !y) return set_error(SR_ERR_INVALID, "sr_rgb2y_u8: null pointer");

@@ -1,0 +1,325 @@
+"""Drop-in mirror of the reference's models.py for the x4 hot path (reference: /root/reference/models.py).
+
+Same constructors, attributes, method names / argument meaning / error behaviour as the reference
+classes; the Keras/TensorFlow graph is replaced by the sm_100a engine (sr100.engine) reached through
+the libsr100 C ABI.  There is no CPU path: constructing a model's graph needs a B200.
+
+Covered: psnr helpers (models.py:43-90), BaseSuperResolutionModel (:93-182), upscaleStepPatch
+(:184-415, the CLI path), DifvdsrDouble (:1146-1270) and the Lambda helpers it uses (:977-986,
+:1383-1399, :1451).  upscalePatch / upscale / evaluate and Difvdsr4 / Difvdsr are "next" rows of
+SURVEY.md section 8(f) and raise NotImplementedError.
+"""
+from __future__ import print_function, division
+
+import math
+import os
+
+import numpy as np
+
+import img_utils
+from advanced import HistoryCheckpoint, SubPixelUpscaling, SubpixelConv2D  # noqa: F401 (models.py:16)
+from keras_subpixel import Subpixel  # noqa: F401 (models.py:17)
+
+train_path = img_utils.output_path
+validation_path = img_utils.validation_output_path
+path_X = img_utils.output_path + "X/"
+path_Y = img_utils.output_path + "y/"
+
+
+def _mean_sq(a, b):
+    from sr100 import ops
+    a, b = np.asarray(a), np.asarray(b)
+    return ops.sum_sq_diff(a, b) / a.size
+
+
+def PSNRLoss(y_true, y_pred):
+    """models.py:43-55: the reference returns K.mean(y_pred) (the PSNR formula after it is dead code)."""
+    return float(np.mean(np.asarray(y_pred)))
+
+
+def PSNRLossTest(y_true, y_pred):
+    """models.py:57-69."""
+    return -10. * np.log10(_mean_sq(y_pred, y_true))
+
+
+def psnr(y_true, y_pred):
+    """models.py:71-76."""
+    assert y_true.shape == y_pred.shape, "Cannot calculate PSNR. Input shapes not same." \
+                                         " y_true shape = %s, y_pred shape = %s" % (str(y_true.shape),
+                                                                                   str(y_pred.shape))
+    return -10. * np.log10(_mean_sq(y_pred, y_true))
+
+
+def psnr2(img1, img2):
+    """models.py:78-83."""
+    mse = _mean_sq(img1, img2)
+    if mse == 0:
+        return 100
+    return 20 * math.log10(255.0 / math.sqrt(mse))
+
+
+def psnr3(img1, img2):
+    """models.py:85-90 (keeps the reference's stray sqrt)."""
+    mse = _mean_sq(img1, img2)
+    if mse == 0:
+        return 100
+    return 10 * math.log10((255.0 ** 2) / math.sqrt(mse))
+
+
+# ---- Lambda helpers used by DifvdsrDouble (tensor-in / tensor-out on device NHWC float32 tensors) ----
+def resizeBlockLight09(my_input):
+    """models.py:977-978: tf.scalar_mul(0.9, x) (fused into the conv epilogue inside the engine)."""
+    return my_input * 0.9
+
+
+def resizeBlockLight01(my_input):
+    """models.py:985-986."""
+    return my_input * 0.1
+
+
+def resizeRes_outputshape(my_input_shape):
+    """models.py:1451."""
+    return my_input_shape
+
+
+def resizeX4_outputshape(my_input_shape):
+    """models.py:1383-1390."""
+    shape = list(my_input_shape)
+    size = [4 * int(s) for s in my_input_shape[1:3]]
+    shape[1] = size[0]
+    shape[2] = size[1]
+    return tuple(shape)
+
+
+resizeX4bil_outputshape = resizeX4_outputshape
+
+
+def resizeX4bil(my_input):
+    """models.py:1392-1399: tf.image.resize_bilinear(x, [4h, 4w]) with TF1 legacy sampling.
+    Accepts a numpy NHWC array or a device tensor (C % 8 == 0); returns the same kind."""
+    import torch
+    from sr100 import ops
+    if isinstance(my_input, np.ndarray):
+        return ops.bilinear4(ops.to_device(my_input, torch.float32)).cpu().numpy()
+    return ops.bilinear4(my_input)
+
+
+class _Adam(object):
+    """optimizers.Adam(lr, beta_1) record (models.py:1212); Keras-2 defaults for the rest."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, decay=0.):
+        self.lr, self.beta_1, self.beta_2, self.epsilon, self.decay = lr, beta_1, beta_2, epsilon, decay
+
+
+class _ModelCheckpoint(object):
+    """keras.callbacks.ModelCheckpoint(filepath, save_weights_only=True, period=1) as used at
+    models.py:141-142: saves every epoch to filepath.format(epoch=epoch+1, **logs)."""
+
+    def __init__(self, filepath, monitor='val_loss', save_best_only=False, mode='auto', save_weights_only=True,
+                 period=1):
+        self.filepath, self.period, self.model = filepath, period, None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_epoch_end(self, epoch, logs=None):
+        logs = dict(logs or {})
+        logs.setdefault("val_acc", float("nan"))
+        if (epoch + 1) % self.period == 0:
+            path = self.filepath.format(epoch=epoch + 1, **logs)
+            d = os.path.dirname(path)
+            if d and not os.path.isdir(d):
+                os.makedirs(d)
+            self.model.save_weights(path, overwrite=True)
+
+
+class BaseSuperResolutionModel(object):
+
+    def __init__(self, model_name, scale_factor):
+        """models.py:95-109."""
+        self.model = None
+        self.model_name = model_name
+        self.scale_factor = scale_factor
+        self.weight_path = None
+
+        self.type_scale_type = "norm"  # Default = "norm" = 1. / 255
+        self.type_requires_divisible_shape = False
+        self.type_true_upscaling = False
+
+        self.evaluation_func = None
+        self.uses_learning_phase = False
+        self._engine = None  # device-resident weights, shared by every create_model() of this object
+
+    def create_model(self, height=32, width=32, channels=3, load_weights=False, batch_size=2):
+        """models.py:111-129: validates the shape and returns the input shape (width-major like the reference)."""
+        if self.type_requires_divisible_shape:
+            assert height * img_utils._image_scale_multiplier % 4 == 0, "Height of the image must be divisible by 4"
+            assert width * img_utils._image_scale_multiplier % 4 == 0, "Width of the image must be divisible by 4"
+        shape = (width * img_utils._image_scale_multiplier, height * img_utils._image_scale_multiplier, channels)
+        return shape
+
+    def fit(self, batch_size=2, nb_epochs=100, save_history=True, history_fn="Model History.txt"):
+        """models.py:131-157."""
+        samples_per_epoch = img_utils.image_count()
+        val_count = img_utils.val_image_count()
+        if self.model is None:
+            self.create_model(batch_size=batch_size)
+        callback_list = [_ModelCheckpoint(self.weight_path, monitor='val_PSNRLoss', save_best_only=False,
+                                          mode='max', save_weights_only=True, period=1)]
+        if save_history:
+            callback_list.append(HistoryCheckpoint(history_fn))
+        print("Training model : %s" % (self.__class__.__name__))
+        trainset = img_utils.image_generator(train_path, scale_factor=self.scale_factor,
+                                             small_train_images=self.type_true_upscaling, batch_size=batch_size)
+        self.model.fit_generator(trainset, steps_per_epoch=samples_per_epoch, epochs=nb_epochs,
+                                 callbacks=callback_list,
+                                 validation_data=img_utils.image_generator(validation_path,
+                                                                           scale_factor=self.scale_factor,
+                                                                           small_train_images=self.type_true_upscaling,
+                                                                           batch_size=batch_size),
+                                 validation_steps=val_count)
+        return self.model
+
+    def evaluate(self, validation_dir):
+        raise NotImplementedError("evaluate()/_evaluate need scipy.misc.imresize bicubic data prep "
+                                  "(models.py:1519-1721); SURVEY.md 8(f) 'next' row")
+
+    def upVideo(self, imgObj, save_intermediate=False, return_image=False, suffix="scaled",
+                patch_size=8, mode="patch", verbose=False):
+        """models.py:165-182: whole-image forward.  Like the reference, the [0,1] network output is clipped and
+        cast to uint8 WITHOUT the x255 rescale (models.py:181)."""
+        img_width, img_height = imgObj.shape[0], imgObj.shape[1]
+        images = np.expand_dims(imgObj, axis=0)
+        img_conv = images.astype(np.float32) / 255.
+        model = self.create_model(img_height, img_width, load_weights=True)
+        result = model.predict(img_conv, batch_size=128, verbose=verbose)
+        result = result[0, :, :, :]
+        return np.clip(result, 0, 255).astype('uint8')
+
+    def upscaleStepPatch(self, img_path, save_intermediate=False, return_image=False, suffix="scaled",
+                         patch_size=256, scalemulti=4, step_patch=64, mode="patch", verbose=True):
+        """models.py:184-415.  The whole chain (zero-pad canvas, 96/64 patch gather, /255, conv stack, x255,
+        stitch with the 8-px crop, clip -> uint8 truncation) runs on the device; only the uint8 image goes in
+        and the uint8 canvas comes back.  `step_patch` is ignored like in the reference (forced to 64, :248)."""
+        import torch
+        from PIL import Image
+        from sr100 import ops
+
+        path = os.path.splitext(img_path)
+        filename = path[0] + "_" + suffix + "(%dx)" % (self.scale_factor) + path[1]
+
+        true_img = np.asarray(Image.open(img_path).convert("RGB"))       # imread(img_path, mode='RGB'), :212
+        orig_height, orig_width = true_img.shape[0], true_img.shape[1]
+        step_patch = 64                                                   # :248
+        if mode == 'patch':
+            canvas_h, canvas_w = ops.canvas_size(orig_height, orig_width, patch_size, step_patch)  # :225-256
+        else:
+            canvas_h, canvas_w = orig_height + patch_size, orig_width + patch_size
+        if verbose:
+            print("Old Size : ", (canvas_h, canvas_w, 3))
+        img_dev = ops.to_device(true_img, torch.uint8)
+
+        if mode == 'patch':
+            images, counts = ops.patch_gather_u8(img_dev, (canvas_h, canvas_w), (patch_size, patch_size),
+                                                 step_patch, divisor=255.0)          # :272 + :336
+            if verbose:
+                print("Number of patches = %d, Patch Shape = (%d, %d)" % (images.shape[0], patch_size, patch_size))
+            if save_intermediate:
+                fn = path[0] + "_intermediate_" + path[1]
+                first = (images[0] * 255.0).cpu().numpy()                             # imsave(fn, images[0]), :329
+                lo, hi = first.min(), first.max()
+                sc = 255.0 / (hi - lo) if hi > lo else 1.0
+                Image.fromarray(((first - lo) * sc + 0.5).astype(np.uint8)).save(fn)
+            model = self.create_model(patch_size, patch_size, load_weights=True)       # :338
+            result = model.engine.forward_device(images)                              # :342
+            _, result_u8 = ops.patch_stitch(result, counts, (patch_size, patch_size), step_patch, scalemulti,
+                                            (canvas_h, canvas_w), mul=255.0, want_f32=False,
+                                            want_u8=True)                             # :351, :382, :391
+        else:
+            canvas = torch.zeros(1, canvas_h, canvas_w, 3, device=img_dev.device, dtype=torch.float32)
+            canvas[0, :orig_height, :orig_width] = img_dev.to(torch.float32) / 255.0
+            model = self.create_model(canvas_h, canvas_w, load_weights=True)
+            result = model.engine.forward_device(canvas)
+            result_u8 = torch.clamp(result[0] * 255.0, 0, 255).to(torch.uint8)
+        result = result_u8.cpu().numpy()
+        if return_image:
+            return result                                                             # uncropped canvas, :405-407
+        if verbose:
+            print("Saving image.")
+        outresult = result[0:orig_height * scalemulti, 0:orig_width * scalemulti]      # :412
+        Image.fromarray(outresult).save(filename)                                     # :415
+
+    def upscale_arrays(self, images, patch_size=96, scalemulti=4, return_canvas=False):
+        """Batched in-memory form of upscaleStepPatch(mode='patch') (no file I/O): list of uint8 (H,W,3) host
+        arrays -> list of uint8 (4H,4W,3) host arrays.  Tiles of all images share one pass over the conv stack.
+        The timed end-to-end path of bench.py: host -> device copies in, device -> host copies out."""
+        import torch
+        model = self.model if self.model is not None else self.create_model(patch_size, patch_size, load_weights=False)
+        eng = model.engine
+        dev = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().to(eng.device, non_blocking=True)
+               for im in images]
+        canv = eng.upscale_images_device(dev, patch=patch_size, step=64, scale=scalemulti)
+        outs = []
+        for im, c in zip(images, canv):
+            full = c.cpu().numpy()
+            outs.append(full if return_canvas else full[0:im.shape[0] * scalemulti, 0:im.shape[1] * scalemulti])
+        return outs
+
+    def upscalePatch(self, *a, **k):
+        raise NotImplementedError("upscalePatch (models.py:419-604) needs PIL-exact bicubic imresize; "
+                                  "SURVEY.md 8(f) 'next' row")
+
+    def upscale(self, *a, **k):
+        raise NotImplementedError("upscale (models.py:606-852) needs PIL-exact bicubic imresize; "
+                                  "SURVEY.md 8(f) 'next' row")
+
+
+class DifvdsrDouble(BaseSuperResolutionModel):
+    """models.py:1146-1270: 1x1 head, 16 5/3 residual blocks, 6 light blocks, bilinear x4, 2 5/3 blocks at HR,
+    3x3 tail; 86 convs, 21,838,211 parameters."""
+
+    weights_file = "weights_Double/weights025-17-0.93.h5"   # models.py:1217
+
+    def __init__(self, scale_factor):
+        super(DifvdsrDouble, self).__init__("Image ScaleGen", scale_factor)
+        self.weight_path = "weights_Double/weights025-{epoch:02d}-{val_acc:.2f}.h5"   # models.py:1155
+        self._loaded_from = None
+
+    def create_model(self, height=32, width=32, channels=3, load_weights=False, batch_size=128):
+        """models.py:1159-1222.  Returns the Keras-like Model (sr100.kmodel.Model) for (height, width) inputs."""
+        from sr100.kmodel import Model
+        from sr100.engine import Engine
+        init = super(DifvdsrDouble, self).create_model(height, width, channels, load_weights, batch_size)
+        if channels != 3:
+            raise ValueError("DifvdsrDouble is a 3-channel model (models.py:1177)")
+        if self._engine is None:
+            self._engine = Engine()                      # glorot_uniform kernels, zero biases (Keras defaults)
+        model = Model(init, engine=self._engine)
+        model.compile(optimizer=_Adam(1e-4, 0.9), loss='mse', metrics=['accuracy'])   # :1212-1213
+        if load_weights:
+            wpath = os.environ.get("SR100_WEIGHTS", self.weights_file)
+            if self._loaded_from != wpath:               # the reference reloads per image (:338); once is enough
+                model.load_weights(wpath)                # :1217-1218
+                self._loaded_from = wpath
+        self.model = model
+        return model
+
+    def fit(self, batch_size=10, nb_epochs=100, save_history=False, history_fn="ScaleGen History.txt"):
+        """models.py:1225-1226."""
+        return super(DifvdsrDouble, self).fit(batch_size, nb_epochs, save_history, history_fn)
+
+
+class Difvdsr4(BaseSuperResolutionModel):
+    def __init__(self, scale_factor):
+        super(Difvdsr4, self).__init__("Image ScaleGen", scale_factor)
+
+    def create_model(self, *a, **k):
+        raise NotImplementedError("Difvdsr4 (models.py:992-1142) is a SURVEY.md 8(f) 'next' row")
+
+
+class Difvdsr(BaseSuperResolutionModel):
+    def __init__(self, scale_factor):
+        super(Difvdsr, self).__init__("Image ScaleGen", scale_factor)
+
+    def create_model(self, *a, **k):
+        raise NotImplementedError("Difvdsr (models.py:1274-1357) is a SURVEY.md 8(f) 'next' row")

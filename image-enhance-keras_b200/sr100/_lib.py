@@ -84,6 +84,7 @@ SIGNATURES = {
     "sr_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_rgb2y_u8": (_i, [_vp, _sz, _vp, _vp]),
     "sr_score_pair_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "sr_sum_sq_diff_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "sr_mse_loss_grad": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
     "sr_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
     "sr_axpby_f32": (_i, [_vp, _vp, _f, _f, _sz, _vp, _vp, _vp]),

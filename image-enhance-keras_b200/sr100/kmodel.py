@@ -1,0 +1,172 @@
+"""Keras-`Model`-shaped facade over the sm_100a engine: exactly the methods the reference calls on the
+object returned by create_model (models.py:178,342,541,783 predict; :1218 load_weights; :1213 compile;
+:146-155 fit_generator; get/set_weights for identical-weights parity)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import Engine, layer_specs
+
+
+class Layer:
+    def __init__(self, model, name, ksize, cin, cout):
+        self._model, self.name = model, name
+        self.kernel_size, self.filters, self.input_channels = (ksize, ksize), cout, cin
+        self.trainable = True
+
+    def get_weights(self):
+        w, b = self._model.engine.master[self.name]
+        return [w.cpu().numpy(), b.cpu().numpy()]
+
+    def set_weights(self, ws):
+        d = self._model.engine.get_weights_dict()
+        d[self.name] = (ws[0], ws[1])
+        self._model.engine.set_weights_dict(d)
+
+    def count_params(self):
+        k = self.kernel_size[0]
+        return k * k * self.input_channels * self.filters + self.filters
+
+
+class Model:
+    def __init__(self, input_shape, engine=None, **engine_kw):
+        self.input_shape = (None,) + tuple(input_shape)
+        h, w, c = input_shape
+        self.output_shape = (None, 4 * h, 4 * w, 3)
+        self.engine = engine if engine is not None else Engine(**engine_kw)
+        self.layers = [Layer(self, *s) for s in layer_specs()]
+        self.optimizer = None
+        self.loss = None
+        self.metrics = []
+        self.stop_training = False
+        self._trainer = None
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, x, batch_size=32, verbose=0):
+        """float NHWC in [0,1] -> float32 NHWC, x4 (Keras Model.predict; batch_size only bounds memory here)."""
+        x = np.asarray(x)
+        if x.ndim != 4 or x.shape[-1] != 3:
+            raise ValueError("Error when checking input: expected 4-D NHWC input with 3 channels, got %s" % (x.shape,))
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.engine.device)
+        out = self.engine.forward_device(xd)
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ weights
+    def get_weights(self):
+        out = []
+        for l in self.layers:
+            out.extend(l.get_weights())
+        return out
+
+    def set_weights(self, ws):
+        if len(ws) != 2 * len(self.layers):
+            raise ValueError("You called `set_weights(weights)` with a weight list of length %d, but the model "
+                             "was expecting %d weights." % (len(ws), 2 * len(self.layers)))
+        d = {l.name: (ws[2 * i], ws[2 * i + 1]) for i, l in enumerate(self.layers)}
+        self.engine.set_weights_dict(d)
+
+    def count_params(self):
+        return sum(l.count_params() for l in self.layers)
+
+    def save_weights(self, path, overwrite=True):
+        d = {}
+        for name, (w, b) in self.engine.get_weights_dict().items():
+            d[name + "/kernel:0"] = w
+            d[name + "/bias:0"] = b
+        if path.endswith(".h5"):
+            path = path[:-3] + ".npz"  # h5py is not available offline; same layer/tensor names, npz container
+        np.savez(path, **d)
+        return path
+
+    def load_weights(self, path):
+        cand = [path]
+        if path.endswith(".h5"):
+            cand.append(path[:-3] + ".npz")
+        for p in cand:
+            if os.path.exists(p) and p.endswith(".npz"):
+                z = np.load(p)
+                self.engine.set_weights_dict({n: (z[n + "/kernel:0"], z[n + "/bias:0"]) for n, _, _, _ in layer_specs()})
+                return
+        if os.path.exists(path) and path.endswith(".h5"):
+            try:
+                import h5py  # noqa: F401
+            except ImportError as e:
+                raise ImportError("`load_weights` of a Keras HDF5 file requires h5py, which is not installed; "
+                                  "convert the file to .npz with keys '<layer>/kernel:0', '<layer>/bias:0'") from e
+            self._load_h5(path)
+            return
+        raise OSError("Unable to open file (unable to open file: name = '%s', errno = 2, error message = "
+                      "'No such file or directory')" % path)
+
+    def _load_h5(self, path):
+        import h5py
+        d = {}
+        with h5py.File(path, "r") as f:
+            g = f["model_weights"] if "model_weights" in f else f
+            for name, _, _, _ in layer_specs():
+                grp = g[name][name] if name in g[name] else g[name]
+                d[name] = (np.asarray(grp["kernel:0"]), np.asarray(grp["bias:0"]))
+        self.engine.set_weights_dict(d)
+
+    # ------------------------------------------------------------------ training facade
+    def compile(self, optimizer=None, loss=None, metrics=None):
+        self.optimizer, self.loss, self.metrics = optimizer, loss, list(metrics or [])
+        if loss not in (None, "mse", "mean_squared_error"):
+            raise ValueError("only loss='mse' is implemented (models.py:1213)")
+
+    def _get_trainer(self):
+        if self._trainer is None:
+            from .train import Trainer
+            opt = self.optimizer
+            self._trainer = Trainer(self.engine, lr=getattr(opt, "lr", 1e-4), beta_1=getattr(opt, "beta_1", 0.9),
+                                    beta_2=getattr(opt, "beta_2", 0.999), epsilon=getattr(opt, "epsilon", 1e-7))
+        return self._trainer
+
+    def train_on_batch(self, x, y):
+        return self._get_trainer().train_on_batch(x, y)
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, callbacks=None, validation_data=None,
+                      validation_steps=None, verbose=1, **_):
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
+        history = {}
+        for epoch in range(epochs):
+            losses = []
+            for _ in range(int(steps_per_epoch)):
+                x, y = next(generator)
+                losses.append(self.train_on_batch(x, y))
+            logs = {"loss": float(np.mean(losses)) if losses else float("nan")}
+            if validation_data is not None and validation_steps:
+                vl = []
+                for _ in range(int(validation_steps)):
+                    x, y = next(validation_data)
+                    vl.append(self._get_trainer().evaluate(x, y))
+                logs["val_loss"] = float(np.mean([v[0] for v in vl]))
+                logs["val_acc"] = float(np.mean([v[1] for v in vl]))
+            for k, v in logs.items():
+                history.setdefault(k, []).append(v)
+            if verbose:
+                print("Epoch %d/%d - %s" % (epoch + 1, epochs, " - ".join("%s: %.6f" % kv for kv in logs.items())))
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        return history
+
+    def summary(self):
+        print("_" * 65)
+        print("%-28s%-26s%s" % ("Layer (type)", "Output Shape", "Param #"))
+        print("=" * 65)
+        for l in self.layers:
+            print("%-28s%-26s%d" % (l.name + " (Conv2D)", "(None, ?, ?, %d)" % l.filters, l.count_params()))
+        print("=" * 65)
+        print("Total params: {:,}".format(self.count_params()))

@@ -165,6 +165,10 @@ typedef struct sr_score_result {
 int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w, int crop,
                      sr_score_result* result, void* stream);
 
+/* *out += sum (a[i]-b[i])^2 in fp64 (device accumulator, zero it first): the reduction inside
+ * PSNR.psnrVDSR / PSNRTorch / psnrSVLAB / psnrNITRE (PSNR.py:7-84) and models.psnr* (models.py:71-90). */
+int sr_sum_sq_diff_f64(const double* a, const double* b, size_t n, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training step pieces (models.py:131-157 fit, :1212-1213 compile: mse + Adam(1e-4, 0.9)).
  * ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,114 @@
+"""-m gpu: whole DifvdsrDouble forward (engine through the Keras-like Model facade) against the CPU oracle with
+identical random-init weights.  Tolerance from BASELINE.json north_star: max-abs <= 2e-2 on [0,1] outputs for the
+bf16 path and <= 0.01 dB PSNR."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _smooth_images(rng, n, h, w):
+    from scipy.ndimage import uniform_filter
+    img = rng.integers(0, 256, size=(n, h + 4, w + 4, 3)).astype(np.float32)
+    img = uniform_filter(img, size=(1, 5, 5, 1))[:, 2:-2, 2:-2]
+    return (img / 255.0).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    from oracle import model as om
+    return om.init_weights(1234, bias_scale=0.01)
+
+
+@pytest.fixture(scope="module")
+def dmodel(weights):
+    import models
+    m = models.DifvdsrDouble(1)
+    model = m.create_model(24, 24)
+    model.engine.set_weights_dict(weights)
+    return m, model
+
+
+def _psnr(a, b):
+    return -10 * np.log10(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 24), (1, 48, 40), (1, 96, 96)])
+def test_forward_matches_oracle(dmodel, weights, shape):
+    from oracle import model as om
+    _, model = dmodel
+    rng = np.random.default_rng(shape[1])
+    x = _smooth_images(rng, *shape)
+    got = model.predict(x, batch_size=1)
+    want = om.forward_numpy(weights, x)
+    assert got.shape == want.shape == (shape[0], 4 * shape[1], 4 * shape[2], 3)
+    assert got.dtype == np.float32 and got.min() >= 0
+    err = np.abs(got - want).max()
+    assert err <= 2e-2, err                      # north_star bf16 tolerance
+    assert err <= 2e-3, err                      # what the fp32-stream design actually achieves (outputs ~0.05)
+    # PSNR against a synthetic HR target must agree within 0.01 dB
+    target = np.clip(want + rng.normal(0, 0.02, size=want.shape), 0, 1)
+    assert abs(_psnr(got, target) - _psnr(want, target)) <= 0.01
+
+
+def test_zero_bias_default_and_stream_variants(weights):
+    """All three residual-stream modes stay inside the tolerance; bf16 stream is the loosest."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    rng = np.random.default_rng(11)
+    x = _smooth_images(rng, 1, 32, 32)
+    want = om.forward_numpy(weights, x)
+    errs = {}
+    for stream in ("bf16", "lr32", "fp32"):
+        eng = Engine(weights, stream=stream)
+        got = eng.forward_device(torch.from_numpy(x).cuda()).cpu().numpy()
+        errs[stream] = float(np.abs(got - want).max())
+        assert errs[stream] <= 2e-2
+    assert errs["fp32"] <= errs["bf16"] + 1e-6
+
+
+def test_a_modes_agree(weights):
+    from sr100.engine import Engine
+    rng = np.random.default_rng(12)
+    x = torch.from_numpy(_smooth_images(rng, 2, 24, 24)).cuda()
+    y0 = Engine(weights, a_mode=0).forward_device(x).cpu().numpy()
+    y1 = Engine(weights, a_mode=1).forward_device(x).cpu().numpy()
+    y2 = Engine(weights, a_mode=0, nacc=2).forward_device(x).cpu().numpy()
+    assert np.abs(y0 - y1).max() < 1e-5 and np.abs(y0 - y2).max() < 1e-5
+
+
+def test_sub_batching_is_invisible(weights):
+    from sr100.engine import Engine
+    rng = np.random.default_rng(13)
+    x = torch.from_numpy(_smooth_images(rng, 5, 16, 16)).cuda()
+    a = Engine(weights, max_pixels=16 * 16 * 2).forward_device(x).cpu().numpy()     # 2 + 2 + 1
+    b = Engine(weights, max_pixels=16 * 16 * 64).forward_device(x).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+def test_weights_roundtrip_and_npz(dmodel, weights, tmp_path):
+    _, model = dmodel
+    ws = model.get_weights()
+    assert len(ws) == 172 and ws[0].shape == (1, 1, 3, 128) and ws[-2].shape == (3, 3, 128, 3)
+    assert sum(w.size for w in ws) == 21838211 == model.count_params()
+    assert np.array_equal(ws[2], weights["conv2d_1"][0])
+    p = model.save_weights(str(tmp_path / "w.h5"))
+    assert p.endswith(".npz")
+    import models
+    m2 = models.DifvdsrDouble(1)
+    mod2 = m2.create_model(24, 24)
+    mod2.load_weights(str(tmp_path / "w.h5"))
+    assert all(np.array_equal(a, b) for a, b in zip(mod2.get_weights(), ws))
+    with pytest.raises(OSError):
+        mod2.load_weights(str(tmp_path / "missing.h5"))
+    with pytest.raises(ValueError):
+        model.set_weights(ws[:-1])
+
+
+def test_predict_rejects_bad_shapes(dmodel):
+    _, model = dmodel
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((24, 24, 3), dtype=np.float32))
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((1, 24, 24, 4), dtype=np.float32))

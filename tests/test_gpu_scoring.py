@@ -1,0 +1,95 @@
+"""-m gpu: scoring kernels (crop + RGB->Y + PSNR + SSIM) and the PSNR.py / scorpath.py mirrors vs the oracle and the
+reference's own PSNR.py outputs.  Tolerances from SURVEY 8(d): PSNR +-0.01 dB, SSIM +-1e-4 (we assert far tighter)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scoring as osc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(rng, h, w, sigma=3.0):
+    a = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+    b = np.clip(a.astype(np.float64) + rng.normal(0, sigma, size=a.shape), 0, 255).astype(np.uint8)
+    return a, b
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (57, 91), (27, 27), (512, 512), (228, 344)])
+def test_score_pair_matches_oracle(shape):
+    import scorpath
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    a, b = _pair(rng, *shape)
+    psnr, ssim_rgb, ssim_y = scorpath.score_pair(a, b, 10)
+    w_psnr, w_rgb, w_y = osc.score_pair(a, b, 10)
+    assert abs(psnr - w_psnr) < 1e-7
+    assert abs(ssim_rgb - w_rgb) < 1e-9
+    assert abs(ssim_y - w_y) < 1e-9
+
+
+def test_score_identical_and_errors():
+    from sr100 import ops
+    from sr100 import _lib as L
+    a = np.random.default_rng(0).integers(0, 256, size=(40, 40, 3)).astype(np.uint8)
+    r = ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(a).cuda(), 10)
+    assert r["ssim_y"] == pytest.approx(1.0, abs=1e-12) and r["psnr_y"] == float("inf")
+    with pytest.raises(L.SrError):
+        ops.score_pair(torch.from_numpy(a[:24, :24].copy()).cuda(), torch.from_numpy(a[:24, :24].copy()).cuda(), 10)
+    with pytest.raises(ValueError):
+        ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(a[:30].copy()).cuda(), 10)
+
+
+def test_batch_scale_checksum():
+    """DIV2K-shaped pair (config 3 output size 1356x2040): blocks partition the image exactly once:
+    sum of squared Y error from the kernel == numpy, n_pix/n_win closed form."""
+    from sr100 import ops
+    rng = np.random.default_rng(8)
+    a, b = _pair(rng, 1356, 2040)
+    r = ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), 10)
+    ya, yb = osc.rgb2ycbcr_y(a[10:-10, 10:-10]), osc.rgb2ycbcr_y(b[10:-10, 10:-10])
+    assert r["n_pix"] == 1336 * 2020 and r["n_win"] == 1330 * 2014
+    assert r["sum_sq_y"] == pytest.approx(float(np.sum((ya - yb) ** 2)), rel=1e-10)
+
+
+def test_rgb2y_and_psnr_mirrors_match_reference_golden(golden_dir):
+    import PSNR
+    import scorpath
+    z = np.load(golden_dir + "/psnr_ref.npz")
+    a, b, ya, yb = z["a"], z["b"], z["ya"], z["yb"]
+    assert np.abs(scorpath.setimgrgb2ycbcr(a) - ya).max() < 1e-10
+    assert PSNR.psnrNITRE(yb, ya, 0) == pytest.approx(float(z["psnrNITRE_y"]), abs=1e-9)
+    assert PSNR.psnrNITRE(yb, ya, 4) == pytest.approx(float(z["psnrNITRE_y_shave4"]), abs=1e-9)
+    assert PSNR.PSNRTorch(yb, ya, 0) == pytest.approx(float(z["PSNRTorch_y"]), abs=1e-9)
+    assert PSNR.PSNRTorch(ya, ya, 0) == 100
+    assert PSNR.psnrVDSR(yb, ya, 2) == pytest.approx(float(z["psnrVDSR_y_2"]), abs=1e-9)
+    assert PSNR.psnrSVLAB(a, b) == pytest.approx(float(z["psnrSVLAB_u8"]), abs=1e-9)
+    assert np.array_equal(PSNR.im2double(a)[:2, :3], z["im2double_a"])
+    assert np.array_equal(PSNR.im2doubleZ(a)[:2, :3], z["im2doubleZ_a"])
+    import models
+    assert models.psnr2(a.astype(np.float64), b.astype(np.float64)) == pytest.approx(
+        osc.psnr_torch(a, b, 0), abs=1e-9)
+
+
+def test_cv2_colour_mirrors_match_reference_golden(golden_dir):
+    import scorpath
+    z = np.load(golden_dir + "/cv2_colour_ref.npz")
+    assert np.array_equal(scorpath.rgb2ycbcrCV(z["a"]), z["ycbcr"])
+    assert np.array_equal(scorpath.ycbcr2rgb(z["ycbcr"].copy()), z["rgb_back"])
+    assert scorpath.crop_border(np.zeros((30, 40, 3)), 10).shape == (10, 20, 3)
+
+
+def test_scorpath_main_on_directory(tmp_path, capsys):
+    from PIL import Image
+    import scorpath
+    rng = np.random.default_rng(2)
+    want = []
+    for name, shape in (("bird_GT", (72, 72)), ("woman_GT", (57, 86))):
+        a, b = _pair(rng, *shape)
+        Image.fromarray(a).save(str(tmp_path / (name + ".bmp")))
+        Image.fromarray(b).save(str(tmp_path / (name + "_scaled(1x).bmp")))
+        want.append(osc.score_pair(a, b, 10))
+    mp, ms, my = scorpath.main(str(tmp_path) + "/")
+    assert mp == pytest.approx(np.mean([w[0] for w in want]), abs=1e-7)
+    assert ms == pytest.approx(np.mean([w[1] for w in want]), abs=1e-9)
+    assert my == pytest.approx(np.mean([w[2] for w in want]), abs=1e-9)
+    assert "SCOR MEAN psnr" in capsys.readouterr().out

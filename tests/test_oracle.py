@@ -1,0 +1,145 @@
+"""CPU tests: the oracle against the reference's own outputs (tests/golden, produced by oracle/refgen.py
+running the reference code verbatim) and against closed-form properties."""
+import numpy as np
+import pytest
+
+from oracle import model as om
+from oracle import scoring as osc
+from oracle import shuffle as osh
+from oracle import tiling as ot
+
+
+def test_tiling_matches_reference_golden(golden_dir):
+    z = np.load(golden_dir + "/tiling_ref.npz")
+    for ci in range(5):
+        ch, cw, p, st, sc, cnt_h, cnt_w = [int(v) for v in z["c%d_meta" % ci]]
+        crng = np.random.default_rng(1000 + ci)
+        canvas = crng.integers(0, 256, size=(ch, cw, 3)).astype(np.float64)
+        assert np.array_equal(canvas.astype(np.uint8), z["c%d_canvas" % ci])
+        patches, counts = ot.extract_patches_step(canvas, (p, p), st)
+        assert counts == (cnt_h, cnt_w)
+        assert np.array_equal(patches.sum(axis=(1, 2, 3)), z["c%d_patches_sum" % ci])
+        assert np.array_equal(patches[0].astype(np.uint8), z["c%d_patches_first" % ci])
+        assert np.array_equal(patches[-1].astype(np.uint8), z["c%d_patches_last" % ci])
+        up = crng.integers(-20, 281, size=(patches.shape[0], p * sc, p * sc, 3)).astype(np.float32)
+        rebuilt = ot.rebuild_from_patches_step((ch, cw), up, (p, p), counts, sc, st)
+        assert np.array_equal(rebuilt.astype(np.int16), z["c%d_rebuilt" % ci])
+    assert int(z["raises_h"][0]) == 1
+    with pytest.raises(ValueError):
+        ot.extract_patches_step(np.zeros((8, 30, 3)), (12, 12), 8)
+
+
+def test_canvas_geometry_matches_reference(golden_dir):
+    geo = np.load(golden_dir + "/tiling_ref.npz")["geometry_96_64"]
+    for h, w, ch, cw, cnt_h, cnt_w in geo.tolist():
+        assert ot.canvas_size(h, w, 96, 64) == (ch, cw)
+        _, counts = ot.extract_patches_step(np.zeros((ch, cw, 3)), (96, 96), 64)
+        assert counts == (cnt_h, cnt_w)
+    # Set5 shapes give 81/25/25/25/30 tiles, DIV2K-shape 54, 1080p 558
+    tiles = {(int(r[0]), int(r[1])): int(r[4] * r[5]) for r in geo}
+    assert tiles[(512, 512)] == 81 and tiles[(288, 288)] == 25 and tiles[(344, 228)] == 30
+    assert tiles[(339, 510)] == 54 and tiles[(1080, 1920)] == 558
+
+
+def test_identity_network_stitch_property():
+    """an 'identity' network (nearest-neighbour x4 of each patch) stitches back to the
+    nearest-neighbour x4 of the image -> defines patch order and ownership."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(70, 45, 3)).astype(np.uint8)
+    full, out = ot.upscale_step_patch(img, lambda x: np.repeat(np.repeat(x, 4, axis=1), 4, axis=2), 24, 16, 4)
+    want = np.repeat(np.repeat(img, 4, axis=0), 4, axis=1)
+    # float32 (v/255)*255 may land just below v -> truncation can lose 1; compare with that tolerance
+    assert out.shape == want.shape
+    assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_psnr_matches_reference_golden(golden_dir):
+    z = np.load(golden_dir + "/psnr_ref.npz")
+    ya, yb, a, b = z["ya"], z["yb"], z["a"], z["b"]
+    assert osc.psnr_nitre(yb, ya, 0) == pytest.approx(float(z["psnrNITRE_y"]), abs=1e-10)
+    assert osc.psnr_nitre(yb, ya, 4) == pytest.approx(float(z["psnrNITRE_y_shave4"]), abs=1e-10)
+    assert osc.psnr_torch(yb, ya, 0) == pytest.approx(float(z["PSNRTorch_y"]), abs=1e-10)
+    assert osc.psnr_torch(ya, ya, 0) == float(z["PSNRTorch_same"]) == 100
+    assert osc.psnr_vdsr(yb, ya, 2) == pytest.approx(float(z["psnrVDSR_y_2"]), abs=1e-10)
+    assert osc.psnr_svlab(a, b) == pytest.approx(float(z["psnrSVLAB_u8"]), abs=1e-10)
+    # PSNRTorch == psnrNITRE on 0..255 inputs
+    assert float(z["PSNRTorch_y"]) == pytest.approx(float(z["psnrNITRE_y"]), abs=1e-9)
+    # the Y formula used by the fixture equals the skimage restatement
+    assert np.allclose(osc.rgb2ycbcr_y(a), ya, atol=1e-10)
+
+
+def test_imgpatch_docstring_known_answer(golden_dir):
+    """imgpatch.py:193-213 (sklearn docstring): extract_patches_2d(arange(16).reshape(4,4), (2,2))."""
+    z = np.load(golden_dir + "/imgpatch_ref.npz")
+    p = z["doc_patches"]
+    assert p.shape == (9, 2, 2)
+    assert p[0].tolist() == [[0, 1], [4, 5]] and p[1].tolist() == [[1, 2], [5, 6]] and p[8].tolist() == [[10, 11], [14, 15]]
+
+
+def test_ssim_basic_properties():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, size=(40, 50, 3)).astype(np.uint8)
+    assert osc.ssim(a, a, 255.0, multichannel=True) == pytest.approx(1.0, abs=1e-12)
+    b = np.clip(a.astype(int) + rng.integers(-20, 21, size=a.shape), 0, 255).astype(np.uint8)
+    s = osc.ssim(a, b, 255.0, multichannel=True)
+    assert 0.5 < s < 1.0
+    assert osc.ssim(a, b, 255.0, multichannel=True) == pytest.approx(osc.ssim(b, a, 255.0, multichannel=True), abs=1e-12)
+
+
+def test_shuffle_index_maps():
+    """The three orderings of SURVEY 8a-6, derived here by replaying the reference tensor programs."""
+    r, C, H, W = 2, 3, 3, 4
+    x = np.arange(1 * H * W * C * r * r, dtype=np.float64).reshape(1, H, W, C * r * r)
+    a = osh.phase_shift_subpixel(x, r)
+    b = osh.depth_to_scale_tf(x, r, C)
+    c = osh.depth_to_scale_th(x.transpose(0, 3, 1, 2), r, C).transpose(0, 2, 3, 1)
+    d = osh.depth_to_space_tf(x, r)
+    for Y in range(H * r):
+        for X in range(W * r):
+            for ch in range(C):
+                src = x[0, Y // r, X // r]
+                assert a[0, Y, X, ch] == src[ch * r * r + (X % r) * r + (Y % r)]
+                assert b[0, Y, X, ch] == src[ch * r * r + (X % r) * r + (Y % r)]
+                assert c[0, Y, X, ch] == src[ch * r * r + (Y % r) * r + (X % r)]
+                assert d[0, Y, X, ch] == src[((Y % r) * r + (X % r)) * C + ch]
+
+
+def test_model_structure_counts():
+    specs = om.layer_specs()
+    assert len(specs) == 86
+    assert om.n_params() == 21838211
+    assert [s[1] for s in specs[1:5]] == [3, 5, 5, 3]     # creation order inside a 5/3 block
+    assert specs[-1] == ("conv2d_85", 3, 128, 3)
+    flop_lr = 2 * 3 * 128 + 16 * (2 * 9 + 2 * 25) * 128 * 128 * 2 + 6 * 18 * 128 * 128 * 2
+    flop_hr = 16 * (2 * 68 * 128 * 128 * 2 + 9 * 128 * 3 * 2)
+    assert flop_lr + flop_hr == 110605056
+
+
+def test_bilinear_legacy_semantics():
+    import torch
+    x = torch.arange(12, dtype=torch.float32).reshape(1, 1, 3, 4)
+    y = om.bilinear_x4_tf1(x)[0, 0]
+    assert y.shape == (12, 16)
+    assert float(y[0, 0]) == 0.0 and float(y[0, 1]) == 0.25 and float(y[0, 4]) == 1.0
+    assert float(y[0, 13]) == float(y[0, 12]) == 3.0          # last 3 columns replicate the edge
+    assert float(y[4, 0]) == 4.0 and float(y[1, 0]) == 1.0    # row step 4 per LR row
+    assert float(y[11, 15]) == 11.0
+
+
+def test_oracle_forward_small_runs_and_is_deterministic():
+    w = om.init_weights(7, bias_scale=0.01)
+    x = np.random.default_rng(0).random((1, 8, 8, 3)).astype(np.float32)
+    y1 = om.forward_numpy(w, x)
+    y2 = om.forward_numpy(w, x)
+    assert y1.shape == (1, 32, 32, 3) and np.array_equal(y1, y2) and y1.min() >= 0
+    y64 = om.forward_numpy(w, x, dtype=__import__("torch").float64)
+    assert np.abs(y1 - y64).max() < 1e-5
+
+
+def test_keras_adam_first_step():
+    import torch
+    p = torch.nn.Parameter(torch.tensor([1.0, -2.0]))
+    opt = om.KerasAdam([p], lr=1e-4)
+    opt.step([torch.tensor([0.5, -0.25])])
+    # t=1: m=(1-b1)g, v=(1-b2)g^2, lr_t = lr*sqrt(1-b2)/(1-b1) -> step ~= lr*sign(g) (eps=1e-7 slightly less)
+    assert torch.allclose(p.detach(), torch.tensor([1.0 - 1e-4, -2.0 + 1e-4]), atol=1e-8)

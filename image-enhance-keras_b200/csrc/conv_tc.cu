@@ -62,6 +62,105 @@ __device__ __forceinline__ uint64_t make_a_desc(uint32_t abase, int pix, int k16
   }
 }
 
+// Staged epilogue for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
+// 32-row x 256 B shared-memory tile as bf16 (16-byte chunks XOR-swizzled by row, conflict-free both
+// ways); phase 2 re-reads it with 16 lanes per pixel so that every global access of the residual,
+// mask and outputs is a fully coalesced 512 B (bf16) / 1 KB (fp32) warp transaction.
+__device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
+                                                    uint32_t t_acc, int f_base, uint8_t* stage,
+                                                    const float* s_bias, int lane) {
+  // ---- phase 1: this lane's pixel row
+  const int f = f_base + lane;
+  const int fr = f / P.PWs;
+  const int yy = fr - P.p;
+  const int xx = f - fr * P.PWs - P.p;
+  const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 && xx < P.BW &&
+                     (c.seg_x0 + xx) < P.W;
+  const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
+  uint8_t* my_row = stage + lane * 256;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(t_acc + cb * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q * 8 + e * 2;
+        const float a = P.alpha * (__uint_as_float(v[j]) + s_bias[cb * 32 + j]);
+        const float b = P.alpha * (__uint_as_float(v[j + 1]) + s_bias[cb * 32 + j + 1]);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  __syncwarp();
+  // ---- phase 2: 16 lanes per pixel, 2 pixels per warp instruction
+  const int half = lane >> 4, q = lane & 15;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = 2 * i + half;
+    const int pix = __shfl_sync(0xffffffffu, my_pix, r);
+    if (pix < 0) continue;
+    const uint4 sv = *reinterpret_cast<const uint4*>(stage + r * 256 + ((q ^ (r & 7)) << 4));
+    const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[2 * e] = __uint_as_float(w[e] << 16);
+      o[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+    }
+    const size_t off = (size_t)pix * 128 + q * 8;
+    if (P.res_f32) {
+      const float4 r0 = *reinterpret_cast<const float4*>(P.res_f32 + off);
+      const float4 r1 = *reinterpret_cast<const float4*>(P.res_f32 + off + 4);
+      o[0] = fmaf(P.beta, r0.x, o[0]); o[1] = fmaf(P.beta, r0.y, o[1]);
+      o[2] = fmaf(P.beta, r0.z, o[2]); o[3] = fmaf(P.beta, r0.w, o[3]);
+      o[4] = fmaf(P.beta, r1.x, o[4]); o[5] = fmaf(P.beta, r1.y, o[5]);
+      o[6] = fmaf(P.beta, r1.z, o[6]); o[7] = fmaf(P.beta, r1.w, o[7]);
+    } else if (P.res_bf16) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(P.res_bf16 + off);
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[2 * e] = fmaf(P.beta, __uint_as_float(rw[e] << 16), o[2 * e]);
+        o[2 * e + 1] = fmaf(P.beta, __uint_as_float(rw[e] & 0xFFFF0000u), o[2 * e + 1]);
+      }
+    }
+    if (P.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    if (P.relu_mask_bf16) {
+      const uint4 mv = *reinterpret_cast<const uint4*>(P.relu_mask_bf16 + off);
+      const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!(__uint_as_float(mw[e] << 16) > 0.f)) o[2 * e] = 0.f;
+        if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f)) o[2 * e + 1] = 0.f;
+      }
+    }
+    if (P.out_f32) {
+      *reinterpret_cast<float4*>(P.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(P.out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (P.out_bf16) {
+      uint32_t pw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+        pw[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(P.out_bf16 + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    }
+  }
+  __syncwarp();
+}
+
 }  // namespace
 
 template <int N_, int AMODE, int NACC, int NBUF>
@@ -85,7 +184,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                              ~uintptr_t(1023));
   uint8_t* a_buf = smem;
   uint8_t* w_buf = smem + 2 * P.a_bytes;
-  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(w_buf + P.num_wstages * WSTAGE);
+  constexpr int STAGE_BYTES = (N_ == 128) ? 4 * 32 * 256 : 0;  // epilogue staging: 32 rows x 256 B per warp
+  uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
+  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + STAGE_BYTES);
   float* s_bias = reinterpret_cast<float*>(bars + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -232,89 +333,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
-        const int f = c.f0 + acc * 128 + ew * 32 + lane;
-        const int fr = f / P.PWs;
-        const int yy = fr - P.p;
-        const int xx = f - fr * P.PWs - P.p;
-        const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                           xx < P.BW && (c.seg_x0 + xx) < P.W;
-        const size_t pix = ((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx;
         if constexpr (N_ == 128) {
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(t_base + acc * N_ + cb * 32, v);
-            tmem_ld_wait();
-            if (valid) {
-              float o[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                o[j] = P.alpha * (__uint_as_float(v[j]) + s_bias[cb * 32 + j]);
-              if (P.res_f32) {
-                const float4* rp = reinterpret_cast<const float4*>(P.res_f32 + pix * 128 + cb * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 r = rp[j];
-                  o[4 * j + 0] = fmaf(P.beta, r.x, o[4 * j + 0]);
-                  o[4 * j + 1] = fmaf(P.beta, r.y, o[4 * j + 1]);
-                  o[4 * j + 2] = fmaf(P.beta, r.z, o[4 * j + 2]);
-                  o[4 * j + 3] = fmaf(P.beta, r.w, o[4 * j + 3]);
-                }
-              } else if (P.res_bf16) {
-                const uint4* rp = reinterpret_cast<const uint4*>(P.res_bf16 + pix * 128 + cb * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 r = rp[j];
-                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    o[8 * j + 2 * q] = fmaf(P.beta, __uint_as_float(w[q] << 16), o[8 * j + 2 * q]);
-                    o[8 * j + 2 * q + 1] =
-                        fmaf(P.beta, __uint_as_float(w[q] & 0xFFFF0000u), o[8 * j + 2 * q + 1]);
-                  }
-                }
-              }
-              if (P.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
-              }
-              if (P.relu_mask_bf16) {
-                const uint4* mp =
-                    reinterpret_cast<const uint4*>(P.relu_mask_bf16 + pix * 128 + cb * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 r = mp[j];
-                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    if (!(__uint_as_float(w[q] << 16) > 0.f)) o[8 * j + 2 * q] = 0.f;
-                    if (!(__uint_as_float(w[q] & 0xFFFF0000u) > 0.f)) o[8 * j + 2 * q + 1] = 0.f;
-                  }
-                }
-              }
-              if (P.out_f32) {
-                float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * 128 + cb * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              }
-              if (P.out_bf16) {
-                uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + pix * 128 + cb * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162 h =
-                        __floats2bfloat162_rn(o[8 * j + 2 * q], o[8 * j + 2 * q + 1]);
-                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                  }
-                  op[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-              }
-            }
-          }
+          epilogue_staged_acc(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
+                              stage_buf + ew * (32 * 256), s_bias, lane);
         } else {
+          const int f = c.f0 + acc * 128 + ew * 32 + lane;
+          const int fr = f / P.PWs;
+          const int yy = fr - P.p;
+          const int xx = f - fr * P.PWs - P.p;
+          const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                             xx < P.BW && (c.seg_x0 + xx) < P.W;
+          const size_t pix = ((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx;
           uint32_t v[16];
           tmem_ld16(t_base + acc * N_, v);
           tmem_ld_wait();
@@ -430,7 +459,8 @@ static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad) 
 static constexpr size_t kSmemBudget = 227 * 1024;
 
 // Choose the column-segment width: maximise useful MMA rows subject to the shared-memory budget.
-static bool choose_geometry(int H, int W, int p, int T, int wstage, ConvKernelParams* P) {
+static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_bytes,
+                            ConvKernelParams* P) {
   double best_eff = -1.0;
   for (int nseg = 1; nseg <= W; ++nseg) {
     const int BW = (W + nseg - 1) / nseg;
@@ -440,8 +470,9 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, ConvKernelPa
     const int NR = (2 * p * PWs + 2 * p + PWs + T - 2) / PWs + 1;
     if (NR > 256) continue;
     const size_t a_bytes = ((size_t)NR * PWs * kChunk * 2 + 1023) & ~(size_t)1023;
-    const size_t fixed = 2 * a_bytes + 1024 /*align slack*/ + sizeof(ConvBarriers) + 128 * 4 + 64;
-    if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;
+    const size_t fixed =
+        2 * a_bytes + 1024 /*align slack*/ + stage_bytes + sizeof(ConvBarriers) + 128 * 4 + 64;
+    if (fixed + 5 * (size_t)wstage > kSmemBudget) continue;  // >= 5 weight stages in flight
     const int f_len = (H - 1) * PWs + BW;
     const int tps = (f_len + T - 1) / T;
     const double eff = (double)H * W / ((double)nseg * tps * T);
@@ -515,7 +546,12 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.W = d->W;
   P.NB = d->NB;
   P.p = p;
-  if (!choose_geometry(d->H, d->W, p, T, wstage, &P)) {
+  const int stage_bytes = pl->n_pad == 128 ? 4 * 32 * 256 : 0;
+  if ((double)d->NB * d->H * d->W >= 2147483647.0) {
+    delete pl;
+    return set_error(SR_ERR_UNSUPPORTED, "more than 2^31 pixels per tensor");
+  }
+  if (!choose_geometry(d->H, d->W, p, T, wstage, stage_bytes, &P)) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "no conv geometry fits shared memory");
   }
@@ -550,7 +586,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   pl->grid = std::min(P.total_tiles, sms);
-  pl->smem_bytes = 1024 + 2 * (size_t)P.a_bytes + (size_t)P.num_wstages * wstage +
+  pl->smem_bytes = 1024 + 2 * (size_t)P.a_bytes + (size_t)P.num_wstages * wstage + stage_bytes +
                    sizeof(ConvBarriers) + 128 * 4 + 64;
   *out = reinterpret_cast<sr_conv_plan*>(pl);
   return SR_OK;

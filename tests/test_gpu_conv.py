@@ -45,26 +45,34 @@ def test_conv_matches_oracle(lib, case, a_mode, nacc):
     got32, got16 = run_tc_conv(lib, xs, ws, bias, relu, alpha, beta, res, res_kind or "f32", cout, a_mode, nacc)
     want = oracle_conv(xs, ws, bias, relu, alpha, beta, res)
     assert not np.isnan(got32).any(), "some output pixels were never written"
-    # identical operands, fp32 accumulation on both sides: only the summation order differs
-    assert np.abs(got32 - want).max() < 2e-4
+    # identical operands, fp32 accumulation on both sides.  For cout == 128 the kernel stages the branch value
+    # alpha*(acc+bias) in bf16 before the residual add, so the fp32 output may differ from the oracle by half a
+    # bf16 ulp of the branch value (plus summation-order noise); the 3-channel tail stays in fp32 throughout.
+    branch = np.abs(oracle_conv(xs, ws, bias, 0, alpha, 0.0, None))
+    half_ulp = np.where(branch > 0, 2.0 ** (np.floor(np.log2(np.maximum(branch, 1e-30))) - 8), 0.0)
+    tol = 2e-4 + (half_ulp * 1.01 if cout == 128 else 0.0)
+    assert (np.abs(got32 - want) <= tol).all(), float(np.abs(got32 - want).max())
     assert np.abs(got16 - want).max() < 2e-2 * max(1.0, np.abs(want).max())
 
 
 def test_conv_linearity_at_full_tile_size(lib):
-    """Size-independent property at the BASELINE tile size (96x96 LR tile batch, 5x5): conv(a+b) = conv(a)+conv(b)."""
+    """Size-independent property at the BASELINE tile size (a batch of 96x96 LR tiles, 5x5 conv, 3-channel tail
+    variant so the output stays fp32): conv(a + b) == conv(a) + conv(b).  a, b are multiples of 1/8 so a + b is
+    exactly representable in bf16."""
     rng = np.random.default_rng(5)
-    a = _rand(rng, (8, 96, 96, 128), 0.25)
-    b = _rand(rng, (8, 96, 96, 128), 0.25)
-    ab = bf16_round(a + b)
-    keep = np.abs(ab - (a + b)).max(axis=3) == 0        # pixels where a+b is exactly representable
-    w = rng.standard_normal((5, 5, 128, 128)).astype(np.float32) / np.sqrt(3200)
-    ya, _ = run_tc_conv(lib, [a], [w], None)
-    yb, _ = run_tc_conv(lib, [b], [w], None)
-    yab, _ = run_tc_conv(lib, [ab], [w], None)
-    # compare only outputs whose whole 5x5 receptive field is exactly representable
-    k = torch.nn.functional.max_pool2d((~torch.from_numpy(keep)).float()[:, None], 5, 1, 2)[:, 0].numpy() == 0
-    assert k.sum() > 1000
-    assert np.abs((ya + yb) - yab)[k].max() < 1e-4
+    a = rng.integers(-16, 17, size=(8, 96, 96, 128)).astype(np.float32) / 8
+    b = rng.integers(-16, 17, size=(8, 96, 96, 128)).astype(np.float32) / 8
+    assert np.array_equal(bf16_round(a + b), a + b)
+    w = rng.standard_normal((5, 5, 128, 3)).astype(np.float32) / np.sqrt(3200)
+    ya, _ = run_tc_conv(lib, [a], [w], None, cout=3)
+    yb, _ = run_tc_conv(lib, [b], [w], None, cout=3)
+    yab, _ = run_tc_conv(lib, [a + b], [w], None, cout=3)
+    assert np.abs((ya + yb) - yab).max() < 1e-4
+    # and the 128-channel kernel agrees with the tail kernel on a shared output channel
+    w128 = np.zeros((5, 5, 128, 128), dtype=np.float32)
+    w128[..., :3] = w
+    y128, _ = run_tc_conv(lib, [a], [w128], None)
+    assert np.abs(y128[..., :3] - ya).max() <= 2e-4 + np.abs(ya).max() * 2.0 ** -8
 
 
 def test_head1x1_matches_oracle(lib):

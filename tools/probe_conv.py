@@ -36,11 +36,11 @@ for mode in (0, 1):
     case(name="k5_nacc2", ks=(5,), mode=mode, nacc=2)
     case(name="k3_w50_h33", ks=(3,), W=50, H=33, NB=3, mode=mode)
     case(name="k5_w384", ks=(5,), W=384, H=24, NB=1, mode=mode)
-    case(name="perf_k5_lr", ks=(5,), NB=32, H=96, W=96, mode=mode, iters=10, check=False)
-    case(name="perf_k3_lr", ks=(3,), NB=32, H=96, W=96, mode=mode, iters=10, check=False)
-    case(name="perf_k5_hr", ks=(5,), NB=2, H=384, W=384, mode=mode, iters=5, check=False)
-    case(name="perf_k5_lr_nacc2", ks=(5,), NB=32, H=96, W=96, mode=mode, nacc=2, iters=10, check=False)
-    case(name="perf_k5k3_hr", ks=(5, 3), NB=2, H=384, W=384, mode=mode, iters=5, check=False,
+    case(name="perf_k5_lr", ks=(5,), NB=32, H=96, W=96, mode=mode, iters=40, check=False)
+    case(name="perf_k3_lr", ks=(3,), NB=32, H=96, W=96, mode=mode, iters=40, check=False)
+    case(name="perf_k5_hr", ks=(5,), NB=2, H=384, W=384, mode=mode, iters=20, check=False)
+    case(name="perf_k5_lr_nacc2", ks=(5,), NB=32, H=96, W=96, mode=mode, nacc=2, iters=40, check=False)
+    case(name="perf_k5k3_hr", ks=(5, 3), NB=2, H=384, W=384, mode=mode, iters=20, check=False,
          res="f32", alpha=0.1, beta=0.9)
 
 

@@ -49,19 +49,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& P, int 
   return c;
 }
 
-template <int AMODE>
-__device__ __forceinline__ uint64_t make_a_desc(uint32_t abase, int pix, int k16, uint32_t lbo) {
-  if constexpr (AMODE == kAModeSwizzle64) {
-    // rows of 64 B (32 ch), 8-row groups 512 B apart, 64B swizzle; K advance = 32 B inside the row
-    return umma_smem_desc(abase + (uint32_t)pix * 64u + (uint32_t)k16 * 32u, 16u, 512u,
-                          SR_LAYOUT_SW64);
-  } else {
-    // [8ch group][pixel][8ch]: rows 16 B apart (SBO = 128 B per 8 rows), K core matrices LBO apart
-    return umma_smem_desc(abase + (uint32_t)pix * 16u + (uint32_t)k16 * 2u * lbo, lbo, 128u,
-                          SR_LAYOUT_NONE);
-  }
-}
-
 // Staged epilogue for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
 // 32-row x 256 B shared-memory tile as bf16 (16-byte chunks XOR-swizzled by row, conflict-free both
 // ways); phase 2 re-reads it with 16 lanes per pixel so that every global access of the residual,
@@ -272,54 +259,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      uint32_t ws = 0, ac = 0, it = 0;
-      const uint32_t lbo = (uint32_t)P.NR * P.PWs * 16u;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
-        const TileCoord c = decode_tile<T>(P, t);
-        const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
-        mbar_wait(&bars->tmem_empty[buf], bph ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + buf * (NACC * N_);
-        bool first = true;
-        for (int s = 0; s < P.nsrc; ++s) {
-          const int k = P.ksize[s];
-          const int pk = (k - 1) / 2;
-          const int ntaps = k * k;
-          for (int ch = 0; ch < kNumChunks; ++ch) {
-            const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
-            mbar_wait(&bars->a_full[aslot], aph);
+    // ------------------------------------------------ MMA issuer
+    // The loop runs warp-convergent (all 32 lanes wait on the barriers and carry the same descriptor words,
+    // so ptxas keeps them in uniform registers); only the elected lane issues tcgen05.mma / commit.
+    // Descriptors are {lo, hi} 32-bit words: hi is constant, lo = (smem address >> 4) | LBO field, so a tap
+    // shift, an accumulator step (128 rows) and a K step are plain 32-bit adds.
+    const bool leader = elect_one();
+    uint32_t ws = 0, ac = 0, it = 0;
+    const uint32_t lbo16 = (uint32_t)P.NR * P.PWs;  // interleave mode: bytes between K core matrices, >> 4
+    constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
+    constexpr uint32_t kHiNone = (128u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_NONE << 29);
+    constexpr uint32_t a_hi = AMODE == kAModeSwizzle64 ? kHiSw64 : kHiNone;
+    const uint32_t a_lo_fields = AMODE == kAModeSwizzle64 ? (1u << 16) : (lbo16 << 16);
+    const uint32_t a_pix = AMODE == kAModeSwizzle64 ? 4u : 1u;            // descriptor units per pixel row
+    const uint32_t a_k16 = AMODE == kAModeSwizzle64 ? 2u : 2u * lbo16;    // descriptor units per K=16 step
+    const uint32_t a_buf_lo = (smem_u32(a_buf) >> 4) | a_lo_fields;
+    const uint32_t a_slot_step = (uint32_t)P.a_bytes >> 4;
+    const uint32_t w_buf_lo = (smem_u32(w_buf) >> 4) | (1u << 16);
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile<T>(P, t);
+      const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+      mbar_wait(&bars->tmem_empty[buf], bph ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (NACC * N_);
+      uint32_t acc_flag = 0;  // 0 only for the first K step of the tile
+      for (int s = 0; s < P.nsrc; ++s) {
+        const int k = P.ksize[s];
+        const int pk = (k - 1) / 2;
+        const int ntaps = k * k;
+        const int row_wrap = (P.PWs - (k - 1)) * (int)a_pix;  // (ky, k-1) -> (ky+1, 0)
+        for (int ch = 0; ch < kNumChunks; ++ch) {
+          const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
+          mbar_wait(&bars->a_full[aslot], aph);
+          tc_fence_after();
+          uint32_t a_lo = a_buf_lo + aslot * a_slot_step +
+                          (uint32_t)(c.off0 - pk * P.PWs - pk) * a_pix;  // tap (0,0)
+          int kx = 0;
+          for (int tap = 0; tap < ntaps; ++tap) {
+            const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
+            mbar_wait(&bars->w_full[wslot], wph);
             tc_fence_after();
-            const uint32_t abase = smem_u32(a_buf + aslot * P.a_bytes);
-            int ky = 0, kx = 0;
-            for (int tap = 0; tap < ntaps; ++tap) {
-              const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
-              mbar_wait(&bars->w_full[wslot], wph);
-              tc_fence_after();
-              const uint32_t wbase = smem_u32(w_buf + wslot * WSTAGE);
-              const int shift = c.off0 + (ky - pk) * P.PWs + (kx - pk);
+            const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
+            if (leader) {
 #pragma unroll
               for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
                 for (int k16 = 0; k16 < 2; ++k16) {
-                  const uint64_t adesc = make_a_desc<AMODE>(abase, shift + acc * 128, k16, lbo);
-                  const uint64_t bdesc =
-                      umma_smem_desc(wbase + (uint32_t)k16 * 32u, 16u, 512u, SR_LAYOUT_SW64);
-                  umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, (first && k16 == 0) ? 0u : 1u);
+                  const uint64_t adesc =
+                      ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + acc * 128 * a_pix + k16 * a_k16);
+                  const uint64_t bdesc = ((uint64_t)kHiSw64 << 32) | (uint64_t)(b_lo + k16 * 2);
+                  umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
                 }
               }
-              first = false;
               umma_commit(&bars->w_empty[wslot]);
-              ++ws;
-              if (++kx == k) { kx = 0; ++ky; }
             }
-            umma_commit(&bars->a_empty[aslot]);
-            ++ac;
+            acc_flag = 1;
+            ++ws;
+            if (++kx == k) {
+              kx = 0;
+              a_lo += row_wrap;
+            } else {
+              a_lo += a_pix;
+            }
           }
+          if (leader) umma_commit(&bars->a_empty[aslot]);
+          ++ac;
         }
-        umma_commit(&bars->tmem_full[buf]);
       }
+      if (leader) umma_commit(&bars->tmem_full[buf]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global

@@ -195,11 +195,13 @@ __global__ void patch_gather_kernel(const void* __restrict__ src, int h, int w, 
 // output coordinate Q is the LAST patch whose cropped span [S*i + c_i, S*i + P - c_i) contains Q
 // (c_0 = 0, c_i = 8), because later patches overwrite earlier ones.
 __device__ __forceinline__ int stitch_owner(int Q, int cnt, int S, int P, int crop) {
-  int i = 0;
-  if (Q >= S + crop) i = min(cnt - 1, (Q - crop) / S);
-  const int c = i == 0 ? 0 : crop;
-  if (Q < S * i + c || Q >= S * i + P - c) return -1;
-  return i;
+  // patches i >= 1: both span ends grow with i, so only the largest i whose start is <= Q can own Q
+  if (cnt > 1 && Q >= S + crop) {
+    const int i = min(cnt - 1, (Q - crop) / S);
+    if (Q < S * i + P - crop) return i;
+  }
+  // otherwise patch 0 (uncropped) if it reaches Q (matters only when step*scale < 8; never on the CLI path)
+  return Q < P ? 0 : -1;
 }
 
 __global__ void patch_stitch_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH,

@@ -55,14 +55,14 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& P, int 
 // mask and outputs is a fully coalesced 512 B (bf16) / 1 KB (fp32) warp transaction.
 __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
                                                     uint32_t t_acc, int f_base, uint8_t* stage,
-                                                    const float* s_bias, int lane) {
+                                                    const float* s_bias, int lane, bool live = true) {
   // ---- phase 1: this lane's pixel row
   const int f = f_base + lane;
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
-  const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 && xx < P.BW &&
-                     (c.seg_x0 + xx) < P.W;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.W;
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
   uint8_t* my_row = stage + lane * 256;
   const int sw = lane & 7;
@@ -371,11 +371,226 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
 
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+// =====================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster process the same tile position of two
+// different images with ONE tcgen05.mma of M = 256.  Each CTA stages its own activation strip and
+// only HALF of every weight stage (64 of the 128 couts); the tensor cores of both SMs read both
+// halves, so per-SM shared-memory operand traffic drops from 8 KB to 6 KB per MMA (128 -> 96 B/clk)
+// and L2 -> SM weight traffic halves.  The leader CTA (rank 0) owns the full-barriers and issues;
+// tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
+// =====================================================================================
+template <int NACC, int NBUF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
+                    const ConvKernelParams P) {
+  constexpr int N_ = 128;
+  constexpr int T = NACC * 128;
+  constexpr int WSTAGE = (N_ / 2) * kChunk * 2;  // this CTA's half of a weight stage
+  constexpr uint32_t TM_COLS = 512;
+  static_assert(NACC * NBUF * N_ == 512, "pair kernel uses the whole TMEM");
+  constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 256u, (uint32_t)N_);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + 2 * P.a_bytes;
+  uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
+  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + 4 * 32 * 256);
+  float* s_bias = reinterpret_cast<float*>(bars + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NS = P.num_wstages;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int per_img = P.nseg * P.tiles_per_seg;
+  const int pair_tiles = ((P.NB + 1) >> 1) * per_img;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bars->w_full[i], 1);
+      mbar_init(&bars->w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 1);
+      mbar_init(&bars->a_empty[i], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 8);  // 4 epilogue warps of each CTA arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmW0);
+    if (P.nsrc > 1) prefetch_tmap(&tmW1);
+  }
+  if (warp == 3 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    if (P.nsrc > 1) prefetch_tmap(&tmA1);
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(&bars->tmem_base, TM_COLS);
+    tmem_relinquish_pair();
+  }
+  if (threadIdx.x >= 128) {
+    for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // tile of this CTA for pair-tile index pt: image 2*j + rank (clamped; a clamped duplicate does not store)
+  auto decode = [&](int pt, bool* live) {
+    const int j = pt / per_img;
+    const int r = pt - j * per_img;
+    int n = 2 * j + (int)rank;
+    *live = n < P.NB;
+    if (n >= P.NB) n = P.NB - 1;
+    return decode_tile<T>(P, n * per_img + r);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight half-stage TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t ws = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+        for (int s = 0; s < P.nsrc; ++s) {
+          const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
+          const int ntaps = P.ksize[s] * P.ksize[s];
+          for (int st = 0; st < kNumChunks * ntaps; ++st) {
+            const uint32_t slot = ws % NS, ph = (ws / NS) & 1;
+            mbar_wait(&bars->w_empty[slot], ph ^ 1);
+            if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * WSTAGE);
+            tma_load_2d_pair(w_buf + slot * WSTAGE, tmW, mapa_shared(smem_u32(&bars->w_full[slot]), 0), 0,
+                             st * N_ + (int)rank * (N_ / 2));
+            ++ws;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------ activation strip TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t ac = 0;
+      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kChunk * 2;
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+        bool live;
+        const TileCoord c = decode(pt, &live);
+        for (int s = 0; s < P.nsrc; ++s) {
+          const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
+            mbar_wait(&bars->a_empty[slot], ph ^ 1);
+            if (is_leader) mbar_expect_tx(&bars->a_full[slot], 2 * strip_bytes);
+            tma_load_4d_pair(a_buf + slot * P.a_bytes, tmA, mapa_shared(smem_u32(&bars->a_full[slot]), 0),
+                             ch * kChunk, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
+            ++ac;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
+    if (is_leader) {
+      const bool leader = elect_one();
+      uint32_t ws = 0, ac = 0, it = 0;
+      constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
+      const uint32_t a_buf_lo = (smem_u32(a_buf) >> 4) | (1u << 16);
+      const uint32_t a_slot_step = (uint32_t)P.a_bytes >> 4;
+      const uint32_t w_buf_lo = (smem_u32(w_buf) >> 4) | (1u << 16);
+      for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+        bool live;
+        const TileCoord c = decode(pt, &live);  // off0 is identical for both CTAs of the pair
+        const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+        mbar_wait(&bars->tmem_empty[buf], bph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + buf * (NACC * N_);
+        uint32_t acc_flag = 0;
+        for (int s = 0; s < P.nsrc; ++s) {
+          const int k = P.ksize[s];
+          const int pk = (k - 1) / 2;
+          const int ntaps = k * k;
+          const int row_wrap = (P.PWs - (k - 1)) * 4;
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
+            mbar_wait(&bars->a_full[aslot], aph);
+            tc_fence_after();
+            uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
+            int kx = 0;
+            for (int tap = 0; tap < ntaps; ++tap) {
+              const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
+              mbar_wait(&bars->w_full[wslot], wph);
+              tc_fence_after();
+              const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
+              if (leader) {
+#pragma unroll
+                for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+                  for (int k16 = 0; k16 < 2; ++k16) {
+                    const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + acc * 512 + k16 * 2);
+                    const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
+                    umma_bf16_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                  }
+                }
+                umma_commit_pair(&bars->w_empty[wslot]);
+              }
+              acc_flag = 1;
+              ++ws;
+              if (++kx == k) {
+                kx = 0;
+                a_lo += row_wrap;
+              } else {
+                a_lo += 4;
+              }
+            }
+            if (leader) umma_commit_pair(&bars->a_empty[aslot]);
+            ++ac;
+          }
+        }
+        if (leader) umma_commit_pair(&bars->tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (both CTAs, own TMEM lanes = own tile)
+    const int ew = warp - 4;
+    uint32_t it = 0;
+    for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+      bool live;
+      const TileCoord c = decode(pt, &live);
+      const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+      mbar_wait(&bars->tmem_full[buf], bph);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc)
+        epilogue_staged_acc(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
+                            stage_buf + ew * (32 * 256), s_bias, lane, live);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
+    }
+  }
+
+  __syncwarp();  // lanes of the single-lane roles reconverge before the aligned cluster barrier
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TM_COLS);
   }
 }
 
@@ -407,6 +622,7 @@ struct ConvPlan {
   int n_pad;     // 128 or 16
   int amode;
   int nacc;
+  int pair;     // 1: CTA-pair (cta_group::2) kernel
   int grid;
   size_t smem_bytes;
   double flops;  // algorithmic FLOPs (2*MAC) of one run
@@ -445,12 +661,12 @@ static int make_a_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, in
   return SR_OK;
 }
 
-static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)kChunk, (cuuint64_t)nstages * n_pad};
   cuuint64_t strides[1] = {(cuuint64_t)kChunk * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)n_pad};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -518,6 +734,23 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   return SR_OK;
 }
 
+template <int NACC, int NBUF>
+static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
+  auto kern = conv_tc_pair_kernel<NACC, NBUF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBudget);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_pair_kernel)");
+    attr_set = true;
+  }
+  kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
+                                                           pl->tmW[1], pl->P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_pair_kernel launch");
+  return SR_OK;
+}
+
 }  // namespace sr
 
 using namespace sr;
@@ -544,7 +777,8 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   pl->amode = d->a_mode == 1 ? kAModeInterleave : kAModeSwizzle64;
   pl->nacc = (d->nacc == 2 && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
-  const int wstage = pl->n_pad * kChunk * 2;
+  pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
+  const int wstage = (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kChunk * 2;
   ConvKernelParams& P = pl->P;
   P.nsrc = d->nsrc;
   P.ksize[0] = d->ksize[0];
@@ -577,7 +811,8 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   for (int s = 0; s < d->nsrc; ++s) {
     int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode);
     if (rc == SR_OK)
-      rc = make_w_map(&pl->tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], pl->n_pad);
+      rc = make_w_map(&pl->tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], pl->n_pad,
+                      pl->pair ? pl->n_pad / 2 : pl->n_pad);
     if (rc != SR_OK) {
       delete pl;
       return rc;
@@ -592,7 +827,12 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  pl->grid = std::min(P.total_tiles, sms);
+  if (pl->pair) {
+    const int pair_tiles = ((P.NB + 1) / 2) * P.nseg * P.tiles_per_seg;
+    pl->grid = 2 * std::min(pair_tiles, sms / 2);
+  } else {
+    pl->grid = std::min(P.total_tiles, sms);
+  }
   pl->smem_bytes = 1024 + 2 * (size_t)P.a_bytes + (size_t)P.num_wstages * wstage + stage_bytes +
                    sizeof(ConvBarriers) + 128 * 4 + 64;
   *out = reinterpret_cast<sr_conv_plan*>(pl);
@@ -603,6 +843,7 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   if (!plan) return set_error(SR_ERR_INVALID, "sr_conv_plan_run: null plan");
   const ConvPlan* pl = reinterpret_cast<const ConvPlan*>(plan);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pl->pair) return pl->nacc == 4 ? launch_pair<4, 1>(pl, st) : launch_pair<2, 2>(pl, st);
   if (pl->n_pad == 128) {
     if (pl->amode == kAModeSwizzle64)
       return pl->nacc == 4 ? launch_variant<128, kAModeSwizzle64, 4, 1>(pl, st)

@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ("relu_mask_bf16", C.c_void_p),
         ("a_mode", C.c_int),
         ("nacc", C.c_int),
+        ("pair", C.c_int),
     ]
 
 

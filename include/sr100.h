@@ -57,6 +57,7 @@ typedef struct sr_conv_desc {
   const void* relu_mask_bf16; /* optional (backward): out = 0 where mask <= 0 */
   int a_mode;            /* 0: 64B-swizzled strip, 1: interleaved no-swizzle strip */
   int nacc;              /* 4 (default): 512 positions / tile; 2: 256 positions, double-buffered TMEM */
+  int pair;              /* 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 over two images); needs NB >= 2 */
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;

@@ -20,7 +20,7 @@ CASES = []
 
 def case(**kw):
     d = dict(NB=2, H=20, W=96, ks=(3,), cout=128, mode=0, nacc=4, res=None, relu=0, alpha=1.0, beta=0.0,
-             iters=0, check=True, outs="both")
+             iters=0, check=True, outs="both", pair=0)
     d.update(kw)
     CASES.append(d)
 
@@ -54,6 +54,24 @@ for nacc in (4, 2):
     case(name="big_k5_hr_relu_bf16" + sfx, ks=(5,), NB=8, H=384, W=384, relu=1, outs="bf16", iters=10, check=False, nacc=nacc)
     case(name="big_k5k3_hr_end_bf16" + sfx, ks=(5, 3), NB=8, H=384, W=384, res="bf16", alpha=0.1, beta=0.9, outs="bf16",
          iters=10, check=False, nacc=nacc)
+
+
+# CTA-pair (cta_group::2) kernel: correctness, then many-wave throughput
+for nacc in (4, 2):
+    sfx = "_nacc%d" % nacc
+    case(name="pair_k3" + sfx, ks=(3,), NB=2, pair=1, nacc=nacc, relu=1)
+    case(name="pair_k5_odd_nb" + sfx, ks=(5,), NB=3, pair=1, nacc=nacc)
+    case(name="pair_k5k3_res" + sfx, ks=(5, 3), NB=4, H=33, W=50, pair=1, nacc=nacc, res="f32", alpha=0.1, beta=0.9)
+    case(name="pair_k5_w384" + sfx, ks=(5,), NB=2, H=24, W=384, pair=1, nacc=nacc)
+for nacc in (4, 2):
+    sfx = "_nacc%d" % nacc
+    case(name="pbig_k5_lr_relu_bf16" + sfx, ks=(5,), NB=148, H=96, W=96, relu=1, outs="bf16", iters=10, check=False, nacc=nacc, pair=1)
+    case(name="pbig_k3_lr_relu_bf16" + sfx, ks=(3,), NB=148, H=96, W=96, relu=1, outs="bf16", iters=20, check=False, nacc=nacc, pair=1)
+    case(name="pbig_k5k3_lr_end" + sfx, ks=(5, 3), NB=148, H=96, W=96, res="f32", alpha=0.1, beta=0.9, iters=10,
+         check=False, nacc=nacc, pair=1)
+    case(name="pbig_k5_hr_relu_bf16" + sfx, ks=(5,), NB=8, H=384, W=384, relu=1, outs="bf16", iters=10, check=False, nacc=nacc, pair=1)
+    case(name="pbig_k5k3_hr_end_bf16" + sfx, ks=(5, 3), NB=8, H=384, W=384, res="bf16", alpha=0.1, beta=0.9, outs="bf16",
+         iters=10, check=False, nacc=nacc, pair=1)
 
 
 def run_case(idx):
@@ -95,7 +113,7 @@ def run_case(idx):
     d.out_bf16 = out_bf16.data_ptr()
     if cs["outs"] == "both":
         d.out_f32 = out_f32.data_ptr()
-    d.a_mode, d.nacc = cs["mode"], cs["nacc"]
+    d.a_mode, d.nacc, d.pair = cs["mode"], cs["nacc"], cs["pair"]
     plan = C.c_void_p()
     L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))
     info = L.ConvPlanInfo()

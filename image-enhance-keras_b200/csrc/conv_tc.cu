@@ -30,6 +30,17 @@ struct __align__(8) ConvBarriers {
   uint32_t pad;
 };
 
+// position in an mbarrier ring: slot index + phase parity (avoids a runtime modulo per stage)
+struct Ring {
+  uint32_t slot, phase, n;
+  __device__ __forceinline__ void advance() {
+    if (++slot == n) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
 struct TileCoord {
   int n, seg_x0, f0, r_lo, off0;
 };
@@ -77,9 +88,7 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = q * 8 + e * 2;
-        const float a = P.alpha * (__uint_as_float(v[j]) + s_bias[cb * 32 + j]);
-        const float b = P.alpha * (__uint_as_float(v[j + 1]) + s_bias[cb * 32 + j + 1]);
-        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
         w[e] = *reinterpret_cast<const uint32_t*>(&h);
       }
       *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -88,6 +97,9 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
   __syncwarp();
   // ---- phase 2: 16 lanes per pixel, 2 pixels per warp instruction
   const int half = lane >> 4, q = lane & 15;
+  float bs[8];  // alpha * bias of this lane's 8 channels
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = P.alpha * s_bias[q * 8 + e];
 #pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     const int r = 2 * i + half;
@@ -98,8 +110,8 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
     float o[8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      o[2 * e] = __uint_as_float(w[e] << 16);
-      o[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+      o[2 * e] = fmaf(P.alpha, __uint_as_float(w[e] << 16), bs[2 * e]);
+      o[2 * e + 1] = fmaf(P.alpha, __uint_as_float(w[e] & 0xFFFF0000u), bs[2 * e + 1]);
     }
     const size_t off = (size_t)pix * 128 + q * 8;
     if (P.res_f32) {
@@ -167,8 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 128u, (uint32_t)N_);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
   uint8_t* a_buf = smem;
   uint8_t* w_buf = smem + 2 * P.a_bytes;
   constexpr int STAGE_BYTES = (N_ == 128) ? 4 * 32 * 256 : 0;  // epilogue staging: 32 rows x 256 B per warp
@@ -218,17 +229,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------ weight-stage TMA producer
     if (lane == 0) {
-      uint32_t ws = 0;
+      Ring wr{0u, 0u, (uint32_t)NS};
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
           for (int st = 0; st < kNumChunks * ntaps; ++st) {
-            const uint32_t slot = ws % NS, ph = (ws / NS) & 1;
+            const uint32_t slot = wr.slot, ph = wr.phase;
             mbar_wait(&bars->w_empty[slot], ph ^ 1);
             mbar_expect_tx(&bars->w_full[slot], WSTAGE);
             tma_load_2d(w_buf + slot * WSTAGE, tmW, &bars->w_full[slot], 0, st * N_);
-            ++ws;
+            wr.advance();
           }
         }
       }
@@ -265,7 +276,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // Descriptors are {lo, hi} 32-bit words: hi is constant, lo = (smem address >> 4) | LBO field, so a tap
     // shift, an accumulator step (128 rows) and a K step are plain 32-bit adds.
     const bool leader = elect_one();
-    uint32_t ws = 0, ac = 0, it = 0;
+    uint32_t ac = 0, it = 0;
+      Ring wr{0u, 0u, (uint32_t)NS};
     const uint32_t lbo16 = (uint32_t)P.NR * P.PWs;  // interleave mode: bytes between K core matrices, >> 4
     constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
     constexpr uint32_t kHiNone = (128u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_NONE << 29);
@@ -296,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                           (uint32_t)(c.off0 - pk * P.PWs - pk) * a_pix;  // tap (0,0)
           int kx = 0;
           for (int tap = 0; tap < ntaps; ++tap) {
-            const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
+            const uint32_t wslot = wr.slot, wph = wr.phase;
             mbar_wait(&bars->w_full[wslot], wph);
             tc_fence_after();
             const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
@@ -314,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               umma_commit(&bars->w_empty[wslot]);
             }
             acc_flag = 1;
-            ++ws;
+            wr.advance();
             if (++kx == k) {
               kx = 0;
               a_lo += row_wrap;
@@ -401,8 +413,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 256u, (uint32_t)N_);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
   uint8_t* a_buf = smem;
   uint8_t* w_buf = smem + 2 * P.a_bytes;
   uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
@@ -466,18 +477,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------ weight half-stage TMA producer (both CTAs)
     if (lane == 0) {
-      uint32_t ws = 0;
+      Ring wr{0u, 0u, (uint32_t)NS};
       for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
           for (int st = 0; st < kNumChunks * ntaps; ++st) {
-            const uint32_t slot = ws % NS, ph = (ws / NS) & 1;
+            const uint32_t slot = wr.slot, ph = wr.phase;
             mbar_wait(&bars->w_empty[slot], ph ^ 1);
             if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * WSTAGE);
             tma_load_2d_pair(w_buf + slot * WSTAGE, tmW, mapa_shared(smem_u32(&bars->w_full[slot]), 0), 0,
                              st * N_ + (int)rank * (N_ / 2));
-            ++ws;
+            wr.advance();
           }
         }
       }
@@ -507,7 +518,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
     if (is_leader) {
       const bool leader = elect_one();
-      uint32_t ws = 0, ac = 0, it = 0;
+      uint32_t ac = 0, it = 0;
+      Ring wr{0u, 0u, (uint32_t)NS};
       constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
       const uint32_t a_buf_lo = (smem_u32(a_buf) >> 4) | (1u << 16);
       const uint32_t a_slot_step = (uint32_t)P.a_bytes >> 4;
@@ -532,7 +544,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
             int kx = 0;
             for (int tap = 0; tap < ntaps; ++tap) {
-              const uint32_t wslot = ws % NS, wph = (ws / NS) & 1;
+              const uint32_t wslot = wr.slot, wph = wr.phase;
               mbar_wait(&bars->w_full[wslot], wph);
               tc_fence_after();
               const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
@@ -549,7 +561,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 umma_commit_pair(&bars->w_empty[wslot]);
               }
               acc_flag = 1;
-              ++ws;
+              wr.advance();
               if (++kx == k) {
                 kx = 0;
                 a_lo += row_wrap;

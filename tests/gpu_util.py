@@ -11,7 +11,7 @@ def bf16_round(a):
 
 
 def run_tc_conv(lib, xs, ws, bias, relu=0, alpha=1.0, beta=0.0, res=None, res_dtype="f32", cout=128, a_mode=0,
-                nacc=4):
+                nacc=4, pair=0):
     """xs: list of float32 NHWC arrays (bf16-representable), ws: list of HWIO float32.  Returns (out_f32, out_bf16)."""
     from sr100 import _lib as L
     dev = "cuda"
@@ -42,7 +42,7 @@ def run_tc_conv(lib, xs, ws, bias, relu=0, alpha=1.0, beta=0.0, res=None, res_dt
     of = torch.full((NB, H, W, cout), float("nan"), device=dev)
     ob = torch.zeros(NB, H, W, cout, device=dev, dtype=torch.bfloat16)
     d.out_f32, d.out_bf16 = of.data_ptr(), ob.data_ptr()
-    d.a_mode, d.nacc = a_mode, nacc
+    d.a_mode, d.nacc, d.pair = a_mode, nacc, pair
     plan = C.c_void_p()
     L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))
     L.check(lib.sr_conv_plan_run(plan, L.stream_ptr()))

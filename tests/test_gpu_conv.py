@@ -29,9 +29,9 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("a_mode,nacc", [(0, 4), (1, 4), (0, 2)])
+@pytest.mark.parametrize("a_mode,nacc,pair", [(0, 4, 0), (1, 4, 0), (0, 2, 0), (0, 4, 1), (0, 2, 1)])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_conv_matches_oracle(lib, case, a_mode, nacc):
+def test_conv_matches_oracle(lib, case, a_mode, nacc, pair):
     name, ks, NB, H, W, cout, relu, alpha, beta, res_kind = case
     rng = np.random.default_rng(__import__("zlib").crc32(name.encode()))
     xs = [_rand(rng, (NB, H, W, 128)) for _ in ks]
@@ -42,15 +42,15 @@ def test_conv_matches_oracle(lib, case, a_mode, nacc):
         res = rng.standard_normal((NB, H, W, cout)).astype(np.float32)
         if res_kind == "bf16":
             res = bf16_round(res)
-    got32, got16 = run_tc_conv(lib, xs, ws, bias, relu, alpha, beta, res, res_kind or "f32", cout, a_mode, nacc)
+    got32, got16 = run_tc_conv(lib, xs, ws, bias, relu, alpha, beta, res, res_kind or "f32", cout, a_mode, nacc, pair)
     want = oracle_conv(xs, ws, bias, relu, alpha, beta, res)
     assert not np.isnan(got32).any(), "some output pixels were never written"
-    # identical operands, fp32 accumulation on both sides.  For cout == 128 the kernel stages the branch value
-    # alpha*(acc+bias) in bf16 before the residual add, so the fp32 output may differ from the oracle by half a
-    # bf16 ulp of the branch value (plus summation-order noise); the 3-channel tail stays in fp32 throughout.
-    branch = np.abs(oracle_conv(xs, ws, bias, 0, alpha, 0.0, None))
-    half_ulp = np.where(branch > 0, 2.0 ** (np.floor(np.log2(np.maximum(branch, 1e-30))) - 8), 0.0)
-    tol = 2e-4 + (half_ulp * 1.01 if cout == 128 else 0.0)
+    # identical operands, fp32 accumulation on both sides.  For cout == 128 the kernel stages the raw accumulator
+    # in bf16 before bias / alpha / residual, so the fp32 output may differ from the oracle by |alpha| * half a
+    # bf16 ulp of the accumulator (plus summation-order noise); the 3-channel tail stays in fp32 throughout.
+    raw = np.abs(oracle_conv(xs, ws, None, 0, 1.0, 0.0, None))
+    half_ulp = np.where(raw > 0, 2.0 ** (np.floor(np.log2(np.maximum(raw, 1e-30))) - 8), 0.0)
+    tol = 2e-4 + (abs(alpha) * half_ulp * 1.01 if cout == 128 else 0.0)
     assert (np.abs(got32 - want) <= tol).all(), float(np.abs(got32 - want).max())
     assert np.abs(got16 - want).max() < 2e-2 * max(1.0, np.abs(want).max())
 

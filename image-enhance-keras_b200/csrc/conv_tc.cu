@@ -18,6 +18,7 @@ namespace sr {
 namespace {
 
 constexpr int kMaxWStages = 16;
+constexpr int kTapsPerStage = 2;  // taps per weight stage: halves the barrier round trips per MMA
 
 struct __align__(8) ConvBarriers {
   uint64_t w_full[kMaxWStages];
@@ -168,7 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const ConvKernelParams P) {
   constexpr int T = NACC * 128;
-  constexpr int WSTAGE = N_ * kChunk * 2;
+  constexpr int WTAP = N_ * kChunk * 2;      // one tap x 32 channels x N couts
+  constexpr int WSTAGE = kTapsPerStage * WTAP;  // a weight stage carries two consecutive taps
   constexpr uint32_t TM_COLS_RAW = NACC * NBUF * N_;
   constexpr uint32_t TM_COLS = TM_COLS_RAW <= 32    ? 32
                                : TM_COLS_RAW <= 64  ? 64
@@ -234,12 +236,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int st = 0; st < kNumChunks * ntaps; ++st) {
-            const uint32_t slot = wr.slot, ph = wr.phase;
-            mbar_wait(&bars->w_empty[slot], ph ^ 1);
-            mbar_expect_tx(&bars->w_full[slot], WSTAGE);
-            tma_load_2d(w_buf + slot * WSTAGE, tmW, &bars->w_full[slot], 0, st * N_);
-            wr.advance();
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
+              // one box = 2 taps (an odd last tap drags in the next 128 rows, unused; OOB rows are zero-filled)
+              const uint32_t slot = wr.slot, ph = wr.phase;
+              mbar_wait(&bars->w_empty[slot], ph ^ 1);
+              mbar_expect_tx(&bars->w_full[slot], WSTAGE);
+              tma_load_2d(w_buf + slot * WSTAGE, tmW, &bars->w_full[slot], 0, (ch * ntaps + tap) * N_);
+              wr.advance();
+            }
           }
         }
       }
@@ -275,9 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // so ptxas keeps them in uniform registers); only the elected lane issues tcgen05.mma / commit.
     // Descriptors are {lo, hi} 32-bit words: hi is constant, lo = (smem address >> 4) | LBO field, so a tap
     // shift, an accumulator step (128 rows) and a K step are plain 32-bit adds.
-    const bool leader = elect_one();
+    const uint32_t leader = elect_one() ? 1u : 0u;
     uint32_t ac = 0, it = 0;
-      Ring wr{0u, 0u, (uint32_t)NS};
+    Ring wr{0u, 0u, (uint32_t)NS};
     const uint32_t lbo16 = (uint32_t)P.NR * P.PWs;  // interleave mode: bytes between K core matrices, >> 4
     constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
     constexpr uint32_t kHiNone = (128u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_NONE << 29);
@@ -307,12 +312,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           uint32_t a_lo = a_buf_lo + aslot * a_slot_step +
                           (uint32_t)(c.off0 - pk * P.PWs - pk) * a_pix;  // tap (0,0)
           int kx = 0;
-          for (int tap = 0; tap < ntaps; ++tap) {
+          for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
             const uint32_t wslot = wr.slot, wph = wr.phase;
             mbar_wait(&bars->w_full[wslot], wph);
             tc_fence_after();
-            const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
-            if (leader) {
+            uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
+#pragma unroll
+            for (int j = 0; j < kTapsPerStage; ++j) {
+              const uint32_t issue = (tap + j < ntaps) ? leader : 0u;
 #pragma unroll
               for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
@@ -320,25 +327,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   const uint64_t adesc =
                       ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + acc * 128 * a_pix + k16 * a_k16);
                   const uint64_t bdesc = ((uint64_t)kHiSw64 << 32) | (uint64_t)(b_lo + k16 * 2);
-                  umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                  umma_bf16_if(issue, d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
                 }
               }
-              umma_commit(&bars->w_empty[wslot]);
+              acc_flag = 1;
+              b_lo += (uint32_t)(WTAP >> 4);
+              if (++kx == k) {
+                kx = 0;
+                a_lo += row_wrap;
+              } else {
+                a_lo += a_pix;
+              }
             }
-            acc_flag = 1;
+            umma_commit_if(leader, &bars->w_empty[wslot]);
             wr.advance();
-            if (++kx == k) {
-              kx = 0;
-              a_lo += row_wrap;
-            } else {
-              a_lo += a_pix;
-            }
           }
-          if (leader) umma_commit(&bars->a_empty[aslot]);
+          umma_commit_if(leader, &bars->a_empty[aslot]);
           ++ac;
         }
       }
-      if (leader) umma_commit(&bars->tmem_full[buf]);
+      umma_commit_if(leader, &bars->tmem_full[buf]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
@@ -407,7 +415,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const ConvKernelParams P) {
   constexpr int N_ = 128;
   constexpr int T = NACC * 128;
-  constexpr int WSTAGE = (N_ / 2) * kChunk * 2;  // this CTA's half of a weight stage
+  constexpr int WTAP = (N_ / 2) * kChunk * 2;   // this CTA's half (64 couts) of one tap x 32 channels
+  constexpr int WSTAGE = kTapsPerStage * WTAP;  // a weight stage carries two consecutive taps
   constexpr uint32_t TM_COLS = 512;
   static_assert(NACC * NBUF * N_ == 512, "pair kernel uses the whole TMEM");
   constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 256u, (uint32_t)N_);
@@ -482,13 +491,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int st = 0; st < kNumChunks * ntaps; ++st) {
-            const uint32_t slot = wr.slot, ph = wr.phase;
-            mbar_wait(&bars->w_empty[slot], ph ^ 1);
-            if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * WSTAGE);
-            tma_load_2d_pair(w_buf + slot * WSTAGE, tmW, mapa_shared(smem_u32(&bars->w_full[slot]), 0), 0,
-                             st * N_ + (int)rank * (N_ / 2));
-            wr.advance();
+          for (int ch = 0; ch < kNumChunks; ++ch) {
+            for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
+              const uint32_t slot = wr.slot, ph = wr.phase;
+              mbar_wait(&bars->w_empty[slot], ph ^ 1);
+              if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * WSTAGE);
+              const uint32_t bar = mapa_shared(smem_u32(&bars->w_full[slot]), 0);
+#pragma unroll
+              for (int j = 0; j < kTapsPerStage; ++j)  // always both boxes: constant byte count per stage
+                tma_load_2d_pair(w_buf + slot * WSTAGE + j * WTAP, tmW, bar, 0,
+                                 (ch * ntaps + tap + j) * N_ + (int)rank * (N_ / 2));
+              wr.advance();
+            }
           }
         }
       }
@@ -517,7 +531,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
     if (is_leader) {
-      const bool leader = elect_one();
+      const uint32_t leader = elect_one() ? 1u : 0u;
       uint32_t ac = 0, it = 0;
       Ring wr{0u, 0u, (uint32_t)NS};
       constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
@@ -543,37 +557,40 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             tc_fence_after();
             uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
             int kx = 0;
-            for (int tap = 0; tap < ntaps; ++tap) {
+            for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t wslot = wr.slot, wph = wr.phase;
               mbar_wait(&bars->w_full[wslot], wph);
               tc_fence_after();
-              const uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
-              if (leader) {
+              uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
+#pragma unroll
+              for (int j = 0; j < kTapsPerStage; ++j) {
+                const uint32_t issue = (tap + j < ntaps) ? leader : 0u;
 #pragma unroll
                 for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
                   for (int k16 = 0; k16 < 2; ++k16) {
                     const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + acc * 512 + k16 * 2);
                     const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
-                    umma_bf16_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    umma_bf16_pair_if(issue, d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
                   }
                 }
-                umma_commit_pair(&bars->w_empty[wslot]);
+                acc_flag = 1;
+                b_lo += (uint32_t)(WTAP >> 4);
+                if (++kx == k) {
+                  kx = 0;
+                  a_lo += row_wrap;
+                } else {
+                  a_lo += 4;
+                }
               }
-              acc_flag = 1;
+              umma_commit_pair_if(leader, &bars->w_empty[wslot]);
               wr.advance();
-              if (++kx == k) {
-                kx = 0;
-                a_lo += row_wrap;
-              } else {
-                a_lo += 4;
-              }
             }
-            if (leader) umma_commit_pair(&bars->a_empty[aslot]);
+            umma_commit_pair_if(leader, &bars->a_empty[aslot]);
             ++ac;
           }
         }
-        if (leader) umma_commit_pair(&bars->tmem_full[buf]);
+        umma_commit_pair_if(leader, &bars->tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -707,7 +724,7 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
     const size_t a_bytes = ((size_t)NR * PWs * kChunk * 2 + 1023) & ~(size_t)1023;
     const size_t fixed =
         2 * a_bytes + 1024 /*align slack*/ + stage_bytes + sizeof(ConvBarriers) + 128 * 4 + 64;
-    if (fixed + 5 * (size_t)wstage > kSmemBudget) continue;  // >= 5 weight stages in flight
+    if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;  // >= 3 two-tap weight stages in flight
     const int f_len = (H - 1) * PWs + BW;
     const int tps = (f_len + T - 1) / T;
     const double eff = (double)H * W / ((double)nseg * tps * T);
@@ -790,7 +807,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   pl->nacc = (d->nacc == 2 && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
   pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
-  const int wstage = (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kChunk * 2;
+  const int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kChunk * 2;
   ConvKernelParams& P = pl->P;
   P.nsrc = d->nsrc;
   P.ksize[0] = d->ksize[0];
@@ -824,7 +841,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
     int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode);
     if (rc == SR_OK)
       rc = make_w_map(&pl->tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], pl->n_pad,
-                      pl->pair ? pl->n_pad / 2 : pl->n_pad);
+                      pl->pair ? pl->n_pad / 2 : kTapsPerStage * pl->n_pad);
     if (rc != SR_OK) {
       delete pl;
       return rc;

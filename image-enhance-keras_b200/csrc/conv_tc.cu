@@ -280,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // so ptxas keeps them in uniform registers); only the elected lane issues tcgen05.mma / commit.
     // Descriptors are {lo, hi} 32-bit words: hi is constant, lo = (smem address >> 4) | LBO field, so a tap
     // shift, an accumulator step (128 rows) and a K step are plain 32-bit adds.
-    const uint32_t leader = elect_one() ? 1u : 0u;
+    const bool leader = elect_one();
     uint32_t ac = 0, it = 0;
     Ring wr{0u, 0u, (uint32_t)NS};
     const uint32_t lbo16 = (uint32_t)P.NR * P.PWs;  // interleave mode: bytes between K core matrices, >> 4
@@ -319,15 +319,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
 #pragma unroll
             for (int j = 0; j < kTapsPerStage; ++j) {
-              const uint32_t issue = (tap + j < ntaps) ? leader : 0u;
+              if (leader && tap + j < ntaps) {
 #pragma unroll
-              for (int acc = 0; acc < NACC; ++acc) {
+                for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16) {
-                  const uint64_t adesc =
-                      ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + acc * 128 * a_pix + k16 * a_k16);
-                  const uint64_t bdesc = ((uint64_t)kHiSw64 << 32) | (uint64_t)(b_lo + k16 * 2);
-                  umma_bf16_if(issue, d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                  for (int k16 = 0; k16 < 2; ++k16) {
+                    const uint64_t adesc =
+                        ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + acc * 128 * a_pix + k16 * a_k16);
+                    const uint64_t bdesc = ((uint64_t)kHiSw64 << 32) | (uint64_t)(b_lo + k16 * 2);
+                    umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                  }
                 }
               }
               acc_flag = 1;
@@ -339,14 +340,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 a_lo += a_pix;
               }
             }
-            umma_commit_if(leader, &bars->w_empty[wslot]);
+            if (leader) umma_commit(&bars->w_empty[wslot]);
             wr.advance();
           }
-          umma_commit_if(leader, &bars->a_empty[aslot]);
+          if (leader) umma_commit(&bars->a_empty[aslot]);
           ++ac;
         }
       }
-      umma_commit_if(leader, &bars->tmem_full[buf]);
+      if (leader) umma_commit(&bars->tmem_full[buf]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
@@ -531,7 +532,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
     if (is_leader) {
-      const uint32_t leader = elect_one() ? 1u : 0u;
+      const bool leader = elect_one();
       uint32_t ac = 0, it = 0;
       Ring wr{0u, 0u, (uint32_t)NS};
       constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
@@ -564,14 +565,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
 #pragma unroll
               for (int j = 0; j < kTapsPerStage; ++j) {
-                const uint32_t issue = (tap + j < ntaps) ? leader : 0u;
+                if (leader && tap + j < ntaps) {
 #pragma unroll
-                for (int acc = 0; acc < NACC; ++acc) {
+                  for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
-                  for (int k16 = 0; k16 < 2; ++k16) {
-                    const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + acc * 512 + k16 * 2);
-                    const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
-                    umma_bf16_pair_if(issue, d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    for (int k16 = 0; k16 < 2; ++k16) {
+                      const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + acc * 512 + k16 * 2);
+                      const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
+                      umma_bf16_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    }
                   }
                 }
                 acc_flag = 1;
@@ -583,14 +585,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                   a_lo += 4;
                 }
               }
-              umma_commit_pair_if(leader, &bars->w_empty[wslot]);
+              if (leader) umma_commit_pair(&bars->w_empty[wslot]);
               wr.advance();
             }
-            umma_commit_pair_if(leader, &bars->a_empty[aslot]);
+            if (leader) umma_commit_pair(&bars->a_empty[aslot]);
             ++ac;
           }
         }
-        umma_commit_pair_if(leader, &bars->tmem_full[buf]);
+        if (leader) umma_commit_pair(&bars->tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {

@@ -121,7 +121,7 @@ class _Graph:
             d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
             d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
             d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
-            d.a_mode, d.nacc = eng.a_mode, eng.nacc
+            d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
             p = _Plan(lib, d)
             self.conv_flops += p.flops
             self.steps.append(p.run)
@@ -170,13 +170,14 @@ class _Graph:
 class Engine:
     """Device-resident DifvdsrDouble weights + cached per-shape graphs."""
 
-    def __init__(self, weights=None, device=None, stream="lr32", a_mode=0, nacc=4, max_pixels=192 * 96 * 96):
+    def __init__(self, weights=None, device=None, stream="lr32", a_mode=0, nacc=2, pair=1,
+                 max_pixels=192 * 96 * 96):
         self.lib = L.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         assert stream in ("bf16", "lr32", "fp32")
         self.stream_lr_fp32 = stream in ("lr32", "fp32")
         self.stream_hr_fp32 = stream == "fp32"
-        self.a_mode, self.nacc = a_mode, nacc
+        self.a_mode, self.nacc, self.pair = a_mode, nacc, pair
         self.max_pixels = max_pixels  # LR pixels per sub-batch (HR activations are 16x this)
         self.specs = layer_specs()
         self.ksize = {n: k for n, k, _, _ in self.specs}

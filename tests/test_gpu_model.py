@@ -72,10 +72,11 @@ def test_a_modes_agree(weights):
     from sr100.engine import Engine
     rng = np.random.default_rng(12)
     x = torch.from_numpy(_smooth_images(rng, 2, 24, 24)).cuda()
-    y0 = Engine(weights, a_mode=0).forward_device(x).cpu().numpy()
-    y1 = Engine(weights, a_mode=1).forward_device(x).cpu().numpy()
-    y2 = Engine(weights, a_mode=0, nacc=2).forward_device(x).cpu().numpy()
-    assert np.abs(y0 - y1).max() < 1e-5 and np.abs(y0 - y2).max() < 1e-5
+    y0 = Engine(weights, a_mode=0, nacc=4, pair=0).forward_device(x).cpu().numpy()
+    y1 = Engine(weights, a_mode=1, nacc=4, pair=0).forward_device(x).cpu().numpy()
+    y2 = Engine(weights, a_mode=0, nacc=2, pair=0).forward_device(x).cpu().numpy()
+    y3 = Engine(weights, a_mode=0, nacc=2, pair=1).forward_device(x).cpu().numpy()
+    assert np.abs(y0 - y1).max() < 1e-5 and np.abs(y0 - y2).max() < 1e-5 and np.abs(y0 - y3).max() < 1e-5
 
 
 def test_sub_batching_is_invisible(weights):

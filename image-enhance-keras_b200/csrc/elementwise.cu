@@ -268,9 +268,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int ntaps, i
     const int chunk = (int)(q / ntaps);
     const int k_in = chunk * 32 + c;  // reduction (input-channel) index of the packed GEMM
     float v = 0.f;
-    if (n < cout) {
-      if (!transpose_flip) v = hwio[((size_t)tap * 128 + k_in) * cout + n];
-      else v = hwio[((size_t)(ntaps - 1 - tap) * 128 + n) * cout + k_in];  // W'[t][co][ci] = W[T-1-t][ci][co]
+    if (!transpose_flip) {
+      if (n < cout) v = hwio[((size_t)tap * 128 + k_in) * cout + n];
+    } else if (k_in < cout) {
+      // input-gradient weights W'[t][n = ci][k = co] = W[T-1-t][ci][co]; couts beyond `cout` are zero rows of K
+      v = hwio[((size_t)(ntaps - 1 - tap) * 128 + n) * cout + k_in];
     }
     dst[idx] = __float2bfloat16_rn(v);
   }
@@ -499,8 +501,7 @@ extern "C" int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int 
                                     void* dst, void* stream) {
   if (!hwio || !dst) return set_error(SR_ERR_INVALID, "sr_pack_conv_weights: null pointer");
   if (!(cout == 128 || (cout >= 1 && cout <= 16))) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: cout must be 128 or <= 16");
-  if (transpose_flip && cout != 128) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: transpose needs cout == 128");
-  const int n_pad = cout == 128 ? 128 : 16;
+  const int n_pad = (cout == 128 || transpose_flip) ? 128 : 16;  // the input-gradient conv always has 128 outputs
   const size_t total = (size_t)4 * ksize * ksize * n_pad * 32;
   pack_weights_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
       hwio, ksize * ksize, cout, n_pad, transpose_flip, reinterpret_cast<__nv_bfloat16*>(dst));

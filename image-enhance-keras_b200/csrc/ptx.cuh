@@ -63,7 +63,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (global_timer_ns() - t0 > SR_MBAR_TIMEOUT_NS) {

@@ -1,0 +1,144 @@
+// Bandwidth-bound pieces of the training step (models.py:131-157 fit; compile(loss='mse', Adam) models.py:1212-1213)
+// that sit around the tensor-core dgrad / wgrad kernels: loss gradient at the tail, bias gradients (column
+// sums), first-layer (1x1, 3->128) weight gradient.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "internal.h"
+
+namespace sr {
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// loss_sum += sum (pred-target)^2 ; g[pix][0..C) = 2*(pred-target)/n_total where pred > 0 (the ReLU of the last
+// Conv2D, models.py:1199), written as bf16 rows of 128 channels (channels >= C are zero) = the operand layout of
+// the dgrad / wgrad kernels.  16 threads per pixel, one 16-byte store each.
+__global__ void mse_tail_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                     size_t npix, int C, float inv_total2, uint4* __restrict__ g128,
+                                     double* __restrict__ loss_sum) {
+  double local = 0.0;
+  const size_t total = npix * 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i >> 4;
+    const int q = (int)(i & 15);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (q * 8 < C) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        v[e] = 0.f;
+        if (c < C) {
+          const float p = pred[pix * C + c];
+          const float d = p - target[pix * C + c];
+          local += (double)d * (double)d;
+          v[e] = p > 0.f ? d * inv_total2 : 0.f;
+        }
+      }
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+      o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+    g128[i] = o;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double sm[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = local;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && loss_sum) atomicAdd(loss_sum, v);
+  }
+}
+
+// out[c] += scale * sum_pix g[pix][c], g bf16 [npix][128].  16 threads per pixel row (8 channels each), 16 rows
+// per block pass; block-level shared-memory reduction, one fp32 atomic per channel per block.
+__global__ void colsum_bf16_kernel(const uint4* __restrict__ g, size_t npix, float scale, float* __restrict__ out) {
+  const int q = threadIdx.x & 15, r = threadIdx.x >> 4;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (size_t pix = (size_t)blockIdx.x * 16 + r; pix < npix; pix += (size_t)gridDim.x * 16) {
+    const uint4 v = g[pix * 16 + q];
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x);
+    acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z);
+    acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+  }
+  __shared__ float sm[16][129];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[r][q * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += sm[i][threadIdx.x];
+    atomicAdd(out + threadIdx.x, scale * s);
+  }
+}
+
+// First layer backward (Convolution2D(128,(1,1),relu,name='level1'), models.py:1177):
+//   g0 = g * (act > 0);  dW[c3][co] += sum_pix x[pix][c3] * g0[pix][co];  db[co] += sum_pix g0[pix][co].
+// One thread per output channel, blocks stride over pixels.
+__global__ void head1x1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ act,
+                                   const float* __restrict__ g_f32, const __nv_bfloat16* __restrict__ g_bf16,
+                                   size_t npix, float* __restrict__ dw, float* __restrict__ db) {
+  const int co = threadIdx.x;  // 128 threads
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+  for (size_t pix = blockIdx.x; pix < npix; pix += gridDim.x) {
+    const size_t o = pix * 128 + co;
+    float gv = g_f32 ? g_f32[o] : __bfloat162float(g_bf16[o]);
+    if (!(__bfloat162float(act[o]) > 0.f)) gv = 0.f;
+    const float x0 = x[pix * 3], x1 = x[pix * 3 + 1], x2 = x[pix * 3 + 2];
+    a0 = fmaf(x0, gv, a0);
+    a1 = fmaf(x1, gv, a1);
+    a2 = fmaf(x2, gv, a2);
+    ab += gv;
+  }
+  atomicAdd(dw + co, a0);
+  atomicAdd(dw + 128 + co, a1);
+  atomicAdd(dw + 256 + co, a2);
+  atomicAdd(db + co, ab);
+}
+
+}  // namespace
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_mse_tail_grad(const float* pred, const float* target, size_t npix, int channels,
+                                size_t n_total, void* g128_bf16, double* loss_sum, void* stream) {
+  if (!pred || !target || !g128_bf16) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad: null pointer");
+  if (channels < 1 || channels > 128) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad: channels must be 1..128");
+  if (npix == 0) return SR_OK;
+  const float inv2 = (float)(2.0 / (double)n_total);
+  mse_tail_grad_kernel<<<grid_for(npix * 16, kBlock, 148 * 16), kBlock, 0, as_stream(stream)>>>(
+      pred, target, npix, channels, inv2, reinterpret_cast<uint4*>(g128_bf16), loss_sum);
+  return check_launch("mse_tail_grad_kernel");
+}
+
+extern "C" int sr_colsum_bf16(const void* g_bf16, size_t npix, float scale, float* out, void* stream) {
+  if (!g_bf16 || !out) return set_error(SR_ERR_INVALID, "sr_colsum_bf16: null pointer");
+  if (npix == 0) return SR_OK;
+  colsum_bf16_kernel<<<grid_for(npix, 16, 148 * 8), kBlock, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(g_bf16), npix, scale, out);
+  return check_launch("colsum_bf16_kernel");
+}
+
+extern "C" int sr_head1x1_bwd(const float* x, const void* act_bf16, const float* g_f32, const void* g_bf16,
+                              size_t npix, float* dw, float* db, void* stream) {
+  if (!x || !act_bf16 || (!g_f32 && !g_bf16) || !dw || !db)
+    return set_error(SR_ERR_INVALID, "sr_head1x1_bwd: null pointer");
+  if (npix == 0) return SR_OK;
+  head1x1_bwd_kernel<<<grid_for(npix, 64, 148 * 8), 128, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(act_bf16), g_f32, reinterpret_cast<const __nv_bfloat16*>(g_bf16),
+      npix, dw, db);
+  return check_launch("head1x1_bwd_kernel");
+}

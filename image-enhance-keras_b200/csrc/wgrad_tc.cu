@@ -1,0 +1,496 @@
+// tcgen05 filter-gradient (wgrad) kernel for the 128->128 convolutions of the DifvdsrDouble stack.
+// Reference semantics: the gradient Keras/TensorFlow computes for Conv2D(padding='same') kernels during
+// fit (models.py:131-157 with compile(mse, Adam) models.py:1212-1213; layers models.py:1231-1270):
+//     dW[ky][kx][ci][co] = scale * sum_{n,y,x} X[n, y+ky-p, x+kx-p, ci] * G[n, y, x, co]      (zero outside)
+//
+// Formulation: per filter tap a GEMM  D_tap[ci][co] = sum_pixels X_shift[pixel][ci] * G[pixel][co]
+// with M = ci = 128, N = co = 128, K = pixels.  Both operands are the NHWC tensors themselves, i.e. the
+// reduction index (pixel) is the SLOW index in memory: they are fed to the tensor cores MN-major
+// (UMMA descriptor a_major = b_major = 1) from TMA 128B-swizzled boxes of [pixels][64 channels].
+//   * a CTA owns a tap group (<= 4 taps = 4 x 128 TMEM columns, fp32) for its whole lifetime and
+//     accumulates over all the (image, column segment, row block) units it is assigned: split-K over
+//     CTAs, one partial per CTA, summed deterministically by wgrad_reduce_kernel;
+//   * the input rows live in a shared-memory ring: every row (with its +-p halo columns, zero-filled by
+//     TMA = SAME padding) is loaded once per unit and reused by all taps of the group; a tap (ky,kx) is
+//     the ring row y+ky-p read at a start address shifted by kx pixels (128 B each);
+//   * G rows stream through their own ring; out-of-range columns of the last segment are zero-filled by
+//     TMA and so contribute nothing.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sr {
+
+namespace {
+
+constexpr int kWgThreads = 256;  // warp0: TMA, warp1: MMA, warp2: TMEM alloc, warps4-7: final TMEM drain
+constexpr int kMaxGroups = 8;
+constexpr int kMaxRing = 12;
+constexpr int kMaxBSlots = 6;
+constexpr int kAccFloats = 128 * 128;
+
+struct WgradParams {
+  int k, p, NB, H, W;
+  int BW, nseg, PWs;   // segment width (multiple of 16), segments per row, ring row pitch (multiple of 8)
+  int RB, nrb;         // rows per unit, row blocks per image column
+  int nring, nbslots;
+  int ngroups;
+  int g_tap0[kMaxGroups], g_ntaps[kMaxGroups], g_cta0[kMaxGroups], g_ncta[kMaxGroups];
+  float* partial;      // [grid][4][128][128]
+};
+
+struct __align__(8) WgradBarriers {
+  uint64_t a_full[kMaxRing], a_empty[kMaxRing];
+  uint64_t b_full[kMaxBSlots], b_empty[kMaxBSlots];
+  uint64_t acc_full;
+  uint32_t tmem_base, pad;
+};
+
+//   [4,6) c format f32, [7,10) a bf16, [10,13) b bf16, [15] a MN-major, [16] b MN-major, N>>3, M>>4
+constexpr uint32_t kIdescMN = umma_idesc(1u, 128u, 128u) | (1u << 15) | (1u << 16);
+
+}  // namespace
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                const WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t a_row_bytes = (uint32_t)P.PWs * 256u;  // two 64-channel halves of PWs x 128 B
+  const uint32_t b_row_bytes = (uint32_t)P.BW * 256u;
+  uint8_t* a_buf = smem;
+  uint8_t* b_buf = a_buf + (size_t)P.nring * a_row_bytes;
+  WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(b_buf + (size_t)P.nbslots * b_row_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tap group and rank of this CTA inside it
+  int g = 0;
+  for (int i = 0; i < P.ngroups; ++i)
+    if ((int)blockIdx.x >= P.g_cta0[i]) g = i;
+  const int rank = (int)blockIdx.x - P.g_cta0[g];
+  const int ncta = P.g_ncta[g];
+  const int tap0 = P.g_tap0[g], ntaps = P.g_ntaps[g];
+  const int kymin = tap0 / P.k, kymax = (tap0 + ntaps - 1) / P.k;
+  const int span = kymax - kymin;  // extra input rows per unit
+  const int units = P.NB * P.nseg * P.nrb;
+  const bool has_work = rank < units;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nring; ++i) {
+      mbar_init(&bars->a_full[i], 1);
+      mbar_init(&bars->a_empty[i], 1);
+    }
+    for (int i = 0; i < P.nbslots; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  auto decode = [&](int u, int* n, int* x0, int* y0, int* rows) {
+    const int rb = u % P.nrb;
+    const int q = u / P.nrb;
+    const int seg = q % P.nseg;
+    *n = q / P.nseg;
+    *x0 = seg * P.BW;
+    *y0 = rb * P.RB;
+    *rows = min(P.RB, P.H - *y0);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer: input rows (ring) and gradient rows
+    if (lane == 0 && has_work) {
+      uint32_t aq = 0, bq = 0;  // running row counters -> ring slot + phase
+      for (int u = rank; u < units; u += ncta) {
+        int n, x0, y0, rows;
+        decode(u, &n, &x0, &y0, &rows);
+        int next_in = y0 + kymin - P.p;  // next input row to load
+        for (int y = y0; y < y0 + rows; ++y) {
+          const int need = y + kymax - P.p;  // newest input row this output row reads
+          for (; next_in <= need; ++next_in, ++aq) {
+            const uint32_t slot = aq % (uint32_t)P.nring, ph = (aq / (uint32_t)P.nring) & 1u;
+            mbar_wait(&bars->a_empty[slot], ph ^ 1u);
+            mbar_expect_tx(&bars->a_full[slot], a_row_bytes);
+            uint8_t* dst = a_buf + (size_t)slot * a_row_bytes;
+            tma_load_4d(dst, &tmX, &bars->a_full[slot], 0, x0 - P.p, next_in, n);
+            tma_load_4d(dst + a_row_bytes / 2, &tmX, &bars->a_full[slot], 64, x0 - P.p, next_in, n);
+          }
+          const uint32_t slot = bq % (uint32_t)P.nbslots, ph = (bq / (uint32_t)P.nbslots) & 1u;
+          mbar_wait(&bars->b_empty[slot], ph ^ 1u);
+          mbar_expect_tx(&bars->b_full[slot], b_row_bytes);
+          uint8_t* dst = b_buf + (size_t)slot * b_row_bytes;
+          tma_load_4d(dst, &tmG, &bars->b_full[slot], 0, x0, y, n);
+          tma_load_4d(dst + b_row_bytes / 2, &tmG, &bars->b_full[slot], 64, x0, y, n);
+          ++bq;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
+    if (has_work) {
+      const bool leader = elect_one();
+      // MN-major SW128 descriptors: LBO = bytes between the two 64-channel halves, SBO = 8 pixel rows
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW128 << 29);
+      const uint32_t a_lo0 = (smem_u32(a_buf) >> 4) | (((a_row_bytes / 2) >> 4) << 16);
+      const uint32_t b_lo0 = (smem_u32(b_buf) >> 4) | (((b_row_bytes / 2) >> 4) << 16);
+      const int k16n = P.BW >> 4;
+      uint32_t aq = 0, bq = 0;  // counters at the START of the current unit / current row
+      uint32_t started = 0;
+      for (int u = rank; u < units; u += ncta) {
+        int n, x0, y0, rows;
+        decode(u, &n, &x0, &y0, &rows);
+        for (int yy = 0; yy < rows; ++yy) {
+          // input rows of this unit are numbered r = 0 .. rows+span-1 (r = y_in - (y0+kymin-p)); output row yy
+          // reads r = yy .. yy+span.  Rows become full in order; wait for the ones not yet seen.
+          for (int r = (yy == 0 ? 0 : yy + span); r <= yy + span; ++r) {
+            const uint32_t q = aq + (uint32_t)r;
+            mbar_wait(&bars->a_full[q % (uint32_t)P.nring], (q / (uint32_t)P.nring) & 1u);
+          }
+          const uint32_t bslot = bq % (uint32_t)P.nbslots;
+          mbar_wait(&bars->b_full[bslot], (bq / (uint32_t)P.nbslots) & 1u);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + bslot * (b_row_bytes >> 4);
+          for (int j = 0; j < ntaps; ++j) {
+            const int tap = tap0 + j;
+            const int ky = tap / P.k, kx = tap - ky * P.k;
+            const uint32_t q = aq + (uint32_t)(yy + ky - kymin);
+            const uint32_t a_lo = a_lo0 + (q % (uint32_t)P.nring) * (a_row_bytes >> 4) + (uint32_t)kx * 8u;
+            const uint32_t d = tmem_base + (uint32_t)j * 128u;
+            for (int s = 0; s < k16n; ++s) {
+              if (leader) {
+                const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)s * 128u);
+                const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)s * 128u);
+                umma_bf16(d, adesc, bdesc, kIdescMN, (started | (uint32_t)s) != 0u ? 1u : 0u);
+              }
+            }
+          }
+          started = 1;
+          if (leader) {
+            umma_commit(&bars->b_empty[bslot]);
+            // the oldest input row (r = yy) is not read by later output rows
+            const uint32_t q = aq + (uint32_t)yy;
+            umma_commit(&bars->a_empty[q % (uint32_t)P.nring]);
+            if (yy == rows - 1) {
+              for (int r = rows; r < rows + span; ++r) {
+                const uint32_t q2 = aq + (uint32_t)r;
+                umma_commit(&bars->a_empty[q2 % (uint32_t)P.nring]);
+              }
+            }
+          }
+          ++bq;
+        }
+        aq += (uint32_t)(rows + span);
+      }
+      if (leader) umma_commit(&bars->acc_full);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ drain: TMEM -> partial[cta][tap][ci][co]
+    const int ew = warp - 4;
+    float* dst = P.partial + (size_t)blockIdx.x * 4 * kAccFloats;
+    if (has_work) {
+      mbar_wait(&bars->acc_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < ntaps; ++j) {
+        float* row = dst + (size_t)j * kAccFloats + (size_t)(ew * 32 + lane) * 128;
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * 128 + cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<uint4*>(row + cb * 32 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+      }
+    } else {
+      for (int j = 0; j < ntaps; ++j) {
+        float4* row = reinterpret_cast<float4*>(dst + (size_t)j * kAccFloats + (size_t)(ew * 32 + lane) * 128);
+        for (int e = 0; e < 32; ++e) row[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dW[tap][ci][co] (= HWIO) = beta * dW + scale * sum over the CTAs of the tap's group of their partials.
+__global__ void wgrad_reduce_kernel(const WgradParams P, float scale, float beta, float* __restrict__ dw) {
+  const int total4 = P.k * P.k * kAccFloats / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int tap = i / (kAccFloats / 4);
+    const int e4 = i - tap * (kAccFloats / 4);
+    int g = 0;
+    for (int q = 0; q < P.ngroups; ++q)
+      if (tap >= P.g_tap0[q]) g = q;
+    const int j = tap - P.g_tap0[g];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < P.g_ncta[g]; ++c) {
+      const float4 v = reinterpret_cast<const float4*>(
+          P.partial + ((size_t)(P.g_cta0[g] + c) * 4 + j) * kAccFloats)[e4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(dw) + i;
+    float4 r = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
+    if (beta != 0.f) {
+      const float4 old = *o;
+      r.x = fmaf(beta, old.x, r.x); r.y = fmaf(beta, old.y, r.y);
+      r.z = fmaf(beta, old.z, r.z); r.w = fmaf(beta, old.w, r.w);
+    }
+    *o = r;
+  }
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled wg_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int make_row_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, int box_w) {
+  PFN_encodeTiled enc = wg_encode_fn();
+  if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(wgrad row map) failed: %d (W=%d H=%d box=%d)", (int)r, W,
+             H, box_w);
+    return set_error(SR_ERR_CUDA, msg);
+  }
+  return SR_OK;
+}
+
+struct WgradPlan {
+  CUtensorMap tmX, tmG;
+  WgradParams P;
+  int grid;
+  size_t smem_bytes;
+  float scale, beta;
+  float* dw;
+  double flops;
+};
+
+static constexpr size_t kWgSmemBudget = 227 * 1024;
+
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" size_t sr_wgrad_workspace_bytes(void) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  return (size_t)sms * 4 * kAccFloats * sizeof(float);
+}
+
+extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out) {
+  if (!d || !out) return set_error(SR_ERR_INVALID, "sr_wgrad_plan_create: null argument");
+  if (!d->x_bf16 || !d->g_bf16 || !d->dw_hwio || !d->workspace)
+    return set_error(SR_ERR_INVALID, "sr_wgrad_plan_create: null tensor pointer");
+  if (!(d->ksize == 1 || d->ksize == 3 || d->ksize == 5))
+    return set_error(SR_ERR_UNSUPPORTED, "wgrad kernel size must be 1, 3 or 5");
+  if (d->NB < 1 || d->H < 1 || d->W < 1) return set_error(SR_ERR_INVALID, "empty tensor");
+  if (d->workspace_bytes < sr_wgrad_workspace_bytes())
+    return set_error(SR_ERR_INVALID, "wgrad workspace too small (see sr_wgrad_workspace_bytes)");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+
+  WgradPlan* pl = new (std::nothrow) WgradPlan();
+  if (!pl) return set_error(SR_ERR_NOMEM, "out of host memory");
+  memset(pl, 0, sizeof *pl);
+  WgradParams& P = pl->P;
+  P.k = d->ksize;
+  P.p = (d->ksize - 1) / 2;
+  P.NB = d->NB;
+  P.H = d->H;
+  P.W = d->W;
+  const int ntaps = P.k * P.k;
+
+  // tap groups of <= 4 consecutive taps (row-major), sizes as even as possible
+  P.ngroups = (ntaps + 3) / 4;
+  {
+    int t = 0;
+    for (int g = 0; g < P.ngroups; ++g) {
+      const int left = ntaps - t, gl = P.ngroups - g;
+      const int sz = (left + gl - 1) / gl;
+      P.g_tap0[g] = t;
+      P.g_ntaps[g] = sz;
+      t += sz;
+    }
+  }
+  int max_span = 0;
+  for (int g = 0; g < P.ngroups; ++g)
+    max_span = std::max(max_span, (P.g_tap0[g] + P.g_ntaps[g] - 1) / P.k - P.g_tap0[g] / P.k);
+
+  // geometry: segment width (multiple of 16, <= 128) and ring depth within the shared-memory budget
+  bool ok = false;
+  for (int maxbw = 128; maxbw >= 16 && !ok; maxbw -= 16) {
+    const int nseg = (d->W + maxbw - 1) / maxbw;
+    const int bw = (((d->W + nseg - 1) / nseg) + 15) & ~15;
+    if (bw > maxbw) continue;
+    const int pws = (bw + 2 * P.p + 7) & ~7;
+    if (pws > 256) continue;
+    const size_t a_row = (size_t)pws * 256, b_row = (size_t)bw * 256;
+    const size_t fixed = 1024 + sizeof(WgradBarriers) + 64;
+    const int min_ring = max_span + 2, min_b = 2;
+    if (fixed + min_ring * a_row + min_b * b_row > kWgSmemBudget) continue;
+    int nring = min_ring, nb = min_b;
+    // grow both rings alternately while they fit
+    for (;;) {
+      bool grew = false;
+      if (nb < kMaxBSlots && nb < 4 && fixed + nring * a_row + (nb + 1) * b_row <= kWgSmemBudget) {
+        ++nb;
+        grew = true;
+      }
+      if (nring < kMaxRing && nring < max_span + 5 && fixed + (nring + 1) * a_row + nb * b_row <= kWgSmemBudget) {
+        ++nring;
+        grew = true;
+      }
+      if (!grew) break;
+    }
+    P.BW = bw;
+    P.nseg = nseg;
+    P.PWs = pws;
+    P.nring = nring;
+    P.nbslots = nb;
+    pl->smem_bytes = fixed + nring * a_row + nb * b_row;
+    ok = true;
+  }
+  if (!ok) {
+    delete pl;
+    return set_error(SR_ERR_UNSUPPORTED, "no wgrad geometry fits shared memory");
+  }
+
+  // CTAs per group proportional to the group's tap count; row blocks so that every group has enough units
+  int assigned = 0;
+  for (int g = 0; g < P.ngroups; ++g) {
+    int n = (int)((double)sms * P.g_ntaps[g] / ntaps);
+    if (n < 1) n = 1;
+    P.g_ncta[g] = n;
+    assigned += n;
+  }
+  for (int g = 0; assigned < sms; g = (g + 1) % P.ngroups) {  // hand out the remainder, larger groups first
+    ++P.g_ncta[g];
+    ++assigned;
+  }
+  while (assigned > sms) {
+    for (int g = P.ngroups - 1; g >= 0 && assigned > sms; --g)
+      if (P.g_ncta[g] > 1) {
+        --P.g_ncta[g];
+        --assigned;
+      }
+  }
+  int max_ncta = 0;
+  for (int g = 0; g < P.ngroups; ++g) max_ncta = std::max(max_ncta, P.g_ncta[g]);
+  P.RB = P.H;
+  P.nrb = 1;
+  while ((long long)P.NB * P.nseg * P.nrb < 12LL * max_ncta && P.RB > 8) {
+    P.RB = (P.RB + 1) / 2;
+    P.nrb = (P.H + P.RB - 1) / P.RB;
+  }
+  {
+    int c = 0;
+    for (int g = 0; g < P.ngroups; ++g) {
+      P.g_cta0[g] = c;
+      c += P.g_ncta[g];
+    }
+    pl->grid = c;
+  }
+  P.partial = reinterpret_cast<float*>(d->workspace);
+  pl->scale = d->scale;
+  pl->beta = d->accumulate ? 1.f : 0.f;
+  pl->dw = d->dw_hwio;
+  pl->flops = 2.0 * (double)d->NB * d->H * d->W * ntaps * 128.0 * 128.0;
+  int rc = make_row_map(&pl->tmX, d->x_bf16, d->NB, d->H, d->W, P.PWs);
+  if (rc == SR_OK) rc = make_row_map(&pl->tmG, d->g_bf16, d->NB, d->H, d->W, P.BW);
+  if (rc != SR_OK) {
+    delete pl;
+    return rc;
+  }
+  *out = reinterpret_cast<sr_wgrad_plan*>(pl);
+  return SR_OK;
+}
+
+extern "C" int sr_wgrad_plan_run(sr_wgrad_plan* plan, void* stream) {
+  if (!plan) return set_error(SR_ERR_INVALID, "sr_wgrad_plan_run: null plan");
+  const WgradPlan* pl = reinterpret_cast<const WgradPlan*>(plan);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kWgSmemBudget);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
+    attr_set = true;
+  }
+  wgrad_tc_kernel<<<pl->grid, kWgThreads, pl->smem_bytes, st>>>(pl->tmX, pl->tmG, pl->P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad_tc_kernel launch");
+  wgrad_reduce_kernel<<<296, 256, 0, st>>>(pl->P, pl->scale, pl->beta, pl->dw);
+  return check_launch("wgrad_reduce_kernel launch");
+}
+
+extern "C" void sr_wgrad_plan_destroy(sr_wgrad_plan* plan) { delete reinterpret_cast<WgradPlan*>(plan); }
+
+extern "C" int sr_wgrad_plan_info(const sr_wgrad_plan* plan, sr_wgrad_plan_info_t* info) {
+  if (!plan || !info) return set_error(SR_ERR_INVALID, "sr_wgrad_plan_info: null argument");
+  const WgradPlan* pl = reinterpret_cast<const WgradPlan*>(plan);
+  info->flops = pl->flops;
+  info->grid = pl->grid;
+  info->smem_bytes = (int)pl->smem_bytes;
+  info->seg_width = pl->P.BW;
+  info->nseg = pl->P.nseg;
+  info->ring_rows = pl->P.nring;
+  info->g_slots = pl->P.nbslots;
+  info->tap_groups = pl->P.ngroups;
+  info->rows_per_unit = pl->P.RB;
+  return SR_OK;
+}

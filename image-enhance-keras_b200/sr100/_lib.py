@@ -50,6 +50,23 @@ class ConvPlanInfo(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("x_bf16", C.c_void_p), ("g_bf16", C.c_void_p),
+        ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("ksize", C.c_int), ("scale", C.c_float), ("accumulate", C.c_int),
+        ("dw_hwio", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class WgradPlanInfo(C.Structure):
+    _fields_ = [
+        ("flops", C.c_double),
+        ("grid", C.c_int), ("smem_bytes", C.c_int), ("seg_width", C.c_int), ("nseg", C.c_int),
+        ("ring_rows", C.c_int), ("g_slots", C.c_int), ("tap_groups", C.c_int), ("rows_per_unit", C.c_int),
+    ]
+
+
 class ScoreResult(C.Structure):
     _fields_ = [
         ("sum_sq_y", C.c_double),
@@ -88,6 +105,14 @@ SIGNATURES = {
     "sr_sum_sq_diff_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "sr_mse_loss_grad": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
     "sr_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
+    "sr_wgrad_workspace_bytes": (_sz, []),
+    "sr_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
+    "sr_wgrad_plan_run": (_i, [_vp, _vp]),
+    "sr_wgrad_plan_destroy": (None, [_vp]),
+    "sr_wgrad_plan_info": (_i, [_vp, C.POINTER(WgradPlanInfo)]),
+    "sr_mse_tail_grad": (_i, [_vp, _vp, _sz, _i, _sz, _vp, _vp, _vp]),
+    "sr_colsum_bf16": (_i, [_vp, _sz, _f, _vp, _vp]),
+    "sr_head1x1_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_axpby_f32": (_i, [_vp, _vp, _f, _f, _sz, _vp, _vp, _vp]),
     "sr_cast_f32_to_bf16": (_i, [_vp, _sz, _vp, _vp]),
     "sr_cast_bf16_to_f32": (_i, [_vp, _sz, _vp, _vp]),

@@ -181,7 +181,20 @@ class Engine:
         self.max_pixels = max_pixels  # LR pixels per sub-batch (HR activations are 16x this)
         self.specs = layer_specs()
         self.ksize = {n: k for n, k, _, _ in self.specs}
-        self.master = {}   # name -> (kernel HWIO fp32 device, bias fp32 device)
+        self.master = {}   # name -> (kernel HWIO fp32 device, bias fp32 device): views into param_arena
+        # one flat fp32 arena in layer order (kernel, bias, kernel, bias, ...): the optimizer step and the
+        # gradient all-reduce of the training path are single launches over it
+        self.param_slices = {}
+        off = 0
+        for name, k, cin, cout in self.specs:
+            nw, nb = k * k * cin * cout, cout
+            self.param_slices[name] = (off, nw, off + nw, nb)
+            off += nw + nb
+        self.n_params = off
+        self.param_arena = torch.zeros(off, dtype=torch.float32, device=self.device)
+        for name, k, cin, cout in self.specs:
+            ow, nw, ob, nb = self.param_slices[name]
+            self.master[name] = (self.param_arena[ow:ow + nw].view(k, k, cin, cout), self.param_arena[ob:ob + nb])
         self.packed = {}
         self._bias_cache = {}
         self._graphs = {}
@@ -197,11 +210,8 @@ class Engine:
             if w.shape != (k, k, cin, cout) or b.shape != (cout,):
                 raise ValueError("layer %s: expected kernel %s / bias %s, got %s / %s"
                                  % (name, (k, k, cin, cout), (cout,), w.shape, b.shape))
-            if name in self.master:
-                self.master[name][0].copy_(torch.from_numpy(w))
-                self.master[name][1].copy_(torch.from_numpy(b))
-            else:
-                self.master[name] = (torch.from_numpy(w).to(self.device), torch.from_numpy(b).to(self.device))
+            self.master[name][0].copy_(torch.from_numpy(w))
+            self.master[name][1].copy_(torch.from_numpy(b))
         self.head_w = self.master["level1"][0].reshape(3, NUMK)
         self.head_b = self.master["level1"][1]
         self.repack()

@@ -1,0 +1,326 @@
+"""Training step of DifvdsrDouble on sm_100a: forward with saved activations, MSE, backward (dgrad / wgrad on
+the tensor cores), data-parallel gradient all-reduce, fused Keras-Adam.
+
+Reference: BaseSuperResolutionModel.fit (models.py:131-157) = Keras fit_generator -> train_on_batch on the graph of
+models.py:1159-1270 compiled with loss='mse', Adam(lr=1e-4, beta_1=0.9) (models.py:1212-1213; Keras-2 defaults
+beta_2=0.999, epsilon=1e-7).
+
+Backward of a 5/3 block  y = 0.1*(conv5_b(t1) + conv3_d(t2)) + 0.9*x,  t1 = relu(conv3_a(x)), t2 = relu(conv5_c(x)):
+    g_t1 = 0.1 * dgrad_b(g_y) * (t1 > 0)          g_t2 = 0.1 * dgrad_d(g_y) * (t2 > 0)
+    g_x  = dgrad_a(g_t1) + dgrad_c(g_t2) + 0.9 * g_y                       (one fused two-source launch)
+    dW_b = 0.1 * wgrad(t1, g_y)   dW_d = 0.1 * wgrad(t2, g_y)   dW_a = wgrad(x, g_t1)   dW_c = wgrad(x, g_t2)
+dgrad is the forward conv kernel with 180-degree-rotated, cin<->cout-transposed weights and a fused ReLU mask;
+wgrad is csrc/wgrad_tc.cu.  Operands are bf16, accumulation fp32, master weights / gradients / Adam state fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import NUMK, _Plan, layer_specs
+
+
+class _WgradPlan:
+    def __init__(self, lib, x, g, shape, ksize, scale, dw, workspace):
+        self.lib = lib
+        d = L.WgradDesc()
+        d.x_bf16, d.g_bf16 = x.data_ptr(), g.data_ptr()
+        d.NB, d.H, d.W = shape
+        d.ksize, d.scale, d.accumulate = ksize, scale, 0
+        d.dw_hwio, d.workspace, d.workspace_bytes = dw.data_ptr(), workspace.data_ptr(), workspace.numel()
+        self.handle = C.c_void_p()
+        L.check(lib.sr_wgrad_plan_create(C.byref(d), C.byref(self.handle)))
+        info = L.WgradPlanInfo()
+        L.check(lib.sr_wgrad_plan_info(self.handle, C.byref(info)))
+        self.flops = info.flops
+
+    def run(self, stream):
+        L.check(self.lib.sr_wgrad_plan_run(self.handle, stream))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.sr_wgrad_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class _TrainGraph:
+    """Buffers and launch lists (forward with saved activations, backward) for one (NB, H, W) minibatch shape."""
+
+    def __init__(self, tr, NB, H, W):
+        eng, lib, dev = tr.engine, tr.engine.lib, tr.engine.device
+        bf, f32 = torch.bfloat16, torch.float32
+        self.NB, self.H, self.W = NB, H, W
+        HH, WW = 4 * H, 4 * W
+        lr, hr = (NB, H, W), (NB, HH, WW)
+        names = [s[0] for s in layer_specs()]
+
+        def act(shape, dtype=bf, ch=NUMK):
+            return torch.empty(*shape, ch, device=dev, dtype=dtype)
+
+        self.x_in = act(lr, f32, 3)
+        self.y_true = act(hr, f32, 3)
+        self.out = act(hr, f32, 3)
+        # saved forward tensors (bf16 = exactly what the convs consumed)
+        S = [act(lr) for _ in range(23)]            # S[0] = head output, S[i+1] = output of LR block i
+        T1 = [act(lr) for _ in range(22)]
+        T2 = [act(lr) for _ in range(16)]
+        s32 = act(lr, f32)                          # fp32 residual stream (rotating, forward only)
+        SH = [act(hr) for _ in range(3)]
+        TH1 = [act(hr) for _ in range(2)]
+        TH2 = [act(hr) for _ in range(2)]
+        # gradients
+        gs, gs32 = act(lr), act(lr, f32)
+        gt1, gt2 = act(lr), act(lr)
+        gsh, gsh32 = act(hr), act(hr, f32)
+        gth1, gth2 = act(hr), act(hr)
+        self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.keep = [S, T1, T2, s32, SH, TH1, TH2, gs, gs32, gt1, gt2, gsh, gsh32, gth1, gth2]
+        self.fwd, self.bwd = [], []
+        self.fwd_flops = self.bwd_flops = 0.0
+
+        def conv(dst, srcs, shape, flip=False, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0,
+                 res32=None, res16=None, mask=None, cout=NUMK, bias=True):
+            d = L.ConvDesc()
+            d.nsrc = len(srcs)
+            for s, (name, x) in enumerate(srcs):
+                d.in_[s] = x.data_ptr()
+                d.wpacked[s] = (tr.packed_t if flip else eng.packed)[name].data_ptr()
+                d.ksize[s] = eng.ksize[name]
+            d.NB, d.H, d.W = shape
+            d.cin, d.cout = NUMK, cout
+            d.bias = eng.bias_for(tuple(n for n, _ in srcs)).data_ptr() if bias else None
+            d.alpha, d.beta, d.relu = alpha, beta, relu
+            d.res_f32 = res32.data_ptr() if res32 is not None else None
+            d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
+            d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+            d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+            d.relu_mask_bf16 = mask.data_ptr() if mask is not None else None
+            d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
+            p = _Plan(lib, d)
+            if dst is self.fwd:
+                self.fwd_flops += p.flops
+            else:
+                self.bwd_flops += p.flops
+            dst.append(p.run)
+
+        def wgrad(x, g, shape, name, scale):
+            p = _WgradPlan(lib, x, g, shape, eng.ksize[name], scale, tr.grad_w(name), tr.workspace)
+            self.bwd_flops += p.flops
+            self.bwd.append(p.run)
+
+        def colsum(g, shape, name, scale, also=None):
+            npix = shape[0] * shape[1] * shape[2]
+            db = tr.grad_b(name)
+            self.bwd.append(lambda st: L.check(lib.sr_colsum_bf16(L.ptr(g), npix, scale, L.ptr(db), st)))
+            if also is not None:
+                db2 = tr.grad_b(also)
+                self.bwd.append(lambda st: db2.copy_(db))
+
+        # ------------------------------------------------------------------ forward
+        npix = NB * H * W
+        self.fwd.append(lambda st: L.check(lib.sr_head1x1_fwd(
+            L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, L.ptr(S[0]), L.ptr(s32), st)))
+        blocks = []  # (kind, first layer index, x, t1, t2, y, shape, f32 stream)
+        i = 1
+        for b in range(16):
+            blocks.append(("53", i, S[b], T1[b], T2[b], S[b + 1], lr, True))
+            i += 4
+        for b in range(6):
+            blocks.append(("light", i, S[16 + b], T1[16 + b], None, S[17 + b], lr, True))
+            i += 2
+        for b in range(2):
+            blocks.append(("53", i, SH[b], TH1[b], TH2[b], SH[b + 1], hr, False))
+            i += 4
+        tail = names[i]
+
+        def fwd_block(kind, i, x, t1, t2, y, shape, f32s):
+            r32 = s32 if f32s else None
+            if kind == "53":
+                conv(self.fwd, [(names[i], x)], shape, out_bf16=t1, relu=1)
+                conv(self.fwd, [(names[i + 2], x)], shape, out_bf16=t2, relu=1)
+                conv(self.fwd, [(names[i + 1], t1), (names[i + 3], t2)], shape, out_bf16=y, out_f32=r32, alpha=0.1,
+                     beta=0.9, res32=r32, res16=x)
+            else:
+                conv(self.fwd, [(names[i], x)], shape, out_bf16=t1, relu=1)
+                conv(self.fwd, [(names[i + 1], t1)], shape, out_bf16=y, out_f32=r32, alpha=0.1, beta=1.0, res32=r32,
+                     res16=x)
+
+        for blk in blocks[:22]:
+            fwd_block(*blk)
+        self.fwd.append(lambda st: L.check(lib.sr_bilinear4_fwd(L.ptr(s32), 0, NB, H, W, NUMK, L.ptr(SH[0]), None, st)))
+        for blk in blocks[22:]:
+            fwd_block(*blk)
+        conv(self.fwd, [(tail, SH[2])], hr, out_f32=self.out, relu=1, cout=3)
+
+        # ------------------------------------------------------------------ backward
+        npix_hr = NB * HH * WW
+        self.n_local = npix_hr * 3
+        self.bwd.append(lambda st: L.check(lib.sr_mse_tail_grad(
+            L.ptr(self.out), L.ptr(self.y_true), npix_hr, 3, self.n_local, L.ptr(gth1), L.ptr(self.loss_sum), st)))
+        # tail conv (128 -> 3): its gradient travels as a 128-channel tensor whose channels >= 3 are zero
+        p = _WgradPlan(lib, SH[2], gth1, hr, 3, 1.0, tr.tail_dw128, tr.workspace)
+        self.bwd_flops += p.flops * 3 / 128.0
+        self.bwd.append(p.run)
+        tail_w, tail_b = tr.grad_w(tail), tr.grad_b(tail)
+        self.bwd.append(lambda st: tail_w.copy_(tr.tail_dw128[..., :3]))
+        self.bwd.append(lambda st: tr.tail_db128.zero_())
+        self.bwd.append(lambda st: L.check(lib.sr_colsum_bf16(L.ptr(gth1), npix_hr, 1.0, L.ptr(tr.tail_db128), st)))
+        self.bwd.append(lambda st: tail_b.copy_(tr.tail_db128[:3]))
+        conv(self.bwd, [(tail, gth1)], hr, flip=True, out_bf16=gsh, bias=False)
+
+        def bwd_block(kind, i, x, t1, t2, y, shape, f32s, last_hr=False):
+            g, g32 = (gs, gs32) if f32s else (gsh, None)
+            a1, a2 = (gt1, gt2) if f32s else (gth1, gth2)
+            o32 = g32 if f32s else (gsh32 if last_hr else None)
+            if kind == "53":
+                na, nb, nc, nd = names[i], names[i + 1], names[i + 2], names[i + 3]
+                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False)
+                conv(self.bwd, [(nd, g)], shape, flip=True, out_bf16=a2, alpha=0.1, mask=t2, bias=False)
+                wgrad(t1, g, shape, nb, 0.1)
+                wgrad(t2, g, shape, nd, 0.1)
+                colsum(g, shape, nb, 0.1, also=nd)
+                conv(self.bwd, [(na, a1), (nc, a2)], shape, flip=True, out_bf16=g, out_f32=o32, alpha=1.0, beta=0.9,
+                     res32=g32, res16=g, bias=False)
+                wgrad(x, a1, shape, na, 1.0)
+                wgrad(x, a2, shape, nc, 1.0)
+                colsum(a1, shape, na, 1.0)
+                colsum(a2, shape, nc, 1.0)
+            else:
+                na, nb = names[i], names[i + 1]
+                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False)
+                wgrad(t1, g, shape, nb, 0.1)
+                colsum(g, shape, nb, 0.1)
+                conv(self.bwd, [(na, a1)], shape, flip=True, out_bf16=g, out_f32=o32, alpha=1.0, beta=1.0, res32=g32,
+                     res16=g, bias=False)
+                wgrad(x, a1, shape, na, 1.0)
+                colsum(a1, shape, na, 1.0)
+
+        bwd_block(*blocks[23])
+        bwd_block(*blocks[22], last_hr=True)
+        self.bwd.append(lambda st: L.check(lib.sr_bilinear4_bwd(L.ptr(gsh32), NB, H, W, NUMK, L.ptr(gs32), st)))
+        self.bwd.append(lambda st: L.check(lib.sr_cast_f32_to_bf16(L.ptr(gs32), npix * NUMK, L.ptr(gs), st)))
+        for blk in reversed(blocks[:22]):
+            bwd_block(*blk)
+        hw, hb = tr.grad_w("level1"), tr.grad_b("level1")
+        self.bwd.append(lambda st: L.check(lib.sr_head1x1_bwd(
+            L.ptr(self.x_in), L.ptr(S[0]), L.ptr(gs32), None, npix, L.ptr(hw), L.ptr(hb), st)))
+
+
+class Trainer:
+    """train_on_batch / evaluate for a kmodel.Model (Keras Model.train_on_batch semantics: returns the loss)."""
+
+    def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.engine = engine
+        self.lib = engine.lib
+        self.lr, self.beta_1, self.beta_2, self.epsilon = float(lr), float(beta_1), float(beta_2), float(epsilon)
+        dev = engine.device
+        n = engine.n_params
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.t = 0
+        self.workspace = torch.empty(self.lib.sr_wgrad_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.tail_dw128 = torch.zeros(3, 3, NUMK, NUMK, dtype=torch.float32, device=dev)
+        self.tail_db128 = torch.zeros(NUMK, dtype=torch.float32, device=dev)
+        self.packed_t = {}      # name -> packed weights of the input-gradient conv
+        self._graphs = {}
+        self.repack_t()
+
+    # ------------------------------------------------------------------ views into the flat arenas
+    def grad_w(self, name):
+        ow, nw, _, _ = self.engine.param_slices[name]
+        k, cin, cout = self.engine.ksize[name], (3 if name == "level1" else NUMK), self.engine.master[name][0].shape[3]
+        return self.grads[ow:ow + nw].view(k, k, cin, cout)
+
+    def grad_b(self, name):
+        _, _, ob, nb = self.engine.param_slices[name]
+        return self.grads[ob:ob + nb]
+
+    def grads_dict(self):
+        return {n: (self.grad_w(n).cpu().numpy(), self.grad_b(n).cpu().numpy()) for n, _, _, _ in self.engine.specs}
+
+    def repack_t(self):
+        st = L.stream_ptr()
+        for name, k, cin, cout in self.engine.specs:
+            if cin != NUMK:
+                continue
+            if name not in self.packed_t:
+                self.packed_t[name] = torch.empty(self.lib.sr_packed_weight_bytes(k, NUMK), dtype=torch.uint8,
+                                                  device=self.engine.device)
+            L.check(self.lib.sr_pack_conv_weights(L.ptr(self.engine.master[name][0]), k, cout, 1,
+                                                  L.ptr(self.packed_t[name]), st))
+
+    def graph(self, NB, H, W):
+        key = (NB, H, W)
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs.clear()   # one minibatch shape resident at a time (saved activations are large)
+            g = _TrainGraph(self, NB, H, W)
+            self._graphs[key] = g
+        return g
+
+    # ------------------------------------------------------------------ steps
+    def _load(self, g, x, y):
+        for dst, src in ((g.x_in, x), (g.y_true, y)):
+            if isinstance(src, torch.Tensor):
+                dst.copy_(src, non_blocking=True)
+            else:
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)), non_blocking=True)
+
+    def forward_backward_device(self, g):
+        """Forward + backward on the tensors already in g.x_in / g.y_true; gradients land in self.grads."""
+        st = L.stream_ptr()
+        self.grads.zero_()
+        g.loss_sum.zero_()
+        for f in g.fwd:
+            f(st)
+        for f in g.bwd:
+            f(st)
+
+    def apply_gradients(self):
+        """Data-parallel mean of the gradients (NCCL all-reduce of the flat arena) + fused Keras Adam + repack."""
+        import torch.distributed as dist
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.t += 1
+        L.check(self.lib.sr_adam_step(L.ptr(self.engine.param_arena), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v),
+                                      self.engine.n_params, self.lr, self.beta_1, self.beta_2, self.epsilon, self.t,
+                                      1.0 / world, L.stream_ptr()))
+        self.engine.repack()
+        self.repack_t()
+
+    def step_device(self, g):
+        self.forward_backward_device(g)
+        self.apply_gradients()
+
+    def train_on_batch(self, x, y):
+        x_shape = tuple(x.shape)
+        if len(x_shape) != 4 or x_shape[-1] != 3 or tuple(y.shape) != (x_shape[0], 4 * x_shape[1], 4 * x_shape[2], 3):
+            raise ValueError("Error when checking target: expected x (N,h,w,3) and y (N,4h,4w,3), got %s and %s"
+                             % (x_shape, tuple(y.shape)))
+        g = self.graph(*x_shape[:3])
+        self._load(g, x, y)
+        self.step_device(g)
+        return float(g.loss_sum.item()) / g.n_local
+
+    def evaluate(self, x, y):
+        """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""
+        g = self.graph(*tuple(x.shape)[:3])
+        self._load(g, x, y)
+        st = L.stream_ptr()
+        for f in g.fwd:
+            f(st)
+        d = g.out - g.y_true
+        acc = (g.out.argmax(dim=-1) == g.y_true.argmax(dim=-1)).float().mean()
+        return float((d * d).mean().item()), float(acc.item())
+
+    def step_flops(self, g):
+        return g.fwd_flops + g.bwd_flops

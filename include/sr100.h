@@ -77,7 +77,9 @@ int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info);
 
 /* Repack Keras HWIO fp32 weights [k,k,cin=128,cout] (device) into the kernel's K-chunked bf16
  * layout [cin/32][k*k][cout_pad][32]; cout_pad = 128 or 16.  transpose_flip = 1 produces the
- * weights of the input-gradient convolution (180-degree rotation, cin<->cout; needs cout == 128).
+ * weights of the input-gradient convolution (180-degree rotation, cin<->cout): always a
+ * 128 -> 128 layout (destination size sr_packed_weight_bytes(ksize, 128)); for cout < 128 the
+ * missing reduction rows are zero, so the gradient tensor may carry anything in channels >= cout.
  * sr_packed_weight_bytes gives the destination size. */
 size_t sr_packed_weight_bytes(int ksize, int cout);
 int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip, void* dst,
@@ -172,7 +174,45 @@ int sr_sum_sq_diff_f64(const double* a, const double* b, size_t n, double* out, 
 
 /* ------------------------------------------------------------------------------------------
  * Training step pieces (models.py:131-157 fit, :1212-1213 compile: mse + Adam(1e-4, 0.9)).
+ * The input gradient of a conv is sr_conv_plan_* with transpose_flip weights (+ relu_mask_bf16).
  * ------------------------------------------------------------------------------------------ */
+/* Filter gradient of a 128 -> 128 Conv2D(padding='same') on the tensor cores:
+ *   dw[ky][kx][ci][co] (HWIO fp32) = (accumulate ? dw : 0) + scale * sum_{n,y,x} x[n,y+ky-p,x+kx-p,ci] * g[n,y,x,co]
+ * x, g: bf16 NHWC [NB,H,W,128].  workspace: device scratch of sr_wgrad_workspace_bytes() bytes
+ * (per-CTA fp32 partials, summed in a fixed order: results are run-to-run deterministic). */
+typedef struct sr_wgrad_desc {
+  const void* x_bf16;
+  const void* g_bf16;
+  int NB, H, W;
+  int ksize;             /* 1, 3 or 5 */
+  float scale;
+  int accumulate;
+  float* dw_hwio;        /* [ksize,ksize,128,128] fp32 */
+  void* workspace;
+  size_t workspace_bytes;
+} sr_wgrad_desc;
+typedef struct sr_wgrad_plan sr_wgrad_plan;
+typedef struct sr_wgrad_plan_info_t {
+  double flops;
+  int grid, smem_bytes, seg_width, nseg, ring_rows, g_slots, tap_groups, rows_per_unit;
+} sr_wgrad_plan_info_t;
+size_t sr_wgrad_workspace_bytes(void);
+int sr_wgrad_plan_create(const sr_wgrad_desc* desc, sr_wgrad_plan** plan);
+int sr_wgrad_plan_run(sr_wgrad_plan* plan, void* stream);
+void sr_wgrad_plan_destroy(sr_wgrad_plan* plan);
+int sr_wgrad_plan_info(const sr_wgrad_plan* plan, sr_wgrad_plan_info_t* info);
+
+/* Loss gradient at the tail: loss_sum += sum (pred-target)^2 (fp64, device); g128[pix][c] =
+ * 2*(pred-target)/n_total where pred > 0 (ReLU of the last Conv2D, models.py:1199), as bf16 rows
+ * of 128 channels (channels >= `channels` zero) = the operand layout of dgrad / wgrad. */
+int sr_mse_tail_grad(const float* pred, const float* target, size_t npix, int channels,
+                     size_t n_total, void* g128_bf16, double* loss_sum, void* stream);
+/* Bias gradient: out[c] += scale * sum_pix g[pix][c]; g bf16 [npix,128]; out fp32 [128]. */
+int sr_colsum_bf16(const void* g_bf16, size_t npix, float scale, float* out, void* stream);
+/* First layer (models.py:1177) backward: g0 = g*(act>0); dw[3][128] += x^T g0; db[128] += colsum g0.
+ * x fp32 [npix,3]; act bf16 [npix,128] (layer output); g fp32 or bf16 [npix,128] (one of them). */
+int sr_head1x1_bwd(const float* x, const void* act_bf16, const float* g_f32, const void* g_bf16,
+                   size_t npix, float* dw, float* db, void* stream);
 /* loss_sum += sum (pred-target)^2 (fp64 accumulator, device); grad = 2*(pred-target)/n_total. */
 int sr_mse_loss_grad(const float* pred, const float* target, size_t n, size_t n_total, float* grad,
                      double* loss_sum, void* stream);

@@ -1,0 +1,236 @@
+"""-m gpu: training-step pieces and the whole step (sr100.train.Trainer) against the CPU oracle (oracle/model.py:
+torch-CPU autograd on the restated graph + hand-written Keras Adam).  Operands are bf16 on the GPU, so whole-model
+gradients are compared in relative L2 / cosine per layer; single kernels are compared with bf16-rounded inputs and
+are exact up to fp32 summation order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import bf16_round
+
+pytestmark = pytest.mark.gpu
+
+
+def _wgrad_gpu(lib, x, g, k, scale=1.0, accumulate=0, dw0=None):
+    from sr100 import _lib as L
+    NB, H, W, _ = x.shape
+    xd = torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous()
+    gd = torch.from_numpy(g).cuda().to(torch.bfloat16).contiguous()
+    dw = torch.zeros(k, k, 128, 128, device="cuda") if dw0 is None else torch.from_numpy(dw0).cuda()
+    ws = torch.empty(lib.sr_wgrad_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    d = L.WgradDesc()
+    d.x_bf16, d.g_bf16 = xd.data_ptr(), gd.data_ptr()
+    d.NB, d.H, d.W, d.ksize = NB, H, W, k
+    d.scale, d.accumulate = scale, accumulate
+    d.dw_hwio, d.workspace, d.workspace_bytes = dw.data_ptr(), ws.data_ptr(), ws.numel()
+    plan = C.c_void_p()
+    L.check(lib.sr_wgrad_plan_create(C.byref(d), C.byref(plan)))
+    L.check(lib.sr_wgrad_plan_run(plan, L.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.sr_wgrad_plan_destroy(plan)
+    return dw.cpu().numpy()
+
+
+def _wgrad_oracle(x, g, k):
+    xin = torch.from_numpy(x).permute(0, 3, 1, 2).contiguous().double()
+    gout = torch.from_numpy(g).permute(0, 3, 1, 2).contiguous().double()
+    w = torch.nn.grad.conv2d_weight(xin, (128, 128, k, k), gout, padding=k // 2)
+    return w.permute(2, 3, 1, 0).contiguous().numpy()
+
+
+@pytest.mark.parametrize("k,shape", [(1, (1, 5, 16)), (3, (2, 12, 48)), (5, (2, 9, 50)), (3, (1, 7, 200)),
+                                     (5, (3, 20, 96)), (5, (1, 1, 1)), (3, (1, 2, 3))])
+def test_wgrad_matches_oracle(lib, k, shape):
+    rng = np.random.default_rng(k * 100 + shape[2])
+    x = bf16_round(rng.normal(0, 0.5, size=shape + (128,)))
+    g = bf16_round(rng.normal(0, 0.5, size=shape + (128,)))
+    got = _wgrad_gpu(lib, x, g, k)
+    want = _wgrad_oracle(x, g, k)
+    tol = 1e-4 * max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= tol
+
+
+def test_wgrad_scale_accumulate_and_determinism(lib):
+    rng = np.random.default_rng(5)
+    x = bf16_round(rng.normal(0, 0.5, size=(4, 16, 48, 128)))
+    g = bf16_round(rng.normal(0, 0.5, size=(4, 16, 48, 128)))
+    dw0 = rng.normal(0, 1, size=(3, 3, 128, 128)).astype(np.float32)
+    got = _wgrad_gpu(lib, x, g, 3, scale=0.1, accumulate=1, dw0=dw0)
+    want = dw0 + 0.1 * _wgrad_oracle(x, g, 3)
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+    again = _wgrad_gpu(lib, x, g, 3, scale=0.1, accumulate=1, dw0=dw0)
+    assert np.array_equal(got, again)          # fixed summation order: bit-identical run to run
+
+
+def test_wgrad_rejects_bad_arguments(lib):
+    from sr100 import _lib as L
+    d = L.WgradDesc()
+    plan = C.c_void_p()
+    assert lib.sr_wgrad_plan_create(C.byref(d), C.byref(plan)) == -1
+    x = torch.zeros(1, 4, 16, 128, device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros(9 * 128 * 128, device="cuda")
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    d.x_bf16 = d.g_bf16 = x.data_ptr()
+    d.NB, d.H, d.W, d.ksize = 1, 4, 16, 3
+    d.dw_hwio, d.workspace, d.workspace_bytes = dw.data_ptr(), ws.data_ptr(), ws.numel()
+    assert lib.sr_wgrad_plan_create(C.byref(d), C.byref(plan)) == -1      # workspace too small
+    d.ksize = 4
+    assert lib.sr_wgrad_plan_create(C.byref(d), C.byref(plan)) == -2
+
+
+def test_dgrad_is_conv_with_flipped_weights(lib):
+    """Input gradient of Conv2D = the forward kernel on transpose_flip-packed weights, with the fused ReLU mask."""
+    from sr100 import _lib as L
+    rng = np.random.default_rng(9)
+    for k, cout in ((3, 128), (5, 128), (3, 3)):
+        NB, H, W = 2, 10, 24
+        w = (rng.normal(0, 1, size=(k, k, 128, cout)) / np.sqrt(k * k * 128)).astype(np.float32)
+        g = np.zeros((NB, H, W, 128), dtype=np.float32)
+        g[..., :cout] = bf16_round(rng.normal(0, 0.5, size=(NB, H, W, cout)))
+        if cout < 128:
+            g[..., cout:] = 7.0          # must be ignored: the packed reduction rows >= cout are zero
+        mask = bf16_round(rng.normal(0, 1, size=(NB, H, W, 128)))
+        gd = torch.from_numpy(g).cuda().to(torch.bfloat16)
+        md = torch.from_numpy(mask).cuda().to(torch.bfloat16)
+        wd = torch.from_numpy(w).cuda()
+        pk = torch.empty(lib.sr_packed_weight_bytes(k, 128), dtype=torch.uint8, device="cuda")
+        L.check(lib.sr_pack_conv_weights(L.ptr(wd), k, cout, 1, L.ptr(pk), L.stream_ptr()))
+        out = torch.zeros(NB, H, W, 128, device="cuda")
+        d = L.ConvDesc()
+        d.nsrc = 1
+        d.in_[0], d.wpacked[0], d.ksize[0] = gd.data_ptr(), pk.data_ptr(), k
+        d.NB, d.H, d.W, d.cin, d.cout = NB, H, W, 128, 128
+        d.alpha, d.beta, d.relu = 0.1, 0.0, 0
+        d.out_f32, d.relu_mask_bf16 = out.data_ptr(), md.data_ptr()
+        d.a_mode, d.nacc, d.pair = 0, 2, 1
+        plan = C.c_void_p()
+        L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))
+        L.check(lib.sr_conv_plan_run(plan, L.stream_ptr()))
+        torch.cuda.synchronize()
+        lib.sr_conv_plan_destroy(plan)
+        # oracle: autograd of the forward conv
+        xin = torch.zeros(NB, 128, H, W, dtype=torch.float64, requires_grad=True)
+        wt = torch.from_numpy(bf16_round(w)).double().permute(3, 2, 0, 1)
+        y = torch.nn.functional.conv2d(xin, wt, padding=k // 2)
+        gy = torch.from_numpy(g[..., :cout]).double().permute(0, 3, 1, 2)
+        (gx,) = torch.autograd.grad(y, xin, gy)
+        want = 0.1 * gx.permute(0, 2, 3, 1).numpy() * (mask > 0)
+        # the epilogue stages the accumulator as bf16 (8-bit mantissa) before alpha/mask: half-ulp = 2^-9 relative
+        assert np.abs(out.cpu().numpy() - want).max() <= 2.0 ** -8 * np.abs(want).max()
+
+
+def test_tail_grad_colsum_head_bwd(lib):
+    from sr100 import _lib as L
+    rng = np.random.default_rng(3)
+    npix, C3 = 1000, 3
+    pred = np.maximum(rng.normal(0.2, 0.3, size=(npix, C3)), 0).astype(np.float32)
+    tgt = rng.random((npix, C3)).astype(np.float32)
+    g128 = torch.full((npix, 128), 5.0, device="cuda", dtype=torch.bfloat16)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    pd, td = torch.from_numpy(pred).cuda(), torch.from_numpy(tgt).cuda()
+    n_total = npix * C3
+    L.check(lib.sr_mse_tail_grad(L.ptr(pd), L.ptr(td), npix, C3, n_total, L.ptr(g128), L.ptr(loss), L.stream_ptr()))
+    want_g = np.where(pred > 0, 2.0 * (pred - tgt) / n_total, 0.0)
+    got = g128.float().cpu().numpy()
+    assert np.array_equal(got[:, 3:], np.zeros((npix, 125), dtype=np.float32))
+    assert np.array_equal(got[:, :3], bf16_round(want_g.astype(np.float32)))
+    assert abs(loss.item() - ((pred.astype(np.float64) - tgt) ** 2).sum()) <= 1e-9 * n_total
+    # bias gradient
+    g = bf16_round(rng.normal(0, 1, size=(777, 128)))
+    out = torch.ones(128, device="cuda")
+    g16 = torch.from_numpy(g).cuda().to(torch.bfloat16)
+    L.check(lib.sr_colsum_bf16(L.ptr(g16), 777, 0.1, L.ptr(out), L.stream_ptr()))
+    assert np.abs(out.cpu().numpy() - (1.0 + 0.1 * g.astype(np.float64).sum(0))).max() <= 1e-4
+    # first-layer backward
+    x = rng.random((500, 3)).astype(np.float32)
+    act = bf16_round(np.maximum(rng.normal(0, 1, size=(500, 128)), 0))
+    gg = rng.normal(0, 1, size=(500, 128)).astype(np.float32)
+    dw, db = torch.zeros(3, 128, device="cuda"), torch.zeros(128, device="cuda")
+    xd, ad, gd = torch.from_numpy(x).cuda(), torch.from_numpy(act).cuda().to(torch.bfloat16), torch.from_numpy(gg).cuda()
+    L.check(lib.sr_head1x1_bwd(L.ptr(xd), L.ptr(ad), L.ptr(gd), None, 500, L.ptr(dw), L.ptr(db), L.stream_ptr()))
+    g0 = gg.astype(np.float64) * (act > 0)
+    assert np.abs(dw.cpu().numpy() - x.astype(np.float64).T @ g0).max() <= 1e-3
+    assert np.abs(db.cpu().numpy() - g0.sum(0)).max() <= 1e-3
+
+
+def test_adam_step_matches_keras_formula(lib):
+    from oracle import model as om
+    from sr100 import _lib as L
+    rng = np.random.default_rng(1)
+    n = 10007
+    p0 = rng.normal(0, 1, n).astype(np.float32)
+    p = torch.from_numpy(p0.copy()).cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pt = torch.from_numpy(p0.copy())
+    opt = om.KerasAdam([pt])
+    for t in range(1, 4):
+        g = rng.normal(0, 1e-3, n).astype(np.float32)
+        g2 = torch.from_numpy(2 * g).cuda()
+        L.check(lib.sr_adam_step(L.ptr(p), L.ptr(g2), L.ptr(m), L.ptr(v), n, 1e-4, 0.9, 0.999, 1e-7, t, 0.5,
+                                 L.stream_ptr()))
+        opt.step([torch.from_numpy(g)])
+        assert np.abs(p.cpu().numpy() - pt.numpy()).max() <= 1e-6
+
+
+def _rel(a, b):
+    a, b = a.astype(np.float64).ravel(), b.astype(np.float64).ravel()
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30), float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
+
+
+def test_train_step_gradients_match_oracle():
+    """One train_on_batch: loss and every layer's gradient against torch-CPU autograd on the oracle graph."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    from sr100.train import Trainer
+    weights = om.init_weights(1234, bias_scale=0.01)
+    rng = np.random.default_rng(7)
+    x = rng.random((2, 12, 12, 3)).astype(np.float32)
+    y = rng.random((2, 48, 48, 3)).astype(np.float32)
+    eng = Engine(weights)
+    tr = Trainer(eng)
+    g = tr.graph(2, 12, 12)
+    tr._load(g, x, y)
+    tr.forward_backward_device(g)
+    torch.cuda.synchronize()
+    loss = g.loss_sum.item() / g.n_local
+    got = tr.grads_dict()
+
+    m = om.DifvdsrDoubleOracle(weights)
+    pred = m(torch.from_numpy(x))
+    want_loss = om.mse_loss(pred, torch.from_numpy(y))
+    params = list(m.parameters())
+    grads = torch.autograd.grad(want_loss, params)
+    byname = {}
+    names = [s[0] for s in om.layer_specs()]
+    for (pname, _), gr in zip(m.named_parameters(), grads):
+        kind, lname = pname.split(".")
+        byname.setdefault(lname, {})[kind] = gr.numpy()
+    assert abs(loss - float(want_loss.detach())) <= 2e-3 * float(want_loss.detach())
+    worst = 0.0
+    for name in names:
+        gw = np.transpose(byname[name]["w"], (2, 3, 1, 0))     # OIHW -> HWIO
+        rel, cos = _rel(got[name][0], gw)
+        worst = max(worst, rel)
+        assert cos >= 0.995 and rel <= 0.1, (name, rel, cos)
+        relb, cosb = _rel(got[name][1], byname[name]["b"])
+        assert cosb >= 0.995 and relb <= 0.1, (name, "bias", relb, cosb)
+    assert worst <= 0.1
+
+
+def test_training_reduces_loss_and_model_facade():
+    """Keras-style facade: compile + train_on_batch on a fixed batch drives the loss down; weights change."""
+    import models
+    m = models.DifvdsrDouble(1)
+    model = m.create_model(8, 8)
+    rng = np.random.default_rng(2)
+    y = rng.random((4, 32, 32, 3)).astype(np.float32)
+    x = y.reshape(4, 8, 4, 8, 4, 3).mean(axis=(2, 4)).astype(np.float32)
+    w0 = model.get_weights()[2].copy()
+    losses = [model.train_on_batch(x, y) for _ in range(6)]
+    assert all(np.isfinite(losses))
+    assert losses[-1] < losses[0]
+    assert not np.array_equal(model.get_weights()[2], w0)
+    out = model.predict(x)
+    assert out.shape == (4, 32, 32, 3)

@@ -1,0 +1,124 @@
+"""Achieved HBM bandwidth of the bandwidth-bound kernels of the hot path (algorithmic bytes =
+compulsory reads + writes at the boundary dtypes), against MEASURED_PEAKS.json hbm_gbs.
+
+    python tools/probe_bw.py [--out gpurun_out/probe_bw.jsonl]
+
+Sizes follow the configs: LR stage of 186 tiles of 96x96 (config 2), one 339x510 image (config 3), a
+1356x2040 output pair for the scoring kernel, the 21.84 M-parameter arena for Adam.  Every timed buffer set is
+larger than the 126 MB L2 or rotated so that the inputs come from HBM."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "image-enhance-keras_b200"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe_bw.jsonl"))
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    import torch
+    from sr100 import _lib as L
+    from sr100 import ops
+    lib = L.require_device()
+    peak = 6551.0
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = json.load(open(p))["hbm_gbs"]
+    dev = "cuda"
+    st = L.stream_ptr
+    recs = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed(name, nbytes, fn, note=""):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(a.iters):
+            flush.fill_(1)              # evict L2 (256 MB write) between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        ms = tot / a.iters
+        gbs = nbytes / ms / 1e6
+        rec = dict(kernel=name, algorithmic_bytes=int(nbytes), ms=round(ms, 4), gbs=round(gbs, 1),
+                   frac_of_hbm_peak=round(gbs / peak, 3), peak_gbs=peak, note=note)
+        recs.append(rec)
+        print(json.dumps(rec), flush=True)
+
+    # ---- bilinear x4 (fp32 LR stream in, bf16 HR out): 512 + 16*256 B per LR pixel
+    NB, H, W = 186, 96, 96
+    x32 = torch.randn(NB, H, W, 128, device=dev)
+    hr16 = torch.empty(NB, 4 * H, 4 * W, 128, device=dev, dtype=torch.bfloat16)
+    timed("bilinear4_fwd_kernel<f32->bf16>", NB * H * W * (512 + 16 * 256),
+          lambda: L.check(lib.sr_bilinear4_fwd(L.ptr(x32), 0, NB, H, W, 128, L.ptr(hr16), None, st())),
+          "186 tiles of 96x96x128")
+    del hr16
+    # ---- bilinear adjoint (fp32 HR grad in, fp32 LR grad out), 32 tiles
+    NB2 = 32
+    g32 = torch.randn(NB2, 4 * H, 4 * W, 128, device=dev)
+    gin = torch.empty(NB2, H, W, 128, device=dev)
+    timed("bilinear4_bwd_kernel", NB2 * H * W * (16 * 512 + 512),
+          lambda: L.check(lib.sr_bilinear4_bwd(L.ptr(g32), NB2, H, W, 128, L.ptr(gin), st())), "32 tiles")
+    del g32, gin
+    # ---- head 1x1: 12 B in, 256 + 512 B out per pixel
+    xin = torch.rand(NB, H, W, 3, device=dev)
+    s16 = torch.empty(NB, H, W, 128, device=dev, dtype=torch.bfloat16)
+    w0, b0 = torch.randn(3, 128, device=dev), torch.randn(128, device=dev)
+    timed("head1x1_kernel", NB * H * W * (12 + 256 + 512),
+          lambda: L.check(lib.sr_head1x1_fwd(L.ptr(xin), L.ptr(w0), L.ptr(b0), NB * H * W, L.ptr(s16), L.ptr(x32), st())))
+    # ---- patch gather: 64 images of 339x510 (config 3) -> 54 tiles each
+    imgs = [torch.randint(0, 256, (339, 510, 3), dtype=torch.uint8, device=dev) for _ in range(8)]
+    ch, cw = ops.canvas_size(339, 510)
+
+    def gather_all():
+        for im in imgs:
+            ops.patch_gather_u8(im, (ch, cw), (96, 96), 64)
+    timed("patch_gather_kernel<u8> x8 images", 8 * (339 * 510 * 3 + 54 * 96 * 96 * 3 * 4), gather_all,
+          "8 launches of 339x510 -> 54 tiles; includes the output allocation")
+    # ---- stitch + quantise: 54 tiles of 384x384x3 fp32 -> uint8 canvas (owned pixels only are compulsory)
+    outp = torch.rand(54, 384, 384, 3, device=dev)
+    cnt = (ops.patch_count(ch, 96, 64), ops.patch_count(cw, 96, 64))
+    timed("patch_stitch_kernel", 16 * ch * cw * 3 * (4 + 1),
+          lambda: ops.patch_stitch(outp, cnt, (96, 96), 64, 4, (ch, cw), mul=255.0, want_f32=False, want_u8=True),
+          "one 339x510 image (448x640 canvas x4); 15 B per output pixel")
+    # ---- scoring: two uint8 1356x2040 RGB images
+    a8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)
+    b8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)
+    res = torch.zeros(64, dtype=torch.uint8, device=dev)
+    timed("score_pair_kernel", 2 * 1356 * 2040 * 3,
+          lambda: L.check(lib.sr_score_pair_u8(L.ptr(a8), L.ptr(b8), 1356, 2040, 10, L.ptr(res), st())),
+          "one 1356x2040 pair (Y-PSNR + Y-SSIM + RGB-SSIM fused)")
+    # ---- Adam over the whole parameter arena: 4 reads + 3 writes fp32
+    n = 21838211
+    pp, gg, mm, vv = (torch.randn(n, device=dev) for _ in range(4))
+    vv.abs_()
+    timed("adam_kernel", n * 28,
+          lambda: L.check(lib.sr_adam_step(L.ptr(pp), L.ptr(gg), L.ptr(mm), L.ptr(vv), n, 1e-4, 0.9, 0.999, 1e-7, 3, 1.0, st())))
+    # ---- training elementwise
+    g16 = torch.randn(NB * H * W, 128, device=dev).to(torch.bfloat16)
+    acc = torch.zeros(128, device=dev)
+    timed("colsum_bf16_kernel", NB * H * W * 256,
+          lambda: L.check(lib.sr_colsum_bf16(L.ptr(g16), NB * H * W, 1.0, L.ptr(acc), st())))
+    npix = 32 * 384 * 384
+    pred, tgt = torch.rand(npix, 3, device=dev), torch.rand(npix, 3, device=dev)
+    g128 = torch.empty(npix, 128, device=dev, dtype=torch.bfloat16)
+    ls = torch.zeros(1, device=dev, dtype=torch.float64)
+    timed("mse_tail_grad_kernel", npix * (24 + 256),
+          lambda: L.check(lib.sr_mse_tail_grad(L.ptr(pred), L.ptr(tgt), npix, 3, npix * 3, L.ptr(g128), L.ptr(ls), st())))
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    with open(a.out, "w") as f:
+        for r in recs:
+            f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

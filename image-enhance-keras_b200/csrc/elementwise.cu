@@ -78,42 +78,57 @@ __device__ __forceinline__ void load8(const void* base, size_t elem_off, float (
   }
 }
 
+// One thread = one LR cell (y0,x0) x 8 channels: the four corner values are loaded once and the 4x4 HR
+// outputs of the cell are produced from them (top/bot interpolants shared by the four output rows: the
+// arithmetic per output is exactly the three-lerp TF formula above).  16 lanes cover the 128 channels of a
+// pixel, so every store instruction writes whole 256 B (bf16) / 512 B (fp32) pixels.
 template <bool IN_BF16>
-__global__ void bilinear4_fwd_kernel(const void* __restrict__ in, int NB, int H, int W, int C,
-                                     uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+__global__ void __launch_bounds__(256)
+bilinear4_fwd_kernel(const void* __restrict__ in, int NB, int H, int W, int C,
+                     uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
   const int C8 = C >> 3;
-  const int OH = 4 * H, OW = 4 * W;
-  const size_t total = (size_t)NB * OH * OW * C8;
+  const int OW = 4 * W;
+  const size_t total = (size_t)NB * H * W * C8;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % C8);
     size_t r = idx / C8;
-    const int X = (int)(r % OW);
-    r /= OW;
-    const int Y = (int)(r % OH);
-    const int n = (int)(r / OH);
-    const int y0 = Y >> 2, x0 = X >> 2;
-    const float ty = (float)(Y & 3) * 0.25f, tx = (float)(X & 3) * 0.25f;
-    const int y1 = ((Y & 3) == 0) ? y0 : min(y0 + 1, H - 1);
-    const int x1 = ((X & 3) == 0) ? x0 : min(x0 + 1, W - 1);
+    const int x0 = (int)(r % W);
+    r /= W;
+    const int y0 = (int)(r % H);
+    const int n = (int)(r / H);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
     const size_t rowb0 = ((size_t)n * H + y0) * W, rowb1 = ((size_t)n * H + y1) * W;
-    float tl[8], tr[8], bl[8], br[8], o[8];
+    float tl[8], tr[8], bl[8], br[8];
     load8<IN_BF16>(in, (rowb0 + x0) * C + c8 * 8, tl);
     load8<IN_BF16>(in, (rowb0 + x1) * C + c8 * 8, tr);
     load8<IN_BF16>(in, (rowb1 + x0) * C + c8 * 8, bl);
     load8<IN_BF16>(in, (rowb1 + x1) * C + c8 * 8, br);
+    const size_t obase = (((size_t)n * 4 * H + 4 * y0) * OW + 4 * x0) * C8 + c8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float top = lerp_tf(tl[j], tr[j], tx);
-      const float bot = lerp_tf(bl[j], br[j], tx);
-      o[j] = lerp_tf(top, bot, ty);
-    }
-    if (out_bf16)
-      out_bf16[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-    if (out_f32) {
-      out_f32[idx * 2] = make_float4(o[0], o[1], o[2], o[3]);
-      out_f32[idx * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    for (int fx = 0; fx < 4; ++fx) {
+      const float tx = (float)fx * 0.25f;
+      float top[8], bot[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        top[j] = lerp_tf(tl[j], tr[j], tx);
+        bot[j] = lerp_tf(bl[j], br[j], tx);
+      }
+#pragma unroll
+      for (int fy = 0; fy < 4; ++fy) {
+        const float ty = (float)fy * 0.25f;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = lerp_tf(top[j], bot[j], ty);
+        const size_t oi = obase + ((size_t)fy * OW + fx) * C8;
+        if (out_bf16)
+          out_bf16[oi] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                    pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        if (out_f32) {
+          out_f32[oi * 2] = make_float4(o[0], o[1], o[2], o[3]);
+          out_f32[oi * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
     }
   }
 }
@@ -130,9 +145,12 @@ __device__ __forceinline__ float axis_weight(int Q, int q, int n) {
   return w;
 }
 
-// Adjoint (gather form, deterministic): gin[y,x] = sum_{Y,X} wy(Y,y) wx(X,x) gout[Y,X].
-__global__ void bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, int H, int W, int C,
-                                     float4* __restrict__ gin) {
+// Adjoint (gather form, deterministic): gin[y,x] = sum_{Y,X} wy(Y,y) wx(X,x) gout[Y,X] over the 7x7 HR
+// window [4y-3,4y+3] x [4x-3,4x+3].  A warp covers the 128 channels of one pixel (512 B per load); the seven
+// loads of a window row are issued together.
+__global__ void __launch_bounds__(256)
+bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, int H, int W, int C,
+                     float4* __restrict__ gin) {
   const int C4 = C >> 2;
   const int OH = 4 * H, OW = 4 * W;
   const size_t total = (size_t)NB * H * W * C4;
@@ -144,18 +162,32 @@ __global__ void bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, in
     r /= W;
     const int y = (int)(r % H);
     const int n = (int)(r / H);
+    float wx[7];
+    int xi[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int X = 4 * x - 3 + j;
+      const bool ok = X >= 0 && X < OW;
+      xi[j] = ok ? X : 4 * x;
+      wx[j] = ok ? axis_weight(X, x, W) : 0.f;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int Y = max(4 * y - 3, 0); Y <= min(4 * y + 3, OH - 1); ++Y) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int Y = 4 * y - 3 + i;
+      if (Y < 0 || Y >= OH) continue;
       const float wy = axis_weight(Y, y, H);
-      if (wy == 0.f) continue;
-      for (int X = max(4 * x - 3, 0); X <= min(4 * x + 3, OW - 1); ++X) {
-        const float wgt = wy * axis_weight(X, x, W);
-        if (wgt == 0.f) continue;
-        const float4 g = gout[(((size_t)n * OH + Y) * OW + X) * C4 + c4];
-        acc.x = fmaf(wgt, g.x, acc.x);
-        acc.y = fmaf(wgt, g.y, acc.y);
-        acc.z = fmaf(wgt, g.z, acc.z);
-        acc.w = fmaf(wgt, g.w, acc.w);
+      const float4* row = gout + ((size_t)n * OH + Y) * OW * C4 + c4;
+      float4 g[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) g[j] = row[(size_t)xi[j] * C4];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float wgt = wy * wx[j];
+        acc.x = fmaf(wgt, g[j].x, acc.x);
+        acc.y = fmaf(wgt, g[j].y, acc.y);
+        acc.z = fmaf(wgt, g[j].z, acc.z);
+        acc.w = fmaf(wgt, g[j].w, acc.w);
       }
     }
     gin[idx] = acc;
@@ -188,6 +220,37 @@ __global__ void patch_gather_kernel(const void* __restrict__ src, int h, int w, 
       v = reinterpret_cast<const float*>(src)[((size_t)y * canvas_w + x) * 3 + c];
     }
     out[idx] = divisor == 1.f ? v : __fdiv_rn(v, divisor);
+  }
+}
+
+// Same gather, four consecutive elements of a patch row per thread (one 16-byte store); needs 3*pw % 4 == 0.
+template <bool FROM_U8>
+__global__ void patch_gather_vec4_kernel(const void* __restrict__ src, int h, int w, int canvas_w,
+                                         int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,
+                                         float4* __restrict__ out) {
+  const int row_q = pw * 3 / 4;
+  const size_t total = (size_t)cnt_h * cnt_w * ph * row_q;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % row_q);
+    size_t r = idx / row_q;
+    const int i = (int)(r % ph);
+    const int n = (int)(r / ph);
+    const int wi = n / cnt_h, hi = n - wi * cnt_h;
+    const int y = hi * step + i;
+    const int e0 = wi * step * 3 + q * 4;  // element offset inside canvas row y
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = e0 + j;
+      if (FROM_U8) {
+        v[j] = (y < h && e < w * 3) ? (float)reinterpret_cast<const uint8_t*>(src)[(size_t)y * w * 3 + e] : 0.f;
+      } else {
+        v[j] = reinterpret_cast<const float*>(src)[(size_t)y * canvas_w * 3 + e];
+      }
+      if (divisor != 1.f) v[j] = __fdiv_rn(v[j], divisor);
+    }
+    out[idx] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -226,6 +289,40 @@ __global__ void patch_stitch_kernel(const float* __restrict__ patches, int cnt_h
       // np.clip(result, 0, 255).astype('uint8'): clamp then truncate toward zero (models.py:391)
       const float cl = fminf(fmaxf(v, 0.f), 255.f);
       out_u8[idx] = (uint8_t)(int)cl;
+    }
+  }
+}
+
+// Four consecutive output elements per thread (16-byte patch load, 4-byte uint8 store).  Valid when every
+// ownership boundary and row length is a multiple of 4 elements: 3*S, 3*crop, 3*PW, 3*out_w all % 4 == 0
+// (true for the reference's 96/64/x4/8-px geometry); the host falls back to the scalar kernel otherwise.
+__global__ void patch_stitch_vec4_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH,
+                                         int PW, int S, int crop, int out_h, int out_w, float mul,
+                                         float4* __restrict__ out_f32, uint32_t* __restrict__ out_u8) {
+  const int row_q = out_w * 3 / 4;
+  const size_t total = (size_t)out_h * row_q;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % row_q);
+    const int Y = (int)(idx / row_q);
+    const int e = q * 4;
+    const int X = e / 3;
+    const int i = stitch_owner(Y, cnt_h, S, PH, crop);
+    const int j = stitch_owner(X, cnt_w, S, PW, crop);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= 0 && j >= 0) {
+      const size_t n = (size_t)j * cnt_h + i;
+      const float4 p = *reinterpret_cast<const float4*>(
+          patches + ((n * PH + (Y - S * i)) * PW) * 3 + (e - 3 * S * j));
+      v = make_float4(__fmul_rn(p.x, mul), __fmul_rn(p.y, mul), __fmul_rn(p.z, mul), __fmul_rn(p.w, mul));
+    }
+    if (out_f32) out_f32[idx] = v;
+    if (out_u8) {
+      const uint32_t b0 = (uint32_t)(int)fminf(fmaxf(v.x, 0.f), 255.f);
+      const uint32_t b1 = (uint32_t)(int)fminf(fmaxf(v.y, 0.f), 255.f);
+      const uint32_t b2 = (uint32_t)(int)fminf(fmaxf(v.z, 0.f), 255.f);
+      const uint32_t b3 = (uint32_t)(int)fminf(fmaxf(v.w, 0.f), 255.f);
+      out_u8[idx] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
   }
 }
@@ -402,7 +499,7 @@ extern "C" int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, i
   if (!in || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: null pointer");
   if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_fwd: C must be a multiple of 8");
   if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: empty tensor");
-  const size_t total = (size_t)NB * H * W * 16 * (C / 8);
+  const size_t total = (size_t)NB * H * W * (C / 8);
   const unsigned g = grid_for(total, kBlock, 148 * 32);
   if (in_is_bf16)
     bilinear4_fwd_kernel<true><<<g, kBlock, 0, as_stream(stream)>>>(
@@ -451,6 +548,11 @@ extern "C" int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h
   const int cnt_h = sr_patch_count(canvas_h, ph, step), cnt_w = sr_patch_count(canvas_w, pw, step);
   const size_t total = (size_t)cnt_h * cnt_w * ph * pw * 3;
   if (total == 0) return SR_OK;
+  if ((pw * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
+    patch_gather_vec4_kernel<true><<<grid_for(total / 4, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+        img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, reinterpret_cast<float4*>(out_f32));
+    return check_launch("patch_gather_vec4_kernel<u8>");
+  }
   patch_gather_kernel<true><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
       img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, out_f32);
   return check_launch("patch_gather_kernel<u8>");
@@ -476,8 +578,18 @@ extern "C" int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int p
   if (cnt_h < 1 || cnt_w < 1 || scale < 1) return set_error(SR_ERR_INVALID, "sr_patch_stitch: bad counts");
   const int out_h = canvas_h * scale, out_w = canvas_w * scale;
   const size_t total = (size_t)out_h * out_w * 3;
+  const int S = step * scale, PW = pw * scale, crop = 8;
+  const bool vec_ok = (3 * S) % 4 == 0 && (3 * crop) % 4 == 0 && (3 * PW) % 4 == 0 && (3 * out_w) % 4 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(patches) | reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0;
+  if (vec_ok) {
+    patch_stitch_vec4_kernel<<<grid_for(total / 4, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+        patches, cnt_h, cnt_w, ph * scale, PW, S, crop, out_h, out_w, mul, reinterpret_cast<float4*>(out_f32),
+        reinterpret_cast<uint32_t*>(out_u8));
+    return check_launch("patch_stitch_vec4_kernel");
+  }
   patch_stitch_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
-      patches, cnt_h, cnt_w, ph * scale, pw * scale, step * scale, 8, out_h, out_w, mul, out_f32, out_u8);
+      patches, cnt_h, cnt_w, ph * scale, PW, S, crop, out_h, out_w, mul, out_f32, out_u8);
   return check_launch("patch_stitch_kernel");
 }
 

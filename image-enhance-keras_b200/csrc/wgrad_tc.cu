@@ -123,28 +123,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------ TMA producer: input rows (ring) and gradient rows
     if (lane == 0 && has_work) {
-      uint32_t aq = 0, bq = 0;  // running row counters -> ring slot + phase
+      uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0;  // ring positions (slot + phase parity)
       for (int u = rank; u < units; u += ncta) {
         int n, x0, y0, rows;
         decode(u, &n, &x0, &y0, &rows);
         int next_in = y0 + kymin - P.p;  // next input row to load
         for (int y = y0; y < y0 + rows; ++y) {
           const int need = y + kymax - P.p;  // newest input row this output row reads
-          for (; next_in <= need; ++next_in, ++aq) {
-            const uint32_t slot = aq % (uint32_t)P.nring, ph = (aq / (uint32_t)P.nring) & 1u;
-            mbar_wait(&bars->a_empty[slot], ph ^ 1u);
-            mbar_expect_tx(&bars->a_full[slot], a_row_bytes);
-            uint8_t* dst = a_buf + (size_t)slot * a_row_bytes;
-            tma_load_4d(dst, &tmX, &bars->a_full[slot], 0, x0 - P.p, next_in, n);
-            tma_load_4d(dst + a_row_bytes / 2, &tmX, &bars->a_full[slot], 64, x0 - P.p, next_in, n);
+          for (; next_in <= need; ++next_in) {
+            mbar_wait(&bars->a_empty[a_slot], a_ph ^ 1u);
+            mbar_expect_tx(&bars->a_full[a_slot], a_row_bytes);
+            uint8_t* dst = a_buf + (size_t)a_slot * a_row_bytes;
+            tma_load_4d(dst, &tmX, &bars->a_full[a_slot], 0, x0 - P.p, next_in, n);
+            tma_load_4d(dst + a_row_bytes / 2, &tmX, &bars->a_full[a_slot], 64, x0 - P.p, next_in, n);
+            if (++a_slot == (uint32_t)P.nring) {
+              a_slot = 0;
+              a_ph ^= 1u;
+            }
           }
-          const uint32_t slot = bq % (uint32_t)P.nbslots, ph = (bq / (uint32_t)P.nbslots) & 1u;
-          mbar_wait(&bars->b_empty[slot], ph ^ 1u);
-          mbar_expect_tx(&bars->b_full[slot], b_row_bytes);
-          uint8_t* dst = b_buf + (size_t)slot * b_row_bytes;
-          tma_load_4d(dst, &tmG, &bars->b_full[slot], 0, x0, y, n);
-          tma_load_4d(dst + b_row_bytes / 2, &tmG, &bars->b_full[slot], 64, x0, y, n);
-          ++bq;
+          mbar_wait(&bars->b_empty[b_slot], b_ph ^ 1u);
+          mbar_expect_tx(&bars->b_full[b_slot], b_row_bytes);
+          uint8_t* dst = b_buf + (size_t)b_slot * b_row_bytes;
+          tma_load_4d(dst, &tmG, &bars->b_full[b_slot], 0, x0, y, n);
+          tma_load_4d(dst + b_row_bytes / 2, &tmG, &bars->b_full[b_slot], 64, x0, y, n);
+          if (++b_slot == (uint32_t)P.nbslots) {
+            b_slot = 0;
+            b_ph ^= 1u;
+          }
         }
       }
     }
@@ -154,64 +159,90 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const bool leader = elect_one();
       // MN-major SW128 descriptors: LBO = bytes between the two 64-channel halves, SBO = 8 pixel rows
       const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW128 << 29);
+      const uint32_t a_row16 = a_row_bytes >> 4, b_row16 = b_row_bytes >> 4;
       const uint32_t a_lo0 = (smem_u32(a_buf) >> 4) | (((a_row_bytes / 2) >> 4) << 16);
       const uint32_t b_lo0 = (smem_u32(b_buf) >> 4) | (((b_row_bytes / 2) >> 4) << 16);
       const int k16n = P.BW >> 4;
-      uint32_t aq = 0, bq = 0;  // counters at the START of the current unit / current row
+      const uint32_t nring = (uint32_t)P.nring, nbs = (uint32_t)P.nbslots;
+      // per-tap ring-row offset (ky - kymin) and start-address shift (kx pixels x 128 B, >> 4)
+      uint32_t t_row[4], t_sh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tap = tap0 + (j < ntaps ? j : 0);
+        const int ky = tap / P.k, kx = tap - ky * P.k;
+        t_row[j] = (uint32_t)(ky - kymin);
+        t_sh[j] = (uint32_t)kx * 8u;
+      }
+      uint32_t base = 0;                   // ring slot of the oldest live input row (r = yy)
+      uint32_t new_slot = 0, new_ph = 0;   // ring position of the next input row to become full
+      uint32_t b_slot = 0, b_ph = 0;
       uint32_t started = 0;
       for (int u = rank; u < units; u += ncta) {
         int n, x0, y0, rows;
         decode(u, &n, &x0, &y0, &rows);
         for (int yy = 0; yy < rows; ++yy) {
-          // input rows of this unit are numbered r = 0 .. rows+span-1 (r = y_in - (y0+kymin-p)); output row yy
-          // reads r = yy .. yy+span.  Rows become full in order; wait for the ones not yet seen.
-          for (int r = (yy == 0 ? 0 : yy + span); r <= yy + span; ++r) {
-            const uint32_t q = aq + (uint32_t)r;
-            mbar_wait(&bars->a_full[q % (uint32_t)P.nring], (q / (uint32_t)P.nring) & 1u);
+          // rows become full in order; output row yy newly needs input row yy+span (rows 0..span at yy == 0)
+          for (int r = (yy == 0 ? 0 : span); r <= span; ++r) {
+            mbar_wait(&bars->a_full[new_slot], new_ph);
+            if (++new_slot == nring) {
+              new_slot = 0;
+              new_ph ^= 1u;
+            }
           }
-          const uint32_t bslot = bq % (uint32_t)P.nbslots;
-          mbar_wait(&bars->b_full[bslot], (bq / (uint32_t)P.nbslots) & 1u);
+          mbar_wait(&bars->b_full[b_slot], b_ph);
           tc_fence_after();
-          const uint32_t b_lo = b_lo0 + bslot * (b_row_bytes >> 4);
-          for (int j = 0; j < ntaps; ++j) {
-            const int tap = tap0 + j;
-            const int ky = tap / P.k, kx = tap - ky * P.k;
-            const uint32_t q = aq + (uint32_t)(yy + ky - kymin);
-            const uint32_t a_lo = a_lo0 + (q % (uint32_t)P.nring) * (a_row_bytes >> 4) + (uint32_t)kx * 8u;
-            const uint32_t d = tmem_base + (uint32_t)j * 128u;
-            for (int s = 0; s < k16n; ++s) {
-              if (leader) {
-                const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)s * 128u);
-                const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)(b_lo + (uint32_t)s * 128u);
-                umma_bf16(d, adesc, bdesc, kIdescMN, (started | (uint32_t)s) != 0u ? 1u : 0u);
+          const uint32_t b_lo = b_lo0 + b_slot * b_row16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < ntaps) {
+              uint32_t slot = base + t_row[j];
+              if (slot >= nring) slot -= nring;
+              uint32_t a_lo = a_lo0 + slot * a_row16 + t_sh[j];
+              uint32_t bl = b_lo;
+              const uint32_t d = tmem_base + (uint32_t)j * 128u;
+              uint32_t accf = started;
+              for (int s = 0; s < k16n; ++s) {
+                if (leader) {
+                  const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)a_lo;
+                  const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)bl;
+                  umma_bf16(d, adesc, bdesc, kIdescMN, accf);
+                }
+                accf = 1u;
+                a_lo += 128u;
+                bl += 128u;
               }
             }
           }
-          started = 1;
+          started = 1u;
           if (leader) {
-            umma_commit(&bars->b_empty[bslot]);
-            // the oldest input row (r = yy) is not read by later output rows
-            const uint32_t q = aq + (uint32_t)yy;
-            umma_commit(&bars->a_empty[q % (uint32_t)P.nring]);
-            if (yy == rows - 1) {
-              for (int r = rows; r < rows + span; ++r) {
-                const uint32_t q2 = aq + (uint32_t)r;
-                umma_commit(&bars->a_empty[q2 % (uint32_t)P.nring]);
-              }
-            }
+            umma_commit(&bars->b_empty[b_slot]);
+            umma_commit(&bars->a_empty[base]);  // the oldest input row is not read by later output rows
           }
-          ++bq;
+          if (++b_slot == nbs) {
+            b_slot = 0;
+            b_ph ^= 1u;
+          }
+          if (++base == nring) base = 0;
         }
-        aq += (uint32_t)(rows + span);
+        // the last `span` input rows of the unit are dead too
+        for (int r = 0; r < span; ++r) {
+          if (leader) umma_commit(&bars->a_empty[base]);
+          if (++base == nring) base = 0;
+        }
       }
       if (leader) umma_commit(&bars->acc_full);
+      // wait for the accumulators here (one polling warp), then release the drain warps from their
+      // hardware barrier: they sleep instead of polling an mbarrier for the whole kernel
+      mbar_wait(&bars->acc_full, 0);
     }
+    __syncwarp();
+    asm volatile("bar.sync 1, 160;" ::: "memory");
   } else if (warp >= 4) {
     // ------------------------------------------------ drain: TMEM -> partial[cta][tap][ci][co]
     const int ew = warp - 4;
     float* dst = P.partial + (size_t)blockIdx.x * 4 * kAccFloats;
+    asm volatile("bar.sync 1, 160;" ::: "memory");
     if (has_work) {
-      mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
       for (int j = 0; j < ntaps; ++j) {
         float* row = dst + (size_t)j * kAccFloats + (size_t)(ew * 32 + lane) * 128;

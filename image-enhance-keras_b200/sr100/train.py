@@ -49,6 +49,16 @@ class _WgradPlan:
             pass
 
 
+class _Op:
+    """A named launch (callable(stream)) so tools/bench_train.py can attribute step time per kernel kind."""
+
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __call__(self, st):
+        return self.fn(st)
+
+
 class _TrainGraph:
     """Buffers and launch lists (forward with saved activations, backward) for one (NB, H, W) minibatch shape."""
 
@@ -107,17 +117,18 @@ class _TrainGraph:
                 self.fwd_flops += p.flops
             else:
                 self.bwd_flops += p.flops
-            dst.append(p.run)
+            kind = ("dgrad" if flip else "conv") + "+".join("k%d" % eng.ksize[n] for n, _ in srcs)
+            dst.append(_Op("%s_%s" % (kind, "hr" if shape[1] != H else "lr"), p.run))
 
         def wgrad(x, g, shape, name, scale):
             p = _WgradPlan(lib, x, g, shape, eng.ksize[name], scale, tr.grad_w(name), tr.workspace)
             self.bwd_flops += p.flops
-            self.bwd.append(p.run)
+            self.bwd.append(_Op("wgrad_k%d_%s" % (eng.ksize[name], "hr" if shape[1] != H else "lr"), p.run))
 
         def colsum(g, shape, name, scale, also=None):
             npix = shape[0] * shape[1] * shape[2]
             db = tr.grad_b(name)
-            self.bwd.append(lambda st: L.check(lib.sr_colsum_bf16(L.ptr(g), npix, scale, L.ptr(db), st)))
+            self.bwd.append(_Op("colsum", lambda st: L.check(lib.sr_colsum_bf16(L.ptr(g), npix, scale, L.ptr(db), st))))
             if also is not None:
                 db2 = tr.grad_b(also)
                 self.bwd.append(lambda st: db2.copy_(db))
@@ -166,7 +177,7 @@ class _TrainGraph:
         # tail conv (128 -> 3): its gradient travels as a 128-channel tensor whose channels >= 3 are zero
         p = _WgradPlan(lib, SH[2], gth1, hr, 3, 1.0, tr.tail_dw128, tr.workspace)
         self.bwd_flops += p.flops * 3 / 128.0
-        self.bwd.append(p.run)
+        self.bwd.append(_Op("wgrad_tail", p.run))
         tail_w, tail_b = tr.grad_w(tail), tr.grad_b(tail)
         self.bwd.append(lambda st: tail_w.copy_(tr.tail_dw128[..., :3]))
         self.bwd.append(lambda st: tr.tail_db128.zero_())

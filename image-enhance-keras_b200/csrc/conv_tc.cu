@@ -61,11 +61,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& P, int 
   return c;
 }
 
-// Staged epilogue for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
+// Generic staged epilogue (any combination of residual / mask, all selected at run time) for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
 // 32-row x 256 B shared-memory tile as bf16 (16-byte chunks XOR-swizzled by row, conflict-free both
 // ways); phase 2 re-reads it with 16 lanes per pixel so that every global access of the residual,
 // mask and outputs is a fully coalesced 512 B (bf16) / 1 KB (fp32) warp transaction.
-__device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
+__device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelParams& P, const TileCoord& c,
                                                     uint32_t t_acc, int f_base, uint8_t* stage,
                                                     const float* s_bias, int lane, bool live = true) {
   // ---- phase 1: this lane's pixel row
@@ -161,9 +161,163 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
   __syncwarp();
 }
 
+// Specialised staged epilogue (EPI = which single global operand the epilogue reads; the host picks the generic
+// kernel for anything else) for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
+// 32-row x 256 B shared-memory tile as bf16 (16-byte chunks XOR-swizzled by row, conflict-free both
+// ways); phase 2 re-reads it with 16 lanes per pixel so that every global access of the residual,
+// mask and outputs is a fully coalesced 512 B (bf16) / 1 KB (fp32) warp transaction.
+template <int EPI>
+__device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
+                                                    uint32_t t_acc, int f_base, uint8_t* stage,
+                                                    const float* s_bias, int lane, bool live = true) {
+  // ---- phase 1: this lane's pixel row
+  const int f = f_base + lane;
+  const int fr = f / P.PWs;
+  const int yy = fr - P.p;
+  const int xx = f - fr * P.PWs - P.p;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
+  // ---- operand prefetch: every global read of the epilogue (residual or ReLU mask) is issued here, before the
+  // TMEM drain, so that one DRAM latency is exposed per accumulator instead of one per unrolled group.
+  // pre[] holds: fp32 residual of pixel pairs 0..7 (2 x 16 B each; pairs 8..15 are fetched between the passes),
+  // or the bf16 residual / the mask of all 16 pairs.
+  const int half = lane >> 4, q = lane & 15;
+  int pixs[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pixs[i] = __shfl_sync(0xffffffffu, my_pix, 2 * i + half);
+  constexpr int pf_mode = EPI;  // 0: no global operand, 1: fp32 residual, 2: bf16 residual, 3: ReLU mask
+  uint4 pre[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (pf_mode == 1) {
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const int pix = pixs[ii];
+      if (pix >= 0) {
+        const uint4* rp = reinterpret_cast<const uint4*>(P.res_f32 + (size_t)pix * 128 + q * 8);
+        pre[2 * ii] = rp[0];
+        pre[2 * ii + 1] = rp[1];
+      }
+    }
+  } else if (pf_mode != 0) {
+    const __nv_bfloat16* src = pf_mode == 2 ? P.res_bf16 : P.relu_mask_bf16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int pix = pixs[i];
+      if (pix >= 0) pre[i] = *reinterpret_cast<const uint4*>(src + (size_t)pix * 128 + q * 8);
+    }
+  }
+  uint8_t* my_row = stage + lane * 256;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(t_acc + cb * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q * 8 + e * 2;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  __syncwarp();
+  // ---- phase 2: 16 lanes per pixel, 2 pixels per warp instruction; two passes of 8 pixel pairs whose
+  // residual / mask operands were all requested up front (pre[])
+  float bs[8];  // alpha * bias of this lane's 8 channels
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = P.alpha * s_bias[q * 8 + e];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && pf_mode == 1) {
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int pix = pixs[8 + ii];
+        if (pix >= 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(P.res_f32 + (size_t)pix * 128 + q * 8);
+          pre[2 * ii] = rp[0];
+          pre[2 * ii + 1] = rp[1];
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const int i = pass * 8 + ii;
+      const int r = 2 * i + half;
+      const int pix = pixs[i];
+      if (pix < 0) continue;
+      const uint4 sv = *reinterpret_cast<const uint4*>(stage + r * 256 + ((q ^ (r & 7)) << 4));
+      const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[2 * e] = fmaf(P.alpha, __uint_as_float(w[e] << 16), bs[2 * e]);
+        o[2 * e + 1] = fmaf(P.alpha, __uint_as_float(w[e] & 0xFFFF0000u), bs[2 * e + 1]);
+      }
+      const size_t off = (size_t)pix * 128 + q * 8;
+      if (pf_mode == 1) {
+        const uint4 r0 = pre[2 * ii], r1 = pre[2 * ii + 1];
+        o[0] = fmaf(P.beta, __uint_as_float(r0.x), o[0]); o[1] = fmaf(P.beta, __uint_as_float(r0.y), o[1]);
+        o[2] = fmaf(P.beta, __uint_as_float(r0.z), o[2]); o[3] = fmaf(P.beta, __uint_as_float(r0.w), o[3]);
+        o[4] = fmaf(P.beta, __uint_as_float(r1.x), o[4]); o[5] = fmaf(P.beta, __uint_as_float(r1.y), o[5]);
+        o[6] = fmaf(P.beta, __uint_as_float(r1.z), o[6]); o[7] = fmaf(P.beta, __uint_as_float(r1.w), o[7]);
+      } else if (pf_mode == 2) {
+        const uint4 rv = pre[i];
+        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[2 * e] = fmaf(P.beta, __uint_as_float(rw[e] << 16), o[2 * e]);
+          o[2 * e + 1] = fmaf(P.beta, __uint_as_float(rw[e] & 0xFFFF0000u), o[2 * e + 1]);
+        }
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      }
+      if (pf_mode == 3) {
+        const uint4 mv = pre[i];
+        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!(__uint_as_float(mw[e] << 16) > 0.f)) o[2 * e] = 0.f;
+          if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f)) o[2 * e + 1] = 0.f;
+        }
+      }
+      if (P.out_f32) {
+        *reinterpret_cast<float4*>(P.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(P.out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (P.out_bf16) {
+        uint32_t pw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+          pw[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(P.out_bf16 + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
+                                             int f_base, uint8_t* stage, const float* s_bias, int lane,
+                                             bool live = true) {
+  if constexpr (EPI < 0) epilogue_staged_acc_generic(P, c, t_acc, f_base, stage, s_bias, lane, live);
+  else epilogue_staged_acc<EPI>(P, c, t_acc, f_base, stage, s_bias, lane, live);
+}
+
 }  // namespace
 
-template <int N_, int AMODE, int NACC, int NBUF>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
@@ -362,8 +516,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
         if constexpr (N_ == 128) {
-          epilogue_staged_acc(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
-                              stage_buf + ew * (32 * 256), s_bias, lane);
+          epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
+                            stage_buf + ew * (32 * 256), s_bias, lane);
         } else {
           const int f = c.f0 + acc * 128 + ew * 32 + lane;
           const int fr = f / P.PWs;
@@ -409,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // and L2 -> SM weight traffic halves.  The leader CTA (rank 0) owns the full-barriers and issues;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
 // =====================================================================================
-template <int NACC, int NBUF>
+template <int NACC, int NBUF, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
@@ -608,8 +762,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc)
-        epilogue_staged_acc(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
-                            stage_buf + ew * (32 * 256), s_bias, lane, live);
+        epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
+                          stage_buf + ew * (32 * 256), s_bias, lane, live);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
@@ -748,9 +902,9 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
   return best_eff > 0;
 }
 
-template <int N_, int AMODE, int NACC, int NBUF>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1>
 static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF>;
+  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -765,9 +919,9 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   return SR_OK;
 }
 
-template <int NACC, int NBUF>
+template <int NACC, int NBUF, int EPI = -1>
 static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_pair_kernel<NACC, NBUF>;
+  auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -874,11 +1028,29 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   if (!plan) return set_error(SR_ERR_INVALID, "sr_conv_plan_run: null plan");
   const ConvPlan* pl = reinterpret_cast<const ConvPlan*>(plan);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (pl->pair) return pl->nacc == 4 ? launch_pair<4, 1>(pl, st) : launch_pair<2, 2>(pl, st);
+  // epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
+  const ConvKernelParams& P = pl->P;
+  const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
+  const int epi = nops != 1 ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  if (pl->pair) {
+    if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
+    switch (epi) {
+      case 1: return launch_pair<2, 2, 1>(pl, st);
+      case 2: return launch_pair<2, 2, 2>(pl, st);
+      case 3: return launch_pair<2, 2, 3>(pl, st);
+      default: return launch_pair<2, 2>(pl, st);
+    }
+  }
   if (pl->n_pad == 128) {
-    if (pl->amode == kAModeSwizzle64)
-      return pl->nacc == 4 ? launch_variant<128, kAModeSwizzle64, 4, 1>(pl, st)
-                           : launch_variant<128, kAModeSwizzle64, 2, 2>(pl, st);
+    if (pl->amode == kAModeSwizzle64) {
+      if (pl->nacc == 4) return launch_variant<128, kAModeSwizzle64, 4, 1>(pl, st);
+      switch (epi) {
+        case 1: return launch_variant<128, kAModeSwizzle64, 2, 2, 1>(pl, st);
+        case 2: return launch_variant<128, kAModeSwizzle64, 2, 2, 2>(pl, st);
+        case 3: return launch_variant<128, kAModeSwizzle64, 2, 2, 3>(pl, st);
+        default: return launch_variant<128, kAModeSwizzle64, 2, 2>(pl, st);
+      }
+    }
     return pl->nacc == 4 ? launch_variant<128, kAModeInterleave, 4, 1>(pl, st)
                          : launch_variant<128, kAModeInterleave, 2, 2>(pl, st);
   }

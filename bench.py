@@ -273,11 +273,9 @@ def main():
         threads = os.cpu_count() or 1
         v, sample, _ = cpu_reference_rate(threads)
         cpu = {"value": round(v, 5), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-    # upscale_arrays: uint8 images in, uncropped uint8 canvases out; scorpath.score_pair: GT + SR in, scores out
-    canvas_bytes = sum(16 * 3 * ops.canvas_size(h, w, 96, 64)[0] * ops.canvas_size(h, w, 96, 64)[1]
-                       for h, w in SET5_SHAPES)
+    # upscale_arrays: uint8 images in, cropped uint8 x4 images out (pinned); scorpath.score_pair: GT + SR in, scores out
     h2d = sum(im.nbytes for im in images) + sum(g_.nbytes for g_ in gts) + sum(16 * im.nbytes for im in images)
-    d2h = canvas_bytes + 5 * 56
+    d2h = sum(16 * im.nbytes for im in images) + 5 * 56
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True,
@@ -293,5 +291,17 @@ def main():
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

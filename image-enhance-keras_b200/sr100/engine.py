@@ -86,6 +86,8 @@ class _Graph:
     def __init__(self, eng, NB, H, W):
         dev = eng.device
         bf, f32 = torch.bfloat16, torch.float32
+        self.eng = eng
+        self.cuda_graph, self.ran_eager = None, False
         self.NB, self.H, self.W = NB, H, W
         self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
         self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=bf)
@@ -161,9 +163,27 @@ class _Graph:
         conv([(names[i], self.s_hr)], out_f32=self.out, relu=1, shape=hr, cout=3)
 
     def run(self):
+        """One forward over the resident x_in.  The launch sequence is fixed (plans are bound to these buffers), so
+        after one eager run it is captured into a CUDA graph and replayed: one submission instead of ~70 ctypes
+        launches (matters for small inputs such as a single 128x128 patch, where launches cost as much as math)."""
+        eng = self.eng
+        if eng.use_graphs and self.cuda_graph is not None:
+            self.cuda_graph.replay()
+            return self.out
         st = L.stream_ptr()
         for step in self.steps:
             step(st)
+        if eng.use_graphs and self.cuda_graph is None and self.ran_eager and not torch.cuda.is_current_stream_capturing():
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    cst = L.stream_ptr()
+                    for step in self.steps:
+                        step(cst)
+                self.cuda_graph = gr
+            except Exception:  # noqa: BLE001  (capture unsupported in this context: stay eager)
+                eng.use_graphs = False
+        self.ran_eager = True
         return self.out
 
 
@@ -171,7 +191,7 @@ class Engine:
     """Device-resident DifvdsrDouble weights + cached per-shape graphs."""
 
     def __init__(self, weights=None, device=None, stream="lr32", a_mode=0, nacc=2, pair=1,
-                 max_pixels=192 * 96 * 96):
+                 max_pixels=192 * 96 * 96, use_graphs=True):
         self.lib = L.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         assert stream in ("bf16", "lr32", "fp32")
@@ -179,6 +199,9 @@ class Engine:
         self.stream_hr_fp32 = stream == "fp32"
         self.a_mode, self.nacc, self.pair = a_mode, nacc, pair
         self.max_pixels = max_pixels  # LR pixels per sub-batch (HR activations are 16x this)
+        self.use_graphs = use_graphs
+        # (weights, biases and activations are read through fixed device pointers: set_weights / repack rewrite them
+        #  in place, so captured graphs stay valid)
         self.specs = layer_specs()
         self.ksize = {n: k for n, k, _, _ in self.specs}
         self.master = {}   # name -> (kernel HWIO fp32 device, bias fp32 device): views into param_arena

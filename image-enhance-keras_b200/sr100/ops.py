@@ -19,10 +19,21 @@ def _dev():
 
 
 def to_device(a, dtype=None):
+    """Host array -> device tensor.  Arrays that already live in page-locked memory (e.g. the outputs of
+    models.upscale_arrays) are DMA-copied directly; pageable arrays take the ordinary staged copy."""
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.to(_dev(), non_blocking=False)
+    return t.to(_dev(), non_blocking=t.is_pinned())
+
+
+def to_host_pinned(t):
+    """Device tensor -> page-locked host tensor, asynchronously on the current stream (the caller
+    synchronises once for all its outputs).  The pinned block comes from torch's caching host allocator and is
+    recycled when the returned array is dropped."""
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    return out
 
 
 def patch_count(dim, patch, step):

@@ -113,3 +113,21 @@ def test_predict_rejects_bad_shapes(dmodel):
         model.predict(np.zeros((24, 24, 3), dtype=np.float32))
     with pytest.raises(ValueError):
         model.predict(np.zeros((1, 24, 24, 4), dtype=np.float32))
+
+
+def test_cuda_graph_replay_matches_eager(weights):
+    """The captured launch sequence reproduces the eager one bit for bit, also after the weights change in place."""
+    from sr100.engine import Engine
+    rng = np.random.default_rng(13)
+    x = torch.from_numpy(_smooth_images(rng, 2, 24, 24)).cuda()
+    eager = Engine(weights, use_graphs=False)
+    graphed = Engine(weights, use_graphs=True)
+    want = eager.forward_device(x).cpu().numpy()
+    outs = [graphed.forward_device(x).cpu().numpy() for _ in range(3)]   # eager, capture, replay
+    assert graphed.graph(2, 24, 24).cuda_graph is not None
+    for o in outs:
+        assert np.array_equal(o, want)
+    w2 = {k: (v[0] * 0.5, v[1] + 0.01) for k, v in weights.items()}
+    eager.set_weights_dict(w2)
+    graphed.set_weights_dict(w2)
+    assert np.array_equal(graphed.forward_device(x).cpu().numpy(), eager.forward_device(x).cpu().numpy())

@@ -83,6 +83,9 @@ def main():
         rec["detail_ms"] = {k: round(v, 3) for k, v in parts.items()}
     if rank == 0:
         print(json.dumps(rec), flush=True)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -258,10 +258,20 @@ def main():
     peaks = load_peaks()
     achieved = g.conv_flops / (conv_ms * 1e-3) / 1e12
     launches_per_step = len(g.steps) + 5 + 5 + 5          # libsr100 kernels only: + gathers, stitches, scores
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": round(achieved, 1),
+    traffic, traffic_src = None, None
+    for cand in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+        if cand.endswith("_ncu_step_summary.json"):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", cand)))["conv_traffic_bytes_per_launch"]
+                traffic_src = "profiles/" + cand + " (ncu dram__bytes_read+write, mean over the 66 conv launches of one forward)"
+            except (OSError, KeyError, ValueError):
+                pass
+            break
+    roofline = {"bound": "tensor", "kernel": "conv_tc_pair_kernel", "achieved": round(achieved, 1),
                 "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                "frac_of_burst_peak": round(achieved / peaks["burst"], 4), "traffic": None,
+                "frac_of_burst_peak": round(achieved / peaks["burst"], 4), "traffic": traffic,
+                "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "launches": len(conv_idx), "avg_launch_ms": round(conv_ms / len(conv_idx), 4),
                 "share_of_forward": round(conv_ms / total_ms, 4),
                 "algorithmic_flops_per_forward": g.conv_flops}

@@ -14,6 +14,7 @@ residual stream is kept in fp32 in HBM at LR (22 blocks of accumulation) and in 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -199,7 +200,7 @@ class Engine:
         self.stream_hr_fp32 = stream == "fp32"
         self.a_mode, self.nacc, self.pair = a_mode, nacc, pair
         self.max_pixels = max_pixels  # LR pixels per sub-batch (HR activations are 16x this)
-        self.use_graphs = use_graphs
+        self.use_graphs = use_graphs and os.environ.get("SR100_NO_GRAPHS", "0") != "1"
         # (weights, biases and activations are read through fixed device pointers: set_weights / repack rewrite them
         #  in place, so captured graphs stay valid)
         self.specs = layer_specs()

@@ -191,12 +191,12 @@ def main():
     dev_gts = [torch.from_numpy(g).cuda() for g in gts]
     score_buf = torch.zeros(5, 64, dtype=torch.uint8, device="cuda")
 
-    def step_resident():
-        canv = eng.upscale_images_device(dev_imgs)
+    def step_resident(full=False):
+        canv = eng.upscale_images_device(dev_imgs, full_canvas=full)
         score_buf.zero_()
         for i, (c, g) in enumerate(zip(canv, dev_gts)):
             h, w = g.shape[0], g.shape[1]
-            sr = c[:h, :w].contiguous()
+            sr = c[:h, :w].contiguous() if full else c
             L.check(eng.lib.sr_score_pair_u8(L.ptr(sr), L.ptr(g), h, w, 10, L.ptr(score_buf[i]), L.stream_ptr()))
         return canv
 
@@ -238,32 +238,41 @@ def main():
     value = world * mp_step * args.steps / t_res
     e2e = world * mp_step * args.steps / t_e2e
 
-    # ---- roofline of the dominant kernel (conv_tc_kernel): per-launch CUDA events over one more step
-    g = eng.graph(186, 96, 96) if (186, 96, 96) in eng._graphs else next(iter(eng._graphs.values()))
+    # the reference's literal tile set (all 186 tiles, full 384x384 HR stage) for comparison: same output pixels
+    t_full = timed(lambda: step_resident(True), max(2, args.steps // 2), 3)
+    value_full = world * mp_step * max(2, args.steps // 2) / t_full
+
+    # ---- roofline of the dominant kernel (conv_tc_pair_kernel): per-launch CUDA events over one more step
+    from sr100.engine import _Plan
+    step_resident()
+    torch.cuda.synchronize()
+    stages = list(eng.last_stages)
+    tiles_run = sum(st_.NB for st_ in stages if hasattr(st_, "x_in"))
+    hr_shapes = sorted({(st_.eh, st_.ew) for st_ in stages if hasattr(st_, "eh")})
     st = L.stream_ptr()
-    g.run()
-    torch.cuda.synchronize()
     evs = []
-    for step in g.steps:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step(st)
-        b.record()
-        evs.append((a, b))
+    for stg in stages:
+        for step in stg.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(st)
+            b.record()
+            evs.append((a, b, isinstance(getattr(step, "__self__", None), _Plan)))
     torch.cuda.synchronize()
-    durs = [a.elapsed_time(b) for a, b in evs]
-    conv_idx = [i for i in range(len(g.steps)) if i not in (0, 1 + 16 * 3 + 6 * 2)]     # all but head, bilinear
-    conv_ms = sum(durs[i] for i in conv_idx)
-    total_ms = sum(durs)
+    conv_ms = sum(a.elapsed_time(b) for a, b, is_conv in evs if is_conv)
+    n_conv = sum(1 for _, _, is_conv in evs if is_conv)
+    total_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+    conv_flops = eng.last_flops()
     peaks = load_peaks()
-    achieved = g.conv_flops / (conv_ms * 1e-3) / 1e12
-    launches_per_step = len(g.steps) + 5 + 5 + 5          # libsr100 kernels only: + gathers, stitches, scores
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    launches_per_step = len(evs) + 5 + 5 + 5          # libsr100 kernels only: + gathers, stitches, scores
     traffic, traffic_src = None, None
-    for cand in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+    prof_dir = os.path.join(ROOT, "profiles")
+    for cand in sorted(os.listdir(prof_dir), reverse=True) if os.path.isdir(prof_dir) else []:
         if cand.endswith("_ncu_step_summary.json"):
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", cand)))["conv_traffic_bytes_per_launch"]
-                traffic_src = "profiles/" + cand + " (ncu dram__bytes_read+write, mean over the 66 conv launches of one forward)"
+                traffic = json.load(open(os.path.join(prof_dir, cand)))["conv_traffic_bytes_per_launch"]
+                traffic_src = "profiles/" + cand + " (ncu dram__bytes_read+write, mean over the conv launches of one forward)"
             except (OSError, KeyError, ValueError):
                 pass
             break
@@ -272,9 +281,10 @@ def main():
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": round(achieved / peaks["burst"], 4), "traffic": traffic,
                 "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
-                "launches": len(conv_idx), "avg_launch_ms": round(conv_ms / len(conv_idx), 4),
+                "launches": n_conv, "avg_launch_ms": round(conv_ms / n_conv, 4),
                 "share_of_forward": round(conv_ms / total_ms, 4),
-                "algorithmic_flops_per_forward": g.conv_flops}
+                "executed_flops_per_step": conv_flops,
+                "reference_tiling_flops_per_step": 189595215986688.0}
 
     if rank != 0:
         return
@@ -291,10 +301,16 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "set5_x4_tiled", "images": SET5_SHAPES, "tiles": 186, "patch": 96, "step": 64,
+                   "tiles_run": tiles_run, "hr_stage_extents": hr_shapes,
+                   "dead_work_elimination": "tiles that own no pixel of the final 4Hx4W image are not run; the HR "
+                                            "stage runs on the 272x272 corner of each 384x384 patch that the stitch "
+                                            "can see (receptive-field radius 7); output pixels bit-identical to the "
+                                            "full tiling (tests/test_gpu_deadwork.py, tests/test_tile_plan.py), which is timed as value_full_tiles",
                    "output_mp_per_step_per_gpu": mp_step, "weights": "glorot_uniform random init",
                    "residual_stream": "fp32 at LR, bf16 at HR",
                    "l2": "activations per conv (0.9-7 GB) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "value_full_tiles": round(value_full, 3),
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -526,6 +526,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
                              xx < P.BW && (c.seg_x0 + xx) < P.W;
           const size_t pix = ((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx;
+          // optional scatter: image n lands in slot out_index[n] of a tensor of out_H x out_W images
+          size_t opix = pix;
+          if (P.out_index && valid)
+            opix = ((size_t)P.out_index[c.n] * P.out_H + yy) * P.out_W + c.seg_x0 + xx;
           uint32_t v[16];
           tmem_ld16(t_base + acc * N_, v);
           tmem_ld_wait();
@@ -534,8 +538,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               float o = P.alpha * (__uint_as_float(v[j]) + s_bias[j]);
               if (P.res_f32) o = fmaf(P.beta, P.res_f32[pix * P.cout + j], o);
               if (P.relu) o = fmaxf(o, 0.f);
-              if (P.out_f32) P.out_f32[pix * P.cout + j] = o;
-              if (P.out_bf16) P.out_bf16[pix * P.cout + j] = __float2bfloat16_rn(o);
+              if (P.out_f32) P.out_f32[opix * P.cout + j] = o;
+              if (P.out_bf16) P.out_bf16[opix * P.cout + j] = __float2bfloat16_rn(o);
             }
           }
         }
@@ -992,6 +996,13 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.out_f32 = d->out_f32;
   P.cout = d->cout;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
+  P.out_index = d->out_index;
+  P.out_H = d->out_h;
+  P.out_W = d->out_w;
+  if (d->out_index && (pl->n_pad == 128 || d->out_h < d->H || d->out_w < d->W)) {
+    delete pl;
+    return set_error(SR_ERR_UNSUPPORTED, "out_index scatter needs cout <= 16 and out_h/out_w >= H/W");
+  }
   double macs = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode);

@@ -84,27 +84,30 @@ __device__ __forceinline__ void load8(const void* base, size_t elem_off, float (
 // pixel, so every store instruction writes whole 256 B (bf16) / 512 B (fp32) pixels.
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
-bilinear4_fwd_kernel(const void* __restrict__ in, int NB, int H, int W, int C,
-                     uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+bilinear4_fwd_kernel(const void* __restrict__ in, const int* __restrict__ src_index, int NB, int H, int W, int C,
+                     int CH, int CW, uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+  // CH x CW: LR cells actually produced (output extent 4CH x 4CW <= 4H x 4W, the cropped HR stage);
+  // src_index: optional gather of the source images (output image n reads input image src_index[n]).
   const int C8 = C >> 3;
-  const int OW = 4 * W;
-  const size_t total = (size_t)NB * H * W * C8;
+  const int OW = 4 * CW;
+  const size_t total = (size_t)NB * CH * CW * C8;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % C8);
     size_t r = idx / C8;
-    const int x0 = (int)(r % W);
-    r /= W;
-    const int y0 = (int)(r % H);
-    const int n = (int)(r / H);
+    const int x0 = (int)(r % CW);
+    r /= CW;
+    const int y0 = (int)(r % CH);
+    const int n = (int)(r / CH);
+    const int ns = src_index ? src_index[n] : n;
     const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const size_t rowb0 = ((size_t)n * H + y0) * W, rowb1 = ((size_t)n * H + y1) * W;
+    const size_t rowb0 = ((size_t)ns * H + y0) * W, rowb1 = ((size_t)ns * H + y1) * W;
     float tl[8], tr[8], bl[8], br[8];
     load8<IN_BF16>(in, (rowb0 + x0) * C + c8 * 8, tl);
     load8<IN_BF16>(in, (rowb0 + x1) * C + c8 * 8, tr);
     load8<IN_BF16>(in, (rowb1 + x0) * C + c8 * 8, bl);
     load8<IN_BF16>(in, (rowb1 + x1) * C + c8 * 8, br);
-    const size_t obase = (((size_t)n * 4 * H + 4 * y0) * OW + 4 * x0) * C8 + c8;
+    const size_t obase = (((size_t)n * 4 * CH + 4 * y0) * OW + 4 * x0) * C8 + c8;
 #pragma unroll
     for (int fx = 0; fx < 4; ++fx) {
       const float tx = (float)fx * 0.25f;
@@ -494,20 +497,37 @@ extern "C" int sr_head1x1_fwd(const float* in, const float* w, const float* bias
   return check_launch("head1x1_kernel");
 }
 
+static int bilinear4_launch(const void* in, int in_is_bf16, const int* src_index, int NB, int H, int W, int C,
+                            int CH, int CW, void* out_bf16, float* out_f32, void* stream) {
+  const size_t total = (size_t)NB * CH * CW * (C / 8);
+  const unsigned g = grid_for(total, kBlock, 148 * 32);
+  if (in_is_bf16)
+    bilinear4_fwd_kernel<true><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, src_index, NB, H, W, C, CH, CW, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  else
+    bilinear4_fwd_kernel<false><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, src_index, NB, H, W, C, CH, CW, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  return check_launch("bilinear4_fwd_kernel");
+}
+
 extern "C" int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C,
                                 void* out_bf16, float* out_f32, void* stream) {
   if (!in || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: null pointer");
   if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_fwd: C must be a multiple of 8");
   if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: empty tensor");
-  const size_t total = (size_t)NB * H * W * (C / 8);
-  const unsigned g = grid_for(total, kBlock, 148 * 32);
-  if (in_is_bf16)
-    bilinear4_fwd_kernel<true><<<g, kBlock, 0, as_stream(stream)>>>(
-        in, NB, H, W, C, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
-  else
-    bilinear4_fwd_kernel<false><<<g, kBlock, 0, as_stream(stream)>>>(
-        in, NB, H, W, C, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
-  return check_launch("bilinear4_fwd_kernel");
+  return bilinear4_launch(in, in_is_bf16, nullptr, NB, H, W, C, H, W, out_bf16, out_f32, stream);
+}
+
+extern "C" int sr_bilinear4_crop_fwd(const void* in, int in_is_bf16, const int* src_index, int n_out, int H,
+                                     int W, int C, int out_h, int out_w, void* out_bf16, float* out_f32,
+                                     void* stream) {
+  if (!in || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_bilinear4_crop_fwd: null pointer");
+  if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_crop_fwd: C must be a multiple of 8");
+  if (n_out < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear4_crop_fwd: empty tensor");
+  if (out_h < 4 || out_w < 4 || out_h % 4 || out_w % 4 || out_h > 4 * H || out_w > 4 * W)
+    return set_error(SR_ERR_INVALID, "sr_bilinear4_crop_fwd: output extent must be a multiple of 4 within 4H x 4W");
+  return bilinear4_launch(in, in_is_bf16, src_index, n_out, H, W, C, out_h / 4, out_w / 4, out_bf16, out_f32,
+                          stream);
 }
 
 extern "C" int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream) {

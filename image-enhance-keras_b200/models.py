@@ -220,21 +220,23 @@ class BaseSuperResolutionModel(object):
         img_dev = ops.to_device(true_img, torch.uint8)
 
         if mode == 'patch':
-            images, counts = ops.patch_gather_u8(img_dev, (canvas_h, canvas_w), (patch_size, patch_size),
-                                                 step_patch, divisor=255.0)          # :272 + :336
+            if verbose or save_intermediate:
+                cnt = (ops.patch_count(canvas_h, patch_size, step_patch), ops.patch_count(canvas_w, patch_size, step_patch))
             if verbose:
-                print("Number of patches = %d, Patch Shape = (%d, %d)" % (images.shape[0], patch_size, patch_size))
+                print("Number of patches = %d, Patch Shape = (%d, %d)" % (cnt[0] * cnt[1], patch_size, patch_size))
             if save_intermediate:
                 fn = path[0] + "_intermediate_" + path[1]
-                first = (images[0] * 255.0).cpu().numpy()                             # imsave(fn, images[0]), :329
+                first = true_img[:patch_size, :patch_size].astype(np.float32)         # imsave(fn, images[0]), :329
+                first = np.pad(first, ((0, patch_size - first.shape[0]), (0, patch_size - first.shape[1]), (0, 0)))
                 lo, hi = first.min(), first.max()
                 sc = 255.0 / (hi - lo) if hi > lo else 1.0
                 Image.fromarray(((first - lo) * sc + 0.5).astype(np.uint8)).save(fn)
             model = self.create_model(patch_size, patch_size, load_weights=True)       # :338
-            result = model.engine.forward_device(images)                              # :342
-            _, result_u8 = ops.patch_stitch(result, counts, (patch_size, patch_size), step_patch, scalemulti,
-                                            (canvas_h, canvas_w), mul=255.0, want_f32=False,
-                                            want_u8=True)                             # :351, :382, :391
+            # :272-:391 on the device.  return_image hands back the whole canvas (:405-407) and therefore runs every
+            # tile in full; the file output is the 4H x 4W crop (:412), for which tiles / patch regions that cannot
+            # reach it are not computed (bit-identical pixels, see Engine.upscale_images_device)
+            result_u8 = model.engine.upscale_images_device([img_dev], patch=patch_size, step=step_patch,
+                                                           scale=scalemulti, full_canvas=bool(return_image))[0]
         else:
             canvas = torch.zeros(1, canvas_h, canvas_w, 3, device=img_dev.device, dtype=torch.float32)
             canvas[0, :orig_height, :orig_width] = img_dev.to(torch.float32) / 255.0
@@ -246,7 +248,7 @@ class BaseSuperResolutionModel(object):
             return result                                                             # uncropped canvas, :405-407
         if verbose:
             print("Saving image.")
-        outresult = result[0:orig_height * scalemulti, 0:orig_width * scalemulti]      # :412
+        outresult = result[0:orig_height * scalemulti, 0:orig_width * scalemulti]      # :412 (no-op in patch mode)
         Image.fromarray(outresult).save(filename)                                     # :415
 
     def upscale_arrays(self, images, patch_size=96, scalemulti=4, return_canvas=False):
@@ -259,12 +261,9 @@ class BaseSuperResolutionModel(object):
         dev = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().to(eng.device, non_blocking=True)
                for im in images]
         from sr100 import ops
-        canv = eng.upscale_images_device(dev, patch=patch_size, step=64, scale=scalemulti)
-        pinned = []
-        for im, c in zip(images, canv):
-            if not return_canvas:                        # crop on the device: only 4H x 4W x 3 bytes cross PCIe (:412)
-                c = c[0:im.shape[0] * scalemulti, 0:im.shape[1] * scalemulti].contiguous()
-            pinned.append(ops.to_host_pinned(c))
+        # return_canvas: every tile in full, uncropped canvases; default: the 4H x 4W images (:412), stitched directly
+        canv = eng.upscale_images_device(dev, patch=patch_size, step=64, scale=scalemulti, full_canvas=return_canvas)
+        pinned = [ops.to_host_pinned(c) for c in canv]
         torch.cuda.current_stream().synchronize()
         return [t.numpy() for t in pinned]
 

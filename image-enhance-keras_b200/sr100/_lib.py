@@ -37,6 +37,8 @@ class ConvDesc(C.Structure):
         ("a_mode", C.c_int),
         ("nacc", C.c_int),
         ("pair", C.c_int),
+        ("out_index", C.c_void_p),
+        ("out_h", C.c_int), ("out_w", C.c_int),
     ]
 
 
@@ -93,6 +95,7 @@ SIGNATURES = {
     "sr_conv2d_direct": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_head1x1_fwd": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_bilinear4_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sr_bilinear4_crop_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sr_bilinear4_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sr_patch_count": (_i, [_i, _i, _i]),
     "sr_canvas_size": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),

@@ -81,96 +81,56 @@ class _Plan:
             pass
 
 
-class _Graph:
-    """Buffers + conv plans for one (NB, H, W) input shape."""
+class _Stage:
+    """A fixed launch sequence on fixed buffers; replayed as a CUDA graph after one eager run (one submission
+    instead of tens of ctypes launches: matters for small inputs where launches cost as much as the math)."""
 
-    def __init__(self, eng, NB, H, W):
-        dev = eng.device
-        bf, f32 = torch.bfloat16, torch.float32
+    def _init_stage(self, eng):
         self.eng = eng
+        self.steps = []          # callables(stream)
+        self.conv_flops = 0.0    # algorithmic FLOPs (2*MAC) of the tensor-core launches of this stage
         self.cuda_graph, self.ran_eager = None, False
-        self.NB, self.H, self.W = NB, H, W
-        self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
-        self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=bf)
-        self.t1_lr = torch.empty_like(self.s_lr)
-        self.t2_lr = torch.empty_like(self.s_lr)
-        self.s_lr32 = torch.empty(NB, H, W, NUMK, device=dev, dtype=f32) if eng.stream_lr_fp32 else None
-        HH, WW = 4 * H, 4 * W
-        self.s_hr = torch.empty(NB, HH, WW, NUMK, device=dev, dtype=bf)
-        self.t1_hr = torch.empty_like(self.s_hr)
-        self.t2_hr = torch.empty_like(self.s_hr)
-        self.s_hr32 = torch.empty(NB, HH, WW, NUMK, device=dev, dtype=f32) if eng.stream_hr_fp32 else None
-        self.out = torch.empty(NB, HH, WW, 3, device=dev, dtype=f32)
-        self.steps = []  # list of callables(stream)
-        self.conv_flops = 0.0
-        lib = eng.lib
-        names = [s[0] for s in layer_specs()]
 
-        def conv(srcs, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0, res32=None, res16=None,
-                 shape=(NB, H, W), cout=NUMK):
-            d = L.ConvDesc()
-            d.nsrc = len(srcs)
-            bias = None
-            for s, (name, x) in enumerate(srcs):
-                d.in_[s] = x.data_ptr()
-                d.wpacked[s] = eng.packed[name].data_ptr()
-                d.ksize[s] = eng.ksize[name]
-            bias = eng.bias_for(tuple(n for n, _ in srcs))
-            d.NB, d.H, d.W = shape
-            d.cin, d.cout = NUMK, cout
-            d.bias = bias.data_ptr()
-            d.alpha, d.beta, d.relu = alpha, beta, relu
-            d.res_f32 = res32.data_ptr() if res32 is not None else None
-            d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
-            d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
-            d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
-            d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
-            p = _Plan(lib, d)
-            self.conv_flops += p.flops
-            self.steps.append(p.run)
-            return p
+    def _conv(self, srcs, shape, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0, res32=None, res16=None,
+              cout=NUMK, out_index=None, out_hw=None):
+        eng = self.eng
+        d = L.ConvDesc()
+        d.nsrc = len(srcs)
+        for s, (name, x) in enumerate(srcs):
+            d.in_[s] = x.data_ptr()
+            d.wpacked[s] = eng.packed[name].data_ptr()
+            d.ksize[s] = eng.ksize[name]
+        d.NB, d.H, d.W = shape
+        d.cin, d.cout = NUMK, cout
+        d.bias = eng.bias_for(tuple(n for n, _ in srcs)).data_ptr()
+        d.alpha, d.beta, d.relu = alpha, beta, relu
+        d.res_f32 = res32.data_ptr() if res32 is not None else None
+        d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
+        d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+        d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        if out_index is not None:
+            d.out_index, (d.out_h, d.out_w) = out_index.data_ptr(), out_hw
+        d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
+        p = _Plan(eng.lib, d)
+        self.conv_flops += p.flops
+        self.steps.append(p.run)
+        return p
 
-        def block53(i, s, s32, t1, t2, shape):
-            conv([(names[i], s)], out_bf16=t1, relu=1, shape=shape)
-            conv([(names[i + 2], s)], out_bf16=t2, relu=1, shape=shape)
-            conv([(names[i + 1], t1), (names[i + 3], t2)], out_bf16=s, out_f32=s32, alpha=0.1, beta=0.9,
-                 res32=s32, res16=s, shape=shape)
+    def _block53(self, names, i, s, s32, t1, t2, shape):
+        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1)
+        self._conv([(names[i + 2], s)], shape, out_bf16=t2, relu=1)
+        self._conv([(names[i + 1], t1), (names[i + 3], t2)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=0.9,
+                   res32=s32, res16=s)
 
-        def block_light(i, s, s32, t1, shape):
-            conv([(names[i], s)], out_bf16=t1, relu=1, shape=shape)
-            conv([(names[i + 1], t1)], out_bf16=s, out_f32=s32, alpha=0.1, beta=1.0, res32=s32, res16=s,
-                 shape=shape)
-
-        npix = NB * H * W
-        w0, b0 = eng.head_w, eng.head_b
-        self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
-            L.ptr(self.x_in), L.ptr(w0), L.ptr(b0), npix, L.ptr(self.s_lr), L.ptr(self.s_lr32), st)))
-        i = 1
-        lr = (NB, H, W)
-        for _ in range(16):
-            block53(i, self.s_lr, self.s_lr32, self.t1_lr, self.t2_lr, lr)
-            i += 4
-        for _ in range(6):
-            block_light(i, self.s_lr, self.s_lr32, self.t1_lr, lr)
-            i += 2
-        src = self.s_lr32 if self.s_lr32 is not None else self.s_lr
-        src_is_bf16 = 0 if self.s_lr32 is not None else 1
-        self.steps.append(lambda st: L.check(lib.sr_bilinear4_fwd(
-            L.ptr(src), src_is_bf16, NB, H, W, NUMK, L.ptr(self.s_hr), L.ptr(self.s_hr32), st)))
-        hr = (NB, HH, WW)
-        for _ in range(2):
-            block53(i, self.s_hr, self.s_hr32, self.t1_hr, self.t2_hr, hr)
-            i += 4
-        conv([(names[i], self.s_hr)], out_f32=self.out, relu=1, shape=hr, cout=3)
+    def _block_light(self, names, i, s, s32, t1, shape):
+        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1)
+        self._conv([(names[i + 1], t1)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=1.0, res32=s32, res16=s)
 
     def run(self):
-        """One forward over the resident x_in.  The launch sequence is fixed (plans are bound to these buffers), so
-        after one eager run it is captured into a CUDA graph and replayed: one submission instead of ~70 ctypes
-        launches (matters for small inputs such as a single 128x128 patch, where launches cost as much as math)."""
         eng = self.eng
         if eng.use_graphs and self.cuda_graph is not None:
             self.cuda_graph.replay()
-            return self.out
+            return
         st = L.stream_ptr()
         for step in self.steps:
             step(st)
@@ -185,7 +145,122 @@ class _Graph:
             except Exception:  # noqa: BLE001  (capture unsupported in this context: stay eager)
                 eng.use_graphs = False
         self.ran_eager = True
-        return self.out
+
+
+class _LRStage(_Stage):
+    """Low-resolution stage for NB patches of HxW: head 1x1 + 16 5/3 blocks + 6 light blocks.  Owns the patch
+    input buffer, the LR residual stream (the HR stages read it) and the full-size output patch slots."""
+
+    def __init__(self, eng, NB, H, W):
+        self._init_stage(eng)
+        dev, bf, f32 = eng.device, torch.bfloat16, torch.float32
+        self.NB, self.H, self.W = NB, H, W
+        self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
+        self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=bf)
+        self.t1_lr = torch.empty_like(self.s_lr)
+        self.t2_lr = torch.empty_like(self.s_lr)
+        self.s_lr32 = torch.empty(NB, H, W, NUMK, device=dev, dtype=f32) if eng.stream_lr_fp32 else None
+        self.out = torch.empty(NB, 4 * H, 4 * W, 3, device=dev, dtype=f32)   # [N,4H,4W,3] patch slots
+        self.hr = {}             # (n, eh, ew) -> _HRStage reading this stage's stream
+        lib = eng.lib
+        names = [s[0] for s in layer_specs()]
+        npix = NB * H * W
+        self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
+            L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, L.ptr(self.s_lr), L.ptr(self.s_lr32), st)))
+        i, lr = 1, (NB, H, W)
+        for _ in range(16):
+            self._block53(names, i, self.s_lr, self.s_lr32, self.t1_lr, self.t2_lr, lr)
+            i += 4
+        for _ in range(6):
+            self._block_light(names, i, self.s_lr, self.s_lr32, self.t1_lr, lr)
+            i += 2
+        self.first_hr_layer = i
+
+    def hr_stage(self, n, eh, ew):
+        key = (n, eh, ew)
+        st = self.hr.get(key)
+        if st is None:
+            if len(self.hr) >= 6:
+                self.hr.pop(next(iter(self.hr)))
+            st = _HRStage(self, n, eh, ew)
+            self.hr[key] = st
+        return st
+
+
+class _HRStage(_Stage):
+    """High-resolution stage for n of the LR stage's patches, on the top-left eh x ew corner of their x4
+    upsampling: bilinear x4 (TF1 legacy) -> 2 5/3 blocks -> tail conv3+relu, written into the LR stage's
+    full-size output slots.  (eh, ew) = (4H, 4W) is the whole patch = model.predict; the tiled inference path
+    uses 272x272: only [8,264) of a 384-pixel patch axis survives the stitch (img_utils.py:700-722) and the HR
+    stage has a receptive-field radius of 7 pixels (2 blocks x (1+2) + 1), so nothing beyond 271 can reach a
+    surviving pixel -- the surviving pixels are bit-identical to the full-patch computation."""
+
+    def __init__(self, lrs, n, eh, ew):
+        eng = lrs.eng
+        self._init_stage(eng)
+        dev, bf, f32 = eng.device, torch.bfloat16, torch.float32
+        self.n, self.eh, self.ew = n, eh, ew
+        self.src_index = torch.arange(n, device=dev, dtype=torch.int32)   # which LR patches (updated per run)
+        self.s_hr = torch.empty(n, eh, ew, NUMK, device=dev, dtype=bf)
+        self.t1_hr = torch.empty_like(self.s_hr)
+        self.t2_hr = torch.empty_like(self.s_hr)
+        self.s_hr32 = torch.empty(n, eh, ew, NUMK, device=dev, dtype=f32) if eng.stream_hr_fp32 else None
+        lib = eng.lib
+        names = [s[0] for s in layer_specs()]
+        src = lrs.s_lr32 if lrs.s_lr32 is not None else lrs.s_lr
+        src_is_bf16 = 0 if lrs.s_lr32 is not None else 1
+        H, W = lrs.H, lrs.W
+        self.steps.append(lambda st: L.check(lib.sr_bilinear4_crop_fwd(
+            L.ptr(src), src_is_bf16, L.ptr(self.src_index), n, H, W, NUMK, eh, ew, L.ptr(self.s_hr),
+            L.ptr(self.s_hr32), st)))
+        i, hr = lrs.first_hr_layer, (n, eh, ew)
+        for _ in range(2):
+            self._block53(names, i, self.s_hr, self.s_hr32, self.t1_hr, self.t2_hr, hr)
+            i += 4
+        self._conv([(names[i], self.s_hr)], hr, out_f32=lrs.out, relu=1, cout=3, out_index=self.src_index,
+                   out_hw=(4 * H, 4 * W))
+
+
+def hr_extent(tile, count, image_dim, patch=96, step=64, scale=4, radius=7, crop=8):
+    """Rows (or columns) of a tile's x4 output that the HR stage must produce so that every pixel the tile
+    contributes to the final [0, scale*image_dim) image is exact: owned span end + receptive-field radius,
+    rounded up to a multiple of 16, at least 272 (= the interior-tile value) to keep the shape classes few."""
+    P, S = patch * scale, step * scale
+    own_hi = S * (tile + 1) + crop if tile < count - 1 else S * tile + P       # exclusive, canvas coordinates
+    own_hi = min(own_hi, scale * image_dim)
+    need = own_hi - S * tile + radius
+    need = max(need, S + crop + radius + 1)
+    return min(P, (need + 15) // 16 * 16)
+
+
+def plan_tiles(h, w, patch=96, step=64, scale=4, full_canvas=False):
+    """Tile plan of one h x w image: (virtual canvas (H', W') handed to the gather, (cnt_h, cnt_w), per-tile HR
+    extents in the gather's column-major order n = wi*cnt_h + hi, or None for full_canvas).
+
+    full_canvas: the reference's canvas and tile grid (models.py:225-256, img_utils.py:622-648).  Otherwise only the
+    tiles that own a pixel of the final [0,scale*h) x [0,scale*w) image (models.py:412): ownership switches from tile
+    i-1 to tile i at scale*step*i + 8 (img_utils.py:700-722, later patches overwrite earlier ones), so the last live
+    tile index per axis is floor((scale*dim - 1 - 8) / (scale*step)); the trailing tiles sit in the zero padding and
+    are overwritten or cropped away."""
+    from . import ops
+    ch, cw = ops.canvas_size(h, w, patch, step)
+    cnt_h, cnt_w = ops.patch_count(ch, patch, step), ops.patch_count(cw, patch, step)
+    if full_canvas:
+        return (ch, cw), (cnt_h, cnt_w), None
+    S, c8 = step * scale, 8
+
+    def live(dim, cnt):
+        last = scale * dim - 1
+        return 1 if last < S + c8 else min(cnt, (last - c8) // S + 1)
+
+    lh, lw = live(h, cnt_h), live(w, cnt_w)
+    gh, gw = (lh - 1) * step + patch + 1, (lw - 1) * step + patch + 1   # smallest canvas with exactly those counts
+    ext = []
+    for wi in range(lw):
+        ew = hr_extent(wi, lw, w, patch, step, scale)
+        for hi in range(lh):
+            ext.append((hr_extent(hi, lh, h, patch, step, scale), ew))
+    return (gh, gw), (lh, lw), ext
 
 
 class Engine:
@@ -264,52 +339,84 @@ class Engine:
 
     # ---------------------------------------------------------------- forward
     def graph(self, NB, H, W):
+        """The LR stage (buffers + plans) for NB patches of HxW; HR stages hang off it."""
         key = (NB, H, W)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 4:  # bound device memory: keep the most recent shapes only
                 self._graphs.pop(next(iter(self._graphs)))
-            g = _Graph(self, NB, H, W)
+            g = _LRStage(self, NB, H, W)
             self._graphs[key] = g
         return g
 
     def sub_batch(self, H, W):
         return max(1, self.max_pixels // (H * W))
 
-    def forward_device(self, x, out=None):
-        """x: device float32 [N,H,W,3] in [0,1] -> device float32 [N,4H,4W,3] (model.predict)."""
+    def forward_device(self, x, out=None, extents=None):
+        """x: device float32 [N,H,W,3] in [0,1] -> device float32 [N,4H,4W,3] (model.predict).
+        extents: optional per-patch (eh, ew): only the top-left eh x ew corner of patch n's output is computed
+        (the rest of its slot is unspecified) -- the tiled path's dead-region elimination, see _HRStage."""
         N, H, W, _ = x.shape
         if out is None:
             out = torch.empty(N, 4 * H, 4 * W, 3, device=self.device, dtype=torch.float32)
         nb = min(N, self.sub_batch(H, W))
+        self.last_stages = []
         for i in range(0, N, nb):
             n = min(nb, N - i)
             g = self.graph(n, H, W)
             g.x_in.copy_(x[i:i + n])
-            out[i:i + n].copy_(g.run())
+            g.run()
+            self.last_stages.append(g)
+            if extents is None:
+                groups = {(4 * H, 4 * W): list(range(n))}
+            else:
+                groups = {}
+                for j in range(n):
+                    groups.setdefault(tuple(extents[i + j]), []).append(j)
+            for (eh, ew), idx in groups.items():
+                hs = g.hr_stage(len(idx), eh, ew)
+                hs.src_index.copy_(torch.tensor(idx, dtype=torch.int32))
+                hs.run()
+                self.last_stages.append(hs)
+            out[i:i + n].copy_(g.out)
         return out
 
-    def upscale_images_device(self, imgs_u8, patch=96, step=64, scale=4):
+    def upscale_images_device(self, imgs_u8, patch=96, step=64, scale=4, full_canvas=False):
         """The device part of upscaleStepPatch (models.py:225-391) for a list of uint8 [h,w,3] device images:
         zero-padded canvas -> 96/64 patch gather (/255) -> conv stack over ALL tiles of all images -> x255,
-        stitch with the 8-px crop, clip -> uint8.  Returns the uncropped uint8 canvases (device)."""
+        stitch with the 8-px crop, clip -> uint8.
+
+        full_canvas=True reproduces every tile and returns the uncropped uint8 canvases (what
+        upscaleStepPatch(return_image=True) hands back, models.py:405-407).  The default returns the final
+        [4h,4w,3] images (models.py:412) and eliminates work that cannot reach them: tiles whose owned span lies
+        entirely in the zero padding are not run, and the HR stage runs on the 272x272 corner of each patch that
+        the stitch can see (hr_extent).  Both give bit-identical pixels inside the final image."""
         from . import ops
-        metas, parts = [], []
+        metas, parts, extents = [], [], []
         for img in imgs_u8:
             h, w, _ = img.shape
+            (gh, gw), counts, ext = plan_tiles(h, w, patch, step, scale, full_canvas)
             ch, cw = ops.canvas_size(h, w, patch, step)
-            p, counts = ops.patch_gather_u8(img, (ch, cw), (patch, patch), step, divisor=255.0)
-            metas.append((ch, cw, counts, p.shape[0]))
+            p, got = ops.patch_gather_u8(img, (gh, gw), (patch, patch), step, divisor=255.0)
+            assert got == counts
+            metas.append((h, w, ch, cw, counts, p.shape[0]))
             parts.append(p)
+            if not full_canvas:
+                extents.extend(ext)
         allp = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
-        out = self.forward_device(allp)
+        out = self.forward_device(allp, extents=None if full_canvas else extents)
         res, off = [], 0
-        for ch, cw, counts, n in metas:
-            _, u8 = ops.patch_stitch(out[off:off + n], counts, (patch, patch), step, scale, (ch, cw), mul=255.0,
+        for h, w, ch, cw, counts, n in metas:
+            oh, ow = (ch, cw) if full_canvas else (h, w)
+            _, u8 = ops.patch_stitch(out[off:off + n], counts, (patch, patch), step, scale, (oh, ow), mul=255.0,
                                      want_f32=False, want_u8=True)
             res.append(u8)
             off += n
         return res
+
+    def last_flops(self):
+        """Algorithmic FLOPs (2*MAC) of the tensor-core launches of the most recent forward_device call."""
+        return float(sum(st.conv_flops for st in getattr(self, "last_stages", [])))
 
     def conv_flops(self, N, H, W):
         """Algorithmic FLOPs (2*MAC) of one forward over N patches of HxW (tensor-core convs + head)."""

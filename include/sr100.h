@@ -58,6 +58,11 @@ typedef struct sr_conv_desc {
   int a_mode;            /* 0: 64B-swizzled strip, 1: interleaved no-swizzle strip */
   int nacc;              /* 4 (default): 512 positions / tile; 2: 256 positions, double-buffered TMEM */
   int pair;              /* 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 over two images); needs NB >= 2 */
+  /* cout <= 16 only (the tail conv): scatter image n of the output into slot out_index[n] (device
+   * int32[NB]) of a tensor whose images are out_h x out_w pixels (>= H x W): the cropped HR stage
+   * writes its H x W result into the top-left corner of the full 384 x 384 patch slot. NULL: dense. */
+  const int* out_index;
+  int out_h, out_w;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -110,6 +115,14 @@ int sr_head1x1_fwd(const float* in, const float* w, const float* bias, size_t np
  * ------------------------------------------------------------------------------------------ */
 int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C, void* out_bf16,
                      float* out_f32, void* stream);
+/* Same sampling, restricted to the top-left out_h x out_w corner of the x4 output (multiples of 4)
+ * and with an optional gather of the source images: out[n] = resize(in[src_index[n]])[:out_h,:out_w].
+ * Used by the tiled inference path: of a 384x384 tile output only [8,264) per axis survives the
+ * stitch (img_utils.py:700-722) and the HR stage (2 blocks + tail) has a 7-pixel receptive-field
+ * radius, so 272 x 272 of the upsampled tile is all the HR stage ever needs. */
+int sr_bilinear4_crop_fwd(const void* in, int in_is_bf16, const int* src_index, int n_out, int H,
+                          int W, int C, int out_h, int out_w, void* out_bf16, float* out_f32,
+                          void* stream);
 /* Adjoint of the above: gin[NB,H,W,C] = sum over the HR samples each LR pixel contributed to. */
 int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream);
 

@@ -1,0 +1,70 @@
+"""-m gpu: the tiled inference path with dead-work elimination (live tiles only, 272x272 HR stage) produces
+bit-identical final images to the reference's literal scheme (every tile of the padded canvas, full 384x384 HR
+stage, uncropped canvas then [0:4H, 0:4W], models.py:382-412), and matches the CPU oracle's tiling around the same
+network."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sr_model():
+    import models
+    from oracle import model as om
+    m = models.DifvdsrDouble(1)
+    model = m.create_model(96, 96)
+    model.engine.set_weights_dict(om.init_weights(77, bias_scale=0.05))   # biases: zero-input tiles are not zero
+    return m
+
+
+@pytest.mark.parametrize("shapes", [[(33, 50)], [(20, 20), (130, 70)], [(256, 256), (65, 200)], [(344, 228)]])
+def test_cropped_path_is_bit_identical_to_full_tiling(sr_model, shapes):
+    rng = np.random.default_rng(sum(h * w for h, w in shapes))
+    imgs = [rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in shapes]
+    fast = sr_model.upscale_arrays(imgs)
+    canv = sr_model.upscale_arrays(imgs, return_canvas=True)
+    for im, f, c in zip(imgs, fast, canv):
+        h, w = im.shape[:2]
+        assert f.shape == (4 * h, 4 * w, 3) and f.dtype == np.uint8
+        assert np.array_equal(f, c[:4 * h, :4 * w])
+
+
+def test_cropped_float_outputs_identical_on_owned_region(sr_model):
+    """Same check before quantisation: the fp32 patch outputs agree exactly wherever the stitch reads them."""
+    from sr100 import ops
+    from sr100.engine import plan_tiles
+    eng = sr_model.model.engine
+    rng = np.random.default_rng(4)
+    img = torch.from_numpy(rng.integers(0, 256, size=(150, 90, 3)).astype(np.uint8)).cuda()
+    (gh, gw), counts, ext = plan_tiles(150, 90)
+    p, got = ops.patch_gather_u8(img, (gh, gw), (96, 96), 64, divisor=255.0)
+    full = eng.forward_device(p).clone()
+    crop = eng.forward_device(p, extents=ext).clone()
+    a, _ = ops.patch_stitch(full, counts, (96, 96), 64, 4, (150, 90), mul=255.0)
+    b, _ = ops.patch_stitch(crop, counts, (96, 96), 64, 4, (150, 90), mul=255.0)
+    assert torch.equal(a, b)
+    for n, (eh, ew) in enumerate(ext):          # and the whole computed corner except the 7-px contaminated rim
+        assert torch.equal(full[n, :eh - 7, :ew - 7], crop[n, :eh - 7, :ew - 7])
+
+
+def test_upscale_step_patch_file_and_canvas(sr_model, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, size=(70, 101, 3)).astype(np.uint8)
+    path = str(tmp_path / "x.png")
+    Image.fromarray(img).save(path)
+    wfile = str(tmp_path / "w.npz")
+    sr_model.model.save_weights(wfile)
+    import os
+    os.environ["SR100_WEIGHTS"] = wfile
+    try:
+        sr_model._loaded_from = None
+        canvas = sr_model.upscaleStepPatch(path, return_image=True, patch_size=96, verbose=False)
+        sr_model.upscaleStepPatch(path, patch_size=96, verbose=False)
+    finally:
+        del os.environ["SR100_WEIGHTS"]
+    out = np.asarray(Image.open(str(tmp_path / "x_scaled(1x).png")))
+    assert canvas.shape == (4 * 192, 4 * 256, 3)                  # 70+96 -> 192, 101+96 -> 256 (models.py:248-256)
+    assert out.shape == (280, 404, 3) and np.array_equal(out, canvas[:280, :404])

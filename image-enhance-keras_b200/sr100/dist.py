@@ -62,6 +62,16 @@ def sum_over_ranks(value):
     return float(t.item())
 
 
+def all_reduce_sum_(tensor):
+    """In-place sum over ranks (the training path's one exchange step: the flat fp32 gradient arena, NCCL over
+    NVLink on the box; the caller folds 1/world into the optimizer step).  Returns the world size."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return dist.get_world_size()
+
+
 def gather_objects(obj):
     """All ranks' python objects, in rank order (host-side result assembly; not on the data path)."""
     import torch.distributed as dist

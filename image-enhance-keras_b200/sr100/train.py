@@ -296,11 +296,8 @@ class Trainer:
 
     def apply_gradients(self):
         """Data-parallel mean of the gradients (NCCL all-reduce of the flat arena) + fused Keras Adam + repack."""
-        import torch.distributed as dist
-        world = 1
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        from .dist import all_reduce_sum_
+        world = all_reduce_sum_(self.grads)
         self.t += 1
         L.check(self.lib.sr_adam_step(L.ptr(self.engine.param_arena), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v),
                                       self.engine.n_params, self.lr, self.beta_1, self.beta_2, self.epsilon, self.t,

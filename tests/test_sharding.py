@@ -60,3 +60,53 @@ def test_world_size_2_gloo():
     rec = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
     assert rec["flat"] == [i * i for i in range(11)]
     assert rec["tmax"] == 3.0 and rec["world"] == 2
+
+
+DP_WORKER = r"""
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "image-enhance-keras_b200"))
+from sr100 import dist as D
+from oracle import model as om
+torch.set_num_threads(2)
+rank, local_rank, world = D.init_process_group(backend="gloo")
+weights = om.init_weights(3, bias_scale=0.01)
+rng = np.random.default_rng(0)
+x = torch.from_numpy(rng.random((4, 6, 6, 3)).astype(np.float32))
+y = torch.from_numpy(rng.random((4, 24, 24, 3)).astype(np.float32))
+lo, hi = D.shard_range(4, rank, world)
+m = om.DifvdsrDoubleOracle(weights)
+params = list(m.parameters())
+loss = om.mse_loss(m(x[lo:hi]), y[lo:hi])                 # per-rank mean over the local minibatch
+flat = torch.cat([g.reshape(-1) for g in torch.autograd.grad(loss, params)])
+w = D.all_reduce_sum_(flat)                               # the training step's exchange
+flat /= w                                                 # (folded into sr_adam_step(grad_scale) on the GPU)
+if rank == 0:
+    full = om.mse_loss(m(x), y)
+    ref = torch.cat([g.reshape(-1) for g in torch.autograd.grad(full, params)])
+    rel = float((flat - ref).norm() / ref.norm())
+    print(json.dumps(dict(rel=rel, world=w, n=int(flat.numel()))))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_data_parallel_gradient_mean_world_2_gloo():
+    """The exchange step of the training path on CPU (gloo, world 2): all-reduce(sum)/world of the per-rank
+    mean-loss gradients == gradient of the mean loss over the global minibatch (oracle graph, autograd)."""
+    import json
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = DP_WORKER % dict(root=ROOT)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    rec = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
+    assert rec["world"] == 2 and rec["n"] == 21838211
+    assert rec["rel"] < 1e-5

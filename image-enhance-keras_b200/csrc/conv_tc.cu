@@ -144,7 +144,23 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
         if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f)) o[2 * e + 1] = 0.f;
       }
     }
-    if (P.out_f32) {
+    if (P.shuffle_r) {
+      // fused depth-to-space (keras_subpixel.py:64-84, advanced.py:87-129,195-196): the shuffle is the store address
+      const int r_ = P.shuffle_r, C_ = P.shuffle_C;
+      const int x = pix % P.W, t = pix / P.W;
+      const int y = t % P.H, n = t / P.H;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = q * 8 + e;
+        if (ch < P.cout) {
+          int cc, ry, rx;
+          if (P.shuffle_order == 0) { cc = ch / (r_ * r_); rx = (ch / r_) % r_; ry = ch % r_; }
+          else if (P.shuffle_order == 1) { cc = ch / (r_ * r_); ry = (ch / r_) % r_; rx = ch % r_; }
+          else { cc = ch % C_; ry = (ch / C_) / r_; rx = (ch / C_) % r_; }
+          P.out_f32[(((size_t)n * P.H * r_ + (y * r_ + ry)) * ((size_t)P.W * r_) + (x * r_ + rx)) * C_ + cc] = o[e];
+        }
+      }
+    } else if (P.out_f32) {
       *reinterpret_cast<float4*>(P.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(P.out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
@@ -948,8 +964,11 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (!d || !out) return set_error(SR_ERR_INVALID, "sr_conv_plan_create: null argument");
   if (d->nsrc < 1 || d->nsrc > 2) return set_error(SR_ERR_INVALID, "nsrc must be 1 or 2");
   if (d->cin != kCin) return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv requires cin == 128");
-  if (!(d->cout == 128 || (d->cout >= 1 && d->cout <= 16)))
-    return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv supports cout == 128 or cout <= 16");
+  if (!(d->cout == 128 || (d->cout >= 1 && d->cout <= 16) || (d->shuffle_r > 0 && d->cout >= 1 && d->cout < 128)))
+    return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv supports cout == 128 or cout <= 16 (any cout <= 128 with shuffle_r)");
+  if (d->shuffle_r > 0 && (d->cout % (d->shuffle_r * d->shuffle_r) != 0 || !d->out_f32 || d->out_bf16 ||
+                           d->shuffle_order < 0 || d->shuffle_order > 2))
+    return set_error(SR_ERR_INVALID, "shuffle_r needs cout divisible by r*r, an fp32 output only, order 0..2");
   if (d->NB < 1 || d->H < 1 || d->W < 1) return set_error(SR_ERR_INVALID, "empty tensor");
   int p = 0;
   for (int s = 0; s < d->nsrc; ++s) {
@@ -962,7 +981,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   ConvPlan* pl = new (std::nothrow) ConvPlan();
   if (!pl) return set_error(SR_ERR_NOMEM, "out of host memory");
   memset(pl, 0, sizeof *pl);
-  pl->n_pad = d->cout == 128 ? 128 : 16;
+  pl->n_pad = (d->cout == 128 || d->shuffle_r > 0) ? 128 : 16;
   pl->amode = d->a_mode == 1 ? kAModeInterleave : kAModeSwizzle64;
   pl->nacc = (d->nacc == 2 && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
@@ -997,6 +1016,9 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.cout = d->cout;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
   P.out_index = d->out_index;
+  P.shuffle_r = d->shuffle_r > 0 ? d->shuffle_r : 0;
+  P.shuffle_order = d->shuffle_order;
+  P.shuffle_C = d->shuffle_r > 0 ? d->cout / (d->shuffle_r * d->shuffle_r) : 0;
   P.out_H = d->out_h;
   P.out_W = d->out_w;
   if (d->out_index && (pl->n_pad == 128 || d->out_h < d->H || d->out_w < d->W)) {
@@ -1042,7 +1064,7 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   // epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
   const ConvKernelParams& P = pl->P;
   const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
-  const int epi = nops != 1 ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  const int epi = (nops != 1 || P.shuffle_r) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
     switch (epi) {

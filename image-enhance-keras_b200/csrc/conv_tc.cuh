@@ -53,6 +53,8 @@ struct ConvKernelParams {
   // cout <= 16 path only: image n is written to slot out_index[n] of a tensor of out_H x out_W pixel images
   const int* out_index;
   int out_H, out_W;
+  // sub-pixel layers: r > 0 stores channel ch of pixel (y,x) at the depth-to-space position (order as sr_depth_to_space)
+  int shuffle_r, shuffle_order, shuffle_C;
 };
 
 }  // namespace sr

@@ -625,15 +625,15 @@ extern "C" int sr_depth_to_space(const float* in, int NB, int H, int W, int C, i
 }
 
 extern "C" size_t sr_packed_weight_bytes(int ksize, int cout) {
-  const int n_pad = cout == 128 ? 128 : 16;
+  const int n_pad = cout > 16 ? 128 : 16;
   return (size_t)4 * ksize * ksize * n_pad * 32 * 2;
 }
 
 extern "C" int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip,
                                     void* dst, void* stream) {
   if (!hwio || !dst) return set_error(SR_ERR_INVALID, "sr_pack_conv_weights: null pointer");
-  if (!(cout == 128 || (cout >= 1 && cout <= 16))) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: cout must be 128 or <= 16");
-  const int n_pad = (cout == 128 || transpose_flip) ? 128 : 16;  // the input-gradient conv always has 128 outputs
+  if (cout < 1 || cout > 128) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights: cout must be 1..128");
+  const int n_pad = (cout > 16 || transpose_flip) ? 128 : 16;  // the input-gradient conv always has 128 outputs
   const size_t total = (size_t)4 * ksize * ksize * n_pad * 32;
   pack_weights_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
       hwio, ksize * ksize, cout, n_pad, transpose_flip, reinterpret_cast<__nv_bfloat16*>(dst));

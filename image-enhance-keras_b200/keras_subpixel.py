@@ -3,8 +3,8 @@
 A conv with r*r*filters outputs followed by the reference's _phase_shift (keras_subpixel.py:64-84), whose
 index map is  out[b, Y, X, c] = conv[b, Y//r, X//r, c*r*r + (X%r)*r + (Y%r)]  (a pixel shuffle with the
 two sub-pixel axes swapped).  Here the shuffle is not a separate pass: it is the store address of the
-conv kernel's epilogue (sr_conv2d_direct with shuffle_order 0), so the r*r-channel tensor never
-round-trips HBM.  The layer is callable on numpy NHWC arrays or device tensors.
+conv kernel's epilogue (the tcgen05 kernel's `shuffle_r` for 128-channel bf16 inputs, sr_conv2d_direct
+otherwise; shuffle_order 0), so the r*r-channel tensor never round-trips HBM.  The layer is callable on numpy NHWC arrays or device tensors.
 """
 import numpy as np
 
@@ -65,8 +65,14 @@ class Subpixel(object):
             self.build(x.shape)
         w = ops.to_device(self.kernel)
         b = ops.to_device(self.bias) if self.use_bias else None
-        y = ops.conv2d_direct(x, w, b, same=(self.padding == 'same'), relu=(self.activation == 'relu'),
-                              shuffle_r=self.r, shuffle_order=0)
+        k = self.kernel_size[0]
+        if (x.shape[-1] == 128 and self.padding == 'same' and k in (1, 3, 5) and self.filters <= 128
+                and not isinstance(inputs, np.ndarray) and inputs.dtype == torch.bfloat16):
+            # a 128-channel bf16 feature map (the width of the models.py stack): tensor-core conv, shuffle in its epilogue
+            y = ops.conv2d_tc_shuffle(inputs.contiguous(), w, b, self.r, 0, relu=(self.activation == 'relu'))
+        else:
+            y = ops.conv2d_direct(x, w, b, same=(self.padding == 'same'), relu=(self.activation == 'relu'),
+                                  shuffle_r=self.r, shuffle_order=0)
         return y.cpu().numpy() if as_numpy else y
 
     __call__ = call

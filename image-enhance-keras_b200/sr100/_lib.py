@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("pair", C.c_int),
         ("out_index", C.c_void_p),
         ("out_h", C.c_int), ("out_w", C.c_int),
+        ("shuffle_r", C.c_int), ("shuffle_order", C.c_int),
     ]
 
 

@@ -122,6 +122,36 @@ def conv2d_direct(x, w_hwio, bias, same=True, relu=False, shuffle_r=0, shuffle_o
     return out
 
 
+def conv2d_tc_shuffle(x_bf16, w_hwio, bias, r, order, relu=False):
+    """Tensor-core conv (cin = 128, SAME, k in {1,3,5}, cout = r*r*C <= 128) with the depth-to-space shuffle fused
+    into the epilogue's store address: bf16 NHWC [N,H,W,128] -> fp32 [N,H*r,W*r,C].  The r*r*C-channel tensor of
+    keras_subpixel.Subpixel (keras_subpixel.py:46-61, 109-110) never exists in HBM."""
+    lib = L.require_device()
+    n, h, w, cin = x_bf16.shape
+    k, _, _, cout = w_hwio.shape
+    if cin != 128 or x_bf16.dtype != torch.bfloat16:
+        raise ValueError("conv2d_tc_shuffle needs a bf16 input with 128 channels")
+    packed = torch.empty(lib.sr_packed_weight_bytes(k, cout), dtype=torch.uint8, device=x_bf16.device)
+    L.check(lib.sr_pack_conv_weights(L.ptr(w_hwio), k, cout, 0, L.ptr(packed), L.stream_ptr()))
+    out = torch.empty(n, h * r, w * r, cout // (r * r), device=x_bf16.device, dtype=torch.float32)
+    d = L.ConvDesc()
+    d.nsrc = 1
+    d.in_[0], d.wpacked[0], d.ksize[0] = x_bf16.data_ptr(), packed.data_ptr(), k
+    d.NB, d.H, d.W, d.cin, d.cout = n, h, w, 128, cout
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.alpha, d.beta, d.relu = 1.0, 0.0, 1 if relu else 0
+    d.out_f32 = out.data_ptr()
+    d.a_mode, d.nacc, d.pair = 0, 2, 1
+    d.shuffle_r, d.shuffle_order = r, order
+    plan = C.c_void_p()
+    L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))
+    try:
+        L.check(lib.sr_conv_plan_run(plan, L.stream_ptr()))
+    finally:
+        lib.sr_conv_plan_destroy(plan)
+    return out
+
+
 def bilinear4(x, out_dtype=torch.float32):
     """tf.image.resize_bilinear x4, TF1 legacy sampling (models.py:1392-1399)."""
     lib = L.require_device()

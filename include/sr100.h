@@ -63,6 +63,11 @@ typedef struct sr_conv_desc {
    * writes its H x W result into the top-left corner of the full 384 x 384 patch slot. NULL: dense. */
   const int* out_index;
   int out_h, out_w;
+  /* Sub-pixel layers (keras_subpixel.Subpixel, advanced.SubPixelUpscaling / SubpixelConv2D): r > 0
+   * fuses the depth-to-space shuffle into the epilogue's store address; cout = r*r*C may then be
+   * any value <= 128 (weights packed with sr_pack_conv_weights(cout)), output fp32
+   * [NB, H*r, W*r, C] only; order as in sr_depth_to_space. */
+  int shuffle_r, shuffle_order;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -81,7 +86,7 @@ void sr_conv_plan_destroy(sr_conv_plan* plan);
 int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info);
 
 /* Repack Keras HWIO fp32 weights [k,k,cin=128,cout] (device) into the kernel's K-chunked bf16
- * layout [cin/32][k*k][cout_pad][32]; cout_pad = 128 or 16.  transpose_flip = 1 produces the
+ * layout [cin/32][k*k][cout_pad][32]; cout_pad = 16 for cout <= 16, else 128 (zero rows beyond cout).  transpose_flip = 1 produces the
  * weights of the input-gradient convolution (180-degree rotation, cin<->cout): always a
  * 128 -> 128 layout (destination size sr_packed_weight_bytes(ksize, 128)); for cout < 128 the
  * missing reduction rows are zero, so the gradient tensor may carry anything in channels >= cout.

@@ -68,3 +68,16 @@ def test_upscale_step_patch_file_and_canvas(sr_model, tmp_path):
     out = np.asarray(Image.open(str(tmp_path / "x_scaled(1x).png")))
     assert canvas.shape == (4 * 192, 4 * 256, 3)                  # 70+96 -> 192, 101+96 -> 256 (models.py:248-256)
     assert out.shape == (280, 404, 3) and np.array_equal(out, canvas[:280, :404])
+
+
+def test_large_image_config5_shape_and_identity(sr_model):
+    """BASELINE.json configs[4] at full size (1080x1920 -> 4320x7680, 558 tiles in the reference grid, 510 run):
+    the fast path equals the literal tiling bit for bit on every pixel of the final image."""
+    rng = np.random.default_rng(9)
+    from scipy.ndimage import uniform_filter
+    img = uniform_filter(rng.integers(0, 256, size=(1080, 1920, 3)).astype(np.float32), size=(5, 5, 1)).astype(np.uint8)
+    fast = sr_model.upscale_arrays([img])[0]
+    assert fast.shape == (4320, 7680, 3)
+    canvas = sr_model.upscale_arrays([img], return_canvas=True)[0]
+    assert canvas.shape == (4 * 1216, 4 * 2048, 3)
+    assert np.array_equal(fast, canvas[:4320, :7680])

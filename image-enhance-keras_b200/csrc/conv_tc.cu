@@ -78,21 +78,27 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
   uint8_t* my_row = stage + lane * 256;
   const int sw = lane & 7;
+  // two TMEM loads in flight per wait (64 columns): halves the exposed tcgen05.ld latency
 #pragma unroll 1
-  for (int cb = 0; cb < 4; ++cb) {
-    uint32_t v[32];
-    tmem_ld32(t_acc + cb * 32, v);
+  for (int cb2 = 0; cb2 < 2; ++cb2) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_acc + cb2 * 64, va);
+    tmem_ld32(t_acc + cb2 * 64 + 32, vb);
     tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t w[4];
+    for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = q * 8 + e * 2;
-        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = q * 8 + e * 2;
+          const float f0 = __uint_as_float(hh ? vb[j] : va[j]), f1 = __uint_as_float(hh ? vb[j + 1] : va[j + 1]);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(my_row + ((((cb2 * 2 + hh) * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
   __syncwarp();
@@ -144,23 +150,7 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
         if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f)) o[2 * e + 1] = 0.f;
       }
     }
-    if (P.shuffle_r) {
-      // fused depth-to-space (keras_subpixel.py:64-84, advanced.py:87-129,195-196): the shuffle is the store address
-      const int r_ = P.shuffle_r, C_ = P.shuffle_C;
-      const int x = pix % P.W, t = pix / P.W;
-      const int y = t % P.H, n = t / P.H;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int ch = q * 8 + e;
-        if (ch < P.cout) {
-          int cc, ry, rx;
-          if (P.shuffle_order == 0) { cc = ch / (r_ * r_); rx = (ch / r_) % r_; ry = ch % r_; }
-          else if (P.shuffle_order == 1) { cc = ch / (r_ * r_); ry = (ch / r_) % r_; rx = ch % r_; }
-          else { cc = ch % C_; ry = (ch / C_) / r_; rx = (ch / C_) % r_; }
-          P.out_f32[(((size_t)n * P.H * r_ + (y * r_ + ry)) * ((size_t)P.W * r_) + (x * r_ + rx)) * C_ + cc] = o[e];
-        }
-      }
-    } else if (P.out_f32) {
+    if (P.out_f32) {
       *reinterpret_cast<float4*>(P.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(P.out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
@@ -177,16 +167,15 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
   __syncwarp();
 }
 
-// Specialised staged epilogue (EPI = which single global operand the epilogue reads; the host picks the generic
-// kernel for anything else) for one 128x128 accumulator: phase 1 drains TMEM (lane = pixel) into this warp's
-// 32-row x 256 B shared-memory tile as bf16 (16-byte chunks XOR-swizzled by row, conflict-free both
-// ways); phase 2 re-reads it with 16 lanes per pixel so that every global access of the residual,
-// mask and outputs is a fully coalesced 512 B (bf16) / 1 KB (fp32) warp transaction.
+// Specialised staged epilogue (EPI = which single global operand the epilogue reads: 1 fp32 residual, 2 bf16
+// residual, 3 ReLU mask; the host picks the generic kernel for anything else) for one 128x128 accumulator.
+// The operand of 8 pixel pairs is requested as one batch BEFORE the TMEM drain / before the pass that uses it, so
+// one DRAM latency is exposed per batch instead of one per pixel pair; the two passes share one (rolled) body to
+// keep the kernel small (instruction-cache footprint decides the short-MMA-phase launches).
 template <int EPI>
 __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
                                                     uint32_t t_acc, int f_base, uint8_t* stage,
                                                     const float* s_bias, int lane, bool live = true) {
-  // ---- phase 1: this lane's pixel row
   const int f = f_base + lane;
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
@@ -194,79 +183,65 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
   const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
                      xx < P.BW && (c.seg_x0 + xx) < P.W;
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
-  // ---- operand prefetch: every global read of the epilogue (residual or ReLU mask) is issued here, before the
-  // TMEM drain, so that one DRAM latency is exposed per accumulator instead of one per unrolled group.
-  // pre[] holds: fp32 residual of pixel pairs 0..7 (2 x 16 B each; pairs 8..15 are fetched between the passes),
-  // or the bf16 residual / the mask of all 16 pairs.
   const int half = lane >> 4, q = lane & 15;
-  int pixs[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) pixs[i] = __shfl_sync(0xffffffffu, my_pix, 2 * i + half);
-  constexpr int pf_mode = EPI;  // 0: no global operand, 1: fp32 residual, 2: bf16 residual, 3: ReLU mask
-  uint4 pre[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (pf_mode == 1) {
+  constexpr int NPRE = EPI == 1 ? 16 : 8;
+  uint4 pre[NPRE];
+  auto prefetch = [&](int pass) {
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
-      const int pix = pixs[ii];
-      if (pix >= 0) {
-        const uint4* rp = reinterpret_cast<const uint4*>(P.res_f32 + (size_t)pix * 128 + q * 8);
-        pre[2 * ii] = rp[0];
-        pre[2 * ii + 1] = rp[1];
-      }
-    }
-  } else if (pf_mode != 0) {
-    const __nv_bfloat16* src = pf_mode == 2 ? P.res_bf16 : P.relu_mask_bf16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int pix = pixs[i];
-      if (pix >= 0) pre[i] = *reinterpret_cast<const uint4*>(src + (size_t)pix * 128 + q * 8);
-    }
-  }
-  uint8_t* my_row = stage + lane * 256;
-  const int sw = lane & 7;
-#pragma unroll 1
-  for (int cb = 0; cb < 4; ++cb) {
-    uint32_t v[32];
-    tmem_ld32(t_acc + cb * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = q * 8 + e * 2;
-        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-        w[e] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-  __syncwarp();
-  // ---- phase 2: 16 lanes per pixel, 2 pixels per warp instruction; two passes of 8 pixel pairs whose
-  // residual / mask operands were all requested up front (pre[])
-  float bs[8];  // alpha * bias of this lane's 8 channels
-#pragma unroll
-  for (int e = 0; e < 8; ++e) bs[e] = P.alpha * s_bias[q * 8 + e];
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1 && pf_mode == 1) {
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const int pix = pixs[8 + ii];
+      const int pix = __shfl_sync(0xffffffffu, my_pix, 2 * (pass * 8 + ii) + half);
+      if constexpr (EPI == 1) {
+        pre[2 * ii] = pre[2 * ii + 1] = make_uint4(0u, 0u, 0u, 0u);
         if (pix >= 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(P.res_f32 + (size_t)pix * 128 + q * 8);
           pre[2 * ii] = rp[0];
           pre[2 * ii + 1] = rp[1];
         }
+      } else {
+        const __nv_bfloat16* src = EPI == 2 ? P.res_bf16 : P.relu_mask_bf16;
+        pre[ii] = make_uint4(0u, 0u, 0u, 0u);
+        if (pix >= 0) pre[ii] = *reinterpret_cast<const uint4*>(src + (size_t)pix * 128 + q * 8);
       }
     }
+  };
+  prefetch(0);
+  uint8_t* my_row = stage + lane * 256;
+  const int sw = lane & 7;
+  // ---- phase 1: drain TMEM (lane = pixel), two loads in flight per wait
+#pragma unroll 1
+  for (int cb2 = 0; cb2 < 2; ++cb2) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_acc + cb2 * 64, va);
+    tmem_ld32(t_acc + cb2 * 64 + 32, vb);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = qq * 8 + e * 2;
+          const float f0 = __uint_as_float(hh ? vb[j] : va[j]), f1 = __uint_as_float(hh ? vb[j + 1] : va[j + 1]);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(my_row + ((((cb2 * 2 + hh) * 4 + qq) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- phase 2: 16 lanes per pixel, 2 pixels per warp instruction
+  float bs[8];  // alpha * bias of this lane's 8 channels
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = P.alpha * s_bias[q * 8 + e];
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) prefetch(1);
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
-      const int i = pass * 8 + ii;
-      const int r = 2 * i + half;
-      const int pix = pixs[i];
+      const int r = 2 * (pass * 8 + ii) + half;
+      const int pix = __shfl_sync(0xffffffffu, my_pix, r);
       if (pix < 0) continue;
       const uint4 sv = *reinterpret_cast<const uint4*>(stage + r * 256 + ((q ^ (r & 7)) << 4));
       const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
@@ -277,14 +252,14 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
         o[2 * e + 1] = fmaf(P.alpha, __uint_as_float(w[e] & 0xFFFF0000u), bs[2 * e + 1]);
       }
       const size_t off = (size_t)pix * 128 + q * 8;
-      if (pf_mode == 1) {
+      if constexpr (EPI == 1) {
         const uint4 r0 = pre[2 * ii], r1 = pre[2 * ii + 1];
         o[0] = fmaf(P.beta, __uint_as_float(r0.x), o[0]); o[1] = fmaf(P.beta, __uint_as_float(r0.y), o[1]);
         o[2] = fmaf(P.beta, __uint_as_float(r0.z), o[2]); o[3] = fmaf(P.beta, __uint_as_float(r0.w), o[3]);
         o[4] = fmaf(P.beta, __uint_as_float(r1.x), o[4]); o[5] = fmaf(P.beta, __uint_as_float(r1.y), o[5]);
         o[6] = fmaf(P.beta, __uint_as_float(r1.z), o[6]); o[7] = fmaf(P.beta, __uint_as_float(r1.w), o[7]);
-      } else if (pf_mode == 2) {
-        const uint4 rv = pre[i];
+      } else if constexpr (EPI == 2) {
+        const uint4 rv = pre[ii];
         const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -296,8 +271,8 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
       }
-      if (pf_mode == 3) {
-        const uint4 mv = pre[i];
+      if constexpr (EPI == 3) {
+        const uint4 mv = pre[ii];
         const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -323,11 +298,106 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
   __syncwarp();
 }
 
+// Sub-pixel epilogue (EPI = 4): conv + bias (+ReLU) whose fp32 result is stored straight at its depth-to-space
+// position (keras_subpixel.py:64-84, advanced.py:87-129,195-196) -- the shuffle is only a store address.
+__device__ __noinline__ void epilogue_shuffle_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
+                                                  int f_base, const float* s_bias, int lane, bool live) {
+  const int f = f_base + lane;
+  const int fr = f / P.PWs;
+  const int yy = fr - P.p;
+  const int xx = f - fr * P.PWs - P.p;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const int r_ = P.shuffle_r, C_ = P.shuffle_C;
+  const int x = c.seg_x0 + xx;
+  const size_t orow = (size_t)P.W * r_;
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(t_acc + cb * 32, v);
+    tmem_ld_wait();
+    if (!valid) continue;
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int ch = cb * 32 + j;
+      if (ch >= P.cout) break;
+      // same rounding as the staged epilogues: accumulator -> bf16, then alpha / bias / ReLU in fp32
+      float o = fmaf(P.alpha, __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))), P.alpha * s_bias[ch]);
+      if (P.relu) o = fmaxf(o, 0.f);
+      int cc, ry, rx;
+      if (P.shuffle_order == 0) { cc = ch / (r_ * r_); rx = (ch / r_) % r_; ry = ch % r_; }
+      else if (P.shuffle_order == 1) { cc = ch / (r_ * r_); ry = (ch / r_) % r_; rx = ch % r_; }
+      else { cc = ch % C_; ry = (ch / C_) / r_; rx = (ch / C_) % r_; }
+      P.out_f32[(((size_t)c.n * P.H * r_ + (yy * r_ + ry)) * orow + (x * r_ + rx)) * C_ + cc] = o;
+    }
+  }
+}
+
+// Lean epilogue for the commonest launch (conv + bias + ReLU -> bf16, no residual / mask / fp32 copy): small code
+// keeps the whole kernel inside the instruction cache, which is what bounds the 3x3 convs (their MMA phase per
+// tile is too short to hide a slow epilogue).
+__device__ __forceinline__ void epilogue_staged_acc_plain(const ConvKernelParams& P, const TileCoord& c,
+                                                          uint32_t t_acc, int f_base, uint8_t* stage,
+                                                          const float* s_bias, int lane, bool live) {
+  const int f = f_base + lane;
+  const int fr = f / P.PWs;
+  const int yy = fr - P.p;
+  const int xx = f - fr * P.PWs - P.p;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
+  uint8_t* my_row = stage + lane * 256;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(t_acc + cb * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q * 8 + e * 2;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(my_row + (((cb * 4 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  __syncwarp();
+  const int half = lane >> 4, q = lane & 15;
+  float bs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = P.alpha * s_bias[q * 8 + e];
+  const float lo = P.relu ? 0.f : -3.4e38f;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = 2 * i + half;
+    const int pix = __shfl_sync(0xffffffffu, my_pix, r);
+    if (pix < 0) continue;
+    const uint4 sv = *reinterpret_cast<const uint4*>(stage + r * 256 + ((q ^ (r & 7)) << 4));
+    const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint32_t pw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float o0 = fmaxf(fmaf(P.alpha, __uint_as_float(w[e] << 16), bs[2 * e]), lo);
+      const float o1 = fmaxf(fmaf(P.alpha, __uint_as_float(w[e] & 0xFFFF0000u), bs[2 * e + 1]), lo);
+      const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+      pw[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(P.out_bf16 + (size_t)pix * 128 + q * 8) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+  }
+  __syncwarp();
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
                                              int f_base, uint8_t* stage, const float* s_bias, int lane,
                                              bool live = true) {
   if constexpr (EPI < 0) epilogue_staged_acc_generic(P, c, t_acc, f_base, stage, s_bias, lane, live);
+  else if constexpr (EPI == 0) epilogue_staged_acc_plain(P, c, t_acc, f_base, stage, s_bias, lane, live);
+  else if constexpr (EPI == 4) epilogue_shuffle_acc(P, c, t_acc, f_base, s_bias, lane, live);
   else epilogue_staged_acc<EPI>(P, c, t_acc, f_base, stage, s_bias, lane, live);
 }
 
@@ -786,7 +856,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                           stage_buf + ew * (32 * 256), s_bias, lane, live);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
     }
   }
 
@@ -964,11 +1034,13 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (!d || !out) return set_error(SR_ERR_INVALID, "sr_conv_plan_create: null argument");
   if (d->nsrc < 1 || d->nsrc > 2) return set_error(SR_ERR_INVALID, "nsrc must be 1 or 2");
   if (d->cin != kCin) return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv requires cin == 128");
-  if (!(d->cout == 128 || (d->cout >= 1 && d->cout <= 16) || (d->shuffle_r > 0 && d->cout >= 1 && d->cout < 128)))
+  if (!(d->cout == 128 || (d->cout >= 1 && d->cout <= 16) || (d->shuffle_r > 0 && d->cout > 16 && d->cout < 128)))
     return set_error(SR_ERR_UNSUPPORTED, "tensor-core conv supports cout == 128 or cout <= 16 (any cout <= 128 with shuffle_r)");
   if (d->shuffle_r > 0 && (d->cout % (d->shuffle_r * d->shuffle_r) != 0 || !d->out_f32 || d->out_bf16 ||
                            d->shuffle_order < 0 || d->shuffle_order > 2))
     return set_error(SR_ERR_INVALID, "shuffle_r needs cout divisible by r*r, an fp32 output only, order 0..2");
+  if (d->shuffle_r > 0 && (d->cout <= 16 || d->res_f32 || d->res_bf16 || d->relu_mask_bf16 || d->a_mode == 1))
+    return set_error(SR_ERR_UNSUPPORTED, "shuffle_r: 16 < cout <= 128, no residual / mask, a_mode 0");
   if (d->NB < 1 || d->H < 1 || d->W < 1) return set_error(SR_ERR_INVALID, "empty tensor");
   int p = 0;
   for (int s = 0; s < d->nsrc; ++s) {
@@ -983,7 +1055,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   memset(pl, 0, sizeof *pl);
   pl->n_pad = (d->cout == 128 || d->shuffle_r > 0) ? 128 : 16;
   pl->amode = d->a_mode == 1 ? kAModeInterleave : kAModeSwizzle64;
-  pl->nacc = (d->nacc == 2 && pl->n_pad == 128) ? 2 : 4;
+  pl->nacc = ((d->nacc == 2 || d->shuffle_r > 0) && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
   pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
   const int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kChunk * 2;
@@ -1064,13 +1136,16 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   // epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
   const ConvKernelParams& P = pl->P;
   const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
-  const int epi = (nops != 1 || P.shuffle_r) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32;
+  const int epi = P.shuffle_r ? 4 : plain ? 0 : nops != 1 ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
     switch (epi) {
+      case 0: return launch_pair<2, 2, 0>(pl, st);
       case 1: return launch_pair<2, 2, 1>(pl, st);
       case 2: return launch_pair<2, 2, 2>(pl, st);
       case 3: return launch_pair<2, 2, 3>(pl, st);
+      case 4: return launch_pair<2, 2, 4>(pl, st);
       default: return launch_pair<2, 2>(pl, st);
     }
   }
@@ -1078,9 +1153,11 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
     if (pl->amode == kAModeSwizzle64) {
       if (pl->nacc == 4) return launch_variant<128, kAModeSwizzle64, 4, 1>(pl, st);
       switch (epi) {
+        case 0: return launch_variant<128, kAModeSwizzle64, 2, 2, 0>(pl, st);
         case 1: return launch_variant<128, kAModeSwizzle64, 2, 2, 1>(pl, st);
         case 2: return launch_variant<128, kAModeSwizzle64, 2, 2, 2>(pl, st);
         case 3: return launch_variant<128, kAModeSwizzle64, 2, 2, 3>(pl, st);
+        case 4: return launch_variant<128, kAModeSwizzle64, 2, 2, 4>(pl, st);
         default: return launch_variant<128, kAModeSwizzle64, 2, 2>(pl, st);
       }
     }

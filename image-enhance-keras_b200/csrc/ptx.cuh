@@ -232,6 +232,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// Relaxed variant for "TMEM accumulator drained": the tcgen05.ld results are already in registers
+// (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; no generic-proxy data is published, so the
+// arrive need not wait for this thread's outstanding global stores (a .release at cluster scope does).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
 // TMA loads whose completion bytes are credited to a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t bar_cluster_addr,
                                                  int c0, int c1) {

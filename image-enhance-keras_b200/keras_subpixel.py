@@ -66,7 +66,7 @@ class Subpixel(object):
         w = ops.to_device(self.kernel)
         b = ops.to_device(self.bias) if self.use_bias else None
         k = self.kernel_size[0]
-        if (x.shape[-1] == 128 and self.padding == 'same' and k in (1, 3, 5) and self.filters <= 128
+        if (x.shape[-1] == 128 and self.padding == 'same' and k in (1, 3, 5) and 16 < self.filters <= 128
                 and not isinstance(inputs, np.ndarray) and inputs.dtype == torch.bfloat16):
             # a 128-channel bf16 feature map (the width of the models.py stack): tensor-core conv, shuffle in its epilogue
             y = ops.conv2d_tc_shuffle(inputs.contiguous(), w, b, self.r, 0, relu=(self.activation == 'relu'))

@@ -299,33 +299,61 @@ __global__ void patch_stitch_kernel(const float* __restrict__ patches, int cnt_h
 // Four consecutive output elements per thread (16-byte patch load, 4-byte uint8 store).  Valid when every
 // ownership boundary and row length is a multiple of 4 elements: 3*S, 3*crop, 3*PW, 3*out_w all % 4 == 0
 // (true for the reference's 96/64/x4/8-px geometry); the host falls back to the scalar kernel otherwise.
-__global__ void patch_stitch_vec4_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH,
-                                         int PW, int S, int crop, int out_h, int out_w, float mul,
-                                         float4* __restrict__ out_f32, uint32_t* __restrict__ out_u8) {
+__global__ void __launch_bounds__(256)
+patch_stitch_vec4_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH, int PW, int S, int crop,
+                         int out_h, int out_w, float mul, float4* __restrict__ out_f32,
+                         uint32_t* __restrict__ out_u8) {
+  // one thread = 4 consecutive quads (16 output elements) of one output row: the row owner is found once, the
+  // four 16-byte patch loads are issued together, the uint8 result leaves as one 16-byte store when aligned
   const int row_q = out_w * 3 / 4;
-  const size_t total = (size_t)out_h * row_q;
+  const int row_g = (row_q + 3) / 4;
+  const size_t total = (size_t)out_h * row_g;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int q = (int)(idx % row_q);
-    const int Y = (int)(idx / row_q);
-    const int e = q * 4;
-    const int X = e / 3;
+    const int g = (int)(idx % row_g);
+    const int Y = (int)(idx / row_g);
     const int i = stitch_owner(Y, cnt_h, S, PH, crop);
-    const int j = stitch_owner(X, cnt_w, S, PW, crop);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i >= 0 && j >= 0) {
-      const size_t n = (size_t)j * cnt_h + i;
-      const float4 p = *reinterpret_cast<const float4*>(
-          patches + ((n * PH + (Y - S * i)) * PW) * 3 + (e - 3 * S * j));
-      v = make_float4(__fmul_rn(p.x, mul), __fmul_rn(p.y, mul), __fmul_rn(p.z, mul), __fmul_rn(p.w, mul));
+    float4 v[4];
+    bool have[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int q = g * 4 + k;
+      have[k] = q < row_q;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (have[k] && i >= 0) {
+        const int e = q * 4;
+        const int j = stitch_owner(e / 3, cnt_w, S, PW, crop);
+        if (j >= 0) {
+          const size_t n = (size_t)j * cnt_h + i;
+          v[k] = *reinterpret_cast<const float4*>(patches + ((n * PH + (Y - S * i)) * PW) * 3 + (e - 3 * S * j));
+        }
+      }
     }
-    if (out_f32) out_f32[idx] = v;
+    uint32_t packed[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = make_float4(__fmul_rn(v[k].x, mul), __fmul_rn(v[k].y, mul), __fmul_rn(v[k].z, mul),
+                         __fmul_rn(v[k].w, mul));
+      const uint32_t b0 = (uint32_t)(int)fminf(fmaxf(v[k].x, 0.f), 255.f);
+      const uint32_t b1 = (uint32_t)(int)fminf(fmaxf(v[k].y, 0.f), 255.f);
+      const uint32_t b2 = (uint32_t)(int)fminf(fmaxf(v[k].z, 0.f), 255.f);
+      const uint32_t b3 = (uint32_t)(int)fminf(fmaxf(v[k].w, 0.f), 255.f);
+      packed[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    const size_t q0 = (size_t)Y * row_q + (size_t)g * 4;
+    if (out_f32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (have[k]) out_f32[q0 + k] = v[k];
+    }
     if (out_u8) {
-      const uint32_t b0 = (uint32_t)(int)fminf(fmaxf(v.x, 0.f), 255.f);
-      const uint32_t b1 = (uint32_t)(int)fminf(fmaxf(v.y, 0.f), 255.f);
-      const uint32_t b2 = (uint32_t)(int)fminf(fmaxf(v.z, 0.f), 255.f);
-      const uint32_t b3 = (uint32_t)(int)fminf(fmaxf(v.w, 0.f), 255.f);
-      out_u8[idx] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      if (have[3] && (q0 & 3) == 0) {
+        *reinterpret_cast<uint4*>(out_u8 + q0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (have[k]) out_u8[q0 + k] = packed[k];
+      }
     }
   }
 }
@@ -601,9 +629,9 @@ extern "C" int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int p
   const int S = step * scale, PW = pw * scale, crop = 8;
   const bool vec_ok = (3 * S) % 4 == 0 && (3 * crop) % 4 == 0 && (3 * PW) % 4 == 0 && (3 * out_w) % 4 == 0 &&
                       ((reinterpret_cast<uintptr_t>(patches) | reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0;
+                      (reinterpret_cast<uintptr_t>(out_u8) & 15) == 0;
   if (vec_ok) {
-    patch_stitch_vec4_kernel<<<grid_for(total / 4, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+    patch_stitch_vec4_kernel<<<grid_for((size_t)out_h * ((out_w * 3 / 4 + 3) / 4), kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
         patches, cnt_h, cnt_w, ph * scale, PW, S, crop, out_h, out_w, mul, reinterpret_cast<float4*>(out_f32),
         reinterpret_cast<uint32_t*>(out_u8));
     return check_launch("patch_stitch_vec4_kernel");

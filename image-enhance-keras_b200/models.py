@@ -256,6 +256,12 @@ class BaseSuperResolutionModel(object):
         arrays -> list of uint8 (4H,4W,3) host arrays.  Tiles of all images share one pass over the conv stack.
         The timed end-to-end path of bench.py: host -> device copies in, device -> host copies out."""
         import torch
+        images = [np.asarray(im) for im in images]
+        for im in images:
+            if im.ndim != 3 or im.shape[2] != 3 or im.dtype != np.uint8 or im.shape[0] < 1 or im.shape[1] < 1:
+                raise ValueError("upscale_arrays expects uint8 arrays of shape (H, W, 3), got %s %s" % (im.shape, im.dtype))
+        if not images:
+            return []
         model = self.model if self.model is not None else self.create_model(patch_size, patch_size, load_weights=False)
         eng = model.engine
         dev = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().to(eng.device, non_blocking=True)

@@ -81,3 +81,20 @@ def test_large_image_config5_shape_and_identity(sr_model):
     canvas = sr_model.upscale_arrays([img], return_canvas=True)[0]
     assert canvas.shape == (4 * 1216, 4 * 2048, 3)
     assert np.array_equal(fast, canvas[:4320, :7680])
+
+
+def test_edge_shapes_and_empty(sr_model):
+    """Empty batch, 1x1 image, exact multiples of the 64-px step, very thin images: shapes follow 4H x 4W and the
+    fast path still equals the literal tiling."""
+    assert sr_model.upscale_arrays([]) == []
+    rng = np.random.default_rng(21)
+    shapes = [(1, 1), (64, 64), (32, 160), (1, 300), (97, 3)]
+    imgs = [rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in shapes]
+    fast = sr_model.upscale_arrays(imgs)
+    canv = sr_model.upscale_arrays(imgs, return_canvas=True)
+    for im, f, c in zip(imgs, fast, canv):
+        h, w = im.shape[:2]
+        assert f.shape == (4 * h, 4 * w, 3)
+        assert np.array_equal(f, c[:4 * h, :4 * w])
+    with pytest.raises((ValueError, RuntimeError)):
+        sr_model.upscale_arrays([np.zeros((8, 8), dtype=np.uint8)])       # not H x W x 3

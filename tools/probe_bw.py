@@ -90,6 +90,17 @@ def main():
     timed("patch_stitch_kernel", 16 * ch * cw * 3 * (4 + 1),
           lambda: ops.patch_stitch(outp, cnt, (96, 96), 64, 4, (ch, cw), mul=255.0, want_f32=False, want_u8=True),
           "one 339x510 image (448x640 canvas x4); 15 B per output pixel")
+    # ---- the same two kernels at config-5 size (one 1080x1920 image, 558 tiles): enough bytes to leave launch latency
+    big = torch.randint(0, 256, (1080, 1920, 3), dtype=torch.uint8, device=dev)
+    bch, bcw = ops.canvas_size(1080, 1920)
+    timed("patch_gather_vec4_kernel (1080x1920)", 1080 * 1920 * 3 + 558 * 96 * 96 * 3 * 4,
+          lambda: ops.patch_gather_u8(big, (bch, bcw), (96, 96), 64), "558 tiles; includes the output allocation")
+    bout = torch.rand(558, 384, 384, 3, device=dev)
+    bcnt = (ops.patch_count(bch, 96, 64), ops.patch_count(bcw, 96, 64))
+    timed("patch_stitch_vec4_kernel (1080x1920 -> 4320x7680)", 16 * 1080 * 1920 * 3 * (4 + 1),
+          lambda: ops.patch_stitch(bout, bcnt, (96, 96), 64, 4, (1080, 1920), mul=255.0, want_f32=False, want_u8=True),
+          "stitched straight into the final 4H x 4W image; 15 B per output pixel")
+    del bout
     # ---- scoring: two uint8 1356x2040 RGB images
     a8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)
     b8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)

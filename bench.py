@@ -185,6 +185,8 @@ def main():
     m = models.DifvdsrDouble(1)
     model = m.create_model(96, 96)                      # random-init glorot weights (no trained weights offline)
     eng = model.engine
+    from sr100.engine import glorot_uniform_weights
+    eng.set_weights_dict(glorot_uniform_weights(seed=1234))   # the same replica on every rank
     dev_imgs = [torch.from_numpy(im).cuda() for im in images]
     rng = np.random.default_rng(7 + rank)
     gts = [rng.integers(0, 256, size=(4 * h, 4 * w, 3)).astype(np.uint8) for h, w in SET5_SHAPES]

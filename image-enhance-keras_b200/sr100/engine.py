@@ -414,6 +414,40 @@ class Engine:
             off += n
         return res
 
+    def upscale_image_sharded(self, img_u8, patch=96, step=64, scale=4):
+        """One (large) image with its tiles sharded over the ranks of the process group (BASELINE config
+        5): every rank runs a contiguous range of the column-major live-tile index through the conv stack -- no
+        exchange on the data path -- then the fp32 patch outputs are gathered on rank 0 (NCCL over NVLink), which
+        stitches and quantises.  Returns the uint8 [4h,4w,3] device image on rank 0, None elsewhere."""
+        import torch.distributed as tdist
+        from . import ops
+        from .dist import shard_range
+        h, w, _ = img_u8.shape
+        (gh, gw), counts, ext = plan_tiles(h, w, patch, step, scale, False)
+        p, got = ops.patch_gather_u8(img_u8, (gh, gw), (patch, patch), step, divisor=255.0)
+        n_tiles = p.shape[0]
+        if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
+            out = self.forward_device(p, extents=ext)
+        else:
+            rank, world = tdist.get_rank(), tdist.get_world_size()
+            lo, hi = shard_range(n_tiles, rank, world)
+            nmax = (n_tiles + world - 1) // world
+            send = torch.zeros(nmax, scale * patch, scale * patch, 3, device=self.device, dtype=torch.float32)
+            if hi > lo:
+                self.forward_device(p[lo:hi], out=send[:hi - lo], extents=ext[lo:hi])
+            recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+            tdist.gather(send, recv, dst=0)
+            if rank != 0:
+                return None
+            parts = []
+            for r in range(world):
+                rlo, rhi = shard_range(n_tiles, r, world)
+                parts.append(recv[r][:rhi - rlo])
+            out = torch.cat(parts, dim=0)
+        _, u8 = ops.patch_stitch(out, counts, (patch, patch), step, scale, (h, w), mul=255.0, want_f32=False,
+                                 want_u8=True)
+        return u8
+
     def last_flops(self):
         """Algorithmic FLOPs (2*MAC) of the tensor-core launches of the most recent forward_device call."""
         return float(sum(st.conv_flops for st in getattr(self, "last_stages", [])))

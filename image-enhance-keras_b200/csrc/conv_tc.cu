@@ -740,12 +740,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t slot = wr.slot, ph = wr.phase;
               mbar_wait(&bars->w_empty[slot], ph ^ 1);
-              if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * WSTAGE);
+              const int nbox = min(kTapsPerStage, ntaps - tap);  // an odd last tap loads one box only
+              if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * nbox * WTAP);
               const uint32_t bar = mapa_shared(smem_u32(&bars->w_full[slot]), 0);
 #pragma unroll
-              for (int j = 0; j < kTapsPerStage; ++j)  // always both boxes: constant byte count per stage
-                tma_load_2d_pair(w_buf + slot * WSTAGE + j * WTAP, tmW, bar, 0,
-                                 (ch * ntaps + tap + j) * N_ + (int)rank * (N_ / 2));
+              for (int j = 0; j < kTapsPerStage; ++j)
+                if (j < nbox)
+                  tma_load_2d_pair(w_buf + slot * WSTAGE + j * WTAP, tmW, bar, 0,
+                                   (ch * ntaps + tap + j) * N_ + (int)rank * (N_ / 2));
               wr.advance();
             }
           }

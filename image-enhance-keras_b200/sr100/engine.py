@@ -180,9 +180,15 @@ class _LRStage(_Stage):
         key = (n, eh, ew)
         st = self.hr.get(key)
         if st is None:
-            if len(self.hr) >= 6:
+            if len(self.hr) >= 4:
                 self.hr.pop(next(iter(self.hr)))
-            st = _HRStage(self, n, eh, ew)
+            try:
+                st = _HRStage(self, n, eh, ew)
+            except torch.cuda.OutOfMemoryError:
+                for other in self.eng._graphs.values():     # free every other cached HR stage, keep this LR stage
+                    other.hr.clear()
+                torch.cuda.empty_cache()
+                st = _HRStage(self, n, eh, ew)
             self.hr[key] = st
         return st
 
@@ -345,9 +351,21 @@ class Engine:
         if g is None:
             if len(self._graphs) >= 4:  # bound device memory: keep the most recent shapes only
                 self._graphs.pop(next(iter(self._graphs)))
-            g = _LRStage(self, NB, H, W)
+            g = self._with_oom_retry(lambda: _LRStage(self, NB, H, W))
             self._graphs[key] = g
         return g
+
+    def _with_oom_retry(self, make):
+        """Stage buffers are cached per shape; if a new shape does not fit next to the cached ones, drop every cached
+        stage (their buffers return to the allocator) and try once more."""
+        try:
+            return make()
+        except torch.cuda.OutOfMemoryError:
+            for st in self._graphs.values():
+                st.hr.clear()
+            self._graphs.clear()
+            torch.cuda.empty_cache()
+            return make()
 
     def sub_batch(self, H, W):
         return max(1, self.max_pixels // (H * W))

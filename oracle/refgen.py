@@ -146,6 +146,36 @@ def main():
         tiling["raises_h"] = np.array([1])
     np.savez_compressed(os.path.join(OUT, "tiling_ref.npz"), **tiling)
 
+    # ---- training data pipeline: _index_generator / image_generator (img_utils.py:290-398) ----------------
+    gen = {}
+    for gi, (N, bs, shuffle, seed) in enumerate([(10, 4, True, 3), (7, 7, True, 11), (5, 2, False, None), (3, 8, True, 0)]):
+        g = iu._index_generator(N, bs, shuffle, seed)
+        idx, cur, cbs = [], [], []
+        for _ in range(9):
+            a_, c_, b_ = next(g)
+            idx.append(np.pad(np.asarray(a_), (0, bs - len(a_)), constant_values=-1))
+            cur.append(c_)
+            cbs.append(b_)
+        gen["g%d_args" % gi] = np.array([N, bs, int(shuffle), -1 if seed is None else seed])
+        gen["g%d_idx" % gi] = np.array(idx)
+        gen["g%d_cur" % gi] = np.array(cur)
+        gen["g%d_bs" % gi] = np.array(cbs)
+    # image_generator on a temp dataset of 16x16 PNG pairs (the only shape the shipped defaults accept:
+    # scale_factor=1 -> image_shape (16,16,3) for X and y, img_utils.py:302-309)
+    from PIL import Image
+    d = tempfile.mkdtemp(prefix="refdata_") + "/"
+    os.makedirs(d + "X")
+    os.makedirs(d + "y")
+    drng = np.random.default_rng(77)
+    for k in range(5):
+        Image.fromarray(drng.integers(0, 256, size=(16, 16, 3)).astype(np.uint8)).save(d + "X/im%d.png" % k)
+        Image.fromarray(drng.integers(0, 256, size=(16, 16, 3)).astype(np.uint8)).save(d + "y/im%d.png" % k)
+    ig = quiet(lambda: iu.image_generator(d, scale_factor=1, shuffle=True, batch_size=2, seed=5))
+    bx, by = quiet(next, ig)
+    bx2, by2 = quiet(next, ig)
+    gen["ig_bx"], gen["ig_by"], gen["ig_bx2"], gen["ig_by2"] = bx, by, bx2, by2
+    np.savez_compressed(os.path.join(OUT, "generator_ref.npz"), **gen)
+
     # ---- PSNR.py ---------------------------------------------------------------------------------
     P = load_psnr()
     a = rng.integers(0, 256, size=(40, 52, 3)).astype(np.uint8)

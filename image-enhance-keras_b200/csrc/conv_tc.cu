@@ -73,8 +73,8 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
-  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.Wc;
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
   uint8_t* my_row = stage + lane * 256;
   const int sw = lane & 7;
@@ -180,8 +180,8 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
-  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.Wc;
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
   const int half = lane >> 4, q = lane & 15;
   constexpr int NPRE = EPI == 1 ? 16 : 8;
@@ -306,8 +306,8 @@ __device__ __noinline__ void epilogue_shuffle_acc(const ConvKernelParams& P, con
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
-  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.Wc;
   const int r_ = P.shuffle_r, C_ = P.shuffle_C;
   const int x = c.seg_x0 + xx;
   const size_t orow = (size_t)P.W * r_;
@@ -343,8 +343,8 @@ __device__ __forceinline__ void epilogue_staged_acc_plain(const ConvKernelParams
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
-  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                     xx < P.BW && (c.seg_x0 + xx) < P.W;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.Wc;
   const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
   uint8_t* my_row = stage + lane * 256;
   const int sw = lane & 7;
@@ -609,8 +609,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int fr = f / P.PWs;
           const int yy = fr - P.p;
           const int xx = f - fr * P.PWs - P.p;
-          const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.H && xx >= 0 &&
-                             xx < P.BW && (c.seg_x0 + xx) < P.W;
+          const bool valid = (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                             xx < P.BW && (c.seg_x0 + xx) < P.Wc;
           const size_t pix = ((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx;
           // optional scatter: image n lands in slot out_index[n] of a tensor of out_H x out_W images
           size_t opix = pix;
@@ -1074,7 +1074,13 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "more than 2^31 pixels per tensor");
   }
-  if (!choose_geometry(d->H, d->W, p, T, wstage, stage_bytes, &P)) {
+  // compute extents: only the top-left comp_h x comp_w corner of every image is produced (the input tensor keeps
+  // its real data beyond it, so nothing but the true image border is zero-padded)
+  const int Hc = (d->comp_h > 0 && d->comp_h < d->H) ? d->comp_h : d->H;
+  const int Wc = (d->comp_w > 0 && d->comp_w < d->W) ? d->comp_w : d->W;
+  P.Hc = Hc;
+  P.Wc = Wc;
+  if (!choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P)) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "no conv geometry fits shared memory");
   }
@@ -1109,7 +1115,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
       delete pl;
       return rc;
     }
-    macs += (double)d->NB * d->H * d->W * d->ksize[s] * d->ksize[s] * kCin * d->cout;
+    macs += (double)d->NB * Hc * Wc * d->ksize[s] * d->ksize[s] * kCin * d->cout;
   }
   if (d->nsrc == 1) {
     pl->tmA[1] = pl->tmA[0];
@@ -1187,6 +1193,6 @@ extern "C" int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* 
   info->num_wstages = pl->P.num_wstages;
   info->tile_positions = pl->nacc * 128;
   info->mma_efficiency =
-      (double)pl->P.NB * pl->P.H * pl->P.W / ((double)pl->P.total_tiles * pl->nacc * 128);
+      (double)pl->P.NB * pl->P.Hc * pl->P.Wc / ((double)pl->P.total_tiles * pl->nacc * 128);
   return SR_OK;
 }

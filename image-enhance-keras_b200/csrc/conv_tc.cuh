@@ -32,7 +32,8 @@ enum ConvAMode : int {
 struct ConvKernelParams {
   int nsrc;          // 1 or 2 K-concatenated sources (second half of a 5/3 block)
   int ksize[2];
-  int H, W, NB;
+  int H, W, NB;     // tensor dims (addressing, TMA bounds)
+  int Hc, Wc;       // compute extents (<= H, W): pixels outside are neither produced nor stored
   int p;             // geometry halo = max (k-1)/2 over sources
   int BW, nseg, PWs, NR;
   int tiles_per_seg, total_tiles;

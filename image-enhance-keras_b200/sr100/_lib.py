@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("out_index", C.c_void_p),
         ("out_h", C.c_int), ("out_w", C.c_int),
         ("shuffle_r", C.c_int), ("shuffle_order", C.c_int),
+        ("comp_h", C.c_int), ("comp_w", C.c_int),
     ]
 
 

@@ -92,7 +92,7 @@ class _Stage:
         self.cuda_graph, self.ran_eager = None, False
 
     def _conv(self, srcs, shape, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0, res32=None, res16=None,
-              cout=NUMK, out_index=None, out_hw=None):
+              cout=NUMK, out_index=None, out_hw=None, comp=None):
         eng = self.eng
         d = L.ConvDesc()
         d.nsrc = len(srcs)
@@ -111,20 +111,24 @@ class _Stage:
         if out_index is not None:
             d.out_index, (d.out_h, d.out_w) = out_index.data_ptr(), out_hw
         d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
+        if comp is not None:
+            d.comp_h, d.comp_w = comp
         p = _Plan(eng.lib, d)
         self.conv_flops += p.flops
         self.steps.append(p.run)
         return p
 
-    def _block53(self, names, i, s, s32, t1, t2, shape):
-        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1)
-        self._conv([(names[i + 2], s)], shape, out_bf16=t2, relu=1)
+    def _block53(self, names, i, s, s32, t1, t2, shape, comp=(None, None, None)):
+        # comp = compute extents (out, t1, t2): t1 feeds the 5x5 (radius 2), t2 the 3x3 (radius 1)
+        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1, comp=comp[1])
+        self._conv([(names[i + 2], s)], shape, out_bf16=t2, relu=1, comp=comp[2])
         self._conv([(names[i + 1], t1), (names[i + 3], t2)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=0.9,
-                   res32=s32, res16=s)
+                   res32=s32, res16=s, comp=comp[0])
 
-    def _block_light(self, names, i, s, s32, t1, shape):
-        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1)
-        self._conv([(names[i + 1], t1)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=1.0, res32=s32, res16=s)
+    def _block_light(self, names, i, s, s32, t1, shape, comp=(None, None)):
+        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1, comp=comp[1])
+        self._conv([(names[i + 1], t1)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=1.0, res32=s32, res16=s,
+                   comp=comp[0])
 
     def run(self):
         eng = self.eng
@@ -151,10 +155,15 @@ class _LRStage(_Stage):
     """Low-resolution stage for NB patches of HxW: head 1x1 + 16 5/3 blocks + 6 light blocks.  Owns the patch
     input buffer, the LR residual stream (the HR stages read it) and the full-size output patch slots."""
 
-    def __init__(self, eng, NB, H, W):
+    def __init__(self, eng, NB, H, W, need=None):
+        """need = (rows, cols) of the final LR stream that the HR stage will read (None: everything).  The layers
+        are then restricted, last to first, to the region whose receptive field can still reach it: a light block
+        grows the needed region by 2 pixels per axis, a 5/3 block by 3 (lr_extents)."""
         self._init_stage(eng)
         dev, bf, f32 = eng.device, torch.bfloat16, torch.float32
         self.NB, self.H, self.W = NB, H, W
+        self.need = (H, W) if need is None else (min(H, need[0]), min(W, need[1]))
+        exts = lr_extents(self.need, (H, W))
         self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
         self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=bf)
         self.t1_lr = torch.empty_like(self.s_lr)
@@ -168,11 +177,11 @@ class _LRStage(_Stage):
         self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
             L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, L.ptr(self.s_lr), L.ptr(self.s_lr32), st)))
         i, lr = 1, (NB, H, W)
-        for _ in range(16):
-            self._block53(names, i, self.s_lr, self.s_lr32, self.t1_lr, self.t2_lr, lr)
+        for b in range(16):
+            self._block53(names, i, self.s_lr, self.s_lr32, self.t1_lr, self.t2_lr, lr, comp=exts[b])
             i += 4
-        for _ in range(6):
-            self._block_light(names, i, self.s_lr, self.s_lr32, self.t1_lr, lr)
+        for b in range(16, 22):
+            self._block_light(names, i, self.s_lr, self.s_lr32, self.t1_lr, lr, comp=exts[b])
             i += 2
         self.first_hr_layer = i
 
@@ -225,6 +234,25 @@ class _HRStage(_Stage):
             i += 4
         self._conv([(names[i], self.s_hr)], hr, out_f32=lrs.out, relu=1, cout=3, out_index=self.src_index,
                    out_hw=(4 * H, 4 * W))
+
+
+def lr_extents(need, full):
+    """Compute extents (rows, cols) of every conv of the 22 LR blocks, given the region `need` of the final LR
+    stream that is read afterwards.  Returns, per block, (out, t1, t2) for 5/3 blocks (0..15) and (out, t1) for light
+    blocks (16..21).  Walking backwards: the fused conv of a 5/3 block reads t1 through a 5x5 (needs out+2) and t2
+    through a 3x3 (out+1), which read the block input through a 3x3 / 5x5 (out+3); a light block needs out+1 / out+2."""
+    def clip(e, add):
+        return (min(full[0], e[0] + add), min(full[1], e[1] + add))
+    e = (min(full[0], need[0]), min(full[1], need[1]))
+    exts = [None] * 22
+    for b in reversed(range(22)):
+        if b >= 16:
+            exts[b] = (e, clip(e, 1))
+            e = clip(e, 2)
+        else:
+            exts[b] = (e, clip(e, 2), clip(e, 1))
+            e = clip(e, 3)
+    return exts
 
 
 def hr_extent(tile, count, image_dim, patch=96, step=64, scale=4, radius=7, crop=8):
@@ -344,14 +372,15 @@ class Engine:
         return {n: (self.master[n][0].cpu().numpy(), self.master[n][1].cpu().numpy()) for n, _, _, _ in self.specs}
 
     # ---------------------------------------------------------------- forward
-    def graph(self, NB, H, W):
-        """The LR stage (buffers + plans) for NB patches of HxW; HR stages hang off it."""
-        key = (NB, H, W)
+    def graph(self, NB, H, W, need=None):
+        """The LR stage (buffers + plans) for NB patches of HxW; HR stages hang off it.  need: see _LRStage."""
+        need = (H, W) if need is None else (min(H, need[0]), min(W, need[1]))
+        key = (NB, H, W) + need
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 4:  # bound device memory: keep the most recent shapes only
                 self._graphs.pop(next(iter(self._graphs)))
-            g = self._with_oom_retry(lambda: _LRStage(self, NB, H, W))
+            g = self._with_oom_retry(lambda: _LRStage(self, NB, H, W, need))
             self._graphs[key] = g
         return g
 
@@ -381,16 +410,19 @@ class Engine:
         self.last_stages = []
         for i in range(0, N, nb):
             n = min(nb, N - i)
-            g = self.graph(n, H, W)
-            g.x_in.copy_(x[i:i + n])
-            g.run()
-            self.last_stages.append(g)
             if extents is None:
                 groups = {(4 * H, 4 * W): list(range(n))}
+                need = None
             else:
                 groups = {}
                 for j in range(n):
                     groups.setdefault(tuple(extents[i + j]), []).append(j)
+                # the bilinear reads LR cells [0, e/4] of the stream: the LR layers shrink towards that region
+                need = (max(e[0] for e in groups) // 4 + 1, max(e[1] for e in groups) // 4 + 1)
+            g = self.graph(n, H, W, need)
+            g.x_in.copy_(x[i:i + n])
+            g.run()
+            self.last_stages.append(g)
             for (eh, ew), idx in groups.items():
                 hs = g.hr_stage(len(idx), eh, ew)
                 hs.src_index.copy_(torch.tensor(idx, dtype=torch.int32))

@@ -68,6 +68,11 @@ typedef struct sr_conv_desc {
    * any value <= 128 (weights packed with sr_pack_conv_weights(cout)), output fp32
    * [NB, H*r, W*r, C] only; order as in sr_depth_to_space. */
   int shuffle_r, shuffle_order;
+  /* Compute extents: > 0 restricts the launch to the top-left comp_h x comp_w corner of every image
+   * (outputs outside are not written; inputs outside are read as they are, only the true image
+   * border is zero-padded).  Lets the tiled path shrink the last LR layers to the region whose
+   * receptive field can still reach a surviving pixel.  0: the whole H x W image. */
+  int comp_h, comp_w;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;

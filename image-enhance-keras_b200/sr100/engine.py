@@ -229,11 +229,16 @@ class _HRStage(_Stage):
             L.ptr(src), src_is_bf16, L.ptr(self.src_index), n, H, W, NUMK, eh, ew, L.ptr(self.s_hr),
             L.ptr(self.s_hr32), st)))
         i, hr = lrs.first_hr_layer, (n, eh, ew)
-        for _ in range(2):
-            self._block53(names, i, self.s_hr, self.s_hr32, self.t1_hr, self.t2_hr, hr)
+        # a cropped extent e (< 4H) was chosen as >= (last surviving pixel + 1) + 7, so the tail only has to be right on
+        # [0, e-7), the second block on e-6 (its t1 / t2 on e-4 / e-5), the first block on e-3 (t1 / t2 on e-1 / e-2)
+        def cut(k):
+            return (eh - k if eh < 4 * H else eh, ew - k if ew < 4 * W else ew)
+        comps = [(cut(3), cut(1), cut(2)), (cut(6), cut(4), cut(5))]
+        for b in range(2):
+            self._block53(names, i, self.s_hr, self.s_hr32, self.t1_hr, self.t2_hr, hr, comp=comps[b])
             i += 4
         self._conv([(names[i], self.s_hr)], hr, out_f32=lrs.out, relu=1, cout=3, out_index=self.src_index,
-                   out_hw=(4 * H, 4 * W))
+                   out_hw=(4 * H, 4 * W), comp=cut(7))
 
 
 def lr_extents(need, full):

@@ -189,7 +189,7 @@ class _LRStage(_Stage):
         key = (n, eh, ew)
         st = self.hr.get(key)
         if st is None:
-            if len(self.hr) >= 4:
+            if len(self.hr) >= 16:
                 self.hr.pop(next(iter(self.hr)))
             try:
                 st = _HRStage(self, n, eh, ew)
@@ -262,13 +262,13 @@ def lr_extents(need, full):
 
 def hr_extent(tile, count, image_dim, patch=96, step=64, scale=4, radius=7, crop=8):
     """Rows (or columns) of a tile's x4 output that the HR stage must produce so that every pixel the tile
-    contributes to the final [0, scale*image_dim) image is exact: owned span end + receptive-field radius,
-    rounded up to a multiple of 16, at least 272 (= the interior-tile value) to keep the shape classes few."""
+    contributes to the final [0, scale*image_dim) image is exact: (end of its owned span, clipped to the image) +
+    receptive-field radius, rounded up to a multiple of 16.  272 for interior tiles of the 96/64/x4 geometry; the
+    last live tile of an axis needs less when the image ends inside it, or the whole patch when it owns its end."""
     P, S = patch * scale, step * scale
     own_hi = S * (tile + 1) + crop if tile < count - 1 else S * tile + P       # exclusive, canvas coordinates
     own_hi = min(own_hi, scale * image_dim)
-    need = own_hi - S * tile + radius
-    need = max(need, S + crop + radius + 1)
+    need = max(own_hi - S * tile, 1) + radius
     return min(P, (need + 15) // 16 * 16)
 
 

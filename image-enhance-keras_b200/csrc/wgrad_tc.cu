@@ -41,6 +41,7 @@ struct WgradParams {
   int k, p, NB, H, W;
   int BW, nseg, PWs;   // segment width (multiple of 16), segments per row, ring row pitch (multiple of 8)
   int RB, nrb;         // rows per unit, row blocks per image column
+  int NI, ngrp;        // images per K row (narrow images are processed NI at a time), image groups
   int nring, nbslots;
   int ngroups;
   int g_tap0[kMaxGroups], g_ntaps[kMaxGroups], g_cta0[kMaxGroups], g_ncta[kMaxGroups];
@@ -64,8 +65,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t a_row_bytes = (uint32_t)P.PWs * 256u;  // two 64-channel halves of PWs x 128 B
-  const uint32_t b_row_bytes = (uint32_t)P.BW * 256u;
+  const uint32_t a_img_bytes = (uint32_t)P.PWs * 128u, b_img_bytes = (uint32_t)P.BW * 128u;  // one image, one half
+  const uint32_t a_row_bytes = (uint32_t)P.NI * a_img_bytes * 2u;  // two 64-channel halves of NI x PWs x 128 B
+  const uint32_t b_row_bytes = (uint32_t)P.NI * b_img_bytes * 2u;
   uint8_t* a_buf = smem;
   uint8_t* b_buf = a_buf + (size_t)P.nring * a_row_bytes;
   WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(b_buf + (size_t)P.nbslots * b_row_bytes);
@@ -82,7 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int tap0 = P.g_tap0[g], ntaps = P.g_ntaps[g];
   const int kymin = tap0 / P.k, kymax = (tap0 + ntaps - 1) / P.k;
   const int span = kymax - kymin;  // extra input rows per unit
-  const int units = P.NB * P.nseg * P.nrb;
+  const int units = P.ngrp * P.nseg * P.nrb;
   const bool has_work = rank < units;
 
   if (threadIdx.x == 0) {
@@ -114,7 +116,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int rb = u % P.nrb;
     const int q = u / P.nrb;
     const int seg = q % P.nseg;
-    *n = q / P.nseg;
+    *n = (q / P.nseg) * P.NI;  // first image of the group (images beyond NB are zero-filled by TMA)
     *x0 = seg * P.BW;
     *y0 = rb * P.RB;
     *rows = min(P.RB, P.H - *y0);
@@ -160,6 +162,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // MN-major SW128 descriptors: LBO = bytes between the two 64-channel halves, SBO = 8 pixel rows
       const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW128 << 29);
       const uint32_t a_row16 = a_row_bytes >> 4, b_row16 = b_row_bytes >> 4;
+      const uint32_t a_img16 = a_img_bytes >> 4, b_img16 = b_img_bytes >> 4;
       const uint32_t a_lo0 = (smem_u32(a_buf) >> 4) | (((a_row_bytes / 2) >> 4) << 16);
       const uint32_t b_lo0 = (smem_u32(b_buf) >> 4) | (((b_row_bytes / 2) >> 4) << 16);
       const int k16n = P.BW >> 4;
@@ -197,19 +200,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (j < ntaps) {
               uint32_t slot = base + t_row[j];
               if (slot >= nring) slot -= nring;
-              uint32_t a_lo = a_lo0 + slot * a_row16 + t_sh[j];
-              uint32_t bl = b_lo;
+              const uint32_t a_tap = a_lo0 + slot * a_row16 + t_sh[j];
               const uint32_t d = tmem_base + (uint32_t)j * 128u;
               uint32_t accf = started;
-              for (int s = 0; s < k16n; ++s) {
-                if (leader) {
-                  const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)a_lo;
-                  const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)bl;
-                  umma_bf16(d, adesc, bdesc, kIdescMN, accf);
+              for (int im = 0; im < P.NI; ++im) {
+                uint32_t a_lo = a_tap + (uint32_t)im * a_img16;
+                uint32_t bl = b_lo + (uint32_t)im * b_img16;
+                for (int s = 0; s < k16n; ++s) {
+                  if (leader) {
+                    const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)a_lo;
+                    const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)bl;
+                    umma_bf16(d, adesc, bdesc, kIdescMN, accf);
+                  }
+                  accf = 1u;
+                  a_lo += 128u;
+                  bl += 128u;
                 }
-                accf = 1u;
-                a_lo += 128u;
-                bl += 128u;
               }
             }
           }
@@ -320,12 +326,12 @@ static PFN_encodeTiled wg_encode_fn() {
   return fn;
 }
 
-static int make_row_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, int box_w) {
+static int make_row_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, int box_w, int box_n) {
   PFN_encodeTiled enc = wg_encode_fn();
   if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_n};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -410,9 +416,13 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
     if (bw > maxbw) continue;
     const int pws = (bw + 2 * P.p + 7) & ~7;
     if (pws > 256) continue;
-    const size_t a_row = (size_t)pws * 256, b_row = (size_t)bw * 256;
     const size_t fixed = 1024 + sizeof(WgradBarriers) + 64;
     const int min_ring = max_span + 2, min_b = 2;
+    // narrow images: NI images share one K row (one barrier round trip feeds NI x BW/16 MMAs per tap)
+    int ni = nseg == 1 ? std::max(1, std::min(std::min(4, d->NB), 128 / bw)) : 1;
+    while (ni > 1 && fixed + (size_t)(min_ring + 1) * ni * pws * 256 + (size_t)(min_b + 1) * ni * bw * 256 > kWgSmemBudget)
+      --ni;
+    const size_t a_row = (size_t)ni * pws * 256, b_row = (size_t)ni * bw * 256;
     if (fixed + min_ring * a_row + min_b * b_row > kWgSmemBudget) continue;
     int nring = min_ring, nb = min_b;
     // grow both rings alternately while they fit
@@ -429,6 +439,8 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
       if (!grew) break;
     }
     P.BW = bw;
+    P.NI = ni;
+    P.ngrp = (d->NB + ni - 1) / ni;
     P.nseg = nseg;
     P.PWs = pws;
     P.nring = nring;
@@ -464,7 +476,7 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   for (int g = 0; g < P.ngroups; ++g) max_ncta = std::max(max_ncta, P.g_ncta[g]);
   P.RB = P.H;
   P.nrb = 1;
-  while ((long long)P.NB * P.nseg * P.nrb < 12LL * max_ncta && P.RB > 8) {
+  while ((long long)P.ngrp * P.nseg * P.nrb < 12LL * max_ncta && P.RB > 8) {
     P.RB = (P.RB + 1) / 2;
     P.nrb = (P.H + P.RB - 1) / P.RB;
   }
@@ -481,8 +493,8 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   pl->beta = d->accumulate ? 1.f : 0.f;
   pl->dw = d->dw_hwio;
   pl->flops = 2.0 * (double)d->NB * d->H * d->W * ntaps * 128.0 * 128.0;
-  int rc = make_row_map(&pl->tmX, d->x_bf16, d->NB, d->H, d->W, P.PWs);
-  if (rc == SR_OK) rc = make_row_map(&pl->tmG, d->g_bf16, d->NB, d->H, d->W, P.BW);
+  int rc = make_row_map(&pl->tmX, d->x_bf16, d->NB, d->H, d->W, P.PWs, P.NI);
+  if (rc == SR_OK) rc = make_row_map(&pl->tmG, d->g_bf16, d->NB, d->H, d->W, P.BW, P.NI);
   if (rc != SR_OK) {
     delete pl;
     return rc;
@@ -523,5 +535,6 @@ extern "C" int sr_wgrad_plan_info(const sr_wgrad_plan* plan, sr_wgrad_plan_info_
   info->g_slots = pl->P.nbslots;
   info->tap_groups = pl->P.ngroups;
   info->rows_per_unit = pl->P.RB;
+  info->images_per_row = pl->P.NI;
   return SR_OK;
 }

@@ -68,6 +68,7 @@ class WgradPlanInfo(C.Structure):
         ("flops", C.c_double),
         ("grid", C.c_int), ("smem_bytes", C.c_int), ("seg_width", C.c_int), ("nseg", C.c_int),
         ("ring_rows", C.c_int), ("g_slots", C.c_int), ("tap_groups", C.c_int), ("rows_per_unit", C.c_int),
+        ("images_per_row", C.c_int),
     ]
 
 

@@ -217,7 +217,7 @@ typedef struct sr_wgrad_desc {
 typedef struct sr_wgrad_plan sr_wgrad_plan;
 typedef struct sr_wgrad_plan_info_t {
   double flops;
-  int grid, smem_bytes, seg_width, nseg, ring_rows, g_slots, tap_groups, rows_per_unit;
+  int grid, smem_bytes, seg_width, nseg, ring_rows, g_slots, tap_groups, rows_per_unit, images_per_row;
 } sr_wgrad_plan_info_t;
 size_t sr_wgrad_workspace_bytes(void);
 int sr_wgrad_plan_create(const sr_wgrad_desc* desc, sr_wgrad_plan** plan);

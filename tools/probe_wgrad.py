@@ -31,6 +31,9 @@ case(name="k3_w96_scale_acc", k=3, W=96, H=20, scale=0.1, accumulate=1)
 case(name="k5_w192_h24", k=5, W=192, H=24, NB=2)
 case(name="k3_w384_h9", k=3, W=384, H=9, NB=1)
 case(name="k5_many_units", k=5, W=48, H=48, NB=40)
+case(name="k3_w32_nb7", k=3, W=32, H=10, NB=7)
+case(name="k5_w16_nb5", k=5, W=16, H=9, NB=5)
+case(name="k3_w48_nb3", k=3, W=48, H=17, NB=3)
 case(name="perf_k3_lr48", k=3, NB=256, H=48, W=48, iters=10, check=False)
 case(name="perf_k5_lr48", k=5, NB=256, H=48, W=48, iters=10, check=False)
 case(name="perf_k3_hr192", k=3, NB=32, H=192, W=192, iters=5, check=False)
@@ -63,7 +66,7 @@ def run_case(idx):
     L.check(lib.sr_wgrad_plan_run(plan, L.stream_ptr()))
     torch.cuda.synchronize()
     rec = dict(case=idx, **cs, grid=info.grid, smem=info.smem_bytes, seg_width=info.seg_width, nseg=info.nseg,
-               ring=info.ring_rows, g_slots=info.g_slots, groups=info.tap_groups, rows_per_unit=info.rows_per_unit)
+               ring=info.ring_rows, g_slots=info.g_slots, groups=info.tap_groups, rows_per_unit=info.rows_per_unit, images_per_row=info.images_per_row)
     if cs["check"]:
         xin = x.float().permute(0, 3, 1, 2).contiguous()
         gout = g.float().permute(0, 3, 1, 2).contiguous()

@@ -69,31 +69,84 @@ __global__ void __launch_bounds__(256) score_pair_kernel(const uint8_t* __restri
           vb = (double)b[o + plane - 1];
         }
       }
-      pa[i] = va;
-      pb[i] = vb;
+      if (plane == 0) {
+        pa[i] = va;
+        pb[i] = vb;
+      } else {          // R, G, B hold integers 0..255: fp32 keeps every window sum (< 2^24) exact
+        reinterpret_cast<float*>(pa)[i] = (float)va;
+        reinterpret_cast<float*>(pb)[i] = (float)vb;
+      }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) {
-      const int ly = i / kTile, lx = i - ly * kTile;
-      if (wy0 + ly >= nwy || wx0 + lx >= nwx) continue;
-      double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+    // Separable window sums: a thread owns window column lx and 4 consecutive window rows.  For each of the 10
+    // halo rows under them it forms the horizontal 7-sums of (x, y, x^2, y^2, xy) once and adds them to the windows
+    // that contain the row (2.8x fewer shared-memory reads than summing 49 taps per window; R/G/B planes hold
+    // integers, so their sums are exact in any order).
+    {
+      const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4;
+      double acc[4][5];
 #pragma unroll
-      for (int dy = 0; dy < kWin; ++dy) {
+      for (int wv = 0; wv < 4; ++wv)
 #pragma unroll
-        for (int dx = 0; dx < kWin; ++dx) {
-          const double x = pa[(ly + dy) * kHalo + lx + dx];
-          const double y = pb[(ly + dy) * kHalo + lx + dx];
-          sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+        for (int k = 0; k < 5; ++k) acc[wv][k] = 0.0;
+      if (plane == 0) {
+#pragma unroll
+        for (int r = 0; r < 4 + kWin - 1; ++r) {
+          const double* ra = pa + (ly0 + r) * kHalo + lx;
+          const double* rb = pb + (ly0 + r) * kHalo + lx;
+          double hx = 0, hy = 0, hxx = 0, hyy = 0, hxy = 0;
+#pragma unroll
+          for (int dx = 0; dx < kWin; ++dx) {
+            const double x = ra[dx], y = rb[dx];
+            hx += x; hy += y; hxx += x * x; hyy += y * y; hxy += x * y;
+          }
+#pragma unroll
+          for (int wv = 0; wv < 4; ++wv) {
+            if (r >= wv && r < wv + kWin) {
+              acc[wv][0] += hx; acc[wv][1] += hy; acc[wv][2] += hxx; acc[wv][3] += hyy; acc[wv][4] += hxy;
+            }
+          }
         }
+      } else {
+        float facc[4][5];
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv)
+#pragma unroll
+          for (int k = 0; k < 5; ++k) facc[wv][k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4 + kWin - 1; ++r) {
+          const float* ra = reinterpret_cast<const float*>(pa) + (ly0 + r) * kHalo + lx;
+          const float* rb = reinterpret_cast<const float*>(pb) + (ly0 + r) * kHalo + lx;
+          float hx = 0, hy = 0, hxx = 0, hyy = 0, hxy = 0;
+#pragma unroll
+          for (int dx = 0; dx < kWin; ++dx) {
+            const float x = ra[dx], y = rb[dx];
+            hx += x; hy += y; hxx = fmaf(x, x, hxx); hyy = fmaf(y, y, hyy); hxy = fmaf(x, y, hxy);
+          }
+#pragma unroll
+          for (int wv = 0; wv < 4; ++wv) {
+            if (r >= wv && r < wv + kWin) {
+              facc[wv][0] += hx; facc[wv][1] += hy; facc[wv][2] += hxx; facc[wv][3] += hyy; facc[wv][4] += hxy;
+            }
+          }
+        }
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv)
+#pragma unroll
+          for (int k = 0; k < 5; ++k) acc[wv][k] = (double)facc[wv][k];
       }
-      const double ux = sx / 49.0, uy = sy / 49.0;
-      const double uxx = sxx / 49.0, uyy = syy / 49.0, uxy = sxy / 49.0;
-      const double vx = cov_norm * (uxx - ux * ux);
-      const double vy = cov_norm * (uyy - uy * uy);
-      const double vxy = cov_norm * (uxy - ux * uy);
-      const double A1 = 2 * ux * uy + C1, A2 = 2 * vxy + C2;
-      const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
-      ssim_acc[plane] += (A1 * A2) / (B1 * B2);
+#pragma unroll
+      for (int wv = 0; wv < 4; ++wv) {
+        if (wy0 + ly0 + wv >= nwy || wx0 + lx >= nwx) continue;
+        const double ux = acc[wv][0] / 49.0, uy = acc[wv][1] / 49.0;
+        const double uxx = acc[wv][2] / 49.0, uyy = acc[wv][3] / 49.0, uxy = acc[wv][4] / 49.0;
+        const double vx = cov_norm * (uxx - ux * ux);
+        const double vy = cov_norm * (uyy - uy * uy);
+        const double vxy = cov_norm * (uxy - ux * uy);
+        const double A1 = 2 * ux * uy + C1, A2 = 2 * vxy + C2;
+        const double B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+        ssim_acc[plane] += (A1 * A2) / (B1 * B2);
+      }
     }
   }
   const double t_sq = block_sum(sum_sq, red);

@@ -34,7 +34,7 @@ def _psnr(a, b):
     return -10 * np.log10(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
 
 
-@pytest.mark.parametrize("shape", [(2, 24, 24), (1, 48, 40), (1, 96, 96)])
+@pytest.mark.parametrize("shape", [(2, 24, 24), (1, 48, 40), (1, 96, 96), (1, 128, 128)])   # last: BASELINE configs[0]
 def test_forward_matches_oracle(dmodel, weights, shape):
     from oracle import model as om
     _, model = dmodel

@@ -6,8 +6,8 @@ the libsr100 C ABI.  There is no CPU path: constructing a model's graph needs a 
 
 Covered: psnr helpers (models.py:43-90), BaseSuperResolutionModel (:93-182), upscaleStepPatch
 (:184-415, the CLI path), DifvdsrDouble (:1146-1270) and the Lambda helpers it uses (:977-986,
-:1383-1399, :1451).  upscalePatch / upscale / evaluate and Difvdsr4 / Difvdsr are "next" rows of
-SURVEY.md section 8(f) and raise NotImplementedError.
+:1383-1399, :1451), upscale(mode='fast') (:606-852).  upscalePatch / upscale(mode='patch') / evaluate and
+Difvdsr4 / Difvdsr are "next" rows of SURVEY.md section 8(f) and raise NotImplementedError.
 """
 from __future__ import print_function, division
 
@@ -277,9 +277,56 @@ class BaseSuperResolutionModel(object):
         raise NotImplementedError("upscalePatch (models.py:419-604) needs PIL-exact bicubic imresize; "
                                   "SURVEY.md 8(f) 'next' row")
 
-    def upscale(self, *a, **k):
-        raise NotImplementedError("upscale (models.py:606-852) needs PIL-exact bicubic imresize; "
-                                  "SURVEY.md 8(f) 'next' row")
+    def upscale(self, img_path, save_intermediate=False, return_image=False, suffix="scaled",
+                patch_size=32, mode="patch", verbose=True):
+        """models.py:606-852.  mode='fast' (the whole image through the network, :681-758, :773-848): the image is
+        bicubic-resized to its own size (`imresize(true_img, (img_width, img_height))` with
+        __match_autoencoder_size returning the input size for this model, :855-889 -- a PIL no-op), written as the
+        `_A<suffix>` side file (:755), run through model.predict, x255, clipped to uint8 and saved.
+        mode='patch' (dense sklearn patches of the x4-bicubic image, :645-680) is a SURVEY 8(f) 'next' row."""
+        from PIL import Image
+        path = os.path.splitext(img_path)
+        filename = path[0] + "_" + suffix + "(%dx)" % (self.scale_factor) + path[1]
+        filenameM = path[0] + "_A" + suffix + "(%dx)" % (self.scale_factor) + path[1]
+        true_img = np.asarray(Image.open(img_path).convert("RGB"))
+        rows, cols = true_img.shape[0], true_img.shape[1]      # the reference calls these init_width, init_height
+        if verbose:
+            print("Old Size : ", true_img.shape)
+            print("New Size : (%d, %d, 3)" % (cols * int(self.scale_factor), rows * int(self.scale_factor)))
+        if mode == "patch" and self.type_true_upscaling:
+            mode = 'fast'
+            print("Patch mode does not work with True Upscaling models yet. Defaulting to mode='fast'")
+        if mode == 'patch':
+            raise NotImplementedError("upscale(mode='patch') (models.py:645-680: dense make_patches of the bicubic x4 "
+                                      "image + sklearn averaging) is a SURVEY.md 8(f) 'next' row; use mode='fast' or "
+                                      "upscaleStepPatch")
+        sf = int(self.scale_factor)
+        img_height, img_width = cols * sf, rows * sf            # __match_autoencoder_size, not AE / not true upscaling
+        if (img_width, img_height) == (rows, cols):
+            images = true_img                                   # PIL resize to the same size returns a copy
+        else:
+            images = np.asarray(Image.fromarray(true_img).resize((img_height, img_width), Image.BICUBIC))
+        Image.fromarray(images).save(filenameM)                  # imsave(filenameM, images), :755
+        if save_intermediate:
+            if verbose:
+                print("Saving intermediate image.")
+            Image.fromarray(images).save(path[0] + "_intermediate_" + path[1])
+        img_conv = np.expand_dims(images, axis=0).astype(np.float32) / 255.
+        model = self.create_model(img_height, img_width, load_weights=True)
+        if verbose:
+            print("Model loaded.")
+        result = model.predict(img_conv, batch_size=10, verbose=verbose)
+        if verbose:
+            print("De-processing images.")
+        result = result.astype(np.float32) * 255.
+        result = np.clip(result[0], 0, 255).astype('uint8')
+        if verbose:
+            print("\nCompleted De-processing image.")
+        if return_image:
+            return result
+        if verbose:
+            print("Saving image.")
+        Image.fromarray(result).save(filename)
 
 
 class DifvdsrDouble(BaseSuperResolutionModel):

@@ -406,6 +406,40 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int ntaps, i
   }
 }
 
+// All layers in ONE launch (the optimizer step repacks 85 layers, forward and transposed: 170 tiny launches
+// otherwise cost more than the all-reduce).  items[i] describes one (layer, orientation); `starts` are the prefix
+// sums of the packed element counts.
+__global__ void pack_weights_batched_kernel(const sr_pack_item* __restrict__ items,
+                                            const unsigned long long* __restrict__ starts, int n_items) {
+  const size_t total = starts[n_items];
+  for (size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < total;
+       gidx += (size_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_items - 1;       // last item whose start <= gidx
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= gidx) lo = mid; else hi = mid - 1;
+    }
+    const sr_pack_item it = items[lo];
+    const size_t idx = gidx - starts[lo];
+    const int ntaps = it.ksize * it.ksize;
+    const int n_pad = (it.cout > 16 || it.transpose_flip) ? 128 : 16;
+    const int c = (int)(idx & 31);
+    size_t q = idx >> 5;
+    const int n = (int)(q % n_pad);
+    q /= n_pad;
+    const int tap = (int)(q % ntaps);
+    const int chunk = (int)(q / ntaps);
+    const int k_in = chunk * 32 + c;
+    float v = 0.f;
+    if (!it.transpose_flip) {
+      if (n < it.cout) v = it.hwio[((size_t)tap * 128 + k_in) * it.cout + n];
+    } else if (k_in < it.cout) {
+      v = it.hwio[((size_t)(ntaps - 1 - tap) * 128 + n) * it.cout + k_in];
+    }
+    reinterpret_cast<__nv_bfloat16*>(it.dst)[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------ direct conv (CUDA cores)
 __global__ void conv_direct_kernel(const void* __restrict__ in, int in_is_bf16,
                                    const float* __restrict__ hwio, int w_round_bf16,
@@ -666,6 +700,15 @@ extern "C" int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int 
   pack_weights_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
       hwio, ksize * ksize, cout, n_pad, transpose_flip, reinterpret_cast<__nv_bfloat16*>(dst));
   return check_launch("pack_weights_kernel");
+}
+
+extern "C" int sr_pack_conv_weights_batched(const sr_pack_item* items_dev, const unsigned long long* starts_dev,
+                                            int n_items, size_t total_elems, void* stream) {
+  if (!items_dev || !starts_dev) return set_error(SR_ERR_INVALID, "sr_pack_conv_weights_batched: null pointer");
+  if (n_items < 1 || total_elems == 0) return SR_OK;
+  pack_weights_batched_kernel<<<grid_for(total_elems, kBlock, 148 * 16), kBlock, 0, as_stream(stream)>>>(
+      items_dev, starts_dev, n_items);
+  return check_launch("pack_weights_batched_kernel");
 }
 
 extern "C" int sr_conv2d_direct(const void* in, int in_is_bf16, const float* hwio, int w_round_bf16,

@@ -54,6 +54,11 @@ class ConvPlanInfo(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("hwio", C.c_void_p), ("dst", C.c_void_p), ("ksize", C.c_int), ("cout", C.c_int),
+                ("transpose_flip", C.c_int), ("pad_", C.c_int)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("x_bf16", C.c_void_p), ("g_bf16", C.c_void_p),
@@ -95,6 +100,7 @@ SIGNATURES = {
     "sr_conv_plan_info": (_i, [_vp, C.POINTER(ConvPlanInfo)]),
     "sr_packed_weight_bytes": (_sz, [_i, _i]),
     "sr_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "sr_pack_conv_weights_batched": (_i, [_vp, _vp, _i, _sz, _vp]),
     "sr_conv2d_direct": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_head1x1_fwd": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_bilinear4_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -273,6 +273,33 @@ def hr_extent(tile, count, image_dim, patch=96, step=64, scale=4, radius=7, crop
     return min(P, (need + 15) // 16 * 16)
 
 
+class PackTable:
+    """Device-side description of every (layer -> packed buffer) repack, so that all layers go in one launch."""
+
+    def __init__(self, eng, packed, flip):
+        import ctypes as C
+        self.lib = eng.lib
+        items, starts, total = [], [0], 0
+        for name, k, cin, cout in eng.specs:
+            if cin != NUMK:
+                continue
+            it = L.PackItem()
+            it.hwio, it.dst = eng.master[name][0].data_ptr(), packed[name].data_ptr()
+            it.ksize, it.cout, it.transpose_flip = k, cout, 1 if flip else 0
+            items.append(it)
+            total += packed[name].numel() // 2
+            starts.append(total)
+        arr = (L.PackItem * len(items))(*items)
+        raw = np.frombuffer(memoryview(arr), dtype=np.uint8).copy()
+        self.items = torch.from_numpy(raw).to(eng.device)
+        self.starts = torch.tensor(starts, dtype=torch.int64).to(eng.device)
+        self.n, self.total = len(items), total
+
+    def run(self):
+        L.check(self.lib.sr_pack_conv_weights_batched(L.ptr(self.items), L.ptr(self.starts), self.n, self.total,
+                                                      L.stream_ptr()))
+
+
 def plan_tiles(h, w, patch=96, step=64, scale=4, full_canvas=False):
     """Tile plan of one h x w image: (virtual canvas (H', W') handed to the gather, (cnt_h, cnt_w), per-tile HR
     extents in the gather's column-major order n = wi*cnt_h + hi, or None for full_canvas).
@@ -335,6 +362,7 @@ class Engine:
             ow, nw, ob, nb = self.param_slices[name]
             self.master[name] = (self.param_arena[ow:ow + nw].view(k, k, cin, cout), self.param_arena[ob:ob + nb])
         self.packed = {}
+        self._pack_table = None
         self._bias_cache = {}
         self._graphs = {}
         self.set_weights_dict(weights if weights is not None else glorot_uniform_weights())
@@ -356,16 +384,15 @@ class Engine:
         self.repack()
 
     def repack(self):
-        """(Re)build the tensor-core weight layout from the fp32 masters (after load / optimizer step)."""
-        st = L.stream_ptr()
-        for name, k, cin, cout in self.specs:
-            if cin != NUMK:
-                continue
-            if name not in self.packed:
-                self.packed[name] = torch.empty(self.lib.sr_packed_weight_bytes(k, cout), dtype=torch.uint8,
-                                                device=self.device)
-            L.check(self.lib.sr_pack_conv_weights(L.ptr(self.master[name][0]), k, cout, 0,
-                                                  L.ptr(self.packed[name]), st))
+        """(Re)build the tensor-core weight layout from the fp32 masters (after load / optimizer step): one launch
+        for all 85 layers (sr_pack_conv_weights_batched)."""
+        if self._pack_table is None:
+            for name, k, cin, cout in self.specs:
+                if cin == NUMK and name not in self.packed:
+                    self.packed[name] = torch.empty(self.lib.sr_packed_weight_bytes(k, cout), dtype=torch.uint8,
+                                                    device=self.device)
+            self._pack_table = PackTable(self, self.packed, flip=False)
+        self._pack_table.run()
         for names, t in self._bias_cache.items():
             t.copy_(sum(self.master[n][1] for n in names))
 

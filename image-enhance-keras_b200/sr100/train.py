@@ -240,6 +240,7 @@ class Trainer:
         self.tail_dw128 = torch.zeros(3, 3, NUMK, NUMK, dtype=torch.float32, device=dev)
         self.tail_db128 = torch.zeros(NUMK, dtype=torch.float32, device=dev)
         self.packed_t = {}      # name -> packed weights of the input-gradient conv
+        self._pack_table_t = None
         self._graphs = {}
         self.repack_t()
 
@@ -257,15 +258,15 @@ class Trainer:
         return {n: (self.grad_w(n).cpu().numpy(), self.grad_b(n).cpu().numpy()) for n, _, _, _ in self.engine.specs}
 
     def repack_t(self):
-        st = L.stream_ptr()
-        for name, k, cin, cout in self.engine.specs:
-            if cin != NUMK:
-                continue
-            if name not in self.packed_t:
-                self.packed_t[name] = torch.empty(self.lib.sr_packed_weight_bytes(k, NUMK), dtype=torch.uint8,
-                                                  device=self.engine.device)
-            L.check(self.lib.sr_pack_conv_weights(L.ptr(self.engine.master[name][0]), k, cout, 1,
-                                                  L.ptr(self.packed_t[name]), st))
+        """Weights of the input-gradient convs (180-degree rotated, cin <-> cout): one launch for all layers."""
+        from .engine import PackTable
+        if self._pack_table_t is None:
+            for name, k, cin, cout in self.engine.specs:
+                if cin == NUMK and name not in self.packed_t:
+                    self.packed_t[name] = torch.empty(self.lib.sr_packed_weight_bytes(k, NUMK), dtype=torch.uint8,
+                                                      device=self.engine.device)
+            self._pack_table_t = PackTable(self.engine, self.packed_t, flip=True)
+        self._pack_table_t.run()
 
     def graph(self, NB, H, W):
         key = (NB, H, W)

@@ -97,6 +97,16 @@ int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info);
  * missing reduction rows are zero, so the gradient tensor may carry anything in channels >= cout.
  * sr_packed_weight_bytes gives the destination size. */
 size_t sr_packed_weight_bytes(int ksize, int cout);
+/* Many layers in one launch (after an optimizer step every layer is repacked, forward and transposed).
+ * items / starts are DEVICE arrays: starts[i] = sum of the packed ELEMENT counts
+ * (sr_packed_weight_bytes / 2) of items 0..i-1, starts[n_items] = total_elems. */
+typedef struct sr_pack_item {
+  const float* hwio;     /* [ksize,ksize,128,cout] fp32 */
+  void* dst;             /* packed bf16 destination */
+  int ksize, cout, transpose_flip, pad_;
+} sr_pack_item;
+int sr_pack_conv_weights_batched(const sr_pack_item* items_dev, const unsigned long long* starts_dev,
+                                 int n_items, size_t total_elems, void* stream);
 int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip, void* dst,
                          void* stream);
 

@@ -363,7 +363,7 @@ class Engine:
             self.master[name] = (self.param_arena[ow:ow + nw].view(k, k, cin, cout), self.param_arena[ob:ob + nb])
         self.packed = {}
         self._pack_table = None
-        self._bias_cache = {}
+        self._init_bias_pairs()
         self._graphs = {}
         self.set_weights_dict(weights if weights is not None else glorot_uniform_weights())
 
@@ -393,12 +393,34 @@ class Engine:
                                                     device=self.device)
             self._pack_table = PackTable(self, self.packed, flip=False)
         self._pack_table.run()
-        for names, t in self._bias_cache.items():
-            t.copy_(sum(self.master[n][1] for n in names))
+        self._refresh_bias_sums()
+
+    def _init_bias_pairs(self):
+        """The 18 two-source launches (fused tails of the 5/3 blocks) add two biases: one [18,128] buffer, refreshed
+        by three launches after every weight change."""
+        names = [s[0] for s in self.specs]
+        pairs, i = [], 1
+        for _ in range(16):
+            pairs.append((names[i + 1], names[i + 3]))
+            i += 4
+        i += 12
+        for _ in range(2):
+            pairs.append((names[i + 1], names[i + 3]))
+            i += 4
+        ar = torch.arange(NUMK, device=self.device)
+        self._pair_ia = torch.stack([self.param_slices[a][2] + ar for a, _ in pairs])
+        self._pair_ib = torch.stack([self.param_slices[b][2] + ar for _, b in pairs])
+        self._pair_buf = torch.zeros(len(pairs), NUMK, device=self.device, dtype=torch.float32)
+        self._bias_cache = {p: self._pair_buf[j] for j, p in enumerate(pairs)}
+
+    def _refresh_bias_sums(self):
+        torch.add(self.param_arena[self._pair_ia], self.param_arena[self._pair_ib], out=self._pair_buf)
 
     def bias_for(self, names):
-        if names not in self._bias_cache:
-            self._bias_cache[names] = sum(self.master[n][1] for n in names).clone()
+        """Device bias vector of a conv launch: the layer's own bias (a view into the parameter arena, always
+        current), or for a two-source launch the sum of both biases (refreshed by repack)."""
+        if len(names) == 1:
+            return self.master[names[0]][1]
         return self._bias_cache[names]
 
     def get_weights_dict(self):

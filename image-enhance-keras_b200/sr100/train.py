@@ -93,6 +93,7 @@ class _TrainGraph:
         self.keep = [S, T1, T2, s32, SH, TH1, TH2, gs, gs32, gt1, gt2, gsh, gsh32, gth1, gth2]
         self.fwd, self.bwd = [], []
         self.fwd_flops = self.bwd_flops = 0.0
+        self.cuda_graph, self.ran_eager = None, False
 
         def conv(dst, srcs, shape, flip=False, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0,
                  res32=None, res16=None, mask=None, cout=NUMK, bias=True):
@@ -286,14 +287,31 @@ class Trainer:
                 dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)), non_blocking=True)
 
     def forward_backward_device(self, g):
-        """Forward + backward on the tensors already in g.x_in / g.y_true; gradients land in self.grads."""
-        st = L.stream_ptr()
-        self.grads.zero_()
-        g.loss_sum.zero_()
-        for f in g.fwd:
-            f(st)
-        for f in g.bwd:
-            f(st)
+        """Forward + backward on the tensors already in g.x_in / g.y_true; gradients land in self.grads.  The ~450
+        launches are a fixed sequence on fixed buffers: after one eager step they replay as one CUDA graph (at 32
+        patches per GPU the step is otherwise launch-bound)."""
+        if self.engine.use_graphs and g.cuda_graph is not None:
+            g.cuda_graph.replay()
+            return
+
+        def body(st):
+            self.grads.zero_()
+            g.loss_sum.zero_()
+            for f in g.fwd:
+                f(st)
+            for f in g.bwd:
+                f(st)
+
+        body(L.stream_ptr())
+        if self.engine.use_graphs and g.ran_eager and not torch.cuda.is_current_stream_capturing():
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    body(L.stream_ptr())
+                g.cuda_graph = gr
+            except Exception:  # noqa: BLE001  (capture unsupported here: stay eager)
+                self.engine.use_graphs = False
+        g.ran_eager = True
 
     def apply_gradients(self):
         """Data-parallel mean of the gradients (NCCL all-reduce of the flat arena) + fused Keras Adam + repack."""

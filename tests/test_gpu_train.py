@@ -274,3 +274,28 @@ def test_fit_end_to_end_with_dataset_dirs(tmp_path, monkeypatch):
     model2.load_weights(str(tmp_path / "weights_Double" / saved[-1]))
     x = rng.random((1, 8, 8, 3)).astype(np.float32)
     assert np.array_equal(model.predict(x), model2.predict(x))
+
+
+def test_training_graph_replay_matches_eager():
+    """forward+backward replayed as a CUDA graph reproduces the eager launches: the kernel (weight) gradients, summed
+    in a fixed order, bit for bit; bias / first-layer gradients and the loss, which use fp32 / fp64 atomics, to
+    rounding."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    from sr100.train import Trainer
+    rng = np.random.default_rng(4)
+    x = rng.random((2, 8, 8, 3)).astype(np.float32)
+    y = rng.random((2, 32, 32, 3)).astype(np.float32)
+    tr = Trainer(Engine(om.init_weights(9, bias_scale=0.01)))
+    g = tr.graph(2, 8, 8)
+    tr._load(g, x, y)
+    outs = []
+    for _ in range(3):                       # eager, eager + capture, replay
+        tr.forward_backward_device(g)
+        torch.cuda.synchronize()
+        outs.append((tr.grads.clone(), float(g.loss_sum.item())))
+    assert g.cuda_graph is not None
+    ow, nw, _, _ = tr.engine.param_slices["conv2d_40"]
+    for gr, ls in outs[1:]:
+        assert torch.equal(gr[ow:ow + nw], outs[0][0][ow:ow + nw])
+        assert torch.allclose(gr, outs[0][0], rtol=1e-4, atol=1e-7) and abs(ls - outs[0][1]) <= 1e-9 * abs(ls)

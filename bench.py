@@ -151,7 +151,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": output_megapixels() / value * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "set5_x4_tiled", "tiles": 186, "output_mp_per_step": output_megapixels()},
+        "config": {"workload": "set5_x4_tiled", "images": SET5_SHAPES, "tiles": 186, "patch": 96, "step": 64,
+                   "output_mp_per_step_per_gpu": output_megapixels(), "weights": "glorot_uniform random init",
+                   "sample": "each step times a bounded sample of the workload's tiles on the host cores and scales to "
+                             "the full step (all 186 tiles of the literal reference tiling)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample + " per step; Keras/TensorFlow cannot be installed offline, so this is the "
                                             "CPU restatement of the reference graph (oracle/model.py)"},

@@ -299,3 +299,19 @@ def test_training_graph_replay_matches_eager():
     for gr, ls in outs[1:]:
         assert torch.equal(gr[ow:ow + nw], outs[0][0][ow:ow + nw])
         assert torch.allclose(gr, outs[0][0], rtol=1e-4, atol=1e-7) and abs(ls - outs[0][1]) <= 1e-9 * abs(ls)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_wgrad_geometry_sweep(lib, seed):
+    """Random (batch, rows, width, kernel) shapes: narrow images sharing K rows, ragged widths, several segments,
+    row-block splits -- against the oracle's filter gradient."""
+    rng = np.random.default_rng(500 + seed)
+    for _ in range(5):
+        k = int(rng.choice([1, 3, 5]))
+        NB, H = int(rng.integers(1, 7)), int(rng.integers(1, 30))
+        W = int(rng.choice([int(rng.integers(1, 50)), int(rng.integers(50, 130)), int(rng.integers(130, 280))]))
+        x = bf16_round(rng.normal(0, 0.5, size=(NB, H, W, 128)))
+        g = bf16_round(rng.normal(0, 0.5, size=(NB, H, W, 128)))
+        got = _wgrad_gpu(lib, x, g, k)
+        want = _wgrad_oracle(x, g, k)
+        assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (k, NB, H, W)

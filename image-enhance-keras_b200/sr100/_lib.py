@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsr100.so")
+LIB_PATH = os.environ.get("SR100_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsr100.so")
 
 
 class SrError(RuntimeError):

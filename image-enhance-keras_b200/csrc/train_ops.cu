@@ -60,6 +60,99 @@ __global__ void mse_tail_grad_kernel(const float* __restrict__ pred, const float
   }
 }
 
+// Same loss gradient, laid out as the im2col of the 3x3 tail conv's backward: channel j = (ky*3+kx)*3 + co of pixel
+// (y,x) holds g3[y-ky+1][x-kx+1][co] (zero outside the image), channels 27..127 zero.  With this tensor both tail
+// gradients are 1x1 problems for the 128-wide tensor-core kernels:
+//   dgrad: gx[pix][ci]  = sum_j A[pix][j] * W[ky][kx][ci][co]                (1x1 conv, K = 27 padded to 128)
+//   wgrad: dW[ky][kx][ci][co] = sum_pix x[pix][ci] * A[pix][j]               (k = 1 filter gradient)
+// loss_sum += sum (pred-target)^2 and db3[co] += sum g3[..][co] (each pixel counted once: by the block that owns it).
+// One block per strip of kColStrip pixels of one image row: the three gradient rows around it are staged in shared
+// memory as bf16-rounded floats (with a 1-pixel halo), then 16 threads per pixel write its 256-byte row.
+constexpr int kColStrip = 128;
+
+__global__ void __launch_bounds__(kBlock)
+mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int strips,
+                         float inv_total2, uint4* __restrict__ a128, double* __restrict__ loss_sum,
+                         float* __restrict__ db3) {
+  constexpr int kRow = (kColStrip + 2) * 3;
+  __shared__ float g[3 * kRow];
+  __shared__ double red_loss[kBlock / 32];
+  __shared__ float red_db[kBlock / 32][3];
+  const int strip = blockIdx.x % strips;
+  const int y = (blockIdx.x / strips) % H;
+  const size_t n = blockIdx.x / ((size_t)strips * H);
+  const int x0 = strip * kColStrip;
+  const int npx = min(kColStrip, W - x0);
+  double loss = 0.0;
+  float db[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < 3 * kRow; i += kBlock) {
+    const int r = i / kRow, rem = i - r * kRow;
+    const int xx = rem / 3, c = rem - xx * 3;
+    const int sy = y - 1 + r, sx = x0 - 1 + xx;
+    float v = 0.f;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W && xx <= npx + 1) {
+      const size_t o = (((size_t)n * H + sy) * W + sx) * 3 + c;
+      const float p = pred[o];
+      const float d = p - target[o];
+      v = __bfloat162float(__float2bfloat16_rn(p > 0.f ? d * inv_total2 : 0.f));
+      if (r == 1 && xx >= 1 && xx <= npx) {
+        loss += (double)d * (double)d;
+        db[0] += c == 0 ? v : 0.f;
+        db[1] += c == 1 ? v : 0.f;
+        db[2] += c == 2 ? v : 0.f;
+      }
+    }
+    g[i] = v;
+  }
+  // element offsets of this thread's 8 channels (fixed: kBlock is a multiple of 16)
+  const int q = threadIdx.x & 15;
+  int off[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int j = q * 8 + e;
+    const int tap = j / 3, co = j - tap * 3;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    off[e] = j < 27 ? ((2 - ky) * (kColStrip + 2) + (2 - kx)) * 3 + co : -1;
+  }
+  __syncthreads();
+  const size_t base = (((size_t)n * H + y) * W + x0) * 16;
+  for (int i = threadIdx.x; i < npx * 16; i += kBlock) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (q < 4) {
+      const int px3 = (i >> 4) * 3;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? g[off[e] + px3] : 0.f;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+      o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+    a128[base + i] = o;
+  }
+  // block reductions: loss (fp64) and the three bias-gradient sums
+  for (int o = 16; o > 0; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) db[c] += __shfl_xor_sync(0xffffffffu, db[c], o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    red_loss[wid] = loss;
+    red_db[wid][0] = db[0]; red_db[wid][1] = db[1]; red_db[wid][2] = db[2];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (int w = 0; w < kBlock / 32; ++w) {
+      l += red_loss[w]; b0 += red_db[w][0]; b1 += red_db[w][1]; b2 += red_db[w][2];
+    }
+    if (loss_sum) atomicAdd(loss_sum, l);
+    if (db3) { atomicAdd(db3, b0); atomicAdd(db3 + 1, b1); atomicAdd(db3 + 2, b2); }
+  }
+}
+
 // out[c] += scale * sum_pix g[pix][c], g bf16 [npix][128].  16 threads per pixel row (8 channels each), 16 rows
 // per block pass; block-level shared-memory reduction, one fp32 atomic per channel per block.
 __global__ void colsum_bf16_kernel(const uint4* __restrict__ g, size_t npix, float scale, float* __restrict__ out) {
@@ -122,6 +215,19 @@ extern "C" int sr_mse_tail_grad(const float* pred, const float* target, size_t n
   mse_tail_grad_kernel<<<grid_for(npix * 16, kBlock, 148 * 16), kBlock, 0, as_stream(stream)>>>(
       pred, target, npix, channels, inv2, reinterpret_cast<uint4*>(g128_bf16), loss_sum);
   return check_launch("mse_tail_grad_kernel");
+}
+
+extern "C" int sr_mse_tail_grad_col(const float* pred, const float* target, int NB, int H, int W, size_t n_total,
+                                    void* a128_bf16, double* loss_sum, float* db3, void* stream) {
+  if (!pred || !target || !a128_bf16) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: null pointer");
+  if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: empty tensor");
+  const float inv2 = (float)(2.0 / (double)n_total);
+  const int strips = (W + kColStrip - 1) / kColStrip;
+  const size_t blocks = (size_t)NB * H * strips;
+  if (blocks > 0x7fffffffull) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: tensor too large");
+  mse_tail_grad_col_kernel<<<(unsigned)blocks, kBlock, 0, as_stream(stream)>>>(
+      pred, target, H, W, strips, inv2, reinterpret_cast<uint4*>(a128_bf16), loss_sum, db3);
+  return check_launch("mse_tail_grad_col_kernel");
 }
 
 extern "C" int sr_colsum_bf16(const void* g_bf16, size_t npix, float scale, float* out, void* stream) {

@@ -123,6 +123,7 @@ SIGNATURES = {
     "sr_wgrad_plan_destroy": (None, [_vp]),
     "sr_wgrad_plan_info": (_i, [_vp, C.POINTER(WgradPlanInfo)]),
     "sr_mse_tail_grad": (_i, [_vp, _vp, _sz, _i, _sz, _vp, _vp, _vp]),
+    "sr_mse_tail_grad_col": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _vp]),
     "sr_colsum_bf16": (_i, [_vp, _sz, _f, _vp, _vp]),
     "sr_head1x1_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_axpby_f32": (_i, [_vp, _vp, _f, _f, _sz, _vp, _vp, _vp]),

@@ -173,18 +173,28 @@ class _TrainGraph:
         # ------------------------------------------------------------------ backward
         npix_hr = NB * HH * WW
         self.n_local = npix_hr * 3
-        self.bwd.append(lambda st: L.check(lib.sr_mse_tail_grad(
-            L.ptr(self.out), L.ptr(self.y_true), npix_hr, 3, self.n_local, L.ptr(gth1), L.ptr(self.loss_sum), st)))
-        # tail conv (128 -> 3): its gradient travels as a 128-channel tensor whose channels >= 3 are zero
-        p = _WgradPlan(lib, SH[2], gth1, hr, 3, 1.0, tr.tail_dw128, tr.workspace)
-        self.bwd_flops += p.flops * 3 / 128.0
+        # tail conv (128 -> 3, 3x3): the loss gradient is written as the im2col of the tail's backward (27 channels of a
+        # 128-channel bf16 tensor), which turns both tail gradients into 1x1 problems for the tensor-core kernels
+        tail_w, tail_b = tr.grad_w(tail), tr.grad_b(tail)       # views of the gradient arena (zeroed every step)
+        self.bwd.append(_Op("tail_grad", lambda st: L.check(lib.sr_mse_tail_grad_col(
+            L.ptr(self.out), L.ptr(self.y_true), NB, HH, WW, self.n_local, L.ptr(gth1), L.ptr(self.loss_sum),
+            L.ptr(tail_b), st))))
+        p = _WgradPlan(lib, SH[2], gth1, hr, 1, 1.0, tr.tail_d128, tr.workspace)      # D[ci][j], j = (ky,kx,co)
+        self.bwd_flops += 2.0 * npix_hr * 27 * NUMK
         self.bwd.append(_Op("wgrad_tail", p.run))
-        tail_w, tail_b = tr.grad_w(tail), tr.grad_b(tail)
-        self.bwd.append(lambda st: tail_w.copy_(tr.tail_dw128[..., :3]))
-        self.bwd.append(lambda st: tr.tail_db128.zero_())
-        self.bwd.append(lambda st: L.check(lib.sr_colsum_bf16(L.ptr(gth1), npix_hr, 1.0, L.ptr(tr.tail_db128), st)))
-        self.bwd.append(lambda st: tail_b.copy_(tr.tail_db128[:3]))
-        conv(self.bwd, [(tail, gth1)], hr, flip=True, out_bf16=gsh, bias=False)
+        self.bwd.append(lambda st: tail_w.copy_(tr.tail_d128.view(NUMK, NUMK)[:, :27].reshape(NUMK, 3, 3, 3)
+                                                .permute(1, 2, 0, 3)))
+        # dgrad: 1x1 conv with B[j][ci] = W[ky][kx][ci][co] (packed at every weight refresh, Trainer.repack_t)
+        d = L.ConvDesc()
+        d.nsrc = 1
+        d.in_[0], d.wpacked[0], d.ksize[0] = gth1.data_ptr(), tr.tail_colw_packed.data_ptr(), 1
+        d.NB, d.H, d.W, d.cin, d.cout = NB, HH, WW, NUMK, NUMK
+        d.alpha, d.beta, d.relu = 1.0, 0.0, 0
+        d.out_bf16 = gsh.data_ptr()
+        d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
+        pl = _Plan(lib, d)
+        self.bwd_flops += 2.0 * npix_hr * 27 * NUMK
+        self.bwd.append(_Op("dgrad_tail", pl.run))
 
         def bwd_block(kind, i, x, t1, t2, y, shape, f32s, last_hr=False):
             g, g32 = (gs, gs32) if f32s else (gsh, None)
@@ -238,8 +248,9 @@ class Trainer:
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.t = 0
         self.workspace = torch.empty(self.lib.sr_wgrad_workspace_bytes(), dtype=torch.uint8, device=dev)
-        self.tail_dw128 = torch.zeros(3, 3, NUMK, NUMK, dtype=torch.float32, device=dev)
-        self.tail_db128 = torch.zeros(NUMK, dtype=torch.float32, device=dev)
+        self.tail_d128 = torch.zeros(1, 1, NUMK, NUMK, dtype=torch.float32, device=dev)    # k=1 wgrad of the tail
+        self.tail_colw = torch.zeros(1, 1, NUMK, NUMK, dtype=torch.float32, device=dev)    # B[j][ci] of its dgrad
+        self.tail_colw_packed = torch.empty(self.lib.sr_packed_weight_bytes(1, NUMK), dtype=torch.uint8, device=dev)
         self.packed_t = {}      # name -> packed weights of the input-gradient conv
         self._pack_table_t = None
         self._graphs = {}
@@ -268,6 +279,12 @@ class Trainer:
                                                       device=self.engine.device)
             self._pack_table_t = PackTable(self.engine, self.packed_t, flip=True)
         self._pack_table_t.run()
+        # tail dgrad as a 1x1 conv over the im2col'ed gradient: B[j = (ky,kx,co)][ci] = W[ky][kx][ci][co]
+        tail = self.engine.specs[-1][0]
+        w = self.engine.master[tail][0]                                   # [3,3,128,3]
+        self.tail_colw.view(NUMK, NUMK)[:27].copy_(w.permute(0, 1, 3, 2).reshape(27, NUMK))
+        L.check(self.lib.sr_pack_conv_weights(L.ptr(self.tail_colw), 1, NUMK, 0, L.ptr(self.tail_colw_packed),
+                                              L.stream_ptr()))
 
     def graph(self, NB, H, W):
         key = (NB, H, W)

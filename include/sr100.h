@@ -240,6 +240,14 @@ int sr_wgrad_plan_info(const sr_wgrad_plan* plan, sr_wgrad_plan_info_t* info);
  * of 128 channels (channels >= `channels` zero) = the operand layout of dgrad / wgrad. */
 int sr_mse_tail_grad(const float* pred, const float* target, size_t npix, int channels,
                      size_t n_total, void* g128_bf16, double* loss_sum, void* stream);
+/* The same loss gradient for a 3-channel 3x3 tail, laid out as the im2col of its backward: channel
+ * j = (ky*3+kx)*3 + co of pixel (y,x) holds g3[y-ky+1][x-kx+1][co] (0 outside the image), channels 27..127 zero.
+ * Both tail gradients then are 1x1 problems for the 128-wide tensor-core kernels:
+ *   dgrad = sr_conv_plan (ksize 1) of this tensor with B[j][ci] = w[ky][kx][ci][co];
+ *   wgrad = sr_wgrad_plan (ksize 1) of (tail input, this tensor): dw[ky][kx][ci][co] = D[ci][j];
+ *   bias gradient: db3[co] += sum over pixels of the (bf16-rounded) gradient, if db3 is not NULL. */
+int sr_mse_tail_grad_col(const float* pred, const float* target, int NB, int H, int W, size_t n_total,
+                         void* a128_bf16, double* loss_sum, float* db3, void* stream);
 /* Bias gradient: out[c] += scale * sum_pix g[pix][c]; g bf16 [npix,128]; out fp32 [128]. */
 int sr_colsum_bf16(const void* g_bf16, size_t npix, float scale, float* out, void* stream);
 /* First layer (models.py:1177) backward: g0 = g*(act>0); dw[3][128] += x^T g0; db[128] += colsum g0.

@@ -121,6 +121,32 @@ def test_dgrad_is_conv_with_flipped_weights(lib):
         assert np.abs(out.cpu().numpy() - want).max() <= 2.0 ** -8 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("NB,H,W", [(2, 7, 10), (1, 3, 300), (3, 1, 129), (1, 5, 128)])
+def test_tail_grad_col_is_im2col_of_loss_gradient(lib, NB, H, W):
+    """sr_mse_tail_grad_col: channel (ky*3+kx)*3+co of pixel (y,x) = g3[y-ky+1][x-kx+1][co], zero outside / >= 27."""
+    from sr100 import _lib as L
+    rng = np.random.default_rng(11)
+    pred = np.maximum(rng.normal(0.2, 0.3, size=(NB, H, W, 3)), 0).astype(np.float32)
+    tgt = rng.random((NB, H, W, 3)).astype(np.float32)
+    n_total = pred.size
+    a = torch.full((NB, H, W, 128), 5.0, device="cuda", dtype=torch.bfloat16)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    pd, td = torch.from_numpy(pred).cuda(), torch.from_numpy(tgt).cuda()
+    db = torch.ones(3, device="cuda")
+    L.check(lib.sr_mse_tail_grad_col(L.ptr(pd), L.ptr(td), NB, H, W, n_total, L.ptr(a), L.ptr(loss), L.ptr(db),
+                                     L.stream_ptr()))
+    g3 = bf16_round(np.where(pred > 0, (pred - tgt) * np.float32(2.0 / n_total), 0.0).astype(np.float32))
+    gp = np.pad(g3, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    want = np.zeros((NB, H, W, 128), dtype=np.float32)
+    for ky in range(3):
+        for kx in range(3):
+            j = (ky * 3 + kx) * 3
+            want[..., j:j + 3] = gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W, :]
+    assert np.array_equal(a.float().cpu().numpy(), want)
+    assert np.abs(db.cpu().numpy() - (1.0 + g3.astype(np.float64).sum((0, 1, 2)))).max() <= 1e-6
+    assert abs(loss.item() - ((pred.astype(np.float64) - tgt) ** 2).sum()) <= 1e-9 * n_total
+
+
 def test_tail_grad_colsum_head_bwd(lib):
     from sr100 import _lib as L
     rng = np.random.default_rng(3)

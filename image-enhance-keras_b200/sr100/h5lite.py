@@ -1,0 +1,667 @@
+"""Minimal HDF5 reader / writer for Keras weight files (no h5py, no libhdf5).
+
+Why: the reference loads and checkpoints its weights as Keras HDF5 (`weights_Double/weights025-17-0.93.h5`,
+models.py:1217-1218 `model.load_weights`; `ModelCheckpoint(self.weight_path, ...)` models.py:141-142, :1155), and
+h5py / libhdf5 are a third-party dependency that is not part of the reference tree and is absent from this image.
+This module restates the parts of the published *HDF5 File Format Specification* (version 2.0, superblock 0-3)
+that such files use:
+
+reader   superblock v0/v1 (libhdf5 `libver='earliest'`, what h5py writes by default) and v2/v3; user blocks /
+         non-zero base address; object headers v1 and v2 (with continuation blocks); old-style groups (symbol-table
+         message -> B-tree v1 -> SNOD -> local heap) and compact new-style groups (link messages); datasets with
+         contiguous, compact or chunked (B-tree v1, optional deflate / shuffle filters) layout, layout message
+         versions 1-3; fixed-point, floating-point and fixed-length string datatypes; attribute messages v1-v3.
+writer   superblock v0, old-style groups, object header v1, contiguous datasets (chunked + deflate optionally, used
+         by the tests to exercise the reader's chunk path), fixed-length string / numeric attributes - the layout
+         h5py produces for `keras.Model.save_weights`.
+
+Parity status: the reader is pinned against a file written by libhdf5 itself (tests/golden/matlab73_testdouble.h5,
+MATLAB 7.3 = HDF5 1.8 with a 512-byte user block); the writer is pinned only through this reader (round trips) -
+"written from the specification, not yet opened with libhdf5" (DESIGN.md section 2).
+
+Keras layout (keras/engine/saving.py `save_weights_to_hdf5_group`, Keras 2.x) [lib]:
+    /            attrs  layer_names = [b'level1', b'conv2d_1', ...], backend = b'tensorflow', keras_version = b'2.x'
+    /<layer>     attrs  weight_names = [b'<layer>/kernel:0', b'<layer>/bias:0']
+    /<layer>/<layer>/kernel:0   float32 HWIO         /<layer>/<layer>/bias:0   float32
+A full-model file (`model.save`) holds the same tree under `/model_weights`.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+
+import numpy as np
+
+SIGNATURE = b"\x89HDF\r\n\x1a\n"
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class H5Error(OSError):
+    pass
+
+
+# ====================================================================================================== reader
+class _Reader:
+    def __init__(self, buf):
+        self.buf = buf
+        self.base = 0
+        self.O = 8       # size of offsets
+        self.Lz = 8      # size of lengths
+        self._find_superblock()
+
+    # ---- primitives
+    def u(self, pos, n):
+        return int.from_bytes(self.buf[pos:pos + n], "little")
+
+    def off(self, pos):
+        return self.u(pos, self.O)
+
+    def length(self, pos):
+        return self.u(pos, self.Lz)
+
+    def addr(self, a):
+        """file address -> position in the buffer (addresses are relative to the base address)"""
+        return self.base + a
+
+    def undef(self, a):
+        return a == (1 << (8 * self.O)) - 1
+
+    # ---- superblock
+    def _find_superblock(self):
+        pos = 0
+        n = len(self.buf)
+        while pos + 8 <= n:                       # the superblock sits at 0, 512, 1024, 2048, ... (user block)
+            if self.buf[pos:pos + 8] == SIGNATURE:
+                break
+            pos = 512 if pos == 0 else pos * 2
+        else:
+            raise H5Error("not an HDF5 file (signature not found)")
+        ver = self.buf[pos + 8]
+        if ver in (0, 1):
+            self.O, self.Lz = self.buf[pos + 13], self.buf[pos + 14]
+            p = pos + 24 + (4 if ver == 1 else 0)
+            base = self.off(p)
+            self.base = pos if base == 0 and pos != 0 else base     # libhdf5 stores the user-block size here
+            p += 4 * self.O                        # base, free-space, end-of-file, driver-info
+            # root group symbol-table entry: name offset, header address, cache type, reserved, scratch
+            self.root_header = self.off(p + self.O)
+        elif ver in (2, 3):
+            self.O, self.Lz = self.buf[pos + 9], self.buf[pos + 10]
+            p = pos + 12
+            base = self.off(p)
+            self.base = pos if base == 0 and pos != 0 else base
+            self.root_header = self.off(p + 3 * self.O)
+        else:
+            raise H5Error("unsupported HDF5 superblock version %d" % ver)
+
+    # ---- object headers -> list of (type, flags, payload_pos, payload_size)
+    def messages(self, header_addr):
+        pos = self.addr(header_addr)
+        if self.buf[pos:pos + 4] == b"OHDR":
+            return self._messages_v2(pos)
+        ver = self.buf[pos]
+        if ver != 1:
+            raise H5Error("unsupported object header version %d at %#x" % (ver, header_addr))
+        nmsg = self.u(pos + 2, 2)
+        size = self.u(pos + 8, 4)
+        blocks = [(pos + 16, size)]               # 12-byte prefix padded to 8
+        out = []
+        while blocks and len(out) < nmsg:
+            p, left = blocks.pop(0)
+            end = p + left
+            while p + 8 <= end and len(out) < nmsg:
+                mtype, msize, mflags = self.u(p, 2), self.u(p + 2, 2), self.buf[p + 4]
+                body = p + 8
+                out.append((mtype, mflags, body, msize))
+                if mtype == 0x10:                  # continuation
+                    blocks.append((self.addr(self.off(body)), self.length(body + self.O)))
+                p = body + msize
+        return out
+
+    def _messages_v2(self, pos):
+        flags = self.buf[pos + 5]
+        p = pos + 6
+        if flags & 0x20:
+            p += 16
+        if flags & 0x10:
+            p += 4
+        nb = 1 << (flags & 3)
+        chunk0 = self.u(p, nb)
+        p += nb
+        track_order = bool(flags & 0x04)
+        blocks = [(p, chunk0)]
+        out = []
+        while blocks:
+            p, left = blocks.pop(0)
+            end = p + left
+            while p + 4 + (2 if track_order else 0) <= end:
+                mtype, msize, mflags = self.buf[p], self.u(p + 1, 2), self.buf[p + 3]
+                body = p + 4 + (2 if track_order else 0)
+                if body + msize > end:
+                    break
+                out.append((mtype, mflags, body, msize))
+                if mtype == 0x10:
+                    a, ln = self.addr(self.off(body)), self.length(body + self.O)
+                    if self.buf[a:a + 4] != b"OCHK":
+                        raise H5Error("bad object header continuation block")
+                    blocks.append((a + 4, ln - 8))         # minus signature and checksum
+                p = body + msize
+        return out
+
+    # ---- groups
+    def links(self, header_addr):
+        """name -> object header address of the children of a group"""
+        out = {}
+        for mtype, _, body, size in self.messages(header_addr):
+            if mtype == 0x11:                      # symbol table: B-tree v1 + local heap
+                btree, heap = self.off(body), self.off(body + self.O)
+                hp = self.addr(heap)
+                if self.buf[hp:hp + 4] != b"HEAP":
+                    raise H5Error("bad local heap signature")
+                data_seg = self.addr(self.off(hp + 8 + 2 * self.Lz))
+                self._walk_group_btree(btree, data_seg, out)
+            elif mtype == 0x06:                    # link message (new-style compact group)
+                self._parse_link(body, out)
+            elif mtype == 0x02:                    # link info: dense storage lives in a fractal heap
+                f = self.buf[body + 1]
+                p = body + 2 + (8 if f & 1 else 0)
+                if not self.undef(self.off(p)):
+                    raise H5Error("dense (fractal-heap) group storage is not supported; re-save the file with "
+                                  "h5py's default libver")
+        return out
+
+    def _walk_group_btree(self, node_addr, data_seg, out):
+        p = self.addr(node_addr)
+        if self.buf[p:p + 4] != b"TREE" or self.buf[p + 4] != 0:
+            raise H5Error("bad group B-tree node")
+        level, used = self.buf[p + 5], self.u(p + 6, 2)
+        q = p + 8 + 2 * self.O
+        for i in range(used):
+            child = self.off(q + self.Lz + i * (self.Lz + self.O))
+            if level > 0:
+                self._walk_group_btree(child, data_seg, out)
+                continue
+            s = self.addr(child)
+            if self.buf[s:s + 4] != b"SNOD":
+                raise H5Error("bad symbol table node")
+            nsym = self.u(s + 6, 2)
+            e = s + 8
+            for _ in range(nsym):
+                name_off, hdr = self.off(e), self.off(e + self.O)
+                a = data_seg + name_off
+                z = self.buf.index(b"\0", a)
+                out[bytes(self.buf[a:z]).decode("utf-8")] = hdr
+                e += 2 * self.O + 24
+
+    def _parse_link(self, p, out):
+        flags = self.buf[p + 1]
+        q = p + 2
+        ltype = 0
+        if flags & 0x08:
+            ltype = self.buf[q]
+            q += 1
+        if flags & 0x04:
+            q += 8
+        if flags & 0x10:
+            q += 1
+        nb = 1 << (flags & 3)
+        nlen = self.u(q, nb)
+        q += nb
+        name = bytes(self.buf[q:q + nlen]).decode("utf-8")
+        q += nlen
+        if ltype == 0:
+            out[name] = self.off(q)
+
+    # ---- datatypes / dataspaces
+    def dtype(self, p):
+        """-> (numpy dtype, bytes consumed); fixed-length strings map to 'S<n>'"""
+        cls = self.buf[p] & 0x0F
+        bits0 = self.buf[p + 1]
+        size = self.u(p + 4, 4)
+        if cls == 0:
+            kind = "i" if bits0 & 0x08 else "u"
+            return np.dtype((">" if bits0 & 1 else "<") + kind + str(size)), 12
+        if cls == 1:
+            return np.dtype((">" if bits0 & 1 else "<") + "f" + str(size)), 20
+        if cls == 3:
+            return np.dtype("S%d" % size), 8
+        raise H5Error("unsupported HDF5 datatype class %d" % cls)
+
+    def shape(self, p):
+        ver, rank, flags = self.buf[p], self.buf[p + 1], self.buf[p + 2]
+        if ver == 1:
+            q = p + 8
+        elif ver == 2:
+            if self.buf[p + 3] == 2:
+                return None                        # null dataspace
+            q = p + 4
+        else:
+            raise H5Error("unsupported dataspace version %d" % ver)
+        return tuple(self.length(q + i * self.Lz) for i in range(rank))
+
+    # ---- attributes
+    def attrs(self, header_addr):
+        out = {}
+        for mtype, _, body, size in self.messages(header_addr):
+            if mtype != 0x0C:
+                continue
+            ver = self.buf[body]
+            nsz, tsz, ssz = self.u(body + 2, 2), self.u(body + 4, 2), self.u(body + 6, 2)
+            p = body + 8 + (1 if ver == 3 else 0)
+            pad = (lambda n: (n + 7) & ~7) if ver == 1 else (lambda n: n)
+            name = bytes(self.buf[p:p + nsz]).split(b"\0")[0].decode("utf-8")
+            p += pad(nsz)
+            try:
+                dt, _ = self.dtype(p)
+            except H5Error:
+                out[name] = None                   # e.g. variable-length strings: not needed for weights
+                continue
+            shp = self.shape(p + pad(tsz))
+            p += pad(tsz) + pad(ssz)
+            if shp is None:
+                out[name] = None
+                continue
+            n = int(np.prod(shp)) if shp else 1
+            a = np.frombuffer(self.buf, dtype=dt, count=n, offset=p).reshape(shp)
+            out[name] = a[()] if shp == () else a.copy()
+        return out
+
+    # ---- datasets
+    def is_dataset(self, header_addr):
+        return any(m[0] == 0x08 for m in self.messages(header_addr))
+
+    def dataset(self, header_addr):
+        dt = shp = layout = None
+        filters = []
+        for mtype, _, body, size in self.messages(header_addr):
+            if mtype == 0x03:
+                dt, _ = self.dtype(body)
+            elif mtype == 0x01:
+                shp = self.shape(body)
+            elif mtype == 0x08:
+                layout = body
+            elif mtype == 0x0B:
+                filters = self._filters(body)
+        if dt is None or shp is None or layout is None:
+            raise H5Error("object at %#x is not a dataset" % header_addr)
+        n = int(np.prod(shp)) if shp else 1
+        ver = self.buf[layout]
+        if ver == 3:
+            cls = self.buf[layout + 1]
+            if cls == 0:
+                sz = self.u(layout + 2, 2)
+                raw = self.buf[layout + 4:layout + 4 + sz]
+                return np.frombuffer(raw, dtype=dt, count=n).reshape(shp).copy()
+            if cls == 1:
+                a = self.off(layout + 2)
+                return self._contiguous(a, dt, shp, n)
+            if cls == 2:
+                nd = self.buf[layout + 2]
+                btree = self.off(layout + 3)
+                cdims = tuple(self.u(layout + 3 + self.O + 4 * i, 4) for i in range(nd))
+                return self._chunked(btree, cdims[:-1], dt, shp, filters)
+            raise H5Error("unsupported layout class %d" % cls)
+        if ver in (1, 2):
+            nd, cls = self.buf[layout + 1], self.buf[layout + 2]
+            p = layout + 8
+            a = None
+            if cls != 0:
+                a = self.off(p)
+                p += self.O
+            dims = tuple(self.u(p + 4 * i, 4) for i in range(nd))
+            p += 4 * nd
+            if cls == 1:
+                return self._contiguous(a, dt, shp, n)
+            if cls == 2:
+                return self._chunked(a, dims[:-1], dt, shp, filters)
+            sz = self.u(p, 4)
+            return np.frombuffer(self.buf[p + 4:p + 4 + sz], dtype=dt, count=n).reshape(shp).copy()
+        raise H5Error("unsupported data layout message version %d" % ver)
+
+    def _contiguous(self, a, dt, shp, n):
+        if self.undef(a):                          # never written: HDF5 returns the fill value (0)
+            return np.zeros(shp, dtype=dt)
+        return np.frombuffer(self.buf, dtype=dt, count=n, offset=self.addr(a)).reshape(shp).copy()
+
+    def _filters(self, p):
+        ver, nf = self.buf[p], self.buf[p + 1]
+        q = p + (8 if ver == 1 else 2)
+        out = []
+        for _ in range(nf):
+            fid = self.u(q, 2)
+            if ver == 1 or fid >= 256:
+                nlen = self.u(q + 2, 2)
+                ncv = self.u(q + 6, 2)
+                q += 8
+                q += (nlen + 7) & ~7 if ver == 1 else nlen
+            else:
+                ncv = self.u(q + 4, 2)
+                q += 6
+            cv = [self.u(q + 4 * i, 4) for i in range(ncv)]
+            q += 4 * ncv
+            if ver == 1 and ncv % 2:
+                q += 4
+            out.append((fid, cv))
+        return out
+
+    def _chunked(self, btree, cdims, dt, shp, filters):
+        out = np.zeros(shp, dtype=dt)
+        if self.undef(btree):
+            return out
+        nd = len(shp)
+        for offs, a, nbytes, mask in self._walk_chunk_btree(btree, nd):
+            raw = bytes(self.buf[self.addr(a):self.addr(a) + nbytes])
+            for i, (fid, cv) in reversed(list(enumerate(filters))):
+                if mask & (1 << i):
+                    continue
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    es = cv[0] if cv else dt.itemsize
+                    raw = np.frombuffer(raw, dtype=np.uint8).reshape(es, -1).T.tobytes()
+                elif fid == 3:
+                    raw = raw[:-4]                  # fletcher32 checksum (not verified)
+                else:
+                    raise H5Error("unsupported HDF5 filter id %d" % fid)
+            chunk = np.frombuffer(raw, dtype=dt, count=int(np.prod(cdims))).reshape(cdims)
+            sl_o = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cdims, shp))
+            sl_c = tuple(slice(0, s.stop - s.start) for s in sl_o)
+            out[sl_o] = chunk[sl_c]
+        return out
+
+    def _walk_chunk_btree(self, node_addr, nd):
+        p = self.addr(node_addr)
+        if self.buf[p:p + 4] != b"TREE" or self.buf[p + 4] != 1:
+            raise H5Error("bad chunk B-tree node")
+        level, used = self.buf[p + 5], self.u(p + 6, 2)
+        q = p + 8 + 2 * self.O
+        ksz = 8 + 8 * (nd + 1)
+        for i in range(used):
+            k = q + i * (ksz + self.O)
+            nbytes, mask = self.u(k, 4), self.u(k + 4, 4)
+            offs = tuple(self.u(k + 8 + 8 * j, 8) for j in range(nd))
+            child = self.off(k + ksz)
+            if level > 0:
+                yield from self._walk_chunk_btree(child, nd)
+            else:
+                yield offs, child, nbytes, mask
+
+
+class Node:
+    """A group or dataset of an open file: `node['a/b']`, `name in node`, `node.keys()`, `node.attrs`,
+    `node.read()` (datasets) - the subset of the h5py API the weight loader uses."""
+
+    def __init__(self, reader, header, path):
+        self._r, self._h, self.name = reader, header, path
+        self._links = None
+
+    @property
+    def is_dataset(self):
+        return self._r.is_dataset(self._h)
+
+    @property
+    def attrs(self):
+        return self._r.attrs(self._h)
+
+    def _children(self):
+        if self._links is None:
+            self._links = self._r.links(self._h)
+        return self._links
+
+    def keys(self):
+        return sorted(self._children())
+
+    def __contains__(self, name):
+        try:
+            self[name]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, path):
+        node = self
+        for part in [p for p in path.split("/") if p]:
+            ch = node._children()
+            if part not in ch:
+                raise KeyError("Unable to open object (object '%s' doesn't exist)" % part)
+            node = Node(self._r, ch[part], node.name.rstrip("/") + "/" + part)
+        return node
+
+    def read(self):
+        return self._r.dataset(self._h)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.read()
+        return a.astype(dtype) if dtype is not None else a
+
+    def visit_datasets(self, prefix=""):
+        """yields (path relative to this node, array) for every dataset below it"""
+        for k in self.keys():
+            ch = self[k]
+            if ch.is_dataset:
+                yield prefix + k, ch.read()
+            else:
+                yield from ch.visit_datasets(prefix + k + "/")
+
+
+def open_file(path_or_bytes):
+    if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
+        buf = bytes(path_or_bytes)
+    else:
+        with open(path_or_bytes, "rb") as f:
+            buf = f.read()
+    r = _Reader(buf)
+    return Node(r, r.root_header, "/")
+
+
+# ====================================================================================================== writer
+def _pad8(b):
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _dtype_msg(dt):
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        exp_bits, mant_bits = {2: (5, 10), 4: (8, 23), 8: (11, 52)}[dt.itemsize]
+        bias = (1 << (exp_bits - 1)) - 1
+        return (struct.pack("<BBBBI", 0x11, 0x20, 8 * dt.itemsize - 1, 0, dt.itemsize)
+                + struct.pack("<HHBBBBI", 0, 8 * dt.itemsize, mant_bits, exp_bits, 0, mant_bits, bias))
+    if dt.kind in "iu":
+        return (struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, dt.itemsize)
+                + struct.pack("<HH", 0, 8 * dt.itemsize))
+    if dt.kind == "S":
+        return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, max(dt.itemsize, 1))      # null-terminated, ASCII
+    raise H5Error("cannot store dtype %s" % dt)
+
+
+def _space_msg(shape):
+    return struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", d) for d in shape)
+
+
+def _attr_msg(name, value):
+    if isinstance(value, str):
+        value = value.encode("utf-8")
+    if isinstance(value, bytes):
+        a = np.array(value, dtype="S%d" % max(len(value), 1))
+    elif isinstance(value, (list, tuple)) and value and isinstance(value[0], (bytes, str)):
+        vals = [v.encode("utf-8") if isinstance(v, str) else v for v in value]
+        a = np.array(vals, dtype="S%d" % max(max(len(v) for v in vals), 1))
+    else:
+        a = np.asarray(value)
+        if a.dtype.kind not in "fiuS":
+            raise H5Error("cannot store attribute %r of dtype %s" % (name, a.dtype))
+        if a.dtype.kind in "fiu":
+            a = a.astype(a.dtype.newbyteorder("<"))
+    nm = name.encode("utf-8") + b"\0"
+    dtm, spm = _dtype_msg(a.dtype), _space_msg(a.shape)
+    return (struct.pack("<BBHHH", 1, 0, len(nm), len(dtm), len(spm)) + _pad8(nm) + _pad8(dtm) + _pad8(spm)
+            + a.tobytes())
+
+
+def _header(msgs):
+    """object header v1 from [(type, payload)]"""
+    body = b"".join(struct.pack("<HHBBBB", t, len(_pad8(p)), 0, 0, 0, 0) + _pad8(p) for t, p in msgs)
+    return struct.pack("<BBHII", 1, 0, len(msgs), 1, len(body)) + b"\0" * 4 + body
+
+
+class _Writer:
+    LEAF_K = 4          # a symbol node holds up to 2K entries
+    INTERNAL_K = 16     # a B-tree node holds up to 2K children
+
+    def __init__(self):
+        self.buf = bytearray()
+
+    def alloc(self, data, align=8):
+        self.buf += b"\0" * (-len(self.buf) % align)
+        a = len(self.buf)
+        self.buf += data
+        return a
+
+    def write_dataset(self, arr, chunk_rows=None, deflate=None):
+        arr = np.asarray(arr).copy(order="C")
+        if arr.dtype.kind in "fiu":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        msgs = [(0x01, _space_msg(arr.shape)), (0x03, _dtype_msg(arr.dtype)),
+                (0x05, struct.pack("<BBBB", 2, 2, 2, 0))]           # fill value v2: late alloc, write if set, undefined
+        if chunk_rows is None or arr.ndim == 0:
+            a = self.alloc(arr.tobytes()) if arr.nbytes else UNDEF
+            msgs.append((0x08, struct.pack("<BBQQ", 3, 1, a, arr.nbytes)))
+        else:
+            cdims = (min(chunk_rows, arr.shape[0]),) + arr.shape[1:]
+            if deflate is not None:
+                msgs.append((0x0B, struct.pack("<BBHI", 1, 1, 0, 0)
+                             + struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<II", deflate, 0)))
+            entries = []
+            for r0 in range(0, arr.shape[0], cdims[0]):
+                chunk = np.zeros(cdims, dtype=arr.dtype)
+                part = arr[r0:r0 + cdims[0]]
+                chunk[:part.shape[0]] = part
+                raw = chunk.tobytes()
+                if deflate is not None:
+                    raw = zlib.compress(raw, deflate)
+                entries.append(((r0,) + (0,) * (arr.ndim - 1), self.alloc(raw), len(raw)))
+            if len(entries) > 2 * 32:
+                raise H5Error("too many chunks for a single B-tree node")
+            nd = arr.ndim
+            node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), UNDEF, UNDEF)
+            for offs, a, nb in entries:
+                node += struct.pack("<II", nb, 0) + b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<Q", 0)
+                node += struct.pack("<Q", a)
+            last = (arr.shape[0] + cdims[0] - 1) // cdims[0] * cdims[0]
+            node += struct.pack("<II", 0, 0) + struct.pack("<Q", last) + b"".join(
+                struct.pack("<Q", 0) for _ in range(nd - 1)) + struct.pack("<Q", 0)
+            bt = self.alloc(node)
+            msgs.append((0x08, struct.pack("<BBB", 3, 2, nd + 1) + struct.pack("<Q", bt)
+                         + b"".join(struct.pack("<I", c) for c in cdims) + struct.pack("<I", arr.dtype.itemsize)))
+        return self.alloc(_header(msgs))
+
+    def write_group(self, children, attrs):
+        """children: {name: (header_addr, is_group, btree, heap)} -> (header_addr, btree_addr, heap_addr)"""
+        names = sorted(children, key=lambda s: s.encode("utf-8"))
+        heap = bytearray(8)                         # offset 0: the empty name
+        name_off = {}
+        for nm in names:
+            name_off[nm] = len(heap)
+            heap += _pad8(nm.encode("utf-8") + b"\0")
+        free_off = len(heap)
+        heap += struct.pack("<QQ", 1, 32) + b"\0" * 16      # one free block (next = 1: end of the free list)
+        heap_data = self.alloc(bytes(heap))
+        heap_addr = self.alloc(b"HEAP" + struct.pack("<BBBBQQQ", 0, 0, 0, 0, len(heap), free_off, heap_data))
+        per = 2 * self.LEAF_K
+        groups = [names[i:i + per] for i in range(0, len(names), per)] or [[]]
+        if len(groups) > 2 * self.INTERNAL_K:
+            raise H5Error("too many links for a single-level group B-tree (%d)" % len(names))
+        snods = []
+        for grp in groups:
+            s = b"SNOD" + struct.pack("<BBH", 1, 0, len(grp))
+            for nm in grp:
+                hdr, is_group, bt, hp = children[nm]
+                s += struct.pack("<QQII", name_off[nm], hdr, 1 if is_group else 0, 0)
+                s += struct.pack("<QQ", bt, hp) if is_group else b"\0" * 16
+            s += b"\0" * (40 * (per - len(grp)))
+            snods.append(self.alloc(s))
+        node = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(groups) if names else 0, UNDEF, UNDEF)
+        node += struct.pack("<Q", 0)                # key 0: the empty name
+        for grp, a in zip(groups, snods):
+            if names:
+                node += struct.pack("<QQ", a, name_off[grp[-1]])
+        node += b"\0" * ((2 * self.INTERNAL_K + 1) * 8 + 2 * self.INTERNAL_K * 8 - (len(node) - 24))
+        btree = self.alloc(node)
+        msgs = [(0x11, struct.pack("<QQ", btree, heap_addr))]
+        msgs += [(0x0C, _attr_msg(k, v)) for k, v in attrs.items()]
+        return self.alloc(_header(msgs)), btree, heap_addr
+
+
+def write_file(path, tree, attrs=None, chunk_rows=None, deflate=None):
+    """tree: nested dict {name: ndarray | dict}; attrs: {group path ('' = root, 'a/b'): {attr name: value}}."""
+    attrs = attrs or {}
+    w = _Writer()
+    w.buf += b"\0" * 96                             # superblock v0 (56 bytes) + root symbol-table entry (40)
+
+    def emit(node, path):
+        children = {}
+        for name, val in node.items():
+            if "/" in name or not name:
+                raise H5Error("bad link name %r" % name)
+            sub = (path + "/" + name) if path else name
+            if isinstance(val, dict):
+                hdr, bt, hp = emit(val, sub)
+                children[name] = (hdr, True, bt, hp)
+            else:
+                children[name] = (w.write_dataset(np.asarray(val), chunk_rows, deflate), False, 0, 0)
+        return w.write_group(children, attrs.get(path, {}))
+
+    root_hdr, root_bt, root_hp = emit(tree, "")
+    eof = len(w.buf)
+    sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _Writer.LEAF_K, _Writer.INTERNAL_K, 0)
+    sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_bt, root_hp)
+    assert len(sb) == 96
+    w.buf[:96] = sb
+    data = bytes(w.buf)
+    if path is None:
+        return data
+    with open(path, "wb") as f:
+        f.write(data)
+    return data
+
+
+# ====================================================================================================== Keras layout
+def save_keras_weights(path, weights, order=None, backend="tensorflow", keras_version="2.2.4"):
+    """weights: {layer: (kernel HWIO, bias)} -> the file `keras.Model.save_weights(path)` writes."""
+    order = list(order) if order is not None else list(weights)
+    tree, attrs = {}, {"": {"layer_names": [n.encode() for n in order], "backend": backend.encode(),
+                            "keras_version": keras_version.encode()}}
+    for name in order:
+        k, b = weights[name]
+        tree[name] = {name: {"kernel:0": np.asarray(k, dtype=np.float32), "bias:0": np.asarray(b, dtype=np.float32)}}
+        attrs[name] = {"weight_names": [("%s/kernel:0" % name).encode(), ("%s/bias:0" % name).encode()]}
+    return write_file(path, tree, attrs)
+
+
+def load_keras_weights(path, layer_names=None):
+    """-> {layer: (kernel, bias)} from `save_weights` / `model.save` files (Keras 2.x layout; Keras 1.x `_W`/`_b`)."""
+    f = open_file(path)
+    g = f["model_weights"] if "model_weights" in f else f
+    at = g.attrs
+    names = layer_names
+    if names is None:
+        ln = at.get("layer_names")
+        names = [n.decode("utf-8") for n in ln] if ln is not None else g.keys()
+    out = {}
+    for name in names:
+        if name not in g:
+            raise KeyError("layer '%s' is not in the weight file" % name)
+        grp = g[name]
+        wn = grp.attrs.get("weight_names")
+        if wn is not None and len(wn):
+            arrs = [grp[w.decode("utf-8")].read() for w in wn]
+        else:
+            arrs = [a for _, a in grp.visit_datasets()]
+        if not arrs:
+            continue                                # layers without weights (Activation, Lambda, Add)
+        if len(arrs) != 2:
+            raise H5Error("layer '%s': expected kernel + bias, found %d tensors" % (name, len(arrs)))
+        k, b = (arrs[0], arrs[1]) if arrs[0].ndim > arrs[1].ndim else (arrs[1], arrs[0])
+        out[name] = (k, b)
+    return out

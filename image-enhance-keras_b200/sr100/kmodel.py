@@ -73,43 +73,41 @@ class Model:
         return sum(l.count_params() for l in self.layers)
 
     def save_weights(self, path, overwrite=True):
-        d = {}
-        for name, (w, b) in self.engine.get_weights_dict().items():
-            d[name + "/kernel:0"] = w
-            d[name + "/bias:0"] = b
-        if path.endswith(".h5"):
-            path = path[:-3] + ".npz"  # h5py is not available offline; same layer/tensor names, npz container
-        np.savez(path, **d)
+        """Keras `save_weights`: an HDF5 file in the Keras 2 layout (sr100.h5lite writes it; no h5py needed), or an
+        .npz with keys '<layer>/kernel:0', '<layer>/bias:0' when the path ends in .npz."""
+        if not overwrite and os.path.exists(path):
+            raise OSError("%s exists and overwrite=False" % path)
+        wd = self.engine.get_weights_dict()
+        if path.endswith(".npz"):
+            d = {}
+            for name, (w, b) in wd.items():
+                d[name + "/kernel:0"] = w
+                d[name + "/bias:0"] = b
+            np.savez(path, **d)
+            return path
+        from . import h5lite
+        h5lite.save_keras_weights(path, wd, order=[n for n, _, _, _ in layer_specs()])
         return path
 
     def load_weights(self, path):
-        cand = [path]
-        if path.endswith(".h5"):
-            cand.append(path[:-3] + ".npz")
-        for p in cand:
-            if os.path.exists(p) and p.endswith(".npz"):
-                z = np.load(p)
-                self.engine.set_weights_dict({n: (z[n + "/kernel:0"], z[n + "/bias:0"]) for n, _, _, _ in layer_specs()})
-                return
-        if os.path.exists(path) and path.endswith(".h5"):
-            try:
-                import h5py  # noqa: F401
-            except ImportError as e:
-                raise ImportError("`load_weights` of a Keras HDF5 file requires h5py, which is not installed; "
-                                  "convert the file to .npz with keys '<layer>/kernel:0', '<layer>/bias:0'") from e
-            self._load_h5(path)
-            return
-        raise OSError("Unable to open file (unable to open file: name = '%s', errno = 2, error message = "
-                      "'No such file or directory')" % path)
-
-    def _load_h5(self, path):
-        import h5py
-        d = {}
-        with h5py.File(path, "r") as f:
-            g = f["model_weights"] if "model_weights" in f else f
-            for name, _, _, _ in layer_specs():
-                grp = g[name][name] if name in g[name] else g[name]
-                d[name] = (np.asarray(grp["kernel:0"]), np.asarray(grp["bias:0"]))
+        """Keras `load_weights` of an HDF5 weight file (`save_weights` or `model.save` layout, models.py:1217-1218),
+        or of the .npz exchange format."""
+        if not os.path.exists(path):
+            raise OSError("Unable to open file (unable to open file: name = '%s', errno = 2, error message = "
+                          "'No such file or directory')" % path)
+        names = [n for n, _, _, _ in layer_specs()]
+        with open(path, "rb") as f:
+            magic = f.read(4)
+        if magic[:2] == b"PK":                           # npz (zip container)
+            z = np.load(path)
+            d = {n: (z[n + "/kernel:0"], z[n + "/bias:0"]) for n in names}
+        else:
+            from . import h5lite
+            d = h5lite.load_keras_weights(path, names)
+        for (n, k, cin, cout) in layer_specs():
+            if tuple(d[n][0].shape) != (k, k, cin, cout) or tuple(d[n][1].shape) != (cout,):
+                raise ValueError("Layer %s: weight file holds kernel %s / bias %s, the model expects %s / %s"
+                                 % (n, tuple(d[n][0].shape), tuple(d[n][1].shape), (k, k, cin, cout), (cout,)))
         self.engine.set_weights_dict(d)
 
     # ------------------------------------------------------------------ training facade

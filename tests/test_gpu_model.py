@@ -88,6 +88,11 @@ def test_sub_batching_is_invisible(weights):
     assert np.array_equal(a, b)
 
 
+def models_mod():
+    import models
+    return models
+
+
 def test_weights_roundtrip_and_npz(dmodel, weights, tmp_path):
     _, model = dmodel
     ws = model.get_weights()
@@ -95,7 +100,12 @@ def test_weights_roundtrip_and_npz(dmodel, weights, tmp_path):
     assert sum(w.size for w in ws) == 21838211 == model.count_params()
     assert np.array_equal(ws[2], weights["conv2d_1"][0])
     p = model.save_weights(str(tmp_path / "w.h5"))
-    assert p.endswith(".npz")
+    with open(p, "rb") as f:
+        assert f.read(8) == b"\x89HDF\r\n\x1a\n"            # a real HDF5 file (sr100.h5lite), Keras 2 layout
+    model.save_weights(str(tmp_path / "w.npz"))
+    mod3 = models_mod().DifvdsrDouble(1).create_model(24, 24)
+    mod3.load_weights(str(tmp_path / "w.npz"))
+    assert all(np.array_equal(a, b) for a, b in zip(mod3.get_weights(), ws))
     import models
     m2 = models.DifvdsrDouble(1)
     mod2 = m2.create_model(24, 24)

@@ -291,7 +291,7 @@ def test_fit_end_to_end_with_dataset_dirs(tmp_path, monkeypatch):
     hist = str(tmp_path / "hist.txt")
     m.fit(batch_size=2, nb_epochs=3, save_history=True, history_fn=hist)
     saved = sorted(os.listdir(str(tmp_path / "weights_Double")))
-    assert len(saved) == 3 and saved[0].startswith("weights025-01-") and saved[0].endswith(".npz")
+    assert len(saved) == 3 and saved[0].startswith("weights025-01-") and saved[0].endswith(".h5")
     assert os.path.exists(hist)
     assert not np.array_equal(model.get_weights()[0], w0)
     # a saved checkpoint loads back into a fresh model and reproduces predict()

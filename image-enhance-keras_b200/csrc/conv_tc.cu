@@ -137,7 +137,10 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
         o[2 * e + 1] = fmaf(P.beta, __uint_as_float(rw[e] & 0xFFFF0000u), o[2 * e + 1]);
       }
     }
-    if (P.relu) {
+    if (P.relu == 2) {  // keras LeakyReLU(alpha): x >= 0 ? x : alpha * x
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = o[e] >= 0.f ? o[e] : P.neg_slope * o[e];
+    } else if (P.relu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
     }
@@ -1044,6 +1047,9 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (d->shuffle_r > 0 && (d->cout <= 16 || d->res_f32 || d->res_bf16 || d->relu_mask_bf16 || d->a_mode == 1))
     return set_error(SR_ERR_UNSUPPORTED, "shuffle_r: 16 < cout <= 128, no residual / mask, a_mode 0");
   if (d->NB < 1 || d->H < 1 || d->W < 1) return set_error(SR_ERR_INVALID, "empty tensor");
+  if (d->relu < 0 || d->relu > 2) return set_error(SR_ERR_INVALID, "relu must be 0, 1 (ReLU) or 2 (LeakyReLU)");
+  if (d->relu == 2 && (d->cout != 128 || d->shuffle_r > 0))
+    return set_error(SR_ERR_UNSUPPORTED, "LeakyReLU epilogue: cout == 128, no shuffle");
   int p = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     const int k = d->ksize[s];
@@ -1089,6 +1095,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.alpha = d->alpha;
   P.beta = d->beta;
   P.relu = d->relu;
+  P.neg_slope = d->leaky_slope;
   P.res_f32 = d->res_f32;
   P.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->res_bf16);
   P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
@@ -1144,8 +1151,8 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   // epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
   const ConvKernelParams& P = pl->P;
   const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
-  const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32;
-  const int epi = P.shuffle_r ? 4 : plain ? 0 : nops != 1 ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32 && P.relu != 2;
+  const int epi = P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
     switch (epi) {

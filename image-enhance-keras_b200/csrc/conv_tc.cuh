@@ -43,7 +43,8 @@ struct ConvKernelParams {
   // epilogue: out = act(alpha * (acc + bias) + beta * res)
   const float* bias;
   float alpha, beta;
-  int relu;
+  int relu;          // 1: ReLU, 2: LeakyReLU(neg_slope) (generic epilogue only)
+  float neg_slope;
   const float* res_f32;
   const __nv_bfloat16* res_bf16;
   __nv_bfloat16* out_bf16;

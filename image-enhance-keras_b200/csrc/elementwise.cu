@@ -82,14 +82,14 @@ __device__ __forceinline__ void load8(const void* base, size_t elem_off, float (
 // outputs of the cell are produced from them (top/bot interpolants shared by the four output rows: the
 // arithmetic per output is exactly the three-lerp TF formula above).  16 lanes cover the 128 channels of a
 // pixel, so every store instruction writes whole 256 B (bf16) / 512 B (fp32) pixels.
-template <bool IN_BF16>
+template <bool IN_BF16, int R = 4>
 __global__ void __launch_bounds__(256)
 bilinear4_fwd_kernel(const void* __restrict__ in, const int* __restrict__ src_index, int NB, int H, int W, int C,
                      int CH, int CW, uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
   // CH x CW: LR cells actually produced (output extent 4CH x 4CW <= 4H x 4W, the cropped HR stage);
   // src_index: optional gather of the source images (output image n reads input image src_index[n]).
   const int C8 = C >> 3;
-  const int OW = 4 * CW;
+  const int OW = R * CW;
   const size_t total = (size_t)NB * CH * CW * C8;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -107,10 +107,10 @@ bilinear4_fwd_kernel(const void* __restrict__ in, const int* __restrict__ src_in
     load8<IN_BF16>(in, (rowb0 + x1) * C + c8 * 8, tr);
     load8<IN_BF16>(in, (rowb1 + x0) * C + c8 * 8, bl);
     load8<IN_BF16>(in, (rowb1 + x1) * C + c8 * 8, br);
-    const size_t obase = (((size_t)n * 4 * CH + 4 * y0) * OW + 4 * x0) * C8 + c8;
+    const size_t obase = (((size_t)n * R * CH + R * y0) * OW + R * x0) * C8 + c8;
 #pragma unroll
-    for (int fx = 0; fx < 4; ++fx) {
-      const float tx = (float)fx * 0.25f;
+    for (int fx = 0; fx < R; ++fx) {
+      const float tx = (float)fx * (1.0f / R);
       float top[8], bot[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -118,8 +118,8 @@ bilinear4_fwd_kernel(const void* __restrict__ in, const int* __restrict__ src_in
         bot[j] = lerp_tf(bl[j], br[j], tx);
       }
 #pragma unroll
-      for (int fy = 0; fy < 4; ++fy) {
-        const float ty = (float)fy * 0.25f;
+      for (int fy = 0; fy < R; ++fy) {
+        const float ty = (float)fy * (1.0f / R);
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = lerp_tf(top[j], bot[j], ty);
@@ -578,6 +578,23 @@ extern "C" int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, i
   if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_fwd: C must be a multiple of 8");
   if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear4_fwd: empty tensor");
   return bilinear4_launch(in, in_is_bf16, nullptr, NB, H, W, C, H, W, out_bf16, out_f32, stream);
+}
+
+// x2 with the same legacy sampling (src = dst * 0.5): Lambda(resize2bil) of Difvdsr4 (models.py:932-940, 1046, 1053)
+extern "C" int sr_bilinear2_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C, void* out_bf16,
+                                float* out_f32, void* stream) {
+  if (!in || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_bilinear2_fwd: null pointer");
+  if (C % 8 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear2_fwd: C must be a multiple of 8");
+  if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_bilinear2_fwd: empty tensor");
+  const size_t total = (size_t)NB * H * W * (C / 8);
+  const unsigned g = grid_for(total, kBlock, 148 * 32);
+  if (in_is_bf16)
+    bilinear4_fwd_kernel<true, 2><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, nullptr, NB, H, W, C, H, W, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  else
+    bilinear4_fwd_kernel<false, 2><<<g, kBlock, 0, as_stream(stream)>>>(
+        in, nullptr, NB, H, W, C, H, W, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  return check_launch("bilinear2_fwd_kernel");
 }
 
 extern "C" int sr_bilinear4_crop_fwd(const void* in, int in_is_bf16, const int* src_index, int n_out, int H,

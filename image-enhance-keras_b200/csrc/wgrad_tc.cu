@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -44,6 +45,7 @@ struct WgradParams {
   int NI, ngrp;        // images per K row (narrow images are processed NI at a time), image groups
   int nring, nbslots;
   int ngroups;
+  int dbg;              // development switches (SR100_WGRAD_DBG): 1 = no TMA after the first ring fill, 2 = no MMA
   int g_tap0[kMaxGroups], g_ntaps[kMaxGroups], g_cta0[kMaxGroups], g_ncta[kMaxGroups];
   float* partial;      // [grid][4][128][128]
 };
@@ -126,6 +128,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ------------------------------------------------ TMA producer: input rows (ring) and gradient rows
     if (lane == 0 && has_work) {
       uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0;  // ring positions (slot + phase parity)
+      bool a_wrapped = false, b_wrapped = false;
       for (int u = rank; u < units; u += ncta) {
         int n, x0, y0, rows;
         decode(u, &n, &x0, &y0, &rows);
@@ -134,23 +137,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int need = y + kymax - P.p;  // newest input row this output row reads
           for (; next_in <= need; ++next_in) {
             mbar_wait(&bars->a_empty[a_slot], a_ph ^ 1u);
-            mbar_expect_tx(&bars->a_full[a_slot], a_row_bytes);
-            uint8_t* dst = a_buf + (size_t)a_slot * a_row_bytes;
-            tma_load_4d(dst, &tmX, &bars->a_full[a_slot], 0, x0 - P.p, next_in, n);
-            tma_load_4d(dst + a_row_bytes / 2, &tmX, &bars->a_full[a_slot], 64, x0 - P.p, next_in, n);
+            if ((P.dbg & 1) && a_wrapped) {
+              mbar_arrive(&bars->a_full[a_slot]);
+            } else {
+              mbar_expect_tx(&bars->a_full[a_slot], a_row_bytes);
+              uint8_t* dst = a_buf + (size_t)a_slot * a_row_bytes;
+              tma_load_4d(dst, &tmX, &bars->a_full[a_slot], 0, x0 - P.p, next_in, n);
+              tma_load_4d(dst + a_row_bytes / 2, &tmX, &bars->a_full[a_slot], 64, x0 - P.p, next_in, n);
+            }
             if (++a_slot == (uint32_t)P.nring) {
               a_slot = 0;
               a_ph ^= 1u;
+              a_wrapped = true;
             }
           }
           mbar_wait(&bars->b_empty[b_slot], b_ph ^ 1u);
-          mbar_expect_tx(&bars->b_full[b_slot], b_row_bytes);
-          uint8_t* dst = b_buf + (size_t)b_slot * b_row_bytes;
-          tma_load_4d(dst, &tmG, &bars->b_full[b_slot], 0, x0, y, n);
-          tma_load_4d(dst + b_row_bytes / 2, &tmG, &bars->b_full[b_slot], 64, x0, y, n);
+          if ((P.dbg & 1) && b_wrapped) {
+            mbar_arrive(&bars->b_full[b_slot]);
+          } else {
+            mbar_expect_tx(&bars->b_full[b_slot], b_row_bytes);
+            uint8_t* dst = b_buf + (size_t)b_slot * b_row_bytes;
+            tma_load_4d(dst, &tmG, &bars->b_full[b_slot], 0, x0, y, n);
+            tma_load_4d(dst + b_row_bytes / 2, &tmG, &bars->b_full[b_slot], 64, x0, y, n);
+          }
           if (++b_slot == (uint32_t)P.nbslots) {
             b_slot = 0;
             b_ph ^= 1u;
+            b_wrapped = true;
           }
         }
       }
@@ -207,7 +220,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 uint32_t a_lo = a_tap + (uint32_t)im * a_img16;
                 uint32_t bl = b_lo + (uint32_t)im * b_img16;
                 for (int s = 0; s < k16n; ++s) {
-                  if (leader) {
+                  if (leader && !(P.dbg & 2)) {
                     const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)a_lo;
                     const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)bl;
                     umma_bf16(d, adesc, bdesc, kIdescMN, accf);
@@ -489,6 +502,10 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
     pl->grid = c;
   }
   P.partial = reinterpret_cast<float*>(d->workspace);
+  {
+    const char* e = getenv("SR100_WGRAD_DBG");
+    P.dbg = e ? atoi(e) : 0;
+  }
   pl->scale = d->scale;
   pl->beta = d->accumulate ? 1.f : 0.f;
   pl->dw = d->dw_hwio;

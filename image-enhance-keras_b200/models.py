@@ -364,17 +364,65 @@ class DifvdsrDouble(BaseSuperResolutionModel):
         return super(DifvdsrDouble, self).fit(batch_size, nb_epochs, save_history, history_fn)
 
 
-class Difvdsr4(BaseSuperResolutionModel):
+class _PlaneNetModel(BaseSuperResolutionModel):
+    """Shared create_model of the two older graphs (sr100.planenet.PlaneNet engines)."""
+    arch = None
+    weights_file = None
+    force_load = False
+
+    def create_model(self, height=32, width=32, channels=3, load_weights=False, batch_size=128):
+        from sr100.kmodel import Model
+        from sr100.planenet import PlaneNet
+        init = BaseSuperResolutionModel.create_model(self, height, width, channels, load_weights, batch_size)
+        if channels != 3:
+            raise ValueError("%s is a 3-channel model" % self.__class__.__name__)
+        if self._engine is None:
+            self._engine = PlaneNet(self.arch)           # glorot_uniform kernels, zero biases (Keras defaults)
+        model = Model(init, engine=self._engine)
+        model.compile(optimizer=_Adam(1e-4, 0.9), loss='mse', metrics=['accuracy'])
+        if load_weights or self.force_load:
+            wpath = os.environ.get("SR100_WEIGHTS", self.weights_file)
+            if getattr(self, "_loaded_from", None) != wpath:
+                model.load_weights(wpath)
+                self._loaded_from = wpath
+        self.model = model
+        return model
+
+
+class Difvdsr4(_PlaneNetModel):
+    """models.py:992-1142: 256 channels; 1x1 head, 6 LeakyReLU(0.001) light blocks, bilinear x2, 20 light blocks with
+    a skip over them, bilinear x2, 6 light blocks, 3x3 tail; 66 convs."""
+    arch = "difvdsr4"
+    weights_file = "weights_Difvdsr2scale/0.1/weights025-18-0.94.h5"       # models.py:1066
+
     def __init__(self, scale_factor):
         super(Difvdsr4, self).__init__("Image ScaleGen", scale_factor)
+        self.weight_path = "weights_Difvdsr2scale/weights-{epoch:02d}-{val_acc:.2f}.h5"   # models.py:1001
 
-    def create_model(self, *a, **k):
-        raise NotImplementedError("Difvdsr4 (models.py:992-1142) is a SURVEY.md 8(f) 'next' row")
+    def create_model(self, height=24, width=24, channels=3, load_weights=False, batch_size=1):
+        """models.py:1006-1076."""
+        return super(Difvdsr4, self).create_model(height, width, channels, load_weights, batch_size)
+
+    def fit(self, batch_size=2, nb_epochs=100, save_history=False, history_fn="ScaleGen History.txt"):
+        """models.py:1079-1080."""
+        return super(Difvdsr4, self).fit(batch_size, nb_epochs, save_history, history_fn)
 
 
-class Difvdsr(BaseSuperResolutionModel):
+class Difvdsr(_PlaneNetModel):
+    """models.py:1274-1357: 192 channels, same resolution; 3x3 head, 32 difference blocks (Subtract, LeakyReLU(0.2),
+    3-way Add, x0.1), 3x3 tail; 130 convs.  Like the reference it always loads its weight file (models.py:1322)."""
+    arch = "difvdsr"
+    weights_file = "weights_Difvdsr/weights-23-0.96.h5"                    # models.py:1323
+    force_load = True
+
     def __init__(self, scale_factor):
         super(Difvdsr, self).__init__("Image ScaleGen", scale_factor)
+        self.weight_path = "weights_Difvdsr/weights-{epoch:02d}-{val_acc:.2f}.h5"         # models.py:1283
 
-    def create_model(self, *a, **k):
-        raise NotImplementedError("Difvdsr (models.py:1274-1357) is a SURVEY.md 8(f) 'next' row")
+    def create_model(self, height=64, width=64, channels=3, load_weights=False, batch_size=128):
+        """models.py:1288-1329."""
+        return super(Difvdsr, self).create_model(height, width, channels, load_weights, batch_size)
+
+    def fit(self, batch_size=8, nb_epochs=100, save_history=False, history_fn="ScaleGen History.txt"):
+        """models.py:1332-1333."""
+        return super(Difvdsr, self).fit(batch_size, nb_epochs, save_history, history_fn)

@@ -41,6 +41,7 @@ class ConvDesc(C.Structure):
         ("out_h", C.c_int), ("out_w", C.c_int),
         ("shuffle_r", C.c_int), ("shuffle_order", C.c_int),
         ("comp_h", C.c_int), ("comp_w", C.c_int),
+        ("leaky_slope", C.c_float),
     ]
 
 
@@ -104,6 +105,7 @@ SIGNATURES = {
     "sr_conv2d_direct": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_head1x1_fwd": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_bilinear4_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sr_bilinear2_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sr_bilinear4_crop_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sr_bilinear4_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sr_patch_count": (_i, [_i, _i, _i]),

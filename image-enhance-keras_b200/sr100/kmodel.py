@@ -36,9 +36,10 @@ class Model:
     def __init__(self, input_shape, engine=None, **engine_kw):
         self.input_shape = (None,) + tuple(input_shape)
         h, w, c = input_shape
-        self.output_shape = (None, 4 * h, 4 * w, 3)
         self.engine = engine if engine is not None else Engine(**engine_kw)
-        self.layers = [Layer(self, *s) for s in layer_specs()]
+        sc = getattr(self.engine, "scale", 4)              # Engine (DifvdsrDouble) and Difvdsr4: x4; Difvdsr: x1
+        self.output_shape = (None, sc * h, sc * w, 3)
+        self.layers = [Layer(self, *s) for s in self.engine.specs]
         self.optimizer = None
         self.loss = None
         self.metrics = []
@@ -86,7 +87,7 @@ class Model:
             np.savez(path, **d)
             return path
         from . import h5lite
-        h5lite.save_keras_weights(path, wd, order=[n for n, _, _, _ in layer_specs()])
+        h5lite.save_keras_weights(path, wd, order=[n for n, _, _, _ in self.engine.specs])
         return path
 
     def load_weights(self, path):
@@ -95,7 +96,7 @@ class Model:
         if not os.path.exists(path):
             raise OSError("Unable to open file (unable to open file: name = '%s', errno = 2, error message = "
                           "'No such file or directory')" % path)
-        names = [n for n, _, _, _ in layer_specs()]
+        names = [n for n, _, _, _ in self.engine.specs]
         with open(path, "rb") as f:
             magic = f.read(4)
         if magic[:2] == b"PK":                           # npz (zip container)
@@ -104,7 +105,7 @@ class Model:
         else:
             from . import h5lite
             d = h5lite.load_keras_weights(path, names)
-        for (n, k, cin, cout) in layer_specs():
+        for (n, k, cin, cout) in self.engine.specs:
             if tuple(d[n][0].shape) != (k, k, cin, cout) or tuple(d[n][1].shape) != (cout,):
                 raise ValueError("Layer %s: weight file holds kernel %s / bias %s, the model expects %s / %s"
                                  % (n, tuple(d[n][0].shape), tuple(d[n][1].shape), (k, k, cin, cout), (cout,)))
@@ -118,6 +119,9 @@ class Model:
 
     def _get_trainer(self):
         if self._trainer is None:
+            if not isinstance(self.engine, Engine):
+                raise NotImplementedError("training is implemented for the DifvdsrDouble graph only (SURVEY.md 8a-7); "
+                                          "Difvdsr4 / Difvdsr run inference")
             from .train import Trainer
             opt = self.optimizer
             self._trainer = Trainer(self.engine, lr=getattr(opt, "lr", 1e-4), beta_1=getattr(opt, "beta_1", 0.9),

@@ -49,7 +49,8 @@ typedef struct sr_conv_desc {
   int cout;              /* 128, or <= 16 (tail conv: 3) */
   const float* bias;     /* [cout] fp32 or NULL; for nsrc == 2 the caller passes bias0 + bias1 */
   float alpha, beta;
-  int relu;              /* 1: ReLU after the residual add */
+  int relu;              /* 1: ReLU after the residual add; 2: LeakyReLU(leaky_slope), keras LeakyReLU of
+                          * Difvdsr4._residual_block_light0 (models.py:1134) / Difvdsr._residual_block (:1351) */
   const float* res_f32;  /* optional residual, fp32 [NB,H,W,cout] */
   const void* res_bf16;  /* optional residual, bf16 (used when res_f32 is NULL) */
   void* out_bf16;        /* optional bf16 output [NB,H,W,cout] */
@@ -73,6 +74,7 @@ typedef struct sr_conv_desc {
    * border is zero-padded).  Lets the tiled path shrink the last LR layers to the region whose
    * receptive field can still reach a surviving pixel.  0: the whole H x W image. */
   int comp_h, comp_w;
+  float leaky_slope;     /* negative-side slope when relu == 2 */
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -143,6 +145,10 @@ int sr_bilinear4_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C
 int sr_bilinear4_crop_fwd(const void* in, int in_is_bf16, const int* src_index, int n_out, int H,
                           int W, int C, int out_h, int out_w, void* out_bf16, float* out_f32,
                           void* stream);
+/* Bilinear x2 with the same TF1 legacy sampling (src = dst * 0.5): Lambda(resize2bil) =
+ * tf.image.resize_bilinear(x, [2h,2w]) of Difvdsr4 (models.py:932-940, applied at :1046 and :1053). */
+int sr_bilinear2_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C, void* out_bf16,
+                     float* out_f32, void* stream);
 /* Adjoint of the above: gin[NB,H,W,C] = sum over the HR samples each LR pixel contributed to. */
 int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream);
 

@@ -1,0 +1,159 @@
+"""-m gpu: the reference's two older graphs, Difvdsr4 (models.py:992-1142) and Difvdsr (models.py:1274-1357), run by
+sr100.planenet on the tensor-core conv kernel (two 128-channel planes per tensor) against the CPU restatement
+oracle/other_models.py (torch fp32).  Tolerance: BASELINE.json north_star's bf16 bound, max-abs 2e-2 on outputs of
+O(1) magnitude; the LeakyReLU epilogue and the x2 bilinear kernel are also checked alone (bit-exact / fp32-exact)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import bf16_round, oracle_conv
+
+pytestmark = pytest.mark.gpu
+
+
+def test_leaky_relu_epilogue_matches_oracle(lib):
+    from sr100 import _lib as L
+    rng = np.random.default_rng(2)
+    NB, H, W = 2, 9, 20
+    x = bf16_round(rng.normal(0, 1, size=(NB, H, W, 128)))
+    w = (rng.standard_normal((3, 3, 128, 128)) / np.sqrt(9 * 128)).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=128).astype(np.float32)
+    for slope in (0.2, 0.001):
+        xd = torch.from_numpy(x).cuda().to(torch.bfloat16)
+        wd = torch.from_numpy(w).cuda()
+        pk = torch.empty(lib.sr_packed_weight_bytes(3, 128), dtype=torch.uint8, device="cuda")
+        L.check(lib.sr_pack_conv_weights(L.ptr(wd), 3, 128, 0, L.ptr(pk), L.stream_ptr()))
+        bd = torch.from_numpy(bias).cuda()
+        of = torch.empty(NB, H, W, 128, device="cuda")
+        d = L.ConvDesc()
+        d.nsrc = 1
+        d.in_[0], d.wpacked[0], d.ksize[0] = xd.data_ptr(), pk.data_ptr(), 3
+        d.NB, d.H, d.W, d.cin, d.cout = NB, H, W, 128, 128
+        d.bias, d.alpha, d.beta, d.relu, d.leaky_slope = bd.data_ptr(), 1.0, 0.0, 2, slope
+        d.out_f32 = of.data_ptr()
+        d.a_mode, d.nacc, d.pair = 0, 2, 1
+        plan = C.c_void_p()
+        L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))
+        L.check(lib.sr_conv_plan_run(plan, L.stream_ptr()))
+        torch.cuda.synchronize()
+        lib.sr_conv_plan_destroy(plan)
+        lin = oracle_conv([x], [w], bias)
+        want = np.where(lin >= 0, lin, slope * lin)
+        got = of.cpu().numpy()
+        # the epilogue stages the accumulator as bf16 before bias/activation: half-ulp = 2^-9 relative
+        assert np.abs(got - want).max() <= 2.0 ** -8 * np.abs(lin).max() + 1e-6
+        neg = lin < -0.05
+        assert neg.any() and np.all(got[neg] < 0) and np.allclose(got[neg] / lin[neg], slope, rtol=0.1)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 8), (2, 5, 7, 128), (1, 3, 4, 16)])
+def test_bilinear2_matches_tf1_legacy(lib, shape):
+    from oracle import other_models as om
+    from sr100 import _lib as L
+    rng = np.random.default_rng(shape[2])
+    x = rng.normal(0, 1, size=shape).astype(np.float32)
+    NB, H, W, Cc = shape
+    xd = torch.from_numpy(x).cuda()
+    of = torch.empty(NB, 2 * H, 2 * W, Cc, device="cuda")
+    ob = torch.empty(NB, 2 * H, 2 * W, Cc, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.sr_bilinear2_fwd(L.ptr(xd), 0, NB, H, W, Cc, L.ptr(ob), L.ptr(of), L.stream_ptr()))
+    want = om.bilinear_tf1(torch.from_numpy(x).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).numpy()
+    assert np.array_equal(of.cpu().numpy(), want)                 # t in {0, 0.5}: same three fp32 lerps
+    assert np.array_equal(ob.float().cpu().numpy(), bf16_round(want))
+
+
+def _check(arch, specs_fn, fwd, shape, gain, tol=2e-2):
+    from oracle import other_models as om
+    from sr100.planenet import PlaneNet
+    specs = specs_fn()
+    weights = om.init_weights(specs, seed=7, bias_scale=0.02, gain=gain)
+    tail = specs[-1][0]
+    w, b = weights[tail]
+    weights[tail] = (w * 3.0, b + 0.3)                            # lift the ReLU'd output off zero
+    rng = np.random.default_rng(5)
+    x = rng.random(shape).astype(np.float32)
+    eng = PlaneNet(arch, weights)
+    got = eng.forward_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = fwd(weights, x)
+    s = eng.scale
+    assert got.shape == want.shape == (shape[0], s * shape[1], s * shape[2], 3)
+    assert want.max() > 0.2 and (want > 0).mean() > 0.3           # a live output, not a dead ReLU
+    err = np.abs(got - want).max()
+    assert err <= tol, "max-abs error %.4g" % err
+    # replay (CUDA graph after the first eager run) gives the same bits
+    again = eng.forward_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    third = eng.forward_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, again) and np.array_equal(got, third)
+    return eng, weights
+
+
+def test_difvdsr4_forward_matches_oracle():
+    from oracle import other_models as om
+    _check("difvdsr4", om.difvdsr4_specs, om.forward_difvdsr4, (2, 10, 12, 3), gain=1.0)
+
+
+def test_difvdsr4_single_image_odd_shape():
+    from oracle import other_models as om
+    _check("difvdsr4", om.difvdsr4_specs, om.forward_difvdsr4, (1, 7, 5, 3), gain=1.0)
+
+
+def test_difvdsr_forward_matches_oracle():
+    from oracle import other_models as om
+    _check("difvdsr", om.difvdsr_specs, om.forward_difvdsr, (2, 14, 18, 3), gain=1.0)
+
+
+def test_model_constructors_predict_weights_and_tiling(tmp_path, monkeypatch):
+    """models.Difvdsr4 / models.Difvdsr behind the reference API: create_model, predict, get/set_weights, .h5 round
+    trip (Difvdsr always loads its file, models.py:1322), upscaleStepPatch through the generic tiler."""
+    import models
+    from oracle import other_models as om
+    from oracle import tiling as ot
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    # Difvdsr4
+    m4 = models.Difvdsr4(1)
+    model = m4.create_model(8, 8)
+    assert model.output_shape == (None, 32, 32, 3) and len(model.layers) == 66
+    assert model.count_params() == sum(k * k * ci * co + co for _, k, ci, co in om.difvdsr4_specs())
+    w4 = om.init_weights(om.difvdsr4_specs(), seed=11, bias_scale=0.02)
+    t = om.difvdsr4_specs()[-1][0]
+    w4[t] = (w4[t][0] * 3.0, w4[t][1] + 0.3)
+    model.engine.set_weights_dict(w4)
+    x = rng.random((1, 8, 8, 3)).astype(np.float32)
+    y = model.predict(x)
+    assert np.abs(y - om.forward_difvdsr4(w4, x)).max() <= 2e-2
+    wfile = str(tmp_path / "w4.h5")
+    model.save_weights(wfile)
+    m4b = models.Difvdsr4(1)
+    monkeypatch.setenv("SR100_WEIGHTS", wfile)
+    model_b = m4b.create_model(8, 8, load_weights=True)
+    assert np.array_equal(model_b.predict(x), y)
+    with pytest.raises(NotImplementedError):
+        model.train_on_batch(x, np.zeros((1, 32, 32, 3), np.float32))
+    # tiled CLI path (upscaleStepPatch) through the generic gather / predict / stitch, against the oracle's tiling
+    img = rng.integers(0, 256, size=(40, 50, 3)).astype(np.uint8)
+    path = str(tmp_path / "im.png")
+    Image.fromarray(img).save(path)
+    canvas = m4b.upscaleStepPatch(path, return_image=True, patch_size=32, scalemulti=4, verbose=False)
+    _, want = ot.upscale_step_patch(img, lambda p: om.forward_difvdsr4(w4, p), 32, 64, 4)
+    assert canvas.shape[0] >= 160 and canvas.shape[1] >= 200
+    d = np.abs(canvas[:160, :200].astype(int) - want.astype(int))
+    assert d.max() <= 6 and (d > 1).mean() < 0.02                  # uint8 after x255 truncation of a 2e-2 float path
+    # Difvdsr: cannot be built without its weight file, exactly like the reference
+    monkeypatch.setenv("SR100_WEIGHTS", str(tmp_path / "missing.h5"))
+    with pytest.raises(OSError):
+        models.Difvdsr(1).create_model(8, 8)
+    from sr100 import h5lite
+    wd = om.init_weights(om.difvdsr_specs(), seed=12, bias_scale=0.02)
+    t = om.difvdsr_specs()[-1][0]
+    wd[t] = (wd[t][0] * 3.0, wd[t][1] + 0.3)
+    dfile = str(tmp_path / "wd.h5")
+    h5lite.save_keras_weights(dfile, wd, order=[s[0] for s in om.difvdsr_specs()])
+    monkeypatch.setenv("SR100_WEIGHTS", dfile)
+    md = models.Difvdsr(1)
+    modeld = md.create_model(12, 10)
+    assert modeld.output_shape == (None, 10, 12, 3) and len(modeld.layers) == 130   # width-major, models.py:121
+    xd = rng.random((2, 10, 12, 3)).astype(np.float32)
+    assert np.abs(modeld.predict(xd) - om.forward_difvdsr(wd, xd)).max() <= 2e-2

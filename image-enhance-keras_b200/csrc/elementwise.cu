@@ -257,6 +257,22 @@ __global__ void patch_gather_vec4_kernel(const void* __restrict__ src, int h, in
   }
 }
 
+// ------------------------------------------------------------------ minibatch assembly from an HBM-resident dataset
+// Reference: img_utils.image_generator (img_utils.py:341-372): batch[i] = imread(file[index[i]]).astype('float32')/255.
+// The decoded uint8 images live in HBM ([N][item_bytes]); one launch gathers the rows named by `index` and
+// normalises them.  Four bytes per thread: one 4-byte load, one 16-byte store.
+__global__ void batch_gather_u8_kernel(const uint8_t* __restrict__ data, size_t item_bytes,
+                                       const long long* __restrict__ index, int n, float divisor,
+                                       float* __restrict__ out) {
+  const size_t q = item_bytes >> 2;  // uchar4 groups per item
+  const size_t total = (size_t)n * q;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / q, e = i - b * q;
+    const uchar4 v = reinterpret_cast<const uchar4*>(data + (size_t)index[b] * item_bytes)[e];
+    reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn((float)v.x, divisor), __fdiv_rn((float)v.y, divisor),
+                                                    __fdiv_rn((float)v.z, divisor), __fdiv_rn((float)v.w, divisor));
+  }
+}
 // Reference: img_utils.rebuild_from_patches_Step (img_utils.py:692-724).  Per axis the owner of
 // output coordinate Q is the LAST patch whose cropped span [S*i + c_i, S*i + P - c_i) contains Q
 // (c_0 = 0, c_i = 8), because later patches overwrite earlier ones.
@@ -655,6 +671,21 @@ extern "C" int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h
   patch_gather_kernel<true><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
       img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, out_f32);
   return check_launch("patch_gather_kernel<u8>");
+}
+
+extern "C" int sr_batch_gather_u8(const uint8_t* data, size_t item_bytes, size_t n_items, const long long* index,
+                                  int n, float divisor, float* out_f32, void* stream) {
+  if (!data || !index || !out_f32) return set_error(SR_ERR_INVALID, "sr_batch_gather_u8: null pointer");
+  if (n < 0 || item_bytes == 0 || divisor == 0.f) return set_error(SR_ERR_INVALID, "sr_batch_gather_u8: bad size");
+  if (n == 0) return SR_OK;
+  (void)n_items;  // the index values are device data: the caller guarantees 0 <= index[i] < n_items
+  if ((item_bytes & 3) != 0)
+    return set_error(SR_ERR_UNSUPPORTED, "sr_batch_gather_u8: item_bytes must be a multiple of 4");
+  if ((reinterpret_cast<uintptr_t>(data) & 3) != 0 || (reinterpret_cast<uintptr_t>(out_f32) & 15) != 0)
+    return set_error(SR_ERR_INVALID, "sr_batch_gather_u8: data must be 4-byte and out 16-byte aligned");
+  batch_gather_u8_kernel<<<grid_for((size_t)n * (item_bytes >> 2), kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      data, item_bytes, index, n, divisor, out_f32);
+  return check_launch("batch_gather_u8_kernel");
 }
 
 extern "C" int sr_patch_gather_f32(const float* canvas, int canvas_h, int canvas_w, int ph, int pw,

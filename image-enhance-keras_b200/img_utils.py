@@ -109,9 +109,19 @@ def _index_generator(N, batch_size=32, shuffle=True, seed=None):
 
 
 def image_generator(directory, scale_factor=2, target_shape=None, channels=3, small_train_images=False,
-                    shuffle=True, batch_size=32, seed=None):
+                    shuffle=True, batch_size=32, seed=None, device_resident=False):
     """img_utils.py:290-372: yields (batch_x, batch_y) float NHWC in [0,1] read from <directory>/X and
-    <directory>/y (same file names)."""
+    <directory>/y (same file names).
+
+    device_resident=True (not in the reference): the files are decoded once into HBM and every batch is one gather
+    launch (sr100.dataset.DeviceDataset); the batches are device float32 tensors with the same values, in the same
+    order, as the host arrays below."""
+    if device_resident:
+        from sr100.dataset import DeviceDataset
+        ds = DeviceDataset(directory)
+        print("Found %d images." % len(ds))
+        for batch in ds.generator(batch_size, shuffle, seed):
+            yield batch
     file_names = [f for f in _listdir_images(directory + "X/")]
     X_filenames = [os.path.join(directory, "X", f) for f in file_names]
     y_filenames = [os.path.join(directory, "y", f) for f in file_names]

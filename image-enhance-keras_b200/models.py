@@ -169,14 +169,23 @@ class BaseSuperResolutionModel(object):
         if save_history:
             callback_list.append(HistoryCheckpoint(history_fn))
         print("Training model : %s" % (self.__class__.__name__))
-        trainset = img_utils.image_generator(train_path, scale_factor=self.scale_factor,
-                                             small_train_images=self.type_true_upscaling, batch_size=batch_size)
-        self.model.fit_generator(trainset, steps_per_epoch=samples_per_epoch, epochs=nb_epochs,
-                                 callbacks=callback_list,
-                                 validation_data=img_utils.image_generator(validation_path,
-                                                                           scale_factor=self.scale_factor,
-                                                                           small_train_images=self.type_true_upscaling,
-                                                                           batch_size=batch_size),
+        # SR100_DEVICE_DATASET=1 (default): decode the two directories once into HBM and assemble every batch on the
+        # device (sr100.dataset); datasets that do not qualify (ragged image shapes, too large) use the reference's
+        # per-batch host decode.  Either way the batches hold the same values in the same order.
+        def gen(directory):
+            kw = dict(scale_factor=self.scale_factor, small_train_images=self.type_true_upscaling,
+                      batch_size=batch_size)
+            if os.environ.get("SR100_DEVICE_DATASET", "1") != "0":
+                try:
+                    from sr100.dataset import DeviceDataset
+                    ds = DeviceDataset(directory)
+                    print("Found %d images." % len(ds))
+                    return ds.generator(batch_size, True, None)
+                except ValueError as e:
+                    print("device-resident dataset not used (%s); decoding per batch on the host" % e)
+            return img_utils.image_generator(directory, **kw)
+        self.model.fit_generator(gen(train_path), steps_per_epoch=samples_per_epoch, epochs=nb_epochs,
+                                 callbacks=callback_list, validation_data=gen(validation_path),
                                  validation_steps=val_count)
         return self.model
 

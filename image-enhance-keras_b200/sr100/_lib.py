@@ -111,6 +111,7 @@ SIGNATURES = {
     "sr_patch_count": (_i, [_i, _i, _i]),
     "sr_canvas_size": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "sr_patch_gather_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "sr_batch_gather_u8": (_i, [_vp, _sz, _sz, _vp, _i, _f, _vp, _vp]),
     "sr_patch_gather_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_patch_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "sr_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

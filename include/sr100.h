@@ -178,6 +178,13 @@ int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int ph, int pw, 
                     int canvas_h, int canvas_w, float mul, float* out_f32, uint8_t* out_u8,
                     void* stream);
 
+/* Minibatch assembly from an HBM-resident dataset.  Replaces the per-batch file decode of
+ * img_utils.image_generator (img_utils.py:341-372): data = N decoded uint8 images of item_bytes bytes each
+ * (item_bytes % 4 == 0), index = device int64[n] chosen by img_utils._index_generator;
+ * out[i] = float32(data[index[i]]) / divisor  (255 -> the reference's astype('float32') / 255.). */
+int sr_batch_gather_u8(const uint8_t* data, size_t item_bytes, size_t n_items, const long long* index,
+                       int n, float divisor, float* out_f32, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Sub-pixel shuffles.  order 0: keras_subpixel.Subpixel._phase_shift (keras_subpixel.py:64-84)
  * and advanced.depth_to_scale_tf (advanced.py:104-129): ch = c*r*r + (X%r)*r + (Y%r);

@@ -3,6 +3,7 @@ torch-CPU autograd on the restated graph + hand-written Keras Adam).  Operands a
 gradients are compared in relative L2 / cosine per layer; single kernels are compared with bf16-rounded inputs and
 are exact up to fp32 summation order."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -341,3 +342,34 @@ def test_wgrad_geometry_sweep(lib, seed):
         got = _wgrad_gpu(lib, x, g, k)
         want = _wgrad_oracle(x, g, k)
         assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (k, NB, H, W)
+
+
+def test_device_resident_dataset_matches_host_generator(tmp_path):
+    """sr100.dataset.DeviceDataset (HBM-resident uint8 set + sr_batch_gather_u8) yields exactly the batches of the
+    host image_generator (img_utils.py:290-372): same order under the same seed, same float32 values, short last batch."""
+    import img_utils
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    d = str(tmp_path / "train") + "/"
+    os.makedirs(d + "X")
+    os.makedirs(d + "y")
+    for i in range(7):
+        Image.fromarray(rng.integers(0, 256, size=(8, 12, 3), dtype=np.uint8)).save(d + "X/%02d.png" % i)
+        Image.fromarray(rng.integers(0, 256, size=(32, 48, 3), dtype=np.uint8)).save(d + "y/%02d.png" % i)
+    host = img_utils.image_generator(d, scale_factor=1, shuffle=True, batch_size=3, seed=9)
+    dev = img_utils.image_generator(d, scale_factor=1, shuffle=True, batch_size=3, seed=9, device_resident=True)
+    sizes = []
+    for _ in range(7):
+        hx, hy = next(host)
+        dx, dy = next(dev)
+        assert dx.is_cuda and dx.dtype == torch.float32
+        assert np.array_equal(dx.cpu().numpy(), hx.astype(np.float32))
+        assert np.array_equal(dy.cpu().numpy(), hy.astype(np.float32))
+        sizes.append(dx.shape[0])
+    assert sizes == [3, 3, 1, 3, 3, 1, 3]
+    # ragged shapes do not qualify (the reference's fixed-shape batch array would fail on them too)
+    Image.fromarray(rng.integers(0, 256, size=(9, 12, 3), dtype=np.uint8)).save(d + "X/99.png")
+    Image.fromarray(rng.integers(0, 256, size=(36, 48, 3), dtype=np.uint8)).save(d + "y/99.png")
+    from sr100.dataset import DeviceDataset
+    with pytest.raises(ValueError):
+        DeviceDataset(d)

@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--detail", action="store_true", help="per-launch CUDA-event breakdown of one step")
+    ap.add_argument("--data", choices=["none", "device", "host"], default="none",
+                    help="feed every step from a PNG dataset: 'device' = HBM-resident set (sr100.dataset), 'host' = "
+                         "the reference's per-batch decode (img_utils.image_generator); 'none' = fixed tensors")
+    ap.add_argument("--dataset-size", type=int, default=1024)
     a = ap.parse_args()
     import torch
     from sr100 import dist as D
@@ -38,8 +42,34 @@ def main():
     gen = torch.Generator(device="cuda").manual_seed(7 + rank)
     g.x_in.copy_(torch.rand(g.x_in.shape, device="cuda", generator=gen))
     g.y_true.copy_(torch.rand(g.y_true.shape, device="cuda", generator=gen))
-    for _ in range(a.warmup):
+    feed = None
+    if a.data != "none":
+        import tempfile
+        import time
+        import numpy as np
+        from PIL import Image
+        import img_utils
+        d = tempfile.mkdtemp(prefix="sr100_ds_") + "/"
+        os.makedirs(d + "X")
+        os.makedirs(d + "y")
+        rng = np.random.default_rng(rank)
+        for i in range(a.dataset_size):
+            Image.fromarray(rng.integers(0, 256, size=(a.size, a.size, 3), dtype=np.uint8)).save(d + "X/%05d.png" % i)
+            Image.fromarray(rng.integers(0, 256, size=(4 * a.size, 4 * a.size, 3), dtype=np.uint8)).save(d + "y/%05d.png" % i)
+        t0 = time.time()
+        feed = img_utils.image_generator(d, scale_factor=1, batch_size=nb, shuffle=True,
+                                         device_resident=(a.data == "device"))
+        first = next(feed)
+        load_s = time.time() - t0
+
+    def step():
+        if feed is not None:
+            x, y = next(feed)
+            tr._load(g, x, y)
         tr.step_device(g)
+
+    for _ in range(a.warmup):
+        step()
     D.barrier()
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -47,6 +77,9 @@ def main():
     e0.record()
     for _ in range(a.steps):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if feed is not None:
+            x, y = next(feed)
+            tr._load(g, x, y)
         s0.record()
         tr.forward_backward_device(g)
         s1.record()
@@ -57,6 +90,14 @@ def main():
     torch.cuda.synchronize()
     D.barrier()
     ms = D.max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    if feed is not None:      # host decode does not show on the device clock: wall time of the same loop
+        import time
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(a.steps):
+            step()
+        torch.cuda.synchronize()
+        ms = D.max_over_ranks((time.time() - t0) * 1e3 / a.steps)
     fb_ms = t_fb / a.steps
     loss = float(g.loss_sum.item()) / g.n_local
     rec = dict(metric="train_step", n_gpus=world, global_batch=a.batch, per_gpu_batch=nb, lr_size=a.size,
@@ -65,7 +106,10 @@ def main():
                algorithmic_tflop_per_step_per_gpu=round(tr.step_flops(g) / 1e12, 3),
                tflops_per_gpu=round(tr.step_flops(g) / (ms * 1e-3) / 1e12, 1),
                fwd_tflop=round(g.fwd_flops / 1e12, 3), bwd_tflop=round(g.bwd_flops / 1e12, 3), loss=loss,
-               mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+               mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), data=a.data)
+    if feed is not None:
+        rec["dataset_pairs"] = a.dataset_size
+        rec["first_batch_s"] = round(load_s, 2)
     if a.detail and rank == 0:
         st = __import__("sr100._lib", fromlist=["x"]).stream_ptr()
         parts = {}

@@ -141,3 +141,153 @@ def image_generator(directory, scale_factor=2, target_shape=None, channels=3, sm
                 batch_y = np.zeros((current_batch_size,) + img.shape)
             batch_y[i] = img
         yield (batch_x, batch_y)
+
+
+# ------------------------------------------------------------------ alternative-tiler helpers (img_utils.py:159-287, 442-599)
+# Used by BaseSuperResolutionModel.upscalePatch / upscale(mode='patch').  The reference materialises every dense patch
+# in host memory and loops over them in Python; the models' own paths (sr100.alt_tilers) never do.  These mirrors keep
+# the function API: the extraction helpers are strided numpy views / index glue like the reference's, the two
+# averaging reconstructions run on the device (sr_patch_average_*: float64 sums in the reference's patch order).
+def imresize(arr, size, interp='bilinear', mode=None):
+    """scipy.misc.imresize (scipy < 1.3; `from scipy.misc import imresize`, img_utils.py:5): toimage (bytescale for
+    non-uint8 input) -> PIL resize -> uint8 array.  size: int (percent), float (fraction) or (rows, cols)."""
+    from PIL import Image
+    arr = np.asarray(arr)
+    if arr.dtype != np.uint8:                     # scipy.misc.bytescale
+        cmin, cmax = arr.min(), arr.max()
+        cscale = cmax - cmin
+        if cscale < 0:
+            raise ValueError("`cmax` should be larger than `cmin`.")
+        elif cscale == 0:
+            cscale = 1
+        arr = (((arr - cmin) * (255.0 / cscale)).clip(0, 255) + 0.5).astype(np.uint8)
+    im = Image.fromarray(arr, mode=mode) if mode is not None else Image.fromarray(arr)
+    if isinstance(size, (int, np.integer)):
+        size = tuple((np.array(im.size) * (size / 100.0)).astype(int))
+    elif isinstance(size, (float, np.floating)):
+        size = tuple((np.array(im.size) * size).astype(int))
+    else:
+        size = (size[1], size[0])
+    func = {'nearest': 0, 'lanczos': 1, 'bilinear': 2, 'bicubic': 3, 'cubic': 3}
+    return np.asarray(im.resize(size, resample=func[interp]))
+
+
+def extract_patches_2dv2(image, patch_size, max_patches=None, random_state=None):
+    """img_utils.py:561-599: sklearn extract_patches_2d of image.astype('uint8')."""
+    import imgpatch
+    return imgpatch.extract_patches_2d(np.asarray(image).astype('uint8'), patch_size, max_patches, random_state)
+
+
+def make_patches(x, scale, patch_size, upscale=True, verbose=1):
+    """img_utils.py:159-172: every dense patch (sklearn extract_patches_2d); `scale` / `upscale` are ignored there."""
+    import imgpatch
+    return imgpatch.extract_patches_2d(np.asarray(x), (patch_size, patch_size))
+
+
+def make_patchesOrig(x, scale, patch_size, upscale=False, verbose=1):
+    """img_utils.py:174-180."""
+    height, width = x.shape[:2]
+    if upscale:
+        x = imresize(x, (height * scale, width * scale))
+    return extract_patches_2dv2(x, (patch_size, patch_size))
+
+
+def make_patchesStep(x, scale, patch_size, upscale=False, extraction_step=24, verbose=1):
+    """img_utils.py:182-187."""
+    height, width = x.shape[:2]
+    if upscale:
+        x = imresize(x, (height * scale, width * scale))
+    return extract_patches_Step(x, (patch_size, patch_size), extraction_step)
+
+
+def extract_patches_2dlocal(image, patches, patch_size, step=None):
+    """img_utils.py:513-556: the dense patches whose (i, j) are multiples of `step`, as float64."""
+    i_h, i_w = image.shape[:2]
+    p_h, p_w = patch_size
+    if p_h > i_h:
+        raise ValueError("Height of the patch should be less than the height"
+                         " of the image.")
+    if p_w > i_w:
+        raise ValueError("Width of the patch should be less than the width"
+                         " of the image.")
+    p_h, p_w = patches.shape[1:3]
+    n_h, n_w = i_h - p_h + 1, i_w - p_w + 1
+    dense = np.asarray(patches)[:n_h * n_w].reshape((n_h, n_w) + patches.shape[1:])
+    sel = dense[::step, ::step]
+    out = np.zeros((sel.shape[0] * sel.shape[1], p_h, p_w, 3))
+    out[...] = sel.reshape((-1,) + patches.shape[1:])
+    return out
+
+
+def _as_f32_patches(p):
+    p = np.asarray(p)
+    if p.ndim != 4 or p.shape[3] != 3:
+        raise ValueError("expected patches of shape (n, p_h, p_w, 3), got %s" % (p.shape,))
+    if p.shape[1] != p.shape[2]:
+        raise ValueError("the device averaging kernel handles square patches, got %s" % (p.shape,))
+    p32 = np.ascontiguousarray(p, dtype=np.float32)
+    if p.dtype != np.float32 and not np.array_equal(p32, p):
+        raise ValueError("patch values must be float32-representable (the network's outputs are)")
+    return p32
+
+
+def _average(patch_values, image_size, n_hw, step, pad, sklearn_count):
+    import torch
+    from sr100 import alt_tilers
+    i_h, i_w = image_size[:2]
+    n_h, n_w = n_hw
+    P = patch_values.shape[1]
+    cnt_h, cnt_w = (n_h - 1) // step + 1, (n_w - 1) // step + 1
+    if patch_values.shape[0] < cnt_h * cnt_w:
+        raise ValueError("need %d patches, got %d" % (cnt_h * cnt_w, patch_values.shape[0]))
+    pd = torch.from_numpy(patch_values[:cnt_h * cnt_w]).cuda()
+    edges = ((n_h - 1) // step if (n_h - 1) % step == 0 else -1, (n_w - 1) // step if (n_w - 1) % step == 0 else -1)
+    _, f64 = alt_tilers.patch_average([(0, cnt_h, pd)], P, step, pad, cnt_h, cnt_w, (i_h, i_w), mul=1.0, want_f64=True,
+                                      sklearn_count=sklearn_count, edges=edges)
+    return f64.cpu().numpy()
+
+
+def reconstruct_from_patches_2dlocal(patches, patchcnn, image_size, step=16):
+    """img_utils.py:442-511: `patches` (the dense set) only gives the patch shape and the (i, j) enumeration; the
+    values averaged are the step-selected `patchcnn`; interior patches contribute their [4, p-4) window; division by
+    the count map (NaN where nothing contributes, as in the reference)."""
+    i_h, i_w = image_size[:2]
+    p_h, p_w = patches.shape[1:3]
+    return _average(_as_f32_patches(patchcnn), image_size, (i_h - p_h + 1, i_w - p_w + 1), int(step), 4, False)
+
+
+def reconstruct_from_patches_2dloc(patches, image_size):
+    """img_utils.py:195-238: sklearn's averaging reconstruction (the code after its `return` is dead)."""
+    i_h, i_w = image_size[:2]
+    p = _as_f32_patches(patches)
+    return _average(p, image_size, (i_h - p.shape[1] + 1, i_w - p.shape[2] + 1), 1, 0, True)
+
+
+def combine_patches(in_patches, out_shape, scale):
+    """img_utils.py:189-193: sklearn.feature_extraction.image.reconstruct_from_patches_2d(in_patches, out_shape)."""
+    return reconstruct_from_patches_2dloc(in_patches, out_shape)
+
+
+def subimage_build_patch_global(img, stride, patch_size, nb_hr_images):
+    """img_utils.py:240-265 (the reference mixes the axes: y runs over range(width) but indexes rows)."""
+    heightini, widthini = img.shape[:2]
+    pos = [(y, x) for y in range(0, widthini, stride) for x in range(0, heightini, stride)
+           if (x + patch_size) < widthini and (y + patch_size) < heightini]
+    subimages = np.empty((len(pos), patch_size, patch_size, 3))
+    for j, (y, x) in enumerate(pos):
+        subimages[j] = img[y:y + patch_size, x:x + patch_size, :]
+    return subimages
+
+
+def subimage_combine_patches_global(imgtrue, patches, stride, patch_size, scale):
+    """img_utils.py:268-287: overwrite the bicubic-upscaled image with the patches, same position rule."""
+    heighttrue, widthtrue = imgtrue.shape[:2]
+    img = imresize(imgtrue, (heighttrue * scale, widthtrue * scale), interp='bicubic').copy()
+    heightini, widthini = img.shape[:2]
+    j = 0
+    for y in range(0, widthini, stride):
+        for x in range(0, heightini, stride):
+            if (x + patch_size) < widthini and (y + patch_size) < heightini:
+                img[y:y + patch_size, x:x + patch_size, :] = patches[j, :, :, :]
+                j += 1
+    return img

@@ -282,9 +282,58 @@ class BaseSuperResolutionModel(object):
         torch.cuda.current_stream().synchronize()
         return [t.numpy() for t in pinned]
 
-    def upscalePatch(self, *a, **k):
-        raise NotImplementedError("upscalePatch (models.py:419-604) needs PIL-exact bicubic imresize; "
-                                  "SURVEY.md 8(f) 'next' row")
+    def upscalePatch(self, img_path, save_intermediate=False, return_image=False, suffix="scaled",
+                     patch_size=32, scalemulti=4, mode="patch", verbose=True):
+        """models.py:419-604: "enhance at the same size".  The image is zero-padded to multiples of 4 (both sides
+        bumped when either is off, :465-470), every 4th `patch_size` patch is shrunk x4 with
+        scipy.misc.imresize(..., 'bicubic') (bytescale + Pillow bicubic, :487-490), run through the network (x4,
+        back to patch_size) and the outputs are averaged by img_utils.reconstruct_from_patches_2dlocal (:556);
+        clip -> uint8, crop to the original size (:575-577).  All of it on the device (sr100.alt_tilers)."""
+        import torch
+        from PIL import Image
+        from sr100 import alt_tilers, ops
+        path = os.path.splitext(img_path)
+        filename = path[0] + "_" + suffix + "(%dx)" % (self.scale_factor) + path[1]
+        true_img = np.asarray(Image.open(img_path).convert("RGB"))
+        orig_height, orig_width = true_img.shape[0], true_img.shape[1]
+        init_height, init_width = orig_height, orig_width
+        if verbose:
+            print("Old Size : ", true_img.shape)
+            print("New Size : (%d, %d, 3)" % (init_height, init_width))
+        if mode != 'patch':
+            # the reference reads img_height before assigning it on this branch (models.py:501)
+            raise UnboundLocalError("local variable 'img_height' referenced before assignment")
+        if int(scalemulti) != 4:
+            raise ValueError("upscalePatch shrinks every patch by scalemulti and the network enlarges it x4: "
+                             "scalemulti must be 4")
+        step_patch = 4
+        if init_width % step_patch != 0 or init_height % step_patch != 0:
+            new_w = int((init_width / step_patch) + 1) * step_patch
+            new_h = int((init_height / step_patch) + 1) * step_patch
+            new_img = np.zeros((new_h, new_w, 3), dtype=np.uint8)
+            new_img[0:init_height, 0:init_width] = true_img
+            true_img = new_img
+            init_height, init_width = new_h, new_w
+        if patch_size % 4 != 0:
+            raise ValueError("patch_size must be a multiple of 4 (each patch is shrunk to patch_size/4)")
+        q = patch_size // 4
+        img_dev = ops.to_device(true_img, torch.uint8)
+        if verbose:
+            cnt = ((init_height - patch_size) // 4 + 1) * ((init_width - patch_size) // 4 + 1)
+            print("Number of patches = %d, Patch Shape = (%d, %d)" % (cnt, q, q))
+        if save_intermediate:                       # imsave(fn, images[0]) (:515): the first shrunk patch
+            first = alt_tilers.patch_down4(img_dev, patch_size, 4, True, 0, 1)[0]
+            Image.fromarray((first * 255.0).round().to(torch.uint8).cpu().numpy()).save(path[0] + "_intermediate_" + path[1])
+        model = self.create_model(q, q, load_weights=True)
+        if verbose:
+            print("Model loaded.")
+        result = alt_tilers.enhance_image_device(model.engine, img_dev, patch_size, 4, stretch=True, pad=4)
+        result = result[0:orig_height, 0:orig_width].contiguous().cpu().numpy()
+        if return_image:
+            return result
+        if verbose:
+            print("Saving image.")
+        Image.fromarray(result).save(filename)
 
     def upscale(self, img_path, save_intermediate=False, return_image=False, suffix="scaled",
                 patch_size=32, mode="patch", verbose=True):
@@ -292,7 +341,7 @@ class BaseSuperResolutionModel(object):
         bicubic-resized to its own size (`imresize(true_img, (img_width, img_height))` with
         __match_autoencoder_size returning the input size for this model, :855-889 -- a PIL no-op), written as the
         `_A<suffix>` side file (:755), run through model.predict, x255, clipped to uint8 and saved.
-        mode='patch' (dense sklearn patches of the x4-bicubic image, :645-680) is a SURVEY 8(f) 'next' row."""
+        mode='patch': dense sklearn patches of the x4-bicubic image (:645-680), see the branch below."""
         from PIL import Image
         path = os.path.splitext(img_path)
         filename = path[0] + "_" + suffix + "(%dx)" % (self.scale_factor) + path[1]
@@ -306,9 +355,32 @@ class BaseSuperResolutionModel(object):
             mode = 'fast'
             print("Patch mode does not work with True Upscaling models yet. Defaulting to mode='fast'")
         if mode == 'patch':
-            raise NotImplementedError("upscale(mode='patch') (models.py:645-680: dense make_patches of the bicubic x4 "
-                                      "image + sklearn averaging) is a SURVEY.md 8(f) 'next' row; use mode='fast' or "
-                                      "upscaleStepPatch")
+            # :645-680, 758-790: bicubic x4 of the whole image (PIL, as scipy.misc.imresize does), the `_A<suffix>` side
+            # file, then every dense patch_size patch shrunk x4 -> network -> sklearn averaging (combine_patches)
+            import torch
+            from sr100 import alt_tilers, ops
+            if patch_size % 4 != 0:
+                raise ValueError("patch_size must be a multiple of 4 (each patch is shrunk to patch_size/4)")
+            big = np.asarray(Image.fromarray(true_img).resize((cols * 4, rows * 4), Image.BICUBIC))
+            Image.fromarray(big).save(filenameM)                                        # :657
+            if verbose:
+                print("Number of patches = %d, Patch Shape = (%d, %d)"
+                      % ((big.shape[0] - patch_size + 1) * (big.shape[1] - patch_size + 1), patch_size // 4, patch_size // 4))
+            big_dev = ops.to_device(big, torch.uint8)
+            if save_intermediate:
+                first = alt_tilers.patch_down4(big_dev, patch_size, 1, False, 0, 1)[0]
+                Image.fromarray((first * 255.0).round().to(torch.uint8).cpu().numpy()).save(path[0] + "_intermediate_" + path[1])
+            model = self.create_model(patch_size // 4, patch_size // 4, load_weights=True)
+            if verbose:
+                print("Model loaded.")
+            result = alt_tilers.enhance_image_device(model.engine, big_dev, patch_size, 1, stretch=False, pad=0)
+            result = result.cpu().numpy()
+            if return_image:
+                return result
+            if verbose:
+                print("Saving image.")
+            Image.fromarray(result).save(filename)
+            return
         sf = int(self.scale_factor)
         img_height, img_width = cols * sf, rows * sf            # __match_autoencoder_size, not AE / not true upscaling
         if (img_width, img_height) == (rows, cols):

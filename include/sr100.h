@@ -186,6 +186,35 @@ int sr_batch_gather_u8(const uint8_t* data, size_t item_bytes, size_t n_items, c
                        int n, float divisor, float* out_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Alternative tilers: BaseSuperResolutionModel.upscalePatch (models.py:419-604) and
+ * upscale(mode='patch') (models.py:645-680, 758-790).
+ * ------------------------------------------------------------------------------------------ */
+/* Patches n in [n0, n1) of the grid n = a*cnt_w + b at (a*step, b*step) of a uint8 image [H,W,3], each p x p
+ * (p % 4 == 0), shrunk x4 like scipy.misc.imresize(patch, (p/4, p/4), interp='bicubic') (models.py:490, 672):
+ * stretch != 0 applies scipy.misc.bytescale first (the reference's float64 patches of upscalePatch are
+ * contrast-stretched to [0,255] per patch; uint8 patches of upscale() are not), then Pillow's 8-bit bicubic
+ * (horizontal pass, uint8 intermediate, vertical pass) with the fixed-point coefficient table (bounds
+ * int32[p/4][2] = (first tap, tap count), kk int32[p/4][ksize]) the host computes as Resample.c does.
+ * out[n - n0] = float32 [p/4, p/4, 3] = value / divisor. */
+int sr_patch_down4_u8(const uint8_t* img, int H, int W, int p, int step, int cnt_h, int cnt_w,
+                      long long n0, long long n1, int stretch, const int* bounds, const int* kk, int ksize,
+                      float divisor, float* out_f32, void* stream);
+/* Averaging stitch of img_utils.reconstruct_from_patches_2dlocal (img_utils.py:442-511; step 4, pad 4: interior
+ * patches contribute rows/columns [pad, P-pad) only; a patch is interior when its grid indices are > 0 and differ
+ * from edge_a / edge_b, the indices sitting on the last dense position, -1 if the grid does not reach it) and of sklearn reconstruct_from_patches_2d behind
+ * img_utils.combine_patches (img_utils.py:189-193; step 1, pad 0).  patches: float32 [(a1-a0)*cnt_w, P, P, 3] =
+ * grid rows a0..a1-1; sum (float64 [out_h,out_w,3]) and count (int32 [out_h,out_w]) accumulate across calls made
+ * in increasing a0 (zero them first): the float64 additions then happen in the reference's (i, j) order.
+ * finalize: img = sum / count - or, closed_P > 0, sum / (min(Y+1,P,H-Y) * min(X+1,P,W-X)), sklearn's closed-form
+ * overlap count (it exceeds the true count on images smaller than 2P-1; the reference divides by it regardless);
+ * out_u8 = np.clip(img, 0, 255).astype('uint8') (models.py:575, 791). */
+int sr_patch_average_accumulate(const float* patches, int P, int step, int pad, int cnt_h, int cnt_w,
+                                int a0, int a1, int edge_a, int edge_b, float mul, int out_h, int out_w,
+                                double* sum, int* count, void* stream);
+int sr_patch_average_finalize(const double* sum, const int* count, int out_h, int out_w, int closed_P,
+                              double* out_f64, uint8_t* out_u8, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Sub-pixel shuffles.  order 0: keras_subpixel.Subpixel._phase_shift (keras_subpixel.py:64-84)
  * and advanced.depth_to_scale_tf (advanced.py:104-129): ch = c*r*r + (X%r)*r + (Y%r);
  * order 1: advanced.depth_to_scale_th (advanced.py:87-100): ch = c*r*r + (Y%r)*r + (X%r);

@@ -125,6 +125,44 @@ def main():
     ls = torch.zeros(1, device=dev, dtype=torch.float64)
     timed("mse_tail_grad_kernel", npix * (24 + 256),
           lambda: L.check(lib.sr_mse_tail_grad(L.ptr(pred), L.ptr(tgt), npix, 3, npix * 3, L.ptr(g128), L.ptr(ls), st())))
+    g128b = torch.empty(npix, 128, device=dev, dtype=torch.bfloat16)
+    db3 = torch.zeros(3, device=dev)
+    timed("mse_tail_grad_col_kernel", npix * (24 + 256),
+          lambda: L.check(lib.sr_mse_tail_grad_col(L.ptr(pred), L.ptr(tgt), 32, 384, 384, npix * 3, L.ptr(g128b), L.ptr(ls),
+                                                   L.ptr(db3), st())), "im2col of the loss gradient + bias gradient")
+    del g128, g128b, pred, tgt
+    # ---- bilinear x2 (Difvdsr4)
+    x2 = torch.randn(64, 96, 96, 128, device=dev)
+    o2 = torch.empty(64, 192, 192, 128, device=dev, dtype=torch.bfloat16)
+    timed("bilinear2_fwd_kernel<f32->bf16>", 64 * 96 * 96 * (512 + 4 * 256),
+          lambda: L.check(lib.sr_bilinear2_fwd(L.ptr(x2), 0, 64, 96, 96, 128, L.ptr(o2), None, st())))
+    del x2, o2
+    # ---- minibatch assembly from the HBM-resident dataset: 256 pairs of 48x48 / 192x192 uint8 -> float32
+    n_ds = 4096
+    ds_y = torch.randint(0, 256, (n_ds, 192, 192, 3), dtype=torch.uint8, device=dev)
+    idx = torch.randperm(n_ds, device=dev)[:256].to(torch.int64)
+    by = torch.empty(256, 192, 192, 3, device=dev)
+    timed("batch_gather_u8_kernel", 256 * 192 * 192 * 3 * (1 + 4),
+          lambda: L.check(lib.sr_batch_gather_u8(L.ptr(ds_y), 192 * 192 * 3, n_ds, L.ptr(idx), 256, 255.0, L.ptr(by), st())),
+          "256 HR targets of 192x192: 1 B read + 4 B written per element")
+    del ds_y, by
+    # ---- alternative tilers: x4 bicubic shrink of every 4th 128-px patch of a 512x512 image, averaging stitch
+    from sr100 import alt_tilers as at
+    im = torch.randint(0, 256, (512, 512, 3), dtype=torch.uint8, device=dev)
+    cnt_p = (512 - 128) // 4 + 1
+    bnd, kk = at.pil_bicubic_coeffs(128, 32)
+    co = (torch.from_numpy(bnd).to(dev), torch.from_numpy(kk).to(dev))
+    timed("patch_down4_kernel", cnt_p * cnt_p * (128 * 128 * 3 + 32 * 32 * 3 * 4),
+          lambda: at.patch_down4(im, 128, 4, True, None, None, co),
+          "9409 patches of 128x128 (bytescale + Pillow fixed-point bicubic): integer compute, patch reads hit L2")
+    rows = 8
+    pv = torch.rand(rows * cnt_p, 128, 128, 3, device=dev)
+    accd = torch.zeros(512, 512, 3, device=dev, dtype=torch.float64)
+    cntd = torch.zeros(512, 512, device=dev, dtype=torch.int32)
+    timed("patch_average_accumulate_kernel", rows * cnt_p * 128 * 128 * 3 * 4,
+          lambda: L.check(lib.sr_patch_average_accumulate(L.ptr(pv), 128, 4, 4, cnt_p, cnt_p, 0, rows, cnt_p - 1, cnt_p - 1,
+                                                          255.0, 512, 512, L.ptr(accd), L.ptr(cntd), st())),
+          "8 grid rows x 97 patches of 128x128x3 fp32 read once, float64 sums in patch order")
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         for r in recs:

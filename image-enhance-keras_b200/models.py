@@ -190,8 +190,11 @@ class BaseSuperResolutionModel(object):
         return self.model
 
     def evaluate(self, validation_dir):
-        raise NotImplementedError("evaluate()/_evaluate need scipy.misc.imresize bicubic data prep "
-                                  "(models.py:1519-1721); SURVEY.md 8(f) 'next' row")
+        """models.py:159-163."""
+        if self.type_requires_divisible_shape:
+            raise NotImplementedError("_evaluate_denoise (models.py:1625-1721) serves the denoising auto-encoders, "
+                                      "none of which this file defines")
+        _evaluate(self, validation_dir)
 
     def upVideo(self, imgObj, save_intermediate=False, return_image=False, suffix="scaled",
                 patch_size=8, mode="patch", verbose=False):
@@ -507,3 +510,55 @@ class Difvdsr(_PlaneNetModel):
     def fit(self, batch_size=8, nb_epochs=100, save_history=False, history_fn="ScaleGen History.txt"):
         """models.py:1332-1333."""
         return super(Difvdsr, self).fit(batch_size, nb_epochs, save_history, history_fn)
+
+
+def _evaluate(sr_model, validation_dir, scale_pred=False):
+    """models.py:1519-1622, line by line: every image of <validation_dir>/set5 and /set14 is read, scaled to [0,1],
+    bicubic-"resized" to its own size twice through scipy.misc.imresize (which byte-scales the float image back to
+    uint8 0..255 - the network is then fed 0..255 values, as in the reference), predicted, and compared with
+    models.psnr; the prediction is written to val_predict/.  Like the reference it only makes sense for same-size
+    models (Difvdsr): for a x4 model psnr() receives arrays of different shapes and numpy raises."""
+    import time
+    from PIL import Image
+    print("Validating %s model" % sr_model.model_name)
+    predict_path = "val_predict/"
+    if not os.path.exists(predict_path):
+        os.makedirs(predict_path)
+    for val_dir in [validation_dir + "set5/", validation_dir + "set14/"]:
+        image_fns = [name for name in os.listdir(val_dir)]
+        nb_images = len(image_fns)
+        print("Validating %d images from path %s" % (nb_images, val_dir))
+        total_psnr = 0.0
+        for impath in os.listdir(val_dir):
+            t1 = time.time()
+            y = np.asarray(Image.open(val_dir + impath).convert("RGB"))
+            width, height, _ = y.shape                       # (rows, cols): the reference's naming
+            y = y.astype('float32')
+            sf = sr_model.scale_factor
+            x_width = width if not sr_model.type_true_upscaling else width // sf
+            x_height = height if not sr_model.type_true_upscaling else height // sf
+            x_temp = y.copy()
+            if sr_model.type_scale_type == "tanh":
+                x_temp = (x_temp - 127.5) / 127.5
+                y = (y - 127.5) / 127.5
+            else:
+                x_temp /= 255.
+                y /= 255.
+            y = np.expand_dims(y, axis=0)
+            img = img_utils.imresize(x_temp, (x_width, x_height), interp='bicubic')
+            if not sr_model.type_true_upscaling:
+                img = img_utils.imresize(img, (x_width, x_height), interp='bicubic')
+            x = np.expand_dims(img, axis=0)
+            model = sr_model.create_model(x_height, x_width, load_weights=True)     # per-shape model (:1524)
+            y_pred = model.predict(x.astype(np.float32), batch_size=1)[0]
+            if scale_pred:
+                y_pred = (y_pred + 1) * 127.5 if sr_model.type_scale_type == "tanh" else y_pred * 255.
+            if sr_model.type_scale_type == 'tanh':
+                y = (y + 1) / 2
+            psnr_val = psnr(y[0], np.clip(y_pred, 0, 255) / 255)
+            total_psnr += psnr_val
+            t2 = time.time()
+            print("Validated image : %s, Time required : %0.2f, PSNR value : %0.4f" % (impath, t2 - t1, psnr_val))
+            generated_path = predict_path + "%s_%s_generated.png" % (sr_model.model_name, os.path.splitext(impath)[0])
+            Image.fromarray(np.clip(y_pred, 0, 255).astype('uint8')).save(generated_path)
+        print("Average PRNS value of validation images = %00.4f \n" % (total_psnr / nb_images))

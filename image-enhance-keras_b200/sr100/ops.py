@@ -21,7 +21,10 @@ def _dev():
 def to_device(a, dtype=None):
     """Host array -> device tensor.  Arrays that already live in page-locked memory (e.g. the outputs of
     models.upscale_arrays) are DMA-copied directly; pageable arrays take the ordinary staged copy."""
-    t = torch.from_numpy(np.ascontiguousarray(a))
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:           # e.g. np.asarray(PIL image): torch wants a writable buffer
+        a = a.copy()
+    t = torch.from_numpy(a)
     if dtype is not None:
         t = t.to(dtype)
     return t.to(_dev(), non_blocking=t.is_pinned())

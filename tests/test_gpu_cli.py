@@ -63,5 +63,4 @@ def test_upscale_fast_mode_whole_image(tmp_path):
     assert np.abs(got.astype(int) - want.astype(int)).max() <= 1          # truncation flips near integers
     assert np.array_equal(np.asarray(Image.open(str(tmp_path / "pic_Ascaled(1x).png"))), img)
     assert np.array_equal(np.asarray(Image.open(str(tmp_path / "pic_scaled(1x).png"))), got)
-    with pytest.raises(NotImplementedError):
-        m.upscale(p, mode="patch", verbose=False)
+    # mode='patch' (dense patches of the x4-bicubic image): tests/test_gpu_alt_tilers.py

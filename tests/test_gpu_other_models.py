@@ -157,3 +157,49 @@ def test_model_constructors_predict_weights_and_tiling(tmp_path, monkeypatch):
     assert modeld.output_shape == (None, 10, 12, 3) and len(modeld.layers) == 130   # width-major, models.py:121
     xd = rng.random((2, 10, 12, 3)).astype(np.float32)
     assert np.abs(modeld.predict(xd) - om.forward_difvdsr(wd, xd)).max() <= 2e-2
+
+
+def test_evaluate_mirrors_reference_validation_loop(tmp_path, monkeypatch, capsys):
+    """models._evaluate (models.py:1519-1622) on a same-size model (Difvdsr): the network is fed the byte-scaled 0..255
+    image, like the reference; PSNR printed per image, prediction written to val_predict/.  A x4 model fails in psnr()
+    with the reference's own assertion."""
+    import os
+    import models
+    from PIL import Image
+    from oracle import other_models as om
+    from oracle import pil_resample as pr
+    from sr100 import h5lite
+    rng = np.random.default_rng(21)
+    val = str(tmp_path / "val") + "/"
+    imgs = {}
+    for sub, names in (("set5", ["a.png", "b.png"]), ("set14", ["c.png"])):
+        os.makedirs(val + sub)
+        for n in names:
+            im = rng.integers(0, 256, size=(10, 12, 3), dtype=np.uint8)
+            Image.fromarray(im).save(val + sub + "/" + n)
+            imgs[n] = im
+    wd = om.init_weights(om.difvdsr_specs(), seed=12, bias_scale=0.02)
+    t = om.difvdsr_specs()[-1][0]
+    wd[t] = (wd[t][0] * 0.01, wd[t][1] + 0.3)
+    dfile = str(tmp_path / "wd.h5")
+    h5lite.save_keras_weights(dfile, wd, order=[s[0] for s in om.difvdsr_specs()])
+    monkeypatch.setenv("SR100_WEIGHTS", dfile)
+    monkeypatch.chdir(tmp_path)
+    md = models.Difvdsr(1)
+    md.evaluate(val)
+    out = capsys.readouterr().out
+    assert out.count("Validated image") == 3 and "Average PRNS value of validation images" in out
+    for n, im in imgs.items():
+        x = pr.imresize_bicubic(pr.imresize_bicubic(im.astype(np.float32) / 255., (10, 12)), (10, 12))
+        want = om.forward_difvdsr(wd, x[None].astype(np.float32))[0]
+        psnr = models.psnr(im.astype(np.float32) / 255., np.clip(want, 0, 255) / 255)
+        line = [l for l in out.splitlines() if "Validated image : %s" % n in l][0]
+        assert abs(float(line.split("PSNR value :")[1]) - psnr) < 0.05
+        got = np.asarray(Image.open(str(tmp_path / "val_predict" / ("Image ScaleGen_%s_generated.png" % n[:-4]))))
+        assert got.shape == (10, 12, 3)
+    m4 = models.Difvdsr4(1)
+    monkeypatch.setenv("SR100_WEIGHTS", str(tmp_path / "none.h5"))
+    with pytest.raises(AssertionError):
+        m4.create_model(8, 8)            # weights not loaded: plain random init
+        m4.create_model = lambda *a, **k: m4.model
+        m4.evaluate(val)                 # x4 output vs same-size target: psnr() asserts equal shapes

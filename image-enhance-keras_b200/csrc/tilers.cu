@@ -12,6 +12,7 @@
 // (i, j) lexicographic patch order.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "internal.h"
@@ -109,9 +110,11 @@ __global__ void patch_average_accumulate_kernel(const float* __restrict__ patche
                                                 int cnt_h, int cnt_w, int a0, int a1, int edge_a, int edge_b, float mul,
                                                 int out_h, int out_w, double* __restrict__ sum,
                                                 int* __restrict__ count) {
-  const size_t total = (size_t)out_h * out_w * 3;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
+  // only the image rows this band of patches can touch: [a0*step, (a1-1)*step + P)
+  const int y_first = a0 * step, y_last = min(out_h, (a1 - 1) * step + P);
+  const size_t total = (size_t)(y_last - y_first) * out_w * 3;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t idx = t + (size_t)y_first * out_w * 3;
     const int c = (int)(idx % 3);
     const size_t px = idx / 3;
     const int X = (int)(px % out_w), Y = (int)(px / out_w);
@@ -201,7 +204,8 @@ extern "C" int sr_patch_average_accumulate(const float* patches, int P, int step
   if (out_h < (cnt_h - 1) * step + P || out_w < (cnt_w - 1) * step + P)
     return set_error(SR_ERR_INVALID, "sr_patch_average_accumulate: the patch grid does not fit the image");
   if (a0 == a1) return SR_OK;
-  const size_t total = (size_t)out_h * out_w * 3;
+  const int y_last = std::min(out_h, (a1 - 1) * step + P);
+  const size_t total = (size_t)(y_last - a0 * step) * out_w * 3;
   patch_average_accumulate_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, as_stream(stream)>>>(
       patches, P, step, pad, cnt_h, cnt_w, a0, a1, edge_a, edge_b, mul, out_h, out_w, sum, count);
   return check_launch("patch_average_accumulate_kernel");

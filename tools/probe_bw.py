@@ -155,14 +155,14 @@ def main():
     timed("patch_down4_kernel", cnt_p * cnt_p * (128 * 128 * 3 + 32 * 32 * 3 * 4),
           lambda: at.patch_down4(im, 128, 4, True, None, None, co),
           "9409 patches of 128x128 (bytescale + Pillow fixed-point bicubic): integer compute, patch reads hit L2")
-    rows = 8
+    rows = 48
     pv = torch.rand(rows * cnt_p, 128, 128, 3, device=dev)
     accd = torch.zeros(512, 512, 3, device=dev, dtype=torch.float64)
     cntd = torch.zeros(512, 512, device=dev, dtype=torch.int32)
     timed("patch_average_accumulate_kernel", rows * cnt_p * 128 * 128 * 3 * 4,
           lambda: L.check(lib.sr_patch_average_accumulate(L.ptr(pv), 128, 4, 4, cnt_p, cnt_p, 0, rows, cnt_p - 1, cnt_p - 1,
                                                           255.0, 512, 512, L.ptr(accd), L.ptr(cntd), st())),
-          "8 grid rows x 97 patches of 128x128x3 fp32 read once, float64 sums in patch order")
+          "48 grid rows x 97 patches of 128x128x3 fp32 (0.9 GB) read once, float64 sums in patch order")
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         for r in recs:

@@ -276,10 +276,13 @@ def main():
     conv_flops = eng.last_flops()
     peaks = load_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    if eng.tf32:     # SR100_PRECISION=tf32: kind::tf32 MMAs run at half the bf16 rate; no measured tf32 peak exists
+        peaks = {"sustained": peaks["sustained"] / 2, "burst": peaks["burst"] / 2,
+                 "src": peaks["src"] + " (halved: tf32 = 0.5x bf16 tensor rate)"}
     launches_per_step = len(evs) + 5 + 5 + 5          # libsr100 kernels only: + gathers, stitches, scores
     traffic, traffic_src = None, None
     prof_dir = os.path.join(ROOT, "profiles")
-    for cand in sorted(os.listdir(prof_dir), reverse=True) if os.path.isdir(prof_dir) else []:
+    for cand in sorted(os.listdir(prof_dir), reverse=True) if os.path.isdir(prof_dir) and not eng.tf32 else []:
         if cand.endswith("_ncu_step_summary.json"):
             try:
                 traffic = json.load(open(os.path.join(prof_dir, cand)))["conv_traffic_bytes_per_launch"]
@@ -310,7 +313,7 @@ def main():
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": eng.precision, "data": "synthetic",
         "config": {"workload": "set5_x4_tiled", "images": SET5_SHAPES, "tiles": 186, "patch": 96, "step": 64,
                    "tiles_run": tiles_run, "hr_stage_extents": hr_shapes,
                    "dead_work_elimination": "tiles that own no pixel of the final 4Hx4W image are not run; the HR "
@@ -318,7 +321,7 @@ def main():
                                             "can see (receptive-field radius 7); output pixels bit-identical to the "
                                             "full tiling (tests/test_gpu_deadwork.py, tests/test_tile_plan.py), which is timed as value_full_tiles",
                    "output_mp_per_step_per_gpu": mp_step, "weights": "glorot_uniform random init",
-                   "residual_stream": "fp32 at LR, bf16 at HR",
+                   "residual_stream": "fp32 at LR and HR (tf32 operands)" if eng.tf32 else "fp32 at LR, bf16 at HR",
                    "l2": "every conv launch streams 0.36-2.9 GB of activations (> 126 MB L2); no flush needed"},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "value_full_tiles": round(value_full, 3),

@@ -394,6 +394,67 @@ __device__ __forceinline__ void epilogue_staged_acc_plain(const ConvKernelParams
   __syncwarp();
 }
 
+// tf32-mode epilogue (EPI = 5): the accumulator stays fp32 all the way.  A 256 B staging row holds 64 fp32
+// channels, so one 128x128 accumulator goes through the warp's staging tile in two halves; phase 2 is the same
+// 16-lanes-per-pixel pass (256 B of contiguous fp32 per pixel and half).  out_f32 = the unrounded result (the
+// residual stream), out_tf32 = the same value rounded to tf32 (what the next conv's MMAs read).
+__device__ __forceinline__ void epilogue_staged_acc_tf32(const ConvKernelParams& P, const TileCoord& c,
+                                                         uint32_t t_acc, int f_base, uint8_t* stage,
+                                                         const float* s_bias, int lane, bool live) {
+  const int f = f_base + lane;
+  const int fr = f / P.PWs;
+  const int yy = fr - P.p;
+  const int xx = f - fr * P.PWs - P.p;
+  const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
+                     xx < P.BW && (c.seg_x0 + xx) < P.Wc;
+  const int my_pix = valid ? (int)(((size_t)c.n * P.H + yy) * P.W + c.seg_x0 + xx) : -1;
+  uint8_t* my_row = stage + lane * 256;
+  const int sw = lane & 7;
+  const int half = lane >> 4, q = lane & 15;
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {
+    {
+      uint32_t va[32], vb[32];
+      tmem_ld32(t_acc + hb * 64, va);
+      tmem_ld32(t_acc + hb * 64 + 32, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = make_uint4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
+        *reinterpret_cast<uint4*>(my_row + (((8 + j) ^ sw) << 4)) = make_uint4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]);
+      }
+    }
+    __syncwarp();
+    float bs[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bs[e] = P.alpha * s_bias[hb * 64 + q * 4 + e];
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = 2 * i + half;
+      const int pix = __shfl_sync(0xffffffffu, my_pix, r);
+      if (pix < 0) continue;
+      const uint4 sv = *reinterpret_cast<const uint4*>(stage + r * 256 + ((q ^ (r & 7)) << 4));
+      float o[4] = {fmaf(P.alpha, __uint_as_float(sv.x), bs[0]), fmaf(P.alpha, __uint_as_float(sv.y), bs[1]),
+                    fmaf(P.alpha, __uint_as_float(sv.z), bs[2]), fmaf(P.alpha, __uint_as_float(sv.w), bs[3])};
+      const size_t off = (size_t)pix * 128 + hb * 64 + q * 4;
+      if (P.res_f32) {
+        const float4 rr = *reinterpret_cast<const float4*>(P.res_f32 + off);
+        o[0] = fmaf(P.beta, rr.x, o[0]); o[1] = fmaf(P.beta, rr.y, o[1]);
+        o[2] = fmaf(P.beta, rr.z, o[2]); o[3] = fmaf(P.beta, rr.w, o[3]);
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+      }
+      if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+      if (P.out_tf32)
+        *reinterpret_cast<float4*>(P.out_tf32 + off) =
+            make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
+    }
+    __syncwarp();  // the next half overwrites the staging rows
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
                                              int f_base, uint8_t* stage, const float* s_bias, int lane,
@@ -401,19 +462,23 @@ __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const Ti
   if constexpr (EPI < 0) epilogue_staged_acc_generic(P, c, t_acc, f_base, stage, s_bias, lane, live);
   else if constexpr (EPI == 0) epilogue_staged_acc_plain(P, c, t_acc, f_base, stage, s_bias, lane, live);
   else if constexpr (EPI == 4) epilogue_shuffle_acc(P, c, t_acc, f_base, s_bias, lane, live);
+  else if constexpr (EPI == 5) epilogue_staged_acc_tf32(P, c, t_acc, f_base, stage, s_bias, lane, live);
   else epilogue_staged_acc<EPI>(P, c, t_acc, f_base, stage, s_bias, lane, live);
 }
 
 }  // namespace
 
-template <int N_, int AMODE, int NACC, int NBUF, int EPI>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI, bool TF32>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                const ConvKernelParams P) {
   constexpr int T = NACC * 128;
-  constexpr int WTAP = N_ * kChunk * 2;      // one tap x 32 channels x N couts
+  constexpr int WTAP = N_ * kRowBytes;       // one tap x one K chunk (32 bf16 / 16 tf32 channels) x N couts
   constexpr int WSTAGE = kTapsPerStage * WTAP;  // a weight stage carries two consecutive taps
+  constexpr int NCH = PrecCfg<TF32>::kChunks, CHE = PrecCfg<TF32>::kElems;
+  static_assert(!TF32 || AMODE == kAModeSwizzle64, "tf32 operands use the swizzled strip");
+  static_assert(!TF32 || N_ != 128 || EPI == 5, "tf32 128-wide launches use the fp32 epilogue");
   constexpr uint32_t TM_COLS_RAW = NACC * NBUF * N_;
   constexpr uint32_t TM_COLS = TM_COLS_RAW <= 32    ? 32
                                : TM_COLS_RAW <= 64  ? 64
@@ -421,7 +486,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                : TM_COLS_RAW <= 256 ? 256
                                                     : 512;
   static_assert(TM_COLS_RAW <= 512, "TMEM overflow");
-  constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 128u, (uint32_t)N_);
+  constexpr uint32_t IDESC = umma_idesc(TF32 ? 2u : 1u /*tf32 : bf16*/, 128u, (uint32_t)N_);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
@@ -479,7 +544,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int ch = 0; ch < kNumChunks; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               // one box = 2 taps (an odd last tap drags in the next 128 rows, unused; OOB rows are zero-filled)
               const uint32_t slot = wr.slot, ph = wr.phase;
@@ -496,17 +561,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------ activation strip TMA producer
     if (lane == 0) {
       uint32_t ac = 0;
-      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kChunk * 2;
+      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kRowBytes;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile<T>(P, t);
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-          for (int ch = 0; ch < kNumChunks; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
             mbar_expect_tx(&bars->a_full[slot], strip_bytes);
             if constexpr (AMODE == kAModeSwizzle64) {
-              tma_load_4d(a_buf + slot * P.a_bytes, tmA, &bars->a_full[slot], ch * kChunk,
+              tma_load_4d(a_buf + slot * P.a_bytes, tmA, &bars->a_full[slot], ch * CHE,
                           c.seg_x0 - P.p, c.r_lo - P.p, c.n);
             } else {
               tma_load_5d(a_buf + slot * P.a_bytes, tmA, &bars->a_full[slot], 0, c.seg_x0 - P.p,
@@ -548,7 +613,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int pk = (k - 1) / 2;
         const int ntaps = k * k;
         const int row_wrap = (P.PWs - (k - 1)) * (int)a_pix;  // (ky, k-1) -> (ky+1, 0)
-        for (int ch = 0; ch < kNumChunks; ++ch) {
+        for (int ch = 0; ch < NCH; ++ch) {
           const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
           mbar_wait(&bars->a_full[aslot], aph);
           tc_fence_after();
@@ -570,7 +635,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint64_t adesc =
                         ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + acc * 128 * a_pix + k16 * a_k16);
                     const uint64_t bdesc = ((uint64_t)kHiSw64 << 32) | (uint64_t)(b_lo + k16 * 2);
-                    umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    if constexpr (TF32) umma_tf32(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    else umma_bf16(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
                   }
                 }
               }
@@ -656,18 +722,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // and L2 -> SM weight traffic halves.  The leader CTA (rank 0) owns the full-barriers and issues;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
 // =====================================================================================
-template <int NACC, int NBUF, int EPI>
+template <int NACC, int NBUF, int EPI, bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
                     const ConvKernelParams P) {
   constexpr int N_ = 128;
   constexpr int T = NACC * 128;
-  constexpr int WTAP = (N_ / 2) * kChunk * 2;   // this CTA's half (64 couts) of one tap x 32 channels
+  constexpr int WTAP = (N_ / 2) * kRowBytes;    // this CTA's half (64 couts) of one tap x one K chunk
+  constexpr int NCH = PrecCfg<TF32>::kChunks, CHE = PrecCfg<TF32>::kElems;
+  static_assert(!TF32 || EPI == 5, "tf32 launches use the fp32 epilogue");
   constexpr int WSTAGE = kTapsPerStage * WTAP;  // a weight stage carries two consecutive taps
   constexpr uint32_t TM_COLS = 512;
   static_assert(NACC * NBUF * N_ == 512, "pair kernel uses the whole TMEM");
-  constexpr uint32_t IDESC = umma_idesc(1u /*bf16*/, 256u, (uint32_t)N_);
+  constexpr uint32_t IDESC = umma_idesc(TF32 ? 2u : 1u /*tf32 : bf16*/, 256u, (uint32_t)N_);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
@@ -739,7 +807,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int ch = 0; ch < kNumChunks; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t slot = wr.slot, ph = wr.phase;
               mbar_wait(&bars->w_empty[slot], ph ^ 1);
@@ -761,18 +829,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ------------------------------------------------ activation strip TMA producer (both CTAs)
     if (lane == 0) {
       uint32_t ac = 0;
-      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kChunk * 2;
+      const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kRowBytes;
       for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
         bool live;
         const TileCoord c = decode(pt, &live);
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-          for (int ch = 0; ch < kNumChunks; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
             if (is_leader) mbar_expect_tx(&bars->a_full[slot], 2 * strip_bytes);
             tma_load_4d_pair(a_buf + slot * P.a_bytes, tmA, mapa_shared(smem_u32(&bars->a_full[slot]), 0),
-                             ch * kChunk, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
+                             ch * CHE, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
             ++ac;
           }
         }
@@ -801,7 +869,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int pk = (k - 1) / 2;
           const int ntaps = k * k;
           const int row_wrap = (P.PWs - (k - 1)) * 4;
-          for (int ch = 0; ch < kNumChunks; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
             mbar_wait(&bars->a_full[aslot], aph);
             tc_fence_after();
@@ -821,7 +889,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     for (int k16 = 0; k16 < 2; ++k16) {
                       const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + acc * 512 + k16 * 2);
                       const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
-                      umma_bf16_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                      if constexpr (TF32) umma_tf32_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                      else umma_bf16_pair(d_base + acc * N_, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
                     }
                   }
                 }
@@ -903,17 +972,28 @@ struct ConvPlan {
   int amode;
   int nacc;
   int pair;     // 1: CTA-pair (cta_group::2) kernel
+  int tf32;     // 1: fp32 tensors, tf32 MMAs
   int grid;
   size_t smem_bytes;
   double flops;  // algorithmic FLOPs (2*MAC) of one run
 };
 
 static int make_a_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, int PWs, int NR,
-                      int amode) {
+                      int amode, int tf32) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUresult r;
-  if (amode == kAModeSwizzle64) {
+  if (tf32) {
+    // fp32 NHWC: a K chunk is 16 channels = the same 64-byte pixel rows as 32 bf16 channels
+    cuuint64_t dims[4] = {(cuuint64_t)kCin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    cuuint64_t strides[3] = {(cuuint64_t)kCin * 4, (cuuint64_t)W * kCin * 4,
+                             (cuuint64_t)H * W * kCin * 4};
+    cuuint32_t box[4] = {(cuuint32_t)PrecCfg<true>::kElems, (cuuint32_t)PWs, (cuuint32_t)NR, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (amode == kAModeSwizzle64) {
     cuuint64_t dims[4] = {(cuuint64_t)kCin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
     cuuint64_t strides[3] = {(cuuint64_t)kCin * 2, (cuuint64_t)W * kCin * 2,
                              (cuuint64_t)H * W * kCin * 2};
@@ -941,14 +1021,15 @@ static int make_a_map(CUtensorMap* tm, const void* ptr, int NB, int H, int W, in
   return SR_OK;
 }
 
-static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad, int box_rows) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad, int box_rows, int tf32) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(SR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)kChunk, (cuuint64_t)nstages * n_pad};
-  cuuint64_t strides[1] = {(cuuint64_t)kChunk * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)box_rows};
+  const int elems = tf32 ? PrecCfg<true>::kElems : kChunk;  // 64-byte rows either way
+  cuuint64_t dims[2] = {(cuuint64_t)elems, (cuuint64_t)nstages * n_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)kRowBytes};
+  cuuint32_t box[2] = {(cuuint32_t)elems, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+  CUresult r = enc(tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -997,9 +1078,9 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
   return best_eff > 0;
 }
 
-template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1, bool TF32 = false>
 static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI>;
+  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1014,9 +1095,9 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   return SR_OK;
 }
 
-template <int NACC, int NBUF, int EPI = -1>
+template <int NACC, int NBUF, int EPI = -1, bool TF32 = false>
 static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI>;
+  auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1050,6 +1131,12 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (d->relu < 0 || d->relu > 2) return set_error(SR_ERR_INVALID, "relu must be 0, 1 (ReLU) or 2 (LeakyReLU)");
   if (d->relu == 2 && (d->cout != 128 || d->shuffle_r > 0))
     return set_error(SR_ERR_UNSUPPORTED, "LeakyReLU epilogue: cout == 128, no shuffle");
+  const int tf32 = d->precision == 1 ? 1 : 0;
+  if (d->precision != 0 && d->precision != 1) return set_error(SR_ERR_INVALID, "precision must be 0 (bf16) or 1 (tf32)");
+  if (tf32 && (d->out_bf16 || d->res_bf16 || d->relu_mask_bf16 || d->shuffle_r > 0 || d->a_mode == 1 || d->relu == 2))
+    return set_error(SR_ERR_UNSUPPORTED, "tf32 precision: fp32 tensors only (out_f32 / out_tf32 / res_f32), a_mode 0, no shuffle / mask / LeakyReLU");
+  if (!tf32 && d->out_tf32) return set_error(SR_ERR_INVALID, "out_tf32 needs precision == 1");
+  if (tf32 && d->cout <= 16 && d->out_tf32) return set_error(SR_ERR_UNSUPPORTED, "out_tf32 needs cout == 128");
   int p = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     const int k = d->ksize[s];
@@ -1063,10 +1150,11 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   memset(pl, 0, sizeof *pl);
   pl->n_pad = (d->cout == 128 || d->shuffle_r > 0) ? 128 : 16;
   pl->amode = d->a_mode == 1 ? kAModeInterleave : kAModeSwizzle64;
-  pl->nacc = ((d->nacc == 2 || d->shuffle_r > 0) && pl->n_pad == 128) ? 2 : 4;
+  pl->tf32 = tf32;
+  pl->nacc = ((d->nacc == 2 || d->shuffle_r > 0 || tf32) && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
   pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
-  const int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kChunk * 2;
+  const int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kRowBytes;
   ConvKernelParams& P = pl->P;
   P.nsrc = d->nsrc;
   P.ksize[0] = d->ksize[0];
@@ -1100,6 +1188,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->res_bf16);
   P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
   P.out_f32 = d->out_f32;
+  P.out_tf32 = d->out_tf32;
   P.cout = d->cout;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
   P.out_index = d->out_index;
@@ -1114,10 +1203,11 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   }
   double macs = 0;
   for (int s = 0; s < d->nsrc; ++s) {
-    int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode);
+    int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode, tf32);
     if (rc == SR_OK)
-      rc = make_w_map(&pl->tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], pl->n_pad,
-                      pl->pair ? pl->n_pad / 2 : kTapsPerStage * pl->n_pad);
+      rc = make_w_map(&pl->tmW[s], d->wpacked[s],
+                      (tf32 ? PrecCfg<true>::kChunks : kNumChunks) * d->ksize[s] * d->ksize[s], pl->n_pad,
+                      pl->pair ? pl->n_pad / 2 : kTapsPerStage * pl->n_pad, tf32);
     if (rc != SR_OK) {
       delete pl;
       return rc;
@@ -1153,6 +1243,11 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
   const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32 && P.relu != 2;
   const int epi = P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  if (pl->tf32) {
+    if (pl->pair) return launch_pair<2, 2, 5, true>(pl, st);
+    if (pl->n_pad == 128) return launch_variant<128, kAModeSwizzle64, 2, 2, 5, true>(pl, st);
+    return launch_variant<16, kAModeSwizzle64, 4, 2, -1, true>(pl, st);
+  }
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
     switch (epi) {

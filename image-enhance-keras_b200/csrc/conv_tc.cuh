@@ -23,6 +23,17 @@ constexpr int kConvThreads = 256;  // warp0: weight TMA, warp1: MMA, warp2: TMEM
 constexpr int kCin = 128;          // every tensor-core conv of the stack has 128 input channels
 constexpr int kChunk = 32;         // channels per K chunk (64-byte rows)
 constexpr int kNumChunks = kCin / kChunk;
+constexpr int kRowBytes = kChunk * 2;  // one pixel row of a K chunk in shared memory: 64 bytes (TMA / UMMA 64B swizzle)
+
+// Operand precision.  bf16: 32 channels per 64-byte row, 4 K chunks, kind::f16 MMAs of K = 16.
+// tf32: the activations and packed weights are fp32 words (rounded to tf32 by their producers), 16 channels
+// per 64-byte row, 8 K chunks, kind::tf32 MMAs of K = 8 -- byte for byte the same strips, weight stages and
+// descriptors, twice as many of them.
+template <bool TF32>
+struct PrecCfg {
+  static constexpr int kElems = TF32 ? 16 : 32;   // channels per K chunk
+  static constexpr int kChunks = kCin / kElems;
+};
 
 enum ConvAMode : int {
   kAModeSwizzle64 = 0,   // A strip [pixel][32ch] with TMA/UMMA 64B swizzle, tap = start-address shift
@@ -49,6 +60,7 @@ struct ConvKernelParams {
   const __nv_bfloat16* res_bf16;
   __nv_bfloat16* out_bf16;
   float* out_f32;
+  float* out_tf32;   // tf32 mode: the output again, rounded to tf32 (round-to-nearest) = the next conv's operand
   int cout;          // real output channels (128; 3 for the tail conv)
   // dgrad-time ReLU mask: if non-null, out *= (mask > 0)
   const __nv_bfloat16* relu_mask_bf16;

@@ -422,6 +422,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int ntaps, i
   }
 }
 
+// tf32 variant: HWIO fp32 [k*k][128][cout] -> fp32 words rounded to tf32, [chunk of 16][tap][n_pad][16]
+__device__ __forceinline__ float round_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__global__ void pack_weights_tf32_kernel(const float* __restrict__ hwio, int ntaps, int cout, int n_pad,
+                                         float* __restrict__ dst) {
+  const size_t total = (size_t)8 * ntaps * n_pad * 16;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 15);
+    size_t q = idx >> 4;
+    const int n = (int)(q % n_pad);
+    q /= n_pad;
+    const int tap = (int)(q % ntaps);
+    const int chunk = (int)(q / ntaps);
+    const int k_in = chunk * 16 + c;
+    dst[idx] = n < cout ? round_tf32_rna(hwio[((size_t)tap * 128 + k_in) * cout + n]) : 0.f;
+  }
+}
+__global__ void round_tf32_kernel(const float4* __restrict__ in, size_t n4, float4* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    out[i] = make_float4(round_tf32_rna(v.x), round_tf32_rna(v.y), round_tf32_rna(v.z), round_tf32_rna(v.w));
+  }
+}
+
 // All layers in ONE launch (the optimizer step repacks 85 layers, forward and transposed: 170 tiny launches
 // otherwise cost more than the all-reduce).  items[i] describes one (layer, orientation); `starts` are the prefix
 // sums of the packed element counts.
@@ -748,6 +776,31 @@ extern "C" int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int 
   pack_weights_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
       hwio, ksize * ksize, cout, n_pad, transpose_flip, reinterpret_cast<__nv_bfloat16*>(dst));
   return check_launch("pack_weights_kernel");
+}
+
+extern "C" size_t sr_packed_weight_bytes_tf32(int ksize, int cout) {
+  const int n_pad = cout > 16 ? 128 : 16;
+  return (size_t)8 * ksize * ksize * n_pad * 16 * 4;
+}
+
+extern "C" int sr_pack_conv_weights_tf32(const float* hwio, int ksize, int cout, void* dst, void* stream) {
+  if (!hwio || !dst) return set_error(SR_ERR_INVALID, "sr_pack_conv_weights_tf32: null pointer");
+  if (cout < 1 || cout > 128) return set_error(SR_ERR_UNSUPPORTED, "sr_pack_conv_weights_tf32: cout must be 1..128");
+  const int n_pad = cout > 16 ? 128 : 16;
+  const size_t total = (size_t)8 * ksize * ksize * n_pad * 16;
+  pack_weights_tf32_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(stream)>>>(
+      hwio, ksize * ksize, cout, n_pad, reinterpret_cast<float*>(dst));
+  return check_launch("pack_weights_tf32_kernel");
+}
+
+extern "C" int sr_round_tf32(const float* in, size_t n, float* out, void* stream) {
+  if (n == 0) return SR_OK;
+  if (!in || !out) return set_error(SR_ERR_INVALID, "sr_round_tf32: null pointer");
+  if (n % 4 != 0 || (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 != 0)
+    return set_error(SR_ERR_UNSUPPORTED, "sr_round_tf32: n % 4 == 0 and 16-byte aligned pointers");
+  round_tf32_kernel<<<grid_for(n / 4, kBlock, 148 * 16), kBlock, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(in), n / 4, reinterpret_cast<float4*>(out));
+  return check_launch("round_tf32_kernel");
 }
 
 extern "C" int sr_pack_conv_weights_batched(const sr_pack_item* items_dev, const unsigned long long* starts_dev,

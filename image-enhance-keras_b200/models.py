@@ -418,6 +418,9 @@ class DifvdsrDouble(BaseSuperResolutionModel):
     3x3 tail; 86 convs, 21,838,211 parameters."""
 
     weights_file = "weights_Double/weights025-17-0.93.h5"   # models.py:1217
+    # conv operand precision of the engine: None -> $SR100_PRECISION or "bf16"; "tf32" = the accuracy mode (fp32
+    # tensors, tf32 MMAs, ~1e-4 of the reference's fp32 graph at half the tensor rate); inference only
+    precision = None
 
     def __init__(self, scale_factor):
         super(DifvdsrDouble, self).__init__("Image ScaleGen", scale_factor)
@@ -432,7 +435,7 @@ class DifvdsrDouble(BaseSuperResolutionModel):
         if channels != 3:
             raise ValueError("DifvdsrDouble is a 3-channel model (models.py:1177)")
         if self._engine is None:
-            self._engine = Engine()                      # glorot_uniform kernels, zero biases (Keras defaults)
+            self._engine = Engine(precision=self.precision)   # glorot_uniform kernels, zero biases (Keras defaults)
         model = Model(init, engine=self._engine)
         model.compile(optimizer=_Adam(1e-4, 0.9), loss='mse', metrics=['accuracy'])   # :1212-1213
         if load_weights:

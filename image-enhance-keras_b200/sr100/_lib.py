@@ -42,6 +42,8 @@ class ConvDesc(C.Structure):
         ("shuffle_r", C.c_int), ("shuffle_order", C.c_int),
         ("comp_h", C.c_int), ("comp_w", C.c_int),
         ("leaky_slope", C.c_float),
+        ("precision", C.c_int),
+        ("out_tf32", C.c_void_p),
     ]
 
 
@@ -102,6 +104,9 @@ SIGNATURES = {
     "sr_packed_weight_bytes": (_sz, [_i, _i]),
     "sr_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sr_pack_conv_weights_batched": (_i, [_vp, _vp, _i, _sz, _vp]),
+    "sr_packed_weight_bytes_tf32": (_sz, [_i, _i]),
+    "sr_pack_conv_weights_tf32": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sr_round_tf32": (_i, [_vp, _sz, _vp, _vp]),
     "sr_conv2d_direct": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_head1x1_fwd": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sr_bilinear4_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -9,7 +9,10 @@ sequence of libsr100 launches on device-resident NHWC tensors:
 
 All 128-channel convs run on tcgen05 tensor cores (bf16 operands, fp32 TMEM accumulators).  The
 residual stream is kept in fp32 in HBM at LR (22 blocks of accumulation) and in bf16 at HR (2 blocks);
-`stream` chooses otherwise.  PyTorch is only the allocator / stream provider here.
+`stream` chooses otherwise.  precision="tf32" is the accuracy mode (the reference's Conv2D is fp32): every
+activation tensor is fp32, operands are rounded to tf32 (round to nearest) by the kernel that produces them, the
+MMAs are tcgen05 kind::tf32 and the whole epilogue algebra is fp32 -- the same launch sequence at half the tensor
+rate.  PyTorch is only the allocator / stream provider here.
 """
 from __future__ import annotations
 
@@ -105,9 +108,16 @@ class _Stage:
         d.bias = eng.bias_for(tuple(n for n, _ in srcs)).data_ptr()
         d.alpha, d.beta, d.relu = alpha, beta, relu
         d.res_f32 = res32.data_ptr() if res32 is not None else None
-        d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
-        d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
         d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        if eng.tf32:
+            # the "operand copy" slot (bf16 in the default mode) is the tf32-rounded fp32 tensor; residuals are
+            # always the fp32 stream
+            assert res16 is None or res32 is not None
+            d.precision = 1
+            d.out_tf32 = out_bf16.data_ptr() if out_bf16 is not None else None
+        else:
+            d.res_bf16 = res16.data_ptr() if (res16 is not None and res32 is None) else None
+            d.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
         if out_index is not None:
             d.out_index, (d.out_h, d.out_w) = out_index.data_ptr(), out_hw
         d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
@@ -164,8 +174,9 @@ class _LRStage(_Stage):
         self.NB, self.H, self.W = NB, H, W
         self.need = (H, W) if need is None else (min(H, need[0]), min(W, need[1]))
         exts = lr_extents(self.need, (H, W))
+        op = f32 if eng.tf32 else bf      # dtype of the conv operands (tf32 operands are fp32 words)
         self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
-        self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=bf)
+        self.s_lr = torch.empty(NB, H, W, NUMK, device=dev, dtype=op)
         self.t1_lr = torch.empty_like(self.s_lr)
         self.t2_lr = torch.empty_like(self.s_lr)
         self.s_lr32 = torch.empty(NB, H, W, NUMK, device=dev, dtype=f32) if eng.stream_lr_fp32 else None
@@ -174,8 +185,14 @@ class _LRStage(_Stage):
         lib = eng.lib
         names = [s[0] for s in layer_specs()]
         npix = NB * H * W
-        self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
-            L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, L.ptr(self.s_lr), L.ptr(self.s_lr32), st)))
+        if eng.tf32:
+            self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
+                L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, None, L.ptr(self.s_lr32), st)))
+            self.steps.append(lambda st: L.check(lib.sr_round_tf32(
+                L.ptr(self.s_lr32), npix * NUMK, L.ptr(self.s_lr), st)))
+        else:
+            self.steps.append(lambda st: L.check(lib.sr_head1x1_fwd(
+                L.ptr(self.x_in), L.ptr(eng.head_w), L.ptr(eng.head_b), npix, L.ptr(self.s_lr), L.ptr(self.s_lr32), st)))
         i, lr = 1, (NB, H, W)
         for b in range(16):
             self._block53(names, i, self.s_lr, self.s_lr32, self.t1_lr, self.t2_lr, lr, comp=exts[b])
@@ -217,7 +234,7 @@ class _HRStage(_Stage):
         self.n, self.eh, self.ew = n, eh, ew
         self.src_index = torch.arange(n, device=dev, dtype=torch.int32)   # which LR patches (updated per run)
         self.idx_host = list(range(n))
-        self.s_hr = torch.empty(n, eh, ew, NUMK, device=dev, dtype=bf)
+        self.s_hr = torch.empty(n, eh, ew, NUMK, device=dev, dtype=f32 if eng.tf32 else bf)
         self.t1_hr = torch.empty_like(self.s_hr)
         self.t2_hr = torch.empty_like(self.s_hr)
         self.s_hr32 = torch.empty(n, eh, ew, NUMK, device=dev, dtype=f32) if eng.stream_hr_fp32 else None
@@ -226,9 +243,15 @@ class _HRStage(_Stage):
         src = lrs.s_lr32 if lrs.s_lr32 is not None else lrs.s_lr
         src_is_bf16 = 0 if lrs.s_lr32 is not None else 1
         H, W = lrs.H, lrs.W
-        self.steps.append(lambda st: L.check(lib.sr_bilinear4_crop_fwd(
-            L.ptr(src), src_is_bf16, L.ptr(self.src_index), n, H, W, NUMK, eh, ew, L.ptr(self.s_hr),
-            L.ptr(self.s_hr32), st)))
+        if eng.tf32:
+            self.steps.append(lambda st: L.check(lib.sr_bilinear4_crop_fwd(
+                L.ptr(src), 0, L.ptr(self.src_index), n, H, W, NUMK, eh, ew, None, L.ptr(self.s_hr32), st)))
+            self.steps.append(lambda st: L.check(lib.sr_round_tf32(
+                L.ptr(self.s_hr32), n * eh * ew * NUMK, L.ptr(self.s_hr), st)))
+        else:
+            self.steps.append(lambda st: L.check(lib.sr_bilinear4_crop_fwd(
+                L.ptr(src), src_is_bf16, L.ptr(self.src_index), n, H, W, NUMK, eh, ew, L.ptr(self.s_hr),
+                L.ptr(self.s_hr32), st)))
         i, hr = lrs.first_hr_layer, (n, eh, ew)
         # a cropped extent e (< 4H) was chosen as >= (last surviving pixel + 1) + 7, so the tail only has to be right on
         # [0, e-7), the second block on e-6 (its t1 / t2 on e-4 / e-5), the first block on e-3 (t1 / t2 on e-1 / e-2)
@@ -334,10 +357,16 @@ class Engine:
     """Device-resident DifvdsrDouble weights + cached per-shape graphs."""
 
     def __init__(self, weights=None, device=None, stream="lr32", a_mode=0, nacc=2, pair=1,
-                 max_pixels=192 * 96 * 96, use_graphs=True):
+                 max_pixels=192 * 96 * 96, use_graphs=True, precision=None):
         self.lib = L.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         assert stream in ("bf16", "lr32", "fp32")
+        precision = precision or os.environ.get("SR100_PRECISION", "bf16")
+        if precision not in ("bf16", "tf32"):
+            raise ValueError("precision must be 'bf16' or 'tf32', got %r" % (precision,))
+        self.precision, self.tf32 = precision, precision == "tf32"
+        if self.tf32:
+            stream, a_mode, nacc = "fp32", 0, 2      # fp32 residual stream at both resolutions
         self.stream_lr_fp32 = stream in ("lr32", "fp32")
         self.stream_hr_fp32 = stream == "fp32"
         self.a_mode, self.nacc, self.pair = a_mode, nacc, pair
@@ -386,6 +415,18 @@ class Engine:
     def repack(self):
         """(Re)build the tensor-core weight layout from the fp32 masters (after load / optimizer step): one launch
         for all 85 layers (sr_pack_conv_weights_batched)."""
+        if self.tf32:
+            st = L.stream_ptr()
+            for name, k, cin, cout in self.specs:
+                if cin != NUMK:
+                    continue
+                if name not in self.packed:
+                    self.packed[name] = torch.empty(self.lib.sr_packed_weight_bytes_tf32(k, cout), dtype=torch.uint8,
+                                                    device=self.device)
+                L.check(self.lib.sr_pack_conv_weights_tf32(L.ptr(self.master[name][0]), k, cout,
+                                                           L.ptr(self.packed[name]), st))
+            self._refresh_bias_sums()
+            return
         if self._pack_table is None:
             for name, k, cin, cout in self.specs:
                 if cin == NUMK and name not in self.packed:

@@ -238,6 +238,9 @@ class Trainer:
     """train_on_batch / evaluate for a kmodel.Model (Keras Model.train_on_batch semantics: returns the loss)."""
 
     def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        if getattr(engine, "tf32", False):
+            raise NotImplementedError("training runs on the bf16 engine (dgrad / wgrad kernels take bf16 operands); "
+                                      "precision='tf32' is an inference mode")
         self.engine = engine
         self.lib = engine.lib
         self.lr, self.beta_1, self.beta_2, self.epsilon = float(lr), float(beta_1), float(beta_2), float(epsilon)

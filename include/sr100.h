@@ -75,6 +75,14 @@ typedef struct sr_conv_desc {
    * receptive field can still reach a surviving pixel.  0: the whole H x W image. */
   int comp_h, comp_w;
   float leaky_slope;     /* negative-side slope when relu == 2 */
+  /* Operand precision.  0: bf16 (above).  1: tf32 -- the "tf32 option" of the conv stack for users who want
+   * the fp32 graph of the reference (Keras/TF Conv2D is fp32) to ~1e-4: in[] are fp32 [NB,H,W,128] whose values
+   * are already rounded to tf32 (out_tf32 of the producing launch, sr_round_tf32), wpacked[] come from
+   * sr_pack_conv_weights_tf32, MMAs are tcgen05 kind::tf32 with fp32 accumulation, the epilogue is fp32
+   * throughout.  Outputs: out_f32 (unrounded: the residual stream) and/or out_tf32; residual: res_f32 only.
+   * bf16 tensors, relu_mask, shuffle_r, LeakyReLU and a_mode 1 are not available in this mode. */
+  int precision;
+  float* out_tf32;       /* precision 1, cout == 128: the output rounded to tf32 (round to nearest) */
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -111,6 +119,13 @@ int sr_pack_conv_weights_batched(const sr_pack_item* items_dev, const unsigned l
                                  int n_items, size_t total_elems, void* stream);
 int sr_pack_conv_weights(const float* hwio, int ksize, int cout, int transpose_flip, void* dst,
                          void* stream);
+/* The same repack for sr_conv_desc.precision == 1: fp32 words rounded to tf32 (round to nearest), layout
+ * [cin/16][k*k][cout_pad][16] (64-byte rows like the bf16 layout, twice as many K chunks). */
+size_t sr_packed_weight_bytes_tf32(int ksize, int cout);
+int sr_pack_conv_weights_tf32(const float* hwio, int ksize, int cout, void* dst, void* stream);
+/* out[i] = in[i] rounded to tf32 (cvt.rna): makes an fp32 tensor a tf32 conv operand (the tensor core would
+ * otherwise truncate the low 13 mantissa bits, a biased error).  in == out is allowed. */
+int sr_round_tf32(const float* in, size_t n, float* out, void* stream);
 
 /* Plain CUDA-core convolution, fp32 accumulate, any cin/cout, SAME or VALID, NHWC.  Used for
  * layers outside the 128-channel stack (Subpixel(Conv2D), keras_subpixel.py:28-62) and as the

@@ -20,7 +20,7 @@ CASES = []
 
 def case(**kw):
     d = dict(NB=2, H=20, W=96, ks=(3,), cout=128, mode=0, nacc=4, res=None, relu=0, alpha=1.0, beta=0.0,
-             iters=0, check=True, outs="both", pair=0)
+             iters=0, check=True, outs="both", pair=0, prec="bf16")
     d.update(kw)
     CASES.append(d)
 
@@ -74,6 +74,16 @@ for nacc in (4, 2):
          iters=10, check=False, nacc=nacc, pair=1)
 
 
+# tf32 option (sr_conv_desc.precision = 1): many-wave throughput of the CTA-pair kernel (correctness: tests/test_gpu_tf32.py)
+case(name="tf32big_k5_lr_relu", ks=(5,), NB=148, H=96, W=96, relu=1, iters=10, check=False, nacc=2, pair=1, prec="tf32")
+case(name="tf32big_k3_lr_relu", ks=(3,), NB=148, H=96, W=96, relu=1, iters=20, check=False, nacc=2, pair=1, prec="tf32")
+case(name="tf32big_k5k3_lr_end", ks=(5, 3), NB=148, H=96, W=96, res="f32", alpha=0.1, beta=0.9, iters=10, check=False,
+     nacc=2, pair=1, prec="tf32", outs="both")
+case(name="tf32big_k5_hr_relu", ks=(5,), NB=8, H=384, W=384, relu=1, iters=10, check=False, nacc=2, pair=1, prec="tf32")
+case(name="tf32big_k5k3_hr_end", ks=(5, 3), NB=8, H=384, W=384, res="f32", alpha=0.1, beta=0.9, iters=10, check=False,
+     nacc=2, pair=1, prec="tf32", outs="both")
+
+
 def run_case(idx):
     import torch
     from sr100 import _lib as L
@@ -83,11 +93,18 @@ def run_case(idx):
     dev = "cuda"
     NB, H, W, cout = cs["NB"], cs["H"], cs["W"], cs["cout"]
     ins, ws, packed = [], [], []
+    tf32 = cs["prec"] == "tf32"
     for k in cs["ks"]:
-        x = (torch.randn(NB, H, W, 128, device=dev) * 0.5).to(torch.bfloat16).contiguous()
+        x = torch.randn(NB, H, W, 128, device=dev) * 0.5
         w = (torch.randn(k, k, 128, cout, device=dev) / (k * k * 128) ** 0.5).contiguous()
-        pk = torch.empty(lib.sr_packed_weight_bytes(k, cout), dtype=torch.uint8, device=dev)
-        L.check(lib.sr_pack_conv_weights(L.ptr(w), k, cout, 0, L.ptr(pk), L.stream_ptr()))
+        if tf32:
+            L.check(lib.sr_round_tf32(L.ptr(x), x.numel(), L.ptr(x), L.stream_ptr()))
+            pk = torch.empty(lib.sr_packed_weight_bytes_tf32(k, cout), dtype=torch.uint8, device=dev)
+            L.check(lib.sr_pack_conv_weights_tf32(L.ptr(w), k, cout, L.ptr(pk), L.stream_ptr()))
+        else:
+            x = x.to(torch.bfloat16).contiguous()
+            pk = torch.empty(lib.sr_packed_weight_bytes(k, cout), dtype=torch.uint8, device=dev)
+            L.check(lib.sr_pack_conv_weights(L.ptr(w), k, cout, 0, L.ptr(pk), L.stream_ptr()))
         ins.append(x); ws.append(w); packed.append(pk)
     bias = torch.randn(cout, device=dev) * 0.1
     res = None
@@ -110,9 +127,15 @@ def run_case(idx):
         d.res_f32 = res.data_ptr()
     elif cs["res"] == "bf16":
         d.res_bf16 = res.data_ptr()
-    d.out_bf16 = out_bf16.data_ptr()
-    if cs["outs"] == "both":
-        d.out_f32 = out_f32.data_ptr()
+    if tf32:      # operand copy (tf32-rounded fp32) always, the unrounded stream for the block-end launches
+        out_t32 = torch.zeros(NB, H, W, cout, device=dev)
+        d.precision, d.out_tf32 = 1, out_t32.data_ptr()
+        if cs["res"]:
+            d.out_f32 = out_f32.data_ptr()
+    else:
+        d.out_bf16 = out_bf16.data_ptr()
+        if cs["outs"] == "both":
+            d.out_f32 = out_f32.data_ptr()
     d.a_mode, d.nacc, d.pair = cs["mode"], cs["nacc"], cs["pair"]
     plan = C.c_void_p()
     L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(plan)))

@@ -303,37 +303,105 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
 
 // Sub-pixel epilogue (EPI = 4): conv + bias (+ReLU) whose fp32 result is stored straight at its depth-to-space
 // position (keras_subpixel.py:64-84, advanced.py:87-129,195-196) -- the shuffle is only a store address.
+// Staged so that the stores are coalesced: this variant's staging rows are 512 B (all 128 fp32 channels of a
+// pixel; kShuffleStageRow), phase 1 drains the accumulator (lane = pixel) into them as finished fp32 values;
+// phase 2 walks the OUTPUT: for each sub-row ry the 32 pixels of the warp own 32 runs of r*C consecutive floats
+// ([rx][c]; adjacent pixels = adjacent runs), so consecutive lanes take consecutive output words -- 128-bit
+// stores when r*C % 4 == 0, 512 B per warp instruction -- and fetch the values from the staging tile through a
+// [ry][rx*C+c] -> channel table built once per CTA.  (The first version stored one channel of 32 pixels per
+// instruction -- 32 sectors for 128 useful bytes -- and was 4-6x slower than not fusing at all.)
+constexpr int kShuffleStageRow = 512;
+constexpr int kShuffleStageBytes = 4 * 32 * kShuffleStageRow + 128 * 4;   // 4 warps + the channel table
+
+__device__ __forceinline__ void shuffle_table_init(const ConvKernelParams& P, int* tbl, int tid, int nthreads) {
+  const int r_ = P.shuffle_r, C_ = P.shuffle_C, RC = r_ * C_, rr = r_ * r_;
+  for (int i = tid; i < P.cout; i += nthreads) {
+    const int ry = i / RC, k = i - ry * RC, rx = k / C_, cc = k - rx * C_;
+    tbl[i] = P.shuffle_order == 0 ? cc * rr + rx * r_ + ry
+           : P.shuffle_order == 1 ? cc * rr + ry * r_ + rx : (ry * r_ + rx) * C_ + cc;
+  }
+}
+
 __device__ __noinline__ void epilogue_shuffle_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
-                                                  int f_base, const float* s_bias, int lane, bool live) {
+                                                  int f_base, uint8_t* stage, const int* tbl, const float* s_bias,
+                                                  int lane, bool live) {
   const int f = f_base + lane;
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
   const int xx = f - fr * P.PWs - P.p;
   const bool valid = live && (f - (P.p * P.PWs + P.p) < P.f_len) && yy < P.Hc && xx >= 0 &&
                      xx < P.BW && (c.seg_x0 + xx) < P.Wc;
-  const int r_ = P.shuffle_r, C_ = P.shuffle_C;
-  const int x = c.seg_x0 + xx;
-  const size_t orow = (size_t)P.W * r_;
+  const int r_ = P.shuffle_r, RC = r_ * P.shuffle_C;
+  const int my_row = valid ? c.n * P.H + yy : -1;   // image row index n*H + y of this lane's pixel
+  const int my_x = c.seg_x0 + xx;
+  const size_t orow = (size_t)P.W * RC;             // floats per output row
+  uint8_t* my_srow = stage + lane * kShuffleStageRow;
+  const int sw = lane & 7;
+  // ---- phase 1: same rounding as the staged epilogues (accumulator -> bf16, then alpha / bias / ReLU in fp32)
+  const float lo = P.relu ? 0.f : -3.4e38f;
 #pragma unroll 1
   for (int cb = 0; cb < 4; ++cb) {
+    if (cb * 32 >= P.cout) break;
     uint32_t v[32];
     tmem_ld32(t_acc + cb * 32, v);
     tmem_ld_wait();
-    if (!valid) continue;
-#pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      const int ch = cb * 32 + j;
-      if (ch >= P.cout) break;
-      // same rounding as the staged epilogues: accumulator -> bf16, then alpha / bias / ReLU in fp32
-      float o = fmaf(P.alpha, __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))), P.alpha * s_bias[ch]);
-      if (P.relu) o = fmaxf(o, 0.f);
-      int cc, ry, rx;
-      if (P.shuffle_order == 0) { cc = ch / (r_ * r_); rx = (ch / r_) % r_; ry = ch % r_; }
-      else if (P.shuffle_order == 1) { cc = ch / (r_ * r_); ry = (ch / r_) % r_; rx = ch % r_; }
-      else { cc = ch % C_; ry = (ch / C_) / r_; rx = (ch / C_) % r_; }
-      P.out_f32[(((size_t)c.n * P.H * r_ + (yy * r_ + ry)) * orow + (x * r_ + rx)) * C_ + cc] = o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = fmaxf(fmaf(P.alpha, __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[4 * j + e]))),
+                          P.alpha * s_bias[cb * 32 + 4 * j + e]), lo);
+      *reinterpret_cast<float4*>(my_srow + (((cb * 8 + j) ^ sw) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
+  __syncwarp();
+  // ---- phase 2
+  auto fetch = [&](uint32_t p, int ch) {
+    return *reinterpret_cast<const float*>(stage + p * kShuffleStageRow + ((((uint32_t)ch >> 2) ^ (p & 7u)) << 4) +
+                                           ((ch & 3) << 2));
+  };
+  if ((RC & 3) == 0) {
+    const uint32_t G = (uint32_t)RC >> 2;            // float4 groups per pixel run
+    const uint32_t q32 = 32u / G, r32 = 32u % G;
+    const uint32_t p0 = (uint32_t)lane / G, g0 = (uint32_t)lane % G;
+#pragma unroll 1
+    for (int ry = 0; ry < r_; ++ry) {
+      const int* t = tbl + ry * RC;
+      uint32_t p = p0, g = g0;
+#pragma unroll 1
+      for (uint32_t it = 0; it < G; ++it) {          // 32*G groups of this sub-row, 32 per iteration
+        const int prow = __shfl_sync(0xffffffffu, my_row, (int)p);
+        const int px = __shfl_sync(0xffffffffu, my_x, (int)p);
+        if (prow >= 0) {
+          const int4 ch = *reinterpret_cast<const int4*>(t + 4 * g);
+          const float4 o = make_float4(fetch(p, ch.x), fetch(p, ch.y), fetch(p, ch.z), fetch(p, ch.w));
+          *reinterpret_cast<float4*>(P.out_f32 + ((size_t)prow * r_ + ry) * orow + (size_t)px * RC + 4 * g) = o;
+        }
+        p += q32;
+        g += r32;
+        if (g >= G) { g -= G; ++p; }
+      }
+    }
+  } else {
+    const uint32_t q32 = 32u / (uint32_t)RC, r32 = 32u % (uint32_t)RC;
+    const uint32_t p0 = (uint32_t)lane / (uint32_t)RC, k0 = (uint32_t)lane % (uint32_t)RC;
+#pragma unroll 1
+    for (int ry = 0; ry < r_; ++ry) {
+      const int* t = tbl + ry * RC;
+      uint32_t p = p0, k = k0;
+#pragma unroll 1
+      for (int it = 0; it < RC; ++it) {
+        const int prow = __shfl_sync(0xffffffffu, my_row, (int)p);
+        const int px = __shfl_sync(0xffffffffu, my_x, (int)p);
+        if (prow >= 0) P.out_f32[((size_t)prow * r_ + ry) * orow + (size_t)px * RC + k] = fetch(p, t[k]);
+        p += q32;
+        k += r32;
+        if (k >= (uint32_t)RC) { k -= RC; ++p; }
+      }
+    }
+  }
+  __syncwarp();  // the next accumulator overwrites the staging rows
 }
 
 // Lean epilogue for the commonest launch (conv + bias + ReLU -> bf16, no residual / mask / fp32 copy): small code
@@ -457,11 +525,15 @@ __device__ __forceinline__ void epilogue_staged_acc_tf32(const ConvKernelParams&
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
-                                             int f_base, uint8_t* stage, const float* s_bias, int lane,
+                                             int f_base, uint8_t* stage_buf, int ew, const float* s_bias, int lane,
                                              bool live = true) {
+  // per-warp staging tile: 32 rows x 256 B (512 B in the sub-pixel variant, whose channel table follows the tiles)
+  uint8_t* stage = stage_buf + ew * (32 * (EPI == 4 ? kShuffleStageRow : 256));
   if constexpr (EPI < 0) epilogue_staged_acc_generic(P, c, t_acc, f_base, stage, s_bias, lane, live);
   else if constexpr (EPI == 0) epilogue_staged_acc_plain(P, c, t_acc, f_base, stage, s_bias, lane, live);
-  else if constexpr (EPI == 4) epilogue_shuffle_acc(P, c, t_acc, f_base, s_bias, lane, live);
+  else if constexpr (EPI == 4)
+    epilogue_shuffle_acc(P, c, t_acc, f_base, stage, reinterpret_cast<const int*>(stage_buf + 4 * 32 * kShuffleStageRow),
+                         s_bias, lane, live);
   else if constexpr (EPI == 5) epilogue_staged_acc_tf32(P, c, t_acc, f_base, stage, s_bias, lane, live);
   else epilogue_staged_acc<EPI>(P, c, t_acc, f_base, stage, s_bias, lane, live);
 }
@@ -492,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
   uint8_t* a_buf = smem;
   uint8_t* w_buf = smem + 2 * P.a_bytes;
-  constexpr int STAGE_BYTES = (N_ == 128) ? 4 * 32 * 256 : 0;  // epilogue staging: 32 rows x 256 B per warp
+  constexpr int STAGE_BYTES = N_ != 128 ? 0 : EPI == 4 ? kShuffleStageBytes : 4 * 32 * 256;  // epilogue staging: 32 rows x 256 B per warp
   uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
   ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + STAGE_BYTES);
   float* s_bias = reinterpret_cast<float*>(bars + 1);
@@ -530,6 +602,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (threadIdx.x >= 128) {
     for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
+    if constexpr (EPI == 4)
+      shuffle_table_init(P, reinterpret_cast<int*>(stage_buf + 4 * 32 * kShuffleStageRow), threadIdx.x - 128, 128);
   }
   tc_fence_before();
   __syncthreads();
@@ -671,8 +745,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
         if constexpr (N_ == 128) {
-          epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
-                            stage_buf + ew * (32 * 256), s_bias, lane);
+          epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane);
         } else {
           const int f = c.f0 + acc * 128 + ew * 32 + lane;
           const int fr = f / P.PWs;
@@ -742,7 +815,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint8_t* a_buf = smem;
   uint8_t* w_buf = smem + 2 * P.a_bytes;
   uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
-  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + 4 * 32 * 256);
+  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + (EPI == 4 ? kShuffleStageBytes : 4 * 32 * 256));
   float* s_bias = reinterpret_cast<float*>(bars + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -782,7 +855,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tmem_relinquish_pair();
   }
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
+    if constexpr (EPI == 4)
+      shuffle_table_init(P, reinterpret_cast<int*>(stage_buf + 4 * 32 * kShuffleStageRow), threadIdx.x - 128, 128);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -926,8 +1001,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc)
-        epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32,
-                          stage_buf + ew * (32 * 256), s_bias, lane, live);
+        epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane, live);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
@@ -1163,7 +1237,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.W = d->W;
   P.NB = d->NB;
   P.p = p;
-  const int stage_bytes = pl->n_pad == 128 ? 4 * 32 * 256 : 0;
+  const int stage_bytes = pl->n_pad != 128 ? 0 : d->shuffle_r > 0 ? kShuffleStageBytes : 4 * 32 * 256;
   if ((double)d->NB * d->H * d->W >= 2147483647.0) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "more than 2^31 pixels per tensor");

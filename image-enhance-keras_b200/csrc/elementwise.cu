@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "internal.h"
@@ -397,6 +398,75 @@ __global__ void depth_to_space_kernel(const float* __restrict__ in, int NB, int 
   }
 }
 
+// Staged version (the one sr_depth_to_space launches): a block takes PIX consecutive input pixels of one row --
+// PIX*C*r*r contiguous floats, read with full-width coalesced loads into shared memory (pixel pitch padded to an odd
+// word count so the permuted reads spread over the banks) -- and writes the r output rows they map to, each a
+// contiguous run of PIX*r*C floats, with 128-bit stores.  Every DRAM sector is read once and written once; the
+// permutation itself happens in shared memory through a [ry][rx*C+c] -> input-channel table.
+__global__ void __launch_bounds__(256)
+depth_to_space_tiled_kernel(const float* __restrict__ in, int NB, int H, int W, int C, int r, int order, int PIX,
+                            float* __restrict__ out) {
+  extern __shared__ float d2s_smem[];
+  const int Cin = C * r * r, RC = r * C, pitch = Cin | 1;
+  float* tile = d2s_smem;                                        // [PIX][pitch]
+  int* tbl = reinterpret_cast<int*>(d2s_smem + (size_t)PIX * pitch);  // [r][RC]
+  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+    const int ry = i / RC, k = i - ry * RC, rx = k / C, c = k - rx * C;
+    tbl[i] = order == 0 ? c * r * r + rx * r + ry : order == 1 ? c * r * r + ry * r + rx : (ry * r + rx) * C + c;
+  }
+  const int strips_per_row = (W + PIX - 1) / PIX;
+  const size_t n_strips = (size_t)NB * H * strips_per_row;
+  const size_t orow = (size_t)W * RC;                            // floats per output row
+  for (size_t sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x) {
+    const int sx = (int)(sidx % strips_per_row);
+    const size_t row = sidx / strips_per_row;                    // n*H + y
+    const int x0 = sx * PIX, npx = min(PIX, W - x0);
+    const float* src = in + (row * W + x0) * Cin;
+    const int nin = npx * Cin;
+    __syncthreads();                                             // previous strip fully written out (and tbl ready)
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (nin & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < nin; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        int px = i / Cin, ch = i - px * Cin;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          tile[px * pitch + ch] = vv[e];
+          if (++ch == Cin) { ch = 0; ++px; }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < nin; i += blockDim.x) {
+        const int px = i / Cin;
+        tile[px * pitch + (i - px * Cin)] = src[i];
+      }
+    }
+    __syncthreads();
+    const int nout = npx * RC;                                   // floats per output row of this strip
+    for (int ry = 0; ry < r; ++ry) {
+      float* dst = out + (row * r + ry) * orow + (size_t)x0 * RC;
+      const int* t = tbl + ry * RC;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nout & 3) == 0) {
+        for (int i = threadIdx.x * 4; i < nout; i += blockDim.x * 4) {
+          int px = i / RC, k = i - px * RC;
+          float vv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            vv[e] = tile[px * pitch + t[k]];
+            if (++k == RC) { k = 0; ++px; }
+          }
+          *reinterpret_cast<float4*>(dst + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+      } else {
+        for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+          const int px = i / RC;
+          dst[i] = tile[px * pitch + t[i - px * RC]];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ weight repack
 // HWIO fp32 [k*k][128][cout] -> bf16 [chunk][tap][n_pad][32]
 __global__ void pack_weights_kernel(const float* __restrict__ hwio, int ntaps, int cout, int n_pad,
@@ -757,6 +827,17 @@ extern "C" int sr_depth_to_space(const float* in, int NB, int H, int W, int C, i
   if (r < 1 || C < 1 || order < 0 || order > 2) return set_error(SR_ERR_INVALID, "sr_depth_to_space: bad r/C/order");
   const size_t total = (size_t)NB * H * r * W * r * C;
   if (total == 0) return SR_OK;
+  const int Cin = C * r * r, pitch = Cin | 1;
+  if ((size_t)pitch * 4 + (size_t)Cin * 4 <= 40 * 1024) {
+    // strips of <= ~24 KB of input: several blocks per SM keep loads and stores of different strips in flight
+    int PIX = (int)std::min<size_t>((size_t)W, std::max<size_t>(1, (24 * 1024) / ((size_t)pitch * 4)));
+    if (PIX >= 4) PIX &= ~3;
+    const size_t smem = (size_t)PIX * pitch * 4 + (size_t)Cin * 4;
+    const size_t n_strips = (size_t)NB * H * ((W + PIX - 1) / PIX);
+    depth_to_space_tiled_kernel<<<(unsigned)std::min<size_t>(n_strips, 148 * 8), kBlock, smem, as_stream(stream)>>>(
+        in, NB, H, W, C, r, order, PIX, out);
+    return check_launch("depth_to_space_tiled_kernel");
+  }
   depth_to_space_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
       in, NB, H, W, C, r, order, out);
   return check_launch("depth_to_space_kernel");

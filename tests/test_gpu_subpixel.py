@@ -55,7 +55,8 @@ def test_subpixel_layer_fused_conv_shuffle(padding, act):
     assert cfg["r"] == 2 and cfg["filters"] == 3 and "rank" not in cfg and "dilation_rate" not in cfg
 
 
-@pytest.mark.parametrize("k,r,C,order", [(3, 4, 3, 0), (5, 2, 8, 1), (3, 2, 32, 2), (1, 4, 8, 0)])
+@pytest.mark.parametrize("k,r,C,order", [(3, 4, 3, 0), (5, 2, 8, 1), (3, 2, 32, 2), (1, 4, 8, 0),
+                                         (3, 3, 3, 0), (3, 2, 5, 2), (5, 3, 11, 1)])   # r*C % 4 != 0: scalar stores
 def test_tensor_core_conv_with_fused_shuffle(k, r, C, order):
     """128-channel bf16 input: the tcgen05 conv stores straight to the depth-to-space position.  Bit-identical to the
     same kernel's unfused output followed by the shuffle kernel, and equal to the oracle conv within fp32 rounding."""

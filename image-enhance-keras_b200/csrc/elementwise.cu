@@ -258,20 +258,85 @@ __global__ void patch_gather_vec4_kernel(const void* __restrict__ src, int h, in
   }
 }
 
+// The production gather (uint8 source, 3*pw % 4 == 0): one warp per patch row, any number of same-shaped images per
+// launch (image m's patches follow image m-1's).  The row's coordinates are computed once per warp, the lanes
+// then cover the row in 16-byte stores (512 B per warp instruction); value / divisor comes from a 256-entry table
+// built per block with the same correctly rounded fp32 division, so results are bit-identical to the scalar kernel.
+// (The flat-index kernels above spend ~250 instructions per 16 bytes on 64-bit div/mod and four fp32 divisions:
+// instruction-bound at ~2 TB/s.)
+__global__ void __launch_bounds__(256)
+patch_gather_u8_rows_kernel(const uint8_t* __restrict__ imgs, int n_img, size_t img_stride, int h, int w,
+                            int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,
+                            float4* __restrict__ out) {
+  // One block per patch (grid-stride): the patch's coordinates are computed once, its ph * (3*pw/4) 16-byte
+  // groups are then walked by all 256 threads with an incrementally updated (row, group) pair -- no division in
+  // the loop, every lane busy, two groups per thread per trip so eight byte loads are in flight before the stores.
+  __shared__ float lut[256];
+  lut[threadIdx.x] = divisor == 1.f ? (float)threadIdx.x : __fdiv_rn((float)threadIdx.x, divisor);
+  __syncthreads();
+  const int row_q = pw * 3 / 4, w3 = w * 3;
+  const int patch_q = ph * row_q;
+  const unsigned per_img = (unsigned)cnt_h * cnt_w, total = per_img * (unsigned)n_img;
+  const int di = 256 / row_q, dq = 256 % row_q;               // +256 groups in (row, group) coordinates
+  for (unsigned pidx = blockIdx.x; pidx < total; pidx += gridDim.x) {
+    const unsigned m = pidx / per_img, n = pidx - m * per_img;
+    const unsigned wi = n / (unsigned)cnt_h, hi = n - wi * (unsigned)cnt_h;
+    const int y0 = (int)(hi * step), e_row = (int)(wi * step) * 3;
+    const uint8_t* img = imgs + (size_t)m * img_stride;
+    float4* dst = out + (size_t)pidx * patch_q;
+    int i0 = (int)threadIdx.x / row_q, q0 = (int)threadIdx.x % row_q;
+    for (int g = threadIdx.x; g < patch_q; g += 512) {
+      int i1 = i0 + di, q1 = q0 + dq;
+      if (q1 >= row_q) { q1 -= row_q; ++i1; }
+      const bool has1 = g + 256 < patch_q;
+      uint8_t b0[4], b1[4];
+      {
+        const int y = y0 + i0, e0 = e_row + q0 * 4;
+        const uint8_t* src = img + (size_t)y * w3 + e0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b0[j] = (y < h && e0 + j < w3) ? src[j] : (uint8_t)0;
+      }
+      {
+        const int y = y0 + i1, e0 = e_row + q1 * 4;
+        const uint8_t* src = img + (size_t)y * w3 + e0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b1[j] = (has1 && y < h && e0 + j < w3) ? src[j] : (uint8_t)0;
+      }
+      dst[g] = make_float4(lut[b0[0]], lut[b0[1]], lut[b0[2]], lut[b0[3]]);
+      if (has1) dst[g + 256] = make_float4(lut[b1[0]], lut[b1[1]], lut[b1[2]], lut[b1[3]]);
+      i0 = i1 + di;
+      q0 = q1 + dq;
+      if (q0 >= row_q) { q0 -= row_q; ++i0; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ minibatch assembly from an HBM-resident dataset
 // Reference: img_utils.image_generator (img_utils.py:341-372): batch[i] = imread(file[index[i]]).astype('float32')/255.
 // The decoded uint8 images live in HBM ([N][item_bytes]); one launch gathers the rows named by `index` and
 // normalises them.  Four bytes per thread: one 4-byte load, one 16-byte store.
-__global__ void batch_gather_u8_kernel(const uint8_t* __restrict__ data, size_t item_bytes,
-                                       const long long* __restrict__ index, int n, float divisor,
-                                       float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+batch_gather_u8_kernel(const uint8_t* __restrict__ data, size_t item_bytes,
+                       const long long* __restrict__ index, int n, float divisor,
+                       float* __restrict__ out) {
+  __shared__ float lut[256];   // v / divisor for every uint8 v (correctly rounded, as the per-element division was)
+  lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, divisor);
+  __syncthreads();
   const size_t q = item_bytes >> 2;  // uchar4 groups per item
   const size_t total = (size_t)n * q;
+  if (total < 0x7fffffffu) {         // 32-bit index arithmetic (64-bit div/mod costs more than the copy)
+    const unsigned q32 = (unsigned)q, tot32 = (unsigned)total;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot32; i += gridDim.x * blockDim.x) {
+      const unsigned b = i / q32, e = i - b * q32;
+      const uchar4 v = reinterpret_cast<const uchar4*>(data + (size_t)index[b] * item_bytes)[e];
+      reinterpret_cast<float4*>(out)[i] = make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]);
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / q, e = i - b * q;
     const uchar4 v = reinterpret_cast<const uchar4*>(data + (size_t)index[b] * item_bytes)[e];
-    reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn((float)v.x, divisor), __fdiv_rn((float)v.y, divisor),
-                                                    __fdiv_rn((float)v.z, divisor), __fdiv_rn((float)v.w, divisor));
+    reinterpret_cast<float4*>(out)[i] = make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]);
   }
 }
 // Reference: img_utils.rebuild_from_patches_Step (img_utils.py:692-724).  Per axis the owner of
@@ -753,22 +818,34 @@ extern "C" int sr_canvas_size(int h, int w, int patch, int step, int* canvas_h, 
   return SR_OK;
 }
 
-extern "C" int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h, int canvas_w, int ph,
-                                  int pw, int step, float divisor, float* out_f32, void* stream) {
-  if (!img || !out_f32) return set_error(SR_ERR_INVALID, "sr_patch_gather_u8: null pointer");
+extern "C" int sr_patch_gather_u8_batched(const uint8_t* imgs, int n_img, size_t img_stride, int h, int w,
+                                          int canvas_h, int canvas_w, int ph, int pw, int step, float divisor,
+                                          float* out_f32, void* stream) {
+  if (!imgs || !out_f32) return set_error(SR_ERR_INVALID, "sr_patch_gather_u8: null pointer");
+  if (n_img < 1 || h < 1 || w < 1 || step < 1 || divisor == 0.f) return set_error(SR_ERR_INVALID, "sr_patch_gather_u8: bad size");
   if (ph > canvas_h) return set_error(SR_ERR_INVALID, "Height of the patch should be less than the height of the image.");
   if (pw > canvas_w) return set_error(SR_ERR_INVALID, "Width of the patch should be less than the width of the image.");
   const int cnt_h = sr_patch_count(canvas_h, ph, step), cnt_w = sr_patch_count(canvas_w, pw, step);
-  const size_t total = (size_t)cnt_h * cnt_w * ph * pw * 3;
-  if (total == 0) return SR_OK;
-  if ((pw * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) {
-    patch_gather_vec4_kernel<true><<<grid_for(total / 4, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
-        img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, reinterpret_cast<float4*>(out_f32));
-    return check_launch("patch_gather_vec4_kernel<u8>");
+  const size_t per_img = (size_t)cnt_h * cnt_w * ph * pw * 3;
+  if (per_img == 0) return SR_OK;
+  const size_t n_patches = (size_t)n_img * cnt_h * cnt_w;
+  if ((pw * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && n_patches < 0x7fffffffu) {
+    patch_gather_u8_rows_kernel<<<grid_for(n_patches, 1, 148 * 8), kBlock, 0, as_stream(stream)>>>(
+        imgs, n_img, img_stride, h, w, cnt_h, cnt_w, ph, pw, step, divisor, reinterpret_cast<float4*>(out_f32));
+    return check_launch("patch_gather_u8_rows_kernel");
   }
-  patch_gather_kernel<true><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
-      img, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, out_f32);
-  return check_launch("patch_gather_kernel<u8>");
+  for (int m = 0; m < n_img; ++m) {     // odd patch widths: the scalar kernel, one image per launch
+    patch_gather_kernel<true><<<grid_for(per_img, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+        imgs + (size_t)m * img_stride, h, w, canvas_w, cnt_h, cnt_w, ph, pw, step, divisor, out_f32 + (size_t)m * per_img);
+    const int rc = check_launch("patch_gather_kernel<u8>");
+    if (rc != SR_OK) return rc;
+  }
+  return SR_OK;
+}
+
+extern "C" int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h, int canvas_w, int ph,
+                                  int pw, int step, float divisor, float* out_f32, void* stream) {
+  return sr_patch_gather_u8_batched(img, 1, 0, h, w, canvas_h, canvas_w, ph, pw, step, divisor, out_f32, stream);
 }
 
 extern "C" int sr_batch_gather_u8(const uint8_t* data, size_t item_bytes, size_t n_items, const long long* index,

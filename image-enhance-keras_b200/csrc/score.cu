@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) score_pair_kernel(const uint8_t* __restri
   __shared__ double pa[kHalo * kHalo];
   __shared__ double pb[kHalo * kHalo];
   __shared__ double red[32];
+  __shared__ double lut[256];   // v / 255.0 for every uint8 v: the correctly rounded quotients img_as_float produces
+  lut[threadIdx.x] = (double)threadIdx.x / 255.0;
   const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;  // cropped size
   const int wy0 = blockIdx.y * kTile, wx0 = blockIdx.x * kTile;  // first window (top-left) of the block
   const int nwy = ch_ - kWin + 1, nwx = cw_ - kWin + 1;          // number of valid windows per axis
@@ -57,8 +59,9 @@ __global__ void __launch_bounds__(256) score_pair_kernel(const uint8_t* __restri
       if (y < ch_ && x < cw_) {
         const size_t o = ((size_t)(y + crop) * w + (x + crop)) * 3;
         if (plane == 0) {
-          va = y_from_rgb(a[o], a[o + 1], a[o + 2]);
-          vb = y_from_rgb(b[o], b[o + 1], b[o + 2]);
+          // same operations in the same order as y_from_rgb, the three divisions looked up
+          va = (lut[a[o]] * 65.481 + lut[a[o + 1]] * 128.553 + lut[a[o + 2]] * 24.966) + 16.0;
+          vb = (lut[b[o]] * 65.481 + lut[b[o + 1]] * 128.553 + lut[b[o + 2]] * 24.966) + 16.0;
           // squared error: every cropped pixel is owned by exactly one block (its tile interior)
           if (ly < kTile && lx < kTile) {
             const double d = va - vb;
@@ -138,8 +141,10 @@ __global__ void __launch_bounds__(256) score_pair_kernel(const uint8_t* __restri
 #pragma unroll
       for (int wv = 0; wv < 4; ++wv) {
         if (wy0 + ly0 + wv >= nwy || wx0 + lx >= nwx) continue;
-        const double ux = acc[wv][0] / 49.0, uy = acc[wv][1] / 49.0;
-        const double uxx = acc[wv][2] / 49.0, uyy = acc[wv][3] / 49.0, uxy = acc[wv][4] / 49.0;
+        // means by multiplication (fp64 division is ~20 instructions; 1/49 rounded once costs 1e-16 relative)
+        constexpr double inv49 = 1.0 / 49.0;
+        const double ux = acc[wv][0] * inv49, uy = acc[wv][1] * inv49;
+        const double uxx = acc[wv][2] * inv49, uyy = acc[wv][3] * inv49, uxy = acc[wv][4] * inv49;
         const double vx = cov_norm * (uxx - ux * ux);
         const double vy = cov_norm * (uyy - uy * uy);
         const double vxy = cov_norm * (uxy - ux * uy);

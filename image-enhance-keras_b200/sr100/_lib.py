@@ -116,6 +116,7 @@ SIGNATURES = {
     "sr_patch_count": (_i, [_i, _i, _i]),
     "sr_canvas_size": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "sr_patch_gather_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "sr_patch_gather_u8_batched": (_i, [_vp, _i, _sz, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "sr_batch_gather_u8": (_i, [_vp, _sz, _sz, _vp, _i, _f, _vp, _vp]),
     "sr_patch_down4_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_longlong, C.c_longlong, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "sr_patch_average_accumulate": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),

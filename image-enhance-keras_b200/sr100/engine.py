@@ -540,21 +540,33 @@ class Engine:
         entirely in the zero padding are not run, and the HR stage runs on the 272x272 corner of each patch that
         the stitch can see (hr_extent).  Both give bit-identical pixels inside the final image."""
         from . import ops
-        metas, parts, extents = [], [], []
+        metas, extents, total = [], [], 0
         for img in imgs_u8:
             h, w, _ = img.shape
             (gh, gw), counts, ext = plan_tiles(h, w, patch, step, scale, full_canvas)
             ch, cw = ops.canvas_size(h, w, patch, step)
-            p, got = ops.patch_gather_u8(img, (gh, gw), (patch, patch), step, divisor=255.0)
-            assert got == counts
-            metas.append((h, w, ch, cw, counts, p.shape[0]))
-            parts.append(p)
+            n = counts[0] * counts[1]
+            metas.append((h, w, ch, cw, counts, n, (gh, gw)))
+            total += n
             if not full_canvas:
                 extents.extend(ext)
-        allp = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+        # gather straight into one patch tensor; runs of same-shaped images (a batch, BASELINE config 3) go in one launch
+        allp = torch.empty(total, patch, patch, 3, device=self.device, dtype=torch.float32)
+        i, off = 0, 0
+        while i < len(imgs_u8):
+            j = i + 1
+            while j < len(imgs_u8) and imgs_u8[j].shape == imgs_u8[i].shape:
+                j += 1
+            n, g = metas[i][5], metas[i][6]
+            batch = imgs_u8[i].unsqueeze(0) if j - i == 1 else torch.stack(imgs_u8[i:j])
+            _, got = ops.patch_gather_u8_batched(batch.contiguous(), g, (patch, patch), step, divisor=255.0,
+                                                 out=allp[off:off + (j - i) * n])
+            assert got == metas[i][4]
+            off += (j - i) * n
+            i = j
         out = self.forward_device(allp, extents=None if full_canvas else extents)
         res, off = [], 0
-        for h, w, ch, cw, counts, n in metas:
+        for h, w, ch, cw, counts, n, _ in metas:
             oh, ow = (ch, cw) if full_canvas else (h, w)
             _, u8 = ops.patch_stitch(out[off:off + n], counts, (patch, patch), step, scale, (oh, ow), mul=255.0,
                                      want_f32=False, want_u8=True)

@@ -65,6 +65,21 @@ def patch_gather_u8(img_u8, canvas_hw, patch, step, divisor=255.0):
     return out, (cnt_h, cnt_w)
 
 
+def patch_gather_u8_batched(imgs_u8, canvas_hw, patch, step, divisor=255.0, out=None):
+    """uint8 [M,h,w,3] device batch of same-shaped images -> fp32 patches [M*N,p,p,3] in one launch (image m's N
+    patches follow image m-1's); `out` may be a preallocated slice to fill."""
+    lib = L.require_device()
+    m, h, w, _ = imgs_u8.shape
+    ch, cw = canvas_hw
+    ph, pw = patch
+    cnt_h, cnt_w = patch_count(ch, ph, step), patch_count(cw, pw, step)
+    if out is None:
+        out = torch.empty(m * cnt_h * cnt_w, ph, pw, 3, device=imgs_u8.device, dtype=torch.float32)
+    L.check(lib.sr_patch_gather_u8_batched(L.ptr(imgs_u8), m, imgs_u8.stride(0), h, w, ch, cw, ph, pw, step,
+                                           float(divisor), L.ptr(out), L.stream_ptr()))
+    return out, (cnt_h, cnt_w)
+
+
 def patch_gather_f32(canvas_f32, patch, step):
     """fp32 [H,W,3] device canvas -> fp32 patches (img_utils.extract_patches_Step, img_utils.py:601-676)."""
     lib = L.require_device()

@@ -182,6 +182,11 @@ int sr_canvas_size(int h, int w, int patch, int step, int* canvas_h, int* canvas
  * by `divisor` in fp32 (1 -> the reference's 0..255 patches; 255 -> the /255. of models.py:336). */
 int sr_patch_gather_u8(const uint8_t* img, int h, int w, int canvas_h, int canvas_w, int ph, int pw,
                        int step, float divisor, float* out_f32, void* stream);
+/* The same gather for n_img images of one shape in ONE launch (a batch of equal-sized inputs, BASELINE config 3):
+ * image m starts img_stride bytes after image m-1, its patches follow those of image m-1 in out_f32. */
+int sr_patch_gather_u8_batched(const uint8_t* imgs, int n_img, size_t img_stride, int h, int w,
+                               int canvas_h, int canvas_w, int ph, int pw, int step, float divisor,
+                               float* out_f32, void* stream);
 /* Generic gather from a float64/float32 canvas (API parity with the numpy function). */
 int sr_patch_gather_f32(const float* canvas, int canvas_h, int canvas_w, int ph, int pw, int step,
                         float* out_f32, void* stream);

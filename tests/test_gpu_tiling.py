@@ -123,3 +123,28 @@ def test_upscale_step_patch_end_to_end(tmp_path):
     assert d.max() <= 1                                          # truncation may flip one LSB near integers
     assert (d > 0).mean() < 0.2
     assert np.abs(full.astype(int) - want_full.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("shape,patch,step,divisor", [((5, 70, 45), 96, 64, 255.0), ((3, 339, 510), 96, 64, 255.0),
+                                                      ((2, 50, 61), 32, 16, 1.0), ((2, 40, 40), 17, 8, 255.0)])
+def test_batched_gather_equals_per_image_gather_and_oracle(shape, patch, step, divisor):
+    """One launch for a batch of same-shaped images (BASELINE config 3) == the per-image gathers, which are the
+    reference's extract_patches_Step on the zero-padded canvas (bit-exact; 17-px patches take the scalar kernel)."""
+    import torch
+    from oracle import tiling as ot
+    from sr100 import ops
+    rng = np.random.default_rng(shape[1])
+    imgs = rng.integers(0, 256, size=shape + (3,)).astype(np.uint8)
+    ch, cw = ops.canvas_size(shape[1], shape[2], patch, step)
+    dev = torch.from_numpy(imgs).cuda()
+    got, counts = ops.patch_gather_u8_batched(dev, (ch, cw), (patch, patch), step, divisor=divisor)
+    n = counts[0] * counts[1]
+    assert got.shape == (shape[0] * n, patch, patch, 3)
+    for m in range(shape[0]):
+        one, c1 = ops.patch_gather_u8(dev[m], (ch, cw), (patch, patch), step, divisor=divisor)
+        assert c1 == counts and torch.equal(one, got[m * n:(m + 1) * n])
+        canvas = np.zeros((ch, cw, 3), dtype=np.float64)
+        canvas[:shape[1], :shape[2]] = imgs[m]
+        want, wc = ot.extract_patches_step(canvas, (patch, patch), step)
+        assert tuple(wc) == tuple(counts)
+        assert np.array_equal(got[m * n:(m + 1) * n].cpu().numpy(), (want.astype(np.float32) / np.float32(divisor)))

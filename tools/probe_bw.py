@@ -84,6 +84,12 @@ def main():
             ops.patch_gather_u8(im, (ch, cw), (96, 96), 64)
     timed("patch_gather_kernel<u8> x8 images", 8 * (339 * 510 * 3 + 54 * 96 * 96 * 3 * 4), gather_all,
           "8 launches of 339x510 -> 54 tiles; includes the output allocation")
+    batch = torch.randint(0, 256, (64, 339, 510, 3), dtype=torch.uint8, device=dev)
+    bout64 = torch.empty(64 * 54, 96, 96, 3, device=dev)
+    timed("patch_gather_u8_rows_kernel (64 x 339x510, one launch)", 64 * (339 * 510 * 3 + 54 * 96 * 96 * 3 * 4),
+          lambda: ops.patch_gather_u8_batched(batch, (ch, cw), (96, 96), 64, out=bout64),
+          "config 3: 64 images -> 3456 tiles in one launch, preallocated output")
+    del batch, bout64
     # ---- stitch + quantise: 54 tiles of 384x384x3 fp32 -> uint8 canvas (owned pixels only are compulsory)
     outp = torch.rand(54, 384, 384, 3, device=dev)
     cnt = (ops.patch_count(ch, 96, 64), ops.patch_count(cw, 96, 64))
@@ -93,7 +99,7 @@ def main():
     # ---- the same two kernels at config-5 size (one 1080x1920 image, 558 tiles): enough bytes to leave launch latency
     big = torch.randint(0, 256, (1080, 1920, 3), dtype=torch.uint8, device=dev)
     bch, bcw = ops.canvas_size(1080, 1920)
-    timed("patch_gather_vec4_kernel (1080x1920)", 1080 * 1920 * 3 + 558 * 96 * 96 * 3 * 4,
+    timed("patch_gather_u8_rows_kernel (1080x1920)", 1080 * 1920 * 3 + 558 * 96 * 96 * 3 * 4,
           lambda: ops.patch_gather_u8(big, (bch, bcw), (96, 96), 64), "558 tiles; includes the output allocation")
     bout = torch.rand(558, 384, 384, 3, device=dev)
     bcnt = (ops.patch_count(bch, 96, 64), ops.patch_count(bcw, 96, 64))

@@ -64,6 +64,58 @@ def rebuild_from_patches_Step(img_initial, patches, patch_size, tupleinit, scale
     return out.cpu().numpy().astype(np.float64)
 
 
+# ------------------------------------------------------------------ dataset preparation (img_utils.py:44-123)
+def transform_images(directory, output_directory, scaling_factor=2, max_nb_images=-1, true_upscale=False):
+    """img_utils.py:44-123: every image of `directory` -> 256 x 256 (bilinear) -> sharpen -> 256 sub-images of
+    16*scaling_factor px; each is saved as ground truth under <out>/y/ and, blurred (sigma 0.5) + bicubic-shrunk to
+    16 px (+ enlarged again unless true_upscale), under <out>/X/ as '<image index>_<sample index>.png'.
+    The pixel work runs on the device (sr100.dataprep) and reproduces the reference's files bit for bit; decode and
+    PNG encode stay on the host (PIL).  Kept as in the reference: the odd max_nb_images assertion, the early stop
+    `index >= max_nb_images` (one image fewer than asked for), and the y samples being contrast-stretched by imsave."""
+    import time
+    import torch
+    from PIL import Image
+    from sr100 import dataprep
+    index = 1
+    for sub in ("X/", "y/"):
+        if not os.path.exists(output_directory + sub):
+            os.makedirs(output_directory + sub)
+    nb_images = len([name for name in os.listdir(directory)])
+    if max_nb_images != -1:
+        print("Transforming %d images." % max_nb_images)
+    else:
+        assert max_nb_images <= nb_images, "Max number of images must be less than number of images in path"
+        print("Transforming %d images." % (nb_images))
+    if nb_images == 0:
+        print("Extract the training images or images from imageset_91.zip (found in the releases of the project) "
+              "into a directory with the name 'input_images'")
+        print("Extract the validation images or images from set5_validation.zip (found in the releases of the project) "
+              "into a directory with the name 'val_images'")
+        exit()
+    for file in os.listdir(directory):
+        t1 = time.time()
+        img = torch.from_numpy(np.array(_imread_rgb(directory + file), dtype=np.uint8)).cuda()
+        y, x = dataprep.transform_image_device(img, scaling_factor, true_upscale)
+        y, x = y.cpu().numpy(), x.cpu().numpy()
+        for i in range(y.shape[0]):
+            Image.fromarray(y[i]).save(output_directory + "/y/" + "%d_%d.png" % (index, i + 1))
+            Image.fromarray(x[i]).save(output_directory + "/X/" + "%d_%d.png" % (index, i + 1))
+        print("Finished image %d in time %0.2f seconds. (%s)" % (index, time.time() - t1, file))
+        index += 1
+        if max_nb_images > 0 and index >= max_nb_images:
+            print("Transformed maximum number of images. ")
+            break
+    print("Images transformed. Saved at directory : %s" % (output_directory))
+
+
+def subimage_generator(img, stride, patch_size, nb_hr_images):
+    """img_utils.py:134-140."""
+    for _ in range(nb_hr_images):
+        for x in range(0, img_size - patch_size, stride):
+            for y in range(0, img_size - patch_size, stride):
+                yield img[x: x + patch_size, y: y + patch_size, :]
+
+
 # ------------------------------------------------------------------ data pipeline (feeds Model.fit_generator)
 def _listdir_images(d):
     return sorted(f for f in os.listdir(d) if not f.startswith("."))

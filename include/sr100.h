@@ -235,6 +235,28 @@ int sr_patch_average_finalize(const double* sum, const int* count, int out_h, in
                               double* out_f64, uint8_t* out_u8, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dataset preparation.  Replaces the per-image body of img_utils.transform_images (img_utils.py:70-117):
+ * imresize to 256 x 256 (Pillow BILINEAR), scipy.misc.imfilter 'sharpen' (Pillow SHARPEN), 256 sub-images,
+ * per sub-image bytescale (imsave), scipy.ndimage.gaussian_filter(sigma 0.5) over all three axes, bytescale +
+ * Pillow BICUBIC down (and up again).  Everything bit-exact against those libraries.
+ * ------------------------------------------------------------------------------------------ */
+/* Pillow's 8-bit two-pass resize (Resample.c) of NB uint8 [H,W,3] images to [out_h,out_w,3]: horizontal pass into
+ * tmp (uint8 [NB,H,out_w,3]; may be NULL when only one axis changes), then vertical.  bounds_* int32 [out][2] =
+ * (first tap, tap count), kk_* int32 [out][ksize] = filter taps with 22 fractional bits, computed on the host the
+ * way precompute_coeffs / normalize_coeffs_8bpc do (any filter: BILINEAR, BICUBIC ...). */
+int sr_resize_u8(const uint8_t* src, int NB, int H, int W, int out_h, int out_w, const int* bounds_x,
+                 const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y, int ksize_y, uint8_t* tmp,
+                 uint8_t* dst, void* stream);
+/* PIL ImageFilter.SHARPEN = scipy.misc.imfilter(img, 'sharpen') (img_utils.py:75); dst != src. */
+int sr_sharpen3x3_u8(const uint8_t* src, int NB, int H, int W, uint8_t* dst, void* stream);
+/* Sub-images n = 0..n_patches-1 of a uint8 [H,W,3] image, P x P at (row, col) = pos[n] (device int32 [n][2]):
+ * y_u8[n] = bytescale(float64 sample) (what imsave writes, img_utils.py:100); g_u8[n] = bytescale(gaussian_filter(
+ * sample, sigma)) with weights[0..radius] = the normalised kernel from its centre outwards (float64, host-computed
+ * like scipy.ndimage._gaussian_kernel1d), reflect boundaries, all three axes.  P <= 64. */
+int sr_dataprep_patches(const uint8_t* img, int H, int W, const int* pos, int n_patches, int P,
+                        const double* weights, int radius, uint8_t* y_u8, uint8_t* g_u8, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Sub-pixel shuffles.  order 0: keras_subpixel.Subpixel._phase_shift (keras_subpixel.py:64-84)
  * and advanced.depth_to_scale_tf (advanced.py:104-129): ch = c*r*r + (X%r)*r + (Y%r);
  * order 1: advanced.depth_to_scale_th (advanced.py:87-100): ch = c*r*r + (Y%r)*r + (X%r);

@@ -540,6 +540,8 @@ class Engine:
         entirely in the zero padding are not run, and the HR stage runs on the 272x272 corner of each patch that
         the stitch can see (hr_extent).  Both give bit-identical pixels inside the final image."""
         from . import ops
+        if len(imgs_u8) == 0:
+            return []
         metas, extents, total = [], [], 0
         for img in imgs_u8:
             h, w, _ = img.shape

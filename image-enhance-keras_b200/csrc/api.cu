@@ -33,3 +33,17 @@ extern "C" int sr_device_supported(void) {
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10 ? 1 : 0;
 }
+
+// Layout check for bindings: sizeof of the ABI structs as this library was compiled (a binding whose struct
+// declaration fell behind the header would otherwise hand the library a short struct).
+extern "C" size_t sr_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(sr_conv_desc);
+    case 1: return sizeof(sr_conv_plan_info_t);
+    case 2: return sizeof(sr_pack_item);
+    case 3: return sizeof(sr_wgrad_desc);
+    case 4: return sizeof(sr_wgrad_plan_info_t);
+    case 5: return sizeof(sr_score_result);
+    default: return 0;
+  }
+}

@@ -97,6 +97,7 @@ SIGNATURES = {
     "sr_last_error_string": (C.c_char_p, []),
     "sr_version": (_i, []),
     "sr_device_supported": (_i, []),
+    "sr_abi_struct_size": (_sz, [_i]),
     "sr_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "sr_conv_plan_run": (_i, [_vp, _vp]),
     "sr_conv_plan_destroy": (None, [_vp]),
@@ -162,6 +163,11 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for which, struct in enumerate((ConvDesc, ConvPlanInfo, PackItem, WgradDesc, WgradPlanInfo, ScoreResult)):
+        if lib.sr_abi_struct_size(which) != C.sizeof(struct):
+            raise SrError(-1, "%s: ctypes layout (%d bytes) does not match libsr100.so (%d bytes); rebuild the "
+                              "library or update sr100/_lib.py" % (struct.__name__, C.sizeof(struct),
+                                                                   lib.sr_abi_struct_size(which)))
     _lib = lib
     return lib
 

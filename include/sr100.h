@@ -31,6 +31,10 @@ const char* sr_last_error_string(void);
 int sr_version(void);
 /* Returns 1 when the current device is compute capability 10.x (sm_100a cubins can run). */
 int sr_device_supported(void);
+/* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
+ * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
+ * 5 sr_score_result; 0 for anything else. */
+size_t sr_abi_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Convolution (tensor cores).  Replaces keras Conv2D(padding='same') of the DifvdsrDouble stack:

@@ -42,6 +42,20 @@ def test_version_and_error_string(lib):
     assert b"cin" in lib.sr_last_error_string()
 
 
+def test_struct_layouts_match_the_library(lib):
+    from sr100 import _lib as L
+    structs = (L.ConvDesc, L.ConvPlanInfo, L.PackItem, L.WgradDesc, L.WgradPlanInfo, L.ScoreResult)
+    for which, st in enumerate(structs):
+        assert lib.sr_abi_struct_size(which) == C.sizeof(st), st.__name__
+    assert lib.sr_abi_struct_size(99) == 0
+    # the binding stub printed in INTEGRATION.md declares the same sr_conv_desc
+    import re
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = src[src.index("class sr_conv_desc"):src.index("stream = ctypes.c_void_p")]
+    names = re.findall(r'\("(\w+)",', block)
+    assert names == [f[0] for f in L.ConvDesc._fields_]
+
+
 def test_patch_count_and_canvas_match_reference(lib, golden_dir):
     geo = np.load(golden_dir + "/tiling_ref.npz")["geometry_96_64"]
     for h, w, ch, cw, cnt_h, cnt_w in geo.tolist():

@@ -14,7 +14,13 @@
 //     TMA = SAME padding) is loaded once per unit and reused by all taps of the group; a tap (ky,kx) is
 //     the ring row y+ky-p read at a start address shifted by kx pixels (128 B each);
 //   * G rows stream through their own ring; out-of-range columns of the last segment are zero-filled by
-//     TMA and so contribute nothing.
+//     TMA and so contribute nothing;
+//   * the MMA computes the TRANSPOSED tap block D^T[co][ci] (A = G, B = X), because that puts the shifted input on
+//     the N side: two vertically adjacent taps (ky, kx), (ky+1, kx) read ring rows r and r+1 at the same column
+//     shift, and in the ring those are exactly one "64-channel half" stride apart four times over (half 0 / half 1
+//     of row r, half 0 / half 1 of row r+1 -- the descriptor's N-atom stride), so ONE tcgen05.mma of N = 256
+//     accumulates both taps: 12 KB of shared-memory operand reads per 2 taps instead of 16 (the kernel is bound by
+//     exactly that).  A group holds items of 1 or 2 taps; the drain transposes back.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -46,8 +52,13 @@ struct WgradParams {
   int nring, nbslots;
   int ngroups;
   int dbg;              // development switches (SR100_WGRAD_DBG): 1 = no TMA after the first ring fill, 2 = no MMA
-  int g_tap0[kMaxGroups], g_ntaps[kMaxGroups], g_cta0[kMaxGroups], g_ncta[kMaxGroups];
-  float* partial;      // [grid][4][128][128]
+  int g_ntaps[kMaxGroups], g_cta0[kMaxGroups], g_ncta[kMaxGroups];
+  // items of a group: a single tap (w = 1, 128 TMEM columns) or a vertical tap pair (ky, kx), (ky+1, kx) (w = 2,
+  // 256 columns, one N = 256 MMA); col = first 128-column unit of the item in the CTA's TMEM / partial block
+  int g_nitems[kMaxGroups];
+  signed char it_ky[kMaxGroups][4], it_kx[kMaxGroups][4], it_w[kMaxGroups][4], it_col[kMaxGroups][4];
+  signed char tap_group[25], tap_col[25];   // filter tap -> group, 128-column unit (for the reduction)
+  float* partial;      // [grid][4][128 ci][128 co]
 };
 
 struct __align__(8) WgradBarriers {
@@ -59,6 +70,7 @@ struct __align__(8) WgradBarriers {
 
 //   [4,6) c format f32, [7,10) a bf16, [10,13) b bf16, [15] a MN-major, [16] b MN-major, N>>3, M>>4
 constexpr uint32_t kIdescMN = umma_idesc(1u, 128u, 128u) | (1u << 15) | (1u << 16);
+constexpr uint32_t kIdescMN256 = umma_idesc(1u, 128u, 256u) | (1u << 15) | (1u << 16);
 
 }  // namespace
 
@@ -83,8 +95,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if ((int)blockIdx.x >= P.g_cta0[i]) g = i;
   const int rank = (int)blockIdx.x - P.g_cta0[g];
   const int ncta = P.g_ncta[g];
-  const int tap0 = P.g_tap0[g], ntaps = P.g_ntaps[g];
-  const int kymin = tap0 / P.k, kymax = (tap0 + ntaps - 1) / P.k;
+  const int nitems = P.g_nitems[g];
+  int kymin = 99, kymax = -1, ncols = 0;
+  for (int j = 0; j < nitems; ++j) {
+    kymin = min(kymin, (int)P.it_ky[g][j]);
+    kymax = max(kymax, (int)P.it_ky[g][j] + P.it_w[g][j] - 1);
+    ncols += P.it_w[g][j];
+  }
   const int span = kymax - kymin;  // extra input rows per unit
   const int units = P.ngrp * P.nseg * P.nrb;
   const bool has_work = rank < units;
@@ -180,14 +197,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t b_lo0 = (smem_u32(b_buf) >> 4) | (((b_row_bytes / 2) >> 4) << 16);
       const int k16n = P.BW >> 4;
       const uint32_t nring = (uint32_t)P.nring, nbs = (uint32_t)P.nbslots;
-      // per-tap ring-row offset (ky - kymin) and start-address shift (kx pixels x 128 B, >> 4)
-      uint32_t t_row[4], t_sh[4];
+      // per-item ring-row offset (ky - kymin), start-address shift (kx pixels x 128 B, >> 4), width, TMEM column
+      uint32_t t_row[4], t_sh[4], t_w[4], t_col[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int tap = tap0 + (j < ntaps ? j : 0);
-        const int ky = tap / P.k, kx = tap - ky * P.k;
-        t_row[j] = (uint32_t)(ky - kymin);
-        t_sh[j] = (uint32_t)kx * 8u;
+        const int jj = j < nitems ? j : 0;
+        t_row[j] = (uint32_t)(P.it_ky[g][jj] - kymin);
+        t_sh[j] = (uint32_t)P.it_kx[g][jj] * 8u;
+        t_w[j] = (uint32_t)P.it_w[g][jj];
+        t_col[j] = (uint32_t)P.it_col[g][jj] * 128u;
       }
       uint32_t base = 0;                   // ring slot of the oldest live input row (r = yy)
       uint32_t new_slot = 0, new_ph = 0;   // ring position of the next input row to become full
@@ -210,24 +228,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t b_lo = b_lo0 + b_slot * b_row16;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (j < ntaps) {
+            if (j < nitems) {
               uint32_t slot = base + t_row[j];
               if (slot >= nring) slot -= nring;
-              const uint32_t a_tap = a_lo0 + slot * a_row16 + t_sh[j];
-              const uint32_t d = tmem_base + (uint32_t)j * 128u;
-              uint32_t accf = started;
-              for (int im = 0; im < P.NI; ++im) {
-                uint32_t a_lo = a_tap + (uint32_t)im * a_img16;
-                uint32_t bl = b_lo + (uint32_t)im * b_img16;
-                for (int s = 0; s < k16n; ++s) {
-                  if (leader && !(P.dbg & 2)) {
-                    const uint64_t adesc = ((uint64_t)hi << 32) | (uint64_t)a_lo;
-                    const uint64_t bdesc = ((uint64_t)hi << 32) | (uint64_t)bl;
-                    umma_bf16(d, adesc, bdesc, kIdescMN, accf);
+              // a pair needs ring rows slot, slot + 1 adjacent in memory; across the ring's wrap it is two N = 128 MMAs
+              const bool wide = t_w[j] == 2u && slot + 1u < nring;
+              const uint32_t nsub = (t_w[j] == 2u && !wide) ? 2u : 1u;
+              for (uint32_t sub = 0; sub < nsub; ++sub) {
+                const uint32_t sl = sub ? 0u : slot;
+                const uint32_t x_tap = a_lo0 + sl * a_row16 + t_sh[j];
+                const uint32_t d = tmem_base + t_col[j] + sub * 128u;
+                uint32_t accf = started;
+                for (int im = 0; im < P.NI; ++im) {
+                  uint32_t x_lo = x_tap + (uint32_t)im * a_img16;
+                  uint32_t gl = b_lo + (uint32_t)im * b_img16;
+                  for (int s = 0; s < k16n; ++s) {
+                    if (leader && !(P.dbg & 2)) {
+                      const uint64_t gdesc = ((uint64_t)hi << 32) | (uint64_t)gl;    // A: G rows, M = co
+                      const uint64_t xdesc = ((uint64_t)hi << 32) | (uint64_t)x_lo;  // B: shifted X rows, N = ci (x2)
+                      umma_bf16(d, gdesc, xdesc, wide ? kIdescMN256 : kIdescMN, accf);
+                    }
+                    accf = 1u;
+                    x_lo += 128u;
+                    gl += 128u;
                   }
-                  accf = 1u;
-                  a_lo += 128u;
-                  bl += 128u;
                 }
               }
             }
@@ -263,20 +287,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     asm volatile("bar.sync 1, 160;" ::: "memory");
     if (has_work) {
       tc_fence_after();
-      for (int j = 0; j < ntaps; ++j) {
-        float* row = dst + (size_t)j * kAccFloats + (size_t)(ew * 32 + lane) * 128;
+      // the accumulators hold D^T: TMEM lane = co, column = ci.  A lane writes its co of 32 consecutive ci rows, so
+      // every store instruction of the warp covers 32 consecutive floats of one [ci] row of the partial block.
+      const int co = ew * 32 + lane;
+      for (int j = 0; j < ncols; ++j) {
+        float* blk = dst + (size_t)j * kAccFloats + co;
 #pragma unroll 1
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * 128 + cb * 32), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<uint4*>(row + cb * 32 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          for (int e = 0; e < 32; ++e) blk[(size_t)(cb * 32 + e) * 128] = __uint_as_float(v[e]);
         }
       }
     } else {
-      for (int j = 0; j < ntaps; ++j) {
+      for (int j = 0; j < ncols; ++j) {
         float4* row = reinterpret_cast<float4*>(dst + (size_t)j * kAccFloats + (size_t)(ew * 32 + lane) * 128);
         for (int e = 0; e < 32; ++e) row[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -298,10 +324,7 @@ __global__ void wgrad_reduce_kernel(const WgradParams P, float scale, float beta
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const int tap = i / (kAccFloats / 4);
     const int e4 = i - tap * (kAccFloats / 4);
-    int g = 0;
-    for (int q = 0; q < P.ngroups; ++q)
-      if (tap >= P.g_tap0[q]) g = q;
-    const int j = tap - P.g_tap0[g];
+    const int g = P.tap_group[tap], j = P.tap_col[tap];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < P.g_ncta[g]; ++c) {
       const float4 v = reinterpret_cast<const float4*>(
@@ -405,21 +428,64 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   P.W = d->W;
   const int ntaps = P.k * P.k;
 
-  // tap groups of <= 4 consecutive taps (row-major), sizes as even as possible
+  // Tap groups: <= 4 taps = 512 TMEM columns each, sizes as even as possible (a CTA's share of the SMs follows its
+  // group's tap count).  Vertical tap pairs become one item (one N = 256 MMA per K step); the tables below tile
+  // the 3x3 / 5x5 taps with such pairs plus single taps so that every group keeps 3-4 taps and spans <= 3 input
+  // rows.  SR100_WGRAD_VPAIR=0: single taps only (groups of consecutive taps, the earlier scheme).
+  struct Item { int ky, kx, w; };
+  static const Item k5_items[7][4] = {
+      {{0, 0, 2}, {0, 1, 2}, {-1, 0, 0}, {-1, 0, 0}}, {{0, 2, 2}, {0, 3, 2}, {-1, 0, 0}, {-1, 0, 0}},
+      {{2, 0, 2}, {2, 1, 2}, {-1, 0, 0}, {-1, 0, 0}}, {{2, 2, 2}, {2, 3, 2}, {-1, 0, 0}, {-1, 0, 0}},
+      {{0, 4, 1}, {1, 4, 2}, {-1, 0, 0}, {-1, 0, 0}}, {{3, 4, 2}, {4, 3, 1}, {-1, 0, 0}, {-1, 0, 0}},
+      {{4, 0, 1}, {4, 1, 1}, {4, 2, 1}, {-1, 0, 0}}};
+  static const Item k3_items[3][4] = {{{0, 0, 2}, {2, 0, 1}, {-1, 0, 0}, {-1, 0, 0}},
+                                      {{0, 1, 2}, {2, 1, 1}, {-1, 0, 0}, {-1, 0, 0}},
+                                      {{0, 2, 2}, {2, 2, 1}, {-1, 0, 0}, {-1, 0, 0}}};
+  const char* vp_env = getenv("SR100_WGRAD_VPAIR");
+  const bool vpair = !(vp_env && atoi(vp_env) == 0) && (P.k == 3 || P.k == 5);
   P.ngroups = (ntaps + 3) / 4;
+  int max_span = 0;
   {
     int t = 0;
     for (int g = 0; g < P.ngroups; ++g) {
-      const int left = ntaps - t, gl = P.ngroups - g;
-      const int sz = (left + gl - 1) / gl;
-      P.g_tap0[g] = t;
-      P.g_ntaps[g] = sz;
-      t += sz;
+      int kymin = 99, kymax = -1, col = 0, nt = 0, ni = 0;
+      if (vpair) {
+        const Item* items = P.k == 5 ? k5_items[g] : k3_items[g];
+        for (int j = 0; j < 4 && items[j].ky >= 0; ++j, ++ni) {
+          P.it_ky[g][j] = (signed char)items[j].ky;
+          P.it_kx[g][j] = (signed char)items[j].kx;
+          P.it_w[g][j] = (signed char)items[j].w;
+          P.it_col[g][j] = (signed char)col;
+          for (int q = 0; q < items[j].w; ++q) {
+            const int tap = (items[j].ky + q) * P.k + items[j].kx;
+            P.tap_group[tap] = (signed char)g;
+            P.tap_col[tap] = (signed char)(col + q);
+          }
+          kymin = std::min(kymin, items[j].ky);
+          kymax = std::max(kymax, items[j].ky + items[j].w - 1);
+          col += items[j].w;
+          nt += items[j].w;
+        }
+      } else {
+        const int left = ntaps - t, gl = P.ngroups - g;
+        const int sz = (left + gl - 1) / gl;
+        for (int j = 0; j < sz; ++j, ++t, ++ni) {
+          P.it_ky[g][j] = (signed char)(t / P.k);
+          P.it_kx[g][j] = (signed char)(t % P.k);
+          P.it_w[g][j] = 1;
+          P.it_col[g][j] = (signed char)j;
+          P.tap_group[t] = (signed char)g;
+          P.tap_col[t] = (signed char)j;
+          kymin = std::min(kymin, t / P.k);
+          kymax = std::max(kymax, t / P.k);
+        }
+        nt = sz;
+      }
+      P.g_nitems[g] = ni;
+      P.g_ntaps[g] = nt;
+      max_span = std::max(max_span, kymax - kymin);
     }
   }
-  int max_span = 0;
-  for (int g = 0; g < P.ngroups; ++g)
-    max_span = std::max(max_span, (P.g_tap0[g] + P.g_ntaps[g] - 1) / P.k - P.g_tap0[g] / P.k);
 
   // geometry: segment width (multiple of 16, <= 128) and ring depth within the shared-memory budget
   bool ok = false;
@@ -451,6 +517,14 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
       }
       if (!grew) break;
     }
+    if (const char* e = getenv("SR100_WGRAD_RING")) {   // development override: "<ring>,<g slots>"
+      int r_ = 0, b_ = 0;
+      if (sscanf(e, "%d,%d", &r_, &b_) == 2 && r_ >= min_ring && r_ <= kMaxRing && b_ >= min_b && b_ <= kMaxBSlots &&
+          fixed + r_ * a_row + b_ * b_row <= kWgSmemBudget) {
+        nring = r_;
+        nb = b_;
+      }
+    }
     P.BW = bw;
     P.NI = ni;
     P.ngrp = (d->NB + ni - 1) / ni;
@@ -466,16 +540,30 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
     return set_error(SR_ERR_UNSUPPORTED, "no wgrad geometry fits shared memory");
   }
 
-  // CTAs per group proportional to the group's tap count; row blocks so that every group has enough units
+  // CTAs per group proportional to the group's cost: a tap of a vertical pair is cheaper than a single tap (one
+  // N = 256 MMA for two taps reads 12 KB of shared memory instead of 16: 0.75 of a single tap, and measured so)
+  double cost[kMaxGroups], total_cost = 0;
+  {
+    const char* e = getenv("SR100_WGRAD_PCOST");
+    const double pair_cost = e ? atof(e) : 1.5;    // cost of a pair item in single-tap units (measured optimum)
+    for (int g = 0; g < P.ngroups; ++g) {
+      cost[g] = 0;
+      for (int j = 0; j < P.g_nitems[g]; ++j) cost[g] += P.it_w[g][j] == 2 ? pair_cost : 1.0;
+      total_cost += cost[g];
+    }
+  }
   int assigned = 0;
   for (int g = 0; g < P.ngroups; ++g) {
-    int n = (int)((double)sms * P.g_ntaps[g] / ntaps);
+    int n = (int)((double)sms * cost[g] / total_cost);
     if (n < 1) n = 1;
     P.g_ncta[g] = n;
     assigned += n;
   }
-  for (int g = 0; assigned < sms; g = (g + 1) % P.ngroups) {  // hand out the remainder, larger groups first
-    ++P.g_ncta[g];
+  while (assigned < sms) {   // hand out the remainder to the group with the highest cost per CTA
+    int best = 0;
+    for (int g = 1; g < P.ngroups; ++g)
+      if (cost[g] / P.g_ncta[g] > cost[best] / P.g_ncta[best]) best = g;
+    ++P.g_ncta[best];
     ++assigned;
   }
   while (assigned > sms) {

@@ -98,3 +98,23 @@ def test_edge_shapes_and_empty(sr_model):
         assert np.array_equal(f, c[:4 * h, :4 * w])
     with pytest.raises((ValueError, RuntimeError)):
         sr_model.upscale_arrays([np.zeros((8, 8), dtype=np.uint8)])       # not H x W x 3
+
+
+def test_batch_of_equal_shapes_config3_equals_one_by_one(sr_model):
+    """BASELINE.json configs[2] shape (339x510 LR images, 54 tiles each; 12 of the 64 here): a batch of same-shaped
+    images goes through ONE gather launch and shared sub-batches of the conv stack -- every image must come out
+    bit-identical to running it alone, in a mixed list too (runs of equal shapes are batched, the rest are not)."""
+    from scipy.ndimage import uniform_filter
+    rng = np.random.default_rng(33)
+    def im(h, w):
+        return uniform_filter(rng.integers(0, 256, size=(h, w, 3)).astype(np.float32), size=(5, 5, 1)).astype(np.uint8)
+    batch = [im(339, 510) for _ in range(12)]
+    together = sr_model.upscale_arrays(batch)
+    assert all(t.shape == (1356, 2040, 3) for t in together)
+    for i in (0, 5, 11):
+        assert np.array_equal(sr_model.upscale_arrays([batch[i]])[0], together[i])
+    mixed = [batch[0], batch[1], im(100, 80), batch[2], im(100, 80), im(100, 80)]
+    out = sr_model.upscale_arrays(mixed)
+    assert np.array_equal(out[0], together[0]) and np.array_equal(out[1], together[1]) and np.array_equal(out[3], together[2])
+    assert np.array_equal(out[2], sr_model.upscale_arrays([mixed[2]])[0])
+    assert np.array_equal(out[5], sr_model.upscale_arrays([mixed[5]])[0])

@@ -227,43 +227,12 @@ __global__ void patch_gather_kernel(const void* __restrict__ src, int h, int w, 
   }
 }
 
-// Same gather, four consecutive elements of a patch row per thread (one 16-byte store); needs 3*pw % 4 == 0.
-template <bool FROM_U8>
-__global__ void patch_gather_vec4_kernel(const void* __restrict__ src, int h, int w, int canvas_w,
-                                         int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,
-                                         float4* __restrict__ out) {
-  const int row_q = pw * 3 / 4;
-  const size_t total = (size_t)cnt_h * cnt_w * ph * row_q;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int q = (int)(idx % row_q);
-    size_t r = idx / row_q;
-    const int i = (int)(r % ph);
-    const int n = (int)(r / ph);
-    const int wi = n / cnt_h, hi = n - wi * cnt_h;
-    const int y = hi * step + i;
-    const int e0 = wi * step * 3 + q * 4;  // element offset inside canvas row y
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = e0 + j;
-      if (FROM_U8) {
-        v[j] = (y < h && e < w * 3) ? (float)reinterpret_cast<const uint8_t*>(src)[(size_t)y * w * 3 + e] : 0.f;
-      } else {
-        v[j] = reinterpret_cast<const float*>(src)[(size_t)y * canvas_w * 3 + e];
-      }
-      if (divisor != 1.f) v[j] = __fdiv_rn(v[j], divisor);
-    }
-    out[idx] = make_float4(v[0], v[1], v[2], v[3]);
-  }
-}
-
 // The production gather (uint8 source, 3*pw % 4 == 0): one warp per patch row, any number of same-shaped images per
 // launch (image m's patches follow image m-1's).  The row's coordinates are computed once per warp, the lanes
 // then cover the row in 16-byte stores (512 B per warp instruction); value / divisor comes from a 256-entry table
 // built per block with the same correctly rounded fp32 division, so results are bit-identical to the scalar kernel.
-// (The flat-index kernels above spend ~250 instructions per 16 bytes on 64-bit div/mod and four fp32 divisions:
-// instruction-bound at ~2 TB/s.)
+// (The flat-index kernel above -- and its 4-element variant this one replaced -- spends ~250 instructions per
+// 16 bytes on 64-bit div/mod and four fp32 divisions: instruction-bound at ~2 TB/s.)
 __global__ void __launch_bounds__(256)
 patch_gather_u8_rows_kernel(const uint8_t* __restrict__ imgs, int n_img, size_t img_stride, int h, int w,
                             int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,

@@ -143,3 +143,36 @@ def test_keras_adam_first_step():
     opt.step([torch.tensor([0.5, -0.25])])
     # t=1: m=(1-b1)g, v=(1-b2)g^2, lr_t = lr*sqrt(1-b2)/(1-b1) -> step ~= lr*sign(g) (eps=1e-7 slightly less)
     assert torch.allclose(p.detach(), torch.tensor([1.0 - 1e-4, -2.0 + 1e-4]), atol=1e-8)
+
+
+def test_oracle_conv_is_keras_conv2d_by_definition():
+    """The torch conv inside oracle/model.py against the definition Keras documents for Conv2D(padding='same',
+    strides 1): out[n,y,x,co] = b[co] + sum_{ky,kx,ci} in[n, y+ky-p, x+kx-p, ci] * kernel[ky,kx,ci,co] (cross-
+    correlation, HWIO kernel, zero padding p = (k-1)/2) -- written out as plain numpy loops, no library conv."""
+    import torch
+    from oracle import model as om
+    rng = np.random.default_rng(3)
+    for k, cin, cout in ((1, 3, 5), (3, 4, 6), (5, 2, 3)):
+        x = rng.standard_normal((2, 6, 7, cin))
+        w = rng.standard_normal((k, k, cin, cout))
+        b = rng.standard_normal(cout)
+        p = (k - 1) // 2
+        xp = np.zeros((2, 6 + 2 * p, 7 + 2 * p, cin))
+        xp[:, p:p + 6, p:p + 7] = x
+        want = np.zeros((2, 6, 7, cout))
+        for ky in range(k):
+            for kx in range(k):
+                want += np.einsum("nyxc,co->nyxo", xp[:, ky:ky + 6, kx:kx + 7], w[ky, kx])
+        want += b
+        # the same call pattern as DifvdsrDoubleOracle.conv: HWIO -> OIHW, F.conv2d, padding (k-1)//2
+        got = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2),
+                                         torch.from_numpy(w).permute(3, 2, 0, 1).contiguous(), torch.from_numpy(b),
+                                         padding=p).permute(0, 2, 3, 1).numpy()
+        assert np.abs(got - want).max() < 1e-12
+    # and through the oracle class itself on the first (1x1) layer: relu(x @ W + b)
+    weights = om.init_weights(5, bias_scale=0.1)
+    m = om.DifvdsrDoubleOracle(weights, dtype=torch.float64)
+    x = rng.random((1, 4, 5, 3))
+    y = m.conv("level1", torch.from_numpy(x).permute(0, 3, 1, 2), relu=True).permute(0, 2, 3, 1).detach().numpy()
+    w0, b0 = weights["level1"]
+    assert np.abs(y - np.maximum(x @ w0[0, 0].astype(np.float64) + b0, 0)).max() < 1e-12

@@ -458,16 +458,27 @@ depth_to_space_tiled_kernel(const float* __restrict__ in, int NB, int H, int W, 
     const float* src = in + (row * W + x0) * Cin;
     const int nin = npx * Cin;
     __syncthreads();                                             // previous strip fully written out (and tbl ready)
+    // (pixel, channel) of a thread's element advance by a constant per trip: one division per phase, none in the loops
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (nin & 3) == 0) {
-      for (int i = threadIdx.x * 4; i < nin; i += blockDim.x * 4) {
+      const int step = blockDim.x * 4, dq = step / Cin, dr = step - dq * Cin;
+      int px = (threadIdx.x * 4) / Cin, ch = threadIdx.x * 4 - px * Cin;
+      for (int i = threadIdx.x * 4; i < nin; i += step) {
         const float4 v = *reinterpret_cast<const float4*>(src + i);
-        int px = i / Cin, ch = i - px * Cin;
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        float* t0 = tile + px * pitch + ch;
+        if (ch + 3 < Cin) {
+          t0[0] = v.x; t0[1] = v.y; t0[2] = v.z; t0[3] = v.w;
+        } else {                                                 // the group straddles two pixels
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          int p2 = px, c2 = ch;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          tile[px * pitch + ch] = vv[e];
-          if (++ch == Cin) { ch = 0; ++px; }
+          for (int e = 0; e < 4; ++e) {
+            tile[p2 * pitch + c2] = vv[e];
+            if (++c2 == Cin) { c2 = 0; ++p2; }
+          }
         }
+        px += dq;
+        ch += dr;
+        if (ch >= Cin) { ch -= Cin; ++px; }
       }
     } else {
       for (int i = threadIdx.x; i < nin; i += blockDim.x) {
@@ -481,15 +492,25 @@ depth_to_space_tiled_kernel(const float* __restrict__ in, int NB, int H, int W, 
       float* dst = out + (row * r + ry) * orow + (size_t)x0 * RC;
       const int* t = tbl + ry * RC;
       if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nout & 3) == 0) {
-        for (int i = threadIdx.x * 4; i < nout; i += blockDim.x * 4) {
-          int px = i / RC, k = i - px * RC;
+        const int step = blockDim.x * 4, dq = step / RC, dr = step - dq * RC;
+        int px = (threadIdx.x * 4) / RC, k = threadIdx.x * 4 - px * RC;
+        for (int i = threadIdx.x * 4; i < nout; i += step) {
           float vv[4];
+          const float* tp = tile + px * pitch;
+          if (k + 3 < RC) {
+            vv[0] = tp[t[k]]; vv[1] = tp[t[k + 1]]; vv[2] = tp[t[k + 2]]; vv[3] = tp[t[k + 3]];
+          } else {
+            int p2 = px, k2 = k;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            vv[e] = tile[px * pitch + t[k]];
-            if (++k == RC) { k = 0; ++px; }
+            for (int e = 0; e < 4; ++e) {
+              vv[e] = tile[p2 * pitch + t[k2]];
+              if (++k2 == RC) { k2 = 0; ++p2; }
+            }
           }
           *reinterpret_cast<float4*>(dst + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          px += dq;
+          k += dr;
+          if (k >= RC) { k -= RC; ++px; }
         }
       } else {
         for (int i = threadIdx.x; i < nout; i += blockDim.x) {

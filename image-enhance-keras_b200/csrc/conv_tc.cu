@@ -1155,13 +1155,8 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
 template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1, bool TF32 = false>
 static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI, TF32>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBudget);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_kernel)")) return rc;
   kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
                                                            pl->tmW[1], pl->P);
   cudaError_t e = cudaGetLastError();
@@ -1172,13 +1167,8 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
 template <int NACC, int NBUF, int EPI = -1, bool TF32 = false>
 static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
   auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI, TF32>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBudget);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_pair_kernel)");
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_pair_kernel)")) return rc;
   kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
                                                            pl->tmW[1], pl->P);
   cudaError_t e = cudaGetLastError();

@@ -205,12 +205,9 @@ extern "C" int sr_dataprep_patches(const uint8_t* img, int H, int W, const int* 
   if (P < 1 || P > H || P > W || radius < 0 || radius > 8) return set_error(SR_ERR_INVALID, "sr_dataprep_patches: bad size");
   const size_t smem = (size_t)2 * P * P * 3 * sizeof(double);
   if (smem > 200 * 1024) return set_error(SR_ERR_UNSUPPORTED, "sr_dataprep_patches: sub-images larger than 64 x 64");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dataprep_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(dataprep_patch_kernel)");
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(dataprep_patch_kernel, 200 * 1024, &attr_done, "cudaFuncSetAttribute(dataprep_patch_kernel)"))
+    return rc;
   dataprep_patch_kernel<<<n_patches, 256, smem, as_stream(stream)>>>(img, H, W, pos, P, weights, radius, y_u8, g_u8);
   return check_launch("dataprep_patch_kernel");
 }

@@ -17,6 +17,20 @@ inline int check_launch(const char* where) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: `done` is the caller's per-kernel bit
+// mask of the devices it has been applied on (a process normally drives one GPU, but nothing here assumes it).
+template <typename Kern>
+inline int ensure_dynamic_smem(Kern kern, int bytes, unsigned long long* done, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done & bit) return SR_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  *done |= bit;
+  return SR_OK;
+}
+
 inline unsigned int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
   size_t g = (work_items + block - 1) / block;
   if (g < 1) g = 1;

@@ -612,13 +612,9 @@ extern "C" int sr_wgrad_plan_run(sr_wgrad_plan* plan, void* stream) {
   if (!plan) return set_error(SR_ERR_INVALID, "sr_wgrad_plan_run: null plan");
   const WgradPlan* pl = reinterpret_cast<const WgradPlan*>(plan);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kWgSmemBudget);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(wgrad_tc_kernel, (int)kWgSmemBudget, &attr_done, "cudaFuncSetAttribute(wgrad_tc_kernel)"))
+    return rc;
   wgrad_tc_kernel<<<pl->grid, kWgThreads, pl->smem_bytes, st>>>(pl->tmX, pl->tmG, pl->P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad_tc_kernel launch");

@@ -824,8 +824,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool is_leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int per_img = P.nseg * P.tiles_per_seg;
-  const int pair_tiles = ((P.NB + 1) >> 1) * per_img;
+  // The two CTAs of a pair take the same tile index of two different COLUMNS (a column = one column segment of
+  // one image): their tiles then start at the same offset inside the strip (off0 depends on the tile index only),
+  // which is what lets one MMA descriptor address both CTAs' shared memory.  Pairing columns rather than images
+  // also pairs the segments of a single image (NB == 1) and leaves no idle CTA when NB is odd but NB * nseg is even.
+  const int tps = P.tiles_per_seg;
+  const int ncol = P.NB * P.nseg;
+  const int pair_tiles = ((ncol + 1) >> 1) * tps;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -864,14 +869,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  // tile of this CTA for pair-tile index pt: image 2*j + rank (clamped; a clamped duplicate does not store)
+  // tile of this CTA for pair-tile index pt: column 2*j + rank (clamped; a clamped duplicate does not store)
   auto decode = [&](int pt, bool* live) {
-    const int j = pt / per_img;
-    const int r = pt - j * per_img;
-    int n = 2 * j + (int)rank;
-    *live = n < P.NB;
-    if (n >= P.NB) n = P.NB - 1;
-    return decode_tile<T>(P, n * per_img + r);
+    const int j = pt / tps;
+    const int ti = pt - j * tps;
+    int col = 2 * j + (int)rank;
+    *live = col < ncol;
+    if (col >= ncol) col = ncol - 1;
+    return decode_tile<T>(P, col * tps + ti);   // tile order is (image, segment, tile index): col = n * nseg + seg
   };
 
   if (warp == 0) {
@@ -1118,9 +1123,9 @@ static constexpr size_t kSmemBudget = 227 * 1024;
 
 // Choose the column-segment width: maximise useful MMA rows subject to the shared-memory budget.
 static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_bytes,
-                            ConvKernelParams* P) {
+                            ConvKernelParams* P, int min_nseg = 1) {
   double best_eff = -1.0;
-  for (int nseg = 1; nseg <= W; ++nseg) {
+  for (int nseg = min_nseg; nseg <= W; ++nseg) {
     const int BW = (W + nseg - 1) / nseg;
     if ((BW * (nseg - 1)) >= W) continue;  // last segment would be empty
     const int PWs = BW + 2 * p;
@@ -1217,8 +1222,11 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   pl->tf32 = tf32;
   pl->nacc = ((d->nacc == 2 || d->shuffle_r > 0 || tf32) && pl->n_pad == 128) ? 2 : 4;
   const int T = pl->nacc * 128;
+  // CTA pairs work on two columns (image x column segment).  A single image could be split into two segments for
+  // it (the kernel handles that), but measured on BASELINE config 1 the extra halo of the forced split costs what
+  // the paired MMAs gain (2.47 vs 2.41 ms), so single images keep the single-CTA kernel.
   pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
-  const int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kRowBytes;
+  int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kRowBytes;
   ConvKernelParams& P = pl->P;
   P.nsrc = d->nsrc;
   P.ksize[0] = d->ksize[0];
@@ -1238,7 +1246,13 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   const int Wc = (d->comp_w > 0 && d->comp_w < d->W) ? d->comp_w : d->W;
   P.Hc = Hc;
   P.Wc = Wc;
-  if (!choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P)) {
+  bool geo = choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P, (pl->pair && d->NB == 1) ? 2 : 1);
+  if (!geo && pl->pair && d->NB == 1) {   // cannot be split in two: the single-CTA kernel
+    pl->pair = 0;
+    wstage = kTapsPerStage * pl->n_pad * kRowBytes;
+    geo = choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P);
+  }
+  if (!geo) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "no conv geometry fits shared memory");
   }
@@ -1287,7 +1301,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   if (pl->pair) {
-    const int pair_tiles = ((P.NB + 1) / 2) * P.nseg * P.tiles_per_seg;
+    const int pair_tiles = ((P.NB * P.nseg + 1) / 2) * P.tiles_per_seg;
     pl->grid = 2 * std::min(pair_tiles, sms / 2);
   } else {
     pl->grid = std::min(P.total_tiles, sms);

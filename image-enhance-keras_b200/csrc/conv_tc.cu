@@ -175,10 +175,13 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
 // The operand of 8 pixel pairs is requested as one batch BEFORE the TMEM drain / before the pass that uses it, so
 // one DRAM latency is exposed per batch instead of one per pixel pair; the two passes share one (rolled) body to
 // keep the kernel small (instruction-cache footprint decides the short-MMA-phase launches).
-template <int EPI>
+// CS: the launch also produces the column sums of its bf16 output (training: the bias gradient of the layer whose
+// output gradient this launch writes, sr_conv_desc.colsum_f32) -- every lane adds the rounded values it stores to
+// eight running sums `cs` (its eight channels), reduced once at the end of the kernel.
+template <int EPI, bool CS = false>
 __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, const TileCoord& c,
                                                     uint32_t t_acc, int f_base, uint8_t* stage,
-                                                    const float* s_bias, int lane, bool live = true) {
+                                                    const float* s_bias, int lane, bool live, float (&cs)[8]) {
   const int f = f_base + lane;
   const int fr = f / P.PWs;
   const int yy = fr - P.p;
@@ -295,6 +298,13 @@ __device__ __forceinline__ void epilogue_staged_acc(const ConvKernelParams& P, c
           pw[e] = *reinterpret_cast<const uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(P.out_bf16 + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        if constexpr (CS) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cs[2 * e] += __uint_as_float(pw[e] << 16);
+            cs[2 * e + 1] += __uint_as_float(pw[e] & 0xFFFF0000u);
+          }
+        }
       }
     }
   }
@@ -523,10 +533,11 @@ __device__ __forceinline__ void epilogue_staged_acc_tf32(const ConvKernelParams&
   }
 }
 
-template <int EPI>
+template <int EPI, bool CS = false>
 __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const TileCoord& c, uint32_t t_acc,
                                              int f_base, uint8_t* stage_buf, int ew, const float* s_bias, int lane,
-                                             bool live = true) {
+                                             bool live, float (&cs)[8]) {
+  static_assert(!CS || (EPI >= 1 && EPI <= 3), "column sums ride the residual / mask epilogues");
   // per-warp staging tile: 32 rows x 256 B (512 B in the sub-pixel variant, whose channel table follows the tiles)
   uint8_t* stage = stage_buf + ew * (32 * (EPI == 4 ? kShuffleStageRow : 256));
   if constexpr (EPI < 0) epilogue_staged_acc_generic(P, c, t_acc, f_base, stage, s_bias, lane, live);
@@ -535,12 +546,22 @@ __device__ __forceinline__ void epilogue_acc(const ConvKernelParams& P, const Ti
     epilogue_shuffle_acc(P, c, t_acc, f_base, stage, reinterpret_cast<const int*>(stage_buf + 4 * 32 * kShuffleStageRow),
                          s_bias, lane, live);
   else if constexpr (EPI == 5) epilogue_staged_acc_tf32(P, c, t_acc, f_base, stage, s_bias, lane, live);
-  else epilogue_staged_acc<EPI>(P, c, t_acc, f_base, stage, s_bias, lane, live);
+  else epilogue_staged_acc<EPI, CS>(P, c, t_acc, f_base, stage, s_bias, lane, live, cs);
+}
+
+// end of an epilogue warp's life: lanes l and l + 16 hold the same eight channels
+__device__ __forceinline__ void colsum_flush(const ConvKernelParams& P, float (&cs)[8], int lane) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+  if (lane < 16) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(P.colsum + lane * 8 + e, P.colsum_scale * cs[e]);
+  }
 }
 
 }  // namespace
 
-template <int N_, int AMODE, int NACC, int NBUF, int EPI, bool TF32>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI, bool TF32, bool CS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
@@ -736,6 +757,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
     const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
     uint32_t it = 0;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
       const TileCoord c = decode_tile<T>(P, t);
       const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
@@ -745,7 +767,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc) {
         if constexpr (N_ == 128) {
-          epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane);
+          epilogue_acc<EPI, CS>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane, true, cs);
         } else {
           const int f = c.f0 + acc * 128 + ew * 32 + lane;
           const int fr = f / P.PWs;
@@ -776,6 +798,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
     }
+    if constexpr (CS) colsum_flush(P, cs, lane);
   }
 
   __syncwarp();
@@ -795,7 +818,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // and L2 -> SM weight traffic halves.  The leader CTA (rank 0) owns the full-barriers and issues;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
 // =====================================================================================
-template <int NACC, int NBUF, int EPI, bool TF32>
+template <int NACC, int NBUF, int EPI, bool TF32, bool CS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
@@ -997,6 +1020,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ------------------------------------------------ epilogue (both CTAs, own TMEM lanes = own tile)
     const int ew = warp - 4;
     uint32_t it = 0;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
       bool live;
       const TileCoord c = decode(pt, &live);
@@ -1006,11 +1030,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc)
-        epilogue_acc<EPI>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane, live);
+        epilogue_acc<EPI, CS>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane, live, cs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
     }
+    if constexpr (CS) colsum_flush(P, cs, lane);
   }
 
   __syncwarp();  // lanes of the single-lane roles reconverge before the aligned cluster barrier
@@ -1157,9 +1182,9 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
   return best_eff > 0;
 }
 
-template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1, bool TF32 = false>
+template <int N_, int AMODE, int NACC, int NBUF, int EPI = -1, bool TF32 = false, bool CS = false>
 static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI, TF32>;
+  auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI, TF32, CS>;
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_kernel)")) return rc;
   kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
@@ -1169,9 +1194,9 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   return SR_OK;
 }
 
-template <int NACC, int NBUF, int EPI = -1, bool TF32 = false>
+template <int NACC, int NBUF, int EPI = -1, bool TF32 = false, bool CS = false>
 static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
-  auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI, TF32>;
+  auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI, TF32, CS>;
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_pair_kernel)")) return rc;
   kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
@@ -1200,6 +1225,10 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (d->relu < 0 || d->relu > 2) return set_error(SR_ERR_INVALID, "relu must be 0, 1 (ReLU) or 2 (LeakyReLU)");
   if (d->relu == 2 && (d->cout != 128 || d->shuffle_r > 0))
     return set_error(SR_ERR_UNSUPPORTED, "LeakyReLU epilogue: cout == 128, no shuffle");
+  if (d->colsum_f32 && (d->cout != 128 || !d->out_bf16 || d->precision == 1 || d->shuffle_r > 0 || d->a_mode == 1 ||
+                        d->relu == 2 || d->nacc != 2 ||
+                        ((d->res_f32 ? 1 : 0) + ((d->res_bf16 && !d->res_f32) ? 1 : 0) + (d->relu_mask_bf16 ? 1 : 0)) != 1))
+    return set_error(SR_ERR_UNSUPPORTED, "colsum_f32: bf16 128-channel output with exactly one of residual / relu mask, nacc 2, a_mode 0");
   const int tf32 = d->precision == 1 ? 1 : 0;
   if (d->precision != 0 && d->precision != 1) return set_error(SR_ERR_INVALID, "precision must be 0 (bf16) or 1 (tf32)");
   if (tf32 && (d->out_bf16 || d->res_bf16 || d->relu_mask_bf16 || d->shuffle_r > 0 || d->a_mode == 1 || d->relu == 2))
@@ -1267,6 +1296,8 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
   P.out_f32 = d->out_f32;
   P.out_tf32 = d->out_tf32;
+  P.colsum = d->colsum_f32;
+  P.colsum_scale = d->colsum_scale;
   P.cout = d->cout;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
   P.out_index = d->out_index;
@@ -1325,6 +1356,20 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
     if (pl->pair) return launch_pair<2, 2, 5, true>(pl, st);
     if (pl->n_pad == 128) return launch_variant<128, kAModeSwizzle64, 2, 2, 5, true>(pl, st);
     return launch_variant<16, kAModeSwizzle64, 4, 2, -1, true>(pl, st);
+  }
+  if (P.colsum) {   // training: column sums of the stored gradient ride the residual / mask epilogues
+    if (pl->pair) {
+      switch (epi) {
+        case 1: return launch_pair<2, 2, 1, false, true>(pl, st);
+        case 2: return launch_pair<2, 2, 2, false, true>(pl, st);
+        default: return launch_pair<2, 2, 3, false, true>(pl, st);
+      }
+    }
+    switch (epi) {
+      case 1: return launch_variant<128, kAModeSwizzle64, 2, 2, 1, false, true>(pl, st);
+      case 2: return launch_variant<128, kAModeSwizzle64, 2, 2, 2, false, true>(pl, st);
+      default: return launch_variant<128, kAModeSwizzle64, 2, 2, 3, false, true>(pl, st);
+    }
   }
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);

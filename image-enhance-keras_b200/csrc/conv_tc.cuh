@@ -60,6 +60,8 @@ struct ConvKernelParams {
   const __nv_bfloat16* res_bf16;
   __nv_bfloat16* out_bf16;
   float* out_f32;
+  float* colsum;     // training: colsum[ch] += colsum_scale * sum over stored pixels of the bf16 output (or null)
+  float colsum_scale;
   float* out_tf32;   // tf32 mode: the output again, rounded to tf32 (round-to-nearest) = the next conv's operand
   int cout;          // real output channels (128; 3 for the tail conv)
   // dgrad-time ReLU mask: if non-null, out *= (mask > 0)

@@ -44,6 +44,8 @@ class ConvDesc(C.Structure):
         ("leaky_slope", C.c_float),
         ("precision", C.c_int),
         ("out_tf32", C.c_void_p),
+        ("colsum_f32", C.c_void_p),
+        ("colsum_scale", C.c_float),
     ]
 
 

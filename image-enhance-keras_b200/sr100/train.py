@@ -15,6 +15,7 @@ wgrad is csrc/wgrad_tc.cu.  Operands are bf16, accumulation fp32, master weights
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -96,7 +97,9 @@ class _TrainGraph:
         self.cuda_graph, self.ran_eager = None, False
 
         def conv(dst, srcs, shape, flip=False, out_bf16=None, out_f32=None, relu=0, alpha=1.0, beta=0.0,
-                 res32=None, res16=None, mask=None, cout=NUMK, bias=True):
+                 res32=None, res16=None, mask=None, cout=NUMK, bias=True, colsum=None):
+            """colsum = (bias-gradient view, scale): the launch also accumulates scale * column sums of its bf16 output
+            (sr_conv_desc.colsum_f32) -- the bias gradient of the layer whose output gradient it writes."""
             d = L.ConvDesc()
             d.nsrc = len(srcs)
             for s, (name, x) in enumerate(srcs):
@@ -113,6 +116,8 @@ class _TrainGraph:
             d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
             d.relu_mask_bf16 = mask.data_ptr() if mask is not None else None
             d.a_mode, d.nacc, d.pair = eng.a_mode, eng.nacc, eng.pair
+            if colsum is not None:
+                d.colsum_f32, d.colsum_scale = colsum[0].data_ptr(), colsum[1]
             p = _Plan(lib, d)
             if dst is self.fwd:
                 self.fwd_flops += p.flops
@@ -126,13 +131,10 @@ class _TrainGraph:
             self.bwd_flops += p.flops
             self.bwd.append(_Op("wgrad_k%d_%s" % (eng.ksize[name], "hr" if shape[1] != H else "lr"), p.run))
 
-        def colsum(g, shape, name, scale, also=None):
+        def colsum(g, shape, name, scale):
             npix = shape[0] * shape[1] * shape[2]
             db = tr.grad_b(name)
             self.bwd.append(_Op("colsum", lambda st: L.check(lib.sr_colsum_bf16(L.ptr(g), npix, scale, L.ptr(db), st))))
-            if also is not None:
-                db2 = tr.grad_b(also)
-                self.bwd.append(lambda st: db2.copy_(db))
 
         # ------------------------------------------------------------------ forward
         npix = NB * H * W
@@ -196,39 +198,69 @@ class _TrainGraph:
         self.bwd_flops += 2.0 * npix_hr * 27 * NUMK
         self.bwd.append(_Op("dgrad_tail", pl.run))
 
-        def bwd_block(kind, i, x, t1, t2, y, shape, f32s, last_hr=False):
+        fuse_cs = eng.nacc == 2 and eng.a_mode == 0 and os.environ.get("SR100_FUSED_COLSUM", "1") != "0"
+
+        def g_bias(blk):
+            """(bias-gradient view, scale, twin) of the layer(s) whose output gradient is the block's incoming g:
+            the 0.1-scaled block tail -- both tail convs of a 5/3 block share it (twin = the second one)."""
+            kind, i = blk[0], blk[1]
+            if kind == "53":
+                return tr.grad_b(names[i + 1]), 0.1, tr.grad_b(names[i + 3])
+            return tr.grad_b(names[i + 1]), 0.1, None
+
+        def bwd_block(blk, g_summed, nxt, last_hr=False):
+            """blk's backward.  g_summed: the bias gradient from the incoming g was already accumulated by the launch
+            that produced g.  nxt: the block processed next (it consumes the g this block writes): its tail bias
+            gradient rides this block's last input-gradient launch."""
+            kind, i, x, t1, t2, y, shape, f32s = blk
             g, g32 = (gs, gs32) if f32s else (gsh, None)
             a1, a2 = (gt1, gt2) if f32s else (gth1, gth2)
             o32 = g32 if f32s else (gsh32 if last_hr else None)
+            db_g, sc_g, twin = g_bias(blk)
+            # the launch that writes the next block's g can carry its column sums only if g stays bf16-resident in the
+            # same buffer (not across the HR -> LR boundary, where g goes through the bilinear adjoint)
+            cs_next = None
+            if fuse_cs and nxt is not None and nxt[7] == f32s:
+                cs_next = g_bias(nxt)[:2]
             if kind == "53":
                 na, nb, nc, nd = names[i], names[i + 1], names[i + 2], names[i + 3]
-                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False)
-                conv(self.bwd, [(nd, g)], shape, flip=True, out_bf16=a2, alpha=0.1, mask=t2, bias=False)
+                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False,
+                     colsum=(tr.grad_b(na), 1.0) if fuse_cs else None)
+                conv(self.bwd, [(nd, g)], shape, flip=True, out_bf16=a2, alpha=0.1, mask=t2, bias=False,
+                     colsum=(tr.grad_b(nc), 1.0) if fuse_cs else None)
                 wgrad(t1, g, shape, nb, 0.1)
                 wgrad(t2, g, shape, nd, 0.1)
-                colsum(g, shape, nb, 0.1, also=nd)
+                if not g_summed:
+                    colsum(g, shape, nb, 0.1)
+                self.bwd.append(lambda st: twin.copy_(db_g))
                 conv(self.bwd, [(na, a1), (nc, a2)], shape, flip=True, out_bf16=g, out_f32=o32, alpha=1.0, beta=0.9,
-                     res32=g32, res16=g, bias=False)
+                     res32=g32, res16=g, bias=False, colsum=cs_next)
                 wgrad(x, a1, shape, na, 1.0)
                 wgrad(x, a2, shape, nc, 1.0)
-                colsum(a1, shape, na, 1.0)
-                colsum(a2, shape, nc, 1.0)
+                if not fuse_cs:
+                    colsum(a1, shape, na, 1.0)
+                    colsum(a2, shape, nc, 1.0)
             else:
                 na, nb = names[i], names[i + 1]
-                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False)
+                conv(self.bwd, [(nb, g)], shape, flip=True, out_bf16=a1, alpha=0.1, mask=t1, bias=False,
+                     colsum=(tr.grad_b(na), 1.0) if fuse_cs else None)
                 wgrad(t1, g, shape, nb, 0.1)
-                colsum(g, shape, nb, 0.1)
+                if not g_summed:
+                    colsum(g, shape, nb, 0.1)
                 conv(self.bwd, [(na, a1)], shape, flip=True, out_bf16=g, out_f32=o32, alpha=1.0, beta=1.0, res32=g32,
-                     res16=g, bias=False)
+                     res16=g, bias=False, colsum=cs_next)
                 wgrad(x, a1, shape, na, 1.0)
-                colsum(a1, shape, na, 1.0)
+                if not fuse_cs:
+                    colsum(a1, shape, na, 1.0)
+            return cs_next is not None
 
-        bwd_block(*blocks[23])
-        bwd_block(*blocks[22], last_hr=True)
+        done = bwd_block(blocks[23], False, blocks[22])
+        bwd_block(blocks[22], done, None, last_hr=True)
         self.bwd.append(lambda st: L.check(lib.sr_bilinear4_bwd(L.ptr(gsh32), NB, H, W, NUMK, L.ptr(gs32), st)))
         self.bwd.append(lambda st: L.check(lib.sr_cast_f32_to_bf16(L.ptr(gs32), npix * NUMK, L.ptr(gs), st)))
-        for blk in reversed(blocks[:22]):
-            bwd_block(*blk)
+        done = False
+        for bi in reversed(range(22)):
+            done = bwd_block(blocks[bi], done, blocks[bi - 1] if bi > 0 else None)
         hw, hb = tr.grad_w("level1"), tr.grad_b("level1")
         self.bwd.append(lambda st: L.check(lib.sr_head1x1_bwd(
             L.ptr(self.x_in), L.ptr(S[0]), L.ptr(gs32), None, npix, L.ptr(hw), L.ptr(hb), st)))

@@ -87,6 +87,12 @@ typedef struct sr_conv_desc {
    * bf16 tensors, relu_mask, shuffle_r, LeakyReLU and a_mode 1 are not available in this mode. */
   int precision;
   float* out_tf32;       /* precision 1, cout == 128: the output rounded to tf32 (round to nearest) */
+  /* Training: colsum_f32[c] += colsum_scale * sum over all pixels of the (bf16-rounded) output -- the bias gradient
+   * of the layer whose output gradient this input-gradient launch writes (what sr_colsum_bf16 would compute in a
+   * second pass over the tensor).  fp32 [128], atomically accumulated; needs out_bf16, cout == 128, nacc == 2 and
+   * exactly one of res_f32 / res_bf16 / relu_mask_bf16. */
+  float* colsum_f32;
+  float colsum_scale;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -906,6 +907,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ------------------------------------------------ weight half-stage TMA producer (both CTAs)
     if (lane == 0) {
       Ring wr{0u, 0u, (uint32_t)NS};
+      bool w_wrapped = false;
       for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
@@ -914,6 +916,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t slot = wr.slot, ph = wr.phase;
               mbar_wait(&bars->w_empty[slot], ph ^ 1);
+              if ((P.dbg & 1) && w_wrapped) {   // timing experiment: the stage keeps whatever it held
+                if (is_leader) mbar_arrive(&bars->w_full[slot]);
+                wr.advance();
+                continue;
+              }
+              if (wr.slot + 1 == wr.n) w_wrapped = true;
               const int nbox = min(kTapsPerStage, ntaps - tap);  // an odd last tap loads one box only
               if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * nbox * WTAP);
               const uint32_t bar = mapa_shared(smem_u32(&bars->w_full[slot]), 0);
@@ -941,6 +949,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
+            if ((P.dbg & 2) && ac >= 2) {       // timing experiment: the strip buffer keeps whatever it held
+              if (is_leader) mbar_arrive(&bars->a_full[slot]);
+              ++ac;
+              continue;
+            }
             if (is_leader) mbar_expect_tx(&bars->a_full[slot], 2 * strip_bytes);
             tma_load_4d_pair(a_buf + slot * P.a_bytes, tmA, mapa_shared(smem_u32(&bars->a_full[slot]), 0),
                              ch * CHE, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
@@ -1296,6 +1309,10 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
   P.out_f32 = d->out_f32;
   P.out_tf32 = d->out_tf32;
+  {
+    const char* e = getenv("SR100_CONV_DBG");
+    P.dbg = e ? atoi(e) : 0;
+  }
   P.colsum = d->colsum_f32;
   P.colsum_scale = d->colsum_scale;
   P.cout = d->cout;

@@ -24,7 +24,6 @@ def main():
     a = ap.parse_args()
     import torch
     from sr100 import _lib as L
-    from sr100 import ops
     lib = L.require_device()
     peak = 6551.0
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")

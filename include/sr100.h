@@ -62,7 +62,7 @@ typedef struct sr_conv_desc {
   const void* relu_mask_bf16; /* optional (backward): out = 0 where mask <= 0 */
   int a_mode;            /* 0: 64B-swizzled strip, 1: interleaved no-swizzle strip */
   int nacc;              /* 4 (default): 512 positions / tile; 2: 256 positions, double-buffered TMEM */
-  int pair;              /* 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 over two images); needs NB >= 2 */
+  int pair;              /* 1: CTA-pair kernel (tcgen05 cta_group::2, M = 256 over two image x column-segment columns); NB >= 2 */
   /* cout <= 16 only (the tail conv): scatter image n of the output into slot out_index[n] (device
    * int32[NB]) of a tensor whose images are out_h x out_w pixels (>= H x W): the cropped HR stage
    * writes its H x W result into the top-left corner of the full 384 x 384 patch slot. NULL: dense. */

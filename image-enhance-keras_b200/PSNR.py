@@ -1,13 +1,26 @@
 """Drop-in mirror of the reference's PSNR.py (PSNR.py:7-109): same function names and return values.
 The sum-of-squared-differences reduction runs on the GPU in fp64 (sr_sum_sq_diff_f64); slicing and the
-final log10 are host scalars."""
+final log10 are host scalars.
+
+Integer inputs keep the reference's dtype arithmetic: `ref_data - target_data` (PSNR.py:14) and `pred - gt`
+(PSNR.py:28) are computed in the arrays' own dtype, so uint8 images (what `np.array(PIL image)` gives) wrap
+around modulo 256, and PSNRTorch's `imdff ** 2` (int exponent) wraps a second time.  Meaningless as a PSNR, but it
+is what the reference returns for those inputs and the goldens of tests/golden/psnr_ref.npz pin it."""
 import math
 
 import numpy as np
 
 
-def _ssd(a, b):
+def _ssd(a, b, int_square=False):
+    """sum((a - b)^2).  Floating inputs: fp64 on the device.  Integer inputs: the difference is taken in the
+    numpy result dtype (wrap-around) as the reference does; int_square additionally squares in that dtype."""
     from sr100 import ops
+    a, b = np.asarray(a), np.asarray(b)
+    if np.result_type(a, b).kind in "iub":
+        d = a - b
+        if int_square:
+            return float(np.sum(d ** 2, dtype=np.float64))   # the squares themselves wrapped: no device SSD form
+        return ops.sum_sq_diff(d.astype(np.float64), np.zeros(d.shape, dtype=np.float64))
     return ops.sum_sq_diff(a, b)
 
 
@@ -27,7 +40,7 @@ def PSNRTorch(pred, gt, shave_border=0):
     height, width = pred.shape[:2]
     pred = pred[shave_border:height - shave_border, shave_border:width - shave_border]
     gt = gt[shave_border:height - shave_border, shave_border:width - shave_border]
-    rmse = math.sqrt(_ssd(pred, gt) / pred.size)
+    rmse = math.sqrt(_ssd(pred, gt, int_square=True) / pred.size)
     if rmse == 0:
         return 100
     return 20 * math.log10(255.0 / rmse)

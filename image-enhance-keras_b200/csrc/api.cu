@@ -26,6 +26,16 @@ extern "C" const char* sr_last_error_string(void) { return sr::g_err; }
 
 extern "C" int sr_version(void) { return 100; }
 
+// 1 when the library was compiled with -DSR_DEV_SWITCHES (timing-only environment switches that can change
+// results); bench.py and the tests refuse such a build.
+extern "C" int sr_dev_switches(void) {
+#ifdef SR_DEV_SWITCHES
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 extern "C" int sr_device_supported(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -916,7 +916,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t slot = wr.slot, ph = wr.phase;
               mbar_wait(&bars->w_empty[slot], ph ^ 1);
-              if ((P.dbg & 1) && w_wrapped) {   // timing experiment: the stage keeps whatever it held
+              if (SR_DBG(P, 1) && w_wrapped) {   // timing experiment: the stage keeps whatever it held
                 if (is_leader) mbar_arrive(&bars->w_full[slot]);
                 wr.advance();
                 continue;
@@ -949,7 +949,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int ch = 0; ch < NCH; ++ch) {
             const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
-            if ((P.dbg & 2) && ac >= 2) {       // timing experiment: the strip buffer keeps whatever it held
+            if (SR_DBG(P, 2) && ac >= 2) {       // timing experiment: the strip buffer keeps whatever it held
               if (is_leader) mbar_arrive(&bars->a_full[slot]);
               ++ac;
               continue;
@@ -1310,7 +1310,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.out_f32 = d->out_f32;
   P.out_tf32 = d->out_tf32;
   {
-    const char* e = getenv("SR100_CONV_DBG");
+    const char* e = dev_getenv("SR100_CONV_DBG");
     P.dbg = e ? atoi(e) : 0;
   }
   P.colsum = d->colsum_f32;

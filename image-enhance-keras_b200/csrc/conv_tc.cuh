@@ -71,7 +71,7 @@ struct ConvKernelParams {
   int out_H, out_W;
   // sub-pixel layers: r > 0 stores channel ch of pixel (y,x) at the depth-to-space position (order as sr_depth_to_space)
   int shuffle_r, shuffle_order, shuffle_C;
-  // development switches of the pair kernel (SR100_CONV_DBG; results are WRONG with either set -- timing only):
+  // development switches of the pair kernel (SR100_CONV_DBG, compiled in only with -DSR_DEV_SWITCHES; results are WRONG with either set -- timing only):
   // 1 = no weight TMA after the first pass over the stage ring, 2 = no activation-strip TMA after the first two
   int dbg;
 };

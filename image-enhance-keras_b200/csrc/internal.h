@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "../../include/sr100.h"
 
 namespace sr {
@@ -14,6 +16,17 @@ inline int check_launch(const char* where) {
   if (e != cudaSuccess) return set_cuda_error(e, where);
   return SR_OK;
 }
+
+// Development switches (timing experiments that make kernels skip operand loads or MMAs, ring / cost overrides):
+// compiled in only with -DSR_DEV_SWITCHES (make DEV=1).  The release library reads no environment variable that
+// can change a result: SR_DBG() is the constant false and dev_getenv() the constant null.
+#ifdef SR_DEV_SWITCHES
+#define SR_DBG(P, bit) (((P).dbg & (bit)) != 0)
+inline const char* dev_getenv(const char* name) { return getenv(name); }
+#else
+#define SR_DBG(P, bit) false
+inline const char* dev_getenv(const char*) { return nullptr; }
+#endif
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

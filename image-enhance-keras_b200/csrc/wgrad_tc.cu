@@ -154,7 +154,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int need = y + kymax - P.p;  // newest input row this output row reads
           for (; next_in <= need; ++next_in) {
             mbar_wait(&bars->a_empty[a_slot], a_ph ^ 1u);
-            if ((P.dbg & 1) && a_wrapped) {
+            if (SR_DBG(P, 1) && a_wrapped) {
               mbar_arrive(&bars->a_full[a_slot]);
             } else {
               mbar_expect_tx(&bars->a_full[a_slot], a_row_bytes);
@@ -169,7 +169,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
           }
           mbar_wait(&bars->b_empty[b_slot], b_ph ^ 1u);
-          if ((P.dbg & 1) && b_wrapped) {
+          if (SR_DBG(P, 1) && b_wrapped) {
             mbar_arrive(&bars->b_full[b_slot]);
           } else {
             mbar_expect_tx(&bars->b_full[b_slot], b_row_bytes);
@@ -243,7 +243,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                   uint32_t x_lo = x_tap + (uint32_t)im * a_img16;
                   uint32_t gl = b_lo + (uint32_t)im * b_img16;
                   for (int s = 0; s < k16n; ++s) {
-                    if (leader && !(P.dbg & 2)) {
+                    if (leader && !SR_DBG(P, 2)) {
                       const uint64_t gdesc = ((uint64_t)hi << 32) | (uint64_t)gl;    // A: G rows, M = co
                       const uint64_t xdesc = ((uint64_t)hi << 32) | (uint64_t)x_lo;  // B: shifted X rows, N = ci (x2)
                       umma_bf16(d, gdesc, xdesc, wide ? kIdescMN256 : kIdescMN, accf);
@@ -441,7 +441,7 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   static const Item k3_items[3][4] = {{{0, 0, 2}, {2, 0, 1}, {-1, 0, 0}, {-1, 0, 0}},
                                       {{0, 1, 2}, {2, 1, 1}, {-1, 0, 0}, {-1, 0, 0}},
                                       {{0, 2, 2}, {2, 2, 1}, {-1, 0, 0}, {-1, 0, 0}}};
-  const char* vp_env = getenv("SR100_WGRAD_VPAIR");
+  const char* vp_env = dev_getenv("SR100_WGRAD_VPAIR");
   const bool vpair = !(vp_env && atoi(vp_env) == 0) && (P.k == 3 || P.k == 5);
   P.ngroups = (ntaps + 3) / 4;
   int max_span = 0;
@@ -517,7 +517,7 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
       }
       if (!grew) break;
     }
-    if (const char* e = getenv("SR100_WGRAD_RING")) {   // development override: "<ring>,<g slots>"
+    if (const char* e = dev_getenv("SR100_WGRAD_RING")) {   // development override: "<ring>,<g slots>"
       int r_ = 0, b_ = 0;
       if (sscanf(e, "%d,%d", &r_, &b_) == 2 && r_ >= min_ring && r_ <= kMaxRing && b_ >= min_b && b_ <= kMaxBSlots &&
           fixed + r_ * a_row + b_ * b_row <= kWgSmemBudget) {
@@ -544,7 +544,7 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   // N = 256 MMA for two taps reads 12 KB of shared memory instead of 16: 0.75 of a single tap, and measured so)
   double cost[kMaxGroups], total_cost = 0;
   {
-    const char* e = getenv("SR100_WGRAD_PCOST");
+    const char* e = dev_getenv("SR100_WGRAD_PCOST");
     const double pair_cost = e ? atof(e) : 1.5;    // cost of a pair item in single-tap units (measured optimum)
     for (int g = 0; g < P.ngroups; ++g) {
       cost[g] = 0;
@@ -591,7 +591,7 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   }
   P.partial = reinterpret_cast<float*>(d->workspace);
   {
-    const char* e = getenv("SR100_WGRAD_DBG");
+    const char* e = dev_getenv("SR100_WGRAD_DBG");
     P.dbg = e ? atoi(e) : 0;
   }
   pl->scale = d->scale;

@@ -123,12 +123,12 @@ def _listdir_images(d):
 
 def image_count():
     """img_utils.py:126-128."""
-    return len([name for name in os.listdir(output_path + "X/")])
+    return len(_listdir_images(output_path + "X/"))      # the same filter as the generators (no dotfiles)
 
 
 def val_image_count():
     """img_utils.py:130-131."""
-    return len([name for name in os.listdir(validation_output_path + "X/")])
+    return len(_listdir_images(validation_output_path + "X/"))
 
 
 def _imread_rgb(path):

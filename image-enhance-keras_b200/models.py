@@ -5,9 +5,10 @@ classes; the Keras/TensorFlow graph is replaced by the sm_100a engine (sr100.eng
 the libsr100 C ABI.  There is no CPU path: constructing a model's graph needs a B200.
 
 Covered: psnr helpers (models.py:43-90), BaseSuperResolutionModel (:93-182), upscaleStepPatch
-(:184-415, the CLI path), DifvdsrDouble (:1146-1270) and the Lambda helpers it uses (:977-986,
-:1383-1399, :1451), upscale(mode='fast') (:606-852).  upscalePatch / upscale(mode='patch') / evaluate and
-Difvdsr4 / Difvdsr are "next" rows of SURVEY.md section 8(f) and raise NotImplementedError.
+(:184-415, the CLI path), upscalePatch (:419-604) and upscale (:606-852, 'fast' and 'patch' modes) on the
+alternative tilers of sr100.alt_tilers, evaluate (:159-163, 1519-1622), DifvdsrDouble (:1146-1270) with the
+Lambda helpers it uses (:977-986, :1383-1399, :1451), and the Difvdsr4 (:992-1142) / Difvdsr (:1274-1357)
+graphs (sr100.planenet).  _evaluate_denoise is out of scope (auto-encoder models this file does not define).
 """
 from __future__ import print_function, division
 

@@ -99,6 +99,7 @@ SIGNATURES = {
     "sr_last_error_string": (C.c_char_p, []),
     "sr_version": (_i, []),
     "sr_device_supported": (_i, []),
+    "sr_dev_switches": (_i, []),
     "sr_abi_struct_size": (_sz, [_i]),
     "sr_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "sr_conv_plan_run": (_i, [_vp, _vp]),

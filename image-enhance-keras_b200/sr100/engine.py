@@ -156,7 +156,10 @@ class _Stage:
                     for step in self.steps:
                         step(cst)
                 self.cuda_graph = gr
-            except Exception:  # noqa: BLE001  (capture unsupported in this context: stay eager)
+            except Exception as e:  # noqa: BLE001  (capture unsupported in this context: stay eager, but say so)
+                import warnings
+                warnings.warn("sr100: CUDA graph capture of a forward stage failed (%s: %s); running eagerly"
+                              % (type(e).__name__, e), RuntimeWarning)
                 eng.use_graphs = False
         self.ran_eager = True
 

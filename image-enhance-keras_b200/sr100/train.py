@@ -361,7 +361,10 @@ class Trainer:
                 with torch.cuda.graph(gr):
                     body(L.stream_ptr())
                 g.cuda_graph = gr
-            except Exception:  # noqa: BLE001  (capture unsupported here: stay eager)
+            except Exception as e:  # noqa: BLE001  (capture unsupported here: stay eager, but say so)
+                import warnings
+                warnings.warn("sr100: CUDA graph capture of the training step failed (%s: %s); running eagerly"
+                              % (type(e).__name__, e), RuntimeWarning)
                 self.engine.use_graphs = False
         g.ran_eager = True
 

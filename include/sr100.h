@@ -31,6 +31,10 @@ const char* sr_last_error_string(void);
 int sr_version(void);
 /* Returns 1 when the current device is compute capability 10.x (sm_100a cubins can run). */
 int sr_device_supported(void);
+/* 1 when the library was built with -DSR_DEV_SWITCHES (development build: environment variables such as
+ * SR100_CONV_DBG can make kernels skip operand loads, i.e. give wrong results for timing experiments); the
+ * default build returns 0 and reads no environment variable that can change a result. */
+int sr_dev_switches(void);
 /* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
  * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
  * 5 sr_score_result; 0 for anything else. */

@@ -190,6 +190,11 @@ def main():
     psnr["PSNRTorch_same"] = np.array(P.PSNRTorch(ya, ya, 0))
     psnr["psnrVDSR_y_2"] = np.array(P.psnrVDSR(yb, ya, 2))
     psnr["psnrSVLAB_u8"] = np.array(P.psnrSVLAB(a, b))
+    # integer inputs: the reference subtracts in the arrays' own dtype (uint8 wrap-around), and PSNRTorch also squares
+    # in it (`imdff ** 2` with an int exponent stays uint8) -- the mirror reproduces both
+    psnr["psnrVDSR_u8_2"] = np.array(P.psnrVDSR(b, a, 2))
+    psnr["PSNRTorch_u8"] = np.array(P.PSNRTorch(b, a, 0))
+    psnr["psnrNITRE_u8"] = np.array(P.psnrNITRE(b, a, 0))
     psnr["im2double_a"] = P.im2double(a)[:2, :3]
     psnr["im2doubleZ_a"] = P.im2doubleZ(a)[:2, :3]
     np.savez_compressed(os.path.join(OUT, "psnr_ref.npz"), **psnr)

@@ -63,6 +63,10 @@ def test_rgb2y_and_psnr_mirrors_match_reference_golden(golden_dir):
     assert PSNR.PSNRTorch(ya, ya, 0) == 100
     assert PSNR.psnrVDSR(yb, ya, 2) == pytest.approx(float(z["psnrVDSR_y_2"]), abs=1e-9)
     assert PSNR.psnrSVLAB(a, b) == pytest.approx(float(z["psnrSVLAB_u8"]), abs=1e-9)
+    # uint8 inputs: the reference's own-dtype (wrap-around) differences, PSNR.py:14,28-29
+    assert PSNR.psnrVDSR(b, a, 2) == pytest.approx(float(z["psnrVDSR_u8_2"]), abs=1e-9)
+    assert PSNR.PSNRTorch(b, a, 0) == pytest.approx(float(z["PSNRTorch_u8"]), abs=1e-9)
+    assert PSNR.psnrNITRE(b, a, 0) == pytest.approx(float(z["psnrNITRE_u8"]), abs=1e-9)
     assert np.array_equal(PSNR.im2double(a)[:2, :3], z["im2double_a"])
     assert np.array_equal(PSNR.im2doubleZ(a)[:2, :3], z["im2doubleZ_a"])
     import models

@@ -1,17 +1,24 @@
-"""Benchmark of the x4 SR hot path (BASELINE.json metric: x4 output megapixels/sec).
+"""Benchmark of the x4 SR hot path (BASELINE.json metric: x4 output megapixels/sec at 1/2/4/8 B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only headline,set5,train,config5,config1]
 
-Workload (config.workload = "set5_x4_tiled", BASELINE.json configs[1]): five synthetic RGB images of the Set5
-shapes (512x512, 288x288, 256x256, 280x280, 344x228) -> x4 through the reference's tiling (96/64 patches,
-81+25+25+25+30 = 186 tiles, 8-px crop stitch) and the 86-conv DifvdsrDouble stack with random-init weights,
-then Y-PSNR / Y-SSIM / RGB-SSIM scoring of every output.  One step = one pass over the five images
-(9.079 output MP).  N > 1: one process per GPU (torchrun), every rank runs the same workload on its own
-images, no data-path collective (weak scaling); value = total MP / max-over-ranks device time.
+Headline workload (config.workload = "batch64_339x510_x4_tiled", BASELINE.json configs[2]):
+64 synthetic RGB images of 339x510 (seeds 100..163) -> 1356x2040 through the reference's tiling (96/64 patches,
+54 tiles per image, 8-px crop stitch; models.py:184-415) and the 86-conv DifvdsrDouble stack with random-init
+weights.  One step = one pass over all 64 images (177.0 output MP); the images are dealt round-robin to the N
+ranks (one process per GPU, torchrun), every rank holds a weight replica, there is no data-path collective:
+STRONG scaling, the total work is fixed.  value = 177.0 MP x K / max-over-ranks device time.
 
-value: inputs resident in HBM when the timed region starts.  e2e: the same step through the public API
-(models.DifvdsrDouble.upscale_arrays + scorpath.score_pair) with host buffers: H2D of the uint8 inputs and
-D2H of the uint8 outputs and the scores inside the timed region.
+value: this rank's images resident in HBM when the timed region starts (CUDA events).  e2e: the same step through
+the public API (models.DifvdsrDouble.upscale_arrays) with pinned HOST buffers: H2D of the uint8 inputs and D2H of
+the uint8 outputs inside the timed region (wall clock around a device synchronize).
+
+The same JSON line carries the other BASELINE configs as objects (each its own timed region, same rules):
+  "set5"       configs[1]: five Set5-shaped images tiled + Y-PSNR / Y-SSIM / RGB-SSIM scoring (every rank its own copy)
+  "train_step" configs[3]: 48x48 LR patches, GLOBAL batch 256 split over the ranks, forward + dgrad/wgrad on the
+               tensor cores, NCCL all-reduce of the 87 MB gradient arena, fused Adam (strong scaling)
+  "config5"    configs[4]: one 1080x1920 image, its 510 live tiles sharded over the ranks, rank 0 stitches
+  "config1"    configs[0]: one 128x128 patch -> 512x512 through model.predict (latency)
 """
 import argparse
 import json
@@ -28,23 +35,35 @@ for p in (PKG, ROOT):
         sys.path.insert(0, p)
 
 SET5_SHAPES = [(512, 512), (288, 288), (256, 256), (280, 280), (344, 228)]   # (H, W) of the Set5 GT files
+B_IMAGES, B_H, B_W = 64, 339, 510                                             # BASELINE configs[2]
 METRIC = "x4_output_megapixels_per_sec"
 UNIT = "MP/s"
 
 
-def synth_images(seed):
+def synth_image(seed, h, w):
+    """uint8 [h,w,3]: uniform noise through a 5x5 box blur (not white noise), SURVEY.md 8d."""
     import numpy as np
     from scipy.ndimage import uniform_filter
     rng = np.random.default_rng(seed)
-    out = []
-    for h, w in SET5_SHAPES:
-        img = rng.integers(0, 256, size=(h + 4, w + 4, 3)).astype(np.float32)
-        out.append(uniform_filter(img, size=(5, 5, 1))[2:-2, 2:-2].astype(np.uint8))   # 5x5 box blur: not white noise
-    return out
+    img = rng.integers(0, 256, size=(h + 4, w + 4, 3)).astype(np.float32)
+    return uniform_filter(img, size=(5, 5, 1))[2:-2, 2:-2].astype(np.uint8)
 
 
-def output_megapixels():
-    return sum(16 * h * w for h, w in SET5_SHAPES) / 1e6
+def synth_set5(seed):
+    return [synth_image(seed * 16 + i, h, w) for i, (h, w) in enumerate(SET5_SHAPES)]
+
+
+def headline_mp():
+    return B_IMAGES * 16 * B_H * B_W / 1e6
+
+
+def headline_config():
+    """The static description of the headline workload: identical in both arms (own and --impl reference)."""
+    return {"workload": "batch64_339x510_x4_tiled", "baseline_config": 2, "images": B_IMAGES, "lr_shape": [B_H, B_W],
+            "hr_shape": [4 * B_H, 4 * B_W], "patch": 96, "step": 64, "tiles_per_image": 54, "tiles": 54 * B_IMAGES,
+            "output_mp_per_step": headline_mp(), "sharding": "images round-robin over ranks, no data-path collective",
+            "weights": "glorot_uniform random init (seed 1234), the same replica on every rank",
+            "l2": "every conv launch streams 0.36-2.9 GB of activations (> 126 MB L2); no flush needed"}
 
 
 class ClockSampler:
@@ -109,16 +128,18 @@ def load_peaks():
 
 
 def cpu_reference_rate(threads, budget_s=15.0, max_tiles=25):
-    """Oracle (CPU restatement of the reference graph; Keras/TF are not installable offline) on a bounded
-    sample: the first n 96x96 tiles of the 256x256 'butterfly' image (25 tiles -> 1.049 output MP)."""
+    """Oracle (CPU restatement of the reference graph; Keras/TF are not installable offline) on a bounded sample of
+    the headline workload: the first n of the 54 96x96 tiles of image 0 (339x510, the reference's literal tiling:
+    every tile through the full network).  MP = n/54 of that image's 2.766 output MP."""
     import numpy as np
     import torch
     from oracle import model as om
     from oracle import tiling as ot
     torch.set_num_threads(threads)
-    img = synth_images(0)[2]
+    img = synth_image(100, B_H, B_W)
     canvas = ot.make_canvas(img, 96, 64)
     patches, counts = ot.extract_patches_step(canvas, (96, 96), 64)
+    assert patches.shape[0] == 54
     x = patches.astype(np.float32) / 255.
     weights = om.init_weights(1234)
     m = om.DifvdsrDoubleOracle(weights)
@@ -131,11 +152,15 @@ def cpu_reference_rate(threads, budget_s=15.0, max_tiles=25):
         y = m(torch.from_numpy(x[:n]))
         dt = time.time() - t0
     assert y.shape[0] == n
-    mp = (n / float(patches.shape[0])) * (16 * 256 * 256 / 1e6)
-    return mp / dt, "first %d of 25 96x96 tiles of the 256x256 image, torch CPU fp32 oracle, %.1f s" % (n, dt), dt
+    mp = (n / 54.0) * (16 * B_H * B_W / 1e6)
+    return mp / dt, "first %d of the 54 96x96 tiles of one 339x510 image, torch CPU fp32 oracle, %.1f s" % (n, dt), dt
 
 
 def run_reference(args):
+    """The reference arm: the reference's CPU path for the same metric/config on the host cores.  Keras 2 / TF 1 cannot
+    be installed offline, so it is the CPU restatement (oracle/model.py, kind 'port'); each step times a bounded sample
+    (8 tiles) of the workload.  Rank 0 alone runs it -- ONE CPU process whatever N is, so the driver's ratio at N > 1
+    compares N GPUs with the same single host."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,15 +174,14 @@ def run_reference(args):
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": output_megapixels() / value * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "set5_x4_tiled", "images": SET5_SHAPES, "tiles": 186, "patch": 96, "step": 64,
-                   "output_mp_per_step_per_gpu": output_megapixels(), "weights": "glorot_uniform random init",
-                   "sample": "each step times a bounded sample of the workload's tiles on the host cores and scales to "
-                             "the full step (all 186 tiles of the literal reference tiling)"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": headline_mp() / value * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": headline_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample + " per step; Keras/TensorFlow cannot be installed offline, so this is the "
-                                            "CPU restatement of the reference graph (oracle/model.py)"},
+                         "sample": sample + " per step (ms_per_step scales that rate to the full 64-image step); "
+                                            "Keras/TensorFlow cannot be installed offline, so this is the CPU "
+                                            "restatement of the reference graph (oracle/model.py); one host process "
+                                            "whatever --gpus is"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -170,6 +194,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="sr100")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", type=str, default="headline,set5,train,config5,config1",
+                    help="comma list of parts to run (headline is needed for a valid line)")
+    ap.add_argument("--profile", action="store_true", help="ncu pass: honour --warmup as given, skip the extras")
+    ap.add_argument("--allow-dev-build", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -178,11 +206,19 @@ def main():
     import torch
     from sr100 import dist as D
     from sr100 import _lib as L
-    from sr100 import ops
     rank, local_rank, world = D.init_process_group()
     torch.cuda.set_device(local_rank if world > 1 else 0)
     import models
     import scorpath
+    from sr100.engine import glorot_uniform_weights
+    lib = L.require_device()
+    if lib.sr_dev_switches() and not args.allow_dev_build:
+        raise SystemExit("libsr100.so is a development build (-DSR_DEV_SWITCHES): its numbers are not bench values")
+    parts = set(args.only.split(","))
+    if args.profile:
+        parts = {"headline"}
+    warmup = args.warmup if args.profile else max(args.warmup, 3)
+    steps = args.steps
 
     def pinned(a):
         """Host arrays of the end-to-end path live in page-locked memory (what a serving loop would reuse)."""
@@ -190,68 +226,63 @@ def main():
         t.numpy()[...] = a
         return t.numpy()
 
-    images = [pinned(im) for im in synth_images(100 + rank)]
-    m = models.DifvdsrDouble(1)
-    model = m.create_model(96, 96)                      # random-init glorot weights (no trained weights offline)
-    eng = model.engine
-    from sr100.engine import glorot_uniform_weights
-    eng.set_weights_dict(glorot_uniform_weights(seed=1234))   # the same replica on every rank
-    dev_imgs = [torch.from_numpy(im).cuda() for im in images]
-    rng = np.random.default_rng(7 + rank)
-    gts = [pinned(rng.integers(0, 256, size=(4 * h, 4 * w, 3)).astype(np.uint8)) for h, w in SET5_SHAPES]
-    dev_gts = [torch.from_numpy(g).cuda() for g in gts]
-    score_buf = torch.zeros(5, 64, dtype=torch.uint8, device="cuda")
-
-    def step_resident(full=False):
-        canv = eng.upscale_images_device(dev_imgs, full_canvas=full)
-        score_buf.zero_()
-        for i, (c, g) in enumerate(zip(canv, dev_gts)):
-            h, w = g.shape[0], g.shape[1]
-            sr = c[:h, :w].contiguous() if full else c
-            L.check(eng.lib.sr_score_pair_u8(L.ptr(sr), L.ptr(g), h, w, 10, L.ptr(score_buf[i]), L.stream_ptr()))
-        return canv
-
-    def step_e2e():
-        outs = m.upscale_arrays(images)
-        return [scorpath.score_pair(g, o, 10) for g, o in zip(gts, outs)]
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
+    def timed(fn, k, w):
+        """W warm-up calls, then K calls between barrier + synchronize, CUDA events, max over ranks (seconds)."""
+        for _ in range(w):
             fn()
         D.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         e1.record()
         torch.cuda.synchronize()
         D.barrier()
         return D.max_over_ranks(e0.elapsed_time(e1) / 1e3)
 
+    def timed_wall(fn, k, w):
+        """The end-to-end variant: wall clock brackets the host work too (events alone would miss the D2H waits)."""
+        for _ in range(w):
+            fn()
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        D.barrier()
+        return D.max_over_ranks(dt)
+
+    m = models.DifvdsrDouble(1)
+    model = m.create_model(96, 96)                      # random-init glorot weights (no trained weights offline)
+    eng = model.engine
+    eng.set_weights_dict(glorot_uniform_weights(seed=1234))   # the same replica on every rank
+    peaks = load_peaks()
+    line = {}
+
+    # =============================================================== headline: configs[2], 64 x 339x510, sharded by image
+    my_ids = D.shard_round_robin(B_IMAGES, rank, world)
+    images = [pinned(synth_image(100 + i, B_H, B_W)) for i in my_ids]
+    dev_imgs = [torch.from_numpy(im).cuda() for im in images]
+
+    def step_resident(full=False):
+        return eng.upscale_images_device(dev_imgs, full_canvas=full)
+
+    def step_e2e():
+        return m.upscale_arrays(images)
+
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
         sampler.start()
-    t_res = timed(step_resident, args.steps, max(args.warmup, 3))
+    t_res = timed(step_resident, steps, warmup)
     clocks = sampler.stop() if rank == 0 else None
-    # end to end: wall clock brackets the host work too (events alone would miss the D2H waits)
-    for _ in range(2):
-        step_e2e()
-    D.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    t_e2e = D.max_over_ranks(time.perf_counter() - t0)
-
-    mp_step = output_megapixels()
-    value = world * mp_step * args.steps / t_res
-    e2e = world * mp_step * args.steps / t_e2e
-
-    # the reference's literal tile set (all 186 tiles, full 384x384 HR stage) for comparison: same output pixels
-    t_full = timed(lambda: step_resident(True), max(2, args.steps // 2), 3)
-    value_full = world * mp_step * max(2, args.steps // 2) / t_full
+    mp_step = headline_mp()
+    value = mp_step * steps / t_res
+    e2e_steps = steps if not args.profile else 1
+    t_e2e = timed_wall(step_e2e, e2e_steps, 2 if not args.profile else 0)
+    e2e = mp_step * e2e_steps / t_e2e
 
     # ---- roofline of the dominant kernel (conv_tc_pair_kernel): per-launch CUDA events over one more step
     from sr100.engine import _Plan
@@ -274,12 +305,13 @@ def main():
     n_conv = sum(1 for _, _, is_conv in evs if is_conv)
     total_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
     conv_flops = eng.last_flops()
-    peaks = load_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    rpeaks = peaks
     if eng.tf32:     # SR100_PRECISION=tf32: kind::tf32 MMAs run at half the bf16 rate; no measured tf32 peak exists
-        peaks = {"sustained": peaks["sustained"] / 2, "burst": peaks["burst"] / 2,
-                 "src": peaks["src"] + " (halved: tf32 = 0.5x bf16 tensor rate)"}
-    launches_per_step = len(evs) + 5 + 5 + 5          # libsr100 kernels only: + gathers, stitches, scores
+        rpeaks = {"sustained": peaks["sustained"] / 2, "burst": peaks["burst"] / 2,
+                  "src": peaks["src"] + " (halved: tf32 = 0.5x bf16 tensor rate)"}
+    # libsr100 kernels per step on this rank: the stage launches + one batched gather + one stitch per image
+    launches_per_step = len(evs) + 1 + len(dev_imgs)
     traffic, traffic_src = None, None
     prof_dir = os.path.join(ROOT, "profiles")
     for cand in sorted(os.listdir(prof_dir), reverse=True) if os.path.isdir(prof_dir) and not eng.tf32 else []:
@@ -291,44 +323,161 @@ def main():
                 pass
             break
     roofline = {"bound": "tensor", "kernel": "conv_tc_pair_kernel", "achieved": round(achieved, 1),
-                "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
-                "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                "frac_of_burst_peak": round(achieved / peaks["burst"], 4), "traffic": traffic,
+                "peak": rpeaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / rpeaks["sustained"], 4),
+                "peak_source": rpeaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "frac_of_burst_peak": round(achieved / rpeaks["burst"], 4), "traffic": traffic,
                 "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "launches": n_conv, "avg_launch_ms": round(conv_ms / n_conv, 4),
                 "share_of_forward": round(conv_ms / total_ms, 4),
-                "executed_flops_per_step": conv_flops,
-                "reference_tiling_flops_per_step": 189595215986688.0}
+                "executed_flops_per_step_this_rank": conv_flops,
+                "reference_tiling_flops_per_step": 54.0 * B_IMAGES * eng.conv_flops(1, 96, 96)}
+    # the reference's literal tile set (all 54 tiles per image, full 384x384 HR stage): same output pixels
+    value_full = None
+    if not args.profile:
+        k_full = 2
+        t_full = timed(lambda: step_resident(True), k_full, 1)
+        value_full = mp_step * k_full / t_full
+    h2d = sum(im.nbytes for im in images)
+    d2h = sum(16 * im.nbytes for im in images)
+    h2d, d2h = int(D.sum_over_ranks(h2d)), int(D.sum_over_ranks(d2h))
+    launches_total = int(D.sum_over_ranks(launches_per_step)) * steps
+    eng._graphs.clear()
+    torch.cuda.empty_cache()
+
+    # =============================================================== configs[1]: Set5 tiled + scoring (every rank its own copy)
+    if "set5" in parts:
+        s_imgs = [pinned(im) for im in synth_set5(100 + rank)]
+        s_dev = [torch.from_numpy(im).cuda() for im in s_imgs]
+        rng = np.random.default_rng(7 + rank)
+        gts = [pinned(rng.integers(0, 256, size=(4 * h, 4 * w, 3)).astype(np.uint8)) for h, w in SET5_SHAPES]
+        dev_gts = [torch.from_numpy(g).cuda() for g in gts]
+        score_buf = torch.zeros(5, 64, dtype=torch.uint8, device="cuda")
+
+        def set5_resident():
+            canv = eng.upscale_images_device(s_dev)
+            score_buf.zero_()
+            for i, (c, g) in enumerate(zip(canv, dev_gts)):
+                L.check(lib.sr_score_pair_u8(L.ptr(c), L.ptr(g), g.shape[0], g.shape[1], 10, L.ptr(score_buf[i]),
+                                             L.stream_ptr()))
+
+        def set5_e2e():
+            outs = m.upscale_arrays(s_imgs)
+            return [scorpath.score_pair(g, o, 10) for g, o in zip(gts, outs)]
+
+        mp5 = sum(16 * h * w for h, w in SET5_SHAPES) / 1e6
+        k5 = max(steps, 10)
+        t5 = timed(set5_resident, k5, 3)
+        t5e = timed_wall(set5_e2e, k5, 2)
+        line["set5"] = {"workload": "set5_x4_tiled (BASELINE configs[1]): 5 images, 186 tiles (154 run), gather + stack + "
+                                    "stitch + Y-PSNR/Y-SSIM/RGB-SSIM; every rank runs its own copy (replicas)",
+                        "value_per_gpu": round(mp5 * k5 / t5, 3), "e2e_per_gpu": round(mp5 * k5 / t5e, 3), "unit": UNIT,
+                        "ms_per_step": round(t5 / k5 * 1e3, 3), "steps": k5}
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+
+    # =============================================================== configs[4]: one 1080x1920 image, tiles sharded over ranks
+    if "config5" in parts:
+        big = torch.from_numpy(synth_image(9, 1080, 1920)).cuda()
+        k = max(3, min(steps, 5))
+        t = timed(lambda: eng.upscale_image_sharded(big), k, 3)
+        mpb = 16 * 1080 * 1920 / 1e6
+        line["config5"] = {"workload": "1 x (1080x1920) -> 4320x7680 (BASELINE configs[4]): 510 live tiles of 558 sharded "
+                                       "over the ranks in contiguous column-major ranges, " + eng.sharded_gather_description, "value": round(mpb * k / t, 2), "unit": UNIT,
+                           "ms_per_step": round(t / k * 1e3, 3), "steps": k, "scaling": "strong"}
+        del big
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+
+    # =============================================================== configs[0]: one 128x128 patch (latency)
+    if "config1" in parts:
+        x1 = torch.rand(1, 128, 128, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+        t = timed(lambda: eng.forward_device(x1), 100, 20)
+        f1 = eng.last_flops()
+        line["config1"] = {"workload": "1 x 128x128 -> 512x512 through model.predict (BASELINE configs[0]), CUDA-graph replay; "
+                                       "every rank runs its own copy", "ms": round(t / 100 * 1e3, 4),
+                           "value_per_gpu": round(0.262144 * 100 / t, 2), "unit": UNIT,
+                           "tflops": round(f1 * 100 / t / 1e12, 1),
+                           "frac_of_sustained_peak": round(f1 * 100 / t / 1e12 / peaks["sustained"], 4)}
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+
+    # =============================================================== configs[3]: training step, global batch 256
+    if "train" in parts and not eng.tf32:
+        from sr100.train import Trainer
+        GB, S = 256, 48
+        lo, hi = D.shard_range(GB, rank, world)
+        tr = Trainer(eng)
+        g = tr.graph(hi - lo, S, S)
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        xs = torch.rand((GB, S, S, 3), device="cuda", generator=gen)       # the same global batch on every rank
+        ys = torch.rand((GB, 4 * S, 4 * S, 3), device="cuda", generator=gen)
+        g.x_in.copy_(xs[lo:hi])
+        g.y_true.copy_(ys[lo:hi])
+        del xs, ys
+        kt = max(3, min(steps, 10))
+        for _ in range(3):
+            tr.step_device(g)
+        D.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        upd = []
+        e0.record()
+        for _ in range(kt):
+            tr.forward_backward_device(g)
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            tr.apply_gradients()
+            u1.record()
+            upd.append((u0, u1))
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = D.max_over_ranks(e0.elapsed_time(e1) / kt)
+        upd_ms = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in upd) / kt)
+        flops = tr.step_flops(g)
+        line["train_step"] = {
+            "workload": "training step (BASELINE configs[3]): 48x48 LR -> 192x192, global batch 256 split over the ranks, "
+                        "forward + dgrad/wgrad bf16 on the tensor cores, NCCL all-reduce (sum) of the flat fp32 gradient "
+                        "arena, fused Keras-Adam, weight repack", "global_batch": GB, "per_gpu_batch": hi - lo,
+            "ms_per_step": round(ms, 3), "images_per_s": round(GB / ms * 1e3, 1), "steps": kt,
+            "allreduce_adam_repack_ms": round(upd_ms, 3),
+            "allreduce_bytes": tr.grads.numel() * 4 if world > 1 else 0,
+            "comm": tr.comm_description() if hasattr(tr, "comm_description") else "one all_reduce after backward",
+            "algorithmic_tflop_per_step_per_gpu": round(flops / 1e12, 3),
+            "tflops_per_gpu": round(flops / (ms * 1e-3) / 1e12, 1),
+            "frac_of_sustained_peak": round(flops / (ms * 1e-3) / 1e12 / peaks["sustained"], 4),
+            "loss": tr.last_loss(g) if hasattr(tr, "last_loss") else float(g.loss_sum.item()) / g.n_local,
+            "scaling": "strong"}
+        del tr, g
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
     cpu = None
-    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (bounded sample, ~10-15 s of CPU work)
+    if not args.no_cpu_baseline and world == 1 and not args.profile:   # rank 0 at N = 1 only (~10-15 s of CPU work)
         threads = os.cpu_count() or 1
         v, sample, _ = cpu_reference_rate(threads)
         cpu = {"value": round(v, 5), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-    # upscale_arrays: uint8 images in, cropped uint8 x4 images out (pinned); scorpath.score_pair: GT + SR in, scores out
-    h2d = sum(im.nbytes for im in images) + sum(g_.nbytes for g_ in gts) + sum(16 * im.nbytes for im in images)
-    d2h = sum(16 * im.nbytes for im in images) + 5 * 56
-    line = {
-        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(t_res / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": eng.precision, "data": "synthetic",
-        "config": {"workload": "set5_x4_tiled", "images": SET5_SHAPES, "tiles": 186, "patch": 96, "step": 64,
-                   "tiles_run": tiles_run, "hr_stage_extents": hr_shapes,
-                   "dead_work_elimination": "tiles that own no pixel of the final 4Hx4W image are not run; the HR "
-                                            "stage runs on the 272x272 corner of each 384x384 patch that the stitch "
-                                            "can see (receptive-field radius 7); output pixels bit-identical to the "
-                                            "full tiling (tests/test_gpu_deadwork.py, tests/test_tile_plan.py), which is timed as value_full_tiles",
-                   "output_mp_per_step_per_gpu": mp_step, "weights": "glorot_uniform random init",
-                   "residual_stream": "fp32 at LR and HR (tf32 operands)" if eng.tf32 else "fp32 at LR, bf16 at HR",
-                   "l2": "every conv launch streams 0.36-2.9 GB of activations (> 126 MB L2); no flush needed"},
-        "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "value_full_tiles": round(value_full, 3),
-        "gpu_launches": launches_per_step * args.steps,
+    out = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(t_res / steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": eng.precision, "data": "synthetic",
+        "config": headline_config(),
+        "detail": {"images_this_rank": len(my_ids), "tiles_run_this_rank": tiles_run, "hr_stage_extents": hr_shapes,
+                   "dead_work_elimination": "tiles that own no pixel of the final 4Hx4W image are not run (48 of 54 per "
+                                            "image are); the HR stage runs on the 272x272 corner of each 384x384 patch "
+                                            "that the stitch can see (receptive-field radius 7); output pixels "
+                                            "bit-identical to the full tiling (tests/test_gpu_deadwork.py, "
+                                            "tests/test_tile_plan.py), which is timed as value_full_tiles",
+                   "residual_stream": "fp32 at LR and HR (tf32 operands)" if eng.tf32 else "fp32 at LR, bf16 at HR"},
+        "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "models.DifvdsrDouble.upscale_arrays (pinned host uint8 in / out, per rank)"},
+        "value_full_tiles": None if value_full is None else round(value_full, 3),
+        "gpu_launches": launches_total,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    out.update(line)
+    print(json.dumps(out), flush=True)
 
 
 def _shutdown():

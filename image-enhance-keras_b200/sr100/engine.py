@@ -579,6 +579,8 @@ class Engine:
             off += n
         return res
 
+    sharded_gather_description = "fp32 patch outputs gathered on rank 0 (NCCL), which stitches"
+
     def upscale_image_sharded(self, img_u8, patch=96, step=64, scale=4):
         """One (large) image with its tiles sharded over the ranks of the process group (BASELINE config
         5): every rank runs a contiguous range of the column-major live-tile index through the conv stack -- no

@@ -288,7 +288,9 @@ class Trainer:
         self.tail_colw_packed = torch.empty(self.lib.sr_packed_weight_bytes(1, NUMK), dtype=torch.uint8, device=dev)
         self.packed_t = {}      # name -> packed weights of the input-gradient conv
         self._pack_table_t = None
-        self._graphs = {}
+        self._graphs = {}      # (NB, H, W) -> _TrainGraph, most recently used last (see graph())
+        self.max_graphs = 3    # the full minibatch, the short last batch of a pass, the validation shape
+        self.sync_replicas()
         self.repack_t()
 
     # ------------------------------------------------------------------ views into the flat arenas
@@ -321,13 +323,40 @@ class Trainer:
         L.check(self.lib.sr_pack_conv_weights(L.ptr(self.tail_colw), 1, NUMK, 0, L.ptr(self.tail_colw_packed),
                                               L.stream_ptr()))
 
+    def sync_replicas(self):
+        """Data parallelism needs identical replicas: broadcast rank 0's parameters and Adam state (m, v, t) to every
+        rank (a no-op for one process).  Called at construction and after loading weights on rank 0 only; without it
+        every rank would start from its own random initialisation and the averaged gradient would be applied to
+        different weights (the ranks never meet again)."""
+        import torch.distributed as tdist
+        if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
+            return False
+        t = torch.tensor([float(self.t)], dtype=torch.float64, device=self.engine.device)
+        for buf in (self.engine.param_arena, self.m, self.v, t):
+            tdist.broadcast(buf, src=0)
+        self.t = int(t.item())
+        self.engine.repack()
+        if self._pack_table_t is not None:
+            self.repack_t()
+        return True
+
     def graph(self, NB, H, W):
+        """Buffers + launch lists for one minibatch shape.  A few shapes stay resident (LRU): `fit` alternates between
+        the full batch, the short last batch of every pass over the data (img_utils._index_generator) and the
+        validation shape, and rebuilding ~450 plans + a CUDA graph each time would stall every epoch.  If a new shape
+        does not fit next to the cached ones, the others are dropped and it is tried once more."""
         key = (NB, H, W)
-        g = self._graphs.get(key)
+        g = self._graphs.pop(key, None)
         if g is None:
-            self._graphs.clear()   # one minibatch shape resident at a time (saved activations are large)
-            g = _TrainGraph(self, NB, H, W)
-            self._graphs[key] = g
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            try:
+                g = _TrainGraph(self, NB, H, W)
+            except torch.cuda.OutOfMemoryError:
+                self._graphs.clear()
+                torch.cuda.empty_cache()
+                g = _TrainGraph(self, NB, H, W)
+        self._graphs[key] = g      # most recently used last
         return g
 
     # ------------------------------------------------------------------ steps
@@ -391,7 +420,19 @@ class Trainer:
         g = self.graph(*x_shape[:3])
         self._load(g, x, y)
         self.step_device(g)
-        return float(g.loss_sum.item()) / g.n_local
+        return self.last_loss(g)
+
+    def last_loss(self, g):
+        """MSE of the step just run, over the GLOBAL minibatch: sum of squared errors and element counts are summed
+        over the ranks (what a single process would report for the concatenated batch)."""
+        from .dist import all_reduce_sum_
+        t = torch.stack([g.loss_sum[0], torch.tensor(float(g.n_local), dtype=torch.float64, device=g.loss_sum.device)])
+        all_reduce_sum_(t)
+        sse, n = t.tolist()
+        return sse / n
+
+    def comm_description(self):
+        return "one NCCL all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % (self.grads.numel() * 4)
 
     def evaluate(self, x, y):
         """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""

@@ -627,20 +627,58 @@ def write_file(path, tree, attrs=None, chunk_rows=None, deflate=None):
 
 
 # ====================================================================================================== Keras layout
-def save_keras_weights(path, weights, order=None, backend="tensorflow", keras_version="2.2.4"):
-    """weights: {layer: (kernel HWIO, bias)} -> the file `keras.Model.save_weights(path)` writes."""
-    order = list(order) if order is not None else list(weights)
-    tree, attrs = {}, {"": {"layer_names": [n.encode() for n in order], "backend": backend.encode(),
+def save_keras_weights(path, weights, order=None, backend="tensorflow", keras_version="2.2.4", layers=None):
+    """weights: {layer: (kernel HWIO, bias)} -> the file `keras.Model.save_weights(path)` writes
+    (keras/engine/saving.py save_weights_to_hdf5_group [lib]): root attribute `layer_names` in `model.layers` ORDER,
+    one group per layer -- weightless layers (InputLayer, Activation, Lambda, Add) included, with an empty
+    `weight_names` -- holding `<layer>/kernel:0`, `<layer>/bias:0`.
+
+    layers: [(name, has_weights)] in `model.layers` order (sr100.keras_graph); order: weighted layers only (older
+    callers).  The order is load-bearing: Keras' load_weights zips weighted layers positionally and ignores names."""
+    if layers is None:
+        layers = [(n, True) for n in (list(order) if order is not None else list(weights))]
+    tree, attrs = {}, {"": {"layer_names": [n.encode() for n, _ in layers], "backend": backend.encode(),
                             "keras_version": keras_version.encode()}}
-    for name in order:
-        k, b = weights[name]
-        tree[name] = {name: {"kernel:0": np.asarray(k, dtype=np.float32), "bias:0": np.asarray(b, dtype=np.float32)}}
-        attrs[name] = {"weight_names": [("%s/kernel:0" % name).encode(), ("%s/bias:0" % name).encode()]}
+    for name, has_w in layers:
+        if has_w:
+            k, b = weights[name]
+            tree[name] = {name: {"kernel:0": np.asarray(k, dtype=np.float32), "bias:0": np.asarray(b, dtype=np.float32)}}
+            attrs[name] = {"weight_names": [("%s/kernel:0" % name).encode(), ("%s/bias:0" % name).encode()]}
+        else:
+            tree[name] = {}
+            attrs[name] = {"weight_names": []}
     return write_file(path, tree, attrs)
 
 
+def _layer_arrays(grp):
+    wn = grp.attrs.get("weight_names")
+    if wn is not None and len(wn):
+        return [grp[w.decode("utf-8")].read() for w in wn]
+    if wn is not None:
+        return []
+    return [a for _, a in grp.visit_datasets()]
+
+
+def load_keras_weights_positional(path):
+    """[(layer name in the file, [arrays])] for the file's WEIGHTED layers in `layer_names` order -- the list Keras'
+    load_weights_from_hdf5_group zips against the model's weighted layers (names are not consulted)."""
+    f = open_file(path)
+    g = f["model_weights"] if "model_weights" in f else f
+    ln = g.attrs.get("layer_names")
+    names = [n.decode("utf-8") for n in ln] if ln is not None else g.keys()
+    out = []
+    for name in names:
+        if name not in g:
+            raise KeyError("layer '%s' of layer_names is not in the weight file" % name)
+        arrs = _layer_arrays(g[name])
+        if arrs:
+            out.append((name, arrs))
+    return out
+
+
 def load_keras_weights(path, layer_names=None):
-    """-> {layer: (kernel, bias)} from `save_weights` / `model.save` files (Keras 2.x layout; Keras 1.x `_W`/`_b`)."""
+    """-> {layer: (kernel, bias)} BY NAME from `save_weights` / `model.save` files (Keras 2.x layout; Keras 1.x
+    `_W`/`_b`) -- Keras' load_weights(by_name=True)."""
     f = open_file(path)
     g = f["model_weights"] if "model_weights" in f else f
     at = g.attrs
@@ -652,12 +690,7 @@ def load_keras_weights(path, layer_names=None):
     for name in names:
         if name not in g:
             raise KeyError("layer '%s' is not in the weight file" % name)
-        grp = g[name]
-        wn = grp.attrs.get("weight_names")
-        if wn is not None and len(wn):
-            arrs = [grp[w.decode("utf-8")].read() for w in wn]
-        else:
-            arrs = [a for _, a in grp.visit_datasets()]
+        arrs = _layer_arrays(g[name])
         if not arrs:
             continue                                # layers without weights (Activation, Lambda, Add)
         if len(arrs) != 2:

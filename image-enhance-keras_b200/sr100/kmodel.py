@@ -39,7 +39,10 @@ class Model:
         self.engine = engine if engine is not None else Engine(**engine_kw)
         sc = getattr(self.engine, "scale", 4)              # Engine (DifvdsrDouble) and Difvdsr4: x4; Difvdsr: x1
         self.output_shape = (None, sc * h, sc * w, 3)
-        self.layers = [Layer(self, *s) for s in self.engine.specs]
+        # the weighted layers in Keras `model.layers` order (depth-sorted: per 5/3 block a3, c5, b5, d3), which is
+        # also the order of get_weights() / set_weights() lists; weightless layers have no object here
+        by_name = {s[0]: s for s in self.engine.specs}
+        self.layers = [Layer(self, *by_name[n]) for n, w in self.keras_layers() if w]
         self.optimizer = None
         self.loss = None
         self.metrics = []
@@ -87,12 +90,24 @@ class Model:
             np.savez(path, **d)
             return path
         from . import h5lite
-        h5lite.save_keras_weights(path, wd, order=[n for n, _, _, _ in self.engine.specs])
+        h5lite.save_keras_weights(path, wd, layers=self.keras_layers())
         return path
 
-    def load_weights(self, path):
+    def keras_layers(self):
+        """[(name, has_weights)] in Keras `model.layers` order (depth-sorted, sr100.keras_graph): what save_weights
+        writes as `layer_names` and what load_weights zips positionally.  DifvdsrDouble has parallel branches (per
+        5/3 block: a3, c5, b5, d3); the chain-shaped Difvdsr4 / Difvdsr graphs are in creation order."""
+        if isinstance(self.engine, Engine):
+            from .keras_graph import difvdsr_double_layers
+            return difvdsr_double_layers()
+        return [(n, True) for n, _, _, _ in self.engine.specs]
+
+    def load_weights(self, path, by_name=False):
         """Keras `load_weights` of an HDF5 weight file (`save_weights` or `model.save` layout, models.py:1217-1218),
-        or of the .npz exchange format."""
+        or of the .npz exchange format.  HDF5 files load the way Keras loads them: POSITIONALLY -- the file's weighted
+        layers in `layer_names` order against this model's weighted layers in `model.layers` order, names ignored
+        (so a file whose auto-names are offset, e.g. written after a second create_model without clear_session,
+        loads exactly as in Keras); by_name=True matches group names instead."""
         if not os.path.exists(path):
             raise OSError("Unable to open file (unable to open file: name = '%s', errno = 2, error message = "
                           "'No such file or directory')" % path)
@@ -104,7 +119,22 @@ class Model:
             d = {n: (z[n + "/kernel:0"], z[n + "/bias:0"]) for n in names}
         else:
             from . import h5lite
-            d = h5lite.load_keras_weights(path, names)
+            if by_name:
+                d = h5lite.load_keras_weights(path, names)
+            else:
+                mine = [n for n, w in self.keras_layers() if w]
+                theirs = h5lite.load_keras_weights_positional(path)
+                if len(theirs) != len(mine):
+                    raise ValueError("You are trying to load a weight file containing %d layers into a model with "
+                                     "%d layers." % (len(theirs), len(mine)))
+                d = {}
+                for n, (fname, arrs) in zip(mine, theirs):
+                    if len(arrs) != 2:
+                        raise ValueError("Layer #%s (named \"%s\" in the current model) was found to correspond to "
+                                         "layer %s in the save file. However the new layer %s expects 2 weights, but "
+                                         "the saved weights have %d elements." % (mine.index(n), n, fname, n, len(arrs)))
+                    k, b = (arrs[0], arrs[1]) if arrs[0].ndim > arrs[1].ndim else (arrs[1], arrs[0])
+                    d[n] = (k, b)
         for (n, k, cin, cout) in self.engine.specs:
             if tuple(d[n][0].shape) != (k, k, cin, cout) or tuple(d[n][1].shape) != (cout,):
                 raise ValueError("Layer %s: weight file holds kernel %s / bias %s, the model expects %s / %s"

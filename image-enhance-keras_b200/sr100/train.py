@@ -397,10 +397,12 @@ class Trainer:
                 self.engine.use_graphs = False
         g.ran_eager = True
 
-    def apply_gradients(self):
-        """Data-parallel mean of the gradients (NCCL all-reduce of the flat arena) + fused Keras Adam + repack."""
+    def apply_gradients(self, summed_over=None):
+        """Data-parallel mean of the gradients (NCCL all-reduce of the flat arena) + fused Keras Adam + repack.
+        summed_over: self.grads already holds the SUM over that many minibatch shards (a logical split run in one
+        process: no collective, only the 1/shards scale) -- what the tests use to check the data-parallel algebra."""
         from .dist import all_reduce_sum_
-        world = all_reduce_sum_(self.grads)
+        world = all_reduce_sum_(self.grads) if summed_over is None else int(summed_over)
         self.t += 1
         L.check(self.lib.sr_adam_step(L.ptr(self.engine.param_arena), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v),
                                       self.engine.n_params, self.lr, self.beta_1, self.beta_2, self.epsilon, self.t,

@@ -115,6 +115,49 @@ def test_weights_roundtrip_and_npz(dmodel, weights, tmp_path):
         mod2.load_weights(str(tmp_path / "missing.h5"))
     with pytest.raises(ValueError):
         model.set_weights(ws[:-1])
+    # get_weights() follows Keras' model.layers order (depth-sorted): level1, then a3, c5, b5, d3 of the first block
+    assert [l.name for l in model.layers[:5]] == ["level1", "conv2d_1", "conv2d_3", "conv2d_2", "conv2d_4"]
+    assert np.array_equal(ws[4], weights["conv2d_3"][0]) and np.array_equal(ws[6], weights["conv2d_2"][0])
+
+
+def test_load_weights_is_positional_like_keras(dmodel, weights, tmp_path):
+    """Keras' load_weights (by_name=False, what models.py:1218 calls) zips the file's weighted layers in
+    `layer_names` order with model.layers and never looks at names:
+    (1) a file whose auto-names are offset (second create_model without clear_session: conv2d_86...) loads;
+    (2) a file written in CREATION order (conv2d_1, conv2d_2, conv2d_3, ...) loads without a shape error and with the
+        two 5x5 kernels of every 5/3 block swapped -- exactly what real Keras would do with such a file;
+    (3) by_name=True matches group names instead."""
+    from sr100 import h5lite
+    from sr100 import keras_graph as kg
+    from sr100.engine import layer_specs
+    _, model = dmodel
+    model.engine.set_weights_dict(weights)
+    # (1) offset names, Keras order
+    layers = kg.difvdsr_double_layers()
+    ren = {}
+    for n, has_w in layers:
+        ren[n] = "conv2d_%d" % (int(n.split("_")[1]) + 85) if n.startswith("conv2d_") else n
+    p1 = str(tmp_path / "offset.h5")
+    h5lite.save_keras_weights(p1, {ren[n]: weights[n] for n, w in layers if w}, layers=[(ren[n], w) for n, w in layers])
+    m2 = models_mod().DifvdsrDouble(1).create_model(24, 24)
+    m2.load_weights(p1)
+    got = m2.engine.get_weights_dict()
+    assert all(np.array_equal(got[n][0], weights[n][0]) and np.array_equal(got[n][1], weights[n][1]) for n in weights)
+    with pytest.raises(KeyError):
+        m2.load_weights(p1, by_name=True)
+    # (2) creation-order file: positional load swaps conv2d_2 <-> conv2d_3 (both 5x5x128x128) in every 5/3 block
+    p2 = str(tmp_path / "creation_order.h5")
+    h5lite.save_keras_weights(p2, weights, order=[s[0] for s in layer_specs()])
+    m2.load_weights(p2)
+    got = m2.engine.get_weights_dict()
+    assert np.array_equal(got["conv2d_2"][0], weights["conv2d_3"][0])
+    assert np.array_equal(got["conv2d_3"][0], weights["conv2d_2"][0])
+    assert np.array_equal(got["conv2d_1"][0], weights["conv2d_1"][0])
+    assert np.array_equal(got["conv2d_65"][0], weights["conv2d_65"][0])       # light blocks: creation == Keras order
+    # (3) by name the same file is read back as written
+    m2.load_weights(p2, by_name=True)
+    got = m2.engine.get_weights_dict()
+    assert all(np.array_equal(got[n][0], weights[n][0]) for n in weights)
 
 
 def test_predict_rejects_bad_shapes(dmodel):

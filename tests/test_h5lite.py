@@ -108,3 +108,48 @@ def test_rejects_non_hdf5(tmp_path):
         f.write(b"not an hdf5 file" * 100)
     with pytest.raises(OSError):
         h.open_file(p)
+
+
+def test_keras_model_layers_order_of_difvdsr_double():
+    """Keras sorts `model.layers` by depth, then by traversal order from the output (sr100.keras_graph): in every 5/3
+    block the weighted layers come a3, c5, b5, d3 -- conv2d_1, conv2d_3, conv2d_2, conv2d_4 -- not in creation order;
+    light blocks and the chain around them are in creation order."""
+    from sr100 import keras_graph as kg
+    layers = kg.difvdsr_double_layers()
+    assert len(layers) == 1 + 1 + 18 * 10 + 6 * 5 + 1 + 1 and layers[0] == ("input_1", False)
+    assert [n for n, _ in layers[1:12]] == ["level1", "conv2d_1", "conv2d_3", "activation_1", "activation_2", "conv2d_2",
+                                            "conv2d_4", "add_1", "lambda_2", "lambda_1", "add_2"]
+    w = kg.difvdsr_double_weighted_order()
+    want = ["level1"]
+    n = 0
+    for _ in range(16):
+        want += ["conv2d_%d" % (n + i) for i in (1, 3, 2, 4)]
+        n += 4
+    want += ["conv2d_%d" % i for i in range(65, 77)]
+    n = 76
+    for _ in range(2):
+        want += ["conv2d_%d" % (n + i) for i in (1, 3, 2, 4)]
+        n += 4
+    want.append("conv2d_85")
+    assert w == want and sorted(w, key=lambda s: (s != "level1", int(s.split("_")[1]) if "_" in s else 0)) == \
+        ["level1"] + ["conv2d_%d" % i for i in range(1, 86)]
+
+
+def test_save_weights_layout_is_keras_model_layers_order(tmp_path):
+    """The writer emits `layer_names` in model.layers order with weightless groups (empty weight_names), and the
+    positional reader returns the weighted layers in exactly the order Keras' load_weights zips them."""
+    from sr100 import keras_graph as kg
+    rng = np.random.default_rng(3)
+    w = _weights(rng)
+    p = str(tmp_path / "w.h5")
+    h.save_keras_weights(p, w, layers=kg.difvdsr_double_layers())
+    f = h.open_file(p)
+    names = [n.decode() for n in f.attrs["layer_names"]]
+    assert names == [n for n, _ in kg.difvdsr_double_layers()]
+    assert len(f["activation_1"].attrs["weight_names"]) == 0 and f["add_3"].keys() == []
+    pos = h.load_keras_weights_positional(p)
+    assert [n for n, _ in pos] == kg.difvdsr_double_weighted_order()
+    assert [n for n, _ in pos][1:5] == ["conv2d_1", "conv2d_3", "conv2d_2", "conv2d_4"]
+    for n, arrs in pos:
+        assert np.array_equal(arrs[0], w[n][0]) and np.array_equal(arrs[1], w[n][1])
+    assert set(h.load_keras_weights(p)) == set(w)            # by name: weightless groups are skipped

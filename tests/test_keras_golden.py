@@ -1,0 +1,91 @@
+"""Consumes the goldens that oracle/refgen_keras.py writes on a machine with the reference's real 2018 stack
+(TensorFlow 1.x / Keras 2.2 / scikit-image < 0.18) -- the pin for the float path.  Neither that stack nor a network
+exists in the authoring container, so until somebody runs the recipe these tests SKIP and the float-path oracle
+stays "parity unpinned" (DESIGN.md section 2).  With the files present they check, on the CPU:
+
+  oracle/model.py forward / loss / gradients / Keras-Adam step      vs  model.predict, K.gradients, train_on_batch
+  oracle.model.bilinear_x4_tf1                                       vs  tf.image.resize_bilinear
+  oracle/scoring.py rgb2ycbcr_y / ssim                               vs  skimage rgb2ycbcr / compare_ssim
+  sr100.keras_graph (model.layers order) and sr100.h5lite (reader)   vs  Keras' own layer list and save_weights file
+"""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NPZ = os.path.join(GOLD, "keras_ref.npz")
+H5 = os.path.join(GOLD, "keras_block53_ref.h5")
+
+needs_keras_golden = pytest.mark.skipif(
+    not os.path.exists(NPZ), reason="parity unpinned: tests/golden/keras_ref.npz absent -- run oracle/refgen_keras.py "
+                                    "on a machine with TensorFlow 1.x + Keras 2.2 + scikit-image < 0.18")
+
+
+def test_recipe_is_committed_and_names_what_it_writes():
+    src = open(os.path.join(os.path.dirname(GOLD), "..", "oracle", "refgen_keras.py")).read()
+    for key in ("keras_ref.npz", "keras_block53_ref.h5", "predict_", "grad/", "adam1/", "bilinear_x4", "ssim_y",
+                "layer_names"):
+        assert key in src
+
+
+@needs_keras_golden
+def test_forward_matches_keras_predict():
+    from oracle import model as om
+    z = np.load(NPZ)
+    w = om.init_weights(1234, bias_scale=0.01)
+    for tag in ("a", "b"):
+        got = om.forward_numpy(w, z["x_" + tag])
+        assert np.abs(got - z["predict_" + tag]).max() <= 2e-5        # fp32 vs fp32, summation order only
+
+
+@needs_keras_golden
+def test_loss_gradients_and_adam_step_match_keras():
+    import torch
+    from oracle import model as om
+    z = np.load(NPZ)
+    w = om.init_weights(1234, bias_scale=0.01)
+    m = om.DifvdsrDoubleOracle(w)
+    opt = om.KerasAdam(m.parameters())
+    x, y = torch.from_numpy(z["x_b"]), torch.from_numpy(z["y_b"])
+    loss, grads = om.train_step(m, opt, x, y)
+    assert abs(loss - float(z["loss_b"])) <= 1e-5 * float(z["loss_b"])
+    for (pn, _), g in zip(m.named_parameters(), grads):
+        kind, name = pn.split(".")
+        want = z["grad/%s/%s:0" % (name, "kernel" if kind == "w" else "bias")]
+        got = g.numpy().transpose(2, 3, 1, 0) if kind == "w" else g.numpy()
+        rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
+        assert rel <= 1e-3, (name, kind, rel)
+    for name in ("level1", "conv2d_1", "conv2d_2", "conv2d_3", "conv2d_66", "conv2d_85"):
+        got = m.w[name].detach().numpy().transpose(2, 3, 1, 0)
+        assert np.abs(got - z["adam1/%s/kernel" % name]).max() <= 2e-6      # one step of 1e-4
+
+
+@needs_keras_golden
+def test_bilinear_and_scoring_match_tf_and_skimage():
+    import torch
+    from oracle import model as om
+    from oracle import scoring as osc
+    z = np.load(NPZ)
+    got = om.bilinear_x4_tf1(torch.from_numpy(z["bilinear_in"]).permute(0, 3, 1, 2)).permute(0, 2, 3, 1).numpy()
+    assert np.array_equal(got, z["bilinear_x4"])                         # weights 0, .25, .5, .75: exact in fp32
+    a, b = z["score_a"], z["score_b"]
+    assert np.abs(osc.rgb2ycbcr_y(a) - z["rgb2ycbcr_y_a"]).max() <= 1e-10
+    assert abs(osc.ssim(osc.rgb2ycbcr_y(a), osc.rgb2ycbcr_y(b), 255.0) - float(z["ssim_y"])) <= 1e-9
+    assert abs(osc.ssim(a, b, 255.0, multichannel=True) - float(z["ssim_rgb"])) <= 1e-9
+
+
+@needs_keras_golden
+def test_keras_layer_order_and_h5_reader_match_keras():
+    from sr100 import h5lite
+    from sr100 import keras_graph as kg
+    z = np.load(NPZ)
+    assert [n for n, _ in kg.difvdsr_double_layers()] == [str(n) for n in z["layer_names"]]
+    assert kg.difvdsr_double_weighted_order() == [str(n) for n in z["weighted_layer_names"]]
+    pos = h5lite.load_keras_weights_positional(H5)
+    f = h5lite.open_file(H5)
+    assert [n.decode() for n in f.attrs["layer_names"]] == [str(n) for n in z["block53_layer_names"]]
+    for name, arrs in pos:
+        for a in arrs:
+            key = "block53/%s/%s:0" % (name, "kernel" if a.ndim == 4 else "bias")
+            assert np.array_equal(a, z[key])

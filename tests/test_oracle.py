@@ -176,3 +176,33 @@ def test_oracle_conv_is_keras_conv2d_by_definition():
     y = m.conv("level1", torch.from_numpy(x).permute(0, 3, 1, 2), relu=True).permute(0, 2, 3, 1).detach().numpy()
     w0, b0 = weights["level1"]
     assert np.abs(y - np.maximum(x @ w0[0, 0].astype(np.float64) + b0, 0)).max() < 1e-12
+
+
+def test_bf16_operand_emulation_is_the_same_graph():
+    """oracle/emu_bf16.py (the engine's rounding points laid over the oracle graph, used by the sharp gradient test
+    on the GPU) must be the SAME function as the fp32 oracle up to bf16 rounding: loss within 1e-4 relative, every
+    layer's gradient within 3e-2 relative L2 -- and not identical (the rounding points are really there)."""
+    import torch
+    from oracle import emu_bf16 as emu
+    from oracle import model as om
+    w = om.init_weights(1234, bias_scale=0.01)
+    rng = np.random.default_rng(7)
+    x = rng.random((1, 8, 10, 3)).astype(np.float32)
+    y = rng.random((1, 32, 40, 3)).astype(np.float32)
+    loss, g = emu.gradients(w, x, y)
+    m = om.DifvdsrDoubleOracle(w)
+    want_loss = om.mse_loss(m(torch.from_numpy(x)), torch.from_numpy(y))
+    grads = torch.autograd.grad(want_loss, list(m.parameters()))
+    by = {}
+    for (pn, _), q in zip(m.named_parameters(), grads):
+        kind, name = pn.split(".")
+        by.setdefault(name, {})[kind] = q.numpy()
+    assert abs(loss - float(want_loss.detach())) <= 1e-4 * float(want_loss.detach())
+    worst = 0.0
+    for name in m.names:
+        gw = np.transpose(by[name]["w"], (2, 3, 1, 0)).astype(np.float64)
+        rel = np.linalg.norm(g[name][0] - gw) / np.linalg.norm(gw)
+        relb = np.linalg.norm(g[name][1] - by[name]["b"]) / max(np.linalg.norm(by[name]["b"]), 1e-30)
+        worst = max(worst, rel, relb)
+        assert rel <= 3e-2 and relb <= 3e-2, (name, rel, relb)
+    assert worst > 1e-4

@@ -22,6 +22,9 @@ glorot weights of oracle/model.init_weights (biases U(+-0.01)) by layer name, an
                                         reference's own _residual_block_light53 (a real libhdf5/Keras-written file for
                                         sr100.h5lite's reader, layer order and layout)
 
+    (keras_ref.npz["h5lite_writer_loaded_by_keras"]: the reverse check -- a file written by sr100.h5lite is loaded by
+     Keras' own load_weights through libhdf5 and compared)
+
 tests/test_keras_golden.py consumes both files when they exist (and is skipped, saying so, while they do not):
 the oracle restatement (oracle/model.py, oracle/scoring.py, sr100.keras_graph) is then pinned to the real stack
 and DESIGN.md's "parity unpinned" rows can be struck.  Everything is seeded; the inputs are stored next to the
@@ -129,6 +132,21 @@ def main(ref_dir):
             out["block53/" + wv.name] = val
     xs = smooth(rng, (1, 8, 8, 3))
     out["block53_x"], out["block53_predict"] = xs, small.predict(xs)
+    # ... and the other direction: a file written by sr100.h5lite (pure Python, no libhdf5) opened by h5py / loaded by
+    # Keras' own load_weights into the same model -- the pin for the WRITER
+    sys.path.insert(0, os.path.join(ROOT, "image-enhance-keras_b200"))
+    from sr100 import h5lite
+    ours = os.path.join(OUT, "h5lite_written_block53.h5")
+    wd = {l.name: tuple(l.get_weights()) for l in small.layers if l.weights}
+    h5lite.save_keras_weights(ours, wd, layers=[(l.name, bool(l.weights)) for l in small.layers])
+    before = [w.copy() for w in small.get_weights()]
+    for l in small.layers:
+        if l.weights:
+            l.set_weights([np.zeros_like(w) for w in l.get_weights()])
+    small.load_weights(ours)                               # Keras + libhdf5 reading our bytes
+    ok = all(np.array_equal(a, b) for a, b in zip(before, small.get_weights()))
+    out["h5lite_writer_loaded_by_keras"] = np.array(ok)
+    assert ok, "Keras did not read back what sr100.h5lite wrote"
 
     np.savez_compressed(os.path.join(OUT, "keras_ref.npz"), **out)
     print("wrote", os.path.join(OUT, "keras_ref.npz"), "and keras_block53_ref.h5 (keras %s, tf %s)"

@@ -89,3 +89,4 @@ def test_keras_layer_order_and_h5_reader_match_keras():
         for a in arrs:
             key = "block53/%s/%s:0" % (name, "kernel" if a.ndim == 4 else "bias")
             assert np.array_equal(a, z[key])
+    assert bool(z["h5lite_writer_loaded_by_keras"])      # the writer: Keras + libhdf5 read back sr100.h5lite's bytes

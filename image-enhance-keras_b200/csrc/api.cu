@@ -36,6 +36,25 @@ extern "C" int sr_dev_switches(void) {
 #endif
 }
 
+#ifdef SR_DEV_SWITCHES
+namespace sr {
+static unsigned long long* g_timeline = nullptr;
+unsigned long long* dev_timeline() { return g_timeline; }
+}  // namespace sr
+#endif
+
+// Development build only: device buffer (16 x 8 bytes per CTA) that conv plans created afterwards stamp their phase
+// clocks into (tools/probe_timeline.py); NULL turns it off.  The release library refuses.
+extern "C" int sr_dev_set_timeline(void* buf) {
+#ifdef SR_DEV_SWITCHES
+  sr::g_timeline = reinterpret_cast<unsigned long long*>(buf);
+  return SR_OK;
+#else
+  (void)buf;
+  return sr::set_error(SR_ERR_UNSUPPORTED, "sr_dev_set_timeline: not a development build (-DSR_DEV_SWITCHES)");
+#endif
+}
+
 extern "C" int sr_device_supported(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

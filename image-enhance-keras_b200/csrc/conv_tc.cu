@@ -24,8 +24,8 @@ constexpr int kTapsPerStage = 2;  // taps per weight stage: halves the barrier r
 struct __align__(8) ConvBarriers {
   uint64_t w_full[kMaxWStages];
   uint64_t w_empty[kMaxWStages];
-  uint64_t a_full[2];
-  uint64_t a_empty[2];
+  uint64_t a_full[4];
+  uint64_t a_empty[4];
   uint64_t tmem_full[4];
   uint64_t tmem_empty[4];
   uint32_t tmem_base;
@@ -837,7 +837,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared space
   uint8_t* a_buf = smem;
-  uint8_t* w_buf = smem + 2 * P.a_bytes;
+  uint8_t* w_buf = smem + P.num_abuf * P.a_bytes;
   uint8_t* stage_buf = w_buf + P.num_wstages * WSTAGE;
   ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + (EPI == 4 ? kShuffleStageBytes : 4 * 32 * 256));
   float* s_bias = reinterpret_cast<float*>(bars + 1);
@@ -855,13 +855,17 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int tps = P.tiles_per_seg;
   const int ncol = P.NB * P.nseg;
   const int pair_tiles = ((ncol + 1) >> 1) * tps;
+  if (threadIdx.x == 0) {
+    SR_STAMP(P, 0);
+    SR_STAMP_NS(P, 14);
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bars->w_full[i], 1);
       mbar_init(&bars->w_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < P.num_abuf; ++i) {
       mbar_init(&bars->a_full[i], 1);
       mbar_init(&bars->a_empty[i], 1);
     }
@@ -892,6 +896,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (threadIdx.x == 0) SR_STAMP(P, 1);
 
   // tile of this CTA for pair-tile index pt: column 2*j + rank (clamped; a clamped duplicate does not store)
   auto decode = [&](int pt, bool* live) {
@@ -923,6 +928,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               }
               if (wr.slot + 1 == wr.n) w_wrapped = true;
               const int nbox = min(kTapsPerStage, ntaps - tap);  // an odd last tap loads one box only
+              if (pt == cluster_id && s == 0 && ch == 0 && tap == 0) SR_STAMP(P, 9);
               if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * nbox * WTAP);
               const uint32_t bar = mapa_shared(smem_u32(&bars->w_full[slot]), 0);
 #pragma unroll
@@ -939,7 +945,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 3) {
     // ------------------------------------------------ activation strip TMA producer (both CTAs)
     if (lane == 0) {
-      uint32_t ac = 0;
+      Ring ar{0u, 0u, (uint32_t)P.num_abuf};
+      bool a_wrapped = false;
       const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kRowBytes;
       for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
         bool live;
@@ -947,17 +954,19 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
           for (int ch = 0; ch < NCH; ++ch) {
-            const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
+            const uint32_t slot = ar.slot, ph = ar.phase;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
-            if (SR_DBG(P, 2) && ac >= 2) {       // timing experiment: the strip buffer keeps whatever it held
+            if (SR_DBG(P, 2) && a_wrapped) {     // timing experiment: the strip buffer keeps whatever it held
               if (is_leader) mbar_arrive(&bars->a_full[slot]);
-              ++ac;
+              ar.advance();
               continue;
             }
+            if (ar.slot + 1 == ar.n) a_wrapped = true;
+            if (pt == cluster_id && s == 0 && ch == 0) SR_STAMP(P, 10);
             if (is_leader) mbar_expect_tx(&bars->a_full[slot], 2 * strip_bytes);
             tma_load_4d_pair(a_buf + slot * P.a_bytes, tmA, mapa_shared(smem_u32(&bars->a_full[slot]), 0),
                              ch * CHE, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
-            ++ac;
+            ar.advance();
           }
         }
       }
@@ -966,8 +975,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
     if (is_leader) {
       const bool leader = elect_one();
-      uint32_t ac = 0, it = 0;
+      uint32_t it = 0;
       Ring wr{0u, 0u, (uint32_t)NS};
+      Ring ar{0u, 0u, (uint32_t)P.num_abuf};
       constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
       const uint32_t a_buf_lo = (smem_u32(a_buf) >> 4) | (1u << 16);
       const uint32_t a_slot_step = (uint32_t)P.a_bytes >> 4;
@@ -986,15 +996,17 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int ntaps = k * k;
           const int row_wrap = (P.PWs - (k - 1)) * 4;
           for (int ch = 0; ch < NCH; ++ch) {
-            const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
+            const uint32_t aslot = ar.slot, aph = ar.phase;
             mbar_wait(&bars->a_full[aslot], aph);
             tc_fence_after();
+            if (it == 0 && s == 0 && leader) SR_STAMP(P, ch == 0 ? 2 : ch == NCH - 1 ? 12 : 13);
             uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
             int kx = 0;
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t wslot = wr.slot, wph = wr.phase;
               mbar_wait(&bars->w_full[wslot], wph);
               tc_fence_after();
+              if (it == 0 && s == 0 && ch == 0 && tap == 0 && leader) SR_STAMP(P, 3);
               uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
 #pragma unroll
               for (int j = 0; j < kTapsPerStage; ++j) {
@@ -1023,10 +1035,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               wr.advance();
             }
             if (leader) umma_commit_pair(&bars->a_empty[aslot]);
-            ++ac;
+            ar.advance();
           }
         }
         if (leader) umma_commit_pair(&bars->tmem_full[buf]);
+        if (it == 0 && leader) SR_STAMP(P, 4);
       }
     }
   } else if (warp >= 4) {
@@ -1040,23 +1053,30 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
       mbar_wait(&bars->tmem_full[buf], bph);
       tc_fence_after();
+      if (it == 0 && ew == 0 && lane == 0) SR_STAMP(P, 5);
       const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int acc = 0; acc < NACC; ++acc)
         epilogue_acc<EPI, CS>(P, c, t_base + acc * N_, c.f0 + acc * 128 + ew * 32, stage_buf, ew, s_bias, lane, live, cs);
       tc_fence_before();
       __syncwarp();
+      if (it == 0 && ew == 0 && lane == 0) SR_STAMP(P, 6);
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
     }
     if constexpr (CS) colsum_flush(P, cs, lane);
   }
 
   __syncwarp();  // lanes of the single-lane roles reconverge before the aligned cluster barrier
+  if (threadIdx.x == 0) SR_STAMP(P, 7);
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, TM_COLS);
+  }
+  if (threadIdx.x == 0) {
+    SR_STAMP(P, 8);
+    SR_STAMP_NS(P, 15);
   }
 }
 
@@ -1161,9 +1181,9 @@ static constexpr size_t kSmemBudget = 227 * 1024;
 
 // Choose the column-segment width: maximise useful MMA rows subject to the shared-memory budget.
 static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_bytes,
-                            ConvKernelParams* P, int min_nseg = 1) {
+                            ConvKernelParams* P, int min_nseg = 1, int nseg_step = 1, int nabuf = 2) {
   double best_eff = -1.0;
-  for (int nseg = min_nseg; nseg <= W; ++nseg) {
+  for (int nseg = min_nseg; nseg <= W; nseg += nseg_step) {
     const int BW = (W + nseg - 1) / nseg;
     if ((BW * (nseg - 1)) >= W) continue;  // last segment would be empty
     const int PWs = BW + 2 * p;
@@ -1172,7 +1192,7 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
     if (NR > 256) continue;
     const size_t a_bytes = ((size_t)NR * PWs * kChunk * 2 + 1023) & ~(size_t)1023;
     const size_t fixed =
-        2 * a_bytes + 1024 /*align slack*/ + stage_bytes + sizeof(ConvBarriers) + 128 * 4 + 64;
+        nabuf * a_bytes + 1024 /*align slack*/ + stage_bytes + sizeof(ConvBarriers) + 128 * 4 + 64;
     if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;  // >= 3 two-tap weight stages in flight
     const int f_len = (H - 1) * PWs + BW;
     const int tps = (f_len + T - 1) / T;
@@ -1185,6 +1205,7 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
       P->PWs = PWs;
       P->NR = NR;
       P->a_bytes = (int)a_bytes;
+      P->num_abuf = nabuf;
       P->f_len = f_len;
       P->tiles_per_seg = tps;
       int ns = (int)((kSmemBudget - fixed) / wstage);
@@ -1222,6 +1243,13 @@ static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
 }  // namespace sr
 
 using namespace sr;
+
+// epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
+static int epilogue_kind(const ConvKernelParams& P) {
+  const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
+  const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32 && P.relu != 2;
+  return P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;
+}
 
 extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (!d || !out) return set_error(SR_ERR_INVALID, "sr_conv_plan_create: null argument");
@@ -1267,7 +1295,10 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   // CTA pairs work on two columns (image x column segment).  A single image could be split into two segments for
   // it (the kernel handles that), but measured on BASELINE config 1 the extra halo of the forced split costs what
   // the paired MMAs gain (2.47 vs 2.41 ms), so single images keep the single-CTA kernel.
-  pl->pair = (d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64 && d->NB >= 2) ? 1 : 0;
+  // A single WIDE image is different: once the strip pitch limit (256 pixels) splits it into >= 2 segments anyway,
+  // the segments pair up at no extra cost (the HR stage of config 1: 512 wide = 4 segments of 128).
+  const bool pair_ok = d->pair && pl->n_pad == 128 && pl->amode == kAModeSwizzle64;
+  pl->pair = (pair_ok && d->NB >= 2) ? 1 : 0;
   int wstage = kTapsPerStage * (pl->pair ? pl->n_pad / 2 : pl->n_pad) * kRowBytes;
   ConvKernelParams& P = pl->P;
   P.nsrc = d->nsrc;
@@ -1288,15 +1319,62 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   const int Wc = (d->comp_w > 0 && d->comp_w < d->W) ? d->comp_w : d->W;
   P.Hc = Hc;
   P.Wc = Wc;
-  bool geo = choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P, (pl->pair && d->NB == 1) ? 2 : 1);
-  if (!geo && pl->pair && d->NB == 1) {   // cannot be split in two: the single-CTA kernel
-    pl->pair = 0;
-    wstage = kTapsPerStage * pl->n_pad * kRowBytes;
-    geo = choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P);
+  bool geo = choose_geometry(Hc, Wc, p, T, wstage, stage_bytes, &P);
+  if (geo && !pl->pair && pair_ok && d->NB == 1 && P.nseg >= 2) {
+    // the single image splits into segments by itself: take the pair kernel on an even number of segments
+    ConvKernelParams Q = P;
+    const int wstage2 = kTapsPerStage * (pl->n_pad / 2) * kRowBytes;
+    if (choose_geometry(Hc, Wc, p, T, wstage2, stage_bytes, &Q, 2, 2)) {   // an even number of segments: no idle CTA
+      P = Q;
+      pl->pair = 1;
+      wstage = wstage2;
+    }
   }
   if (!geo) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "no conv geometry fits shared memory");
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  P.res_f32 = d->res_f32;
+  P.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->res_bf16);
+  P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
+  P.out_f32 = d->out_f32;
+  P.relu = d->relu;
+  P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
+  P.shuffle_r = d->shuffle_r > 0 ? d->shuffle_r : 0;
+  // Launches of less than one wave (a single small image: BASELINE config 1's LR stage is 65 tiles of 256 positions
+  // on 148 SMs): halve the tile to T = 128 (one accumulator, four TMEM buffers) on CTA pairs -- a single image is
+  // split into two column segments for it -- so twice as many SMs share the MMAs while every CTA still fetches only
+  // half of each weight stage; the strips of all four K chunks are in flight at once (num_abuf up to 4): a tile's
+  // MMA phase is too short to hide a strip load behind it.
+  if (pair_ok && !tf32 && pl->nacc == 2 && !d->colsum_f32) {
+    const int ek = epilogue_kind(P);
+    const int clusters = sms / 2;
+    const long long cur_tiles = pl->pair ? (long long)((P.NB * P.nseg + 1) / 2) * P.tiles_per_seg
+                                         : (long long)P.NB * P.nseg * P.tiles_per_seg;
+    const long long cur_waves = pl->pair ? (cur_tiles + clusters - 1) / clusters : (cur_tiles + sms - 1) / sms;
+    if ((ek == 0 || ek == 1) && cur_waves == 1) {
+      ConvKernelParams Q = P;
+      const int wstage2 = kTapsPerStage * (pl->n_pad / 2) * kRowBytes;
+      bool ok = false;
+      for (int nab = 4; nab >= 2 && !ok; --nab) {
+        ok = (d->NB >= 2) ? choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 1, 1, nab)
+                          : choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 2, 2, nab);
+        if (ok && Q.num_wstages < 6 && nab > 2) ok = false;    // keep a useful weight ring
+      }
+      if (ok) {
+        const long long t128 = (long long)((Q.NB * Q.nseg + 1) / 2) * Q.tiles_per_seg;
+        const long long w128 = (t128 + clusters - 1) / clusters;
+        if (w128 * 128 < cur_waves * 256) {
+          P = Q;
+          pl->pair = 1;
+          pl->nacc = 1;
+          wstage = wstage2;
+        }
+      }
+    }
   }
   P.total_tiles = P.NB * P.nseg * P.tiles_per_seg;
   P.bias = d->bias;
@@ -1312,6 +1390,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   {
     const char* e = dev_getenv("SR100_CONV_DBG");
     P.dbg = e ? atoi(e) : 0;
+    P.timeline = dev_timeline();
   }
   P.colsum = d->colsum_f32;
   P.colsum_scale = d->colsum_scale;
@@ -1345,16 +1424,13 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
     pl->tmW[1] = pl->tmW[0];
   }
   pl->flops = 2.0 * macs;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   if (pl->pair) {
     const int pair_tiles = ((P.NB * P.nseg + 1) / 2) * P.tiles_per_seg;
     pl->grid = 2 * std::min(pair_tiles, sms / 2);
   } else {
     pl->grid = std::min(P.total_tiles, sms);
   }
-  pl->smem_bytes = 1024 + 2 * (size_t)P.a_bytes + (size_t)P.num_wstages * wstage + stage_bytes +
+  pl->smem_bytes = 1024 + (size_t)P.num_abuf * P.a_bytes + (size_t)P.num_wstages * wstage + stage_bytes +
                    sizeof(ConvBarriers) + 128 * 4 + 64;
   *out = reinterpret_cast<sr_conv_plan*>(pl);
   return SR_OK;
@@ -1366,9 +1442,7 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // epilogue specialisation: which single global operand it reads (-1: generic run-time epilogue)
   const ConvKernelParams& P = pl->P;
-  const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
-  const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32 && P.relu != 2;
-  const int epi = P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;  // no operand: the compact generic code
+  const int epi = epilogue_kind(P);
   if (pl->tf32) {
     if (pl->pair) return launch_pair<2, 2, 5, true>(pl, st);
     if (pl->n_pad == 128) return launch_variant<128, kAModeSwizzle64, 2, 2, 5, true>(pl, st);
@@ -1390,6 +1464,7 @@ extern "C" int sr_conv_plan_run(sr_conv_plan* plan, void* stream) {
   }
   if (pl->pair) {
     if (pl->nacc == 4) return launch_pair<4, 1>(pl, st);
+    if (pl->nacc == 1) return epi == 0 ? launch_pair<1, 4, 0>(pl, st) : launch_pair<1, 4, 1>(pl, st);
     switch (epi) {
       case 0: return launch_pair<2, 2, 0>(pl, st);
       case 1: return launch_pair<2, 2, 1>(pl, st);

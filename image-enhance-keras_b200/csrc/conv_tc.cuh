@@ -49,6 +49,7 @@ struct ConvKernelParams {
   int BW, nseg, PWs, NR;
   int tiles_per_seg, total_tiles;
   int a_bytes;       // bytes of one A strip buffer (1024-aligned)
+  int num_abuf;      // strip buffers in flight (2; up to 4 in the pair kernel for launches of less than one wave)
   int num_wstages;
   int f_len;         // number of useful flat positions per segment
   // epilogue: out = act(alpha * (acc + bias) + beta * res)
@@ -74,6 +75,8 @@ struct ConvKernelParams {
   // development switches of the pair kernel (SR100_CONV_DBG, compiled in only with -DSR_DEV_SWITCHES; results are WRONG with either set -- timing only):
   // 1 = no weight TMA after the first pass over the stage ring, 2 = no activation-strip TMA after the first two
   int dbg;
+  // development build only: per-CTA clock64 stamps of the pair kernel's phases (sr_dev_set_timeline), 16 per CTA
+  unsigned long long* timeline;
 };
 
 }  // namespace sr

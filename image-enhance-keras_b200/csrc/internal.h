@@ -23,9 +23,26 @@ inline int check_launch(const char* where) {
 #ifdef SR_DEV_SWITCHES
 #define SR_DBG(P, bit) (((P).dbg & (bit)) != 0)
 inline const char* dev_getenv(const char* name) { return getenv(name); }
+// phase stamps: P.timeline[cta * 16 + idx] = SM clock (idx 14 / 15: globaltimer at entry / exit)
+#define SR_STAMP(P, idx)                                                                      \
+  do {                                                                                        \
+    if ((P).timeline) (P).timeline[(size_t)blockIdx.x * 16 + (idx)] = (unsigned long long)clock64(); \
+  } while (0)
+#define SR_STAMP_NS(P, idx)                                                                   \
+  do {                                                                                        \
+    if ((P).timeline) {                                                                       \
+      unsigned long long t_;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
+      (P).timeline[(size_t)blockIdx.x * 16 + (idx)] = t_;                                     \
+    }                                                                                         \
+  } while (0)
+unsigned long long* dev_timeline();
 #else
 #define SR_DBG(P, bit) false
+#define SR_STAMP(P, idx) do { } while (0)
+#define SR_STAMP_NS(P, idx) do { } while (0)
 inline const char* dev_getenv(const char*) { return nullptr; }
+inline unsigned long long* dev_timeline() { return nullptr; }
 #endif
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -100,6 +100,7 @@ SIGNATURES = {
     "sr_version": (_i, []),
     "sr_device_supported": (_i, []),
     "sr_dev_switches": (_i, []),
+    "sr_dev_set_timeline": (_i, [_vp]),
     "sr_abi_struct_size": (_sz, [_i]),
     "sr_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "sr_conv_plan_run": (_i, [_vp, _vp]),

@@ -91,6 +91,7 @@ class _Stage:
     def _init_stage(self, eng):
         self.eng = eng
         self.steps = []          # callables(stream)
+        self.par = set()         # indices i: steps[i] may run concurrently with steps[i - 1] (independent launches)
         self.conv_flops = 0.0    # algorithmic FLOPs (2*MAC) of the tensor-core launches of this stage
         self.cuda_graph, self.ran_eager = None, False
 
@@ -130,8 +131,12 @@ class _Stage:
 
     def _block53(self, names, i, s, s32, t1, t2, shape, comp=(None, None, None)):
         # comp = compute extents (out, t1, t2): t1 feeds the 5x5 (radius 2), t2 the 3x3 (radius 1)
-        self._conv([(names[i], s)], shape, out_bf16=t1, relu=1, comp=comp[1])
-        self._conv([(names[i + 2], s)], shape, out_bf16=t2, relu=1, comp=comp[2])
+        pa = self._conv([(names[i], s)], shape, out_bf16=t1, relu=1, comp=comp[1])
+        pb = self._conv([(names[i + 2], s)], shape, out_bf16=t2, relu=1, comp=comp[2])
+        # the two branch heads read the same tensor and write different ones: when both grids fit on the chip
+        # together (small inputs: one CTA per tile, fewer tiles than SMs) they run concurrently on two streams
+        if pa.info.grid + pb.info.grid <= self.eng.sm_count:
+            self.par.add(len(self.steps) - 1)
         self._conv([(names[i + 1], t1), (names[i + 3], t2)], shape, out_bf16=s, out_f32=s32, alpha=0.1, beta=0.9,
                    res32=s32, res16=s, comp=comp[0])
 
@@ -145,16 +150,12 @@ class _Stage:
         if eng.use_graphs and self.cuda_graph is not None:
             self.cuda_graph.replay()
             return
-        st = L.stream_ptr()
-        for step in self.steps:
-            step(st)
+        self._launch_all()
         if eng.use_graphs and self.cuda_graph is None and self.ran_eager and not torch.cuda.is_current_stream_capturing():
             try:
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
-                    cst = L.stream_ptr()
-                    for step in self.steps:
-                        step(cst)
+                    self._launch_all()
                 self.cuda_graph = gr
             except Exception as e:  # noqa: BLE001  (capture unsupported in this context: stay eager, but say so)
                 import warnings
@@ -162,6 +163,30 @@ class _Stage:
                               % (type(e).__name__, e), RuntimeWarning)
                 eng.use_graphs = False
         self.ran_eager = True
+
+
+    def _launch_all(self):
+        """Issue the launch sequence on the current stream; steps marked in `par` fork onto the engine's side stream
+        and join again (inside a CUDA-graph capture this becomes two parallel branches of the graph)."""
+        eng = self.eng
+        main = torch.cuda.current_stream()
+        st = L.stream_ptr()
+        side = eng.side_stream if self.par else None
+        i, n = 0, len(self.steps)
+        while i < n:
+            if side is not None and (i + 1) in self.par:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                self.steps[i + 1](C.c_void_p(side.cuda_stream))
+                self.steps[i](st)
+                join = torch.cuda.Event()
+                join.record(side)
+                main.wait_event(join)
+                i += 2
+            else:
+                self.steps[i](st)
+                i += 1
 
 
 class _LRStage(_Stage):
@@ -397,6 +422,9 @@ class Engine:
         self._pack_table = None
         self._init_bias_pairs()
         self._graphs = {}
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # second stream for independent launches of small inputs (_Stage._launch_all); SR100_NO_OVERLAP=1 disables it
+        self.side_stream = None if os.environ.get("SR100_NO_OVERLAP", "0") == "1" else torch.cuda.Stream(self.device)
         self.set_weights_dict(weights if weights is not None else glorot_uniform_weights())
 
     # ---------------------------------------------------------------- weights

@@ -35,6 +35,9 @@ int sr_device_supported(void);
  * SR100_CONV_DBG can make kernels skip operand loads, i.e. give wrong results for timing experiments); the
  * default build returns 0 and reads no environment variable that can change a result. */
 int sr_dev_switches(void);
+/* Development build only (SR_ERR_UNSUPPORTED otherwise): conv plans created after this call stamp per-CTA phase clocks
+ * (16 x uint64 per CTA) into `buf` -- the intra-kernel timeline behind profiles/r02_probe_timeline*.json. */
+int sr_dev_set_timeline(void* buf);
 /* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
  * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
  * 5 sr_score_result; 0 for anything else. */

@@ -351,7 +351,7 @@ def main():
         rng = np.random.default_rng(7 + rank)
         gts = [pinned(rng.integers(0, 256, size=(4 * h, 4 * w, 3)).astype(np.uint8)) for h, w in SET5_SHAPES]
         dev_gts = [torch.from_numpy(g).cuda() for g in gts]
-        score_buf = torch.zeros(5, 64, dtype=torch.uint8, device="cuda")
+        score_buf = torch.zeros(5, 128, dtype=torch.uint8, device="cuda")   # sr_score_result: 112 bytes
 
         def set5_resident():
             canv = eng.upscale_images_device(s_dev)

@@ -89,6 +89,8 @@ class ScoreResult(C.Structure):
         ("ssim_rgb_sum", C.c_double * 3),
         ("n_pix", C.c_int64),
         ("n_win", C.c_int64),
+        ("acc", C.c_uint64 * 6),
+        ("ticket", C.c_uint64),
     ]
 
 

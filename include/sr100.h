@@ -296,9 +296,14 @@ typedef struct sr_score_result {
   double ssim_rgb_sum[3];
   int64_t n_pix;     /* cropped pixel count */
   int64_t n_win;     /* number of valid windows */
+  /* internal: integer accumulators (2^-40 fixed-point SSIM sums of Y, R, G, B; low / high halves of the exact
+   * integer squared error in units of 1/255000^2) and the count of finished blocks.  All cross-block sums are
+   * integer atomics, so the public fields above -- written by the last block -- are bit-reproducible. */
+  uint64_t acc[6];
+  uint64_t ticket;
 } sr_score_result;
 /* a, b: uint8 [h,w,3] (same shape), crop = border removed from every side first.  `result` is a
- * device pointer to one sr_score_result which must be zeroed by the caller before the call. */
+ * device pointer to one sr_score_result (112 bytes) which must be zeroed by the caller before the call. */
 int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w, int crop,
                      sr_score_result* result, void* stream);
 

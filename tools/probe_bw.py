@@ -110,7 +110,7 @@ def main():
     # ---- scoring: two uint8 1356x2040 RGB images
     a8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)
     b8 = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device=dev)
-    res = torch.zeros(64, dtype=torch.uint8, device=dev)
+    res = torch.zeros(128, dtype=torch.uint8, device=dev)
     timed("score_pair_kernel", 2 * 1356 * 2040 * 3,
           lambda: L.check(lib.sr_score_pair_u8(L.ptr(a8), L.ptr(b8), 1356, 2040, 10, L.ptr(res), st())),
           "one 1356x2040 pair (Y-PSNR + Y-SSIM + RGB-SSIM fused)")

@@ -347,6 +347,47 @@ __global__ void patch_stitch_kernel(const float* __restrict__ patches, int cnt_h
   }
 }
 
+// Sharded stitch (BASELINE config 5): this rank ran only tiles [tile_lo, tile_hi) of the column-major tile
+// index (patches[0] = tile tile_lo) and writes the uint8 strip of output columns [x0, x0 + strip_w): a pixel whose
+// owner tile is in the range gets its value (x mul, clip, truncate -- exactly patch_stitch_kernel's), every other
+// pixel 0.  Strips of different ranks are disjoint where non-zero, so rank 0 composes them with a bitwise OR and
+// the result is bit-identical to the unsharded stitch; what crosses NVLink is owned uint8 pixels (3 B) instead of
+// whole fp32 patches (12 B x 2.25 overlap).  Four bytes per thread, one 4-byte store.
+__global__ void __launch_bounds__(256)
+patch_stitch_range_kernel(const float* __restrict__ patches, int cnt_h, int cnt_w, int PH, int PW, int S, int crop,
+                          int out_h, int tile_lo, int tile_hi, int x0, int strip_w, float mul,
+                          uint8_t* __restrict__ out_u8) {
+  const size_t row_elems = (size_t)strip_w * 3;
+  const size_t row_q = (row_elems + 3) / 4;
+  const size_t total = (size_t)out_h * row_q;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int Y = (int)(idx / row_q);
+    const int e0 = (int)(idx - (size_t)Y * row_q) * 4;
+    const int i = stitch_owner(Y, cnt_h, S, PH, crop);
+    uint8_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k;
+      if (e >= (int)row_elems || i < 0) continue;
+      const int X = x0 + e / 3, c = e % 3;
+      const int j = stitch_owner(X, cnt_w, S, PW, crop);
+      if (j < 0) continue;
+      const int n = j * cnt_h + i;
+      if (n < tile_lo || n >= tile_hi) continue;
+      const float f = __fmul_rn(patches[(((size_t)(n - tile_lo) * PH + (Y - S * i)) * PW + (X - S * j)) * 3 + c], mul);
+      v[k] = (uint8_t)(int)fminf(fmaxf(f, 0.f), 255.f);
+    }
+    uint8_t* dst = out_u8 + (size_t)Y * row_elems + e0;
+    if (e0 + 3 < (int)row_elems && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(dst) = v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24);
+    } else {
+      for (int k = 0; k < 4; ++k)
+        if (e0 + k < (int)row_elems) dst[k] = v[k];
+    }
+  }
+}
+
 // Four consecutive output elements per thread (16-byte patch load, 4-byte uint8 store).  Valid when every
 // ownership boundary and row length is a multiple of 4 elements: 3*S, 3*crop, 3*PW, 3*out_w all % 4 == 0
 // (true for the reference's 96/64/x4/8-px geometry); the host falls back to the scalar kernel otherwise.
@@ -886,6 +927,20 @@ extern "C" int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int p
   patch_stitch_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
       patches, cnt_h, cnt_w, ph * scale, PW, S, crop, out_h, out_w, mul, out_f32, out_u8);
   return check_launch("patch_stitch_kernel");
+}
+
+extern "C" int sr_patch_stitch_range(const float* patches, int cnt_h, int cnt_w, int ph, int pw, int step,
+                                     int scale, int canvas_h, int tile_lo, int tile_hi, int x0, int strip_w,
+                                     float mul, uint8_t* out_u8, void* stream) {
+  if (!patches || !out_u8) return set_error(SR_ERR_INVALID, "sr_patch_stitch_range: null pointer");
+  if (cnt_h < 1 || cnt_w < 1 || scale < 1 || tile_lo < 0 || tile_hi < tile_lo || tile_hi > cnt_h * cnt_w ||
+      x0 < 0 || strip_w < 1)
+    return set_error(SR_ERR_INVALID, "sr_patch_stitch_range: bad counts / tile range / strip");
+  const int out_h = canvas_h * scale;
+  const size_t total = (size_t)out_h * (((size_t)strip_w * 3 + 3) / 4);
+  patch_stitch_range_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      patches, cnt_h, cnt_w, ph * scale, pw * scale, step * scale, 8, out_h, tile_lo, tile_hi, x0, strip_w, mul, out_u8);
+  return check_launch("patch_stitch_range_kernel");
 }
 
 extern "C" int sr_depth_to_space(const float* in, int NB, int H, int W, int C, int r, int order,

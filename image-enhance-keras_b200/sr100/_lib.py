@@ -130,6 +130,7 @@ SIGNATURES = {
     "sr_patch_average_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sr_patch_gather_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_patch_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "sr_patch_stitch_range": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "sr_resize_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "sr_sharpen3x3_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sr_dataprep_patches": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),

@@ -607,40 +607,68 @@ class Engine:
             off += n
         return res
 
-    sharded_gather_description = "fp32 patch outputs gathered on rank 0 (NCCL), which stitches"
+    sharded_gather_description = ("every rank stitches the pixels its tiles own into a uint8 column strip, the strips are "
+                                  "gathered on rank 0 (NCCL) and OR-ed into the image")
 
-    def upscale_image_sharded(self, img_u8, patch=96, step=64, scale=4):
-        """One (large) image with its tiles sharded over the ranks of the process group (SURVEY 8e, BASELINE config
-        5): every rank runs a contiguous range of the column-major live-tile index through the conv stack -- no
-        exchange on the data path -- then the fp32 patch outputs are gathered on rank 0 (NCCL over NVLink), which
-        stitches and quantises.  Returns the uint8 [4h,4w,3] device image on rank 0, None elsewhere."""
-        import torch.distributed as tdist
+    def shard_plan(self, h, w, world, patch=96, step=64, scale=4):
+        """[(tile_lo, tile_hi, x0, x1)] per rank for one h x w image, + the tile plan: contiguous ranges of the
+        column-major live-tile index and the output columns each range can own."""
         from . import ops
         from .dist import shard_range
-        h, w, _ = img_u8.shape
         (gh, gw), counts, ext = plan_tiles(h, w, patch, step, scale, False)
+        n_tiles = counts[0] * counts[1]
+        shards = []
+        for r in range(world):
+            lo, hi = shard_range(n_tiles, r, world)
+            x0, x1 = ops.shard_strip(counts, (patch, patch), step, scale, scale * w, lo, hi) if hi > lo else (0, 0)
+            shards.append((lo, hi, x0, x1))
+        return (gh, gw), counts, ext, shards
+
+    def stitch_shard(self, out, counts, h, lo, hi, x0, width, patch=96, step=64, scale=4):
+        """uint8 strip [scale*h, width, 3] of the pixels tiles [lo, hi) own (zeros elsewhere); out = their patches."""
+        from . import ops
+        strip = torch.zeros(scale * h, width, 3, device=self.device, dtype=torch.uint8)
+        if hi > lo:
+            ops.patch_stitch_range(out, counts, (patch, patch), step, scale, h, lo, hi, x0, width, mul=255.0, out=strip)
+        return strip
+
+    def upscale_image_sharded(self, img_u8, patch=96, step=64, scale=4, world=None, rank=None, group_gather=None):
+        """One (large) image with its tiles sharded over the ranks of the process group (SURVEY 8e, BASELINE config
+        5): every rank runs a contiguous range of the column-major live-tile index through the conv stack and
+        stitches the pixels those tiles OWN into a uint8 column strip -- no exchange on the data path -- then the
+        strips (3 bytes per owned pixel, not 12-byte fp32 patches with their 2.25x overlap) are gathered on rank 0
+        (NCCL over NVLink) and OR-ed into the image: non-owned pixels of a strip are 0 and ownership is a partition,
+        so the result is bit-identical to the single-rank stitch.  Returns the uint8 [4h,4w,3] device image on
+        rank 0, None elsewhere.  (world / rank / group_gather: a logical split inside one process, for tests.)"""
+        import torch.distributed as tdist
+        from . import ops
+        h, w, _ = img_u8.shape
+        dist_on = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+        if world is None:
+            world, rank = (tdist.get_world_size(), tdist.get_rank()) if dist_on else (1, 0)
+        (gh, gw), counts, ext, shards = self.shard_plan(h, w, world, patch, step, scale)
         p, got = ops.patch_gather_u8(img_u8, (gh, gw), (patch, patch), step, divisor=255.0)
-        n_tiles = p.shape[0]
-        if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
+        assert got == counts
+        if world == 1:
             out = self.forward_device(p, extents=ext)
+            _, u8 = ops.patch_stitch(out, counts, (patch, patch), step, scale, (h, w), mul=255.0, want_f32=False,
+                                     want_u8=True)
+            return u8
+        lo, hi, x0, x1 = shards[rank]
+        wmax = max(s[3] - s[2] for s in shards)
+        out = self.forward_device(p[lo:hi], extents=ext[lo:hi]) if hi > lo else p[:0]
+        send = self.stitch_shard(out, counts, h, lo, hi, x0, wmax, patch, step, scale)
+        if group_gather is not None:
+            recv = group_gather(send)                      # tests: the logical ranks' strips, in rank order
         else:
-            rank, world = tdist.get_rank(), tdist.get_world_size()
-            lo, hi = shard_range(n_tiles, rank, world)
-            nmax = (n_tiles + world - 1) // world
-            send = torch.zeros(nmax, scale * patch, scale * patch, 3, device=self.device, dtype=torch.float32)
-            if hi > lo:
-                self.forward_device(p[lo:hi], out=send[:hi - lo], extents=ext[lo:hi])
             recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
             tdist.gather(send, recv, dst=0)
-            if rank != 0:
-                return None
-            parts = []
-            for r in range(world):
-                rlo, rhi = shard_range(n_tiles, r, world)
-                parts.append(recv[r][:rhi - rlo])
-            out = torch.cat(parts, dim=0)
-        _, u8 = ops.patch_stitch(out, counts, (patch, patch), step, scale, (h, w), mul=255.0, want_f32=False,
-                                 want_u8=True)
+        if rank != 0 or recv is None:
+            return None
+        u8 = torch.zeros(scale * h, scale * w, 3, device=self.device, dtype=torch.uint8)
+        for (rlo, rhi, rx0, rx1), strip in zip(shards, recv):
+            if rhi > rlo:
+                u8[:, rx0:rx1].bitwise_or_(strip[:, :rx1 - rx0])
         return u8
 
     def last_flops(self):

@@ -110,6 +110,30 @@ def patch_stitch(patches, counts, patch, step, scale, canvas_hw, mul=1.0, want_f
     return of, ou
 
 
+def shard_strip(counts, patch, step, scale, out_w, tile_lo, tile_hi, crop=8):
+    """Output columns [x0, x1) that tiles [tile_lo, tile_hi) of the column-major index can own: from the first
+    owned column of the first tile column to the last owned column of the last one (ownership passes from tile
+    column j-1 to j at scale*step*j + crop, img_utils.py:700-722), clipped to the image."""
+    cnt_h, cnt_w = counts
+    S, P = step * scale, patch[1] * scale
+    j_lo, j_hi = tile_lo // cnt_h, (tile_hi - 1) // cnt_h
+    x0 = 0 if j_lo == 0 else S * j_lo + crop
+    x1 = S * (j_hi + 1) + crop if j_hi < cnt_w - 1 else S * j_hi + P
+    return min(x0, out_w), min(x1, out_w)
+
+
+def patch_stitch_range(patches, counts, patch, step, scale, canvas_h, tile_lo, tile_hi, x0, strip_w, mul=255.0,
+                       out=None):
+    """uint8 strip [canvas_h*scale, strip_w, 3] of one shard's owned pixels (sr_patch_stitch_range)."""
+    lib = L.require_device()
+    cnt_h, cnt_w = counts
+    if out is None:
+        out = torch.empty(canvas_h * scale, strip_w, 3, device=patches.device, dtype=torch.uint8)
+    L.check(lib.sr_patch_stitch_range(L.ptr(patches), cnt_h, cnt_w, patch[0], patch[1], step, scale, canvas_h,
+                                      tile_lo, tile_hi, x0, strip_w, float(mul), L.ptr(out), L.stream_ptr()))
+    return out
+
+
 def depth_to_space(x, r, order):
     """fp32 NHWC [N,H,W,C*r*r] -> [N,H*r,W*r,C]; order 0 Subpixel/_phase_shift & depth_to_scale_tf,
     1 depth_to_scale_th, 2 tf.depth_to_space (keras_subpixel.py:64-84, advanced.py:87-129,195-196)."""

@@ -254,16 +254,28 @@ class _TrainGraph:
                     colsum(a1, shape, na, 1.0)
             return cs_next is not None
 
+        # Gradient buckets for the overlapped all-reduce (Trainer.step_device): the arena is in layer order and the
+        # backward runs last layer first, so "everything from layer L to the end of the previous bucket" is final
+        # once the backward of the block that starts at L has run.  marks: (len(self.bwd) at that point, arena lo, hi).
+        off = lambda bi: eng.param_slices[names[blocks[bi][1]]][0]
+        self.marks = []
         done = bwd_block(blocks[23], False, blocks[22])
         bwd_block(blocks[22], done, None, last_hr=True)
         self.bwd.append(lambda st: L.check(lib.sr_bilinear4_bwd(L.ptr(gsh32), NB, H, W, NUMK, L.ptr(gs32), st)))
         self.bwd.append(lambda st: L.check(lib.sr_cast_f32_to_bf16(L.ptr(gs32), npix * NUMK, L.ptr(gs), st)))
+        self.marks.append((len(self.bwd), off(22), eng.n_params))            # HR stage + tail: 9 layers, 9.4 MB
         done = False
         for bi in reversed(range(22)):
             done = bwd_block(blocks[bi], done, blocks[bi - 1] if bi > 0 else None)
+            if bi == 11:
+                # the launch that wrote block 10's tail bias gradient (cs_next) ran inside this block: that range
+                # belongs to the LAST bucket, which is reduced after everything
+                self.marks.append((len(self.bwd), off(11), off(22)))          # LR blocks 11..21: 39 MB
         hw, hb = tr.grad_w("level1"), tr.grad_b("level1")
         self.bwd.append(lambda st: L.check(lib.sr_head1x1_bwd(
             L.ptr(self.x_in), L.ptr(S[0]), L.ptr(gs32), None, npix, L.ptr(hw), L.ptr(hb), st)))
+        self.marks.append((len(self.bwd), 0, off(11)))                        # head + LR blocks 0..10: 39 MB
+        self.seg_graphs, self.seg_eager = {}, set()
 
 
 class Trainer:
@@ -288,6 +300,7 @@ class Trainer:
         self.tail_colw_packed = torch.empty(self.lib.sr_packed_weight_bytes(1, NUMK), dtype=torch.uint8, device=dev)
         self.packed_t = {}      # name -> packed weights of the input-gradient conv
         self._pack_table_t = None
+        self.comm_stream = None
         self._graphs = {}      # (NB, H, W) -> _TrainGraph, most recently used last (see graph())
         self.max_graphs = 3    # the full minibatch, the short last batch of a pass, the validation shape
         self.sync_replicas()
@@ -410,9 +423,75 @@ class Trainer:
         self.engine.repack()
         self.repack_t()
 
-    def step_device(self, g):
-        self.forward_backward_device(g)
-        self.apply_gradients()
+    def _world(self):
+        import torch.distributed as tdist
+        return tdist.get_world_size() if (tdist.is_available() and tdist.is_initialized()) else 1
+
+    def _run_segment(self, g, k, lo, hi):
+        """Launches [lo, hi) of (zero, forward, backward) as segment k: eager the first time, then captured and
+        replayed as its own CUDA graph (the all-reduce of a finished bucket is issued between segments)."""
+        ops = g.all_ops
+        gr = g.seg_graphs.get(k)
+        if self.engine.use_graphs and gr is not None:
+            gr.replay()
+            return
+
+        def body():
+            st = L.stream_ptr()
+            for f in ops[lo:hi]:
+                f(st)
+
+        body()
+        if self.engine.use_graphs and k in g.seg_eager and not torch.cuda.is_current_stream_capturing():
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    body()
+                g.seg_graphs[k] = gr
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn("sr100: CUDA graph capture of a training segment failed (%s: %s); running eagerly"
+                              % (type(e).__name__, e), RuntimeWarning)
+                self.engine.use_graphs = False
+        g.seg_eager.add(k)
+
+    def step_device(self, g, overlap=None):
+        """One optimizer step on the tensors in g.x_in / g.y_true.  With more than one rank the backward runs in
+        three segments and the gradient bucket each segment completes (HR stage + tail; LR blocks 11-21; the rest) is
+        all-reduced on a side stream while the next segment computes ("bucketed so the wgrad of early
+        layers overlaps"); only the last bucket's all-reduce is exposed.  overlap=False (or SR100_NO_OVERLAP=1): the
+        single all-reduce of the whole arena after backward.  World 1: no exchange at all."""
+        import torch.distributed as tdist
+        world = self._world()
+        if overlap is None:
+            overlap = os.environ.get("SR100_NO_OVERLAP", "0") != "1"
+        if world == 1 or not overlap:
+            self.forward_backward_device(g)
+            self.apply_gradients()
+            return
+        if not hasattr(g, "all_ops"):
+            zero = [lambda st: self.grads.zero_(), lambda st: g.loss_sum.zero_()]
+            g.all_ops = zero + list(g.fwd) + list(g.bwd)
+            base = len(zero) + len(g.fwd)
+            g.segments, prev = [], 0
+            for end, lo, hi in g.marks:
+                g.segments.append((prev, base + end, lo, hi))
+                prev = base + end
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(self.engine.device)
+        main = torch.cuda.current_stream()
+        works = []
+        for k, (a, b, lo, hi) in enumerate(g.segments):
+            self._run_segment(g, k, a, b)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                works.append(tdist.all_reduce(self.grads[lo:hi], op=tdist.ReduceOp.SUM, async_op=True))
+        for wk in works:
+            wk.wait()                       # the main stream waits for the reductions
+        main.wait_stream(self.comm_stream)
+        self.apply_gradients(summed_over=world)
 
     def train_on_batch(self, x, y):
         x_shape = tuple(x.shape)
@@ -434,7 +513,11 @@ class Trainer:
         return sse / n
 
     def comm_description(self):
-        return "one NCCL all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % (self.grads.numel() * 4)
+        if os.environ.get("SR100_NO_OVERLAP", "0") == "1":
+            return "one all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % (self.grads.numel() * 4)
+        return ("three all_reduce(sum) buckets of the fp32 gradient arena (%d bytes: HR stage + tail, LR blocks 11-21, "
+                "head + LR blocks 0-10), each issued on a side stream as soon as the backward segment that completes "
+                "it has been launched; only the last one is exposed" % (self.grads.numel() * 4))
 
     def evaluate(self, x, y):
         """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""

@@ -215,6 +215,15 @@ int sr_patch_stitch(const float* patches, int cnt_h, int cnt_w, int ph, int pw, 
                     int canvas_h, int canvas_w, float mul, float* out_f32, uint8_t* out_u8,
                     void* stream);
 
+/* The stitch of ONE SHARD of a tile-sharded image (the exchange of img_utils.py:692-724 when the
+ * tiles of one image ran on several GPUs): patches holds tiles [tile_lo, tile_hi) of the column-major tile index
+ * only; out_u8 is the uint8 strip [canvas_h*scale, strip_w, 3] of output columns [x0, x0 + strip_w) -- pixels owned
+ * by a tile of the range carry the stitched value (x mul, clip, truncate), all others 0.  The strips of all
+ * shards OR-ed together are bit-identical to sr_patch_stitch over all tiles. */
+int sr_patch_stitch_range(const float* patches, int cnt_h, int cnt_w, int ph, int pw, int step, int scale,
+                          int canvas_h, int tile_lo, int tile_hi, int x0, int strip_w, float mul,
+                          uint8_t* out_u8, void* stream);
+
 /* Minibatch assembly from an HBM-resident dataset.  Replaces the per-batch file decode of
  * img_utils.image_generator (img_utils.py:341-372): data = N decoded uint8 images of item_bytes bytes each
  * (item_bytes % 4 == 0), index = device int64[n] chosen by img_utils._index_generator;

@@ -118,3 +118,37 @@ def test_batch_of_equal_shapes_config3_equals_one_by_one(sr_model):
     assert np.array_equal(out[0], together[0]) and np.array_equal(out[1], together[1]) and np.array_equal(out[3], together[2])
     assert np.array_equal(out[2], sr_model.upscale_arrays([mixed[2]])[0])
     assert np.array_equal(out[5], sr_model.upscale_arrays([mixed[5]])[0])
+
+
+@pytest.mark.parametrize("shape,world", [((200, 330), 3), ((97, 610), 4), ((339, 510), 8), ((130, 70), 2)])
+def test_tile_sharded_image_is_bit_identical(shape, world):
+    """BASELINE config 5's sharding run as a LOGICAL split on one GPU: every logical rank runs its contiguous range of
+    the column-major live-tile index and stitches the pixels its tiles own into a uint8 column strip
+    (sr_patch_stitch_range); the strips OR-ed together on rank 0 equal the single-rank image bit for bit."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    rng = np.random.default_rng(shape[0] + world)
+    img = torch.from_numpy(rng.integers(0, 256, size=shape + (3,)).astype(np.uint8)).cuda()
+    w = om.init_weights(1234, bias_scale=0.01)
+    k, b = w["conv2d_85"]
+    w["conv2d_85"] = (k * 8.0, b + 0.3)
+    eng = Engine(w)
+    want = eng.upscale_images_device([img])[0]
+    strips = {}
+
+    def collect(rank):
+        def cb(send):
+            strips[rank] = send.clone()
+            return [strips[r] for r in range(world)] if rank == 0 else None
+        return cb
+
+    got = None
+    for rank in reversed(range(world)):
+        got = eng.upscale_image_sharded(img, world=world, rank=rank, group_gather=collect(rank))
+    assert got is not None and got.shape == want.shape
+    assert torch.equal(got, want)
+    # what crosses the link: owned uint8 pixels, not fp32 patches
+    _, counts, _, shards = eng.shard_plan(shape[0], shape[1], world)
+    sent = sum(4 * shape[0] * max(s[3] - s[2] for s in shards) * 3 for s in shards[1:])
+    patches = sum((s[1] - s[0]) * 384 * 384 * 3 * 4 for s in shards[1:])
+    assert sent < patches

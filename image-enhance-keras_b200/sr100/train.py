@@ -456,15 +456,18 @@ class Trainer:
         g.seg_eager.add(k)
 
     def step_device(self, g, overlap=None):
-        """One optimizer step on the tensors in g.x_in / g.y_true.  With more than one rank the backward runs in
-        three segments and the gradient bucket each segment completes (HR stage + tail; LR blocks 11-21; the rest) is
+        """One optimizer step on the tensors in g.x_in / g.y_true.  Default exchange: ONE all-reduce of the flat
+        gradient arena after backward.  overlap=True (or SR100_OVERLAP_ALLREDUCE=1): the backward runs in three
+        segments and the gradient bucket each segment completes (HR stage + tail; LR blocks 11-21; the rest) is
         all-reduced on a side stream while the next segment computes ("bucketed so the wgrad of early
-        layers overlaps"); only the last bucket's all-reduce is exposed.  overlap=False (or SR100_NO_OVERLAP=1): the
-        single all-reduce of the whole arena after backward.  World 1: no exchange at all."""
+        layers overlaps").  Measured on 2 B200s (profiles/r02_bench_n2_b.json): 89.4 ms overlapped vs 88.6 ms serial
+        vs 87.8 ms without any exchange -- the NCCL kernel takes SMs away from the persistent one-CTA-per-SM conv /
+        wgrad kernels it overlaps with, which costs more than the 0.8 ms it hides, so the serial exchange is the
+        default and bench.py reports both.  World 1: no exchange at all."""
         import torch.distributed as tdist
         world = self._world()
         if overlap is None:
-            overlap = os.environ.get("SR100_NO_OVERLAP", "0") != "1"
+            overlap = os.environ.get("SR100_OVERLAP_ALLREDUCE", "0") == "1"
         if world == 1 or not overlap:
             self.forward_backward_device(g)
             self.apply_gradients()
@@ -513,22 +516,9 @@ class Trainer:
         return sse / n
 
     def comm_description(self):
-        if os.environ.get("SR100_NO_OVERLAP", "0") == "1":
-            return "one all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % (self.grads.numel() * 4)
-        return ("three all_reduce(sum) buckets of the fp32 gradient arena (%d bytes: HR stage + tail, LR blocks 11-21, "
-                "head + LR blocks 0-10), each issued on a side stream as soon as the backward segment that completes "
-                "it has been launched; only the last one is exposed" % (self.grads.numel() * 4))
-
-    def evaluate(self, x, y):
-        """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""
-        g = self.graph(*tuple(x.shape)[:3])
-        self._load(g, x, y)
-        st = L.stream_ptr()
-        for f in g.fwd:
-            f(st)
-        d = g.out - g.y_true
-        acc = (g.out.argmax(dim=-1) == g.y_true.argmax(dim=-1)).float().mean()
-        return float((d * d).mean().item()), float(acc.item())
-
-    def step_flops(self, g):
-        return g.fwd_flops + g.bwd_flops
+        n = self.grads.numel() * 4
+        if os.environ.get("SR100_OVERLAP_ALLREDUCE", "0") == "1":
+            return ("three all_reduce(sum) buckets of the fp32 gradient arena (%d bytes: HR stage + tail, LR blocks 11-21, "
+                    "head + LR blocks 0-10), each issued on a side stream as soon as the backward segment that completes "
+                    "it has been launched" % n)
+        return "one all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % n

@@ -522,3 +522,17 @@ class Trainer:
                     "head + LR blocks 0-10), each issued on a side stream as soon as the backward segment that completes "
                     "it has been launched" % n)
         return "one all_reduce(sum) of the flat fp32 gradient arena (%d bytes) after backward" % n
+
+    def evaluate(self, x, y):
+        """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""
+        g = self.graph(*tuple(x.shape)[:3])
+        self._load(g, x, y)
+        st = L.stream_ptr()
+        for f in g.fwd:
+            f(st)
+        d = g.out - g.y_true
+        acc = (g.out.argmax(dim=-1) == g.y_true.argmax(dim=-1)).float().mean()
+        return float((d * d).mean().item()), float(acc.item())
+
+    def step_flops(self, g):
+        return g.fwd_flops + g.bwd_flops

@@ -285,25 +285,15 @@ def main():
     e2e = mp_step * e2e_steps / t_e2e
 
     # ---- roofline of the dominant kernel (conv_tc_pair_kernel): per-launch CUDA events over one more step
-    from sr100.engine import _Plan
+    # (sr_model_forward_timed: the same launches issued one by one between event pairs on the launching stream)
     step_resident()
     torch.cuda.synchronize()
-    stages = list(eng.last_stages)
-    tiles_run = sum(st_.NB for st_ in stages if hasattr(st_, "x_in"))
-    hr_shapes = sorted({(st_.eh, st_.ew) for st_ in stages if hasattr(st_, "eh")})
-    st = L.stream_ptr()
-    evs = []
-    for stg in stages:
-        for step in stg.steps:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            step(st)
-            b.record()
-            evs.append((a, b, isinstance(getattr(step, "__self__", None), _Plan)))
-    torch.cuda.synchronize()
-    conv_ms = sum(a.elapsed_time(b) for a, b, is_conv in evs if is_conv)
-    n_conv = sum(1 for _, _, is_conv in evs if is_conv)
-    total_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+    tiles_run, hr_shapes = eng.last_run_summary()
+    recs = eng.timed_launches()                      # [(ms, flops)], flops > 0 only for tensor-core conv launches
+    conv_ms = sum(ms for ms, fl in recs if fl > 0)
+    n_conv = sum(1 for ms, fl in recs if fl > 0)
+    total_ms = sum(ms for ms, _ in recs)
+    evs = recs
     conv_flops = eng.last_flops()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     rpeaks = peaks
@@ -341,8 +331,7 @@ def main():
     d2h = sum(16 * im.nbytes for im in images)
     h2d, d2h = int(D.sum_over_ranks(h2d)), int(D.sum_over_ranks(d2h))
     launches_total = int(D.sum_over_ranks(launches_per_step)) * steps
-    eng._graphs.clear()
-    torch.cuda.empty_cache()
+    eng.release()
 
     # =============================================================== configs[1]: Set5 tiled + scoring (every rank its own copy)
     if "set5" in parts:
@@ -372,8 +361,7 @@ def main():
                                     "stitch + Y-PSNR/Y-SSIM/RGB-SSIM; every rank runs its own copy (replicas)",
                         "value_per_gpu": round(mp5 * k5 / t5, 3), "e2e_per_gpu": round(mp5 * k5 / t5e, 3), "unit": UNIT,
                         "ms_per_step": round(t5 / k5 * 1e3, 3), "steps": k5}
-        eng._graphs.clear()
-        torch.cuda.empty_cache()
+        eng.release()
 
     # =============================================================== configs[4]: one 1080x1920 image, tiles sharded over ranks
     if "config5" in parts:
@@ -385,8 +373,7 @@ def main():
                                        "over the ranks in contiguous column-major ranges, " + eng.sharded_gather_description, "value": round(mpb * k / t, 2), "unit": UNIT,
                            "ms_per_step": round(t / k * 1e3, 3), "steps": k, "scaling": "strong"}
         del big
-        eng._graphs.clear()
-        torch.cuda.empty_cache()
+        eng.release()
 
     # =============================================================== configs[0]: one 128x128 patch (latency)
     if "config1" in parts:
@@ -398,8 +385,7 @@ def main():
                            "value_per_gpu": round(0.262144 * 100 / t, 2), "unit": UNIT,
                            "tflops": round(f1 * 100 / t / 1e12, 1),
                            "frac_of_sustained_peak": round(f1 * 100 / t / 1e12 / peaks["sustained"], 4)}
-        eng._graphs.clear()
-        torch.cuda.empty_cache()
+        eng.release()
 
     # =============================================================== configs[3]: training step, global batch 256
     if "train" in parts and not eng.tf32:
@@ -435,7 +421,9 @@ def main():
             tr.apply_gradients(summed_over=world)
 
         ms = run_steps(lambda: tr.step_device(g))                       # the default step (one all-reduce after backward)
-        ms_overlap = run_steps(lambda: tr.step_device(g, overlap=True)) if world > 1 else ms
+        ms_overlap = None
+        if world > 1 and eng.sequencer == "python":   # the bucketed overlap needs the Python launch lists
+            ms_overlap = run_steps(lambda: tr.step_device(g, overlap=True))
         ms_floor = run_steps(step_no_comm) if world > 1 else ms
         upd_ms = ms - ms_floor
         flops = tr.step_flops(g)
@@ -444,7 +432,9 @@ def main():
                         "forward + dgrad/wgrad bf16 on the tensor cores, NCCL all-reduce (sum) of the flat fp32 gradient "
                         "arena, fused Keras-Adam, weight repack", "global_batch": GB, "per_gpu_batch": hi - lo,
             "ms_per_step": round(ms, 3), "images_per_s": round(GB / ms * 1e3, 1), "steps": kt,
-            "ms_per_step_bucketed_overlapped_allreduce": round(ms_overlap, 3),
+            "ms_per_step_bucketed_overlapped_allreduce": None if ms_overlap is None else round(ms_overlap, 3),
+            "sequencer": "sr_model_forward_backward + sr_model_apply_gradients (libsr100)" if eng.sequencer == "c"
+                         else "python launch lists",
             "ms_per_step_without_exchange": round(ms_floor, 3),
             "exposed_allreduce_ms": round(upd_ms, 3),
             "allreduce_bytes": tr.grads.numel() * 4 if world > 1 else 0,

@@ -73,6 +73,10 @@ extern "C" size_t sr_abi_struct_size(int which) {
     case 3: return sizeof(sr_wgrad_desc);
     case 4: return sizeof(sr_wgrad_plan_info_t);
     case 5: return sizeof(sr_score_result);
+    case 6: return sizeof(sr_model_config);
+    case 7: return sizeof(sr_forward_desc);
+    case 8: return sizeof(sr_train_desc);
+    case 9: return sizeof(sr_model_run_info);
     default: return 0;
   }
 }

@@ -94,6 +94,36 @@ class ScoreResult(C.Structure):
     ]
 
 
+class ModelConfig(C.Structure):
+    _fields_ = [("precision", C.c_int), ("stream_lr_fp32", C.c_int), ("stream_hr_fp32", C.c_int),
+                ("a_mode", C.c_int), ("nacc", C.c_int), ("pair", C.c_int), ("use_graphs", C.c_int),
+                ("overlap_heads", C.c_int), ("fused_colsum", C.c_int)]
+
+
+class ForwardDesc(C.Structure):
+    _fields_ = [
+        ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("x", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("n_groups", C.c_int),
+        ("group_eh", C.POINTER(C.c_int)), ("group_ew", C.POINTER(C.c_int)), ("group_n", C.POINTER(C.c_int)),
+        ("group_index", C.POINTER(C.c_int)),
+    ]
+
+
+class TrainDesc(C.Structure):
+    _fields_ = [
+        ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("grads", C.c_void_p), ("loss_sum", C.c_void_p),
+        ("pred", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class ModelRunInfo(C.Structure):
+    _fields_ = [("conv_flops", C.c_double), ("launches", C.c_int), ("conv_launches", C.c_int),
+                ("graph_replay", C.c_int)]
+
+
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol declared in include/sr100.h
@@ -152,6 +182,24 @@ SIGNATURES = {
     "sr_axpby_f32": (_i, [_vp, _vp, _f, _f, _sz, _vp, _vp, _vp]),
     "sr_cast_f32_to_bf16": (_i, [_vp, _sz, _vp, _vp]),
     "sr_cast_bf16_to_f32": (_i, [_vp, _sz, _vp, _vp]),
+    "sr_model_default_config": (None, [C.POINTER(ModelConfig)]),
+    "sr_model_num_layers": (_i, []),
+    "sr_model_param_count": (_sz, []),
+    "sr_model_layer": (_i, [_i, C.c_char_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz),
+                            C.POINTER(_sz)]),
+    "sr_model_create": (_i, [_vp, C.POINTER(ModelConfig), C.POINTER(_vp)]),
+    "sr_model_destroy": (None, [_vp]),
+    "sr_model_refresh": (_i, [_vp, _vp]),
+    "sr_model_forward_workspace_bytes": (_sz, [_vp, C.POINTER(ForwardDesc)]),
+    "sr_model_forward": (_i, [_vp, C.POINTER(ForwardDesc), _vp]),
+    "sr_model_forward_info": (_i, [_vp, C.POINTER(ForwardDesc), C.POINTER(ModelRunInfo)]),
+    "sr_model_forward_timed": (_i, [_vp, C.POINTER(ForwardDesc), _vp, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                    _i, C.POINTER(_i)]),
+    "sr_model_train_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "sr_model_forward_backward": (_i, [_vp, C.POINTER(TrainDesc), _vp]),
+    "sr_model_train_info": (_i, [_vp, C.POINTER(TrainDesc), C.POINTER(ModelRunInfo)]),
+    "sr_model_apply_gradients": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
+    "sr_model_train_step": (_i, [_vp, C.POINTER(TrainDesc), _vp, _vp, _i, _f, _f, _f, _f, _vp]),
 }
 
 _lib = None
@@ -170,7 +218,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    for which, struct in enumerate((ConvDesc, ConvPlanInfo, PackItem, WgradDesc, WgradPlanInfo, ScoreResult)):
+    for which, struct in enumerate((ConvDesc, ConvPlanInfo, PackItem, WgradDesc, WgradPlanInfo, ScoreResult, ModelConfig,
+                                    ForwardDesc, TrainDesc, ModelRunInfo)):
         if lib.sr_abi_struct_size(which) != C.sizeof(struct):
             raise SrError(-1, "%s: ctypes layout (%d bytes) does not match libsr100.so (%d bytes); rebuild the "
                               "library or update sr100/_lib.py" % (struct.__name__, C.sizeof(struct),

@@ -385,8 +385,16 @@ class Engine:
     """Device-resident DifvdsrDouble weights + cached per-shape graphs."""
 
     def __init__(self, weights=None, device=None, stream="lr32", a_mode=0, nacc=2, pair=1,
-                 max_pixels=192 * 96 * 96, use_graphs=True, precision=None):
+                 max_pixels=192 * 96 * 96, use_graphs=True, precision=None, sequencer=None):
+        """sequencer: "c" (default) -- the launch sequence, its plans and CUDA graphs live in libsr100 behind
+        sr_model_forward / sr_model_forward_backward (csrc/model.cu; one ctypes call per forward); "python"
+        (SR100_PY_SEQUENCE=1) -- the same sequence issued launch by launch from this module (_LRStage / _HRStage),
+        kept for per-launch tooling and as the bit-for-bit cross-check of the C entry points."""
         self.lib = L.require_device()
+        sequencer = sequencer or ("python" if os.environ.get("SR100_PY_SEQUENCE", "0") == "1" else "c")
+        if sequencer not in ("c", "python"):
+            raise ValueError("sequencer must be 'c' or 'python', got %r" % (sequencer,))
+        self.sequencer = sequencer
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         assert stream in ("bf16", "lr32", "fp32")
         precision = precision or os.environ.get("SR100_PRECISION", "bf16")
@@ -420,12 +428,46 @@ class Engine:
             self.master[name] = (self.param_arena[ow:ow + nw].view(k, k, cin, cout), self.param_arena[ob:ob + nb])
         self.packed = {}
         self._pack_table = None
+        self._py_packed = self.sequencer != "c"     # C sequencer: the Python-side packed copy is built on first use
         self._init_bias_pairs()
         self._graphs = {}
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         # second stream for independent launches of small inputs (_Stage._launch_all); SR100_NO_OVERLAP=1 disables it
         self.side_stream = None if os.environ.get("SR100_NO_OVERLAP", "0") == "1" else torch.cuda.Stream(self.device)
+        self.model = C.c_void_p()            # sr_model*: owns packed weights, plans and graphs of the C sequencer
+        self._ws = self._x_buf = self._out_buf = None
+        self.last_calls, self.last_stages = [], []
         self.set_weights_dict(weights if weights is not None else glorot_uniform_weights())
+
+    def _ensure_model(self):
+        if not self.model:
+            cfg = L.ModelConfig()
+            self.lib.sr_model_default_config(C.byref(cfg))
+            cfg.precision = 1 if self.tf32 else 0
+            cfg.stream_lr_fp32, cfg.stream_hr_fp32 = int(self.stream_lr_fp32), int(self.stream_hr_fp32)
+            cfg.a_mode, cfg.nacc, cfg.pair = self.a_mode, self.nacc, self.pair
+            cfg.use_graphs = int(self.use_graphs)
+            cfg.overlap_heads = int(self.side_stream is not None)
+            cfg.fused_colsum = int(os.environ.get("SR100_FUSED_COLSUM", "1") != "0")
+            with torch.cuda.device(self.device):
+                L.check(self.lib.sr_model_create(L.ptr(self.param_arena), C.byref(cfg), C.byref(self.model)))
+        return self.model
+
+    def __del__(self):
+        try:
+            if self.model:
+                self.lib.sr_model_destroy(self.model)
+                self.model = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def release(self):
+        """Give the cached activation buffers back to the allocator (plans stay; they are rebuilt on demand)."""
+        for st in self._graphs.values():
+            st.hr.clear()
+        self._graphs.clear()
+        self._ws = self._x_buf = self._out_buf = None
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- weights
     def set_weights_dict(self, weights):
@@ -443,9 +485,14 @@ class Engine:
         self.head_b = self.master["level1"][1]
         self.repack()
 
-    def repack(self):
+    def repack(self, c_model=True):
         """(Re)build the tensor-core weight layout from the fp32 masters (after load / optimizer step): one launch
-        for all 85 layers (sr_pack_conv_weights_batched)."""
+        for all 85 layers (sr_pack_conv_weights_batched).  The C sequencer keeps its own packed copy (sr_model_refresh);
+        the Python-side copy exists only once something asked for it (ensure_py_packed)."""
+        if c_model and self.sequencer == "c":
+            L.check(self.lib.sr_model_refresh(self._ensure_model(), L.stream_ptr()))
+        if self.sequencer == "c" and not self._py_packed:
+            return
         if self.tf32:
             st = L.stream_ptr()
             for name, k, cin, cout in self.specs:
@@ -466,6 +513,12 @@ class Engine:
             self._pack_table = PackTable(self, self.packed, flip=False)
         self._pack_table.run()
         self._refresh_bias_sums()
+
+    def ensure_py_packed(self):
+        """Packed weights for plans created from Python (the "python" sequencer, Trainer's Python launch lists)."""
+        if not self._py_packed:
+            self._py_packed = True
+            self.repack(c_model=False)
 
     def _init_bias_pairs(self):
         """The 18 two-source launches (fused tails of the 5/3 blocks) add two biases: one [18,128] buffer, refreshed
@@ -501,6 +554,7 @@ class Engine:
     # ---------------------------------------------------------------- forward
     def graph(self, NB, H, W, need=None):
         """The LR stage (buffers + plans) for NB patches of HxW; HR stages hang off it.  need: see _LRStage."""
+        self.ensure_py_packed()
         need = (H, W) if need is None else (min(H, need[0]), min(W, need[1]))
         key = (NB, H, W) + need
         g = self._graphs.get(key)
@@ -534,7 +588,12 @@ class Engine:
         if out is None:
             out = torch.empty(N, 4 * H, 4 * W, 3, device=self.device, dtype=torch.float32)
         nb = min(N, self.sub_batch(H, W))
-        self.last_stages = []
+        self.last_stages, self.last_calls = [], []
+        if self.sequencer == "c":
+            for i in range(0, N, nb):
+                n = min(nb, N - i)
+                self._forward_c(x[i:i + n], out[i:i + n], None if extents is None else extents[i:i + n])
+            return out
         for i in range(0, N, nb):
             n = min(nb, N - i)
             if extents is None:
@@ -559,6 +618,102 @@ class Engine:
                 self.last_stages.append(hs)
             out[i:i + n].copy_(g.out)
         return out
+
+    # ---------------------------------------------------------------- the C sequencer (sr_model_forward)
+    def _forward_desc(self, n, H, W, extents):
+        """sr_forward_desc of one sub-batch on the engine's shared buffers (+ the ctypes arrays it points to)."""
+        d = L.ForwardDesc()
+        d.NB, d.H, d.W = n, H, W
+        keep, groups = [], {}
+        if extents is not None:
+            for j in range(n):
+                groups.setdefault((int(extents[j][0]), int(extents[j][1])), []).append(j)
+            arr = lambda v: (C.c_int * len(v))(*v)
+            eh, ew = arr([k[0] for k in groups]), arr([k[1] for k in groups])
+            cnt, idx = arr([len(v) for v in groups.values()]), arr([j for v in groups.values() for j in v])
+            d.n_groups, d.group_eh, d.group_ew, d.group_n, d.group_index = len(groups), eh, ew, cnt, idx
+            keep = [eh, ew, cnt, idx]
+        return d, keep, groups
+
+    def _bind_buffers(self, d):
+        """Point the descriptor at the shared grow-only buffers (workspace, input, output): stable pointers keep the
+        library's plan / graph cache hot; a forward runs start to end on one stream, so sharing is safe."""
+        need = self.lib.sr_model_forward_workspace_bytes(self._ensure_model(), C.byref(d))
+        if need == 0:
+            L.check(-1)
+        nx = d.NB * d.H * d.W * 3
+        try:
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if self._x_buf is None or self._x_buf.numel() < nx:
+                self._x_buf = self._out_buf = None
+                self._x_buf = torch.empty(nx, dtype=torch.float32, device=self.device)
+                self._out_buf = torch.empty(16 * nx, dtype=torch.float32, device=self.device)
+        except torch.cuda.OutOfMemoryError:
+            self.release()
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._x_buf = torch.empty(nx, dtype=torch.float32, device=self.device)
+            self._out_buf = torch.empty(16 * nx, dtype=torch.float32, device=self.device)
+        d.x, d.out = self._x_buf.data_ptr(), self._out_buf.data_ptr()
+        d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+
+    def _forward_c(self, x, out, extents):
+        n, H, W, _ = x.shape
+        d, keep, groups = self._forward_desc(n, H, W, extents)
+        self._bind_buffers(d)
+        nx = n * H * W * 3
+        self._x_buf[:nx].view(n, H, W, 3).copy_(x)
+        L.check(self.lib.sr_model_forward(self.model, C.byref(d), L.stream_ptr()))
+        out.copy_(self._out_buf[:16 * nx].view(n, 4 * H, 4 * W, 3))
+        self.last_calls.append((d, keep, groups))
+
+    def timed_launches(self):
+        """[(ms, flops)] of every launch of the most recent forward_device call, re-run launch by launch between
+        CUDA events (sr_model_forward_timed; flops = 0 for launches that are not tensor-core convs)."""
+        res = []
+        if self.sequencer != "c":
+            st = L.stream_ptr()
+            evs = []
+            for stg in self.last_stages:
+                for step in stg.steps:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    step(st)
+                    b.record()
+                    owner = getattr(step, "__self__", None)
+                    evs.append((a, b, owner.flops if isinstance(owner, _Plan) else 0.0))
+            torch.cuda.synchronize()
+            return [(a.elapsed_time(b), f) for a, b, f in evs]
+        for d, keep, _ in self.last_calls:
+            info = L.ModelRunInfo()
+            L.check(self.lib.sr_model_forward_info(self.model, C.byref(d), C.byref(info)))
+            ms, fl, cnt = (C.c_float * info.launches)(), (C.c_double * info.launches)(), C.c_int(0)
+            L.check(self.lib.sr_model_forward_timed(self.model, C.byref(d), L.stream_ptr(), ms, fl, info.launches,
+                                                    C.byref(cnt)))
+            res.extend(zip(list(ms), list(fl)))
+        return res
+
+    def last_run_summary(self):
+        """(patches run, sorted HR-stage extents) of the most recent forward_device call."""
+        if self.sequencer == "c":
+            tiles = sum(d.NB for d, _, _ in self.last_calls)
+            ext = sorted({k for _, _, g in self.last_calls for k in g} or
+                         {(4 * d.H, 4 * d.W) for d, _, _ in self.last_calls})
+            return tiles, ext
+        tiles = sum(st_.NB for st_ in self.last_stages if hasattr(st_, "x_in"))
+        return tiles, sorted({(st_.eh, st_.ew) for st_ in self.last_stages if hasattr(st_, "eh")})
+
+    def graph_ready(self):
+        """True when the next forward of the most recent shape replays a captured CUDA graph."""
+        if self.sequencer == "c":
+            ok = bool(self.last_calls)
+            for d, _, _ in self.last_calls:
+                info = L.ModelRunInfo()
+                L.check(self.lib.sr_model_forward_info(self.model, C.byref(d), C.byref(info)))
+                ok = ok and bool(info.graph_replay)
+            return ok
+        return bool(self.last_stages) and all(st.cuda_graph is not None for st in self.last_stages)
 
     def upscale_images_device(self, imgs_u8, patch=96, step=64, scale=4, full_canvas=False):
         """The device part of upscaleStepPatch (models.py:225-391) for a list of uint8 [h,w,3] device images:
@@ -673,6 +828,13 @@ class Engine:
 
     def last_flops(self):
         """Algorithmic FLOPs (2*MAC) of the tensor-core launches of the most recent forward_device call."""
+        if self.sequencer == "c":
+            tot = 0.0
+            for d, _, _ in self.last_calls:
+                info = L.ModelRunInfo()
+                L.check(self.lib.sr_model_forward_info(self.model, C.byref(d), C.byref(info)))
+                tot += info.conv_flops
+            return tot
         return float(sum(st.conv_flops for st in getattr(self, "last_stages", [])))
 
     def conv_flops(self, N, H, W):

@@ -278,6 +278,33 @@ class _TrainGraph:
         self.seg_graphs, self.seg_eager = {}, set()
 
 
+class _CTrainGraph:
+    """One minibatch shape on the C sequencer: the tensors the caller fills / reads and the sr_train_desc that binds
+    them; plans, launch order and the CUDA graph live in libsr100 (sr_model_forward_backward, csrc/model.cu)."""
+
+    def __init__(self, tr, NB, H, W):
+        eng, dev = tr.engine, tr.engine.device
+        self.NB, self.H, self.W = NB, H, W
+        f32 = torch.float32
+        self.x_in = torch.empty(NB, H, W, 3, device=dev, dtype=f32)
+        self.y_true = torch.empty(NB, 4 * H, 4 * W, 3, device=dev, dtype=f32)
+        self.out = torch.empty(NB, 4 * H, 4 * W, 3, device=dev, dtype=f32)
+        self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.n_local = NB * 16 * H * W * 3
+        model = eng._ensure_model()
+        need = eng.lib.sr_model_train_workspace_bytes(model, NB, H, W)
+        self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        d = L.TrainDesc()
+        d.NB, d.H, d.W = NB, H, W
+        d.x, d.y, d.grads = self.x_in.data_ptr(), self.y_true.data_ptr(), tr.grads.data_ptr()
+        d.loss_sum, d.pred = self.loss_sum.data_ptr(), self.out.data_ptr()
+        d.workspace, d.workspace_bytes = self.workspace.data_ptr(), need
+        self.desc = d
+        info = L.ModelRunInfo()
+        L.check(eng.lib.sr_model_train_info(model, C.byref(d), C.byref(info)))
+        self.flops, self.launches = info.conv_flops, info.launches
+
+
 class Trainer:
     """train_on_batch / evaluate for a kmodel.Model (Keras Model.train_on_batch semantics: returns the loss)."""
 
@@ -303,8 +330,12 @@ class Trainer:
         self.comm_stream = None
         self._graphs = {}      # (NB, H, W) -> _TrainGraph, most recently used last (see graph())
         self.max_graphs = 3    # the full minibatch, the short last batch of a pass, the validation shape
+        # "c": sr_model_forward_backward / sr_model_apply_gradients own the launch sequence; "python": the launch lists
+        # of _TrainGraph (needed for the bucketed overlap and the per-kernel breakdown of tools/bench_train.py)
+        self.sequencer = engine.sequencer
         self.sync_replicas()
-        self.repack_t()
+        if self.sequencer != "c":
+            self.repack_t()
 
     # ------------------------------------------------------------------ views into the flat arenas
     def grad_w(self, name):
@@ -322,6 +353,7 @@ class Trainer:
     def repack_t(self):
         """Weights of the input-gradient convs (180-degree rotated, cin <-> cout): one launch for all layers."""
         from .engine import PackTable
+        self.engine.ensure_py_packed()
         if self._pack_table_t is None:
             for name, k, cin, cout in self.engine.specs:
                 if cin == NUMK and name not in self.packed_t:
@@ -363,12 +395,15 @@ class Trainer:
         if g is None:
             while len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
+            make = _CTrainGraph if self.sequencer == "c" else _TrainGraph
+            if make is _TrainGraph and self._pack_table_t is None:
+                self.repack_t()
             try:
-                g = _TrainGraph(self, NB, H, W)
+                g = make(self, NB, H, W)
             except torch.cuda.OutOfMemoryError:
                 self._graphs.clear()
                 torch.cuda.empty_cache()
-                g = _TrainGraph(self, NB, H, W)
+                g = make(self, NB, H, W)
         self._graphs[key] = g      # most recently used last
         return g
 
@@ -384,6 +419,9 @@ class Trainer:
         """Forward + backward on the tensors already in g.x_in / g.y_true; gradients land in self.grads.  The ~450
         launches are a fixed sequence on fixed buffers: after one eager step they replay as one CUDA graph (at 32
         patches per GPU the step is otherwise launch-bound)."""
+        if isinstance(g, _CTrainGraph):
+            L.check(self.lib.sr_model_forward_backward(self.engine.model, C.byref(g.desc), L.stream_ptr()))
+            return
         if self.engine.use_graphs and g.cuda_graph is not None:
             g.cuda_graph.replay()
             return
@@ -417,6 +455,15 @@ class Trainer:
         from .dist import all_reduce_sum_
         world = all_reduce_sum_(self.grads) if summed_over is None else int(summed_over)
         self.t += 1
+        if self.sequencer == "c":      # Adam + every weight repack behind one entry point
+            L.check(self.lib.sr_model_apply_gradients(self.engine.model, L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v),
+                                                      self.t, self.lr, self.beta_1, self.beta_2, self.epsilon,
+                                                      1.0 / world, L.stream_ptr()))
+            if self.engine._py_packed:           # something built Python-side plans too: keep their copies current
+                self.engine.repack(c_model=False)
+                if self._pack_table_t is not None:
+                    self.repack_t()
+            return
         L.check(self.lib.sr_adam_step(L.ptr(self.engine.param_arena), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v),
                                       self.engine.n_params, self.lr, self.beta_1, self.beta_2, self.epsilon, self.t,
                                       1.0 / world, L.stream_ptr()))
@@ -472,6 +519,9 @@ class Trainer:
             self.forward_backward_device(g)
             self.apply_gradients()
             return
+        if isinstance(g, _CTrainGraph):
+            raise RuntimeError("the bucketed overlapped all-reduce needs the Python launch lists: "
+                               "Engine(sequencer='python') or SR100_PY_SEQUENCE=1")
         if not hasattr(g, "all_ops"):
             zero = [lambda st: self.grads.zero_(), lambda st: g.loss_sum.zero_()]
             g.all_ops = zero + list(g.fwd) + list(g.bwd)
@@ -527,12 +577,23 @@ class Trainer:
         """(mse, categorical accuracy over the 3 colour channels) -- the compile(metrics=['accuracy']) pair."""
         g = self.graph(*tuple(x.shape)[:3])
         self._load(g, x, y)
-        st = L.stream_ptr()
-        for f in g.fwd:
-            f(st)
+        if isinstance(g, _CTrainGraph):
+            g.out.copy_(self.engine.forward_device(g.x_in))
+        else:
+            st = L.stream_ptr()
+            for f in g.fwd:
+                f(st)
         d = g.out - g.y_true
         acc = (g.out.argmax(dim=-1) == g.y_true.argmax(dim=-1)).float().mean()
         return float((d * d).mean().item()), float(acc.item())
 
+    def graph_ready(self, g):
+        """True when the next forward_backward_device(g) replays a captured CUDA graph."""
+        if isinstance(g, _CTrainGraph):
+            info = L.ModelRunInfo()
+            L.check(self.lib.sr_model_train_info(self.engine.model, C.byref(g.desc), C.byref(info)))
+            return bool(info.graph_replay)
+        return g.cuda_graph is not None
+
     def step_flops(self, g):
-        return g.fwd_flops + g.bwd_flops
+        return g.flops if isinstance(g, _CTrainGraph) else g.fwd_flops + g.bwd_flops

@@ -40,7 +40,7 @@ int sr_dev_switches(void);
 int sr_dev_set_timeline(void* buf);
 /* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
  * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
- * 5 sr_score_result; 0 for anything else. */
+ * 5 sr_score_result, 6 sr_model_config, 7 sr_forward_desc, 8 sr_train_desc, 9 sr_model_run_info; 0 for anything else. */
 size_t sr_abi_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -381,6 +381,103 @@ int sr_axpby_f32(const float* x, const float* y, float a, float b, size_t n, flo
                  void* out_bf16, void* stream);
 int sr_cast_f32_to_bf16(const float* in, size_t n, void* out_bf16, void* stream);
 int sr_cast_bf16_to_f32(const void* in_bf16, size_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph-level entry points.  Replace keras Model.predict (models.py:178, 342, 541, 783) and one
+ * train_on_batch of Model.fit_generator (models.py:146-157) on the DifvdsrDouble graph
+ * (models.py:1159-1270): the whole launch sequence (head 1x1 -> 16 5/3 blocks -> 6 light blocks ->
+ * bilinear x4 -> 2 5/3 blocks -> tail conv; its backward; Adam) lives in the library, so a binding that is
+ * not Python can run the model.  An sr_model owns the packed tensor-core weights, the conv / wgrad plans
+ * (TMA descriptors) per shape and the CUDA graphs that replay them; activations live in a caller-provided
+ * workspace (size query + pointer, the library never allocates caller-visible tensors).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sr_model sr_model;
+
+typedef struct sr_model_config {
+  int precision;       /* 0: bf16 operands (default); 1: tf32 operands, fp32 tensors (inference only) */
+  int stream_lr_fp32;  /* 1 (default): the residual stream of the 22 LR blocks is also kept in fp32 */
+  int stream_hr_fp32;  /* 1: the HR stage too (forced for tf32); default 0 */
+  int a_mode, nacc, pair; /* sr_conv_desc fields of every launch; defaults 0, 2, 1 */
+  int use_graphs;      /* 1 (default): a (shape, pointers) combination runs eagerly once, then is captured into a
+                        * CUDA graph that later calls replay with one submission */
+  int overlap_heads;   /* 1 (default): the two branch heads of a 5/3 block (independent launches) run concurrently on
+                        * an internal second stream when both grids fit on the chip together (small inputs) */
+  int fused_colsum;    /* 1 (default): bias gradients ride the input-gradient launches (sr_conv_desc.colsum_f32);
+                        * 0: separate sr_colsum_bf16 passes (same values, another fp32 summation order) */
+} sr_model_config;
+void sr_model_default_config(sr_model_config* cfg);
+
+/* The parameter arena: all 86 layers in Keras creation order ('level1', conv2d_1 .. conv2d_85), each as
+ * kernel (HWIO fp32) then bias; offsets in floats.  name: at least 16 bytes. */
+int sr_model_num_layers(void);
+size_t sr_model_param_count(void);
+int sr_model_layer(int index, char* name, int* ksize, int* cin, int* cout, size_t* kernel_offset,
+                   size_t* bias_offset);
+
+/* params: DEVICE fp32 [sr_model_param_count()], caller-owned, read at every sr_model_refresh (and updated in
+ * place by sr_model_apply_gradients).  Creating the model packs the weights once (synchronous). */
+int sr_model_create(float* params, const sr_model_config* cfg, sr_model** model);
+void sr_model_destroy(sr_model* model);
+/* Re-pack the tensor-core weight layouts after the caller changed params (load_weights / set_weights). */
+int sr_model_refresh(sr_model* model, void* stream);
+
+typedef struct sr_forward_desc {
+  int NB, H, W;
+  const float* x;       /* fp32 [NB,H,W,3] in [0,1] (the /255 patch stack, models.py:336) */
+  float* out;           /* fp32 [NB,4H,4W,3] (what model.predict returns) */
+  void* workspace;      /* device scratch, >= sr_model_forward_workspace_bytes() */
+  size_t workspace_bytes;
+  /* Optional dead-region elimination of the tiled path (img_utils.py:700-722 keeps [8,264) of a 384-pixel patch
+   * axis): the patches are partitioned into n_groups classes; the patches group_index[...] of class g get only
+   * the top-left group_eh[g] x group_ew[g] corner (multiples of 4) of their output computed, the rest of their
+   * slot is left untouched, and the last LR layers shrink to the region that corner can see.  HOST arrays;
+   * group_index holds sum(group_n) = NB patch numbers, class after class.  n_groups = 0: every patch whole. */
+  int n_groups;
+  const int* group_eh;
+  const int* group_ew;
+  const int* group_n;
+  const int* group_index;
+} sr_forward_desc;
+
+typedef struct sr_model_run_info {
+  double conv_flops;    /* algorithmic FLOPs (2*MAC) of the tensor-core launches */
+  int launches;         /* kernel launches of one call */
+  int conv_launches;    /* of which tensor-core conv / wgrad launches */
+  int graph_replay;     /* 1 when the next call will replay a captured CUDA graph */
+} sr_model_run_info;
+
+size_t sr_model_forward_workspace_bytes(const sr_model* model, const sr_forward_desc* desc);
+int sr_model_forward(sr_model* model, const sr_forward_desc* desc, void* stream);
+int sr_model_forward_info(sr_model* model, const sr_forward_desc* desc, sr_model_run_info* info);
+/* The same forward launch by launch with CUDA events around every kernel (synchronises `stream`): ms[i], flops[i]
+ * (0 for launches that are not tensor-core convs) for i < min(*n, max_records); *n = launches.  For roofline
+ * measurements (bench.py); never replays a graph. */
+int sr_model_forward_timed(sr_model* model, const sr_forward_desc* desc, void* stream, float* ms,
+                           double* flops, int max_records, int* n);
+
+typedef struct sr_train_desc {
+  int NB, H, W;
+  const float* x;       /* fp32 [NB,H,W,3] */
+  const float* y;       /* fp32 [NB,4H,4W,3] target */
+  float* grads;         /* fp32 [sr_model_param_count()]: zeroed, then d(mse over this batch)/d(param) */
+  double* loss_sum;     /* device fp64: zeroed, then sum of squared errors of this batch */
+  float* pred;          /* optional fp32 [NB,4H,4W,3]: the forward output (NULL: kept in the workspace) */
+  void* workspace;
+  size_t workspace_bytes;
+} sr_train_desc;
+
+size_t sr_model_train_workspace_bytes(const sr_model* model, int NB, int H, int W);
+/* Forward with saved activations, loss='mse' and the whole backward (dgrad / wgrad on the tensor cores, bias and
+ * head gradients): compile(loss='mse') + the gradient half of train_on_batch (models.py:1212-1213, 146). */
+int sr_model_forward_backward(sr_model* model, const sr_train_desc* desc, void* stream);
+int sr_model_train_info(sr_model* model, const sr_train_desc* desc, sr_model_run_info* info);
+/* Keras-2 Adam (sr_adam_step) over the whole arena with the model's own params, then sr_model_refresh.
+ * grad_scale: 1/world after an all-reduce(sum) of `grads` over data-parallel ranks, else 1. */
+int sr_model_apply_gradients(sr_model* model, const float* grads, float* m, float* v, int t, float lr,
+                             float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* One single-process optimizer step: sr_model_forward_backward + sr_model_apply_gradients(grad_scale 1). */
+int sr_model_train_step(sr_model* model, const sr_train_desc* desc, float* m, float* v, int t, float lr,
+                        float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,8 @@ def test_version_and_error_string(lib):
 
 def test_struct_layouts_match_the_library(lib):
     from sr100 import _lib as L
-    structs = (L.ConvDesc, L.ConvPlanInfo, L.PackItem, L.WgradDesc, L.WgradPlanInfo, L.ScoreResult)
+    structs = (L.ConvDesc, L.ConvPlanInfo, L.PackItem, L.WgradDesc, L.WgradPlanInfo, L.ScoreResult, L.ModelConfig,
+               L.ForwardDesc, L.TrainDesc, L.ModelRunInfo)
     for which, st in enumerate(structs):
         assert lib.sr_abi_struct_size(which) == C.sizeof(st), st.__name__
     assert lib.sr_abi_struct_size(99) == 0
@@ -76,6 +77,27 @@ def test_packed_weight_bytes(lib):
     assert lib.sr_packed_weight_bytes(3, 128) == 9 * 128 * 128 * 2
     assert lib.sr_packed_weight_bytes(5, 128) == 25 * 128 * 128 * 2
     assert lib.sr_packed_weight_bytes(3, 3) == 9 * 128 * 16 * 2
+
+
+def test_model_layer_table_is_the_keras_creation_order(lib):
+    """sr_model_layer (host only): 'level1', conv2d_1..conv2d_85 as models.py:1177-1199 creates them, laid out in the
+    flat arena exactly like the engine's parameter slices (kernel HWIO, then bias)."""
+    from sr100.engine import layer_specs
+    specs = layer_specs()
+    assert lib.sr_model_num_layers() == len(specs) == 86
+    name = C.create_string_buffer(16)
+    k, cin, cout, wo, bo = C.c_int(), C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+    off = 0
+    for i, (n, kk, ci, co) in enumerate(specs):
+        assert lib.sr_model_layer(i, name, C.byref(k), C.byref(cin), C.byref(cout), C.byref(wo), C.byref(bo)) == 0
+        assert (name.value.decode(), k.value, cin.value, cout.value) == (n, kk, ci, co)
+        assert wo.value == off and bo.value == off + kk * kk * ci * co
+        off = bo.value + co
+    assert lib.sr_model_param_count() == off == 21838211          # SURVEY.md 8d
+    assert lib.sr_model_layer(86, name, None, None, None, None, None) == -1
+    cfg = __import__("sr100._lib", fromlist=["ModelConfig"]).ModelConfig()
+    lib.sr_model_default_config(C.byref(cfg))
+    assert (cfg.precision, cfg.stream_lr_fp32, cfg.nacc, cfg.pair, cfg.use_graphs) == (0, 1, 2, 1, 1)
 
 
 def test_null_pointer_errors_do_not_touch_the_device(lib):

@@ -1,0 +1,218 @@
+"""-m gpu: the graph-level C entry points (include/sr100.h: sr_model_create / sr_model_forward /
+sr_model_forward_backward / sr_model_apply_gradients / sr_model_train_step, csrc/model.cu) -- what replaces
+model.predict (models.py:342) and one train_on_batch of fit_generator (models.py:146) for a binding that is not Python.
+
+Checked three ways: (1) raw ctypes calls with nothing but device pointers against the CPU oracle, (2) bit for bit
+against the same launch sequence issued from Python (Engine(sequencer='python')), (3) CUDA-graph replay == eager."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _smooth(rng, n, h, w):
+    from scipy.ndimage import uniform_filter
+    a = rng.integers(0, 256, size=(n, h, w, 3)).astype(np.float32)
+    return (uniform_filter(a, size=(1, 5, 5, 1)) / 255.0).astype(np.float32)
+
+
+def _arena(lib, weights):
+    """The flat fp32 parameter arena of sr_model_layer's table, filled from a {name: (kernel, bias)} dict."""
+    n = lib.sr_model_param_count()
+    a = np.zeros(n, dtype=np.float32)
+    name = C.create_string_buffer(16)
+    k, cin, cout, wo, bo = C.c_int(), C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+    for i in range(lib.sr_model_num_layers()):
+        assert lib.sr_model_layer(i, name, C.byref(k), C.byref(cin), C.byref(cout), C.byref(wo), C.byref(bo)) == 0
+        w, b = weights[name.value.decode()]
+        assert w.shape == (k.value, k.value, cin.value, cout.value)
+        a[wo.value:wo.value + w.size] = w.ravel()
+        a[bo.value:bo.value + b.size] = b
+    return a
+
+
+def test_c_abi_forward_matches_oracle(lib):
+    """Nothing but the C ABI: arena in, sr_model_create, workspace query, sr_model_forward -- against the fp32 oracle
+    graph (tolerance of the bf16 engine)."""
+    from oracle import model as om
+    from sr100 import _lib as L
+    weights = om.init_weights(1234, bias_scale=0.01)
+    w, b = weights["conv2d_85"]
+    weights["conv2d_85"] = (w * 8.0, b + 0.3)
+    params = torch.from_numpy(_arena(lib, weights)).cuda()
+    model = C.c_void_p()
+    L.check(lib.sr_model_create(L.ptr(params), None, C.byref(model)))
+    try:
+        rng = np.random.default_rng(3)
+        for shape in ((2, 24, 24), (1, 40, 28), (3, 16, 20)):
+            x = _smooth(rng, *shape)
+            xd = torch.from_numpy(x).cuda()
+            out = torch.full((shape[0], 4 * shape[1], 4 * shape[2], 3), float("nan"), device="cuda")
+            d = L.ForwardDesc()
+            d.NB, d.H, d.W = shape
+            d.x, d.out = xd.data_ptr(), out.data_ptr()
+            need = lib.sr_model_forward_workspace_bytes(model, C.byref(d))
+            assert need > 0
+            ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+            d.workspace, d.workspace_bytes = ws.data_ptr(), need - 1
+            assert lib.sr_model_forward(model, C.byref(d), L.stream_ptr()) == -1        # workspace too small
+            assert b"workspace" in lib.sr_last_error_string()
+            d.workspace_bytes = need
+            want = om.forward_numpy(weights, x)
+            for it in range(3):               # eager, capture + replay, replay
+                out.fill_(float("nan"))
+                L.check(lib.sr_model_forward(model, C.byref(d), L.stream_ptr()))
+                torch.cuda.synchronize()
+                got = out.cpu().numpy()
+                # north_star bf16 tolerance 2e-2 on [0,1] outputs; the fp32-stream design reaches ~2e-3 on these
+                # O(0.4) outputs (the tail is lifted x8 off zero; 2e-3 is asserted on the plain init in test_gpu_model)
+                assert np.abs(got - want).max() <= 4e-3, (shape, it, np.abs(got - want).max())
+            info = L.ModelRunInfo()
+            L.check(lib.sr_model_forward_info(model, C.byref(d), C.byref(info)))
+            assert info.graph_replay == 1 and info.conv_launches == 85 and info.launches >= 87
+            # algorithmic FLOPs of the 85 tensor-core convs (the 1x1 head runs on CUDA cores)
+            lr_px = shape[0] * shape[1] * shape[2]
+            want_flops = lr_px * (16 * 68 + 6 * 18) * 128 * 128 * 2 + 16 * lr_px * (2 * 68 * 128 * 128 * 2 + 9 * 128 * 3 * 2)
+            assert abs(info.conv_flops - want_flops) <= 1e-9 * want_flops
+    finally:
+        lib.sr_model_destroy(model)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_c_sequencer_equals_python_sequencer(precision):
+    """sr_model_forward issues exactly the launches the Python stages issue: outputs are bit-identical, whole patches
+    and with the tiled path's per-class HR extents (dead-region elimination)."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    weights = om.init_weights(77, bias_scale=0.01)
+    w, b = weights["conv2d_85"]
+    weights["conv2d_85"] = (w * 8.0, b + 0.3)
+    ec = Engine(weights, precision=precision, sequencer="c")
+    ep = Engine(weights, precision=precision, sequencer="python")
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(_smooth(rng, 5, 32, 32)).cuda()
+    a, b_ = ec.forward_device(x), ep.forward_device(x)
+    assert torch.equal(a, b_)
+    ext = [(80, 80), (128, 80), (80, 80), (128, 128), (64, 128)]
+    oc = torch.zeros(5, 128, 128, 3, device="cuda")
+    op = torch.zeros(5, 128, 128, 3, device="cuda")
+    for _ in range(3):
+        ec.forward_device(x, out=oc, extents=ext)
+        ep.forward_device(x, out=op, extents=ext)
+    for n, (eh, ew) in enumerate(ext):     # the tail is right on [0, e-7) of a cropped extent, the whole patch otherwise
+        ch, cw = (eh - 7 if eh < 128 else eh), (ew - 7 if ew < 128 else ew)
+        assert torch.equal(oc[n, :ch, :cw], op[n, :ch, :cw]), n
+    assert ec.last_flops() == ep.last_flops()
+    assert ec.graph_ready()
+    # sub-batching goes through the same entry point
+    es = Engine(weights, precision=precision, sequencer="c", max_pixels=2 * 32 * 32)
+    assert torch.equal(es.forward_device(x), a)
+
+
+def test_c_sequencer_tiled_path_equals_python():
+    """upscale_images_device (gather -> stack -> stitch) through both sequencers: identical uint8 images."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    weights = om.init_weights(1234, bias_scale=0.01)
+    w, b = weights["conv2d_85"]
+    weights["conv2d_85"] = (w * 8.0, b + 0.3)
+    rng = np.random.default_rng(11)
+    imgs = [torch.from_numpy(rng.integers(0, 256, size=s + (3,)).astype(np.uint8)).cuda()
+            for s in ((70, 45), (40, 100), (70, 45))]
+    ec, ep = Engine(weights, sequencer="c"), Engine(weights, sequencer="python")
+    for full in (False, True):
+        a = ec.upscale_images_device(imgs, patch=32, full_canvas=full)
+        b_ = ep.upscale_images_device(imgs, patch=32, full_canvas=full)
+        for u, v in zip(a, b_):
+            assert torch.equal(u, v)
+    recs = ec.timed_launches()
+    assert len(recs) >= 87 and sum(1 for ms, fl in recs if fl > 0) >= 85 and all(ms > 0 for ms, _ in recs)
+
+
+def test_c_train_step_equals_python_launch_lists():
+    """sr_model_forward_backward + sr_model_apply_gradients against the Python launch lists of sr100.train: kernel
+    gradients (fixed summation order) bit for bit, bias / head gradients and the loss (atomics) to rounding, and the
+    parameters after two Adam steps."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    from sr100.train import Trainer
+    weights = om.init_weights(21, bias_scale=0.01)
+    rng = np.random.default_rng(9)
+    x = rng.random((3, 12, 16, 3)).astype(np.float32)
+    y = rng.random((3, 48, 64, 3)).astype(np.float32)
+    tc, tp = Trainer(Engine(weights, sequencer="c")), Trainer(Engine(weights, sequencer="python"))
+    gc, gp = tc.graph(3, 12, 16), tp.graph(3, 12, 16)
+    for step in range(2):
+        for tr, g in ((tc, gc), (tp, gp)):
+            tr._load(g, x, y)
+            tr.forward_backward_device(g)
+        torch.cuda.synchronize()
+        assert abs(gc.loss_sum.item() - gp.loss_sum.item()) <= 1e-9 * abs(gp.loss_sum.item())
+        assert torch.equal(gc.out, gp.out)
+        for name, k, cin, cout in tc.engine.specs:
+            ow, nw, ob, nb = tc.engine.param_slices[name]
+            if cin == 128:
+                assert torch.equal(tc.grads[ow:ow + nw], tp.grads[ow:ow + nw]), (step, name)
+            else:
+                assert torch.allclose(tc.grads[ow:ow + nw], tp.grads[ow:ow + nw], rtol=1e-4, atol=1e-8), (step, name)
+            assert torch.allclose(tc.grads[ob:ob + nb], tp.grads[ob:ob + nb], rtol=1e-4, atol=1e-8), (step, name, "bias")
+        # identical gradients in, so that the optimizer comparison is exact
+        tp.grads.copy_(tc.grads)
+        tc.apply_gradients()
+        tp.apply_gradients()
+        torch.cuda.synchronize()
+        assert torch.equal(tc.engine.param_arena, tp.engine.param_arena)
+    assert tc.graph_ready(gc)
+    assert tc.step_flops(gc) == pytest.approx(tp.step_flops(gp), rel=1e-12)
+    # the refreshed packed weights of the C model drive the next forward exactly like the Python-side copies
+    xd = torch.from_numpy(x).cuda()
+    assert torch.equal(tc.engine.forward_device(xd), tp.engine.forward_device(xd))
+
+
+def test_c_abi_train_step_raw(lib):
+    """sr_model_train_step with raw pointers: the loss falls over a few steps on a fixed batch and the parameters move
+    by ~lr per step (first Adam steps), tf32 models refuse to train."""
+    from oracle import model as om
+    from sr100 import _lib as L
+    weights = om.init_weights(4, bias_scale=0.01)
+    params = torch.from_numpy(_arena(lib, weights)).cuda()
+    p0 = params.clone()
+    model = C.c_void_p()
+    L.check(lib.sr_model_create(L.ptr(params), None, C.byref(model)))
+    try:
+        NB, H, W = 2, 10, 12
+        rng = np.random.default_rng(1)
+        x = torch.from_numpy(_smooth(rng, NB, H, W)).cuda()
+        y = torch.from_numpy(_smooth(rng, NB, 4 * H, 4 * W)).cuda()
+        n = lib.sr_model_param_count()
+        grads, m, v = (torch.zeros(n, device="cuda") for _ in range(3))
+        loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        need = lib.sr_model_train_workspace_bytes(model, NB, H, W)
+        ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        d = L.TrainDesc()
+        d.NB, d.H, d.W = NB, H, W
+        d.x, d.y, d.grads, d.loss_sum = x.data_ptr(), y.data_ptr(), grads.data_ptr(), loss.data_ptr()
+        d.workspace, d.workspace_bytes = ws.data_ptr(), need
+        losses = []
+        for t in range(1, 7):
+            L.check(lib.sr_model_train_step(model, C.byref(d), L.ptr(m), L.ptr(v), t, 1e-3, 0.9, 0.999, 1e-7,
+                                            L.stream_ptr()))
+            torch.cuda.synchronize()
+            losses.append(loss.item() / (NB * 16 * H * W * 3))
+        assert losses[-1] < losses[0], losses
+        moved = (params - p0).abs()
+        assert 1e-4 < float(moved.max()) <= 6.1e-3
+    finally:
+        lib.sr_model_destroy(model)
+    cfg = L.ModelConfig()
+    lib.sr_model_default_config(C.byref(cfg))
+    cfg.precision = 1
+    model = C.c_void_p()
+    L.check(lib.sr_model_create(L.ptr(params), C.byref(cfg), C.byref(model)))
+    try:
+        assert lib.sr_model_forward_backward(model, C.byref(d), L.stream_ptr()) == -2
+    finally:
+        lib.sr_model_destroy(model)

@@ -472,7 +472,7 @@ def test_training_graph_replay_matches_eager():
         tr.forward_backward_device(g)
         torch.cuda.synchronize()
         outs.append((tr.grads.clone(), float(g.loss_sum.item())))
-    assert g.cuda_graph is not None
+    assert tr.graph_ready(g)
     ow, nw, _, _ = tr.engine.param_slices["conv2d_40"]
     for gr, ls in outs[1:]:
         assert torch.equal(gr[ow:ow + nw], outs[0][0][ow:ow + nw])

@@ -300,8 +300,10 @@ def main():
     if eng.tf32:     # SR100_PRECISION=tf32: kind::tf32 MMAs run at half the bf16 rate; no measured tf32 peak exists
         rpeaks = {"sustained": peaks["sustained"] / 2, "burst": peaks["burst"] / 2,
                   "src": peaks["src"] + " (halved: tf32 = 0.5x bf16 tensor rate)"}
-    # libsr100 kernels per step on this rank: the stage launches + one batched gather + one stitch per image
-    launches_per_step = len(evs) + 1 + len(dev_imgs)
+    # libsr100 kernels per step on this rank: the stage launches + one batched gather (+ one stitch per image when the
+    # stitch is not fused into the tail convs' epilogues)
+    fused_stitch = eng.sequencer == "c" and os.environ.get("SR100_FUSED_STITCH", "1") != "0"
+    launches_per_step = len(evs) + 1 + (0 if fused_stitch else len(dev_imgs))
     traffic, traffic_src = None, None
     prof_dir = os.path.join(ROOT, "profiles")
     for cand in sorted(os.listdir(prof_dir), reverse=True) if os.path.isdir(prof_dir) and not eng.tf32 else []:
@@ -465,7 +467,11 @@ def main():
                                             "that the stitch can see (receptive-field radius 7); output pixels "
                                             "bit-identical to the full tiling (tests/test_gpu_deadwork.py, "
                                             "tests/test_tile_plan.py), which is timed as value_full_tiles",
-                   "residual_stream": "fp32 at LR and HR (tf32 operands)" if eng.tf32 else "fp32 at LR, bf16 at HR"},
+                   "residual_stream": "fp32 at LR and HR (tf32 operands)" if eng.tf32 else "fp32 at LR, bf16 at HR",
+                   "sequencer": "sr_model_forward (libsr100 owns launch order, plans, CUDA graphs)" if eng.sequencer == "c"
+                                else "python launch lists",
+                   "stitch": "x255 / clip / uint8 / 8-px-crop stitch fused into the tail convs' epilogues" if fused_stitch
+                             else "separate sr_patch_stitch pass per image"},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "models.DifvdsrDouble.upscale_arrays (pinned host uint8 in / out, per rank)"},
         "value_full_tiles": None if value_full is None else round(value_full, 3),

@@ -77,6 +77,7 @@ extern "C" size_t sr_abi_struct_size(int which) {
     case 7: return sizeof(sr_forward_desc);
     case 8: return sizeof(sr_train_desc);
     case 9: return sizeof(sr_model_run_info);
+    case 10: return sizeof(sr_stitch_tile);
     default: return 0;
   }
 }

@@ -785,12 +785,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld16(t_base + acc * N_, v);
           tmem_ld_wait();
           if (valid) {
+            // fused stitch: does this patch own the pixel, and does it fall inside the (cropped) image?
+            unsigned char* u8 = nullptr;
+            if (P.stitch_u8) {
+              const sr_stitch_tile tl = P.stitch_tiles[P.out_index ? P.out_index[c.n] : c.n];
+              const int px = c.seg_x0 + xx;
+              const int Y = tl.y0 + yy, X = tl.x0 + px;
+              if (yy >= tl.oy0 && yy < tl.oy1 && px >= tl.ox0 && px < tl.ox1 && Y >= 0 && Y < tl.img_h && X >= 0 &&
+                  X < tl.img_w)
+                u8 = P.stitch_u8 + tl.img_offset + ((size_t)Y * tl.img_w + X) * 3;
+            }
             for (int j = 0; j < P.cout; ++j) {
               float o = P.alpha * (__uint_as_float(v[j]) + s_bias[j]);
               if (P.res_f32) o = fmaf(P.beta, P.res_f32[pix * P.cout + j], o);
               if (P.relu) o = fmaxf(o, 0.f);
               if (P.out_f32) P.out_f32[opix * P.cout + j] = o;
               if (P.out_bf16) P.out_bf16[opix * P.cout + j] = __float2bfloat16_rn(o);
+              // np.clip(x * 255, 0, 255).astype('uint8') (models.py:351, 391): the arithmetic of patch_stitch_kernel
+              if (u8 && j < 3) u8[j] = (unsigned char)(int)fminf(fmaxf(__fmul_rn(o, P.stitch_mul), 0.f), 255.f);
             }
           }
         }
@@ -1397,14 +1409,21 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.cout = d->cout;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
   P.out_index = d->out_index;
+  P.stitch_tiles = d->stitch_u8 ? d->stitch_tiles : nullptr;
+  P.stitch_u8 = d->stitch_u8;
+  P.stitch_mul = d->stitch_mul;
   P.shuffle_r = d->shuffle_r > 0 ? d->shuffle_r : 0;
   P.shuffle_order = d->shuffle_order;
   P.shuffle_C = d->shuffle_r > 0 ? d->cout / (d->shuffle_r * d->shuffle_r) : 0;
   P.out_H = d->out_h;
   P.out_W = d->out_w;
-  if (d->out_index && (pl->n_pad == 128 || d->out_h < d->H || d->out_w < d->W)) {
+  if (d->out_index && (pl->n_pad == 128 || (d->out_f32 && (d->out_h < d->H || d->out_w < d->W)))) {
     delete pl;
     return set_error(SR_ERR_UNSUPPORTED, "out_index scatter needs cout <= 16 and out_h/out_w >= H/W");
+  }
+  if (d->stitch_u8 && (pl->n_pad == 128 || d->cout != 3 || !d->stitch_tiles)) {
+    delete pl;
+    return set_error(SR_ERR_UNSUPPORTED, "fused stitch needs cout == 3 and a stitch_tiles table");
   }
   double macs = 0;
   for (int s = 0; s < d->nsrc; ++s) {

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "../../include/sr100.h"
+
 namespace sr {
 
 constexpr int kConvThreads = 256;  // warp0: weight TMA, warp1: MMA, warp2: TMEM alloc, warp3: A TMA, warps4-7: epilogue
@@ -70,6 +72,10 @@ struct ConvKernelParams {
   // cout <= 16 path only: image n is written to slot out_index[n] of a tensor of out_H x out_W pixel images
   const int* out_index;
   int out_H, out_W;
+  // cout <= 16 path only: fused quantise + stitch (sr_conv_desc.stitch_*); tiles indexed like out_index slots
+  const sr_stitch_tile* stitch_tiles;
+  unsigned char* stitch_u8;
+  float stitch_mul;
   // sub-pixel layers: r > 0 stores channel ch of pixel (y,x) at the depth-to-space position (order as sr_depth_to_space)
   int shuffle_r, shuffle_order, shuffle_C;
   // development switches of the pair kernel (SR100_CONV_DBG, compiled in only with -DSR_DEV_SWITCHES; results are WRONG with either set -- timing only):

@@ -313,6 +313,9 @@ struct ConvArgs {
   int comp_h = 0, comp_w = 0;
   float* colsum = nullptr;
   float colsum_scale = 0.f;
+  const sr_stitch_tile* stitch_tiles = nullptr;
+  uint8_t* stitch_u8 = nullptr;
+  float stitch_mul = 0.f;
 };
 
 int add_conv(sr_model* m, Sequence* seq, const ConvArgs& a, sr_conv_plan_info_t* info_out = nullptr) {
@@ -344,6 +347,7 @@ int add_conv(sr_model* m, Sequence* seq, const ConvArgs& a, sr_conv_plan_info_t*
   d.out_index = a.out_index, d.out_h = a.out_h, d.out_w = a.out_w;
   d.comp_h = a.comp_h, d.comp_w = a.comp_w;
   d.colsum_f32 = a.colsum, d.colsum_scale = a.colsum_scale;
+  d.stitch_tiles = a.stitch_tiles, d.stitch_u8 = a.stitch_u8, d.stitch_mul = a.stitch_mul;
   Step st;
   SR_TRY(sr_conv_plan_create(&d, &st.cp));
   sr_conv_plan_info_t info;
@@ -633,6 +637,7 @@ int build_forward(sr_model* m, const sr_forward_desc* d, const FwdGeom& g, Seque
     t.NB = n, t.H = eh, t.W = ew;
     t.layer[0] = li, t.in[0] = l.s_hr, t.out_f32 = d->out, t.relu = 1, t.cout = 3;
     t.out_index = idx, t.out_h = 4 * H, t.out_w = 4 * W;
+    t.stitch_tiles = d->stitch_tiles, t.stitch_u8 = d->stitch_u8, t.stitch_mul = d->stitch_mul;
     const Ext c7 = cut(7);
     t.comp_h = c7.h, t.comp_w = c7.w;
     SR_TRY(add_conv(m, seq, t));
@@ -643,13 +648,16 @@ int build_forward(sr_model* m, const sr_forward_desc* d, const FwdGeom& g, Seque
 int get_forward(sr_model* m, const sr_forward_desc* d, Sequence** out) {
   FwdGeom g;
   SR_TRY(forward_geometry(d, &g));
-  if (!d->x || !d->out || !d->workspace) return set_error(SR_ERR_INVALID, "sr_model_forward: null tensor / workspace");
+  if (!d->x || !d->workspace || (!d->out && !d->stitch_u8))
+    return set_error(SR_ERR_INVALID, "sr_model_forward: null tensor / workspace");
+  if (d->stitch_u8 && !d->stitch_tiles) return set_error(SR_ERR_INVALID, "sr_model_forward: stitch_u8 needs stitch_tiles");
   const FwdLayout l = forward_layout(m, d, g, nullptr);
   if (d->workspace_bytes < l.bytes)
     return set_error(SR_ERR_INVALID, "sr_model_forward: workspace too small (see sr_model_forward_workspace_bytes)");
   std::string key;
   key_add(&key, d->NB), key_add(&key, d->H), key_add(&key, d->W);
   key_add(&key, d->x), key_add(&key, d->out), key_add(&key, d->workspace);
+  key_add(&key, d->stitch_tiles), key_add(&key, d->stitch_u8), key_add(&key, d->stitch_mul);
   key_add(&key, g.n_groups);
   for (int v : g.eh) key_add(&key, v);
   for (int v : g.ew) key_add(&key, v);

@@ -46,7 +46,15 @@ class ConvDesc(C.Structure):
         ("out_tf32", C.c_void_p),
         ("colsum_f32", C.c_void_p),
         ("colsum_scale", C.c_float),
+        ("stitch_tiles", C.c_void_p),
+        ("stitch_u8", C.c_void_p),
+        ("stitch_mul", C.c_float),
     ]
+
+
+class StitchTile(C.Structure):
+    _fields_ = [("img_offset", C.c_longlong), ("img_h", C.c_int), ("img_w", C.c_int), ("y0", C.c_int), ("x0", C.c_int),
+                ("oy0", C.c_int), ("oy1", C.c_int), ("ox0", C.c_int), ("ox1", C.c_int)]
 
 
 class ConvPlanInfo(C.Structure):
@@ -108,6 +116,7 @@ class ForwardDesc(C.Structure):
         ("n_groups", C.c_int),
         ("group_eh", C.POINTER(C.c_int)), ("group_ew", C.POINTER(C.c_int)), ("group_n", C.POINTER(C.c_int)),
         ("group_index", C.POINTER(C.c_int)),
+        ("stitch_tiles", C.c_void_p), ("stitch_u8", C.c_void_p), ("stitch_mul", C.c_float),
     ]
 
 
@@ -219,7 +228,7 @@ def load():
         fn.restype = res
         fn.argtypes = args
     for which, struct in enumerate((ConvDesc, ConvPlanInfo, PackItem, WgradDesc, WgradPlanInfo, ScoreResult, ModelConfig,
-                                    ForwardDesc, TrainDesc, ModelRunInfo)):
+                                    ForwardDesc, TrainDesc, ModelRunInfo, StitchTile)):
         if lib.sr_abi_struct_size(which) != C.sizeof(struct):
             raise SrError(-1, "%s: ctypes layout (%d bytes) does not match libsr100.so (%d bytes); rebuild the "
                               "library or update sr100/_lib.py" % (struct.__name__, C.sizeof(struct),

@@ -435,7 +435,8 @@ class Engine:
         # second stream for independent launches of small inputs (_Stage._launch_all); SR100_NO_OVERLAP=1 disables it
         self.side_stream = None if os.environ.get("SR100_NO_OVERLAP", "0") == "1" else torch.cuda.Stream(self.device)
         self.model = C.c_void_p()            # sr_model*: owns packed weights, plans and graphs of the C sequencer
-        self._ws = self._x_buf = self._out_buf = None
+        self._ws = self._x_buf = self._out_buf = self._u8_buf = None
+        self._stitch_cache = {}
         self.last_calls, self.last_stages = [], []
         self.set_weights_dict(weights if weights is not None else glorot_uniform_weights())
 
@@ -466,7 +467,7 @@ class Engine:
         for st in self._graphs.values():
             st.hr.clear()
         self._graphs.clear()
-        self._ws = self._x_buf = self._out_buf = None
+        self._ws = self._x_buf = self._out_buf = self._u8_buf = None
         torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- weights
@@ -635,38 +636,92 @@ class Engine:
             keep = [eh, ew, cnt, idx]
         return d, keep, groups
 
-    def _bind_buffers(self, d):
+    def _bind_buffers(self, d, need_out=True):
         """Point the descriptor at the shared grow-only buffers (workspace, input, output): stable pointers keep the
         library's plan / graph cache hot; a forward runs start to end on one stream, so sharing is safe."""
         need = self.lib.sr_model_forward_workspace_bytes(self._ensure_model(), C.byref(d))
         if need == 0:
             L.check(-1)
         nx = d.NB * d.H * d.W * 3
-        try:
+
+        def grow():
             if self._ws is None or self._ws.numel() < need:
                 self._ws = None
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             if self._x_buf is None or self._x_buf.numel() < nx:
-                self._x_buf = self._out_buf = None
+                self._x_buf = None
                 self._x_buf = torch.empty(nx, dtype=torch.float32, device=self.device)
+            if need_out and (self._out_buf is None or self._out_buf.numel() < 16 * nx):
+                self._out_buf = None
                 self._out_buf = torch.empty(16 * nx, dtype=torch.float32, device=self.device)
+
+        try:
+            grow()
         except torch.cuda.OutOfMemoryError:
             self.release()
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._x_buf = torch.empty(nx, dtype=torch.float32, device=self.device)
-            self._out_buf = torch.empty(16 * nx, dtype=torch.float32, device=self.device)
-        d.x, d.out = self._x_buf.data_ptr(), self._out_buf.data_ptr()
+            grow()
+        d.x = self._x_buf.data_ptr()
+        d.out = self._out_buf.data_ptr() if need_out else None
         d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
 
-    def _forward_c(self, x, out, extents):
+    def _forward_c(self, x, out, extents, stitch=None):
+        """One sub-batch through sr_model_forward.  stitch = (device pointer of this sub-batch's sr_stitch_tile rows,
+        device pointer of the uint8 image buffer, mul): the tail convs write the owned uint8 pixels themselves and
+        no fp32 patch tensor is produced (out is None)."""
         n, H, W, _ = x.shape
         d, keep, groups = self._forward_desc(n, H, W, extents)
-        self._bind_buffers(d)
+        if stitch is not None:
+            d.stitch_tiles, d.stitch_u8, d.stitch_mul = stitch
+        self._bind_buffers(d, need_out=stitch is None)
         nx = n * H * W * 3
         self._x_buf[:nx].view(n, H, W, 3).copy_(x)
         L.check(self.lib.sr_model_forward(self.model, C.byref(d), L.stream_ptr()))
-        out.copy_(self._out_buf[:16 * nx].view(n, 4 * H, 4 * W, 3))
+        if stitch is None:
+            out.copy_(self._out_buf[:16 * nx].view(n, 4 * H, 4 * W, 3))
         self.last_calls.append((d, keep, groups))
+
+    def forward_stitched(self, x, extents, tiles_dev, u8_buf, mul=255.0):
+        """The conv stack over all patches x [N,H,W,3] with the quantise + stitch fused into the tail convs
+        (sr_forward_desc.stitch_*): patch n writes the pixels stitch tile n owns into u8_buf."""
+        N, H, W, _ = x.shape
+        nb = min(N, self.sub_batch(H, W))
+        self.last_stages, self.last_calls = [], []
+        tsz = C.sizeof(L.StitchTile)
+        for i in range(0, N, nb):
+            n = min(nb, N - i)
+            self._forward_c(x[i:i + n], None, None if extents is None else extents[i:i + n],
+                            stitch=(tiles_dev.data_ptr() + i * tsz, u8_buf.data_ptr(), float(mul)))
+
+    @staticmethod
+    def stitch_tiles_host(metas, patch, step, scale, crop=8):
+        """sr_stitch_tile rows (numpy structured array) of all patches of a list of images, in gather order, and the
+        byte size of the uint8 buffer that holds the images.  metas: [(out_h, out_w, (cnt_h, cnt_w), x_shift)] per
+        image (x_shift: image column of canvas column 0, negative for a column strip of a sharded image).
+        Ownership (img_utils.py:700-722, later patches overwrite earlier ones): patch i of an axis writes
+        [c_i, P - c_i) of its P pixels (c_0 = 0, else 8) and loses everything from S + 8 on to patch i + 1."""
+        P, S = patch * scale, step * scale
+        dt = np.dtype([("img_offset", "<i8"), ("img_h", "<i4"), ("img_w", "<i4"), ("y0", "<i4"), ("x0", "<i4"),
+                       ("oy0", "<i4"), ("oy1", "<i4"), ("ox0", "<i4"), ("ox1", "<i4")])
+        assert dt.itemsize == C.sizeof(L.StitchTile)
+
+        def own(i, cnt):
+            lo = np.where(i == 0, 0, crop)
+            end = np.where(i == 0, P, P - crop)
+            return lo, np.where(i < cnt - 1, np.minimum(end, S + crop), end)
+
+        rows, off, offsets = [], 0, []
+        for oh, ow, (cnt_h, cnt_w), x_shift in metas:
+            n = np.arange(cnt_h * cnt_w)
+            wi, hi = n // cnt_h, n % cnt_h
+            t = np.zeros(n.size, dtype=dt)
+            t["img_offset"], t["img_h"], t["img_w"] = off, oh, ow
+            t["y0"], t["x0"] = S * hi, S * wi + x_shift
+            t["oy0"], t["oy1"] = own(hi, cnt_h)
+            t["ox0"], t["ox1"] = own(wi, cnt_w)
+            rows.append(t)
+            offsets.append(off)
+            off += (oh * ow * 3 + 255) // 256 * 256
+        return np.concatenate(rows), offsets, off
 
     def timed_launches(self):
         """[(ms, flops)] of every launch of the most recent forward_device call, re-run launch by launch between
@@ -752,6 +807,27 @@ class Engine:
             assert got == metas[i][4]
             off += (j - i) * n
             i = j
+        if self.sequencer == "c" and os.environ.get("SR100_FUSED_STITCH", "1") != "0":
+            # x255, clip -> uint8 and the 8-px-crop stitch happen in the tail convs' epilogues: every patch writes
+            # the pixels it owns straight into its image (no fp32 patch tensor, no stitch pass)
+            key = (tuple((m[0], m[1]) for m in metas), patch, step, scale, bool(full_canvas))
+            cached = self._stitch_cache.get(key)
+            if cached is None:
+                sm = [((scale * ch, scale * cw) if full_canvas else (scale * h, scale * w)) + (counts, 0)
+                      for h, w, ch, cw, counts, n, _ in metas]
+                rows, offsets, nbytes = self.stitch_tiles_host(sm, patch, step, scale)
+                if len(self._stitch_cache) >= 8:
+                    self._stitch_cache.pop(next(iter(self._stitch_cache)))
+                cached = (torch.from_numpy(rows.view(np.uint8)).to(self.device), offsets, nbytes,
+                          [(m[0], m[1]) for m in sm])
+                self._stitch_cache[key] = cached
+            tiles_dev, offsets, nbytes, dims = cached
+            if self._u8_buf is None or self._u8_buf.numel() < nbytes:
+                self._u8_buf = None
+                self._u8_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._u8_buf[:nbytes].zero_()          # pixels no patch owns stay 0 (the reference's zero canvas)
+            self.forward_stitched(allp, None if full_canvas else extents, tiles_dev, self._u8_buf)
+            return [self._u8_buf[o:o + oh * ow * 3].view(oh, ow, 3).clone() for o, (oh, ow) in zip(offsets, dims)]
         out = self.forward_device(allp, extents=None if full_canvas else extents)
         res, off = [], 0
         for h, w, ch, cw, counts, n, _ in metas:
@@ -804,15 +880,42 @@ class Engine:
         (gh, gw), counts, ext, shards = self.shard_plan(h, w, world, patch, step, scale)
         p, got = ops.patch_gather_u8(img_u8, (gh, gw), (patch, patch), step, divisor=255.0)
         assert got == counts
+        fused = self.sequencer == "c" and os.environ.get("SR100_FUSED_STITCH", "1") != "0"
+
+        def run_fused(lo, hi, x0, width):
+            """Tiles [lo, hi) with the stitch fused into the tail convs: their owned pixels land in a zeroed uint8
+            strip of output columns [x0, x0 + width)."""
+            key = ("shard", h, w, patch, step, scale, lo, hi, x0, width)
+            cached = self._stitch_cache.get(key)
+            if cached is None:
+                rows, _, _ = self.stitch_tiles_host([(scale * h, width, counts, -x0)], patch, step, scale)
+                if len(self._stitch_cache) >= 8:
+                    self._stitch_cache.pop(next(iter(self._stitch_cache)))
+                cached = torch.from_numpy(np.ascontiguousarray(rows[lo:hi]).view(np.uint8)).to(self.device)
+                self._stitch_cache[key] = cached
+            nbytes = scale * h * width * 3
+            if self._u8_buf is None or self._u8_buf.numel() < nbytes:
+                self._u8_buf = None
+                self._u8_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._u8_buf[:nbytes].zero_()
+            if hi > lo:
+                self.forward_stitched(p[lo:hi], ext[lo:hi], cached, self._u8_buf)
+            return self._u8_buf[:nbytes].view(scale * h, width, 3)
+
         if world == 1:
+            if fused:
+                return run_fused(0, counts[0] * counts[1], 0, scale * w).clone()
             out = self.forward_device(p, extents=ext)
             _, u8 = ops.patch_stitch(out, counts, (patch, patch), step, scale, (h, w), mul=255.0, want_f32=False,
                                      want_u8=True)
             return u8
         lo, hi, x0, x1 = shards[rank]
         wmax = max(s[3] - s[2] for s in shards)
-        out = self.forward_device(p[lo:hi], extents=ext[lo:hi]) if hi > lo else p[:0]
-        send = self.stitch_shard(out, counts, h, lo, hi, x0, wmax, patch, step, scale)
+        if fused:
+            send = run_fused(lo, hi, x0, wmax)
+        else:
+            out = self.forward_device(p[lo:hi], extents=ext[lo:hi]) if hi > lo else p[:0]
+            send = self.stitch_shard(out, counts, h, lo, hi, x0, wmax, patch, step, scale)
         if group_gather is not None:
             recv = group_gather(send)                      # tests: the logical ranks' strips, in rank order
         else:

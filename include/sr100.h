@@ -40,7 +40,8 @@ int sr_dev_switches(void);
 int sr_dev_set_timeline(void* buf);
 /* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
  * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
- * 5 sr_score_result, 6 sr_model_config, 7 sr_forward_desc, 8 sr_train_desc, 9 sr_model_run_info; 0 for anything else. */
+ * 5 sr_score_result, 6 sr_model_config, 7 sr_forward_desc, 8 sr_train_desc, 9 sr_model_run_info,
+ * 10 sr_stitch_tile; 0 for anything else. */
 size_t sr_abi_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -50,6 +51,16 @@ size_t sr_abi_struct_size(int which);
  *     out = act( alpha * (sum_s conv(in[s], w[s]) + bias) + beta * res )
  * Activations are NHWC bf16 with 128 channels; accumulation is fp32 in TMEM.
  * ------------------------------------------------------------------------------------------ */
+/* One patch of a fused tail-conv stitch (sr_conv_desc.stitch_tiles): where the patch sits in its image and which of its
+ * pixels it OWNS under the last-writer-wins overwrite order of img_utils.rebuild_from_patches_Step
+ * (img_utils.py:700-722: ownership passes from tile i-1 to tile i at scale*step*i + 8). */
+typedef struct sr_stitch_tile {
+  long long img_offset;  /* byte offset of the patch's uint8 image [img_h, img_w, 3] inside stitch_u8 */
+  int img_h, img_w;      /* image size in pixels; writes outside are dropped (the crop to 4H x 4W, models.py:412) */
+  int y0, x0;            /* image coordinates of patch pixel (0, 0) (x0 may be negative for a column strip) */
+  int oy0, oy1, ox0, ox1;/* owned patch-local pixel range [oy0, oy1) x [ox0, ox1) */
+} sr_stitch_tile;
+
 typedef struct sr_conv_desc {
   int nsrc;              /* 1, or 2 = two convolutions accumulated into one output (5/3 block tail) */
   const void* in[2];     /* bf16 [NB,H,W,128] */
@@ -100,6 +111,14 @@ typedef struct sr_conv_desc {
    * exactly one of res_f32 / res_bf16 / relu_mask_bf16. */
   float* colsum_f32;
   float colsum_scale;
+  /* cout <= 16 only (the tail conv): quantise + stitch fused into the epilogue.  Patch n of the
+   * launch (slot out_index[n] when out_index is given) is described by stitch_tiles[slot] (DEVICE array); every
+   * output pixel the patch owns is written as uint8 = trunc(clip(value * stitch_mul, 0, 255)) (models.py:351, 391)
+   * straight into its image inside stitch_u8 -- the fp32 patch tensor (out_f32, may then be NULL) and the separate
+   * sr_patch_stitch pass disappear.  Bit-identical to conv -> sr_patch_stitch. */
+  const sr_stitch_tile* stitch_tiles;
+  uint8_t* stitch_u8;
+  float stitch_mul;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -437,6 +456,11 @@ typedef struct sr_forward_desc {
   const int* group_ew;
   const int* group_n;
   const int* group_index;
+  /* Optional fused stitch (sr_conv_desc.stitch_*): DEVICE array of NB tiles, patch n -> stitch_tiles[n]; the tail
+   * convs then write the owned uint8 pixels into stitch_u8 and `out` may be NULL. */
+  const sr_stitch_tile* stitch_tiles;
+  uint8_t* stitch_u8;
+  float stitch_mul;
 } sr_forward_desc;
 
 typedef struct sr_model_run_info {

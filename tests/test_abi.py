@@ -45,7 +45,7 @@ def test_version_and_error_string(lib):
 def test_struct_layouts_match_the_library(lib):
     from sr100 import _lib as L
     structs = (L.ConvDesc, L.ConvPlanInfo, L.PackItem, L.WgradDesc, L.WgradPlanInfo, L.ScoreResult, L.ModelConfig,
-               L.ForwardDesc, L.TrainDesc, L.ModelRunInfo)
+               L.ForwardDesc, L.TrainDesc, L.ModelRunInfo, L.StitchTile)
     for which, st in enumerate(structs):
         assert lib.sr_abi_struct_size(which) == C.sizeof(st), st.__name__
     assert lib.sr_abi_struct_size(99) == 0

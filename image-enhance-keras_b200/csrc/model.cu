@@ -176,6 +176,7 @@ struct sr_model {
   size_t total_elems = 0, total_elems_t = 0;
   // training-only state (allocated at first use)
   void* wgrad_ws = nullptr;
+  void* wgrad_ws2 = nullptr;                // second split-K scratch: two wgrad launches may run side by side
   size_t wgrad_ws_bytes = 0;
   float* tail_d128 = nullptr;
   float* tail_colw = nullptr;
@@ -260,6 +261,7 @@ int ensure_training_state(sr_model* m) {
                                          "precision tf32 is an inference mode");
   m->wgrad_ws_bytes = sr_wgrad_workspace_bytes();
   SR_TRY(dev_alloc(m, &m->wgrad_ws, m->wgrad_ws_bytes));
+  SR_TRY(dev_alloc(m, &m->wgrad_ws2, m->wgrad_ws_bytes));
   SR_TRY(dev_alloc(m, &m->tail_d128, (size_t)kC * kC * 4, true));
   SR_TRY(dev_alloc(m, &m->tail_colw, (size_t)kC * kC * 4, true));
   SR_TRY(dev_alloc(m, &m->tail_colw_packed, sr_packed_weight_bytes(1, kC)));
@@ -715,13 +717,13 @@ struct Block {
 };
 
 int add_wgrad(sr_model* m, Sequence* seq, const void* x, const void* g, int NB, int H, int W, int ksize, float scale,
-              float* dw) {
+              float* dw, bool second_ws = false) {
   sr_wgrad_desc d;
   memset(&d, 0, sizeof d);
   d.x_bf16 = x, d.g_bf16 = g;
   d.NB = NB, d.H = H, d.W = W;
   d.ksize = ksize, d.scale = scale, d.accumulate = 0;
-  d.dw_hwio = dw, d.workspace = m->wgrad_ws, d.workspace_bytes = m->wgrad_ws_bytes;
+  d.dw_hwio = dw, d.workspace = second_ws ? m->wgrad_ws2 : m->wgrad_ws, d.workspace_bytes = m->wgrad_ws_bytes;
   Step st;
   SR_TRY(sr_wgrad_plan_create(&d, &st.wp));
   sr_wgrad_plan_info_t info;
@@ -768,6 +770,7 @@ int build_train(sr_model* m, const sr_train_desc* d, Sequence* seq) {
   for (int b = 0; b < 2; ++b, li += 4)
     blocks.push_back(Block{true, li, l.SH[b], l.TH1[b], l.TH2[b], l.SH[b + 1], NB, HH, WW, false});
   const int tail = li;
+  const bool par = m->cfg.overlap_train != 0;   // independent launches pair up on two streams
   const Ext none{0, 0};
   auto fwd_block = [&](const Block& k) -> int {
     float* r32 = k.f32s ? l.s32 : nullptr;
@@ -781,6 +784,7 @@ int build_train(sr_model* m, const sr_train_desc* d, Sequence* seq) {
     if (k.is53) {
       a.layer[0] = k.li + 2, a.out_op = k.t2;
       SR_TRY(add_conv(m, seq, a));
+      if (par) seq->steps.back().par_with_prev = true;
       f.nsrc = 2, f.layer[0] = k.li + 1, f.in[0] = k.t1, f.layer[1] = k.li + 3, f.in[1] = k.t2, f.beta = 0.9f;
     } else {
       f.layer[0] = k.li + 1, f.in[0] = k.t1, f.beta = 1.0f;
@@ -856,8 +860,10 @@ int build_train(sr_model* m, const sr_train_desc* d, Sequence* seq) {
     if (k.is53) {
       SR_TRY(dgrad_masked(nb, a1, k.t1, na));
       SR_TRY(dgrad_masked(nd, a2, k.t2, nc));
+      if (par) seq->steps.back().par_with_prev = true;
       SR_TRY(add_wgrad(m, seq, k.t1, g, k.NB, k.H, k.W, L[nb].k, 0.1f, gw(nb)));
-      SR_TRY(add_wgrad(m, seq, k.t2, g, k.NB, k.H, k.W, L[nd].k, 0.1f, gw(nd)));
+      SR_TRY(add_wgrad(m, seq, k.t2, g, k.NB, k.H, k.W, L[nd].k, 0.1f, gw(nd), par));
+      if (par) seq->steps.back().par_with_prev = true;
       if (!g_summed) colsum(g, k, gbk.db, 0.1f);
       {
         float* twin = gbk.twin;
@@ -874,7 +880,8 @@ int build_train(sr_model* m, const sr_train_desc* d, Sequence* seq) {
       if (cs_next) f.colsum = gbn.db, f.colsum_scale = gbn.scale;
       SR_TRY(add_conv(m, seq, f));
       SR_TRY(add_wgrad(m, seq, k.x, a1, k.NB, k.H, k.W, L[na].k, 1.0f, gw(na)));
-      SR_TRY(add_wgrad(m, seq, k.x, a2, k.NB, k.H, k.W, L[nc].k, 1.0f, gw(nc)));
+      SR_TRY(add_wgrad(m, seq, k.x, a2, k.NB, k.H, k.W, L[nc].k, 1.0f, gw(nc), par));
+      if (par) seq->steps.back().par_with_prev = true;
       if (!fuse_cs) {
         colsum(a1, k, gb(na), 1.0f);
         colsum(a2, k, gb(nc), 1.0f);

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 
 #include "internal.h"
@@ -72,19 +74,32 @@ constexpr int kColStrip = 128;
 
 __global__ void __launch_bounds__(kBlock)
 mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int strips,
-                         float inv_total2, uint4* __restrict__ a128, double* __restrict__ loss_sum,
+                         size_t n_units, float inv_total2, uint4* __restrict__ a128, double* __restrict__ loss_sum,
                          float* __restrict__ db3) {
   constexpr int kRow = (kColStrip + 2) * 3;
   __shared__ float g[3 * kRow];
   __shared__ double red_loss[kBlock / 32];
   __shared__ float red_db[kBlock / 32][3];
-  const int strip = blockIdx.x % strips;
-  const int y = (blockIdx.x / strips) % H;
-  const size_t n = blockIdx.x / ((size_t)strips * H);
-  const int x0 = strip * kColStrip;
-  const int npx = min(kColStrip, W - x0);
   double loss = 0.0;
   float db[3] = {0.f, 0.f, 0.f};
+  // element offsets of this thread's 8 channels (fixed: kBlock is a multiple of 16)
+  const int q = threadIdx.x & 15;
+  int off[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int j = q * 8 + e;
+    const int tap = j / 3, co = j - tap * 3;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    off[e] = j < 27 ? ((2 - ky) * (kColStrip + 2) + (2 - kx)) * 3 + co : -1;
+  }
+  // persistent blocks over the (image, row, strip) units: the loss / bias-gradient sums stay in registers and reach
+  // the four global accumulators once per block (one block per unit meant ~150 k blocks x 4 same-address atomics)
+  for (size_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+  const int strip = (int)(unit % strips);
+  const int y = (int)((unit / strips) % H);
+  const size_t n = unit / ((size_t)strips * H);
+  const int x0 = strip * kColStrip;
+  const int npx = min(kColStrip, W - x0);
   for (int i = threadIdx.x; i < 3 * kRow; i += kBlock) {
     const int r = i / kRow, rem = i - r * kRow;
     const int xx = rem / 3, c = rem - xx * 3;
@@ -104,16 +119,6 @@ mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict
     }
     g[i] = v;
   }
-  // element offsets of this thread's 8 channels (fixed: kBlock is a multiple of 16)
-  const int q = threadIdx.x & 15;
-  int off[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int j = q * 8 + e;
-    const int tap = j / 3, co = j - tap * 3;
-    const int ky = tap / 3, kx = tap - ky * 3;
-    off[e] = j < 27 ? ((2 - ky) * (kColStrip + 2) + (2 - kx)) * 3 + co : -1;
-  }
   __syncthreads();
   const size_t base = (((size_t)n * H + y) * W + x0) * 16;
   for (int i = threadIdx.x; i < npx * 16; i += kBlock) {
@@ -129,6 +134,8 @@ mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict
                      *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
     }
     a128[base + i] = o;
+  }
+  __syncthreads();   // the next unit overwrites g
   }
   // block reductions: loss (fp64) and the three bias-gradient sums
   for (int o = 16; o > 0; o >>= 1) {
@@ -225,8 +232,8 @@ extern "C" int sr_mse_tail_grad_col(const float* pred, const float* target, int 
   const int strips = (W + kColStrip - 1) / kColStrip;
   const size_t blocks = (size_t)NB * H * strips;
   if (blocks > 0x7fffffffull) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: tensor too large");
-  mse_tail_grad_col_kernel<<<(unsigned)blocks, kBlock, 0, as_stream(stream)>>>(
-      pred, target, H, W, strips, inv2, reinterpret_cast<uint4*>(a128_bf16), loss_sum, db3);
+  mse_tail_grad_col_kernel<<<(unsigned)std::min<size_t>(blocks, 148 * 8), kBlock, 0, as_stream(stream)>>>(
+      pred, target, H, W, strips, blocks, inv2, reinterpret_cast<uint4*>(a128_bf16), loss_sum, db3);
   return check_launch("mse_tail_grad_col_kernel");
 }
 

@@ -105,7 +105,7 @@ class ScoreResult(C.Structure):
 class ModelConfig(C.Structure):
     _fields_ = [("precision", C.c_int), ("stream_lr_fp32", C.c_int), ("stream_hr_fp32", C.c_int),
                 ("a_mode", C.c_int), ("nacc", C.c_int), ("pair", C.c_int), ("use_graphs", C.c_int),
-                ("overlap_heads", C.c_int), ("fused_colsum", C.c_int)]
+                ("overlap_heads", C.c_int), ("fused_colsum", C.c_int), ("overlap_train", C.c_int)]
 
 
 class ForwardDesc(C.Structure):

@@ -450,6 +450,7 @@ class Engine:
             cfg.use_graphs = int(self.use_graphs)
             cfg.overlap_heads = int(self.side_stream is not None)
             cfg.fused_colsum = int(os.environ.get("SR100_FUSED_COLSUM", "1") != "0")
+            cfg.overlap_train = int(os.environ.get("SR100_OVERLAP_TRAIN", str(cfg.overlap_train)) != "0")
             with torch.cuda.device(self.device):
                 L.check(self.lib.sr_model_create(L.ptr(self.param_arena), C.byref(cfg), C.byref(self.model)))
         return self.model

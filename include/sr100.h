@@ -423,6 +423,9 @@ typedef struct sr_model_config {
                         * an internal second stream when both grids fit on the chip together (small inputs) */
   int fused_colsum;    /* 1 (default): bias gradients ride the input-gradient launches (sr_conv_desc.colsum_f32);
                         * 0: separate sr_colsum_bf16 passes (same values, another fp32 summation order) */
+  int overlap_train;   /* 1: independent launches of the training step (the two branch heads of a 5/3 block, their two
+                        * input-gradient launches, the wgrad pairs) are issued on two streams, so the tail wave of one
+                        * persistent kernel is back-filled by the first CTAs of the other; 0 (default): one stream */
 } sr_model_config;
 void sr_model_default_config(sr_model_config* cfg);
 

@@ -59,6 +59,28 @@ def main(src, dst):
             conv_n += d["launches"]
     out["conv_traffic_bytes_per_launch"] = round(conv_bytes / max(conv_n, 1))
     out["conv_launches"] = conv_n
+    # a whole step of the batched headline workload = everything between two patch-gather launches (one gather per
+    # step); when the capture holds one, the per-kernel shares and the conv traffic are taken over the whole step
+    gathers = [i for i, l in enumerate(seq) if "patch_gather" in l["name"]]
+    if len(gathers) >= 2:
+        step = seq[gathers[-2]:gathers[-1]]
+        tot_s = sum(l["gpu__time_duration.sum"] for l in step)
+        per_s, cb, cn = {}, 0.0, 0
+        for l in step:
+            short = l["name"].split("(")[0].replace("void ", "").replace("sr::", "")
+            d = per_s.setdefault(short, dict(launches=0, ms=0.0, dram=0.0))
+            d["launches"] += 1
+            d["ms"] += l["gpu__time_duration.sum"]
+            d["dram"] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
+            if "conv_tc_pair_kernel" in short:
+                cb += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
+                cn += 1
+        out["step"] = {"launches": len(step), "ms_under_ncu": round(tot_s, 3),
+                       "kernels": {k: dict(launches=d["launches"], ms=round(d["ms"], 3), share=round(d["ms"] / tot_s, 4),
+                                           dram_bytes_per_launch=round(d["dram"] / d["launches"]))
+                                   for k, d in sorted(per_s.items(), key=lambda kv: -kv[1]["ms"])}}
+        out["conv_traffic_bytes_per_launch"] = round(cb / max(cn, 1))
+        out["conv_launches"] = cn
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))
 

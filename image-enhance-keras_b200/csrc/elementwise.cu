@@ -24,35 +24,56 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 
 // ------------------------------------------------------------------ head 1x1 conv (3 -> 128) + ReLU
 // Reference: models.py:1177 Convolution2D(128,(1,1),activation='relu',name='level1').
-// One warp per pixel and trip, four channels per lane: a warp instruction stores 512 contiguous bytes of the fp32
-// tensor (float4 per lane) and 256 of the bf16 tensor (uint2 per lane) -- full 32-byte sectors.  (Eight channels per
-// lane made every fp32 store instruction touch 32 half-filled sectors: 0.69 of the HBM copy peak.)
+// 16 threads per pixel, 8 channels each.  The grid stride is a multiple of 16, so a thread keeps the same 8 channels
+// for its whole life: their 24 weights + 8 biases sit in registers, and the loop is unrolled over four pixels whose
+// 12-byte inputs are requested together (one dependent load per 768 B written left the kernel latency-bound at
+// 0.69 of the copy bandwidth; a pure-write kernel can exceed it: torch.fill reaches 7.3 TB/s on the same box).
 __global__ void __launch_bounds__(256)
 head1x1_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, size_t npix,
-               uint2* __restrict__ out_bf16, float4* __restrict__ out_f32) {
-  const int c0 = (threadIdx.x & 31) * 4;
-  float wr[4], wg[4], wb[4], bs[4];
+               uint4* __restrict__ out_bf16, float4* __restrict__ out_f32) {
+  const int c0 = (threadIdx.x & 15) * 8;
+  float wr[8], wg[8], wb[8], bs[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     wr[j] = w[c0 + j], wg[j] = w[128 + c0 + j], wb[j] = w[256 + c0 + j];
     bs[j] = bias ? bias[c0 + j] : 0.f;
   }
-  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += warps) {
-    const float r = in[pix * 3 + 0], g = in[pix * 3 + 1], b = in[pix * 3 + 2];
-    float o[4];
+  const size_t total = npix * 16;  // 16 groups of 8 channels per pixel
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += U * stride) {
+    float r[U], g[U], b[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // accumulate in channel order like a 3-term dot product, then bias, then ReLU
-      float a = __fmul_rn(r, wr[j]);
-      a = __fmaf_rn(g, wg[j], a);
-      a = __fmaf_rn(b, wb[j], a);
-      a = __fadd_rn(a, bs[j]);
-      o[j] = fmaxf(a, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const size_t idx = idx0 + u * stride;
+      r[u] = g[u] = b[u] = 0.f;
+      if (idx < total) {
+        const size_t pix = idx >> 4;
+        r[u] = in[pix * 3 + 0], g[u] = in[pix * 3 + 1], b[u] = in[pix * 3 + 2];
+      }
     }
-    const size_t idx = pix * 32 + (threadIdx.x & 31);
-    if (out_bf16) out_bf16[idx] = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
-    if (out_f32) out_f32[idx] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t idx = idx0 + u * stride;
+      if (idx >= total) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // accumulate in channel order like a 3-term dot product, then bias, then ReLU
+        float a = __fmul_rn(r[u], wr[j]);
+        a = __fmaf_rn(g[u], wg[j], a);
+        a = __fmaf_rn(b[u], wb[j], a);
+        a = __fadd_rn(a, bs[j]);
+        o[j] = fmaxf(a, 0.f);
+      }
+      if (out_bf16)
+        out_bf16[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      if (out_f32) {
+        out_f32[idx * 2] = make_float4(o[0], o[1], o[2], o[3]);
+        out_f32[idx * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
   }
 }
 
@@ -232,16 +253,32 @@ __global__ void patch_gather_kernel(const void* __restrict__ src, int h, int w, 
 // built per block with the same correctly rounded fp32 division, so results are bit-identical to the scalar kernel.
 // (The flat-index kernel above -- and its 4-element variant this one replaced -- spends ~250 instructions per
 // 16 bytes on 64-bit div/mod and four fp32 divisions: instruction-bound at ~2 TB/s.)
+// b / 255 correctly rounded, for a byte b: one product with fl(1/255) and one Newton correction through two FMAs
+// (the fast path of a correctly rounded fp32 division); equal to __fdiv_rn((float)b, 255.f) for all 256 inputs
+// (tests/test_gpu_tiling.py checks every byte value against numpy's float32 division).
+__device__ __forceinline__ float div255(uint32_t b) {
+  const float x = (float)b, c = 0x1.010102p-8f;
+  const float q = x * c;
+  return __fmaf_rn(__fmaf_rn(-q, 255.f, x), c, q);
+}
+
+// MODE 0: value / divisor through a 256-entry shared-memory table (any divisor); 1: divisor == 255 in arithmetic
+// (no table: 32 random table reads per warp instruction serialise on bank conflicts and made the LSU the
+// co-bottleneck of a write-bound kernel); 2: divisor == 1.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 patch_gather_u8_rows_kernel(const uint8_t* __restrict__ imgs, int n_img, size_t img_stride, int h, int w,
                             int cnt_h, int cnt_w, int ph, int pw, int step, float divisor,
                             float4* __restrict__ out) {
   // One block per patch (grid-stride): the patch's coordinates are computed once, its ph * (3*pw/4) 16-byte
   // groups are then walked by all 256 threads with an incrementally updated (row, group) pair -- no division in
-  // the loop, every lane busy, two groups per thread per trip so eight byte loads are in flight before the stores.
-  __shared__ float lut[256];
-  lut[threadIdx.x] = divisor == 1.f ? (float)threadIdx.x : __fdiv_rn((float)threadIdx.x, divisor);
-  __syncthreads();
+  // the loop, every lane busy.  The four bytes of a group come from the one or two aligned 32-bit words that hold
+  // them (funnel shift), not from four byte loads.
+  __shared__ float lut[MODE == 0 ? 256 : 1];
+  if constexpr (MODE == 0) {
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, divisor);
+    __syncthreads();
+  }
   const int row_q = pw * 3 / 4, w3 = w * 3;
   const int patch_q = ph * row_q;
   const unsigned per_img = (unsigned)cnt_h * cnt_w, total = per_img * (unsigned)n_img;
@@ -252,29 +289,40 @@ patch_gather_u8_rows_kernel(const uint8_t* __restrict__ imgs, int n_img, size_t 
     const int y0 = (int)(hi * step), e_row = (int)(wi * step) * 3;
     const uint8_t* img = imgs + (size_t)m * img_stride;
     float4* dst = out + (size_t)pidx * patch_q;
-    int i0 = (int)threadIdx.x / row_q, q0 = (int)threadIdx.x % row_q;
-    for (int g = threadIdx.x; g < patch_q; g += 512) {
-      int i1 = i0 + di, q1 = q0 + dq;
-      if (q1 >= row_q) { q1 -= row_q; ++i1; }
-      const bool has1 = g + 256 < patch_q;
-      uint8_t b0[4], b1[4];
-      {
-        const int y = y0 + i0, e0 = e_row + q0 * 4;
-        const uint8_t* src = img + (size_t)y * w3 + e0;
+    int ii = (int)threadIdx.x / row_q, qq = (int)threadIdx.x % row_q;
+    constexpr int U = 4;                      // groups per thread and trip: their loads are in flight together
+    for (int g = threadIdx.x; g < patch_q; g += 256 * U) {
+      uint32_t word[U];
+      bool has[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b0[j] = (y < h && e0 + j < w3) ? src[j] : (uint8_t)0;
+      for (int u = 0; u < U; ++u) {
+        has[u] = g + 256 * u < patch_q;
+        const int y = y0 + ii, e0 = e_row + qq * 4;
+        const int nb = (has[u] && y < h) ? min(4, w3 - e0) : 0;          // bytes of the group inside the image row
+        word[u] = 0u;
+        if (nb > 0) {
+          const uintptr_t a = reinterpret_cast<uintptr_t>(img + (size_t)y * w3 + e0);
+          const uint32_t sh = (uint32_t)(a & 3u);
+          const uint32_t* p = reinterpret_cast<const uint32_t*>(a - sh);
+          const uint32_t lo = p[0];
+          const uint32_t hi2 = sh + (uint32_t)nb > 4u ? p[1] : 0u;       // second word only when the bytes spill into it
+          word[u] = __funnelshift_r(lo, hi2, sh * 8u);
+          if (nb < 4) word[u] &= (1u << (8 * nb)) - 1u;
+        }
+        ii += di;
+        qq += dq;
+        if (qq >= row_q) { qq -= row_q; ++ii; }
       }
-      {
-        const int y = y0 + i1, e0 = e_row + q1 * 4;
-        const uint8_t* src = img + (size_t)y * w3 + e0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b1[j] = (has1 && y < h && e0 + j < w3) ? src[j] : (uint8_t)0;
+      for (int u = 0; u < U; ++u) {
+        if (!has[u]) continue;
+        const uint32_t b0 = word[u] & 255u, b1 = (word[u] >> 8) & 255u, b2 = (word[u] >> 16) & 255u, b3 = word[u] >> 24;
+        float4 v;
+        if constexpr (MODE == 0) v = make_float4(lut[b0], lut[b1], lut[b2], lut[b3]);
+        else if constexpr (MODE == 1) v = make_float4(div255(b0), div255(b1), div255(b2), div255(b3));
+        else v = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+        dst[g + 256 * u] = v;
       }
-      dst[g] = make_float4(lut[b0[0]], lut[b0[1]], lut[b0[2]], lut[b0[3]]);
-      if (has1) dst[g + 256] = make_float4(lut[b1[0]], lut[b1[1]], lut[b1[2]], lut[b1[3]]);
-      i0 = i1 + di;
-      q0 = q1 + dq;
-      if (q0 >= row_q) { q0 -= row_q; ++i0; }
     }
   }
 }
@@ -283,28 +331,51 @@ patch_gather_u8_rows_kernel(const uint8_t* __restrict__ imgs, int n_img, size_t 
 // Reference: img_utils.image_generator (img_utils.py:341-372): batch[i] = imread(file[index[i]]).astype('float32')/255.
 // The decoded uint8 images live in HBM ([N][item_bytes]); one launch gathers the rows named by `index` and
 // normalises them.  Four bytes per thread: one 4-byte load, one 16-byte store.
+template <bool DIV255>
 __global__ void __launch_bounds__(256)
 batch_gather_u8_kernel(const uint8_t* __restrict__ data, size_t item_bytes,
                        const long long* __restrict__ index, int n, float divisor,
                        float* __restrict__ out) {
-  __shared__ float lut[256];   // v / divisor for every uint8 v (correctly rounded, as the per-element division was)
-  lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, divisor);
-  __syncthreads();
+  // v / divisor for every uint8 v: a table of the correctly rounded quotients, or (divisor == 255, the reference's
+  // case) div255's three fp32 operations -- random table reads serialise on shared-memory bank conflicts
+  __shared__ float lut_[DIV255 ? 1 : 256];
+  if constexpr (!DIV255) {
+    lut_[threadIdx.x] = __fdiv_rn((float)threadIdx.x, divisor);
+    __syncthreads();
+  }
+  auto lut = [&](uint32_t b) { if constexpr (DIV255) return div255(b); else return lut_[b]; };
   const size_t q = item_bytes >> 2;  // uchar4 groups per item
   const size_t total = (size_t)n * q;
   if (total < 0x7fffffffu) {         // 32-bit index arithmetic (64-bit div/mod costs more than the copy)
-    const unsigned q32 = (unsigned)q, tot32 = (unsigned)total;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot32; i += gridDim.x * blockDim.x) {
-      const unsigned b = i / q32, e = i - b * q32;
-      const uchar4 v = reinterpret_cast<const uchar4*>(data + (size_t)index[b] * item_bytes)[e];
-      reinterpret_cast<float4*>(out)[i] = make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]);
+    // four groups per trip, the loads of each level issued together: index -> bytes -> store is a chain of two
+    // dependent loads, and one chain per trip left the kernel latency-bound
+    const unsigned q32 = (unsigned)q, tot32 = (unsigned)total, stride = gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < tot32; i0 += U * stride) {
+      unsigned e[U];
+      long long ix[U];
+      uchar4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned i = i0 + u * stride;
+        const unsigned b = i < tot32 ? i / q32 : 0u;     // (i0 + u * stride cannot wrap: tot32 < 2^31)
+        e[u] = i - b * q32;
+        ix[u] = i < tot32 ? index[b] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        v[u] = ix[u] >= 0 ? reinterpret_cast<const uchar4*>(data + (size_t)ix[u] * item_bytes)[e[u]] : make_uchar4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ix[u] >= 0)
+          reinterpret_cast<float4*>(out)[i0 + u * stride] = make_float4(lut(v[u].x), lut(v[u].y), lut(v[u].z), lut(v[u].w));
     }
     return;
   }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / q, e = i - b * q;
     const uchar4 v = reinterpret_cast<const uchar4*>(data + (size_t)index[b] * item_bytes)[e];
-    reinterpret_cast<float4*>(out)[i] = make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]);
+    reinterpret_cast<float4*>(out)[i] = make_float4(lut(v.x), lut(v.y), lut(v.z), lut(v.w));
   }
 }
 // Reference: img_utils.rebuild_from_patches_Step (img_utils.py:692-724).  Per axis the owner of
@@ -763,8 +834,8 @@ extern "C" int sr_head1x1_fwd(const float* in, const float* w, const float* bias
                               void* out_bf16, float* out_f32, void* stream) {
   if (!in || !w || (!out_bf16 && !out_f32)) return set_error(SR_ERR_INVALID, "sr_head1x1_fwd: null pointer");
   if (npix == 0) return SR_OK;
-  head1x1_kernel<<<grid_for(npix * 32, kBlock, 148 * 8), kBlock, 0, as_stream(stream)>>>(
-      in, w, bias, npix, reinterpret_cast<uint2*>(out_bf16), reinterpret_cast<float4*>(out_f32));
+  head1x1_kernel<<<grid_for(npix * 16, kBlock * 4, 148 * 8), kBlock, 0, as_stream(stream)>>>(
+      in, w, bias, npix, reinterpret_cast<uint4*>(out_bf16), reinterpret_cast<float4*>(out_f32));
   return check_launch("head1x1_kernel");
 }
 
@@ -860,8 +931,17 @@ extern "C" int sr_patch_gather_u8_batched(const uint8_t* imgs, int n_img, size_t
   if (per_img == 0) return SR_OK;
   const size_t n_patches = (size_t)n_img * cnt_h * cnt_w;
   if ((pw * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && n_patches < 0x7fffffffu) {
-    patch_gather_u8_rows_kernel<<<grid_for(n_patches, 1, 148 * 8), kBlock, 0, as_stream(stream)>>>(
-        imgs, n_img, img_stride, h, w, cnt_h, cnt_w, ph, pw, step, divisor, reinterpret_cast<float4*>(out_f32));
+    const unsigned grid = grid_for(n_patches, 1, 148 * 8);
+    float4* o4 = reinterpret_cast<float4*>(out_f32);
+    if (divisor == 255.f)
+      patch_gather_u8_rows_kernel<1><<<grid, kBlock, 0, as_stream(stream)>>>(imgs, n_img, img_stride, h, w, cnt_h, cnt_w,
+                                                                            ph, pw, step, divisor, o4);
+    else if (divisor == 1.f)
+      patch_gather_u8_rows_kernel<2><<<grid, kBlock, 0, as_stream(stream)>>>(imgs, n_img, img_stride, h, w, cnt_h, cnt_w,
+                                                                            ph, pw, step, divisor, o4);
+    else
+      patch_gather_u8_rows_kernel<0><<<grid, kBlock, 0, as_stream(stream)>>>(imgs, n_img, img_stride, h, w, cnt_h, cnt_w,
+                                                                            ph, pw, step, divisor, o4);
     return check_launch("patch_gather_u8_rows_kernel");
   }
   for (int m = 0; m < n_img; ++m) {     // odd patch widths: the scalar kernel, one image per launch
@@ -888,8 +968,11 @@ extern "C" int sr_batch_gather_u8(const uint8_t* data, size_t item_bytes, size_t
     return set_error(SR_ERR_UNSUPPORTED, "sr_batch_gather_u8: item_bytes must be a multiple of 4");
   if ((reinterpret_cast<uintptr_t>(data) & 3) != 0 || (reinterpret_cast<uintptr_t>(out_f32) & 15) != 0)
     return set_error(SR_ERR_INVALID, "sr_batch_gather_u8: data must be 4-byte and out 16-byte aligned");
-  batch_gather_u8_kernel<<<grid_for((size_t)n * (item_bytes >> 2), kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
-      data, item_bytes, index, n, divisor, out_f32);
+  const unsigned grid = grid_for((size_t)n * (item_bytes >> 2), kBlock * 4, 148 * 8);
+  if (divisor == 255.f)
+    batch_gather_u8_kernel<true><<<grid, kBlock, 0, as_stream(stream)>>>(data, item_bytes, index, n, divisor, out_f32);
+  else
+    batch_gather_u8_kernel<false><<<grid, kBlock, 0, as_stream(stream)>>>(data, item_bytes, index, n, divisor, out_f32);
   return check_launch("batch_gather_u8_kernel");
 }
 

@@ -4,8 +4,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
-#include <algorithm>
-
 #include <cstdint>
 
 #include "internal.h"
@@ -68,20 +66,52 @@ __global__ void mse_tail_grad_kernel(const float* __restrict__ pred, const float
 //   dgrad: gx[pix][ci]  = sum_j A[pix][j] * W[ky][kx][ci][co]                (1x1 conv, K = 27 padded to 128)
 //   wgrad: dW[ky][kx][ci][co] = sum_pix x[pix][ci] * A[pix][j]               (k = 1 filter gradient)
 // loss_sum += sum (pred-target)^2 and db3[co] += sum g3[..][co] (each pixel counted once: by the block that owns it).
-// One block per strip of kColStrip pixels of one image row: the three gradient rows around it are staged in shared
-// memory as bf16-rounded floats (with a 1-pixel halo), then 16 threads per pixel write its 256-byte row.
+// One block per strip of kColStrip pixels x kColRows image rows: the kColRows + 2 gradient rows around it are staged
+// in shared memory as bf16-rounded floats (with a 1-pixel halo: 1.25x redundant reads instead of the 3x of one-row
+// blocks, and the two barriers / the block reduction / the four atomics are paid once per 256 KB written instead of
+// once per 32 KB), then 16 threads per pixel write its 256-byte row.
 constexpr int kColStrip = 128;
+constexpr int kColRows = 8;
 
 __global__ void __launch_bounds__(kBlock)
 mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int strips,
-                         size_t n_units, float inv_total2, uint4* __restrict__ a128, double* __restrict__ loss_sum,
+                         int row_blocks, float inv_total2, uint4* __restrict__ a128, double* __restrict__ loss_sum,
                          float* __restrict__ db3) {
   constexpr int kRow = (kColStrip + 2) * 3;
-  __shared__ float g[3 * kRow];
+  __shared__ float g[(kColRows + 2) * kRow];
   __shared__ double red_loss[kBlock / 32];
   __shared__ float red_db[kBlock / 32][3];
+  const int strip = blockIdx.x % strips;
+  const int yb = (blockIdx.x / strips) % row_blocks;
+  const size_t n = blockIdx.x / ((size_t)strips * row_blocks);
+  const int x0 = strip * kColStrip, y0 = yb * kColRows;
+  const int npx = min(kColStrip, W - x0), nrows = min(kColRows, H - y0);
   double loss = 0.0;
   float db[3] = {0.f, 0.f, 0.f};
+  for (int r = 0; r < nrows + 2; ++r) {
+    const int sy = y0 - 1 + r;
+    const bool row_in = sy >= 0 && sy < H;
+    const bool own_row = r >= 1 && r <= nrows;
+    const float* prow = pred + (((size_t)n * H + (row_in ? sy : 0)) * W) * 3;
+    const float* trow = target + (((size_t)n * H + (row_in ? sy : 0)) * W) * 3;
+    for (int i = threadIdx.x; i < kRow; i += kBlock) {
+      const int xx = i / 3, c = i - xx * 3;
+      const int sx = x0 - 1 + xx;
+      float v = 0.f;
+      if (row_in && sx >= 0 && sx < W && xx <= npx + 1) {
+        const float p = prow[(size_t)sx * 3 + c];
+        const float d = p - trow[(size_t)sx * 3 + c];
+        v = __bfloat162float(__float2bfloat16_rn(p > 0.f ? d * inv_total2 : 0.f));
+        if (own_row && xx >= 1 && xx <= npx) {
+          loss += (double)d * (double)d;
+          db[0] += c == 0 ? v : 0.f;
+          db[1] += c == 1 ? v : 0.f;
+          db[2] += c == 2 ? v : 0.f;
+        }
+      }
+      g[r * kRow + i] = v;
+    }
+  }
   // element offsets of this thread's 8 channels (fixed: kBlock is a multiple of 16)
   const int q = threadIdx.x & 15;
   int off[8];
@@ -92,50 +122,24 @@ mse_tail_grad_col_kernel(const float* __restrict__ pred, const float* __restrict
     const int ky = tap / 3, kx = tap - ky * 3;
     off[e] = j < 27 ? ((2 - ky) * (kColStrip + 2) + (2 - kx)) * 3 + co : -1;
   }
-  // persistent blocks over the (image, row, strip) units: the loss / bias-gradient sums stay in registers and reach
-  // the four global accumulators once per block (one block per unit meant ~150 k blocks x 4 same-address atomics)
-  for (size_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-  const int strip = (int)(unit % strips);
-  const int y = (int)((unit / strips) % H);
-  const size_t n = unit / ((size_t)strips * H);
-  const int x0 = strip * kColStrip;
-  const int npx = min(kColStrip, W - x0);
-  for (int i = threadIdx.x; i < 3 * kRow; i += kBlock) {
-    const int r = i / kRow, rem = i - r * kRow;
-    const int xx = rem / 3, c = rem - xx * 3;
-    const int sy = y - 1 + r, sx = x0 - 1 + xx;
-    float v = 0.f;
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W && xx <= npx + 1) {
-      const size_t o = (((size_t)n * H + sy) * W + sx) * 3 + c;
-      const float p = pred[o];
-      const float d = p - target[o];
-      v = __bfloat162float(__float2bfloat16_rn(p > 0.f ? d * inv_total2 : 0.f));
-      if (r == 1 && xx >= 1 && xx <= npx) {
-        loss += (double)d * (double)d;
-        db[0] += c == 0 ? v : 0.f;
-        db[1] += c == 1 ? v : 0.f;
-        db[2] += c == 2 ? v : 0.f;
-      }
-    }
-    g[i] = v;
-  }
   __syncthreads();
-  const size_t base = (((size_t)n * H + y) * W + x0) * 16;
-  for (int i = threadIdx.x; i < npx * 16; i += kBlock) {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (q < 4) {
-      const int px3 = (i >> 4) * 3;
-      float v[8];
+  for (int rr = 0; rr < nrows; ++rr) {
+    const size_t base = (((size_t)n * H + y0 + rr) * W + x0) * 16;
+    const float* gr = g + rr * kRow;
+    for (int i = threadIdx.x; i < npx * 16; i += kBlock) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (q < 4) {
+        const int px3 = (i >> 4) * 3;
+        float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? g[off[e] + px3] : 0.f;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-      o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? gr[off[e] + px3] : 0.f;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      }
+      a128[base + i] = o;
     }
-    a128[base + i] = o;
-  }
-  __syncthreads();   // the next unit overwrites g
   }
   // block reductions: loss (fp64) and the three bias-gradient sums
   for (int o = 16; o > 0; o >>= 1) {
@@ -230,10 +234,11 @@ extern "C" int sr_mse_tail_grad_col(const float* pred, const float* target, int 
   if (NB < 1 || H < 1 || W < 1) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: empty tensor");
   const float inv2 = (float)(2.0 / (double)n_total);
   const int strips = (W + kColStrip - 1) / kColStrip;
-  const size_t blocks = (size_t)NB * H * strips;
+  const int row_blocks = (H + kColRows - 1) / kColRows;
+  const size_t blocks = (size_t)NB * row_blocks * strips;
   if (blocks > 0x7fffffffull) return set_error(SR_ERR_INVALID, "sr_mse_tail_grad_col: tensor too large");
-  mse_tail_grad_col_kernel<<<(unsigned)std::min<size_t>(blocks, 148 * 8), kBlock, 0, as_stream(stream)>>>(
-      pred, target, H, W, strips, blocks, inv2, reinterpret_cast<uint4*>(a128_bf16), loss_sum, db3);
+  mse_tail_grad_col_kernel<<<(unsigned)blocks, kBlock, 0, as_stream(stream)>>>(
+      pred, target, H, W, strips, row_blocks, inv2, reinterpret_cast<uint4*>(a128_bf16), loss_sum, db3);
   return check_launch("mse_tail_grad_col_kernel");
 }
 

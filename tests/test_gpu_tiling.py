@@ -126,7 +126,8 @@ def test_upscale_step_patch_end_to_end(tmp_path):
 
 
 @pytest.mark.parametrize("shape,patch,step,divisor", [((5, 70, 45), 96, 64, 255.0), ((3, 339, 510), 96, 64, 255.0),
-                                                      ((2, 50, 61), 32, 16, 1.0), ((2, 40, 40), 17, 8, 255.0)])
+                                                      ((2, 50, 61), 32, 16, 1.0), ((2, 40, 40), 17, 8, 255.0),
+                                                      ((2, 50, 61), 32, 16, 100.0), ((3, 33, 35), 32, 16, 255.0)])
 def test_batched_gather_equals_per_image_gather_and_oracle(shape, patch, step, divisor):
     """One launch for a batch of same-shaped images (BASELINE config 3) == the per-image gathers, which are the
     reference's extract_patches_Step on the zero-padded canvas (bit-exact; 17-px patches take the scalar kernel)."""
@@ -148,3 +149,27 @@ def test_batched_gather_equals_per_image_gather_and_oracle(shape, patch, step, d
         want, wc = ot.extract_patches_step(canvas, (patch, patch), step)
         assert tuple(wc) == tuple(counts)
         assert np.array_equal(got[m * n:(m + 1) * n].cpu().numpy(), (want.astype(np.float32) / np.float32(divisor)))
+
+
+def test_gather_divides_every_byte_value_like_numpy():
+    """The /255 of models.py:336 for all 256 byte values (the kernel's arithmetic path: one product + two FMAs) and
+    for an image view that starts at an odd address (the word loads + funnel shift), bit for bit against numpy's
+    correctly rounded float32 division."""
+    import torch
+    from sr100 import ops
+    base = torch.arange(3 * 40 * 44 + 7, dtype=torch.int64).remainder(256).to(torch.uint8).cuda()
+    for off in (0, 1, 2, 3, 5):
+        img = base[off:off + 3 * 40 * 44].view(40, 44, 3)
+        ch, cw = ops.canvas_size(40, 44, 32, 16)
+        got, counts = ops.patch_gather_u8(img, (ch, cw), (32, 32), 16, divisor=255.0)
+        host = img.cpu().numpy()
+        canvas = np.zeros((ch, cw, 3), dtype=np.uint8)
+        canvas[:40, :44] = host
+        n = 0
+        g = got.cpu().numpy()
+        assert set(np.unique(host)) == set(range(256))
+        for wi in range(counts[1]):
+            for hi in range(counts[0]):
+                want = canvas[hi * 16:hi * 16 + 32, wi * 16:wi * 16 + 32].astype(np.float32) / np.float32(255)
+                assert np.array_equal(g[n], want), (off, n)
+                n += 1

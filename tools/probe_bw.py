@@ -33,6 +33,7 @@ def main():
     st = L.stream_ptr
     recs = []
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB, only ever read
 
     def timed(name, nbytes, fn, note=""):
         for _ in range(3):
@@ -40,7 +41,11 @@ def main():
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(a.iters):
-            flush.fill_(1)              # evict L2 (256 MB write) between timed launches
+            # evict L2 between timed launches: a 256 MB write, then a 256 MB READ of another buffer, so that the
+            # cache holds clean lines when the timed kernel starts (after the write alone ~100 MB of dirty lines
+            # were written back INSIDE the timed region: 10-15 us charged to kernels that take 20-100 us)
+            flush.fill_(1)
+            flush_rd.sum()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -54,6 +59,14 @@ def main():
         recs.append(rec)
         print(json.dumps(rec), flush=True)
 
+    # ---- reference points on this box, same method: what plain torch kernels reach at the sizes probed below
+    for mb in (128, 1024):
+        n = mb * 1024 * 1024 // 4
+        a_, b_ = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        timed("reference: torch copy (read + write), %d MB each way" % mb, 2 * n * 4, lambda: b_.copy_(a_))
+        timed("reference: torch fill (write only), %d MB" % mb, n * 4, lambda: b_.fill_(1.0))
+        timed("reference: torch sum (read only), %d MB" % mb, n * 4, lambda: a_.sum())
+        del a_, b_
     # ---- bilinear x4 (fp32 LR stream in, bf16 HR out): 512 + 16*256 B per LR pixel
     NB, H, W = 186, 96, 96
     x32 = torch.randn(NB, H, W, 128, device=dev)

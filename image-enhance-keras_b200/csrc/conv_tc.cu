@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -1092,6 +1093,331 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   }
 }
 
+
+// =====================================================================================
+// Chain kernel: a whole SEQUENCE of convolutions in one persistent launch (small inputs).
+//
+// A single 128x128 patch (BASELINE config 1) gives every CTA one 128-position tile per layer: a per-layer launch
+// then spends more time on launch gap, barrier / TMEM setup, first weight fetch and teardown than on its MMAs
+// (tools/probe_timeline.py: 5.7 us of MMA in an 18.6 us k3 launch).  Here the CTA pairs stay resident and walk a list
+// of PHASES; a phase is one or two independent convolutions (the two branch heads of a 5/3 block read the same
+// tensor), phases are separated by a grid-wide barrier (every output of phase i is in L2 before a strip of phase
+// i+1 is requested).  What survives per layer is the barrier (~1.5 us) and the first strip's L2 latency: weights of
+// the next phase stream into the ring while the current one computes, TMEM / mbarriers are set up once, and the
+// epilogue of the first head tile overlaps the MMAs of the second.
+// Same tiles, same tap / chunk / source order per output position as the per-layer kernels: bit-identical results.
+// =====================================================================================
+struct alignas(128) ChainConv {
+  CUtensorMap tmA[2], tmW[2];
+  ConvKernelParams P;
+  int phase;        // convs of one phase are independent of each other; phases run in order
+  int pair_tiles;   // ((NB * nseg + 1) / 2) * tiles_per_seg
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Spin until *counter >= target.  The poll itself is one acquire load (an L2 round trip); the bounded-wait check
+// (a protocol bug traps instead of hanging the GPU) reads the global timer only every 2048 polls.
+static __device__ __noinline__ void chain_wait_counter(const unsigned* counter, unsigned target) {
+  if (ld_acquire_gpu(counter) >= target) return;
+  const uint64_t t0 = global_timer_ns();
+  for (unsigned spins = 1;; ++spins) {
+    if (ld_acquire_gpu(counter) >= target) return;
+    if ((spins & 2047u) == 0 && global_timer_ns() - t0 > SR_MBAR_TIMEOUT_NS) {
+      printf("sr100: chain grid barrier timed out (block %d)\n", (int)blockIdx.x);
+      __trap();
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_tc_chain_kernel(const ChainConv* __restrict__ convs, int n_convs, int n_phases, unsigned* sync_counter,
+                     int a_slot_bytes, int num_abuf, int num_wstages, unsigned long long* tl) {
+  constexpr int N_ = 128, NACC = 1, NBUF = 4, T = 128;
+  constexpr int WTAP = (N_ / 2) * kRowBytes;
+  constexpr int NCH = kNumChunks, CHE = kChunk;
+  constexpr int WSTAGE = kTapsPerStage * WTAP;
+  constexpr uint32_t TM_COLS = 512;
+  constexpr uint32_t IDESC = umma_idesc(1u, 256u, (uint32_t)N_);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + num_abuf * a_slot_bytes;
+  uint8_t* stage_buf = w_buf + num_wstages * WSTAGE;
+  ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(stage_buf + 4 * 32 * 256);
+  float* s_bias = reinterpret_cast<float*>(bars + 1);   // [4 epilogue warps][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NS = num_wstages;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&bars->w_full[i], 1);
+      mbar_init(&bars->w_empty[i], 1);
+    }
+    for (int i = 0; i < num_abuf; ++i) {
+      mbar_init(&bars->a_full[i], 1);
+      mbar_init(&bars->a_empty[i], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(&bars->tmem_base, TM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  // development build (sr_dev_set_timeline): globaltimer stamps, 8 per (CTA, phase) -- 0 barrier passed, 1 / 2 first /
+  // last strip of the phase's first tile ready, 3 MMAs committed, 4 / 5 epilogue sees the accumulator / is done,
+  // 6 fenced, about to arrive (tools/probe_chain.py)
+#ifdef SR_DEV_SWITCHES
+#define CH_STAMP(ph_, idx_) do { if (tl) tl[((size_t)blockIdx.x * n_phases + (ph_)) * 8 + (idx_)] = global_timer_ns(); } while (0)
+#else
+#define CH_STAMP(ph_, idx_) do { (void)tl; } while (0)
+#endif
+
+  // first pair tile of conv `pt_total` tiles this cluster owns, when the phase's tiles before it number g0
+  auto first_tile = [&](int g0) {
+    int r = (cluster_id - g0) % num_clusters;
+    return r < 0 ? r + num_clusters : r;
+  };
+  auto decode = [&](const ConvKernelParams& P, int pt, bool* live) {
+    const int tps = P.tiles_per_seg, ncol = P.NB * P.nseg;
+    const int j = pt / tps;
+    const int ti = pt - j * tps;
+    int col = 2 * j + (int)rank;
+    *live = col < ncol;
+    if (col >= ncol) col = ncol - 1;
+    return decode_tile<T>(P, col * tps + ti);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight half-stage TMA producer: free-running over all phases
+    if (lane == 0) {
+      Ring wr{0u, 0u, (uint32_t)NS};
+      int g0 = 0, ph = 0;
+      for (int ci = 0; ci < n_convs; ++ci) {
+        const ChainConv& cv = convs[ci];
+        if (cv.phase != ph) { ph = cv.phase; g0 = 0; }
+        const ConvKernelParams& P = cv.P;
+        for (int pt = first_tile(g0); pt < cv.pair_tiles; pt += num_clusters) {
+          for (int s = 0; s < P.nsrc; ++s) {
+            const CUtensorMap* tmW = &cv.tmW[s];
+            const int ntaps = P.ksize[s] * P.ksize[s];
+            for (int ch = 0; ch < NCH; ++ch) {
+              for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
+                const uint32_t slot = wr.slot, wph = wr.phase;
+                mbar_wait(&bars->w_empty[slot], wph ^ 1);
+                const int nbox = min(kTapsPerStage, ntaps - tap);
+                if (is_leader) mbar_expect_tx(&bars->w_full[slot], 2 * nbox * WTAP);
+                const uint32_t bar = mapa_shared(smem_u32(&bars->w_full[slot]), 0);
+#pragma unroll
+                for (int j = 0; j < kTapsPerStage; ++j)
+                  if (j < nbox)
+                    tma_load_2d_pair(w_buf + slot * WSTAGE + j * WTAP, tmW, bar, 0,
+                                     (ch * ntaps + tap + j) * N_ + (int)rank * (N_ / 2));
+                wr.advance();
+              }
+            }
+          }
+        }
+        g0 += cv.pair_tiles;
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------ activation strip TMA producer; waits for the grid barrier
+    if (lane == 0) {
+      Ring ar{0u, 0u, (uint32_t)num_abuf};
+      int g0 = 0, ph = 0;
+      for (int ci = 0; ci < n_convs; ++ci) {
+        const ChainConv& cv = convs[ci];
+        if (cv.phase != ph) {
+          ph = cv.phase;
+          g0 = 0;
+          // every CTA of the grid has stored (and fenced) its outputs of phase ph - 1
+          chain_wait_counter(sync_counter, (unsigned)ph * gridDim.x);
+          CH_STAMP(ph, 0);
+          fence_proxy_async_all();   // generic-proxy stores of other SMs -> this thread's async-proxy (TMA) reads
+        }
+        const ConvKernelParams& P = cv.P;
+        const uint32_t strip_bytes = (uint32_t)P.NR * P.PWs * kRowBytes;
+        for (int pt = first_tile(g0); pt < cv.pair_tiles; pt += num_clusters) {
+          bool live;
+          const TileCoord c = decode(P, pt, &live);
+          for (int s = 0; s < P.nsrc; ++s) {
+            const CUtensorMap* tmA = &cv.tmA[s];
+            for (int ch = 0; ch < NCH; ++ch) {
+              const uint32_t slot = ar.slot, aph = ar.phase;
+              mbar_wait(&bars->a_empty[slot], aph ^ 1);
+              if (is_leader) mbar_expect_tx(&bars->a_full[slot], 2 * strip_bytes);
+              tma_load_4d_pair(a_buf + slot * a_slot_bytes, tmA, mapa_shared(smem_u32(&bars->a_full[slot]), 0),
+                               ch * CHE, c.seg_x0 - P.p, c.r_lo - P.p, c.n);
+              ar.advance();
+            }
+          }
+        }
+        g0 += cv.pair_tiles;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only, warp-convergent)
+    if (is_leader) {
+      const bool leader = elect_one();
+      uint32_t it = 0;
+      Ring wr{0u, 0u, (uint32_t)NS};
+      Ring ar{0u, 0u, (uint32_t)num_abuf};
+      constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW64 << 29);
+      const uint32_t a_buf_lo = (smem_u32(a_buf) >> 4) | (1u << 16);
+      const uint32_t a_slot_step = (uint32_t)a_slot_bytes >> 4;
+      const uint32_t w_buf_lo = (smem_u32(w_buf) >> 4) | (1u << 16);
+      int g0 = 0, ph = 0;
+      for (int ci = 0; ci < n_convs; ++ci) {
+        const ChainConv& cv = convs[ci];
+        if (cv.phase != ph) { ph = cv.phase; g0 = 0; }
+        const ConvKernelParams& P = cv.P;
+        for (int pt = first_tile(g0); pt < cv.pair_tiles; pt += num_clusters, ++it) {
+          bool live;
+          const TileCoord c = decode(P, pt, &live);
+          const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+          mbar_wait(&bars->tmem_empty[buf], bph ^ 1);
+          tc_fence_after();
+          const uint32_t d_base = tmem_base + buf * (NACC * N_);
+          uint32_t acc_flag = 0;
+          for (int s = 0; s < P.nsrc; ++s) {
+            const int k = P.ksize[s];
+            const int pk = (k - 1) / 2;
+            const int ntaps = k * k;
+            const int row_wrap = (P.PWs - (k - 1)) * 4;
+            for (int ch = 0; ch < NCH; ++ch) {
+              const uint32_t aslot = ar.slot, aph = ar.phase;
+              mbar_wait(&bars->a_full[aslot], aph);
+              tc_fence_after();
+              if (leader && s == 0 && ch == 0) CH_STAMP(cv.phase, 1);
+              if (leader && s == P.nsrc - 1 && ch == NCH - 1) CH_STAMP(cv.phase, 2);
+              uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
+              int kx = 0;
+              for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
+                const uint32_t wslot = wr.slot, wph = wr.phase;
+                mbar_wait(&bars->w_full[wslot], wph);
+                tc_fence_after();
+                uint32_t b_lo = w_buf_lo + wslot * (uint32_t)(WSTAGE >> 4);
+#pragma unroll
+                for (int j = 0; j < kTapsPerStage; ++j) {
+                  if (leader && tap + j < ntaps) {
+#pragma unroll
+                    for (int k16 = 0; k16 < 2; ++k16) {
+                      const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + k16 * 2);
+                      const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + k16 * 2);
+                      umma_bf16_pair(d_base, adesc, bdesc, IDESC, k16 == 0 ? acc_flag : 1u);
+                    }
+                  }
+                  acc_flag = 1;
+                  b_lo += (uint32_t)(WTAP >> 4);
+                  if (++kx == k) {
+                    kx = 0;
+                    a_lo += row_wrap;
+                  } else {
+                    a_lo += 4;
+                  }
+                }
+                if (leader) umma_commit_pair(&bars->w_empty[wslot]);
+                wr.advance();
+              }
+              if (leader) umma_commit_pair(&bars->a_empty[aslot]);
+              ar.advance();
+            }
+          }
+          if (leader) umma_commit_pair(&bars->tmem_full[buf]);
+          if (leader) CH_STAMP(cv.phase, 3);
+        }
+        g0 += cv.pair_tiles;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (both CTAs); arrives at the grid barrier per phase
+    const int ew = warp - 4;
+    uint32_t it = 0;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float* my_bias = s_bias + ew * N_;
+    int g0 = 0, ph = 0;
+    auto end_phase = [&]() {
+      // this CTA's outputs of the phase are stored: make them visible GPU-wide (also to the async proxy of the
+      // SMs that will TMA-load them), then one arrival per CTA
+      __threadfence();
+      fence_proxy_async_all();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ew == 0 && lane == 0) CH_STAMP(ph, 6);
+      if (ew == 0 && lane == 0) {
+        // A CTA without tiles in this phase must not run ahead: it may only arrive for phase ph once every CTA has
+        // arrived for phase ph - 1 (for a CTA with tiles that already holds -- its strips waited for it).  Then
+        // "counter >= (ph + 1) * gridDim.x" really means that every CTA has finished phase ph.
+        chain_wait_counter(sync_counter, (unsigned)ph * gridDim.x);
+        red_release_gpu_add(sync_counter, 1u);
+      }
+    };
+    for (int ci = 0; ci < n_convs; ++ci) {
+      const ChainConv& cv = convs[ci];
+      if (cv.phase != ph) {
+        end_phase();
+        ph = cv.phase;
+        g0 = 0;
+      }
+      const ConvKernelParams& P = cv.P;
+      bool bias_loaded = false;
+      for (int pt = first_tile(g0); pt < cv.pair_tiles; pt += num_clusters, ++it) {
+        if (!bias_loaded) {
+          __syncwarp();
+          for (int i = lane; i < N_; i += 32) my_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
+          __syncwarp();
+          bias_loaded = true;
+        }
+        bool live;
+        const TileCoord c = decode(P, pt, &live);
+        const uint32_t buf = it % NBUF, bph = (it / NBUF) & 1;
+        mbar_wait(&bars->tmem_full[buf], bph);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) CH_STAMP(cv.phase, 4);
+        const uint32_t t_base = tmem_base + buf * (NACC * N_) + ((uint32_t)(ew * 32) << 16);
+        uint8_t* stage = stage_buf + ew * (32 * 256);
+        if (P.res_f32) epilogue_staged_acc<1, false>(P, c, t_base, c.f0 + ew * 32, stage, my_bias, lane, live, cs);
+        else epilogue_staged_acc_plain(P, c, t_base, c.f0 + ew * 32, stage, my_bias, lane, live);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&bars->tmem_empty[buf]), 0));
+        if (ew == 0 && lane == 0) CH_STAMP(cv.phase, 5);
+      }
+      g0 += cv.pair_tiles;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TM_COLS);
+  }
+#undef CH_STAMP
+}
+
 // =====================================================================================
 // Host side: plan
 // =====================================================================================
@@ -1530,5 +1856,165 @@ extern "C" int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* 
   info->tile_positions = pl->nacc * 128;
   info->mma_efficiency =
       (double)pl->P.NB * pl->P.Hc * pl->P.Wc / ((double)pl->P.total_tiles * pl->nacc * 128);
+  return SR_OK;
+}
+
+
+// ------------------------------------------------------------------ chain plan (see conv_tc_chain_kernel)
+struct ConvChain {
+  sr::ChainConv* dev = nullptr;       // device copy of the conv list
+  unsigned* counter = nullptr;        // grid barrier arrivals (zeroed by every run)
+  int n_convs = 0, n_phases = 0, grid = 0, a_slot_bytes = 0, num_abuf = 0, num_wstages = 0;
+  size_t smem_bytes = 0;
+  double flops = 0;
+  int total_tiles = 0;
+};
+
+extern "C" int sr_conv_chain_create(const sr_conv_desc* descs, const int* phase, int n, sr_conv_chain** out) {
+  if (!descs || !phase || !out || n < 1) return set_error(SR_ERR_INVALID, "sr_conv_chain_create: bad argument");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  const int wstage = kTapsPerStage * 64 * kRowBytes;      // a CTA's half of a two-tap weight stage
+  const int stage_bytes = 4 * 32 * 256;
+  std::vector<sr::ChainConv> host((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const sr_conv_desc* d = &descs[i];
+    if (d->nsrc < 1 || d->nsrc > 2 || d->cin != kCin || d->cout != 128 || d->precision != 0 || d->a_mode != 0 ||
+        d->shuffle_r > 0 || d->relu_mask_bf16 || d->colsum_f32 || d->relu == 2 || d->out_index || d->stitch_u8 ||
+        !d->out_bf16 || (d->res_bf16 && !d->res_f32) || (d->out_f32 && !d->res_f32) || d->NB < 1 || d->H < 1 || d->W < 1)
+      return set_error(SR_ERR_UNSUPPORTED, "sr_conv_chain_create: 128 -> 128 bf16 convs with the plain (bf16 out) or "
+                                           "fp32-residual epilogue only");
+    if (i > 0 && (phase[i] < phase[i - 1] || phase[i] > phase[i - 1] + 1))
+      return set_error(SR_ERR_INVALID, "sr_conv_chain_create: phases must be non-decreasing without gaps");
+    if (i == 0 && phase[0] != 0) return set_error(SR_ERR_INVALID, "sr_conv_chain_create: the first phase is 0");
+    for (int s = 0; s < d->nsrc; ++s) {
+      const int k = d->ksize[s];
+      if (!(k == 1 || k == 3 || k == 5 || k == 7) || !d->in[s] || !d->wpacked[s])
+        return set_error(SR_ERR_INVALID, "sr_conv_chain_create: bad source");
+    }
+  }
+  // one strip-ring / weight-ring geometry for all convs: as many strip buffers as leave a useful weight ring
+  int nab = 4, a_slot = 0, nstages = 0;
+  for (; nab >= 2; --nab) {
+    a_slot = 0;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+      const sr_conv_desc* d = &descs[i];
+      ConvKernelParams& P = host[i].P;
+      memset(&P, 0, sizeof P);
+      int p = 0;
+      for (int s = 0; s < d->nsrc; ++s) p = std::max(p, (d->ksize[s] - 1) / 2);
+      P.nsrc = d->nsrc;
+      P.ksize[0] = d->ksize[0];
+      P.ksize[1] = d->nsrc > 1 ? d->ksize[1] : 0;
+      P.H = d->H, P.W = d->W, P.NB = d->NB, P.p = p;
+      P.Hc = (d->comp_h > 0 && d->comp_h < d->H) ? d->comp_h : d->H;
+      P.Wc = (d->comp_w > 0 && d->comp_w < d->W) ? d->comp_w : d->W;
+      const int step = d->NB >= 2 ? 1 : 2;     // a single image: an even number of column segments (no idle CTA)
+      ok = choose_geometry(P.Hc, P.Wc, p, 128, wstage, stage_bytes, &P, step, step, nab);
+      a_slot = std::max(a_slot, P.a_bytes);
+    }
+    if (!ok) continue;
+    const size_t fixed = 1024 + (size_t)nab * a_slot + stage_bytes + sizeof(ConvBarriers) + 4 * 128 * 4 + 64;
+    if (fixed + 6 * (size_t)wstage > kSmemBudget && nab > 2) continue;
+    if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;
+    nstages = std::min((int)((kSmemBudget - fixed) / wstage), kMaxWStages);
+    break;
+  }
+  if (nab < 2 || nstages < 3) return set_error(SR_ERR_UNSUPPORTED, "sr_conv_chain_create: no geometry fits shared memory");
+  ConvChain* ch = new (std::nothrow) ConvChain();
+  if (!ch) return set_error(SR_ERR_NOMEM, "out of host memory");
+  int max_phase_tiles = 0, cur_phase_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const sr_conv_desc* d = &descs[i];
+    sr::ChainConv& cv = host[i];
+    ConvKernelParams& P = cv.P;
+    P.num_abuf = nab;
+    P.num_wstages = nstages;
+    P.total_tiles = P.NB * P.nseg * P.tiles_per_seg;
+    P.bias = d->bias;
+    P.alpha = d->alpha, P.beta = d->beta, P.relu = d->relu;
+    P.res_f32 = d->res_f32;
+    P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
+    P.out_f32 = d->out_f32;
+    P.cout = d->cout;
+    cv.phase = phase[i];
+    cv.pair_tiles = ((P.NB * P.nseg + 1) / 2) * P.tiles_per_seg;
+    if (i > 0 && phase[i] != phase[i - 1]) cur_phase_tiles = 0;
+    cur_phase_tiles += cv.pair_tiles;
+    max_phase_tiles = std::max(max_phase_tiles, cur_phase_tiles);
+    ch->total_tiles += P.total_tiles;
+    for (int s = 0; s < d->nsrc; ++s) {
+      int rc = make_a_map(&cv.tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, kAModeSwizzle64, 0);
+      if (rc == SR_OK) rc = make_w_map(&cv.tmW[s], d->wpacked[s], kNumChunks * d->ksize[s] * d->ksize[s], 128, 64, 0);
+      if (rc != SR_OK) {
+        delete ch;
+        return rc;
+      }
+      ch->flops += 2.0 * (double)d->NB * P.Hc * P.Wc * d->ksize[s] * d->ksize[s] * kCin * d->cout;
+    }
+    if (d->nsrc == 1) cv.tmA[1] = cv.tmA[0], cv.tmW[1] = cv.tmW[0];
+  }
+  ch->n_convs = n;
+  ch->n_phases = phase[n - 1] + 1;
+  ch->a_slot_bytes = a_slot, ch->num_abuf = nab, ch->num_wstages = nstages;
+  ch->grid = 2 * std::min(max_phase_tiles, sms / 2);
+  ch->smem_bytes = 1024 + (size_t)nab * a_slot + (size_t)nstages * wstage + stage_bytes + sizeof(ConvBarriers) +
+                   4 * 128 * 4 + 64;
+  void* devp = nullptr;
+  if (cudaMalloc(&devp, (size_t)n * sizeof(sr::ChainConv) + 256) != cudaSuccess) {
+    cudaGetLastError();
+    delete ch;
+    return set_error(SR_ERR_NOMEM, "sr_conv_chain_create: cudaMalloc failed");
+  }
+  ch->counter = reinterpret_cast<unsigned*>(devp);
+  ch->dev = reinterpret_cast<sr::ChainConv*>(reinterpret_cast<char*>(devp) + 256);
+  if (cudaMemcpy(ch->dev, host.data(), (size_t)n * sizeof(sr::ChainConv), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(devp);
+    delete ch;
+    return set_error(SR_ERR_CUDA, "sr_conv_chain_create: upload failed");
+  }
+  *out = reinterpret_cast<sr_conv_chain*>(ch);
+  return SR_OK;
+}
+
+extern "C" int sr_conv_chain_run(sr_conv_chain* chain, void* stream) {
+  if (!chain) return set_error(SR_ERR_INVALID, "sr_conv_chain_run: null chain");
+  const ConvChain* ch = reinterpret_cast<const ConvChain*>(chain);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static unsigned long long attr_done = 0;
+  if (int rc = ensure_dynamic_smem(conv_tc_chain_kernel, (int)kSmemBudget, &attr_done,
+                                   "cudaFuncSetAttribute(conv_tc_chain_kernel)"))
+    return rc;
+  cudaError_t e = cudaMemsetAsync(ch->counter, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "sr_conv_chain_run: memset");
+  conv_tc_chain_kernel<<<ch->grid, kConvThreads, ch->smem_bytes, st>>>(ch->dev, ch->n_convs, ch->n_phases, ch->counter,
+                                                                     ch->a_slot_bytes, ch->num_abuf, ch->num_wstages,
+                                                                     dev_timeline());
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_chain_kernel launch");
+  return SR_OK;
+}
+
+extern "C" void sr_conv_chain_destroy(sr_conv_chain* chain) {
+  ConvChain* ch = reinterpret_cast<ConvChain*>(chain);
+  if (!ch) return;
+  if (ch->counter) cudaFree(ch->counter);
+  delete ch;
+}
+
+extern "C" int sr_conv_chain_info(const sr_conv_chain* chain, sr_conv_plan_info_t* info) {
+  if (!chain || !info) return set_error(SR_ERR_INVALID, "sr_conv_chain_info: null argument");
+  const ConvChain* ch = reinterpret_cast<const ConvChain*>(chain);
+  memset(info, 0, sizeof *info);
+  info->flops = ch->flops;
+  info->total_tiles = ch->total_tiles;
+  info->grid = ch->grid;
+  info->smem_bytes = (int)ch->smem_bytes;
+  info->num_wstages = ch->num_wstages;
+  info->tile_positions = 128;
+  info->strip_rows = ch->n_phases;     // (reused field: number of phases)
+  info->nseg = ch->n_convs;            // (reused field: number of convolutions)
   return SR_OK;
 }

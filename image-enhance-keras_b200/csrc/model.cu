@@ -114,12 +114,14 @@ __global__ void tail_dw_kernel(const float* d128, float* dw) {
 struct Step {
   sr_conv_plan* cp = nullptr;
   sr_wgrad_plan* wp = nullptr;
+  sr_conv_chain* ch = nullptr;           // many convolutions in one persistent launch (small inputs)
   std::function<int(cudaStream_t)> fn;   // anything else
   bool par_with_prev = false;            // independent of the previous step: may run beside it on the side stream
   double flops = 0;                      // tensor-core launches only
   int run(cudaStream_t st) const {
     if (cp) return sr_conv_plan_run(cp, st);
     if (wp) return sr_wgrad_plan_run(wp, st);
+    if (ch) return sr_conv_chain_run(ch, st);
     return fn(st);
   }
 };
@@ -140,6 +142,7 @@ struct Sequence {
     for (auto& s : steps) {
       if (s.cp) sr_conv_plan_destroy(s.cp);
       if (s.wp) sr_wgrad_plan_destroy(s.wp);
+      if (s.ch) sr_conv_chain_destroy(s.ch);
     }
     for (auto e : events) cudaEventDestroy(e);
     for (auto p : owned_dev) cudaFree(p);
@@ -320,9 +323,9 @@ struct ConvArgs {
   float stitch_mul = 0.f;
 };
 
-int add_conv(sr_model* m, Sequence* seq, const ConvArgs& a, sr_conv_plan_info_t* info_out = nullptr) {
+int make_desc(const sr_model* m, const ConvArgs& a, sr_conv_desc* out) {
   const auto& L = layers();
-  sr_conv_desc d;
+  sr_conv_desc& d = *out;
   memset(&d, 0, sizeof d);
   d.nsrc = a.nsrc;
   for (int s = 0; s < a.nsrc; ++s) {
@@ -350,6 +353,27 @@ int add_conv(sr_model* m, Sequence* seq, const ConvArgs& a, sr_conv_plan_info_t*
   d.comp_h = a.comp_h, d.comp_w = a.comp_w;
   d.colsum_f32 = a.colsum, d.colsum_scale = a.colsum_scale;
   d.stitch_tiles = a.stitch_tiles, d.stitch_u8 = a.stitch_u8, d.stitch_mul = a.stitch_mul;
+  return SR_OK;
+}
+
+// When non-null, add_conv only RECORDS the convolution (descriptor + phase) instead of creating a plan: the LR stage
+// of a small input becomes one chain launch (sr_conv_chain_create).
+struct ChainBuilder {
+  std::vector<sr_conv_desc> descs;
+  std::vector<int> phase;
+  int cur_phase = 0;
+};
+
+int add_conv(sr_model* m, Sequence* seq, const ConvArgs& a, sr_conv_plan_info_t* info_out = nullptr,
+             ChainBuilder* chain = nullptr) {
+  sr_conv_desc d;
+  SR_TRY(make_desc(m, a, &d));
+  if (chain) {
+    chain->descs.push_back(d);
+    chain->phase.push_back(chain->cur_phase);
+    if (info_out) memset(info_out, 0, sizeof *info_out), info_out->grid = 1 << 20;
+    return SR_OK;
+  }
   Step st;
   SR_TRY(sr_conv_plan_create(&d, &st.cp));
   sr_conv_plan_info_t info;
@@ -373,35 +397,41 @@ struct Ext { int h, w; };
 
 // one 5/3 block of the forward: t1 = relu(conv3_a(s)), t2 = relu(conv5_c(s)), s = 0.1*(conv5_b(t1)+conv3_d(t2)) + 0.9*s
 int fwd_block53(sr_model* m, Sequence* seq, int li, void* s, float* s32, void* t1, void* t2, int NB, int H, int W,
-                Ext c_out, Ext c_t1, Ext c_t2, const void* res16) {
+                Ext c_out, Ext c_t1, Ext c_t2, const void* res16, ChainBuilder* chain = nullptr) {
   ConvArgs a;
   a.NB = NB, a.H = H, a.W = W;
   a.layer[0] = li, a.in[0] = s, a.out_op = t1, a.relu = 1, a.comp_h = c_t1.h, a.comp_w = c_t1.w;
   sr_conv_plan_info_t ia, ib;
-  SR_TRY(add_conv(m, seq, a, &ia));
+  SR_TRY(add_conv(m, seq, a, &ia, chain));             // the two heads share a phase of a chain
   a.layer[0] = li + 2, a.out_op = t2, a.comp_h = c_t2.h, a.comp_w = c_t2.w;
-  SR_TRY(add_conv(m, seq, a, &ib));
-  if (m->cfg.overlap_heads && ia.grid + ib.grid <= m->sms) seq->steps.back().par_with_prev = true;
+  SR_TRY(add_conv(m, seq, a, &ib, chain));
+  if (chain) chain->cur_phase += 1;
+  if (!chain && m->cfg.overlap_heads && ia.grid + ib.grid <= m->sms) seq->steps.back().par_with_prev = true;
   ConvArgs f;
   f.NB = NB, f.H = H, f.W = W, f.nsrc = 2;
   f.layer[0] = li + 1, f.in[0] = t1, f.layer[1] = li + 3, f.in[1] = t2;
   f.out_op = s, f.out_f32 = s32, f.alpha = 0.1f, f.beta = 0.9f, f.res32 = s32, f.res16 = res16;
   f.comp_h = c_out.h, f.comp_w = c_out.w;
-  return add_conv(m, seq, f);
+  SR_TRY(add_conv(m, seq, f, nullptr, chain));
+  if (chain) chain->cur_phase += 1;
+  return SR_OK;
 }
 
 int fwd_light(sr_model* m, Sequence* seq, int li, void* s, float* s32, void* t1, int NB, int H, int W, Ext c_out,
-              Ext c_t1, const void* res16) {
+              Ext c_t1, const void* res16, ChainBuilder* chain = nullptr) {
   ConvArgs a;
   a.NB = NB, a.H = H, a.W = W;
   a.layer[0] = li, a.in[0] = s, a.out_op = t1, a.relu = 1, a.comp_h = c_t1.h, a.comp_w = c_t1.w;
-  SR_TRY(add_conv(m, seq, a));
+  SR_TRY(add_conv(m, seq, a, nullptr, chain));
+  if (chain) chain->cur_phase += 1;
   ConvArgs f;
   f.NB = NB, f.H = H, f.W = W;
   f.layer[0] = li + 1, f.in[0] = t1;
   f.out_op = s, f.out_f32 = s32, f.alpha = 0.1f, f.beta = 1.0f, f.res32 = s32, f.res16 = res16;
   f.comp_h = c_out.h, f.comp_w = c_out.w;
-  return add_conv(m, seq, f);
+  SR_TRY(add_conv(m, seq, f, nullptr, chain));
+  if (chain) chain->cur_phase += 1;
+  return SR_OK;
 }
 
 // ------------------------------------------------------------------ running a sequence
@@ -593,12 +623,46 @@ int build_forward(sr_model* m, const sr_forward_desc* d, const FwdGeom& g, Seque
   }
   Ext exts[22][3];
   lr_extents(Ext{g.need_h, g.need_w}, Ext{H, W}, exts);
+  // Opt-in (sr_model_config.chain_lr): a small LR stage (every CTA pair gets about one 128-position tile per layer:
+  // a single 128 x 128 patch, BASELINE config 1) as ONE persistent chain launch instead of 60 launches.  Bit-identical,
+  // but measured SLOWER than the per-layer launches under a CUDA graph (the grid barrier + the exposed
+  // strip burst and epilogue of a one-tile phase cost more than the launch boundary they replace), so it is off by
+  // default.
+  const bool small_lr = npix <= (size_t)m->sms * 128;
+  bool chained = false;
   int li = 1;
-  for (int b = 0; b < 16; ++b, li += 4)
-    SR_TRY(fwd_block53(m, seq, li, l.s_lr, l.s_lr32, l.t1_lr, l.t2_lr, NB, H, W, exts[b][0], exts[b][1], exts[b][2],
-                       l.s_lr));
-  for (int b = 16; b < 22; ++b, li += 2)
-    SR_TRY(fwd_light(m, seq, li, l.s_lr, l.s_lr32, l.t1_lr, NB, H, W, exts[b][0], exts[b][1], l.s_lr));
+  if (m->cfg.chain_lr && small_lr && !m->tf32 && l.s_lr32 && m->cfg.a_mode == 0 && m->cfg.pair == 1 && m->cfg.nacc == 2) {
+    ChainBuilder cb;
+    int lj = 1;
+    int rc = SR_OK;
+    for (int b = 0; b < 16 && rc == SR_OK; ++b, lj += 4)
+      rc = fwd_block53(m, seq, lj, l.s_lr, l.s_lr32, l.t1_lr, l.t2_lr, NB, H, W, exts[b][0], exts[b][1], exts[b][2],
+                       l.s_lr, &cb);
+    for (int b = 16; b < 22 && rc == SR_OK; ++b, lj += 2)
+      rc = fwd_light(m, seq, lj, l.s_lr, l.s_lr32, l.t1_lr, NB, H, W, exts[b][0], exts[b][1], l.s_lr, &cb);
+    SR_TRY(rc);
+    Step st;
+    rc = sr_conv_chain_create(cb.descs.data(), cb.phase.data(), (int)cb.descs.size(), &st.ch);
+    if (rc == SR_OK) {
+      sr_conv_plan_info_t info;
+      sr_conv_chain_info(st.ch, &info);
+      st.flops = info.flops;
+      seq->conv_flops += info.flops;
+      seq->conv_launches += 1;
+      seq->steps.push_back(std::move(st));
+      chained = true;
+      li = lj;
+    } else if (rc != SR_ERR_UNSUPPORTED) {
+      return rc;
+    }
+  }
+  if (!chained) {
+    for (int b = 0; b < 16; ++b, li += 4)
+      SR_TRY(fwd_block53(m, seq, li, l.s_lr, l.s_lr32, l.t1_lr, l.t2_lr, NB, H, W, exts[b][0], exts[b][1], exts[b][2],
+                         l.s_lr));
+    for (int b = 16; b < 22; ++b, li += 2)
+      SR_TRY(fwd_light(m, seq, li, l.s_lr, l.s_lr32, l.t1_lr, NB, H, W, exts[b][0], exts[b][1], l.s_lr));
+  }
   const int first_hr = li;
   // the index tables of all groups: one device array, uploaded once
   int* idx_dev = nullptr;
@@ -970,6 +1034,7 @@ extern "C" void sr_model_default_config(sr_model_config* c) {
   memset(c, 0, sizeof *c);
   c->precision = 0, c->stream_lr_fp32 = 1, c->stream_hr_fp32 = 0;
   c->a_mode = 0, c->nacc = 2, c->pair = 1, c->use_graphs = 1, c->overlap_heads = 1, c->fused_colsum = 1;
+  c->chain_lr = 0;
 }
 
 extern "C" int sr_model_num_layers(void) { return (int)layers().size(); }

@@ -105,7 +105,8 @@ class ScoreResult(C.Structure):
 class ModelConfig(C.Structure):
     _fields_ = [("precision", C.c_int), ("stream_lr_fp32", C.c_int), ("stream_hr_fp32", C.c_int),
                 ("a_mode", C.c_int), ("nacc", C.c_int), ("pair", C.c_int), ("use_graphs", C.c_int),
-                ("overlap_heads", C.c_int), ("fused_colsum", C.c_int), ("overlap_train", C.c_int)]
+                ("overlap_heads", C.c_int), ("fused_colsum", C.c_int), ("chain_lr", C.c_int),
+                ("overlap_train", C.c_int)]
 
 
 class ForwardDesc(C.Structure):
@@ -147,6 +148,10 @@ SIGNATURES = {
     "sr_conv_plan_run": (_i, [_vp, _vp]),
     "sr_conv_plan_destroy": (None, [_vp]),
     "sr_conv_plan_info": (_i, [_vp, C.POINTER(ConvPlanInfo)]),
+    "sr_conv_chain_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "sr_conv_chain_run": (_i, [_vp, _vp]),
+    "sr_conv_chain_destroy": (None, [_vp]),
+    "sr_conv_chain_info": (_i, [_vp, C.POINTER(ConvPlanInfo)]),
     "sr_packed_weight_bytes": (_sz, [_i, _i]),
     "sr_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sr_pack_conv_weights_batched": (_i, [_vp, _vp, _i, _sz, _vp]),

@@ -451,6 +451,7 @@ class Engine:
             cfg.overlap_heads = int(self.side_stream is not None)
             cfg.fused_colsum = int(os.environ.get("SR100_FUSED_COLSUM", "1") != "0")
             cfg.overlap_train = int(os.environ.get("SR100_OVERLAP_TRAIN", str(cfg.overlap_train)) != "0")
+            cfg.chain_lr = int(os.environ.get("SR100_CHAIN_LR", "0") == "1")
             with torch.cuda.device(self.device):
                 L.check(self.lib.sr_model_create(L.ptr(self.param_arena), C.byref(cfg), C.byref(self.model)))
         return self.model

@@ -136,6 +136,23 @@ int sr_conv_plan_run(sr_conv_plan* plan, void* stream);
 void sr_conv_plan_destroy(sr_conv_plan* plan);
 int sr_conv_plan_info(const sr_conv_plan* plan, sr_conv_plan_info_t* info);
 
+/* A SEQUENCE of 128 -> 128 bf16 convolutions in ONE persistent launch, for inputs so small that a per-layer launch is
+ * mostly launch gap, setup and teardown (one 128 x 128 patch through model.predict, models.py:342 / 165-182: BASELINE
+ * config 1).  descs[i] as for sr_conv_plan_create (plain bf16-out epilogue, or fp32 residual + fp32 / bf16 outputs);
+ * phase[i] (HOST array, non-decreasing from 0) groups convolutions that do not depend on each other -- the two branch
+ * heads of a 5/3 block read the same tensor -- and phases are separated by a grid-wide barrier inside the kernel:
+ * every output of phase p is visible before any input of phase p + 1 is read.  Results are bit-identical to running
+ * the plans one by one.  The chain owns a small device buffer (tensor maps + barrier counter).
+ * Measured on B200 (tools/probe_chain.py, profiles/r02_probe_chain.txt): per phase the barrier costs ~4 us and the
+ * strip burst + epilogue of a one-tile phase stay exposed, so the chain is SLOWER than per-layer launches replayed from
+ * a CUDA graph (config 1: 2.33 vs 2.06 ms); kept as an entry point and as the record of that experiment. */
+typedef struct sr_conv_chain sr_conv_chain;
+int sr_conv_chain_create(const sr_conv_desc* descs, const int* phase, int n, sr_conv_chain** chain);
+int sr_conv_chain_run(sr_conv_chain* chain, void* stream);
+void sr_conv_chain_destroy(sr_conv_chain* chain);
+/* flops, grid, smem_bytes, num_wstages, total_tiles; strip_rows = number of phases, nseg = number of convolutions */
+int sr_conv_chain_info(const sr_conv_chain* chain, sr_conv_plan_info_t* info);
+
 /* Repack Keras HWIO fp32 weights [k,k,cin=128,cout] (device) into the kernel's K-chunked bf16
  * layout [cin/32][k*k][cout_pad][32]; cout_pad = 16 for cout <= 16, else 128 (zero rows beyond cout).  transpose_flip = 1 produces the
  * weights of the input-gradient convolution (180-degree rotation, cin<->cout): always a
@@ -423,6 +440,9 @@ typedef struct sr_model_config {
                         * an internal second stream when both grids fit on the chip together (small inputs) */
   int fused_colsum;    /* 1 (default): bias gradients ride the input-gradient launches (sr_conv_desc.colsum_f32);
                         * 0: separate sr_colsum_bf16 passes (same values, another fp32 summation order) */
+  int chain_lr;        /* 1: the 60 launches of the LR stage of a SMALL input (about one 128-position tile per CTA pair
+                        * and layer: one 128 x 128 patch) run as one persistent sr_conv_chain launch.  Bit-identical,
+                        * measured slower than the per-layer launches under a graph: default 0 */
   int overlap_train;   /* 1: independent launches of the training step (the two branch heads of a 5/3 block, their two
                         * input-gradient launches, the wgrad pairs) are issued on two streams, so the tail wave of one
                         * persistent kernel is back-filled by the first CTAs of the other; 0 (default): one stream */

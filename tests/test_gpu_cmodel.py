@@ -217,3 +217,111 @@ def test_c_abi_train_step_raw(lib):
         assert lib.sr_model_forward_backward(model, C.byref(d), L.stream_ptr()) == -2
     finally:
         lib.sr_model_destroy(model)
+
+
+def _chain_case(lib, rng, NB, H, W):
+    """Two 5/3 blocks' worth of launches (heads phase + fused tail phase, twice) as one chain and as single plans."""
+    from sr100 import _lib as L
+    dev = "cuda"
+    bf = torch.bfloat16
+
+    def packed(k):
+        w = torch.from_numpy((rng.normal(0, 0.03, size=(k, k, 128, 128))).astype(np.float32)).to(dev)
+        pk = torch.empty(lib.sr_packed_weight_bytes(k, 128), dtype=torch.uint8, device=dev)
+        L.check(lib.sr_pack_conv_weights(L.ptr(w), k, 128, 0, L.ptr(pk), L.stream_ptr()))
+        return pk
+
+    keep = []
+    x0 = torch.from_numpy(rng.normal(0, 1, size=(NB, H, W, 128)).astype(np.float32)).to(dev)
+
+    def run(chain):
+        s32 = x0.clone()
+        s = s32.to(bf)
+        t1, t2 = torch.zeros_like(s), torch.zeros_like(s)
+        descs, phases = [], []
+        ph = 0
+        for blk in range(2):
+            w3a, w5c, w5b, w3d = weights[blk]
+            for (wk, k, dst) in ((w3a, 3, t1), (w5c, 5, t2)):
+                d = L.ConvDesc()
+                d.nsrc, d.NB, d.H, d.W, d.cin, d.cout = 1, NB, H, W, 128, 128
+                d.in_[0], d.wpacked[0], d.ksize[0] = s.data_ptr(), wk.data_ptr(), k
+                d.bias, d.alpha, d.beta, d.relu = bias[blk][0].data_ptr(), 1.0, 0.0, 1
+                d.out_bf16 = dst.data_ptr()
+                d.nacc, d.pair = 2, 1
+                descs.append(d)
+                phases.append(ph)
+            ph += 1
+            d = L.ConvDesc()
+            d.nsrc, d.NB, d.H, d.W, d.cin, d.cout = 2, NB, H, W, 128, 128
+            d.in_[0], d.wpacked[0], d.ksize[0] = t1.data_ptr(), w5b.data_ptr(), 5
+            d.in_[1], d.wpacked[1], d.ksize[1] = t2.data_ptr(), w3d.data_ptr(), 3
+            d.bias, d.alpha, d.beta, d.relu = bias[blk][1].data_ptr(), 0.1, 0.9, 0
+            d.res_f32, d.out_f32, d.out_bf16 = s32.data_ptr(), s32.data_ptr(), s.data_ptr()
+            d.nacc, d.pair = 2, 1
+            descs.append(d)
+            phases.append(ph)
+            ph += 1
+        if chain:
+            arr = (L.ConvDesc * len(descs))(*descs)
+            pa = (C.c_int * len(phases))(*phases)
+            h = C.c_void_p()
+            L.check(lib.sr_conv_chain_create(arr, pa, len(descs), C.byref(h)))
+            info = L.ConvPlanInfo()
+            L.check(lib.sr_conv_chain_info(h, C.byref(info)))
+            assert info.nseg == 6 and info.strip_rows == 4 and info.grid <= 148
+            for _ in range(2):                 # a second run on its own outputs would differ: reset the stream first
+                s32.copy_(x0)
+                s.copy_(x0.to(bf))
+                L.check(lib.sr_conv_chain_run(h, L.stream_ptr()))
+            torch.cuda.synchronize()
+            lib.sr_conv_chain_destroy(h)
+        else:
+            for d in descs:
+                p = C.c_void_p()
+                L.check(lib.sr_conv_plan_create(C.byref(d), C.byref(p)))
+                L.check(lib.sr_conv_plan_run(p, L.stream_ptr()))
+                torch.cuda.synchronize()
+                lib.sr_conv_plan_destroy(p)
+        return s32.clone(), s.clone(), t1.clone(), t2.clone()
+
+    weights = [[packed(3), packed(5), packed(5), packed(3)] for _ in range(2)]
+    bias = [[torch.from_numpy(rng.normal(0, 0.1, size=128).astype(np.float32)).to(dev) for _ in range(2)] for _ in range(2)]
+    a = run(True)
+    b = run(False)
+    for u, v, name in zip(a, b, ("s32", "s", "t1", "t2")):
+        assert torch.equal(u, v), (NB, H, W, name, float((u.float() - v.float()).abs().max()))
+    assert float(a[0].abs().max()) > 0.5 and torch.isfinite(a[0]).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 128), (1, 40, 56), (2, 48, 48), (3, 33, 20), (1, 7, 9), (5, 96, 96)])
+def test_conv_chain_equals_single_launches(lib, shape):
+    """sr_conv_chain (one persistent launch, grid barrier between phases) == the same convolutions as single plans,
+    bit for bit: one tile per CTA (config 1), fewer tiles than CTAs, several tiles per CTA (5 x 96 x 96), odd sizes."""
+    _chain_case(lib, np.random.default_rng(sum(shape)), *shape)
+
+
+def test_chained_lr_stage_equals_per_layer_launches(monkeypatch):
+    """model.predict of one 128 x 128 patch (BASELINE config 1): the LR stage as one chain launch (SR100_CHAIN_LR=1,
+    opt-in: measured slower) against the 60 per-layer launches (the default), eager and graph replay -- bit-identical."""
+    from oracle import model as om
+    from sr100.engine import Engine
+    from sr100 import _lib as L
+    weights = om.init_weights(1234, bias_scale=0.01)
+    rng = np.random.default_rng(1)
+    for shape in ((1, 128, 128), (1, 64, 80), (2, 40, 40)):
+        x = torch.from_numpy(_smooth(rng, *shape)).cuda()
+        monkeypatch.setenv("SR100_CHAIN_LR", "1")
+        ec = Engine(weights)
+        outs = [ec.forward_device(x).clone() for _ in range(3)]
+        info = L.ModelRunInfo()
+        d = ec.last_calls[0][0]
+        L.check(ec.lib.sr_model_forward_info(ec.model, C.byref(d), C.byref(info)))
+        assert info.launches == 2 + 1 + 6 + 1, info.launches      # head, chain, bilinear + 2 HR blocks + tail
+        monkeypatch.setenv("SR100_CHAIN_LR", "0")
+        ep = Engine(weights)
+        want = ep.forward_device(x)
+        for o in outs:
+            assert torch.equal(o, want), shape
+    got = outs[-1].cpu().numpy()
+    assert np.abs(got - om.forward_numpy(weights, x.cpu().numpy())).max() <= 2e-3

@@ -1518,8 +1518,14 @@ static int make_w_map(CUtensorMap* tm, const void* ptr, int nstages, int n_pad, 
 static constexpr size_t kSmemBudget = 227 * 1024;
 
 // Choose the column-segment width: maximise useful MMA rows subject to the shared-memory budget.
+// max_cols_tiles > 0 (sub-wave launches, every CTA pair gets at most one tile): among the geometries whose
+// NB * nseg * tiles_per_seg stays <= max_cols_tiles choose the one with the FEWEST STRIP BYTES per tile instead of the
+// best MMA row efficiency -- such a launch is bound by the burst of strip loads after it starts (a 128-position tile of
+// a 66-pixel-wide segment fetches 5-6 strip rows for its 2 image rows; narrower segments cut that by 28-40 %), not by
+// the discarded halo positions.
 static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_bytes,
-                            ConvKernelParams* P, int min_nseg = 1, int nseg_step = 1, int nabuf = 2) {
+                            ConvKernelParams* P, int min_nseg = 1, int nseg_step = 1, int nabuf = 2,
+                            int NB = 1, long long max_cols_tiles = 0) {
   double best_eff = -1.0;
   for (int nseg = min_nseg; nseg <= W; nseg += nseg_step) {
     const int BW = (W + nseg - 1) / nseg;
@@ -1534,7 +1540,11 @@ static bool choose_geometry(int H, int W, int p, int T, int wstage, int stage_by
     if (fixed + 3 * (size_t)wstage > kSmemBudget) continue;  // >= 3 two-tap weight stages in flight
     const int f_len = (H - 1) * PWs + BW;
     const int tps = (f_len + T - 1) / T;
-    const double eff = (double)H * W / ((double)nseg * tps * T);
+    double eff = (double)H * W / ((double)nseg * tps * T);
+    if (max_cols_tiles > 0) {
+      if ((long long)NB * nseg * tps > max_cols_tiles) continue;
+      eff = 1.0 / ((double)NR * PWs);            // fewest strip pixels wins
+    }
     // prefer fewer segments on ties (less halo traffic)
     if (eff > best_eff + 1e-9) {
       best_eff = eff;
@@ -1698,8 +1708,12 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
       const int wstage2 = kTapsPerStage * (pl->n_pad / 2) * kRowBytes;
       bool ok = false;
       for (int nab = 4; nab >= 2 && !ok; --nab) {
-        ok = (d->NB >= 2) ? choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 1, 1, nab)
-                          : choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 2, 2, nab);
+        // first choice: one tile per CTA pair with the fewest strip bytes (2 * clusters tiles at most)
+        ok = (d->NB >= 2) ? choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 1, 1, nab, d->NB, 2LL * clusters)
+                          : choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 2, 2, nab, d->NB, 2LL * clusters);
+        if (!ok)
+          ok = (d->NB >= 2) ? choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 1, 1, nab)
+                            : choose_geometry(Hc, Wc, p, 128, wstage2, stage_bytes, &Q, 2, 2, nab);
         if (ok && Q.num_wstages < 6 && nab > 2) ok = false;    // keep a useful weight ring
       }
       if (ok) {

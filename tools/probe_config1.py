@@ -23,7 +23,7 @@ def main():
     import torch
     from sr100 import _lib as L
     from sr100.engine import Engine, _Plan, glorot_uniform_weights
-    eng = Engine(glorot_uniform_weights(seed=1234))
+    eng = Engine(glorot_uniform_weights(seed=1234), sequencer="python")     # per-launch access needs the Python launch lists
     x = torch.rand(a.nb, a.h, a.w, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     for _ in range(5):
         eng.forward_device(x)

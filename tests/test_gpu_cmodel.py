@@ -325,3 +325,28 @@ def test_chained_lr_stage_equals_per_layer_launches(monkeypatch):
             assert torch.equal(o, want), shape
     got = outs[-1].cpu().numpy()
     assert np.abs(got - om.forward_numpy(weights, x.cpu().numpy())).max() <= 2e-3
+
+
+def test_plain_c_client_equals_engine(tmp_path):
+    """examples/sr_predict.c (gcc, C99, no torch / Python in the process) drives sr_model_create / sr_model_forward
+    with a parameter arena written by tools/export_arena.py: its output file equals Engine.forward_device bit for
+    bit (same library, same launch sequence) -- the graph-level ABI is usable from a non-Python binding."""
+    import os
+    import subprocess
+    import sys
+    from sr100 import _lib as L
+    from sr100.engine import Engine, glorot_uniform_weights
+    exe = os.path.join(os.path.dirname(L.LIB_PATH), "sr_predict")
+    assert os.path.exists(exe), "sr_predict was not built (csrc/Makefile builds it next to libsr100.so)"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pf, xf, yf = (str(tmp_path / n) for n in ("params.f32", "x.f32", "y.f32"))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "export_arena.py"), "--out", pf, "--seed", "77"])
+    x = _smooth(np.random.default_rng(11), 2, 24, 40)
+    x.tofile(xf)
+    out = subprocess.run([exe, pf, xf, "2", "24", "40", yf, "5"], check=True, capture_output=True, text=True).stdout
+    import json
+    info = json.loads(out.strip().splitlines()[-1])
+    assert info["graph_replay"] == 1 and info["launches"] > 60
+    got = np.fromfile(yf, dtype=np.float32).reshape(2, 96, 160, 3)
+    want = Engine(glorot_uniform_weights(seed=77)).forward_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)

@@ -1,6 +1,6 @@
 """Benchmark of the x4 SR hot path (BASELINE.json metric: x4 output megapixels/sec at 1/2/4/8 B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only headline,set5,train,config5,config1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only headline,set5,train,config5,whole,config1]
 
 Headline workload (config.workload = "batch64_339x510_x4_tiled", BASELINE.json configs[2]):
 64 synthetic RGB images of 339x510 (seeds 100..163) -> 1356x2040 through the reference's tiling (96/64 patches,
@@ -16,8 +16,10 @@ the uint8 outputs inside the timed region (wall clock around a device synchroniz
 The same JSON line carries the other BASELINE configs as objects (each its own timed region, same rules):
   "set5"       configs[1]: five Set5-shaped images tiled + Y-PSNR / Y-SSIM / RGB-SSIM scoring (every rank its own copy)
   "train_step" configs[3]: 48x48 LR patches, GLOBAL batch 256 split over the ranks, forward + dgrad/wgrad on the
-               tensor cores, NCCL all-reduce of the 87 MB gradient arena, fused Adam (strong scaling)
+               tensor cores, then ONE fused reduce-scatter + Adam + all-gather kernel per rank over NVLink peer memory
+               (csrc/exchange.cu; the ncclAllReduce + Adam variant is timed beside it) (strong scaling)
   "config5"    configs[4]: one 1080x1920 image, its 510 live tiles sharded over the ranks, rank 0 stitches
+  "whole_image" configs[2] again in whole-image mode (model.predict of the 339x510 images, no tiling)
   "config1"    configs[0]: one 128x128 patch -> 512x512 through model.predict (latency)
 """
 import argparse
@@ -194,7 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="sr100")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", type=str, default="headline,set5,train,config5,config1",
+    ap.add_argument("--only", type=str, default="headline,set5,train,config5,whole,config1",
                     help="comma list of parts to run (headline is needed for a valid line)")
     ap.add_argument("--profile", action="store_true", help="ncu pass: honour --warmup as given, skip the extras")
     ap.add_argument("--allow-dev-build", action="store_true")
@@ -377,6 +379,23 @@ def main():
         del big
         eng.release()
 
+    # =============================================================== configs[2] secondary: whole-image mode
+    if "whole" in parts:
+        xw = torch.stack([d.float() for d in dev_imgs]).div_(255.0) if dev_imgs else None
+        outw = torch.empty(len(dev_imgs), 4 * B_H, 4 * B_W, 3, device="cuda") if dev_imgs else None
+        kw = max(2, min(steps, 3))
+        tw = timed(lambda: eng.forward_device(xw, out=outw) if xw is not None else None, kw, 3)
+        fw = D.sum_over_ranks(eng.conv_flops(len(dev_imgs), B_H, B_W))
+        line["whole_image"] = {"workload": "the same 64 x 339x510 images as whole images through model.predict (the "
+                                           "reference's upVideo path, models.py:165-182: no tiling, no 2.5x tile "
+                                           "redundancy), images round-robin over the ranks, fp32 [0,1] in HBM -> fp32 x4 out",
+                               "value": round(mp_step * kw / tw, 3), "unit": UNIT, "ms_per_step": round(tw / kw * 1e3, 3),
+                               "steps": kw, "tflops": round(fw * kw / tw / 1e12, 1),
+                               "frac_of_sustained_peak": round(fw * kw / tw / 1e12 / peaks["sustained"] / world, 4),
+                               "scaling": "strong"}
+        del xw, outw
+        eng.release()
+
     # =============================================================== configs[0]: one 128x128 patch (latency)
     if "config1" in parts:
         x1 = torch.rand(1, 128, 128, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
@@ -422,7 +441,15 @@ def main():
             tr.forward_backward_device(g)
             tr.apply_gradients(summed_over=world)
 
-        ms = run_steps(lambda: tr.step_device(g))                       # the default step (one all-reduce after backward)
+        # the default step: world > 1 -> backward, then ONE fused reduce-scatter + Adam + all-gather kernel per rank over
+        # NVLink peer memory (csrc/exchange.cu); the same step with ncclAllReduce + full-arena Adam is timed beside it
+        ms = run_steps(lambda: tr.step_device(g))
+        ms_nccl, p2p = None, tr.exchange is not None
+        if p2p:
+            ex, tr.exchange = tr.exchange, None
+            ms_nccl = run_steps(lambda: tr.step_device(g))
+            tr.exchange = ex
+            assert not ex.timed_out(), "peer-memory exchange: a wait on a peer expired"
         ms_overlap = None
         if world > 1 and eng.sequencer == "python":   # the bucketed overlap needs the Python launch lists
             ms_overlap = run_steps(lambda: tr.step_device(g, overlap=True))
@@ -431,15 +458,18 @@ def main():
         flops = tr.step_flops(g)
         line["train_step"] = {
             "workload": "training step (BASELINE configs[3]): 48x48 LR -> 192x192, global batch 256 split over the ranks, "
-                        "forward + dgrad/wgrad bf16 on the tensor cores, NCCL all-reduce (sum) of the flat fp32 gradient "
-                        "arena, fused Keras-Adam, weight repack", "global_batch": GB, "per_gpu_batch": hi - lo,
+                        "forward + dgrad/wgrad bf16 on the tensor cores, gradient exchange + Keras-Adam (see comm), "
+                        "weight repack", "global_batch": GB, "per_gpu_batch": hi - lo,
             "ms_per_step": round(ms, 3), "images_per_s": round(GB / ms * 1e3, 1), "steps": kt,
+            "exchange": "p2p" if p2p else ("nccl" if world > 1 else "none"),
+            "ms_per_step_nccl_allreduce_then_adam": None if ms_nccl is None else round(ms_nccl, 3),
             "ms_per_step_bucketed_overlapped_allreduce": None if ms_overlap is None else round(ms_overlap, 3),
             "sequencer": "sr_model_forward_backward + sr_model_apply_gradients (libsr100)" if eng.sequencer == "c"
                          else "python launch lists",
             "ms_per_step_without_exchange": round(ms_floor, 3),
-            "exposed_allreduce_ms": round(upd_ms, 3),
-            "allreduce_bytes": tr.grads.numel() * 4 if world > 1 else 0,
+            "exposed_exchange_ms": round(upd_ms, 3),
+            "exposed_exchange_ms_nccl": None if ms_nccl is None else round(ms_nccl - ms_floor, 3),
+            "exchange_bytes_per_rank": int(2 * (world - 1) / world * tr.grads.numel() * 4) if world > 1 else 0,
             "comm": tr.comm_description() if hasattr(tr, "comm_description") else "one all_reduce after backward",
             "algorithmic_tflop_per_step_per_gpu": round(flops / 1e12, 3),
             "tflops_per_gpu": round(flops / (ms * 1e-3) / 1e12, 1),

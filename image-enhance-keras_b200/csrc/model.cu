@@ -1201,6 +1201,14 @@ extern "C" int sr_model_apply_gradients(sr_model* m, const float* grads, float* 
   return refresh(m, sr::as_stream(stream));
 }
 
+extern "C" int sr_model_apply_gradients_exchange(sr_model* m, sr_exchange* ex, float* mom, float* vel, int t, float lr,
+                                                 float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!m || !ex || !mom || !vel) return set_error(SR_ERR_INVALID, "sr_model_apply_gradients_exchange: null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  SR_TRY(sr_exchange_adam_step(ex, mom, vel, t, lr, beta1, beta2, eps, grad_scale, 0, stream));
+  return refresh(m, sr::as_stream(stream));
+}
+
 extern "C" int sr_model_train_step(sr_model* m, const sr_train_desc* d, float* mom, float* vel, int t, float lr,
                                    float beta1, float beta2, float eps, void* stream) {
   SR_TRY(sr_model_forward_backward(m, d, stream));

@@ -214,6 +214,17 @@ SIGNATURES = {
     "sr_model_train_info": (_i, [_vp, C.POINTER(TrainDesc), C.POINTER(ModelRunInfo)]),
     "sr_model_apply_gradients": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
     "sr_model_train_step": (_i, [_vp, C.POINTER(TrainDesc), _vp, _vp, _i, _f, _f, _f, _f, _vp]),
+    "sr_ipc_export": (_i, [_vp, C.c_char_p, C.POINTER(_sz)]),
+    "sr_ipc_open": (_i, [C.c_char_p, _sz, C.POINTER(_vp)]),
+    "sr_ipc_close": (_i, [_vp, _sz]),
+    "sr_exchange_signal_bytes": (_sz, []),
+    "sr_exchange_shard": (_i, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "sr_exchange_create": (_i, [_i, _i, _sz, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sr_exchange_destroy": (None, [_vp]),
+    "sr_exchange_set_timeout_ms": (_i, [_vp, C.c_double]),
+    "sr_exchange_adam_step": (_i, [_vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _i, _vp]),
+    "sr_exchange_status": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "sr_model_apply_gradients_exchange": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
 }
 
 _lib = None

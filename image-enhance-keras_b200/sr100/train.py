@@ -308,7 +308,7 @@ class _CTrainGraph:
 class Trainer:
     """train_on_batch / evaluate for a kmodel.Model (Keras Model.train_on_batch semantics: returns the loss)."""
 
-    def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+    def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7, exchange=None):
         if getattr(engine, "tf32", False):
             raise NotImplementedError("training runs on the bf16 engine (dgrad / wgrad kernels take bf16 operands); "
                                       "precision='tf32' is an inference mode")
@@ -333,9 +333,44 @@ class Trainer:
         # "c": sr_model_forward_backward / sr_model_apply_gradients own the launch sequence; "python": the launch lists
         # of _TrainGraph (needed for the bucketed overlap and the per-kernel breakdown of tools/bench_train.py)
         self.sequencer = engine.sequencer
+        self.exchange = None   # sr100.peer.Exchange: fused reduce-scatter + Adam + all-gather over NVLink peer memory
         self.sync_replicas()
         if self.sequencer != "c":
             self.repack_t()
+        self._connect_exchange(exchange)
+
+    def _connect_exchange(self, mode):
+        """World > 1: the gradient exchange + optimizer step run as ONE kernel per rank over peer memory
+        (csrc/exchange.cu) when every rank is on this node and the arenas can be mapped with CUDA IPC ('p2p', the
+        default under NCCL); otherwise -- or with exchange='nccl' / SR100_EXCHANGE=nccl -- an all-reduce of the arena
+        followed by the full-arena Adam launch."""
+        import torch.distributed as tdist
+        if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
+            return
+        mode = mode or os.environ.get("SR100_EXCHANGE") or ("p2p" if tdist.get_backend() == "nccl" else "nccl")
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl', got %r" % (mode,))
+        if mode == "nccl":
+            return
+        from . import peer
+        try:
+            self.exchange = peer.connect(self.lib, self.grads, self.engine.param_arena)
+        except RuntimeError as e:
+            import warnings
+            warnings.warn("sr100: %s; using the all-reduce exchange" % e, RuntimeWarning)
+
+    def gather_optimizer_state(self):
+        """With the peer-memory exchange every rank holds the Adam moments of its own shard only; this makes m and v
+        whole on every rank again (before a checkpoint of the optimizer state or a replica re-sync)."""
+        if self.exchange is None:
+            return
+        from .dist import all_reduce_sum_
+        lo, hi = self.exchange.lo, self.exchange.hi
+        for buf in (self.m, self.v):
+            own = buf[lo:hi].clone()
+            buf.zero_()
+            buf[lo:hi] = own
+            all_reduce_sum_(buf)
 
     # ------------------------------------------------------------------ views into the flat arenas
     def grad_w(self, name):
@@ -376,6 +411,7 @@ class Trainer:
         import torch.distributed as tdist
         if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() == 1:
             return False
+        self.gather_optimizer_state()
         t = torch.tensor([float(self.t)], dtype=torch.float64, device=self.engine.device)
         for buf in (self.engine.param_arena, self.m, self.v, t):
             tdist.broadcast(buf, src=0)
@@ -453,6 +489,21 @@ class Trainer:
         summed_over: self.grads already holds the SUM over that many minibatch shards (a logical split run in one
         process: no collective, only the 1/shards scale) -- what the tests use to check the data-parallel algebra."""
         from .dist import all_reduce_sum_
+        if self.exchange is not None and summed_over is None:
+            self.t += 1
+            ex = self.exchange
+            args = (L.ptr(self.m), L.ptr(self.v), self.t, self.lr, self.beta_1, self.beta_2, self.epsilon, 1.0 / ex.world)
+            if self.sequencer == "c":
+                L.check(self.lib.sr_model_apply_gradients_exchange(self.engine.model, ex.handle, *args, L.stream_ptr()))
+                if self.engine._py_packed:
+                    self.engine.repack(c_model=False)
+                    if self._pack_table_t is not None:
+                        self.repack_t()
+            else:
+                L.check(self.lib.sr_exchange_adam_step(ex.handle, *args, 0, L.stream_ptr()))
+                self.engine.repack()
+                self.repack_t()
+            return
         world = all_reduce_sum_(self.grads) if summed_over is None else int(summed_over)
         self.t += 1
         if self.sequencer == "c":      # Adam + every weight repack behind one entry point
@@ -567,6 +618,10 @@ class Trainer:
 
     def comm_description(self):
         n = self.grads.numel() * 4
+        if self.exchange is not None:
+            return ("one fused kernel per rank over NVLink peer memory (CUDA IPC): reduce-scatter of the fp32 gradient "
+                    "arena (%d bytes) in rank order + Keras-Adam on the rank's 1/%d shard + all-gather of the new "
+                    "parameters into every rank's arena; no NCCL call on the data path" % (n, self.exchange.world))
         if os.environ.get("SR100_OVERLAP_ALLREDUCE", "0") == "1":
             return ("three all_reduce(sum) buckets of the fp32 gradient arena (%d bytes: HR stage + tail, LR blocks 11-21, "
                     "head + LR blocks 0-10), each issued on a side stream as soon as the backward segment that completes "

@@ -526,6 +526,45 @@ int sr_model_apply_gradients(sr_model* model, const float* grads, float* m, floa
 int sr_model_train_step(sr_model* model, const sr_train_desc* desc, float* m, float* v, int t, float lr,
                         float beta1, float beta2, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The path's one exchange step (data-parallel training): average the minibatch shards' gradients and
+ * apply compile(Adam(1e-4, 0.9)) (models.py:1212-1213) to identical replicas -- as ONE kernel per rank that does
+ * reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/exchange.cu) instead of ncclAllReduce followed by
+ * a full-arena Adam pass.  One process per GPU on one node; the gradient arena, the parameter arena and a small
+ * zero-initialised signal pad of every rank are shared with CUDA IPC (sr_ipc_*; the 64-byte handles travel over any
+ * side channel, e.g. torch.distributed.all_gather_object).  Rank r reduces, updates and broadcasts the shard
+ * sr_exchange_shard(n, r, world); its Adam state m, v is valid on that shard only (sharded optimizer state).
+ * All ranks must call sr_exchange_adam_step the same number of times; waits on peers are bounded
+ * (sr_exchange_set_timeout_ms, default 30 s) and a time-out is reported by sr_exchange_status instead of a hang.
+ * ------------------------------------------------------------------------------------------ */
+#define SR_IPC_HANDLE_BYTES 64
+#define SR_EXCHANGE_MAX_RANKS 8
+/* handle + byte offset of dev_ptr inside its cudaMalloc allocation (works for pointers into a caching allocator's
+ * blocks); open in ANOTHER process -> that process's pointer to the same bytes (peer access enabled lazily). */
+int sr_ipc_export(const void* dev_ptr, unsigned char* handle, size_t* offset);
+int sr_ipc_open(const unsigned char* handle, size_t offset, void** dev_ptr);
+int sr_ipc_close(void* dev_ptr, size_t offset);
+
+typedef struct sr_exchange sr_exchange;
+size_t sr_exchange_signal_bytes(void);
+/* [lo, hi) in floats of rank's shard of an n-float arena (multiples of 4 except the very end). */
+int sr_exchange_shard(size_t n, int rank, int world, size_t* lo, size_t* hi);
+/* grads[r], params[r], signals[r]: THIS process's pointers to rank r's arenas / signal pad (r == rank: its own). */
+int sr_exchange_create(int rank, int world, size_t n, float* const* grads, float* const* params,
+                       void* const* signals, sr_exchange** exchange);
+void sr_exchange_destroy(sr_exchange* exchange);
+int sr_exchange_set_timeout_ms(sr_exchange* exchange, double ms);
+/* sum the ranks' gradients (rank order), Keras-2 Adam with grad_scale (1/world) on the shard, new parameters into
+ * every rank's arena; returns when launched, completes when every peer's shard has arrived.  max_blocks 0: default. */
+int sr_exchange_adam_step(sr_exchange* exchange, float* m, float* v, int t, float lr, float beta1, float beta2,
+                          float eps, float grad_scale, int max_blocks, void* stream);
+/* synchronises `stream`; *timed_out = 1 if any wait on a peer expired since creation (results are then invalid). */
+int sr_exchange_status(sr_exchange* exchange, void* stream, int* timed_out);
+/* sr_model_apply_gradients with the exchange kernel in place of all-reduce + sr_adam_step: the exchange must have
+ * been created over the models' parameter arenas (params[rank] == the pointer given to sr_model_create). */
+int sr_model_apply_gradients_exchange(sr_model* model, sr_exchange* exchange, float* m, float* v, int t, float lr,
+                                      float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

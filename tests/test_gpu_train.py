@@ -348,17 +348,20 @@ allp = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(allp, mine)
 if rank == 0:
     print(json.dumps(dict(equal=bool(all(torch.equal(allp[0], p) for p in allp)), losses=losses,
-                          moved=float((mine - w0.cpu()).abs().max()))))
+                          moved=float((mine - w0.cpu()).abs().max()), p2p=tr.exchange is not None)))
     np.save(%(out)r, np.stack([w0.cpu().numpy(), mine.numpy()]))
 dist.barrier()
 dist.destroy_process_group()
 """
 
 
-def test_data_parallel_trainer_two_ranks_gloo_on_one_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_data_parallel_trainer_two_ranks_gloo_on_one_gpu(tmp_path, exchange):
     """sr100.train.Trainer itself under torch.distributed, world 2 (both ranks on the one GPU, gloo backend: NCCL
     refuses two ranks per device): replicas start from rank 0's weights (sync_replicas), stay bit-identical over
-    three steps, report the GLOBAL loss, and land where the single-process step on the whole batch lands."""
+    three steps, report the GLOBAL loss, and land where the single-process step on the whole batch lands.
+    exchange 'nccl' = all_reduce of the gradient arena + Adam (gloo carries it here); 'p2p' = the fused
+    reduce-scatter + Adam + all-gather kernel over CUDA-IPC-mapped arenas (csrc/exchange.cu)."""
     import json
     import socket
     import subprocess
@@ -372,14 +375,14 @@ def test_data_parallel_trainer_two_ranks_gloo_on_one_gpu(tmp_path):
     procs = []
     for rank in range(2):
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port))
+                   MASTER_PORT=str(port), SR100_EXCHANGE=exchange)
         procs.append(subprocess.Popen([_sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=600) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     rec = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
     assert rec["equal"], "replicas diverged"
-    assert rec["moved"] > 0
+    assert rec["moved"] > 0 and rec["p2p"] == (exchange == "p2p")
     w0, w_dp = np.load(out)
     # single process, whole batch, same start
     eng = Engine()

@@ -105,12 +105,15 @@ def main():
                fwd_bwd_ms=round(fb_ms, 3), update_ms=round(ms - fb_ms, 3),
                algorithmic_tflop_per_step_per_gpu=round(tr.step_flops(g) / 1e12, 3),
                tflops_per_gpu=round(tr.step_flops(g) / (ms * 1e-3) / 1e12, 1),
-               fwd_tflop=round(g.fwd_flops / 1e12, 3), bwd_tflop=round(g.bwd_flops / 1e12, 3), loss=loss,
+               loss=loss, sequencer=eng.sequencer,
                mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), data=a.data)
     if feed is not None:
         rec["dataset_pairs"] = a.dataset_size
         rec["first_batch_s"] = round(load_s, 2)
+    if hasattr(g, "fwd_flops"):
+        rec.update(fwd_tflop=round(g.fwd_flops / 1e12, 3), bwd_tflop=round(g.bwd_flops / 1e12, 3))
     if a.detail and rank == 0:
+        assert eng.sequencer == "python", "--detail times the Python launch lists: run with SR100_PY_SEQUENCE=1"
         st = __import__("sr100._lib", fromlist=["x"]).stream_ptr()
         parts = {}
         for label, lst in (("fwd", g.fwd), ("bwd", g.bwd)):

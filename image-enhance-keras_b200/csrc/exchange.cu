@@ -97,6 +97,9 @@ __device__ __forceinline__ float adam_one(float g, float& m, float& v, float p, 
   return p - P.lr_t * mi / (sqrtf(vi) + P.eps);
 }
 
+// W = world size, U = float4 elements per thread and iteration: U * W remote 16-byte loads are in flight per thread
+// (NVLink latency is paid once per iteration), 8 for every world size.
+template <int W, int U>
 __global__ void __launch_bounds__(kThreads) exchange_adam_kernel(const ExParams P) {
   unsigned* my = P.sig[P.rank];
   __shared__ unsigned s_epoch;
@@ -105,34 +108,41 @@ __global__ void __launch_bounds__(kThreads) exchange_adam_kernel(const ExParams 
   __syncthreads();
   const unsigned e = s_epoch;
   // ready: the gradient arena of this rank was completed by earlier kernels of this stream
-  if (blockIdx.x == 0 && threadIdx.x < P.world) st_release_sys(P.sig[threadIdx.x] + kReady + P.rank, e);
-  if (threadIdx.x < P.world) wait_flag(my + kReady + threadIdx.x, e, my + kStatus, P.timeout_ns);
+  if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(P.sig[threadIdx.x] + kReady + P.rank, e);
+  if (threadIdx.x < W) wait_flag(my + kReady + threadIdx.x, e, my + kStatus, P.timeout_ns);
   __syncthreads();
 
-  const int W = P.world;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i4 = P.lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < P.hi4; i4 += stride) {
-    const size_t i = i4 * 4;
-    float4 q[kMaxPeers];   // all W loads in flight together (remote latency is paid once per element, not W times)
+  const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+  for (size_t base = P.lo4 + (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < P.hi4; base += stride) {
+    float4 q[U][W];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r)
-      if (r < W) q[r] = ld_sys_f4(P.grads[r] + i);
-    float4 g = q[0];
+    for (int u = 0; u < U; ++u) {
+      const size_t i4 = base + (size_t)u * kThreads;
+      if (i4 < P.hi4) {
 #pragma unroll
-    for (int r = 1; r < kMaxPeers; ++r)
-      if (r < W) g.x += q[r].x, g.y += q[r].y, g.z += q[r].z, g.w += q[r].w;
-    float4 m = *reinterpret_cast<const float4*>(P.m + i);
-    float4 v = *reinterpret_cast<const float4*>(P.v + i);
-    float4 p = *reinterpret_cast<const float4*>(P.params[P.rank] + i);
-    p.x = adam_one(g.x, m.x, v.x, p.x, P);
-    p.y = adam_one(g.y, m.y, v.y, p.y, P);
-    p.z = adam_one(g.z, m.z, v.z, p.z, P);
-    p.w = adam_one(g.w, m.w, v.w, p.w, P);
-    *reinterpret_cast<float4*>(P.m + i) = m;
-    *reinterpret_cast<float4*>(P.v + i) = v;
+        for (int r = 0; r < W; ++r) q[u][r] = ld_sys_f4(P.grads[r] + i4 * 4);
+      }
+    }
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r)
-      if (r < W) *reinterpret_cast<float4*>(P.params[r] + i) = p;
+    for (int u = 0; u < U; ++u) {
+      const size_t i4 = base + (size_t)u * kThreads;
+      if (i4 >= P.hi4) break;
+      const size_t i = i4 * 4;
+      float4 g = q[u][0];
+#pragma unroll
+      for (int r = 1; r < W; ++r) g.x += q[u][r].x, g.y += q[u][r].y, g.z += q[u][r].z, g.w += q[u][r].w;
+      float4 m = *reinterpret_cast<const float4*>(P.m + i);
+      float4 v = *reinterpret_cast<const float4*>(P.v + i);
+      float4 p = *reinterpret_cast<const float4*>(P.params[P.rank] + i);
+      p.x = adam_one(g.x, m.x, v.x, p.x, P);
+      p.y = adam_one(g.y, m.y, v.y, p.y, P);
+      p.z = adam_one(g.z, m.z, v.z, p.z, P);
+      p.w = adam_one(g.w, m.w, v.w, p.w, P);
+      *reinterpret_cast<float4*>(P.m + i) = m;
+      *reinterpret_cast<float4*>(P.v + i) = v;
+#pragma unroll
+      for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(P.params[r] + i) = p;
+    }
   }
   // the last n % 4 floats belong to the last rank
   if (P.rank == W - 1 && blockIdx.x == 0 && threadIdx.x < (int)(P.n & 3)) {
@@ -283,7 +293,17 @@ extern "C" int sr_exchange_adam_step(sr_exchange* ex, float* m, float* v, int t,
   const size_t work = P.hi4 > P.lo4 ? P.hi4 - P.lo4 : 1;
   const size_t need = (work + kThreads - 1) / kThreads;
   if ((size_t)grid > need) grid = (int)need;
-  exchange_adam_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(P);
+  cudaStream_t st = as_stream(stream);
+  switch (P.world) {
+    case 1: exchange_adam_kernel<1, 4><<<grid, kThreads, 0, st>>>(P); break;
+    case 2: exchange_adam_kernel<2, 4><<<grid, kThreads, 0, st>>>(P); break;
+    case 3: exchange_adam_kernel<3, 2><<<grid, kThreads, 0, st>>>(P); break;
+    case 4: exchange_adam_kernel<4, 2><<<grid, kThreads, 0, st>>>(P); break;
+    case 5: exchange_adam_kernel<5, 1><<<grid, kThreads, 0, st>>>(P); break;
+    case 6: exchange_adam_kernel<6, 1><<<grid, kThreads, 0, st>>>(P); break;
+    case 7: exchange_adam_kernel<7, 1><<<grid, kThreads, 0, st>>>(P); break;
+    default: exchange_adam_kernel<8, 1><<<grid, kThreads, 0, st>>>(P); break;
+  }
   return check_launch("exchange_adam_kernel");
 }
 

@@ -174,6 +174,29 @@ __global__ void __launch_bounds__(kThreads) exchange_adam_kernel(const ExParams 
   }
 }
 
+// Barrier over the ranks' signal pads: "everything this rank launched before on this stream (its stores into peer
+// memory included) is done" -- one warp signals every peer and waits for every peer.
+struct BarrierParams {
+  unsigned* sig[kMaxPeers];
+  int rank, world;
+  unsigned long long timeout_ns;
+};
+
+__global__ void peer_barrier_kernel(const BarrierParams P) {
+  unsigned* my = P.sig[P.rank];
+  const unsigned e = *reinterpret_cast<volatile unsigned*>(my + kEpoch) + 1u;
+  __threadfence_system();
+  if (threadIdx.x < P.world) {
+    st_release_sys(P.sig[threadIdx.x] + kReady + P.rank, e);
+    wait_flag(my + kReady + threadIdx.x, e, my + kStatus, P.timeout_ns);
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned*>(my + kEpoch) = e;
+    __threadfence();
+  }
+}
+
 }  // namespace
 }  // namespace sr
 
@@ -253,7 +276,7 @@ extern "C" int sr_exchange_create(int rank, int world, size_t n, float* const* g
       return set_error(SR_ERR_INVALID, "sr_exchange_create: arenas must be 16-byte aligned");
   }
   sr_exchange* ex = new (std::nothrow) sr_exchange();
-  if (!ex) return set_error(SR_ERR_INVALID, "sr_exchange_create: out of memory");
+  if (!ex) return set_error(SR_ERR_NOMEM, "sr_exchange_create: out of memory");
   memset(&ex->P, 0, sizeof ex->P);
   for (int r = 0; r < world; ++r) {
     ex->P.grads[r] = grads[r];
@@ -313,6 +336,57 @@ extern "C" int sr_exchange_status(sr_exchange* ex, void* stream, int* timed_out)
   cudaError_t e = cudaMemcpyAsync(&s, ex->P.sig[ex->P.rank] + kStatus, sizeof s, cudaMemcpyDeviceToHost, as_stream(stream));
   if (e == cudaSuccess) e = cudaStreamSynchronize(as_stream(stream));
   if (e != cudaSuccess) return set_cuda_error(e, "sr_exchange_status");
+  *timed_out = (int)(s & 1u);
+  return SR_OK;
+}
+
+struct sr_peer_barrier {
+  BarrierParams P;
+  double timeout_ms;
+};
+
+extern "C" int sr_peer_barrier_create(int rank, int world, void* const* signals, sr_peer_barrier** out) {
+  if (!signals || !out) return set_error(SR_ERR_INVALID, "sr_peer_barrier_create: null argument");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return set_error(SR_ERR_INVALID, "sr_peer_barrier_create: world must be 1..8 and 0 <= rank < world");
+  sr_peer_barrier* b = new (std::nothrow) sr_peer_barrier();
+  if (!b) return set_error(SR_ERR_NOMEM, "sr_peer_barrier_create: out of memory");
+  memset(&b->P, 0, sizeof b->P);
+  for (int r = 0; r < world; ++r) {
+    if (!signals[r]) {
+      delete b;
+      return set_error(SR_ERR_INVALID, "sr_peer_barrier_create: null peer pointer");
+    }
+    b->P.sig[r] = reinterpret_cast<unsigned*>(signals[r]);
+  }
+  b->P.rank = rank, b->P.world = world;
+  b->timeout_ms = 30000.0;
+  *out = b;
+  return SR_OK;
+}
+
+extern "C" void sr_peer_barrier_destroy(sr_peer_barrier* b) { delete b; }
+
+extern "C" int sr_peer_barrier_set_timeout_ms(sr_peer_barrier* b, double ms) {
+  if (!b || !(ms > 0)) return set_error(SR_ERR_INVALID, "sr_peer_barrier_set_timeout_ms: bad argument");
+  b->timeout_ms = ms;
+  return SR_OK;
+}
+
+extern "C" int sr_peer_barrier_arrive_wait(sr_peer_barrier* b, void* stream) {
+  if (!b) return set_error(SR_ERR_INVALID, "sr_peer_barrier_arrive_wait: null argument");
+  BarrierParams P = b->P;
+  P.timeout_ns = (unsigned long long)(b->timeout_ms * 1e6);
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(P);
+  return check_launch("peer_barrier_kernel");
+}
+
+extern "C" int sr_peer_barrier_status(sr_peer_barrier* b, void* stream, int* timed_out) {
+  if (!b || !timed_out) return set_error(SR_ERR_INVALID, "sr_peer_barrier_status: null argument");
+  unsigned s = 0;
+  cudaError_t e = cudaMemcpyAsync(&s, b->P.sig[b->P.rank] + kStatus, sizeof s, cudaMemcpyDeviceToHost, as_stream(stream));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(as_stream(stream));
+  if (e != cudaSuccess) return set_cuda_error(e, "sr_peer_barrier_status");
   *timed_out = (int)(s & 1u);
   return SR_OK;
 }

@@ -224,6 +224,11 @@ SIGNATURES = {
     "sr_exchange_set_timeout_ms": (_i, [_vp, C.c_double]),
     "sr_exchange_adam_step": (_i, [_vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _i, _vp]),
     "sr_exchange_status": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "sr_peer_barrier_create": (_i, [_i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "sr_peer_barrier_destroy": (None, [_vp]),
+    "sr_peer_barrier_set_timeout_ms": (_i, [_vp, C.c_double]),
+    "sr_peer_barrier_arrive_wait": (_i, [_vp, _vp]),
+    "sr_peer_barrier_status": (_i, [_vp, _vp, C.POINTER(_i)]),
     "sr_model_apply_gradients_exchange": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
 }
 

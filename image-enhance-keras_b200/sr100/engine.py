@@ -684,7 +684,8 @@ class Engine:
 
     def forward_stitched(self, x, extents, tiles_dev, u8_buf, mul=255.0):
         """The conv stack over all patches x [N,H,W,3] with the quantise + stitch fused into the tail convs
-        (sr_forward_desc.stitch_*): patch n writes the pixels stitch tile n owns into u8_buf."""
+        (sr_forward_desc.stitch_*): patch n writes the pixels stitch tile n owns into u8_buf (a uint8 tensor, or a raw
+        device pointer -- e.g. rank 0's image mapped over NVLink, upscale_image_sharded)."""
         N, H, W, _ = x.shape
         nb = min(N, self.sub_batch(H, W))
         self.last_stages, self.last_calls = [], []
@@ -692,7 +693,8 @@ class Engine:
         for i in range(0, N, nb):
             n = min(nb, N - i)
             self._forward_c(x[i:i + n], None, None if extents is None else extents[i:i + n],
-                            stitch=(tiles_dev.data_ptr() + i * tsz, u8_buf.data_ptr(), float(mul)))
+                            stitch=(tiles_dev.data_ptr() + i * tsz,
+                                    u8_buf if isinstance(u8_buf, int) else u8_buf.data_ptr(), float(mul)))
 
     @staticmethod
     def stitch_tiles_host(metas, patch, step, scale, crop=8):
@@ -840,9 +842,6 @@ class Engine:
             off += n
         return res
 
-    sharded_gather_description = ("every rank stitches the pixels its tiles own into a uint8 column strip, the strips are "
-                                  "gathered on rank 0 (NCCL) and OR-ed into the image")
-
     def shard_plan(self, h, w, world, patch=96, step=64, scale=4):
         """[(tile_lo, tile_hi, x0, x1)] per rank for one h x w image, + the tile plan: contiguous ranges of the
         column-major live-tile index and the output columns each range can own."""
@@ -867,12 +866,15 @@ class Engine:
 
     def upscale_image_sharded(self, img_u8, patch=96, step=64, scale=4, world=None, rank=None, group_gather=None):
         """One (large) image with its tiles sharded over the ranks of the process group (BASELINE config
-        5): every rank runs a contiguous range of the column-major live-tile index through the conv stack and
-        stitches the pixels those tiles OWN into a uint8 column strip -- no exchange on the data path -- then the
-        strips (3 bytes per owned pixel, not 12-byte fp32 patches with their 2.25x overlap) are gathered on rank 0
-        (NCCL over NVLink) and OR-ed into the image: non-owned pixels of a strip are 0 and ownership is a partition,
-        so the result is bit-identical to the single-rank stitch.  Returns the uint8 [4h,4w,3] device image on
-        rank 0, None elsewhere.  (world / rank / group_gather: a logical split inside one process, for tests.)"""
+        5): every rank runs a contiguous range of the column-major live-tile index through the conv stack; the tail
+        convs' epilogues write the uint8 pixels those tiles OWN (3 bytes per owned pixel, not 12-byte fp32 patches
+        with their 2.25x overlap).  Default under NCCL ('p2p'): straight into rank 0's image, mapped into every
+        rank over NVLink peer memory (CUDA IPC) -- the transfer rides the tail convs' stores, one stream-ordered peer
+        barrier ends the step, there is no gather and no merge pass.  Otherwise (SR100_SHARD_GATHER=nccl, ranks on
+        several hosts): into a per-rank column strip, gathered on rank 0 and OR-ed into the image.  Ownership is a
+        partition (and non-owned strip pixels are 0), so both are bit-identical to the single-rank stitch.  Returns
+        the uint8 [4h,4w,3] device image on rank 0, None elsewhere.  (world / rank / group_gather: a logical split
+        inside one process, for tests.)"""
         import torch.distributed as tdist
         from . import ops
         h, w, _ = img_u8.shape
@@ -912,6 +914,27 @@ class Engine:
                                      want_u8=True)
             return u8
         lo, hi, x0, x1 = shards[rank]
+        if fused and group_gather is None and dist_on and self._peer_canvas_mode() == "p2p":
+            st = self._peer_canvas(scale * h * scale * w * 3)
+            if st is not None:
+                # every rank's tail convs store the pixels its tiles own straight into rank 0's image over NVLink
+                # (ownership is a partition: no two ranks write the same byte); one barrier says "all written",
+                # rank 0 copies the image out, a second barrier hands the canvas back for the next call
+                ptr, canvas, bar = st
+                key = ("p2p", h, w, patch, step, scale, lo, hi)
+                cached = self._stitch_cache.get(key)
+                if cached is None:
+                    rows, _, _ = self.stitch_tiles_host([(scale * h, scale * w, counts, 0)], patch, step, scale)
+                    if len(self._stitch_cache) >= 8:
+                        self._stitch_cache.pop(next(iter(self._stitch_cache)))
+                    cached = torch.from_numpy(np.ascontiguousarray(rows[lo:hi]).view(np.uint8)).to(self.device)
+                    self._stitch_cache[key] = cached
+                if hi > lo:
+                    self.forward_stitched(p[lo:hi], ext[lo:hi], cached, ptr)
+                bar.arrive_wait()
+                out = canvas[:scale * h * scale * w * 3].view(scale * h, scale * w, 3).clone() if rank == 0 else None
+                bar.arrive_wait()
+                return out
         wmax = max(s[3] - s[2] for s in shards)
         if fused:
             send = run_fused(lo, hi, x0, wmax)
@@ -930,6 +953,40 @@ class Engine:
             if rhi > rlo:
                 u8[:, rx0:rx1].bitwise_or_(strip[:, :rx1 - rx0])
         return u8
+
+    @staticmethod
+    def _peer_canvas_mode():
+        import torch.distributed as tdist
+        return os.environ.get("SR100_SHARD_GATHER") or ("p2p" if tdist.get_backend() == "nccl" else "nccl")
+
+    def _peer_canvas(self, nbytes):
+        """(canvas pointer valid in this process, rank 0's canvas tensor, PeerBarrier) -- rank 0's uint8 image mapped
+        into every rank with CUDA IPC (collective on first use and when a larger image arrives); None if the ranks do
+        not share a node or the mapping fails (the caller falls back to the strip gather, on every rank alike)."""
+        st = getattr(self, "_peer_canvas_state", None)
+        if st is not None and (st == "unavailable" or st[0] >= nbytes):
+            return None if st == "unavailable" else st[1:]
+        from . import peer
+        try:
+            ptr, canvas, bar = peer.connect_canvas(self.lib, self.device, nbytes)
+            self._peer_canvas_state = (nbytes, ptr, canvas, bar)
+            return ptr, canvas, bar
+        except RuntimeError as e:
+            import warnings
+            warnings.warn("sr100: %s; tile-sharded images use the strip gather" % e, RuntimeWarning)
+            self._peer_canvas_state = "unavailable"
+            return None
+
+    @property
+    def sharded_gather_description(self):
+        import torch.distributed as tdist
+        dist_on = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+        st = getattr(self, "_peer_canvas_state", None)
+        if dist_on and st is not None and st != "unavailable":
+            return ("every rank's tail convs store the uint8 pixels its tiles own straight into rank 0's image over "
+                    "NVLink peer memory (CUDA IPC), one stream-ordered peer barrier, no gather / merge pass")
+        return ("every rank stitches the pixels its tiles own into a uint8 column strip, the strips are gathered on "
+                "rank 0 (NCCL) and OR-ed into the image")
 
     def last_flops(self):
         """Algorithmic FLOPs (2*MAC) of the tensor-core launches of the most recent forward_device call."""

@@ -1,6 +1,10 @@
-"""Peer-memory plumbing of the training exchange (csrc/exchange.cu): one process per GPU on one node,
-every rank's gradient arena, parameter arena and signal pad mapped into every other rank with CUDA IPC, and the
-fused reduce-scatter + Adam + all-gather kernel (`sr_exchange_adam_step`) launched over them.
+"""Peer-memory plumbing: one process per GPU on one node, device buffers of every rank mapped into every
+other rank with CUDA IPC (sr_ipc_*), and the two things that run over them:
+
+* the training exchange (csrc/exchange.cu `sr_exchange_adam_step`): gradient arena, parameter arena and a signal pad of
+  every rank -> ONE fused reduce-scatter + Adam + all-gather kernel per rank;
+* the tile-sharded image (BASELINE config 5): rank 0's uint8 image mapped into every rank, written by every rank's tail
+  convs, closed by a stream-ordered `sr_peer_barrier`.
 
 torch.distributed is only the side channel that carries the 64-byte IPC handles (all_gather_object) and the barrier
 that orders set-up; no collective runs on the data path."""
@@ -97,3 +101,78 @@ def connect(lib, grads, params, group=None):
     ex = Exchange(lib, rank, world, n, ptrs["grads"], ptrs["params"], ptrs["signal"], keep=(grads, params, signal))
     dist.barrier(group=group)       # every pad is zeroed and mapped before the first step can signal
     return ex
+
+
+class PeerBarrier:
+    """Stream-ordered barrier over the ranks' signal pads (sr_peer_barrier_*)."""
+
+    def __init__(self, lib, rank, world, signal_ptrs, keep=()):
+        self.lib, self.rank, self.world = lib, rank, world
+        self.keep = list(keep)
+        self.handle = C.c_void_p()
+        arr = (C.c_void_p * world)(*[C.c_void_p(p) for p in signal_ptrs])
+        L.check(lib.sr_peer_barrier_create(rank, world, arr, C.byref(self.handle)))
+
+    def set_timeout_ms(self, ms):
+        L.check(self.lib.sr_peer_barrier_set_timeout_ms(self.handle, float(ms)))
+
+    def arrive_wait(self, stream=None):
+        L.check(self.lib.sr_peer_barrier_arrive_wait(self.handle, stream if stream is not None else L.stream_ptr()))
+
+    def timed_out(self):
+        flag = C.c_int()
+        L.check(self.lib.sr_peer_barrier_status(self.handle, L.stream_ptr(), C.byref(flag)))
+        return bool(flag.value)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.sr_peer_barrier_destroy(h)
+
+
+def _gather_and_open(lib, mine, keys, rank, world, group):
+    """all ranks' handle records -> per key the list of THIS process's pointers (own entry: the local pointer given in
+    mine['_own'][key]); collective, raises the same error on every rank."""
+    import socket
+    import torch.distributed as dist
+    own = mine.pop("_own")
+    mine["host"] = socket.gethostname()
+    table = [None] * world
+    dist.all_gather_object(table, mine, group=group)
+    err = None
+    ptrs = {k: [] for k in keys}
+    if any(t["host"] != mine["host"] for t in table):
+        err = "ranks are on different hosts"
+    else:
+        try:
+            for r, t in enumerate(table):
+                for k in keys:
+                    if t.get(k) is None:
+                        ptrs[k].append(0)
+                    else:
+                        ptrs[k].append(own[k] if r == rank else open_handle(lib, *t[k]))
+        except L.SrError as e:
+            err = str(e)
+    errs = [None] * world
+    dist.all_gather_object(errs, err, group=group)
+    if any(errs):
+        raise RuntimeError("peer memory: %s" % next(e for e in errs if e))
+    return ptrs
+
+
+def connect_canvas(lib, device, nbytes, group=None):
+    """Rank 0's uint8 canvas of `nbytes` mapped into every rank + a PeerBarrier over fresh signal pads.
+    Returns (pointer to the canvas valid in THIS process, canvas tensor on rank 0 / None elsewhere, barrier)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world > 8:
+        raise RuntimeError("peer memory covers one node (<= 8 ranks), got world size %d" % world)
+    signal = torch.zeros(lib.sr_exchange_signal_bytes() // 4, dtype=torch.int32, device=device)
+    canvas = torch.zeros(nbytes, dtype=torch.uint8, device=device) if rank == 0 else None
+    torch.cuda.synchronize(device)
+    mine = dict(signal=export_handle(lib, signal), canvas=export_handle(lib, canvas) if canvas is not None else None,
+                _own=dict(signal=signal.data_ptr(), canvas=canvas.data_ptr() if canvas is not None else 0))
+    ptrs = _gather_and_open(lib, mine, ("signal", "canvas"), rank, world, group)
+    bar = PeerBarrier(lib, rank, world, ptrs["signal"], keep=(signal, canvas))
+    dist.barrier(group=group)
+    return ptrs["canvas"][0], canvas, bar

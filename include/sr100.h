@@ -560,6 +560,17 @@ int sr_exchange_adam_step(sr_exchange* exchange, float* m, float* v, int t, floa
                           float eps, float grad_scale, int max_blocks, void* stream);
 /* synchronises `stream`; *timed_out = 1 if any wait on a peer expired since creation (results are then invalid). */
 int sr_exchange_status(sr_exchange* exchange, void* stream, int* timed_out);
+/* Stream-ordered barrier over the ranks' signal pads (each a zeroed buffer of sr_exchange_signal_bytes(), NOT shared
+ * with an sr_exchange): when the kernel retires on a rank, everything every rank launched before its own call --
+ * stores into peer memory included -- is complete.  Used by the tile-sharded image path (BASELINE config
+ * 5): every rank's tail convs store the uint8 pixels their tiles own (img_utils.py:700-722) straight into rank 0's
+ * image over NVLink (sr_forward_desc.stitch_u8 = the mapped pointer), then one barrier -- no gather, no merge pass. */
+typedef struct sr_peer_barrier sr_peer_barrier;
+int sr_peer_barrier_create(int rank, int world, void* const* signals, sr_peer_barrier** barrier);
+void sr_peer_barrier_destroy(sr_peer_barrier* barrier);
+int sr_peer_barrier_set_timeout_ms(sr_peer_barrier* barrier, double ms);
+int sr_peer_barrier_arrive_wait(sr_peer_barrier* barrier, void* stream);
+int sr_peer_barrier_status(sr_peer_barrier* barrier, void* stream, int* timed_out);
 /* sr_model_apply_gradients with the exchange kernel in place of all-reduce + sr_adam_step: the exchange must have
  * been created over the models' parameter arenas (params[rank] == the pointer given to sr_model_create). */
 int sr_model_apply_gradients_exchange(sr_model* model, sr_exchange* exchange, float* m, float* v, int t, float lr,

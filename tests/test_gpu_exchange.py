@@ -146,3 +146,52 @@ def test_two_processes_over_cuda_ipc(tmp_path):
     assert all(r["ok"] for r in recs), recs
     recs.sort(key=lambda r: r["rank"])
     assert recs[0]["lo"] == 0 and recs[0]["hi"] == recs[1]["lo"] and recs[1]["hi"] == 300007
+
+
+SHARD_WORKER = r"""
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "image-enhance-keras_b200"))
+torch.cuda.set_device(0)
+from sr100 import dist as D
+from sr100.engine import Engine, glorot_uniform_weights
+rank, local_rank, world = D.init_process_group(backend="gloo")
+eng = Engine(glorot_uniform_weights(seed=3))
+rng = np.random.default_rng(4)
+outs = []
+for (h, w) in ((150, 330), (100, 200), (150, 330)):        # a smaller image after a larger one reuses the mapped canvas
+    img = torch.from_numpy(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).cuda()
+    got = eng.upscale_image_sharded(img)
+    torch.cuda.synchronize()
+    if rank == 0:
+        want = eng.upscale_image_sharded(img, world=1, rank=0)
+        outs.append(bool(torch.equal(got, want)) and tuple(got.shape) == (4 * h, 4 * w, 3))
+    else:
+        assert got is None
+    dist.barrier()
+if rank == 0:
+    st = eng._peer_canvas_state
+    print(json.dumps(dict(equal=outs, p2p=st is not None and st != "unavailable", timed_out=st[3].timed_out())))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_tile_sharded_image_written_into_rank0_over_peer_memory():
+    """BASELINE config 5 with the peer-memory path on: two processes (ranks) on the test box's one GPU, rank 1's tail
+    convs store their owned pixels through a CUDA-IPC mapping of rank 0's image; bit-identical to one rank."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = SHARD_WORKER % dict(root=root)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), SR100_SHARD_GATHER="p2p")
+        procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    rec = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
+    assert rec["p2p"] and not rec["timed_out"] and rec["equal"] == [True, True, True], rec

@@ -641,7 +641,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < P.nch[s]; ++ch) {
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               // one box = 2 taps (an odd last tap drags in the next 128 rows, unused; OOB rows are zero-filled)
               const uint32_t slot = wr.slot, ph = wr.phase;
@@ -663,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const TileCoord c = decode_tile<T>(P, t);
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < P.nch[s]; ++ch) {
             const uint32_t slot = ac & 1, ph = (ac >> 1) & 1;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
             mbar_expect_tx(&bars->a_full[slot], strip_bytes);
@@ -710,7 +710,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int pk = (k - 1) / 2;
         const int ntaps = k * k;
         const int row_wrap = (P.PWs - (k - 1)) * (int)a_pix;  // (ky, k-1) -> (ky+1, 0)
-        for (int ch = 0; ch < NCH; ++ch) {
+        for (int ch = 0; ch < P.nch[s]; ++ch) {
           const uint32_t aslot = ac & 1, aph = (ac >> 1) & 1;
           mbar_wait(&bars->a_full[aslot], aph);
           tc_fence_after();
@@ -930,7 +930,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmW = s == 0 ? &tmW0 : &tmW1;
           const int ntaps = P.ksize[s] * P.ksize[s];
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < P.nch[s]; ++ch) {
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
               const uint32_t slot = wr.slot, ph = wr.phase;
               mbar_wait(&bars->w_empty[slot], ph ^ 1);
@@ -966,7 +966,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const TileCoord c = decode(pt, &live);
         for (int s = 0; s < P.nsrc; ++s) {
           const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < P.nch[s]; ++ch) {
             const uint32_t slot = ar.slot, ph = ar.phase;
             mbar_wait(&bars->a_empty[slot], ph ^ 1);
             if (SR_DBG(P, 2) && a_wrapped) {     // timing experiment: the strip buffer keeps whatever it held
@@ -1008,11 +1008,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int pk = (k - 1) / 2;
           const int ntaps = k * k;
           const int row_wrap = (P.PWs - (k - 1)) * 4;
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < P.nch[s]; ++ch) {
             const uint32_t aslot = ar.slot, aph = ar.phase;
             mbar_wait(&bars->a_full[aslot], aph);
             tc_fence_after();
-            if (it == 0 && s == 0 && leader) SR_STAMP(P, ch == 0 ? 2 : ch == NCH - 1 ? 12 : 13);
+            if (it == 0 && s == 0 && leader) SR_STAMP(P, ch == 0 ? 2 : ch == P.nch[s] - 1 ? 12 : 13);
             uint32_t a_lo = a_buf_lo + aslot * a_slot_step + (uint32_t)(c.off0 - pk * P.PWs - pk) * 4u;
             int kx = 0;
             for (int tap = 0; tap < ntaps; tap += kTapsPerStage) {
@@ -1766,6 +1766,15 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
     return set_error(SR_ERR_UNSUPPORTED, "fused stitch needs cout == 3 and a stitch_tiles table");
   }
   double macs = 0;
+  for (int s = 0; s < 2; ++s) {   // K chunks per source: channels >= cin_valid are zeros the launch never multiplies
+    const int che = tf32 ? PrecCfg<true>::kElems : kChunk;
+    const int cv = (s < d->nsrc && d->cin_valid[s] > 0) ? d->cin_valid[s] : kCin;
+    if (cv > kCin || cv % che != 0) {
+      delete pl;
+      return set_error(SR_ERR_INVALID, "cin_valid must be a multiple of the K chunk (32 bf16 / 16 tf32 channels), <= 128");
+    }
+    P.nch[s] = cv / che;
+  }
   for (int s = 0; s < d->nsrc; ++s) {
     int rc = make_a_map(&pl->tmA[s], d->in[s], d->NB, d->H, d->W, P.PWs, P.NR, pl->amode, tf32);
     if (rc == SR_OK)
@@ -1776,7 +1785,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
       delete pl;
       return rc;
     }
-    macs += (double)d->NB * Hc * Wc * d->ksize[s] * d->ksize[s] * kCin * d->cout;
+    macs += (double)d->NB * Hc * Wc * d->ksize[s] * d->ksize[s] * (d->cin_valid[s] > 0 ? d->cin_valid[s] : kCin) * d->cout;
   }
   if (d->nsrc == 1) {
     pl->tmA[1] = pl->tmA[0];
@@ -1896,7 +1905,7 @@ extern "C" int sr_conv_chain_create(const sr_conv_desc* descs, const int* phase,
     const sr_conv_desc* d = &descs[i];
     if (d->nsrc < 1 || d->nsrc > 2 || d->cin != kCin || d->cout != 128 || d->precision != 0 || d->a_mode != 0 ||
         d->shuffle_r > 0 || d->relu_mask_bf16 || d->colsum_f32 || d->relu == 2 || d->out_index || d->stitch_u8 ||
-        !d->out_bf16 || (d->res_bf16 && !d->res_f32) || (d->out_f32 && !d->res_f32) || d->NB < 1 || d->H < 1 || d->W < 1)
+        d->cin_valid[0] || d->cin_valid[1] || !d->out_bf16 || (d->res_bf16 && !d->res_f32) || (d->out_f32 && !d->res_f32) || d->NB < 1 || d->H < 1 || d->W < 1)
       return set_error(SR_ERR_UNSUPPORTED, "sr_conv_chain_create: 128 -> 128 bf16 convs with the plain (bf16 out) or "
                                            "fp32-residual epilogue only");
     if (i > 0 && (phase[i] < phase[i - 1] || phase[i] > phase[i - 1] + 1))

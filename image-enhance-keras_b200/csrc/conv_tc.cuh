@@ -45,6 +45,7 @@ enum ConvAMode : int {
 struct ConvKernelParams {
   int nsrc;          // 1 or 2 K-concatenated sources (second half of a 5/3 block)
   int ksize[2];
+  int nch[2];        // K chunks per source actually multiplied (sr_conv_desc.cin_valid; all of them by default)
   int H, W, NB;     // tensor dims (addressing, TMA bounds)
   int Hc, Wc;       // compute extents (<= H, W): pixels outside are neither produced nor stored
   int p;             // geometry halo = max (k-1)/2 over sources

@@ -49,6 +49,7 @@ class ConvDesc(C.Structure):
         ("stitch_tiles", C.c_void_p),
         ("stitch_u8", C.c_void_p),
         ("stitch_mul", C.c_float),
+        ("cin_valid", C.c_int * 2),
     ]
 
 

@@ -93,6 +93,7 @@ class _Net(_Stage):
                 d.ksize[i] = 3
             d.NB, d.H, d.W = shape
             d.cin, d.cout = NUMK, NUMK
+            d.cin_valid[1] = eng.C - NUMK if eng.skip_zero_k else 0    # 192 channels: plane 1 carries 64 real ones
             d.bias = eng.bias[(name, j)].data_ptr()
             d.alpha, d.beta, d.relu, d.leaky_slope = alpha, beta, relu, slope
             d.res_f32 = res32[j].data_ptr() if res32 is not None else None
@@ -113,6 +114,7 @@ class _Net(_Stage):
             d.ksize[i] = 3
         d.NB, d.H, d.W = shape
         d.cin, d.cout = NUMK, 3
+        d.cin_valid[1] = eng.C - NUMK if eng.skip_zero_k else 0
         d.bias = eng.master[name][1].data_ptr()
         d.alpha, d.beta, d.relu = 1.0, 0.0, 1
         d.out_f32 = self.out.data_ptr()
@@ -222,6 +224,9 @@ class PlaneNet:
         spec_fn, self.C, self.scale = ARCHS[arch]
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.use_graphs = use_graphs and os.environ.get("SR100_NO_GRAPHS", "0") != "1"
+        # the zero half of a 192-channel tensor's second plane is not multiplied (sr_conv_desc.cin_valid); the switch
+        # exists for the bit-for-bit test against the padded launches
+        self.skip_zero_k = self.C < 2 * NUMK and os.environ.get("SR100_SKIP_ZERO_K", "1") != "0"
         self.specs = spec_fn()
         self.names = [s[0] for s in self.specs]
         self.master, self.packed, self.bias = {}, {}, {}

@@ -119,6 +119,10 @@ typedef struct sr_conv_desc {
   const sr_stitch_tile* stitch_tiles;
   uint8_t* stitch_u8;
   float stitch_mul;
+  /* cin_valid[s] > 0: only the first cin_valid[s] input channels of source s are real (a multiple of 32; 16 for
+   * tf32), the rest of its 128 are zero padding that the launch does not load or multiply -- the second plane of a
+   * 192-channel tensor (Difvdsr, models.py:1274-1357) costs K = 64 instead of 128.  0: all 128. */
+  int cin_valid[2];
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;

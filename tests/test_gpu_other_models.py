@@ -104,6 +104,29 @@ def test_difvdsr_forward_matches_oracle():
     _check("difvdsr", om.difvdsr_specs, om.forward_difvdsr, (2, 14, 18, 3), gain=1.0)
 
 
+def test_difvdsr_skips_the_zero_half_of_its_second_plane(monkeypatch):
+    """192 channels = a full plane + a plane with 64 real channels: sr_conv_desc.cin_valid = 64 drops the two all-zero
+    K chunks of that plane from every launch (K = 192 instead of 256).  Zeros add nothing to an fp32 accumulator, so
+    the outputs equal the padded launches bit for bit -- single image (single-CTA kernel) and a batch (CTA pairs)."""
+    from oracle import other_models as om
+    from sr100.planenet import PlaneNet
+    weights = om.init_weights(om.difvdsr_specs(), seed=11, bias_scale=0.02, gain=1.0)
+    rng = np.random.default_rng(6)
+    for shape in ((1, 20, 12, 3), (3, 14, 18, 3)):
+        x = torch.from_numpy(rng.random(shape).astype(np.float32)).cuda()
+        eng = PlaneNet("difvdsr", weights)
+        assert eng.skip_zero_k
+        got = eng.forward_device(x)
+        flops_skip = eng.net(*shape[:3]).conv_flops
+        monkeypatch.setenv("SR100_SKIP_ZERO_K", "0")
+        ref = PlaneNet("difvdsr", weights)
+        monkeypatch.delenv("SR100_SKIP_ZERO_K")
+        assert not ref.skip_zero_k
+        want = ref.forward_device(x)
+        assert torch.equal(got, want)
+        assert flops_skip < 0.80 * ref.net(*shape[:3]).conv_flops      # 192/256 of the K work
+
+
 def test_model_constructors_predict_weights_and_tiling(tmp_path, monkeypatch):
     """models.Difvdsr4 / models.Difvdsr behind the reference API: create_model, predict, get/set_weights, .h5 round
     trip (Difvdsr always loads its file, models.py:1322), upscaleStepPatch through the generic tiler."""

@@ -24,6 +24,20 @@ int set_cuda_error(cudaError_t e, const char* where) {
 
 extern "C" const char* sr_last_error_string(void) { return sr::g_err; }
 
+namespace sr {
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+}  // namespace sr
+
+// 1 (default): the tensor-core kernels are launched with programmatic stream serialization (see internal.h);
+// 0: plain stream-ordered launches.  Same results either way; takes effect for launches (and graph captures) made
+// afterwards.  Returns the previous setting.
+extern "C" int sr_set_pdl(int enabled) {
+  const int prev = sr::g_pdl;
+  sr::g_pdl = enabled ? 1 : 0;
+  return prev;
+}
+
 extern "C" int sr_version(void) { return 100; }
 
 // 1 when the library was compiled with -DSR_DEV_SWITCHES (timing-only environment switches that can change

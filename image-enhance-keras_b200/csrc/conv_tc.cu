@@ -623,6 +623,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tmem_alloc(&bars->tmem_base, TM_COLS);
     tmem_relinquish();
   }
+  griddep_wait();   // everything above overlapped the predecessor's tail; every global access comes after this
   if (threadIdx.x >= 128) {
     for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
     if constexpr (EPI == 4)
@@ -631,6 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
@@ -900,6 +902,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tmem_alloc_pair(&bars->tmem_base, TM_COLS);
     tmem_relinquish_pair();
   }
+  griddep_wait();   // everything above overlapped the predecessor's tail; every global access comes after this
   if (threadIdx.x >= 128) {
     for (int i = threadIdx.x - 128; i < N_; i += 128) s_bias[i] = (i < P.cout && P.bias) ? P.bias[i] : 0.f;
     if constexpr (EPI == 4)
@@ -908,6 +911,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  griddep_launch_dependents();
   const uint32_t tmem_base = bars->tmem_base;
   if (threadIdx.x == 0) SR_STAMP(P, 1);
 
@@ -1569,9 +1573,8 @@ static int launch_variant(const ConvPlan* pl, cudaStream_t stream) {
   auto kern = conv_tc_kernel<N_, AMODE, NACC, NBUF, EPI, TF32, CS>;
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_kernel)")) return rc;
-  kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
-                                                           pl->tmW[1], pl->P);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, pl->grid, kConvThreads, pl->smem_bytes, stream, pl->tmA[0], pl->tmW[0], pl->tmA[1],
+                             pl->tmW[1], pl->P);
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
   return SR_OK;
 }
@@ -1581,9 +1584,8 @@ static int launch_pair(const ConvPlan* pl, cudaStream_t stream) {
   auto kern = conv_tc_pair_kernel<NACC, NBUF, EPI, TF32, CS>;
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(kern, (int)kSmemBudget, &attr_done, "cudaFuncSetAttribute(conv_tc_pair_kernel)")) return rc;
-  kern<<<pl->grid, kConvThreads, pl->smem_bytes, stream>>>(pl->tmA[0], pl->tmW[0], pl->tmA[1],
-                                                           pl->tmW[1], pl->P);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, pl->grid, kConvThreads, pl->smem_bytes, stream, pl->tmA[0], pl->tmW[0], pl->tmA[1],
+                             pl->tmW[1], pl->P);
   if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_pair_kernel launch");
   return SR_OK;
 }

@@ -47,6 +47,26 @@ inline unsigned long long* dev_timeline() { return nullptr; }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch of the tensor-core kernels (sr_set_pdl; default on): the kernel may become resident
+// while its predecessor in the stream drains, so its set-up (barriers, TMEM allocation, descriptor prefetch) and the
+// launch latency leave the critical path; the kernels call griddep_wait() before their first global access.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: `done` is the caller's per-kernel bit
 // mask of the devices it has been applied on (a process normally drives one GPU, but nothing here assumes it).
 template <typename Kern>

@@ -116,6 +116,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
                "r"(ncols)
                : "memory");
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still running; griddep_wait() returns once the predecessor (and,
+// transitively, everything before it) has completed and its writes are visible -- every global access of the kernel
+// comes after it.  griddep_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this
+// grid has issued it (or exited).  Both are no-ops for a plain launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_relinquish() {
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }

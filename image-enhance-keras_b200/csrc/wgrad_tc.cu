@@ -126,9 +126,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tmem_alloc(&bars->tmem_base, 512);
     tmem_relinquish();
   }
+  griddep_wait();   // programmatic dependent launch: the set-up above overlapped the predecessor's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();
   const uint32_t tmem_base = bars->tmem_base;
 
   auto decode = [&](int u, int* n, int* x0, int* y0, int* rows) {
@@ -320,6 +322,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 // dW[tap][ci][co] (= HWIO) = beta * dW + scale * sum over the CTAs of the tap's group of their partials.
 __global__ void wgrad_reduce_kernel(const WgradParams P, float scale, float beta, float* __restrict__ dw) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int total4 = P.k * P.k * kAccFloats / 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const int tap = i / (kAccFloats / 4);
@@ -615,11 +619,11 @@ extern "C" int sr_wgrad_plan_run(sr_wgrad_plan* plan, void* stream) {
   static unsigned long long attr_done = 0;
   if (int rc = ensure_dynamic_smem(wgrad_tc_kernel, (int)kWgSmemBudget, &attr_done, "cudaFuncSetAttribute(wgrad_tc_kernel)"))
     return rc;
-  wgrad_tc_kernel<<<pl->grid, kWgThreads, pl->smem_bytes, st>>>(pl->tmX, pl->tmG, pl->P);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(wgrad_tc_kernel, pl->grid, kWgThreads, pl->smem_bytes, st, pl->tmX, pl->tmG, pl->P);
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad_tc_kernel launch");
-  wgrad_reduce_kernel<<<296, 256, 0, st>>>(pl->P, pl->scale, pl->beta, pl->dw);
-  return check_launch("wgrad_reduce_kernel launch");
+  e = launch_pdl(wgrad_reduce_kernel, 296u, 256u, 0, st, pl->P, pl->scale, pl->beta, pl->dw);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad_reduce_kernel launch");
+  return SR_OK;
 }
 
 extern "C" void sr_wgrad_plan_destroy(sr_wgrad_plan* plan) { delete reinterpret_cast<WgradPlan*>(plan); }

@@ -215,6 +215,7 @@ SIGNATURES = {
     "sr_model_train_info": (_i, [_vp, C.POINTER(TrainDesc), C.POINTER(ModelRunInfo)]),
     "sr_model_apply_gradients": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
     "sr_model_train_step": (_i, [_vp, C.POINTER(TrainDesc), _vp, _vp, _i, _f, _f, _f, _f, _vp]),
+    "sr_set_pdl": (_i, [_i]),
     "sr_ipc_export": (_i, [_vp, C.c_char_p, C.POINTER(_sz)]),
     "sr_ipc_open": (_i, [C.c_char_p, _sz, C.POINTER(_vp)]),
     "sr_ipc_close": (_i, [_vp, _sz]),
@@ -255,6 +256,8 @@ def load():
             raise SrError(-1, "%s: ctypes layout (%d bytes) does not match libsr100.so (%d bytes); rebuild the "
                               "library or update sr100/_lib.py" % (struct.__name__, C.sizeof(struct),
                                                                    lib.sr_abi_struct_size(which)))
+    if os.environ.get("SR100_PDL", "1") == "0":      # A/B switch: plain stream-ordered launches of the conv kernels
+        lib.sr_set_pdl(0)
     _lib = lib
     return lib
 

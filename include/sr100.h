@@ -35,6 +35,11 @@ int sr_device_supported(void);
  * SR100_CONV_DBG can make kernels skip operand loads, i.e. give wrong results for timing experiments); the
  * default build returns 0 and reads no environment variable that can change a result. */
 int sr_dev_switches(void);
+/* Programmatic dependent launch of the tensor-core kernels (default 1): a conv / wgrad launch may become resident
+ * while its predecessor in the stream drains (its set-up and the launch latency leave the critical path; the kernels
+ * wait for the predecessor before their first global access).  0: plain stream-ordered launches; same results.
+ * Applies to launches and graph captures made afterwards; returns the previous setting. */
+int sr_set_pdl(int enabled);
 /* Development build only (SR_ERR_UNSUPPORTED otherwise): conv plans created after this call stamp per-CTA phase clocks
  * (16 x uint64 per CTA) into `buf` -- the intra-kernel timeline behind profiles/r02_probe_timeline*.json. */
 int sr_dev_set_timeline(void* buf);

@@ -39,6 +39,8 @@ case(name="perf_k5_lr48", k=5, NB=256, H=48, W=48, iters=10, check=False)
 case(name="perf_k3_hr192", k=3, NB=32, H=192, W=192, iters=5, check=False)
 case(name="perf_k5_hr192", k=5, NB=32, H=192, W=192, iters=5, check=False)
 case(name="perf_k5_lr96", k=5, NB=148, H=96, W=96, iters=5, check=False)
+case(name="perf_k5_hr192_nb256", k=5, NB=256, H=192, W=192, iters=5, check=False)   # the training step's HR shape
+case(name="perf_k3_hr192_nb256", k=3, NB=256, H=192, W=192, iters=5, check=False)
 
 
 def run_case(idx):

@@ -206,3 +206,88 @@ def test_bf16_operand_emulation_is_the_same_graph():
         worst = max(worst, rel, relb)
         assert rel <= 3e-2 and relb <= 3e-2, (name, rel, relb)
     assert worst > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Cross-checks of the float-path restatements against INDEPENDENT implementations that are installed here (scipy,
+# torch.optim, numpy).  Keras 2 / TF 1 / skimage themselves are not installable offline, so what stays
+# unpinned after these is only the library's documented *definition* (which coordinates TF1's legacy bilinear samples,
+# where Keras puts epsilon), not the arithmetic that follows from it.
+
+def test_bilinear_restatement_equals_scipy_linear_interpolation():
+    """tf.image.resize_bilinear (TF1 default: align_corners=False, no half-pixel centres) samples the source at
+    dst * (in / out) and clamps at the far edge: scipy.ndimage.map_coordinates(order=1, mode='nearest') evaluated
+    at exactly those coordinates is an independent implementation of the same interpolation."""
+    import torch
+    from scipy.ndimage import map_coordinates
+    rng = np.random.default_rng(3)
+    for h, w in ((5, 7), (12, 9), (1, 4)):
+        x = rng.random((h, w))
+        got = om.bilinear_x4_tf1(torch.from_numpy(x).reshape(1, 1, h, w))[0, 0].numpy()
+        yy, xx = np.meshgrid(np.arange(4 * h) * 0.25, np.arange(4 * w) * 0.25, indexing="ij")
+        want = map_coordinates(x, [yy, xx], order=1, mode="nearest")
+        assert got.shape == want.shape == (4 * h, 4 * w)
+        assert np.abs(got - want).max() <= 1e-12
+
+
+def test_keras_adam_restatement_equals_torch_adam_up_to_epsilon_placement():
+    """Keras 2: p -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps).  torch.optim.Adam divides sqrt(v) by
+    sqrt(1 - b2^t) BEFORE adding its eps, i.e. it is the same update with eps_torch = eps_keras / sqrt(1 - b2^t):
+    feeding torch that per-step epsilon must reproduce the restatement step for step."""
+    import math
+    import torch
+    rng = np.random.default_rng(5)
+    p0 = rng.standard_normal(257)
+    pk = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    pt = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-7
+    keras = om.KerasAdam([pk], lr=lr, beta_1=b1, beta_2=b2, epsilon=eps)
+    ref = torch.optim.Adam([pt], lr=lr, betas=(b1, b2), eps=eps)
+    for t in range(1, 8):
+        g = torch.from_numpy(rng.standard_normal(257) * 10.0 ** rng.integers(-6, 1))
+        keras.step([g])
+        ref.param_groups[0]["eps"] = eps / math.sqrt(1.0 - b2 ** t)
+        pt.grad = g.clone()
+        ref.step()
+        assert float((pk.detach() - pt.detach()).abs().max()) <= 1e-12, t
+
+
+def test_ssim_restatement_equals_window_by_window_definition():
+    """compare_ssim(win_size=7, uniform window, use_sample_covariance=True, data_range=255): for every 7x7 window
+    the sample means / variances / covariance straight from numpy (np.var / np.cov with ddof=1), the SSIM formula of
+    Wang et al. with K1 = 0.01, K2 = 0.03, and the mean over all windows that lie inside the image (= the map
+    cropped by 3 px) -- against the filtered-moments form the oracle (like skimage) evaluates."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    rng = np.random.default_rng(9)
+    x = rng.integers(0, 256, size=(19, 23)).astype(np.float64)
+    y = np.clip(x + rng.normal(0, 12, size=x.shape), 0, 255)
+    wx = sliding_window_view(x, (7, 7)).reshape(-1, 49)
+    wy = sliding_window_view(y, (7, 7)).reshape(-1, 49)
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    vals = []
+    for a, b in zip(wx, wy):
+        ux, uy = a.mean(), b.mean()
+        vx, vy = a.var(ddof=1), b.var(ddof=1)
+        vxy = np.cov(a, b, ddof=1)[0, 1]
+        vals.append((2 * ux * uy + c1) * (2 * vxy + c2) / ((ux * ux + uy * uy + c1) * (vx + vy + c2)))
+    assert abs(osc.ssim(x, y, 255.0) - float(np.mean(vals))) <= 1e-10
+    rgb_a = rng.integers(0, 256, size=(15, 16, 3)).astype(np.float64)
+    rgb_b = np.clip(rgb_a + rng.normal(0, 5, size=rgb_a.shape), 0, 255)
+    per = [osc.ssim(rgb_a[..., c], rgb_b[..., c], 255.0) for c in range(3)]
+    assert abs(osc.ssim(rgb_a, rgb_b, 255.0, multichannel=True) - float(np.mean(per))) <= 1e-15
+
+
+def test_mse_and_glorot_follow_their_keras_definitions():
+    """loss='mse' = mean over ALL elements (keras.losses.mean_squared_error averaged over the batch);
+    glorot_uniform = U(+-sqrt(6 / (fan_in + fan_out))) with fan = kh * kw * channels (keras.initializers)."""
+    import torch
+    rng = np.random.default_rng(1)
+    a, b = rng.random((2, 8, 8, 3)), rng.random((2, 8, 8, 3))
+    assert abs(float(om.mse_loss(torch.from_numpy(a), torch.from_numpy(b))) - float(((a - b) ** 2).mean())) <= 1e-15
+    w = om.init_weights(3)
+    for name, k, cin, cout in om.layer_specs():
+        kern, bias = w[name]
+        limit = np.sqrt(6.0 / (k * k * cin + k * k * cout))
+        assert kern.shape == (k, k, cin, cout) and np.abs(kern).max() <= limit and not bias.any()
+        if kern.size > 10000:
+            assert np.abs(kern).max() >= 0.99 * limit and abs(kern.mean()) <= 0.02 * limit

@@ -151,8 +151,9 @@ __device__ __forceinline__ void epilogue_staged_acc_generic(const ConvKernelPara
       const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (!(__uint_as_float(mw[e] << 16) > 0.f)) o[2 * e] = 0.f;
-        if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f)) o[2 * e + 1] = 0.f;
+        if (!(__uint_as_float(mw[e] << 16) > 0.f)) o[2 * e] = P.mask_slope == 0.f ? 0.f : o[2 * e] * P.mask_slope;
+        if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.f))
+          o[2 * e + 1] = P.mask_slope == 0.f ? 0.f : o[2 * e + 1] * P.mask_slope;
       }
     }
     if (P.out_f32) {
@@ -1598,7 +1599,7 @@ using namespace sr;
 static int epilogue_kind(const ConvKernelParams& P) {
   const int nops = (P.res_f32 ? 1 : 0) + ((P.res_bf16 && !P.res_f32) ? 1 : 0) + (P.relu_mask_bf16 ? 1 : 0);
   const bool plain = nops == 0 && !P.shuffle_r && P.out_bf16 && !P.out_f32 && P.relu != 2;
-  return P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;
+  return P.shuffle_r ? 4 : plain ? 0 : (nops != 1 || P.relu == 2 || P.mask_slope != 0.f) ? -1 : P.res_f32 ? 1 : P.res_bf16 ? 2 : 3;
 }
 
 extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
@@ -1617,7 +1618,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   if (d->relu == 2 && (d->cout != 128 || d->shuffle_r > 0))
     return set_error(SR_ERR_UNSUPPORTED, "LeakyReLU epilogue: cout == 128, no shuffle");
   if (d->colsum_f32 && (d->cout != 128 || !d->out_bf16 || d->precision == 1 || d->shuffle_r > 0 || d->a_mode == 1 ||
-                        d->relu == 2 || d->nacc != 2 ||
+                        d->relu == 2 || d->nacc != 2 || (d->relu_mask_bf16 && d->relu_mask_slope != 0.f) ||
                         ((d->res_f32 ? 1 : 0) + ((d->res_bf16 && !d->res_f32) ? 1 : 0) + (d->relu_mask_bf16 ? 1 : 0)) != 1))
     return set_error(SR_ERR_UNSUPPORTED, "colsum_f32: bf16 128-channel output with exactly one of residual / relu mask, nacc 2, a_mode 0");
   const int tf32 = d->precision == 1 ? 1 : 0;
@@ -1693,6 +1694,7 @@ extern "C" int sr_conv_plan_create(const sr_conv_desc* d, sr_conv_plan** out) {
   P.out_f32 = d->out_f32;
   P.relu = d->relu;
   P.relu_mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d->relu_mask_bf16);
+  P.mask_slope = d->relu_mask_bf16 ? d->relu_mask_slope : 0.f;
   P.shuffle_r = d->shuffle_r > 0 ? d->shuffle_r : 0;
   // Launches of less than one wave (a single small image: BASELINE config 1's LR stage is 65 tiles of 256 positions
   // on 148 SMs): halve the tile to T = 128 (one accumulator, four TMEM buffers) on CTA pairs -- a single image is

@@ -70,6 +70,7 @@ struct ConvKernelParams {
   int cout;          // real output channels (128; 3 for the tail conv)
   // dgrad-time ReLU mask: if non-null, out *= (mask > 0)
   const __nv_bfloat16* relu_mask_bf16;
+  float mask_slope;  // factor where the mask is <= 0 (0 = ReLU backward; LeakyReLU backward: generic epilogue only)
   // cout <= 16 path only: image n is written to slot out_index[n] of a tensor of out_H x out_W pixel images
   const int* out_index;
   int out_H, out_W;

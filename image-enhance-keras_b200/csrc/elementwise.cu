@@ -157,26 +157,29 @@ bilinear4_fwd_kernel(const void* __restrict__ in, const int* __restrict__ src_in
   }
 }
 
-// weight with which HR index Q (0..4n-1) samples LR index q, along one axis
+// weight with which HR index Q (0..F*n-1) samples LR index q, along one axis (F = 4 or 2)
+template <int F>
 __device__ __forceinline__ float axis_weight(int Q, int q, int n) {
-  const int lo = Q >> 2;
-  const int fr = Q & 3;
+  const int lo = Q / F;
+  const int fr = Q - lo * F;
   const int hi = fr == 0 ? lo : min(lo + 1, n - 1);
-  const float t = (float)fr * 0.25f;
+  const float t = (float)fr * (1.f / F);
   float w = 0.f;
   if (lo == q) w += 1.f - t;
   if (hi == q) w += t;
   return w;
 }
 
-// Adjoint (gather form, deterministic): gin[y,x] = sum_{Y,X} wy(Y,y) wx(X,x) gout[Y,X] over the 7x7 HR
-// window [4y-3,4y+3] x [4x-3,4x+3].  A warp covers the 128 channels of one pixel (512 B per load); the seven
-// loads of a window row are issued together.
+// Adjoint (gather form, deterministic): gin[y,x] = sum_{Y,X} wy(Y,y) wx(X,x) gout[Y,X] over the (2F-1)^2 HR
+// window [Fy-(F-1),Fy+(F-1)] x [Fx-(F-1),Fx+(F-1)] (7x7 for x4, 3x3 for x2).  A warp covers the 128 channels of
+// one pixel (512 B per load); the loads of a window row are issued together.
+template <int F>
 __global__ void __launch_bounds__(256)
 bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, int H, int W, int C,
                      float4* __restrict__ gin) {
+  constexpr int WN = 2 * F - 1;
   const int C4 = C >> 2;
-  const int OH = 4 * H, OW = 4 * W;
+  const int OH = F * H, OW = F * W;
   const size_t total = (size_t)NB * H * W * C4;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -186,27 +189,27 @@ bilinear4_bwd_kernel(const float4* __restrict__ gout, int NB, int H, int W, int 
     r /= W;
     const int y = (int)(r % H);
     const int n = (int)(r / H);
-    float wx[7];
-    int xi[7];
+    float wx[WN];
+    int xi[WN];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int X = 4 * x - 3 + j;
+    for (int j = 0; j < WN; ++j) {
+      const int X = F * x - (F - 1) + j;
       const bool ok = X >= 0 && X < OW;
-      xi[j] = ok ? X : 4 * x;
-      wx[j] = ok ? axis_weight(X, x, W) : 0.f;
+      xi[j] = ok ? X : F * x;
+      wx[j] = ok ? axis_weight<F>(X, x, W) : 0.f;
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int Y = 4 * y - 3 + i;
+    for (int i = 0; i < WN; ++i) {
+      const int Y = F * y - (F - 1) + i;
       if (Y < 0 || Y >= OH) continue;
-      const float wy = axis_weight(Y, y, H);
+      const float wy = axis_weight<F>(Y, y, H);
       const float4* row = gout + ((size_t)n * OH + Y) * OW * C4 + c4;
-      float4 g[7];
+      float4 g[WN];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) g[j] = row[(size_t)xi[j] * C4];
+      for (int j = 0; j < WN; ++j) g[j] = row[(size_t)xi[j] * C4];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
+      for (int j = 0; j < WN; ++j) {
         const float wgt = wy * wx[j];
         acc.x = fmaf(wgt, g[j].x, acc.x);
         acc.y = fmaf(wgt, g[j].y, acc.y);
@@ -893,9 +896,18 @@ extern "C" int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, 
   if (!gout || !gin) return set_error(SR_ERR_INVALID, "sr_bilinear4_bwd: null pointer");
   if (C % 4 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear4_bwd: C must be a multiple of 4");
   const size_t total = (size_t)NB * H * W * (C / 4);
-  bilinear4_bwd_kernel<<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+  bilinear4_bwd_kernel<4><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(gout), NB, H, W, C, reinterpret_cast<float4*>(gin));
   return check_launch("bilinear4_bwd_kernel");
+}
+
+extern "C" int sr_bilinear2_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream) {
+  if (!gout || !gin) return set_error(SR_ERR_INVALID, "sr_bilinear2_bwd: null pointer");
+  if (C % 4 != 0) return set_error(SR_ERR_UNSUPPORTED, "sr_bilinear2_bwd: C must be a multiple of 4");
+  const size_t total = (size_t)NB * H * W * (C / 4);
+  bilinear4_bwd_kernel<2><<<grid_for(total, kBlock, 148 * 32), kBlock, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(gout), NB, H, W, C, reinterpret_cast<float4*>(gin));
+  return check_launch("bilinear2_bwd_kernel");
 }
 
 extern "C" int sr_patch_count(int dim, int patch, int step) {

@@ -50,6 +50,7 @@ class ConvDesc(C.Structure):
         ("stitch_u8", C.c_void_p),
         ("stitch_mul", C.c_float),
         ("cin_valid", C.c_int * 2),
+        ("relu_mask_slope", C.c_float),
     ]
 
 
@@ -216,6 +217,7 @@ SIGNATURES = {
     "sr_model_apply_gradients": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _vp]),
     "sr_model_train_step": (_i, [_vp, C.POINTER(TrainDesc), _vp, _vp, _i, _f, _f, _f, _f, _vp]),
     "sr_set_pdl": (_i, [_i]),
+    "sr_bilinear2_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sr_ipc_export": (_i, [_vp, C.c_char_p, C.POINTER(_sz)]),
     "sr_ipc_open": (_i, [C.c_char_p, _sz, C.POINTER(_vp)]),
     "sr_ipc_close": (_i, [_vp, _sz]),

@@ -149,13 +149,15 @@ class Model:
 
     def _get_trainer(self):
         if self._trainer is None:
-            if not isinstance(self.engine, Engine):
-                raise NotImplementedError("training is implemented for the DifvdsrDouble graph only (SURVEY.md 8a-7); "
-                                          "Difvdsr4 / Difvdsr run inference")
-            from .train import Trainer
             opt = self.optimizer
-            self._trainer = Trainer(self.engine, lr=getattr(opt, "lr", 1e-4), beta_1=getattr(opt, "beta_1", 0.9),
-                                    beta_2=getattr(opt, "beta_2", 0.999), epsilon=getattr(opt, "epsilon", 1e-7))
+            kw = dict(lr=getattr(opt, "lr", 1e-4), beta_1=getattr(opt, "beta_1", 0.9),
+                      beta_2=getattr(opt, "beta_2", 0.999), epsilon=getattr(opt, "epsilon", 1e-7))
+            if isinstance(self.engine, Engine):
+                from .train import Trainer
+                self._trainer = Trainer(self.engine, **kw)
+            else:                                   # Difvdsr4 / Difvdsr (models.py:1079-1080, 1332-1333)
+                from .planetrain import PlaneTrainer
+                self._trainer = PlaneTrainer(self.engine, **kw)
         return self._trainer
 
     def train_on_batch(self, x, y):

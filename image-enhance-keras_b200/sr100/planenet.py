@@ -115,7 +115,7 @@ class _Net(_Stage):
         d.NB, d.H, d.W = shape
         d.cin, d.cout = NUMK, 3
         d.cin_valid[1] = eng.C - NUMK if eng.skip_zero_k else 0
-        d.bias = eng.master[name][1].data_ptr()
+        d.bias = eng.bias[(name, 0)].data_ptr()
         d.alpha, d.beta, d.relu = 1.0, 0.0, 1
         d.out_f32 = self.out.data_ptr()
         d.a_mode, d.nacc, d.pair = 0, 2, 0
@@ -190,7 +190,7 @@ class _Net(_Stage):
         t16, d16, d32, r32 = self.planes(shape, bf), self.planes(shape, bf), self.planes(shape, f32), self.planes(shape, f32)
         head = torch.empty(NB, H, W, C, device=eng.device, dtype=f32)
         self.keep.append(head)
-        w0, b0 = eng.master["level1"]
+        w0, b0 = eng.blocks[("level1", 0, 0)], eng.bias[("level1", 0)]
         self.steps.append(lambda st: L.check(lib.sr_conv2d_direct(          # level1: 3x3, 3 -> 192, ReLU (:1304)
             L.ptr(self.x_in), 0, L.ptr(w0), 0, L.ptr(b0), NB, H, W, 3, C, 3, 1, 1, 0, 0, L.ptr(head), st)))
 
@@ -213,7 +213,15 @@ class _Net(_Stage):
 
 
 class PlaneNet:
-    """Device-resident weights of Difvdsr4 / Difvdsr + cached per-shape launch lists."""
+    """Device-resident weights of Difvdsr4 / Difvdsr + cached per-shape launch lists.
+
+    Parameters live in ONE flat fp32 arena, stored the way the kernels consume them: a C -> C kernel as its four
+    dense [k,k,128,128] plane blocks (input plane i, output plane j; rows / columns beyond C are zero and stay zero),
+    a bias as two [128] blocks, the Difvdsr4 head as two [3,128] matrices, the tail as two [k,k,128,3] blocks; only
+    the 3-channel Difvdsr head stays a dense Keras kernel (it runs on the direct conv).  Packing for the tensor
+    cores is then one batched launch over dense blocks, and training (sr100.planetrain) writes filter gradients
+    straight into a gradient arena of the same layout and updates everything with one Adam launch.
+    get_weights_dict / set_weights_dict convert to and from the Keras HWIO tensors."""
 
     def __init__(self, arch, weights=None, device=None, use_graphs=True, max_cached=4):
         import os
@@ -229,20 +237,54 @@ class PlaneNet:
         self.skip_zero_k = self.C < 2 * NUMK and os.environ.get("SR100_SKIP_ZERO_K", "1") != "0"
         self.specs = spec_fn()
         self.names = [s[0] for s in self.specs]
-        self.master, self.packed, self.bias = {}, {}, {}
-        self._scratch = {}
+        self.ksize = {s[0]: s[1] for s in self.specs}
+        # ---- arena layout: name -> [(kind, key, offset, shape)]
+        self.layout, off = {}, 0
+
+        def add(name, kind, key, shape):
+            nonlocal off
+            n = int(np.prod(shape))
+            self.layout.setdefault(name, []).append((kind, key, off, tuple(shape)))
+            off += (n + 3) // 4 * 4                           # every piece 16-byte aligned
         for name, k, cin, cout in self.specs:
-            self.master[name] = (torch.zeros(k, k, cin, cout, device=self.device),
-                                 torch.zeros(cout, device=self.device))
-            for j in range(2 if cout == self.C else 1):
-                self.bias[(name, j)] = torch.zeros(NUMK, device=self.device)
+            if cin == self.C and cout == self.C:
+                for i in range(2):
+                    for j in range(2):
+                        add(name, "w", (i, j), (k, k, NUMK, NUMK))
+                for j in range(2):
+                    add(name, "b", j, (NUMK,))
+            elif cin == self.C:                              # tail: C -> 3
+                for i in range(2):
+                    add(name, "w", (i, 0), (k, k, NUMK, cout))
+                add(name, "b", 0, (cout,))
+            elif k == 1:                                     # Difvdsr4 head: [1,1,3,256] -> two [3,128] matrices
+                for j in range(2):
+                    add(name, "w", (0, j), (3, NUMK))
+                for j in range(2):
+                    add(name, "b", j, (NUMK,))
+            else:                                            # Difvdsr head: dense 3x3x3xC kernel for the direct conv
+                add(name, "w", (0, 0), (k, k, cin, cout))
+                add(name, "b", 0, (cout,))
+        self.n_arena = off
+        self.param_arena = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.blocks, self.bias, self.packed = {}, {}, {}
+        for name, pieces in self.layout.items():
+            for kind, key, o, shape in pieces:
+                view = self.param_arena[o:o + int(np.prod(shape))].view(*shape)
+                if kind == "w":
+                    self.blocks[(name,) + key] = view
+                else:
+                    self.bias[(name, key)] = view
+        self.head_w = [self.blocks[("level1", 0, j)] for j in range(2)] if self.ksize["level1"] == 1 else None
+        self.tail = self.names[-1]
+        for name, k, cin, cout in self.specs:
             if cin == self.C:
                 pc = NUMK if cout == self.C else cout
                 for i in range(2):
                     for j in range(2 if cout == self.C else 1):
                         self.packed[(name, i, j)] = torch.empty(self.lib.sr_packed_weight_bytes(k, pc),
                                                                 dtype=torch.uint8, device=self.device)
-        self.head_w = [torch.zeros(3, NUMK, device=self.device) for _ in range(2)]
+        self._pack_table = self.make_pack_table(self.packed, flip=False)
         self._nets = {}
         self.max_cached = max_cached
         self.set_weights_dict(weights if weights is not None else glorot_uniform(self.specs))
@@ -251,12 +293,65 @@ class PlaneNet:
     def n_params(self):
         return sum(k * k * ci * co + co for _, k, ci, co in self.specs)
 
+    # ------------------------------------------------------------------ packing
+    def make_pack_table(self, packed, flip):
+        """(items, starts, n, total) of one sr_pack_conv_weights_batched launch over every plane block that has a
+        buffer in `packed`: packed[(name, a, b)] = block(name, a, b) as is (flip False), or -- for the input-gradient
+        convs -- packed[(name, j, i)] = block(name, i, j) rotated by 180 degrees with cin <-> cout swapped."""
+        items, starts, total = [], [0], 0
+        for (name, a, b), buf in packed.items():
+            blk = self.blocks[(name, b, a)] if flip else self.blocks[(name, a, b)]
+            it = L.PackItem()
+            it.hwio, it.dst = blk.data_ptr(), buf.data_ptr()
+            it.ksize, it.cout, it.transpose_flip = self.ksize[name], blk.shape[3], 1 if flip else 0
+            items.append(it)
+            total += buf.numel() // 2
+            starts.append(total)
+        arr = (L.PackItem * len(items))(*items)
+        raw = np.frombuffer(memoryview(arr), dtype=np.uint8).copy()
+        return (torch.from_numpy(raw).to(self.device), torch.tensor(starts, dtype=torch.int64).to(self.device),
+                len(items), total)
+
+    def run_pack_table(self, table):
+        items, starts, n, total = table
+        L.check(self.lib.sr_pack_conv_weights_batched(L.ptr(items), L.ptr(starts), n, total, L.stream_ptr()))
+
+    def repack(self):
+        """Tensor-core layouts of every plane block from the current arena: one launch."""
+        self.run_pack_table(self._pack_table)
+
+    # ------------------------------------------------------------------ Keras-shaped weights
+    @property
+    def master(self):
+        """{name: (kernel HWIO, bias)} as fresh device tensors assembled from the arena (read-only view of the
+        weights for get_weights / the Keras facade)."""
+        out = {}
+        C = self.C
+        for name, k, cin, cout in self.specs:
+            if cin == C and cout == C:
+                w = torch.zeros(k, k, 2 * NUMK, 2 * NUMK, device=self.device)
+                for i in range(2):
+                    for j in range(2):
+                        w[:, :, i * NUMK:(i + 1) * NUMK, j * NUMK:(j + 1) * NUMK] = self.blocks[(name, i, j)]
+                b = torch.cat([self.bias[(name, 0)], self.bias[(name, 1)]])
+                out[name] = (w[:, :, :C, :C].contiguous(), b[:C].contiguous())
+            elif cin == C:
+                w = torch.cat([self.blocks[(name, 0, 0)], self.blocks[(name, 1, 0)]], dim=2)
+                out[name] = (w[:, :, :C].contiguous(), self.bias[(name, 0)].clone())
+            elif k == 1:
+                w = torch.cat([self.blocks[(name, 0, 0)], self.blocks[(name, 0, 1)]], dim=1)
+                b = torch.cat([self.bias[(name, 0)], self.bias[(name, 1)]])
+                out[name] = (w[:, :C].reshape(1, 1, 3, C).contiguous(), b[:C].contiguous())
+            else:
+                out[name] = (self.blocks[(name, 0, 0)].clone(), self.bias[(name, 0)].clone())
+        return out
+
     def get_weights_dict(self):
         return {n: (w.cpu().numpy(), b.cpu().numpy()) for n, (w, b) in self.master.items()}
 
     def set_weights_dict(self, weights):
-        st = L.stream_ptr()
         C = self.C
+        self.param_arena.zero_()
         for name, k, cin, cout in self.specs:
             w, b = weights[name]
             w = np.ascontiguousarray(w, dtype=np.float32)
@@ -264,27 +359,31 @@ class PlaneNet:
             if w.shape != (k, k, cin, cout) or b.shape != (cout,):
                 raise ValueError("layer %s: expected kernel %s / bias %s, got %s / %s"
                                  % (name, (k, k, cin, cout), (cout,), w.shape, b.shape))
-            mw, mb = self.master[name]
-            mw.copy_(torch.from_numpy(w))
-            mb.copy_(torch.from_numpy(b))
-            if cout == C:
-                for j in range(2):
-                    n = min(NUMK, C - j * NUMK)
-                    self.bias[(name, j)].zero_()
-                    self.bias[(name, j)][:n].copy_(mb[j * NUMK:j * NUMK + n])
-            if cin == C:
-                pc = NUMK if cout == C else cout
+            wd, bd = torch.from_numpy(w).to(self.device), torch.from_numpy(b).to(self.device)
+            if cin == C and cout == C:
                 for i in range(2):
                     ni = min(NUMK, C - i * NUMK)
-                    for j in range(2 if cout == C else 1):
-                        nj = min(pc, cout - j * NUMK)
-                        blk = torch.zeros(k, k, NUMK, pc, device=self.device)
-                        blk[:, :, :ni, :nj].copy_(mw[:, :, i * NUMK:i * NUMK + ni, j * NUMK:j * NUMK + nj])
-                        L.check(self.lib.sr_pack_conv_weights(L.ptr(blk), k, pc, 0, L.ptr(self.packed[(name, i, j)]), st))
-            elif k == 1:                                   # Difvdsr4 head: [1,1,3,256] -> two [3,128] matrices
+                    for j in range(2):
+                        nj = min(NUMK, C - j * NUMK)
+                        self.blocks[(name, i, j)][:, :, :ni, :nj] = wd[:, :, i * NUMK:i * NUMK + ni, j * NUMK:j * NUMK + nj]
                 for j in range(2):
-                    self.head_w[j].copy_(mw.reshape(3, C)[:, j * NUMK:(j + 1) * NUMK])
-        torch.cuda.current_stream().synchronize()          # the staging blocks above are freed on return
+                    nj = min(NUMK, C - j * NUMK)
+                    self.bias[(name, j)][:nj] = bd[j * NUMK:j * NUMK + nj]
+            elif cin == C:
+                for i in range(2):
+                    ni = min(NUMK, C - i * NUMK)
+                    self.blocks[(name, i, 0)][:, :, :ni] = wd[:, :, i * NUMK:i * NUMK + ni]
+                self.bias[(name, 0)].copy_(bd)
+            elif k == 1:
+                for j in range(2):
+                    nj = min(NUMK, C - j * NUMK)
+                    self.blocks[(name, 0, j)][:, :nj] = wd.reshape(3, C)[:, j * NUMK:j * NUMK + nj]
+                    self.bias[(name, j)][:nj] = bd[j * NUMK:j * NUMK + nj]
+            else:
+                self.blocks[(name, 0, 0)].copy_(wd)
+                self.bias[(name, 0)].copy_(bd)
+        self.repack()
+        torch.cuda.current_stream().synchronize()
 
     def net(self, NB, H, W):
         key = (NB, H, W)

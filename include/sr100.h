@@ -128,6 +128,9 @@ typedef struct sr_conv_desc {
    * tf32), the rest of its 128 are zero padding that the launch does not load or multiply -- the second plane of a
    * 192-channel tensor (Difvdsr, models.py:1274-1357) costs K = 64 instead of 128.  0: all 128. */
   int cin_valid[2];
+  /* With relu_mask_bf16: the factor applied where the mask is <= 0 (0: ReLU backward; alpha: the backward of
+   * LeakyReLU(alpha), models.py:1024-1032 / 1345-1350, whose output has the sign of its input). */
+  float relu_mask_slope;
 } sr_conv_desc;
 
 typedef struct sr_conv_plan sr_conv_plan;
@@ -228,6 +231,9 @@ int sr_bilinear2_fwd(const void* in, int in_is_bf16, int NB, int H, int W, int C
                      float* out_f32, void* stream);
 /* Adjoint of the above: gin[NB,H,W,C] = sum over the HR samples each LR pixel contributed to. */
 int sr_bilinear4_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream);
+/* The adjoint of sr_bilinear2_fwd (Lambda(resize2bil) of Difvdsr4, models.py:932-940, in training): gout fp32
+ * [NB,2H,2W,C] -> gin fp32 [NB,H,W,C]. */
+int sr_bilinear2_bwd(const float* gout, int NB, int H, int W, int C, float* gin, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch tiling.  Replaces img_utils.extract_patches_Step (img_utils.py:601-676) and

@@ -98,41 +98,76 @@ class _Net:
         return F.conv2d(x, self.w[name], self.b[name], padding=(self.k[name] - 1) // 2)
 
 
+def _graph_difvdsr4(net, x):
+    x = F.relu(net.conv("level1", x))
+    i = 1
+    for _ in range(6):
+        t = F.leaky_relu(net.conv(net.names[i], x), 0.001)
+        x = 0.1 * net.conv(net.names[i + 1], t) + x
+        i += 2
+    x = bilinear_tf1(x, 2)
+    x_inp = x
+    for _ in range(20):
+        x = 0.1 * net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x))) + x
+        i += 2
+    x = x + x_inp
+    x = bilinear_tf1(x, 2)
+    for _ in range(6):
+        x = 0.1 * net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x))) + x
+        i += 2
+    return F.relu(net.conv(net.names[i], x))
+
+
+def _graph_difvdsr(net, x):
+    x = F.relu(net.conv("level1", x))
+    i = 1
+    for _ in range(32):
+        a = net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x)))
+        d = a - x
+        e = net.conv(net.names[i + 3], F.leaky_relu(net.conv(net.names[i + 2], d), 0.2))
+        x = 0.1 * (d + e + a) + x
+        i += 4
+    return F.relu(net.conv(net.names[i], x))
+
+
 def forward_difvdsr4(weights, x_nhwc, dtype=torch.float32, numk=256):
     net = _Net(difvdsr4_specs(numk), weights, dtype)
     with torch.no_grad():
         x = torch.from_numpy(np.ascontiguousarray(x_nhwc)).to(dtype).permute(0, 3, 1, 2)
-        x = F.relu(net.conv("level1", x))
-        i = 1
-        for _ in range(6):
-            t = F.leaky_relu(net.conv(net.names[i], x), 0.001)
-            x = 0.1 * net.conv(net.names[i + 1], t) + x
-            i += 2
-        x = bilinear_tf1(x, 2)
-        x_inp = x
-        for _ in range(20):
-            x = 0.1 * net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x))) + x
-            i += 2
-        x = x + x_inp
-        x = bilinear_tf1(x, 2)
-        for _ in range(6):
-            x = 0.1 * net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x))) + x
-            i += 2
-        x = F.relu(net.conv(net.names[i], x))
-        return x.permute(0, 2, 3, 1).to(torch.float32).numpy()
+        return _graph_difvdsr4(net, x).permute(0, 2, 3, 1).to(torch.float32).numpy()
 
 
 def forward_difvdsr(weights, x_nhwc, dtype=torch.float32, numk=192):
     net = _Net(difvdsr_specs(numk), weights, dtype)
     with torch.no_grad():
         x = torch.from_numpy(np.ascontiguousarray(x_nhwc)).to(dtype).permute(0, 3, 1, 2)
-        x = F.relu(net.conv("level1", x))
-        i = 1
-        for _ in range(32):
-            a = net.conv(net.names[i + 1], F.relu(net.conv(net.names[i], x)))
-            d = a - x
-            e = net.conv(net.names[i + 3], F.leaky_relu(net.conv(net.names[i + 2], d), 0.2))
-            x = 0.1 * (d + e + a) + x
-            i += 4
-        x = F.relu(net.conv(net.names[i], x))
-        return x.permute(0, 2, 3, 1).to(torch.float32).numpy()
+        return _graph_difvdsr(net, x).permute(0, 2, 3, 1).to(torch.float32).numpy()
+
+
+def loss_and_grads(arch, weights, x_nhwc, y_nhwc, dtype=torch.float64):
+    """compile(loss='mse') + one backward pass (models.py:1057-1058, 1318-1319): (loss, {name: (d loss / d kernel in
+    HWIO, d loss / d bias)}) by torch autograd on the same graph.  Difvdsr's 'level1' is trainable=False in the
+    reference (models.py:1304): its entry is zeros."""
+    specs = difvdsr4_specs() if arch == "difvdsr4" else difvdsr_specs()
+    net = _Net(specs, weights, dtype)
+    frozen = {"level1"} if arch == "difvdsr" else set()
+    params = []
+    for n in net.names:
+        if n not in frozen:
+            net.w[n].requires_grad_(True)
+            net.b[n].requires_grad_(True)
+            params += [net.w[n], net.b[n]]
+    x = torch.from_numpy(np.ascontiguousarray(x_nhwc)).to(dtype).permute(0, 3, 1, 2)
+    y = torch.from_numpy(np.ascontiguousarray(y_nhwc)).to(dtype).permute(0, 3, 1, 2)
+    pred = (_graph_difvdsr4 if arch == "difvdsr4" else _graph_difvdsr)(net, x)
+    loss = torch.mean((pred - y) ** 2)
+    grads = torch.autograd.grad(loss, params)
+    out, it = {}, iter(grads)
+    for n in net.names:
+        if n in frozen:
+            out[n] = (np.zeros(tuple(net.w[n].permute(2, 3, 1, 0).shape), np.float32),
+                      np.zeros(tuple(net.b[n].shape), np.float32))
+        else:
+            gw, gb = next(it), next(it)
+            out[n] = (gw.permute(2, 3, 1, 0).contiguous().to(torch.float32).numpy(), gb.to(torch.float32).numpy())
+    return float(loss.detach()), out, pred.detach().permute(0, 2, 3, 1).to(torch.float32).numpy()

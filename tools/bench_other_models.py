@@ -18,6 +18,9 @@ def main():
     ap.add_argument("--tiles", type=int, default=32)
     ap.add_argument("--size", type=int, default=96)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--train", action="store_true", help="also time one optimizer step (sr100.planetrain)")
+    ap.add_argument("--train-tiles", type=int, default=32)
+    ap.add_argument("--train-size", type=int, default=48)
     a = ap.parse_args()
     import torch
     from sr100.planenet import PlaneNet
@@ -48,7 +51,28 @@ def main():
                               algorithmic_tflops=round(2 * macs / ms / 1e9, 1),
                               executed_tflops=round(net.conv_flops / ms / 1e9, 1),
                               mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))), flush=True)
-        del net, eng
+        del net
+        if a.train:
+            from sr100.planetrain import PlaneTrainer
+            tr = PlaneTrainer(eng)
+            g = tr.graph(a.train_tiles, a.train_size, a.train_size)
+            g.x_in.copy_(torch.rand(g.x_in.shape, device="cuda"))
+            g.y_true.copy_(torch.rand(g.y_true.shape, device="cuda"))
+            for _ in range(2):
+                tr.step_device(g)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(a.iters):
+                tr.step_device(g)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.iters
+            print(json.dumps(dict(model=arch, train_step=True, tiles=a.train_tiles, size=a.train_size, ms=round(ms, 3),
+                                  images_per_s=round(a.train_tiles / ms * 1e3, 1),
+                                  executed_tflops=round(g.flops / ms / 1e9, 1), launches=len(g.fwd) + len(g.bwd),
+                                  mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))), flush=True)
+            del tr, g
+        del eng
         torch.cuda.empty_cache()
 
 

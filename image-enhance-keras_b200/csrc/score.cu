@@ -1,8 +1,8 @@
 // Y-channel PSNR + SSIM scoring (reference: scorpath.py:174-228, PSNR.py:54-84, skimage
 // rgb2ycbcr / compare_ssim semantics restated in oracle/scoring.py).
 // One fused pass: uint8 RGB pair -> crop -> integer {R,G,B,Z} planes in shared memory -> separable sliding 7x7
-// window sums (exact integers) -> SSIM map value -> block reduction (warp shuffles) -> 64-bit integer atomics
-// (bit-reproducible); see score_pair_kernel.
+// window sums (exact integers; a block walks down a band of columns carrying the vertical sums in registers) ->
+// SSIM map value -> warp reduction (shuffles) -> 64-bit integer atomics (bit-reproducible); see score_pair_kernel.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -13,12 +13,17 @@ namespace sr {
 namespace {
 
 constexpr int kWin = 7;
-constexpr int kTW = 32, kTH = 26;                       // window positions (= cropped pixels owned) per block
-constexpr int kHW = kTW + kWin - 1, kHH = kTH + kWin - 1;  // 38 x 32 halo pixels: 32 rows x 8 column runs = 256 threads
-constexpr int kNPix = kHH * kHW, kNH = kHH * kTW;
-constexpr unsigned kK = 255000u;                        // Y = 16 + Z / kK with Z = 65481 R + 128553 G + 24966 B (integer)
-constexpr int kScoreSmem = (5 * kNPix + 8 * kNH) * 4;   // 24,320 B of pixels + 32,768 B of row sums
-constexpr double kFix = 1099511627776.0;                // SSIM values are accumulated as 2^-40 fixed point (int64)
+constexpr int kBW = 32;                     // window columns (= owned pixel columns) of a block's column band
+constexpr int kPC = kBW + kWin - 1;         // 38 pixel columns staged per row
+constexpr int kRS = 8;                      // pixel rows per step of the walk down the band
+constexpr int kPxStride = 68;               // words per staged pixel row (permuted columns; == 4 mod 32)
+constexpr int kHsStride = 36;               // words per row of horizontal sums (permuted columns; == 4 mod 32)
+constexpr int kSlots = 16;                  // ring of row-sum rows: 8 new + 7 old
+constexpr int kNVal = 15;                   // words per (row, column): 3 x {s, q, d2} + Y {sa, sb, q lo/hi, d2 lo/hi}
+constexpr int kScoreThreads = 128;          // four warps = four roles (R, G, B, Y), rotated with the block index
+constexpr unsigned kK = 255000u;            // Y = 16 + Z / kK with Z = 65481 R + 128553 G + 24966 B (integer)
+constexpr double kFix = 1099511627776.0;    // SSIM values are accumulated as 2^-40 fixed point (int64)
+constexpr unsigned long long kFixBias = 0x4338000000000000ull;   // bits of 1.5 * 2^52
 
 __device__ __forceinline__ double y_from_rgb(double r, double g, double b) {
   // skimage.color.rgb2ycbcr on img_as_float(uint8): (r*65.481 + g*128.553 + b*24.966) + 16
@@ -39,215 +44,294 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// a / b for b > 0: fp32 reciprocal refined by two Newton steps in fp64 (relative error ~1e-16; a full-precision
-// fp64 division costs several times as much and this kernel does four per pixel)
-__device__ __forceinline__ double fast_div(double a, double b) {
-  double r = (double)__frcp_rn((float)b);
-  r = r * (2.0 - b * r);
-  r = r * (2.0 - b * r);
-  return a * r;
+// exact integer -> fp64 conversions on the fp64 pipe (one DADD) instead of the quarter-rate conversion unit
+__device__ __forceinline__ double u32_to_f64(uint32_t u) {
+  return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0;              // (2^52 + u) - 2^52
+}
+__device__ __forceinline__ double s32_to_f64(int v) {
+  return __hiloint2double(0x43300000, v ^ (int)0x80000000) - 4503601774854144.0;  // (2^52 + 2^31 + v) - (2^52 + 2^31)
+}
+// 1 / b for b > 0: the 20-bit hardware seed refined by two Newton steps (relative error ~2^-52)
+__device__ __forceinline__ double rcp_f64(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(r, fma(-b, r, 1.0), r);
+  r = fma(r, fma(-b, r, 1.0), r);
+  return r;
+}
+// bits of (1.5 * 2^52 + rint(v * 2^40)): the integer sits in the mantissa, rounded to nearest even by the fma
+__device__ __forceinline__ unsigned long long fix40_bits(double v) {
+  return (unsigned long long)__double_as_longlong(fma(v, kFix, 6755399441055744.0));
 }
 
-// Fused scoring of one image pair in EXACT INTEGER window arithmetic.
-//   * R, G, B are bytes and Y = 16 + Z / 255000 with Z an integer < 2^26, so every 7x7 window moment (sum x, sum y,
-//     sum x^2, sum y^2, sum xy) is an integer: < 2^32 for the colour planes, < 2^63 for Z -- no rounding, any order.
-//   * separable SLIDING sums: one pass of horizontal 7-sums per halo row (a thread slides along 4 columns), one
-//     pass of vertical 7-sums (a thread slides down 4 windows); ~3 pixel evaluations per window and pass instead of
-//     the 17 of summing taps directly.
-//   * the variance / covariance numerators (49 Sxy - Sx Sy, ...) are formed in integers -- the cancellation that
-//     makes SSIM need fp64 never meets a rounded number -- then four conversions, two products and one division
-//     per plane in fp64.
-//   * per-window SSIM values are accumulated as 2^-40 fixed point and all cross-block sums are 64-bit INTEGER
-//     atomics, so the result is bit-reproducible run to run (fp64 atomics were not); the last block to finish
-//     (ticket counter) converts the accumulators into the public double fields.
-__global__ void __launch_bounds__(256) score_pair_kernel(const uint8_t* __restrict__ a,
-                                                         const uint8_t* __restrict__ b, int h, int w,
-                                                         int crop, sr_score_result* __restrict__ res) {
-  extern __shared__ uint32_t sm[];
-  uint32_t* px = sm;                 // [5][kNPix]: R, G, B as (a | b << 16); Za; Zb
-  uint32_t* hb = sm + 5 * kNPix;     // row sums: colour phase 4 x u32 [kNH]; Y phase 2 x u32 + 3 x u64 [kNH]
-  __shared__ long long red[8][5];
-  const int tid = threadIdx.x;
-  const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;                 // cropped size
-  const int wy0 = blockIdx.y * kTH, wx0 = blockIdx.x * kTW;         // first window (top-left) / first owned pixel
-  const int nwy = ch_ - kWin + 1, nwx = cw_ - kWin + 1;             // valid windows per axis
+// column permutations that make every shared-memory access of the kernel bank-conflict free (see the kernel)
+__device__ __forceinline__ int px_col(int c) { return ((c & 7) << 2) + ((c >> 3) & 3) + ((c >> 5) << 5); }
+__device__ __forceinline__ int hs_col(int x) { return ((x & 7) << 2) + (x >> 3); }
 
-  // ---- pixels -> shared memory; squared Y error of the owned pixels (exact: (Za - Zb)^2)
+struct ScoreSmem {
+  uint32_t px[5][kRS][kPxStride];          // R, G, B as (a | b << 16); Za; Zb -- the 8 pixel rows of the current step
+  uint32_t hs[kNVal][kSlots][kHsStride];   // horizontal 7-sums of the per-pixel moments, ring of pixel rows
+};
+
+// SSIM of one window of a colour plane from its exact integer moments:
+//   s = Sx | Sy << 16, q = sum (x^2 + y^2), d2 = sum (x - y)^2   (so 2 Sxy = q - d2)
+// SSIM = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)), u = S / 49, v = (49 S2 - S S) / (48 * 49):
+// both factors scaled to integers (10^4 * 49^2 and 100 * 48 * 49), formed exactly, then one fp64 division.
+__device__ __forceinline__ unsigned long long ssim_colour_fix(uint32_t s, uint32_t q, uint32_t d2) {
+  const uint32_t Sx = s & 0xffffu, Sy = s >> 16;
+  const uint32_t P = Sx * Sy, XY = Sx * Sx + Sy * Sy;
+  const int T2 = (int)(49u * (q - d2)) - (int)(2u * P);          // 2 * 48 * 49 * vxy
+  const uint32_t U = 49u * q - XY;                               // 48 * 49 * (vx + vy) >= 0
+  const double NA1 = fma(20000.0, u32_to_f64(P), 156125025.0);   // 10^4 (2 Sx Sy + 49^2 C1), C1 = 6.5025
+  const double NB1 = fma(10000.0, u32_to_f64(XY), 156125025.0);
+  const double NA2 = fma(100.0, s32_to_f64(T2), 13764492.0);     // 100 (2 T + 2352 C2), C2 = 58.5225
+  const double NB2 = fma(100.0, u32_to_f64(U), 13764492.0);
+  return fix40_bits((NA1 * NA2) * rcp_f64(NB1 * NB2));
+}
+
+// The same for Y = 16 + Z / 255000 from the integer moments of Z (second moments need 64 bits):
+//   sa = sum Za, sb = sum Zb, q = sum (Za^2 + Zb^2), d2 = sum (Za - Zb)^2.  49 q < 2^64 (Z < 2^25.74).
+__device__ __forceinline__ unsigned long long ssim_y_fix(uint32_t sa, uint32_t sb, unsigned long long q,
+                                                         unsigned long long d2) {
+  const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+  const double inv49k = 1.0 / (49.0 * (double)kK);
+  const double invv = 1.0 / (48.0 * 49.0 * (double)kK * (double)kK);
+  const unsigned long long pa = (unsigned long long)sa * sa, pb = (unsigned long long)sb * sb;
+  const unsigned long long U = 49ull * q - pa - pb;                                        // Txx + Tyy >= 0
+  const long long T2 = (long long)(49ull * (q - d2) - 2ull * ((unsigned long long)sa * sb));  // 2 Txy
+  const double ux = fma(u32_to_f64(sa), inv49k, 16.0), uy = fma(u32_to_f64(sb), inv49k, 16.0);
+  const double A1 = fma(2.0 * ux, uy, C1), B1 = fma(ux, ux, fma(uy, uy, C1));
+  const double A2 = fma((double)T2, invv, C2), B2 = fma((double)U, invv, C2);
+  return fix40_bits((A1 * A2) * rcp_f64(B1 * B2));
+}
+
+// Fused scoring of one image pair in EXACT INTEGER window arithmetic (reference: scorpath.py:174-228).
+//   * R, G, B are bytes and Y = 16 + Z / 255000 with Z an integer < 2^26, so every 7x7 window moment is an
+//     integer; the variance / covariance numerators (49 S2 - S S) are formed in integers -- the cancellation that
+//     makes SSIM need fp64 never meets a rounded number -- and only the final ratio is fp64.
+//   * a block owns a band of 32 window columns and WALKS DOWN a chunk of rows, 8 pixel rows per step:
+//       convert   128 threads turn the step's 8 x 38 pixels into packed planes in shared memory (the next step's
+//                 bytes are fetched into registers one step ahead) and add the owned pixels' squared Y error;
+//       H         one warp per plane (R, G, B, Y; the role rotates with the block index so that the heavier Y warps
+//                 spread over the SM's four schedulers): lane = (row, 8-column segment) computes the per-pixel
+//                 moments of 14 pixels once and slides the horizontal 7-sums along its 8 outputs;
+//       V         lane = window column keeps the vertical 7-row sums in REGISTERS across the whole walk (add the new
+//                 row, subtract the row seven up, both from a 16-row ring), forms SSIM and accumulates.
+//     No halo rows are recomputed between steps; the only redundancy is 6 columns per band and 6 rows per chunk.
+//   * three moments per colour plane (s, q = sum x^2 + y^2, d2 = sum (x - y)^2) instead of four.
+//   * columns are stored permuted (px_col / hs_col) with row strides == 4 mod 32 words: every load and store of
+//     the three phases touches 32 distinct banks.
+//   * per-window SSIM values are accumulated as 2^-40 fixed point and all cross-block sums are 64-bit INTEGER
+//     atomics, so the result is bit-reproducible run to run; the last block to finish (ticket counter) converts
+//     the accumulators into the public double fields.
+__global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t* __restrict__ a,
+                                                                   const uint8_t* __restrict__ b, int h, int w,
+                                                                   int crop, int chunk_rows, int steps,
+                                                                   sr_score_result* __restrict__ res) {
+  __shared__ ScoreSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int role = ((tid >> 5) + blockIdx.x + blockIdx.y) & 3;      // 0..2 colour plane, 3 = Y
+  const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;                 // cropped size
+  const int nwy = ch_ - kWin + 1, nwx = cw_ - kWin + 1;             // valid windows per axis
+  const int bx0 = blockIdx.x * kBW, cy0 = blockIdx.y * chunk_rows;  // first owned pixel = first window of the block
+
+  // ---- convert: pixel k of this thread is index tid + 128 k of the step's 8 x 38 pixels
+  constexpr int kPixPerThread = (kRS * kPC + kScoreThreads - 1) / kScoreThreads;   // 3
+  int p_r[kPixPerThread], p_c[kPixPerThread];
+  uint32_t raw[kPixPerThread][2];                                   // a / b bytes of the prefetched pixels
+#pragma unroll
+  for (int k = 0; k < kPixPerThread; ++k) {
+    const int idx = tid + k * kScoreThreads;
+    p_r[k] = idx / kPC;
+    p_c[k] = idx - p_r[k] * kPC;
+  }
+  auto fetch = [&](int step) {
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      const int y = cy0 + step * kRS + p_r[k], x = bx0 + p_c[k];
+      uint32_t va = 0, vb = 0;
+      if (p_r[k] < kRS && y < ch_ && x < cw_) {
+        const size_t o = ((size_t)(y + crop) * w + (x + crop)) * 3;
+        va = a[o] | ((uint32_t)a[o + 1] << 8) | ((uint32_t)a[o + 2] << 16);
+        vb = b[o] | ((uint32_t)b[o + 1] << 8) | ((uint32_t)b[o + 2] << 16);
+      }
+      raw[k][0] = va;
+      raw[k][1] = vb;
+    }
+  };
   unsigned long long ssd = 0;
-  for (int i = tid; i < kNPix; i += 256) {
-    const int ly = i / kHW, lx = i - ly * kHW;
-    const int y = wy0 + ly, x = wx0 + lx;
-    uint32_t pr = 0, pg = 0, pb = 0, za = 0, zb = 0;
-    if (y < ch_ && x < cw_) {
-      const size_t o = ((size_t)(y + crop) * w + (x + crop)) * 3;
-      const uint32_t ar = a[o], ag = a[o + 1], ab = a[o + 2], br = b[o], bg = b[o + 1], bb = b[o + 2];
-      pr = ar | (br << 16);
-      pg = ag | (bg << 16);
-      pb = ab | (bb << 16);
-      za = 65481u * ar + 128553u * ag + 24966u * ab;
-      zb = 65481u * br + 128553u * bg + 24966u * bb;
-      if (ly < kTH && lx < kTW) {
-        const long long d = (long long)za - (long long)zb;
-        ssd += (unsigned long long)(d * d);
+  auto convert = [&](int step) {
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+      if (p_r[k] < kRS) {
+        const uint32_t va = raw[k][0], vb = raw[k][1];
+        const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = va >> 16;
+        const uint32_t br = vb & 0xffu, bg = (vb >> 8) & 0xffu, bb = vb >> 16;
+        const uint32_t za = 65481u * ar + 128553u * ag + 24966u * ab;
+        const uint32_t zb = 65481u * br + 128553u * bg + 24966u * bb;
+        const int o = p_r[k] * kPxStride + px_col(p_c[k]);
+        (&sm.px[0][0][0])[o] = ar | (br << 16);
+        (&sm.px[1][0][0])[o] = ag | (bg << 16);
+        (&sm.px[2][0][0])[o] = ab | (bb << 16);
+        (&sm.px[3][0][0])[o] = za;
+        (&sm.px[4][0][0])[o] = zb;
+        // squared Y error of the pixels this block owns (zero-filled pixels outside the image add nothing)
+        if (p_c[k] < kBW && step * kRS + p_r[k] < chunk_rows) {
+          const long long d = (long long)za - (long long)zb;
+          ssd += (unsigned long long)(d * d);
+        }
       }
     }
-    px[i] = pr;
-    px[kNPix + i] = pg;
-    px[2 * kNPix + i] = pb;
-    px[3 * kNPix + i] = za;
-    px[4 * kNPix + i] = zb;
-  }
+  };
+
+  // ---- per-lane state of the two sliding phases
+  const int hr = lane >> 2, hseg = lane & 3;                    // H: pixel row of the step, 8-column segment
+  const int h_in0 = hr * kPxStride + hseg;                      // px_col(8 seg + i)     = 4 i + seg        (i < 8)
+  const int h_in1 = hr * kPxStride + (hseg == 3 ? 32 : hseg + 1);   // px_col(8 seg + 8 + i) = 4 i + this   (i < 6)
+  const int h_out = hseg;                                       // hs_col(8 seg + j)     = 4 j + seg
+  const int v_col = hs_col(lane);                               // V: window column = lane
+  const bool col_ok = bx0 + lane < nwx;
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;                      // vertical sums: colour {s, q, d2}; Y {sa, sb} + 64-bit pair
+  unsigned long long wq = 0, wd = 0;
+  unsigned long long acc = 0;                                   // sum of fix40_bits (bias removed at the end)
+  unsigned int nacc = 0;
+
+  fetch(0);
+  convert(0);
   __syncthreads();
 
-  const int hr = tid >> 3, hx0 = (tid & 7) * 4;           // horizontal task: halo row, first of 4 window columns
-  const int vx = tid & 31, vy0 = (tid >> 5) * 4;          // vertical task: window column, first of <= 4 window rows
-  const int vrows = min(4, kTH - vy0);
-  const bool col_ok = wx0 + vx < nwx;
-  long long acc_y = 0, acc_r = 0, acc_g = 0, acc_b = 0;   // fixed-point SSIM sums
+  for (int step = 0; step < steps; ++step) {
+    if (step + 1 < steps) fetch(step + 1);
+    const int slot0 = (step * kRS) & (kSlots - 1);              // ring slot of the step's first pixel row (0 or 8)
 
-  // ---- colour planes
-#pragma unroll 1
-  for (int c = 0; c < 3; ++c) {
-    long long cacc = 0;
-    {
-      const uint32_t* row = px + c * kNPix + hr * kHW + hx0;
-      uint32_t s1 = 0, sxx = 0, syy = 0, sxy = 0;         // s1 = sum x | sum y << 16 (each <= 7 * 255)
+    // ---- H: horizontal 7-sums of the step's 8 pixel rows
+    if (role < 3) {
+      const uint32_t* in = &sm.px[role][0][0];
+      uint32_t ms[14], mq[14], md[14];
 #pragma unroll
-      for (int dx = 0; dx < kWin; ++dx) {
-        const uint32_t p = row[dx], x = p & 0xffffu, y = p >> 16;
-        s1 += p; sxx += x * x; syy += y * y; sxy += x * y;
+      for (int i = 0; i < 14; ++i) {
+        const uint32_t p = i < 8 ? in[h_in0 + 4 * i] : in[h_in1 + 4 * (i - 8)];
+        const uint32_t x = p & 0xffffu, y = p >> 16;
+        const int d = (int)x - (int)y;
+        ms[i] = p;
+        mq[i] = x * x + y * y;
+        md[i] = (uint32_t)(d * d);
       }
-      uint32_t* o = hb + hr * kTW + hx0;
-      o[0] = s1; o[kNH] = sxx; o[2 * kNH] = syy; o[3 * kNH] = sxy;
+      uint32_t* o0 = &sm.hs[3 * role][slot0 + hr][h_out];
+      uint32_t s = 0, q = 0, d2 = 0;
 #pragma unroll
-      for (int j = 1; j < 4; ++j) {
-        const uint32_t pn = row[j + kWin - 1], xn = pn & 0xffffu, yn = pn >> 16;
-        const uint32_t po = row[j - 1], xo = po & 0xffffu, yo = po >> 16;
-        s1 += pn - po; sxx += xn * xn - xo * xo; syy += yn * yn - yo * yo; sxy += xn * yn - xo * yo;
-        o[j] = s1; o[kNH + j] = sxx; o[2 * kNH + j] = syy; o[3 * kNH + j] = sxy;
+      for (int i = 0; i < 7; ++i) { s += ms[i]; q += mq[i]; d2 += md[i]; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j > 0) { s += ms[j + 6] - ms[j - 1]; q += mq[j + 6] - mq[j - 1]; d2 += md[j + 6] - md[j - 1]; }
+        o0[4 * j] = s;
+        o0[kSlots * kHsStride + 4 * j] = q;
+        o0[2 * kSlots * kHsStride + 4 * j] = d2;
+      }
+    } else {
+      const uint32_t* ina = &sm.px[3][0][0];
+      const uint32_t* inb = &sm.px[4][0][0];
+      uint32_t za[14], zb[14];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) {
+        const int o = i < 8 ? h_in0 + 4 * i : h_in1 + 4 * (i - 8);
+        za[i] = ina[o];
+        zb[i] = inb[o];
+      }
+      uint32_t* o0 = &sm.hs[9][slot0 + hr][h_out];
+      uint32_t sa = 0, sb = 0;
+      unsigned long long q = 0, d2 = 0;
+      auto mom_q = [](uint32_t x, uint32_t y) { return (unsigned long long)x * x + (unsigned long long)y * y; };
+      auto mom_d = [](uint32_t x, uint32_t y) {
+        const long long d = (long long)x - (long long)y;
+        return (unsigned long long)(d * d);
+      };
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { sa += za[i]; sb += zb[i]; q += mom_q(za[i], zb[i]); d2 += mom_d(za[i], zb[i]); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j > 0) {
+          sa += za[j + 6] - za[j - 1];
+          sb += zb[j + 6] - zb[j - 1];
+          q += mom_q(za[j + 6], zb[j + 6]) - mom_q(za[j - 1], zb[j - 1]);
+          d2 += mom_d(za[j + 6], zb[j + 6]) - mom_d(za[j - 1], zb[j - 1]);
+        }
+        o0[4 * j] = sa;
+        o0[kSlots * kHsStride + 4 * j] = sb;
+        o0[2 * kSlots * kHsStride + 4 * j] = (uint32_t)q;
+        o0[3 * kSlots * kHsStride + 4 * j] = (uint32_t)(q >> 32);
+        o0[4 * kSlots * kHsStride + 4 * j] = (uint32_t)d2;
+        o0[5 * kSlots * kHsStride + 4 * j] = (uint32_t)(d2 >> 32);
       }
     }
-    __syncthreads();
-    if (vrows > 0) {
-      const uint32_t* col = hb + vy0 * kTW + vx;
-      uint32_t s1 = 0, sxx = 0, syy = 0, sxy = 0;         // window sums: s1 fields <= 49 * 255 = 12495
+    __syncthreads();                         // row sums of the step are in the ring; the pixel buffer is free
+    if (step + 1 < steps) convert(step + 1);
+
+    // ---- V: vertical 7-row sums carried in registers, SSIM of the window rows that complete in this step
+    {
+      const int row0 = step * kRS;           // chunk-relative index of the step's first pixel row
+      constexpr int kPlane = kSlots * kHsStride;
+      if (role < 3) {
+        const uint32_t* base = &sm.hs[3 * role][0][v_col];
 #pragma unroll
-      for (int dy = 0; dy < kWin; ++dy) {
-        const uint32_t* q = col + dy * kTW;
-        s1 += q[0]; sxx += q[kNH]; syy += q[2 * kNH]; sxy += q[3 * kNH];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < vrows) {
-          if (j > 0) {
-            const uint32_t* qn = col + (j + kWin - 1) * kTW;
-            const uint32_t* qo = col + (j - 1) * kTW;
-            s1 += qn[0] - qo[0]; sxx += qn[kNH] - qo[kNH]; syy += qn[2 * kNH] - qo[2 * kNH];
-            sxy += qn[3 * kNH] - qo[3 * kNH];
+        for (int j = 0; j < kRS; ++j) {
+          const int rho = row0 + j;
+          const uint32_t* n = base + ((slot0 + j) & (kSlots - 1)) * kHsStride;
+          w0 += n[0]; w1 += n[kPlane]; w2 += n[2 * kPlane];
+          if (rho >= kWin) {
+            const uint32_t* o = base + ((slot0 + j - kWin) & (kSlots - 1)) * kHsStride;
+            w0 -= o[0]; w1 -= o[kPlane]; w2 -= o[2 * kPlane];
           }
-          if (col_ok && wy0 + vy0 + j < nwy) {
-            // SSIM = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)) with u = S / 49, v = 49/48 (..):
-            // numerator and denominator scaled by 10^4 * 49^2 (first factor) and 100 * 48 * 49 (second) are integers
-            const uint32_t Sx = s1 & 0xffffu, Sy = s1 >> 16;
-            const uint32_t P = Sx * Sy, X2 = Sx * Sx, Y2 = Sy * Sy;
-            const long long NA1 = 20000ll * P + 156125025ll;            // 10^4 (2 Sx Sy + 49^2 C1), C1 = 6.5025
-            const long long NB1 = 10000ll * ((long long)X2 + Y2) + 156125025ll;
-            const int T = (int)(49u * sxy) - (int)P;                      // 48 * 49 * vxy
-            const uint32_t U = 49u * (sxx + syy) - X2 - Y2;               // 48 * 49 * (vx + vy) >= 0
-            const long long NA2 = 200ll * T + 13764492ll;                 // 100 (2 T + 2352 C2), C2 = 58.5225
-            const long long NB2 = 100ll * U + 13764492ll;
-            const double v = fast_div((double)NA1 * (double)NA2, (double)NB1 * (double)NB2);
-            cacc += __double2ll_rn(v * kFix);
+          const int wrow = rho - (kWin - 1);
+          if (wrow >= 0 && wrow < chunk_rows && cy0 + wrow < nwy && col_ok) {
+            acc += ssim_colour_fix(w0, w1, w2);
+            ++nacc;
+          }
+        }
+      } else {
+        const uint32_t* base = &sm.hs[9][0][v_col];
+#pragma unroll
+        for (int j = 0; j < kRS; ++j) {
+          const int rho = row0 + j;
+          const uint32_t* n = base + ((slot0 + j) & (kSlots - 1)) * kHsStride;
+          w0 += n[0]; w1 += n[kPlane];
+          wq += (unsigned long long)n[2 * kPlane] | ((unsigned long long)n[3 * kPlane] << 32);
+          wd += (unsigned long long)n[4 * kPlane] | ((unsigned long long)n[5 * kPlane] << 32);
+          if (rho >= kWin) {
+            const uint32_t* o = base + ((slot0 + j - kWin) & (kSlots - 1)) * kHsStride;
+            w0 -= o[0]; w1 -= o[kPlane];
+            wq -= (unsigned long long)o[2 * kPlane] | ((unsigned long long)o[3 * kPlane] << 32);
+            wd -= (unsigned long long)o[4 * kPlane] | ((unsigned long long)o[5 * kPlane] << 32);
+          }
+          const int wrow = rho - (kWin - 1);
+          if (wrow >= 0 && wrow < chunk_rows && cy0 + wrow < nwy && col_ok) {
+            acc += ssim_y_fix(w0, w1, wq, wd);
+            ++nacc;
           }
         }
       }
     }
-    acc_r += c == 0 ? cacc : 0;
-    acc_g += c == 1 ? cacc : 0;
-    acc_b += c == 2 ? cacc : 0;
-    __syncthreads();
+    __syncthreads();                         // the next step's pixels are staged; ring rows older than 7 are free
   }
+  (void)w3;
 
-  // ---- Y plane: the same two passes on Z (sums of Z fit u32, second moments need u64)
-  {
-    unsigned long long* hq = reinterpret_cast<unsigned long long*>(hb + 2 * kNH);   // [3][kNH]
-    {
-      const uint32_t* ra = px + 3 * kNPix + hr * kHW + hx0;
-      const uint32_t* rb = px + 4 * kNPix + hr * kHW + hx0;
-      uint32_t sa = 0, sb = 0;
-      unsigned long long saa = 0, sbb = 0, sab = 0;
+  // ---- reduction: integers, so the order does not matter.  One atomic per warp and accumulator, then the last
+  // block (ticket) converts.
+  acc -= (unsigned long long)nacc * kFixBias;
 #pragma unroll
-      for (int dx = 0; dx < kWin; ++dx) {
-        const unsigned long long x = ra[dx], y = rb[dx];
-        sa += (uint32_t)x; sb += (uint32_t)y; saa += x * x; sbb += y * y; sab += x * y;
-      }
-      const int o = hr * kTW + hx0;
-      hb[o] = sa; hb[kNH + o] = sb; hq[o] = saa; hq[kNH + o] = sbb; hq[2 * kNH + o] = sab;
-#pragma unroll
-      for (int j = 1; j < 4; ++j) {
-        const unsigned long long xn = ra[j + kWin - 1], yn = rb[j + kWin - 1], xo = ra[j - 1], yo = rb[j - 1];
-        sa += (uint32_t)xn - (uint32_t)xo; sb += (uint32_t)yn - (uint32_t)yo;
-        saa += xn * xn - xo * xo; sbb += yn * yn - yo * yo; sab += xn * yn - xo * yo;
-        hb[o + j] = sa; hb[kNH + o + j] = sb; hq[o + j] = saa; hq[kNH + o + j] = sbb; hq[2 * kNH + o + j] = sab;
-      }
-    }
-    __syncthreads();
-    if (vrows > 0) {
-      const int o0 = vy0 * kTW + vx;
-      uint32_t sa = 0, sb = 0;
-      unsigned long long saa = 0, sbb = 0, sab = 0;
-#pragma unroll
-      for (int dy = 0; dy < kWin; ++dy) {
-        const int o = o0 + dy * kTW;
-        sa += hb[o]; sb += hb[kNH + o]; saa += hq[o]; sbb += hq[kNH + o]; sab += hq[2 * kNH + o];
-      }
-      const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
-      const double inv49k = 1.0 / (49.0 * (double)kK);
-      const double invv = 1.0 / (48.0 * 49.0 * (double)kK * (double)kK);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < vrows) {
-          if (j > 0) {
-            const int on = o0 + (j + kWin - 1) * kTW, oo = o0 + (j - 1) * kTW;
-            sa += hb[on] - hb[oo]; sb += hb[kNH + on] - hb[kNH + oo];
-            saa += hq[on] - hq[oo]; sbb += hq[kNH + on] - hq[kNH + oo]; sab += hq[2 * kNH + on] - hq[2 * kNH + oo];
-          }
-          if (col_ok && wy0 + vy0 + j < nwy) {
-            // 49 Sab - Sa Sb etc. are exact in int64 (49 * 49 * Z^2 < 7.5e18): the variances never see a rounded sum
-            const unsigned long long pa = (unsigned long long)sa * sa, pb = (unsigned long long)sb * sb;
-            const long long Txy = (long long)(49ull * sab) - (long long)((unsigned long long)sa * sb);
-            const long long Txx = (long long)(49ull * saa - pa), Tyy = (long long)(49ull * sbb - pb);
-            const double ux = 16.0 + (double)sa * inv49k, uy = 16.0 + (double)sb * inv49k;
-            const double A1 = 2.0 * ux * uy + C1, B1 = ux * ux + uy * uy + C1;
-            const double A2 = 2.0 * ((double)Txy * invv) + C2;
-            const double B2 = ((double)Txx + (double)Tyy) * invv + C2;
-            acc_y += __double2ll_rn(fast_div(A1 * A2, B1 * B2) * kFix);
-          }
-        }
-      }
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    ssd += __shfl_xor_sync(0xffffffffu, ssd, o);
   }
-
-  // ---- block reduction (integers: order does not matter), integer atomics, last block converts
-  long long v5[5] = {acc_y, acc_r, acc_g, acc_b, (long long)ssd};
-#pragma unroll
-  for (int k = 0; k < 5; ++k)
-    for (int o = 16; o > 0; o >>= 1) v5[k] += __shfl_xor_sync(0xffffffffu, v5[k], o);
-  if ((tid & 31) == 0)
-    for (int k = 0; k < 5; ++k) red[tid >> 5][k] = v5[k];
+  unsigned long long* gacc = reinterpret_cast<unsigned long long*>(res->acc);
+  if (lane == 0) {
+    atomicAdd(gacc + (role == 3 ? 0 : 1 + role), acc);
+    atomicAdd(gacc + 4, ssd & 0xffffffffull);      // squared error: low / high halves (the total can exceed 2^64)
+    atomicAdd(gacc + 5, ssd >> 32);
+    __threadfence();
+  }
   __syncthreads();
   if (tid == 0) {
-    unsigned long long t[5];
-    for (int k = 0; k < 5; ++k) {
-      long long s_ = 0;
-      for (int wv = 0; wv < 8; ++wv) s_ += red[wv][k];
-      t[k] = (unsigned long long)s_;
-    }
-    unsigned long long* gacc = reinterpret_cast<unsigned long long*>(res->acc);
-    for (int k = 0; k < 4; ++k) atomicAdd(gacc + k, t[k]);
-    atomicAdd(gacc + 4, t[4] & 0xffffffffull);     // squared error: low / high halves (the total exceeds 2^64)
-    atomicAdd(gacc + 5, t[4] >> 32);
-    __threadfence();
     const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(&res->ticket), 1ull);
     if (done == (unsigned long long)gridDim.x * gridDim.y - 1) {
       __threadfence();
@@ -306,11 +390,19 @@ extern "C" int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w
   if (crop < 0 || h - 2 * crop < 7 || w - 2 * crop < 7)
     return set_error(SR_ERR_INVALID, "sr_score_pair_u8: image smaller than the 7x7 SSIM window after cropping");
   const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;
-  dim3 grid((cw_ + kTW - 1) / kTW, (ch_ + kTH - 1) / kTH);
+  // bands of 32 columns x chunks of rows: about one resident wave of blocks (4 per SM) on a large image, chunks of
+  // at least 26 window rows on a small one; a chunk is processed in steps of 8 pixel rows (chunk + 6 halo rows)
+  const int bands = (cw_ + kBW - 1) / kBW;
+  int chunks = (148 * 4 + bands / 2) / bands;
+  const int max_chunks = (ch_ + 25) / 26;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int chunk_rows = (ch_ + chunks - 1) / chunks;
+  const int steps = (chunk_rows + kWin - 1 + kRS - 1) / kRS;
+  chunk_rows = steps * kRS - (kWin - 1);
+  chunks = (ch_ + chunk_rows - 1) / chunk_rows;
+  dim3 grid(bands, chunks);
   if (grid.y > 65535u) return set_error(SR_ERR_UNSUPPORTED, "sr_score_pair_u8: image taller than 1.7 M rows");
-  static unsigned long long attr_done = 0;
-  if (int rc = ensure_dynamic_smem(score_pair_kernel, kScoreSmem, &attr_done, "cudaFuncSetAttribute(score_pair_kernel)"))
-    return rc;
-  score_pair_kernel<<<grid, 256, kScoreSmem, as_stream(stream)>>>(a, b, h, w, crop, result);
+  score_pair_kernel<<<grid, kScoreThreads, 0, as_stream(stream)>>>(a, b, h, w, crop, chunk_rows, steps, result);
   return check_launch("score_pair_kernel");
 }

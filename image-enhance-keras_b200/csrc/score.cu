@@ -44,24 +44,22 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// exact integer -> fp64 conversions on the fp64 pipe (one DADD) instead of the quarter-rate conversion unit
-__device__ __forceinline__ double u32_to_f64(uint32_t u) {
-  return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0;              // (2^52 + u) - 2^52
-}
-__device__ __forceinline__ double s32_to_f64(int v) {
-  return __hiloint2double(0x43300000, v ^ (int)0x80000000) - 4503601774854144.0;  // (2^52 + 2^31 + v) - (2^52 + 2^31)
-}
-// 1 / b for b > 0: the 20-bit hardware seed refined by two Newton steps (relative error ~2^-52)
+// 1 / b for b > 0: the hardware seed (MUFU.RCP64H) refined by SR_SCORE_NEWTON Newton steps
+#ifndef SR_SCORE_NEWTON
+#define SR_SCORE_NEWTON 2
+#endif
 __device__ __forceinline__ double rcp_f64(double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  r = fma(r, fma(-b, r, 1.0), r);
-  r = fma(r, fma(-b, r, 1.0), r);
+#pragma unroll
+  for (int i = 0; i < SR_SCORE_NEWTON; ++i) r = fma(r, fma(-b, r, 1.0), r);
   return r;
 }
-// bits of (1.5 * 2^52 + rint(v * 2^40)): the integer sits in the mantissa, rounded to nearest even by the fma
-__device__ __forceinline__ unsigned long long fix40_bits(double v) {
-  return (unsigned long long)__double_as_longlong(fma(v, kFix, 6755399441055744.0));
+// bits of (1.5 * 2^52 + rint(num * r * 2^40)) for |num * r| <= 1: the scaling by 2^40 is an exponent increment of
+// num, the integer sits in the mantissa of the sum, rounded to nearest even by the fma
+__device__ __forceinline__ unsigned long long fix40_bits(double num, double r) {
+  const double ns = __hiloint2double(__double2hiint(num) + (40 << 20), __double2loint(num));   // num * 2^40 (num != 0)
+  return (unsigned long long)__double_as_longlong(fma(ns, r, 6755399441055744.0));
 }
 
 // column permutations that make every shared-memory access of the kernel bank-conflict free (see the kernel)
@@ -75,18 +73,19 @@ struct ScoreSmem {
 
 // SSIM of one window of a colour plane from its exact integer moments:
 //   s = Sx | Sy << 16, q = sum (x^2 + y^2), d2 = sum (x - y)^2   (so 2 Sxy = q - d2)
-// SSIM = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)), u = S / 49, v = (49 S2 - S S) / (48 * 49):
-// both factors scaled to integers (10^4 * 49^2 and 100 * 48 * 49), formed exactly, then one fp64 division.
+// SSIM = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)), u = S / 49, v = (49 S2 - S S) / (48 * 49).
+// With both factors scaled by 49^2 and 48 * 49 the variable parts are the exact integers 2 Sx Sy, Sx^2 + Sy^2,
+// 2 T = 49 (q - d2) - 2 Sx Sy and U = 49 q - Sx^2 - Sy^2 -- the cancellation that makes SSIM need fp64 happens in
+// integers -- and only the four sums with the scaled constants and the ratio are fp64.
 __device__ __forceinline__ unsigned long long ssim_colour_fix(uint32_t s, uint32_t q, uint32_t d2) {
+  constexpr double k1 = 49.0 * 49.0 * 6.5025, k2 = 48.0 * 49.0 * 58.5225;      // 15612.5025, 137644.92
   const uint32_t Sx = s & 0xffffu, Sy = s >> 16;
-  const uint32_t P = Sx * Sy, XY = Sx * Sx + Sy * Sy;
-  const int T2 = (int)(49u * (q - d2)) - (int)(2u * P);          // 2 * 48 * 49 * vxy
+  const uint32_t P2 = 2u * Sx * Sy, XY = Sx * Sx + Sy * Sy;
+  const int T2 = (int)(49u * (q - d2)) - (int)P2;                // 2 * 48 * 49 * vxy
   const uint32_t U = 49u * q - XY;                               // 48 * 49 * (vx + vy) >= 0
-  const double NA1 = fma(20000.0, u32_to_f64(P), 156125025.0);   // 10^4 (2 Sx Sy + 49^2 C1), C1 = 6.5025
-  const double NB1 = fma(10000.0, u32_to_f64(XY), 156125025.0);
-  const double NA2 = fma(100.0, s32_to_f64(T2), 13764492.0);     // 100 (2 T + 2352 C2), C2 = 58.5225
-  const double NB2 = fma(100.0, u32_to_f64(U), 13764492.0);
-  return fix40_bits((NA1 * NA2) * rcp_f64(NB1 * NB2));
+  const double A1 = (double)P2 + k1, B1 = (double)XY + k1;
+  const double A2 = (double)T2 + k2, B2 = (double)U + k2;
+  return fix40_bits(A1 * A2, rcp_f64(B1 * B2));
 }
 
 // The same for Y = 16 + Z / 255000 from the integer moments of Z (second moments need 64 bits):
@@ -99,10 +98,10 @@ __device__ __forceinline__ unsigned long long ssim_y_fix(uint32_t sa, uint32_t s
   const unsigned long long pa = (unsigned long long)sa * sa, pb = (unsigned long long)sb * sb;
   const unsigned long long U = 49ull * q - pa - pb;                                        // Txx + Tyy >= 0
   const long long T2 = (long long)(49ull * (q - d2) - 2ull * ((unsigned long long)sa * sb));  // 2 Txy
-  const double ux = fma(u32_to_f64(sa), inv49k, 16.0), uy = fma(u32_to_f64(sb), inv49k, 16.0);
+  const double ux = fma((double)sa, inv49k, 16.0), uy = fma((double)sb, inv49k, 16.0);
   const double A1 = fma(2.0 * ux, uy, C1), B1 = fma(ux, ux, fma(uy, uy, C1));
   const double A2 = fma((double)T2, invv, C2), B2 = fma((double)U, invv, C2);
-  return fix40_bits((A1 * A2) * rcp_f64(B1 * B2));
+  return fix40_bits(A1 * A2, rcp_f64(B1 * B2));
 }
 
 // Fused scoring of one image pair in EXACT INTEGER window arithmetic (reference: scorpath.py:174-228).
@@ -135,50 +134,77 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
   const int nwy = ch_ - kWin + 1, nwx = cw_ - kWin + 1;             // valid windows per axis
   const int bx0 = blockIdx.x * kBW, cy0 = blockIdx.y * chunk_rows;  // first owned pixel = first window of the block
 
-  // ---- convert: pixel k of this thread is index tid + 128 k of the step's 8 x 38 pixels
-  constexpr int kPixPerThread = (kRS * kPC + kScoreThreads - 1) / kScoreThreads;   // 3
-  int p_r[kPixPerThread], p_c[kPixPerThread];
-  uint32_t raw[kPixPerThread][2];                                   // a / b bytes of the prefetched pixels
+  // ---- convert (the three colour warps; the Y warp's H and V passes are the longer ones): pixel k of a thread
+  // is index ctid + 96 k of the step's 8 x 38 pixels.  The three bytes of a pixel come from the one or two aligned
+  // 32-bit words that hold them (funnel shift); a step advances every pointer by 8 rows = 24 w bytes, a multiple
+  // of four, so the alignment of a pixel is the same in every step.
+  constexpr int kConvThreads = 96, kPixPerThread = (kRS * kPC + kConvThreads - 1) / kConvThreads;   // 4 (the 4th: 16 threads)
+  const int ctid = role * 32 + lane;                   // only used when role < 3
+  uint32_t p_wa[kPixPerThread], p_wb[kPixPerThread];   // byte offset of the pixel's first aligned word from base_a / base_b
+  uint32_t p_inf[kPixPerThread];                       // shift of a | shift of b << 8 | row in the step (255: none) << 16 | owned column << 24
+  int p_so[kPixPerThread];                             // shared-memory word offset
+  uint32_t raw[kPixPerThread][4];                      // prefetched words: a lo, a hi, b lo, b hi
+  const uint8_t* blk_a = a + ((size_t)(cy0 + crop) * w + (bx0 + crop)) * 3;     // the block's first pixel, step 0
+  const uint8_t* blk_b = b + ((size_t)(cy0 + crop) * w + (bx0 + crop)) * 3;
+  const uint32_t da = (uint32_t)(reinterpret_cast<uintptr_t>(blk_a) & 3u), db = (uint32_t)(reinterpret_cast<uintptr_t>(blk_b) & 3u);
+  const uint8_t* base_a = blk_a - da;                  // aligned down; advanced by 24 w bytes per step
+  const uint8_t* base_b = blk_b - db;
 #pragma unroll
   for (int k = 0; k < kPixPerThread; ++k) {
-    const int idx = tid + k * kScoreThreads;
-    p_r[k] = idx / kPC;
-    p_c[k] = idx - p_r[k] * kPC;
+    const int idx = ctid + k * kConvThreads;
+    const int r = idx / kPC, c = idx - r * kPC;
+    const bool on = role < 3 && r < kRS && bx0 + c < cw_;        // columns right of the image stay zero
+    const uint32_t oa = da + (uint32_t)(r * w + c) * 3u, ob = db + (uint32_t)(r * w + c) * 3u;
+    p_wa[k] = oa & ~3u;
+    p_wb[k] = ob & ~3u;
+    p_inf[k] = ((oa & 3u) * 8u) | (((ob & 3u) * 8u) << 8) | ((uint32_t)(on ? r : 255) << 16) | ((c < kBW ? 1u : 0u) << 24);
+    p_so[k] = r * kPxStride + px_col(c);
+    raw[k][0] = raw[k][1] = raw[k][2] = raw[k][3] = 0u;
   }
+  const size_t step_bytes = (size_t)kRS * w * 3;
+  // fetch only LOADS (no use of the loaded words): they are consumed one step later by convert()
   auto fetch = [&](int step) {
+    const int rows_left = ch_ - cy0 - step * kRS;      // image rows from the step's first row on
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-      const int y = cy0 + step * kRS + p_r[k], x = bx0 + p_c[k];
-      uint32_t va = 0, vb = 0;
-      if (p_r[k] < kRS && y < ch_ && x < cw_) {
-        const size_t o = ((size_t)(y + crop) * w + (x + crop)) * 3;
-        va = a[o] | ((uint32_t)a[o + 1] << 8) | ((uint32_t)a[o + 2] << 16);
-        vb = b[o] | ((uint32_t)b[o + 1] << 8) | ((uint32_t)b[o + 2] << 16);
+      const int r = (int)((p_inf[k] >> 16) & 255u);
+      if (r < rows_left) {                             // r = 255 for pixels this thread does not convert
+        const uint32_t* qa = reinterpret_cast<const uint32_t*>(base_a + p_wa[k]);
+        const uint32_t* qb = reinterpret_cast<const uint32_t*>(base_b + p_wb[k]);
+        raw[k][0] = qa[0];
+        if ((p_inf[k] & 0x10u) != 0u) raw[k][1] = qa[1];          // shift 16 or 24: the bytes spill into the next word
+        raw[k][2] = qb[0];
+        if ((p_inf[k] & 0x1000u) != 0u) raw[k][3] = qb[1];
+      } else {
+        raw[k][0] = raw[k][2] = 0u;                    // rows below the image: zero pixels (shift in zeros too)
+        raw[k][1] = raw[k][3] = 0u;
       }
-      raw[k][0] = va;
-      raw[k][1] = vb;
     }
+    base_a += step_bytes;
+    base_b += step_bytes;
   };
   unsigned long long ssd = 0;
   auto convert = [&](int step) {
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-      if (p_r[k] < kRS) {
-        const uint32_t va = raw[k][0], vb = raw[k][1];
-        const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = va >> 16;
-        const uint32_t br = vb & 0xffu, bg = (vb >> 8) & 0xffu, bb = vb >> 16;
+      if (k < kPixPerThread - 1 || ctid < kRS * kPC - (kPixPerThread - 1) * kConvThreads) {
+        const uint32_t va = __funnelshift_r(raw[k][0], raw[k][1], p_inf[k] & 31u);
+        const uint32_t vb = __funnelshift_r(raw[k][2], raw[k][3], (p_inf[k] >> 8) & 31u);
+        const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = (va >> 16) & 0xffu;
+        const uint32_t br = vb & 0xffu, bg = (vb >> 8) & 0xffu, bb = (vb >> 16) & 0xffu;
         const uint32_t za = 65481u * ar + 128553u * ag + 24966u * ab;
         const uint32_t zb = 65481u * br + 128553u * bg + 24966u * bb;
-        const int o = p_r[k] * kPxStride + px_col(p_c[k]);
-        (&sm.px[0][0][0])[o] = ar | (br << 16);
-        (&sm.px[1][0][0])[o] = ag | (bg << 16);
-        (&sm.px[2][0][0])[o] = ab | (bb << 16);
-        (&sm.px[3][0][0])[o] = za;
-        (&sm.px[4][0][0])[o] = zb;
-        // squared Y error of the pixels this block owns (zero-filled pixels outside the image add nothing)
-        if (p_c[k] < kBW && step * kRS + p_r[k] < chunk_rows) {
-          const long long d = (long long)za - (long long)zb;
-          ssd += (unsigned long long)(d * d);
+        uint32_t* o = &sm.px[0][0][0] + p_so[k];
+        constexpr int kPl = kRS * kPxStride;
+        o[0] = ar | (br << 16);
+        o[kPl] = ag | (bg << 16);
+        o[2 * kPl] = ab | (bb << 16);
+        o[3 * kPl] = za;
+        o[4 * kPl] = zb;
+        // squared Y error of the pixels this block owns (zero pixels outside the image add nothing)
+        if ((p_inf[k] >> 24) != 0u && step * kRS + (int)((p_inf[k] >> 16) & 255u) < chunk_rows) {
+          const int d = (int)za - (int)zb;
+          ssd += (unsigned long long)((long long)d * d);
         }
       }
     }
@@ -188,21 +214,24 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
   const int hr = lane >> 2, hseg = lane & 3;                    // H: pixel row of the step, 8-column segment
   const int h_in0 = hr * kPxStride + hseg;                      // px_col(8 seg + i)     = 4 i + seg        (i < 8)
   const int h_in1 = hr * kPxStride + (hseg == 3 ? 32 : hseg + 1);   // px_col(8 seg + 8 + i) = 4 i + this   (i < 6)
-  const int h_out = hseg;                                       // hs_col(8 seg + j)     = 4 j + seg
+  const int h_out = hr * kHsStride + hseg;                      // hs_col(8 seg + j)     = 4 j + seg
   const int v_col = hs_col(lane);                               // V: window column = lane
-  const bool col_ok = bx0 + lane < nwx;
-  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;                      // vertical sums: colour {s, q, d2}; Y {sa, sb} + 64-bit pair
+  // window rows of the chunk this lane scores: [0, wend) (none for a column right of the last window)
+  const int wend = bx0 + lane < nwx ? min(chunk_rows, nwy - cy0) : 0;
+  uint32_t w0 = 0, w1 = 0, w2 = 0;                              // vertical sums: colour {s, q, d2}; Y {sa, sb} + 64-bit pair
   unsigned long long wq = 0, wd = 0;
   unsigned long long acc = 0;                                   // sum of fix40_bits (bias removed at the end)
-  unsigned int nacc = 0;
+  constexpr int kPlane = kSlots * kHsStride;
 
-  fetch(0);
-  convert(0);
+  if (role < 3) {
+    fetch(0);
+    convert(0);
+  }
   __syncthreads();
 
   for (int step = 0; step < steps; ++step) {
-    if (step + 1 < steps) fetch(step + 1);
-    const int slot0 = (step * kRS) & (kSlots - 1);              // ring slot of the step's first pixel row (0 or 8)
+    if (role < 3 && step + 1 < steps) fetch(step + 1);
+    const int half = (step & 1) * kRS * kHsStride;              // the step's 8 rows: ring slots 0-7 or 8-15
 
     // ---- H: horizontal 7-sums of the step's 8 pixel rows
     if (role < 3) {
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
         mq[i] = x * x + y * y;
         md[i] = (uint32_t)(d * d);
       }
-      uint32_t* o0 = &sm.hs[3 * role][slot0 + hr][h_out];
+      uint32_t* o0 = &sm.hs[3 * role][0][0] + half + h_out;
       uint32_t s = 0, q = 0, d2 = 0;
 #pragma unroll
       for (int i = 0; i < 7; ++i) { s += ms[i]; q += mq[i]; d2 += md[i]; }
@@ -225,8 +254,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
       for (int j = 0; j < 8; ++j) {
         if (j > 0) { s += ms[j + 6] - ms[j - 1]; q += mq[j + 6] - mq[j - 1]; d2 += md[j + 6] - md[j - 1]; }
         o0[4 * j] = s;
-        o0[kSlots * kHsStride + 4 * j] = q;
-        o0[2 * kSlots * kHsStride + 4 * j] = d2;
+        o0[kPlane + 4 * j] = q;
+        o0[2 * kPlane + 4 * j] = d2;
       }
     } else {
       const uint32_t* ina = &sm.px[3][0][0];
@@ -238,13 +267,13 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
         za[i] = ina[o];
         zb[i] = inb[o];
       }
-      uint32_t* o0 = &sm.hs[9][slot0 + hr][h_out];
+      uint32_t* o0 = &sm.hs[9][0][0] + half + h_out;
       uint32_t sa = 0, sb = 0;
       unsigned long long q = 0, d2 = 0;
       auto mom_q = [](uint32_t x, uint32_t y) { return (unsigned long long)x * x + (unsigned long long)y * y; };
       auto mom_d = [](uint32_t x, uint32_t y) {
-        const long long d = (long long)x - (long long)y;
-        return (unsigned long long)(d * d);
+        const int d = (int)x - (int)y;
+        return (unsigned long long)((long long)d * d);
       };
 #pragma unroll
       for (int i = 0; i < 7; ++i) { sa += za[i]; sb += zb[i]; q += mom_q(za[i], zb[i]); d2 += mom_d(za[i], zb[i]); }
@@ -257,67 +286,60 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
           d2 += mom_d(za[j + 6], zb[j + 6]) - mom_d(za[j - 1], zb[j - 1]);
         }
         o0[4 * j] = sa;
-        o0[kSlots * kHsStride + 4 * j] = sb;
-        o0[2 * kSlots * kHsStride + 4 * j] = (uint32_t)q;
-        o0[3 * kSlots * kHsStride + 4 * j] = (uint32_t)(q >> 32);
-        o0[4 * kSlots * kHsStride + 4 * j] = (uint32_t)d2;
-        o0[5 * kSlots * kHsStride + 4 * j] = (uint32_t)(d2 >> 32);
+        o0[kPlane + 4 * j] = sb;
+        o0[2 * kPlane + 4 * j] = (uint32_t)q;
+        o0[3 * kPlane + 4 * j] = (uint32_t)(q >> 32);
+        o0[4 * kPlane + 4 * j] = (uint32_t)d2;
+        o0[5 * kPlane + 4 * j] = (uint32_t)(d2 >> 32);
       }
     }
     __syncthreads();                         // row sums of the step are in the ring; the pixel buffer is free
-    if (step + 1 < steps) convert(step + 1);
+    if (role < 3 && step + 1 < steps) convert(step + 1);
 
-    // ---- V: vertical 7-row sums carried in registers, SSIM of the window rows that complete in this step
+    // ---- V: vertical 7-row sums carried in registers, SSIM of the window rows that complete in this step.
+    // Pixel row j of the step is ring row half + j; the row seven up is row j + 1 of the OTHER half (j < 7) or
+    // row 0 of this half (j = 7): every address is a base plus an immediate.
     {
-      const int row0 = step * kRS;           // chunk-relative index of the step's first pixel row
-      constexpr int kPlane = kSlots * kHsStride;
+      const int wrow0 = step * kRS - (kWin - 1);   // window row completed by the step's first pixel row
+      const bool first = step == 0;                // rows 0..6 of the chunk have nothing to subtract / complete
       if (role < 3) {
-        const uint32_t* base = &sm.hs[3 * role][0][v_col];
+        const uint32_t* cur = &sm.hs[3 * role][0][0] + half + v_col;
+        const uint32_t* oth = &sm.hs[3 * role][0][0] + (half ^ (kRS * kHsStride)) + v_col;
 #pragma unroll
         for (int j = 0; j < kRS; ++j) {
-          const int rho = row0 + j;
-          const uint32_t* n = base + ((slot0 + j) & (kSlots - 1)) * kHsStride;
+          const uint32_t* n = cur + j * kHsStride;
           w0 += n[0]; w1 += n[kPlane]; w2 += n[2 * kPlane];
-          if (rho >= kWin) {
-            const uint32_t* o = base + ((slot0 + j - kWin) & (kSlots - 1)) * kHsStride;
+          if (j == kRS - 1 || !first) {
+            const uint32_t* o = j == kRS - 1 ? cur : oth + (j + 1) * kHsStride;
             w0 -= o[0]; w1 -= o[kPlane]; w2 -= o[2 * kPlane];
           }
-          const int wrow = rho - (kWin - 1);
-          if (wrow >= 0 && wrow < chunk_rows && cy0 + wrow < nwy && col_ok) {
-            acc += ssim_colour_fix(w0, w1, w2);
-            ++nacc;
-          }
+          if ((j >= kWin - 1 || !first) && wrow0 + j < wend) acc += ssim_colour_fix(w0, w1, w2);
         }
       } else {
-        const uint32_t* base = &sm.hs[9][0][v_col];
+        const uint32_t* cur = &sm.hs[9][0][0] + half + v_col;
+        const uint32_t* oth = &sm.hs[9][0][0] + (half ^ (kRS * kHsStride)) + v_col;
 #pragma unroll
         for (int j = 0; j < kRS; ++j) {
-          const int rho = row0 + j;
-          const uint32_t* n = base + ((slot0 + j) & (kSlots - 1)) * kHsStride;
+          const uint32_t* n = cur + j * kHsStride;
           w0 += n[0]; w1 += n[kPlane];
           wq += (unsigned long long)n[2 * kPlane] | ((unsigned long long)n[3 * kPlane] << 32);
           wd += (unsigned long long)n[4 * kPlane] | ((unsigned long long)n[5 * kPlane] << 32);
-          if (rho >= kWin) {
-            const uint32_t* o = base + ((slot0 + j - kWin) & (kSlots - 1)) * kHsStride;
+          if (j == kRS - 1 || !first) {
+            const uint32_t* o = j == kRS - 1 ? cur : oth + (j + 1) * kHsStride;
             w0 -= o[0]; w1 -= o[kPlane];
             wq -= (unsigned long long)o[2 * kPlane] | ((unsigned long long)o[3 * kPlane] << 32);
             wd -= (unsigned long long)o[4 * kPlane] | ((unsigned long long)o[5 * kPlane] << 32);
           }
-          const int wrow = rho - (kWin - 1);
-          if (wrow >= 0 && wrow < chunk_rows && cy0 + wrow < nwy && col_ok) {
-            acc += ssim_y_fix(w0, w1, wq, wd);
-            ++nacc;
-          }
+          if ((j >= kWin - 1 || !first) && wrow0 + j < wend) acc += ssim_y_fix(w0, w1, wq, wd);
         }
       }
     }
     __syncthreads();                         // the next step's pixels are staged; ring rows older than 7 are free
   }
-  (void)w3;
 
   // ---- reduction: integers, so the order does not matter.  One atomic per warp and accumulator, then the last
   // block (ticket) converts.
-  acc -= (unsigned long long)nacc * kFixBias;
+  acc -= (unsigned long long)(wend > 0 ? wend : 0) * kFixBias;   // every scored window added the bias once
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -44,22 +44,27 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// 1 / b for b > 0: the hardware seed (MUFU.RCP64H) refined by SR_SCORE_NEWTON Newton steps
-#ifndef SR_SCORE_NEWTON
-#define SR_SCORE_NEWTON 2
+// bits of (1.5 * 2^52 + rint(2^40 * num / den)) for den > 0, |num / den| <= 1.
+//   * the reciprocal is the hardware seed r0 (MUFU.RCP64H, relative error e with |e| < 2^-20) corrected
+//     SR_SCORE_DIV_TERMS times: num / den = num r0 / (1 - e) = num r0 (1 + e + e^2 + ...), e = 1 - den r0; two
+//     terms leave a relative error e^3 < 2^-60, below the fp64 rounding of the operands.  The chain is
+//     seed -> e -> (e + e^2) -> quotient; num r0 does not wait for e.
+//   * the scaling by 2^40 is an exponent increment of num (no multiplication); the integer then sits in the
+//     mantissa of the sum with 1.5 * 2^52, rounded to nearest even by that addition.
+#ifndef SR_SCORE_BLOCKS_PER_SM
+#define SR_SCORE_BLOCKS_PER_SM 4   // blocks the launch aims at per SM (= the resident blocks: one wave)
 #endif
-__device__ __forceinline__ double rcp_f64(double b) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-#pragma unroll
-  for (int i = 0; i < SR_SCORE_NEWTON; ++i) r = fma(r, fma(-b, r, 1.0), r);
-  return r;
-}
-// bits of (1.5 * 2^52 + rint(num * r * 2^40)) for |num * r| <= 1: the scaling by 2^40 is an exponent increment of
-// num, the integer sits in the mantissa of the sum, rounded to nearest even by the fma
-__device__ __forceinline__ unsigned long long fix40_bits(double num, double r) {
+#ifndef SR_SCORE_DIV_TERMS
+#define SR_SCORE_DIV_TERMS 2
+#endif
+__device__ __forceinline__ unsigned long long fix40_div_bits(double num, double den) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
   const double ns = __hiloint2double(__double2hiint(num) + (40 << 20), __double2loint(num));   // num * 2^40 (num != 0)
-  return (unsigned long long)__double_as_longlong(fma(ns, r, 6755399441055744.0));
+  const double t = ns * r0;
+  const double e = fma(-den, r0, 1.0);
+  const double p = SR_SCORE_DIV_TERMS >= 2 ? fma(e, e, e) : e;
+  return (unsigned long long)__double_as_longlong(fma(t, p, t) + 6755399441055744.0);
 }
 
 // column permutations that make every shared-memory access of the kernel bank-conflict free (see the kernel)
@@ -85,7 +90,7 @@ __device__ __forceinline__ unsigned long long ssim_colour_fix(uint32_t s, uint32
   const uint32_t U = 49u * q - XY;                               // 48 * 49 * (vx + vy) >= 0
   const double A1 = (double)P2 + k1, B1 = (double)XY + k1;
   const double A2 = (double)T2 + k2, B2 = (double)U + k2;
-  return fix40_bits(A1 * A2, rcp_f64(B1 * B2));
+  return fix40_div_bits(A1 * A2, B1 * B2);
 }
 
 // The same for Y = 16 + Z / 255000 from the integer moments of Z (second moments need 64 bits):
@@ -101,7 +106,7 @@ __device__ __forceinline__ unsigned long long ssim_y_fix(uint32_t sa, uint32_t s
   const double ux = fma((double)sa, inv49k, 16.0), uy = fma((double)sb, inv49k, 16.0);
   const double A1 = fma(2.0 * ux, uy, C1), B1 = fma(ux, ux, fma(uy, uy, C1));
   const double A2 = fma((double)T2, invv, C2), B2 = fma((double)U, invv, C2);
-  return fix40_bits(A1 * A2, rcp_f64(B1 * B2));
+  return fix40_div_bits(A1 * A2, B1 * B2);
 }
 
 // Fused scoring of one image pair in EXACT INTEGER window arithmetic (reference: scorpath.py:174-228).
@@ -157,52 +162,51 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
     const uint32_t oa = da + (uint32_t)(r * w + c) * 3u, ob = db + (uint32_t)(r * w + c) * 3u;
     p_wa[k] = oa & ~3u;
     p_wb[k] = ob & ~3u;
-    p_inf[k] = ((oa & 3u) * 8u) | (((ob & 3u) * 8u) << 8) | ((uint32_t)(on ? r : 255) << 16) | ((c < kBW ? 1u : 0u) << 24);
+    p_inf[k] = ((oa & 3u) * 8u) | (((ob & 3u) * 8u) << 8) | ((uint32_t)(on ? r : 255) << 16) | ((on && c < kBW ? 1u : 0u) << 24);
     p_so[k] = r * kPxStride + px_col(c);
     raw[k][0] = raw[k][1] = raw[k][2] = raw[k][3] = 0u;
   }
   const size_t step_bytes = (size_t)kRS * w * 3;
-  // fetch only LOADS (no use of the loaded words): they are consumed one step later by convert()
+  // fetch only LOADS, straight into the registers convert() reads one step later (no other use, no merge with a
+  // zero: a pixel below the image keeps the stale words of the step before -- such pixels only reach windows that
+  // are not scored, and the squared error below is guarded by own_rows)
   auto fetch = [&](int step) {
     const int rows_left = ch_ - cy0 - step * kRS;      // image rows from the step's first row on
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-      const int r = (int)((p_inf[k] >> 16) & 255u);
-      if (r < rows_left) {                             // r = 255 for pixels this thread does not convert
-        const uint32_t* qa = reinterpret_cast<const uint32_t*>(base_a + p_wa[k]);
-        const uint32_t* qb = reinterpret_cast<const uint32_t*>(base_b + p_wb[k]);
-        raw[k][0] = qa[0];
-        if ((p_inf[k] & 0x10u) != 0u) raw[k][1] = qa[1];          // shift 16 or 24: the bytes spill into the next word
-        raw[k][2] = qb[0];
-        if ((p_inf[k] & 0x1000u) != 0u) raw[k][3] = qb[1];
-      } else {
-        raw[k][0] = raw[k][2] = 0u;                    // rows below the image: zero pixels (shift in zeros too)
-        raw[k][1] = raw[k][3] = 0u;
-      }
+      const int r = (int)((p_inf[k] >> 16) & 255u);    // 255 for pixels this thread does not convert
+      const bool ok = r < rows_left;
+      const uint32_t* qa = reinterpret_cast<const uint32_t*>(base_a + p_wa[k]);
+      const uint32_t* qb = reinterpret_cast<const uint32_t*>(base_b + p_wb[k]);
+      if (ok) raw[k][0] = qa[0];
+      if (ok && (p_inf[k] & 0x10u) != 0u) raw[k][1] = qa[1];      // shift 16 or 24: the bytes spill into the next word
+      if (ok) raw[k][2] = qb[0];
+      if (ok && (p_inf[k] & 0x1000u) != 0u) raw[k][3] = qb[1];
     }
     base_a += step_bytes;
     base_b += step_bytes;
   };
   unsigned long long ssd = 0;
+  const int own_rows = min(chunk_rows, ch_ - cy0);     // pixel rows of the chunk this block owns
   auto convert = [&](int step) {
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
       if (k < kPixPerThread - 1 || ctid < kRS * kPC - (kPixPerThread - 1) * kConvThreads) {
-        const uint32_t va = __funnelshift_r(raw[k][0], raw[k][1], p_inf[k] & 31u);
-        const uint32_t vb = __funnelshift_r(raw[k][2], raw[k][3], (p_inf[k] >> 8) & 31u);
-        const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = (va >> 16) & 0xffu;
-        const uint32_t br = vb & 0xffu, bg = (vb >> 8) & 0xffu, bb = (vb >> 16) & 0xffu;
+        const uint32_t va = __funnelshift_r(raw[k][0], raw[k][1], p_inf[k] & 31u) & 0xffffffu;   // r | g << 8 | b << 16
+        const uint32_t vb = __funnelshift_r(raw[k][2], raw[k][3], (p_inf[k] >> 8) & 31u) & 0xffffffu;
+        const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = va >> 16;
+        const uint32_t br = vb & 0xffu, bg = (vb >> 8) & 0xffu, bb = vb >> 16;
         const uint32_t za = 65481u * ar + 128553u * ag + 24966u * ab;
         const uint32_t zb = 65481u * br + 128553u * bg + 24966u * bb;
         uint32_t* o = &sm.px[0][0][0] + p_so[k];
         constexpr int kPl = kRS * kPxStride;
-        o[0] = ar | (br << 16);
-        o[kPl] = ag | (bg << 16);
-        o[2 * kPl] = ab | (bb << 16);
+        o[0] = __byte_perm(va, vb, 0x3430);            // a.r | b.r << 16 (byte 3 of va is zero)
+        o[kPl] = __byte_perm(va, vb, 0x3531);
+        o[2 * kPl] = __byte_perm(va, vb, 0x3632);
         o[3 * kPl] = za;
         o[4 * kPl] = zb;
-        // squared Y error of the pixels this block owns (zero pixels outside the image add nothing)
-        if ((p_inf[k] >> 24) != 0u && step * kRS + (int)((p_inf[k] >> 16) & 255u) < chunk_rows) {
+        // squared Y error of the pixels this block owns
+        if ((p_inf[k] >> 24) != 0u && step * kRS + (int)((p_inf[k] >> 16) & 255u) < own_rows) {
           const int d = (int)za - (int)zb;
           ssd += (unsigned long long)((long long)d * d);
         }
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
   const int wend = bx0 + lane < nwx ? min(chunk_rows, nwy - cy0) : 0;
   uint32_t w0 = 0, w1 = 0, w2 = 0;                              // vertical sums: colour {s, q, d2}; Y {sa, sb} + 64-bit pair
   unsigned long long wq = 0, wd = 0;
-  unsigned long long acc = 0;                                   // sum of fix40_bits (bias removed at the end)
+  unsigned long long acc = 0;                                   // sum of fix40_div_bits (bias removed at the end)
   constexpr int kPlane = kSlots * kHsStride;
 
   if (role < 3) {
@@ -415,7 +419,7 @@ extern "C" int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w
   // bands of 32 columns x chunks of rows: about one resident wave of blocks (4 per SM) on a large image, chunks of
   // at least 26 window rows on a small one; a chunk is processed in steps of 8 pixel rows (chunk + 6 halo rows)
   const int bands = (cw_ + kBW - 1) / kBW;
-  int chunks = (148 * 4 + bands / 2) / bands;
+  int chunks = (148 * SR_SCORE_BLOCKS_PER_SM + bands / 2) / bands;
   const int max_chunks = (ch_ + 25) / 26;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

@@ -102,7 +102,7 @@ def test_scorpath_main_on_directory(tmp_path, capsys):
 def test_scoring_is_bit_reproducible_and_handles_odd_sizes():
     """All cross-block sums of the scoring kernel are 64-bit integer atomics (exact integer window arithmetic,
     2^-40 fixed-point SSIM values): repeated runs give bit-identical results whatever order the blocks finish in,
-    and sizes that are not multiples of the 32 x 26 block tile agree with the oracle like the others."""
+    and sizes that are not multiples of the 32-column band or the 8-row step agree with the oracle like the others."""
     from oracle import scoring as osc
     from sr100 import ops
     rng = np.random.default_rng(11)
@@ -119,3 +119,44 @@ def test_scoring_is_bit_reproducible_and_handles_odd_sizes():
     big_b = torch.randint(0, 256, (1356, 2040, 3), dtype=torch.uint8, device="cuda")
     r = [ops.score_pair(big_a, big_b) for _ in range(4)]
     assert all(x == r[0] for x in r)
+
+
+def test_scoring_band_and_chunk_geometry():
+    """The scoring kernel walks 32-column bands in chunks of rows (8 pixel rows per step): shapes whose last band has
+    pixels but no window (cropped width 33..38), the smallest legal image (7 x 7), tall narrow images (many chunks,
+    one band), images shorter than one step, the extreme pixel values (largest 64-bit Y moments) and base pointers
+    that are not 4-byte aligned (the pixel bytes come from aligned word loads + funnel shift)."""
+    from oracle import scoring as osc
+    from sr100 import ops
+    rng = np.random.default_rng(21)
+    cases = [(7, 7, 0), (8, 39, 0), (40, 33, 0), (40, 38, 0), (41, 71, 0), (900, 20, 0), (1500, 41, 3), (13, 300, 2),
+             (70, 64, 0), (64, 70, 0)]
+    for h, w, crop in cases:
+        a = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-30, 31, size=a.shape), 0, 255).astype(np.uint8)
+        r = ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), crop=crop)
+        wp, wrgb, wy = osc.score_pair(a, b, crop)
+        assert abs(r["psnr_y"] - wp) < 1e-7, (h, w, crop)
+        assert abs(r["ssim_y"] - wy) < 1e-9 and abs(r["ssim_rgb"] - wrgb) < 1e-9, (h, w, crop)
+        assert r["n_pix"] == (h - 2 * crop) * (w - 2 * crop) and r["n_win"] == (h - 2 * crop - 6) * (w - 2 * crop - 6)
+    # extremes: white vs black, white vs white-ish noise, black vs black-ish noise
+    h, w = 50, 45
+    white, black = np.full((h, w, 3), 255, np.uint8), np.zeros((h, w, 3), np.uint8)
+    near_white = (255 - rng.integers(0, 3, size=(h, w, 3))).astype(np.uint8)
+    for a, b in ((white, black), (white, near_white), (black, 255 - near_white)):
+        r = ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), crop=0)
+        wp, wrgb, wy = osc.score_pair(a, b, 0)
+        assert abs(r["psnr_y"] - wp) < 1e-7
+        assert abs(r["ssim_y"] - wy) < 1e-9 and abs(r["ssim_rgb"] - wrgb) < 1e-9
+    # misaligned base pointers: the images start 1, 2 and 3 bytes into their allocations
+    h, w = 45, 50
+    a = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-9, 10, size=a.shape), 0, 255).astype(np.uint8)
+    want = ops.score_pair(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), crop=4)
+    for oa, ob in ((1, 0), (2, 3), (3, 1)):
+        fa = torch.zeros(h * w * 3 + 8, dtype=torch.uint8, device="cuda")
+        fb = torch.zeros(h * w * 3 + 8, dtype=torch.uint8, device="cuda")
+        va, vb = fa[oa:oa + h * w * 3].view(h, w, 3), fb[ob:ob + h * w * 3].view(h, w, 3)
+        va.copy_(torch.from_numpy(a))
+        vb.copy_(torch.from_numpy(b))
+        assert ops.score_pair(va, vb, crop=4) == want

@@ -92,6 +92,7 @@ extern "C" size_t sr_abi_struct_size(int which) {
     case 8: return sizeof(sr_train_desc);
     case 9: return sizeof(sr_model_run_info);
     case 10: return sizeof(sr_stitch_tile);
+    case 11: return sizeof(sr_score_item);
     default: return 0;
   }
 }

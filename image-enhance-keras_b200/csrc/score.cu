@@ -128,11 +128,24 @@ __device__ __forceinline__ unsigned long long ssim_y_fix(uint32_t sa, uint32_t s
 //   * per-window SSIM values are accumulated as 2^-40 fixed point and all cross-block sums are 64-bit INTEGER
 //     atomics, so the result is bit-reproducible run to run; the last block to finish (ticket counter) converts
 //     the accumulators into the public double fields.
-__global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t* __restrict__ a,
-                                                                   const uint8_t* __restrict__ b, int h, int w,
-                                                                   int crop, int chunk_rows, int steps,
-                                                                   sr_score_result* __restrict__ res) {
+// One launch scores up to kScoreBatch pairs (blockIdx.z); the pairs may differ in shape, a block outside its pair's
+// bands x chunks leaves at once.
+constexpr int kScoreBatch = 32;
+struct ScoreBatchParams {
+  sr_score_item item[kScoreBatch];
+  int chunk_rows[kScoreBatch], steps[kScoreBatch], bands[kScoreBatch], chunks[kScoreBatch];
+};
+
+__global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const __grid_constant__ ScoreBatchParams B, int crop,
+                                                                   sr_score_result* __restrict__ results) {
   __shared__ ScoreSmem sm;
+  const int bands = B.bands[blockIdx.z], chunks = B.chunks[blockIdx.z];
+  if ((int)blockIdx.x >= bands || (int)blockIdx.y >= chunks) return;
+  const uint8_t* __restrict__ a = B.item[blockIdx.z].a;
+  const uint8_t* __restrict__ b = B.item[blockIdx.z].b;
+  const int h = B.item[blockIdx.z].h, w = B.item[blockIdx.z].w;
+  const int chunk_rows = B.chunk_rows[blockIdx.z], steps = B.steps[blockIdx.z];
+  sr_score_result* __restrict__ res = results + blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
   const int role = ((tid >> 5) + blockIdx.x + blockIdx.y) & 3;      // 0..2 colour plane, 3 = Y
   const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;                 // cropped size
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const uint8_t
   __syncthreads();
   if (tid == 0) {
     const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(&res->ticket), 1ull);
-    if (done == (unsigned long long)gridDim.x * gridDim.y - 1) {
+    if (done == (unsigned long long)bands * chunks - 1) {
       __threadfence();
       volatile unsigned long long* ac = gacc;
       const double kk = (double)kK * (double)kK;
@@ -410,25 +423,51 @@ extern "C" int sr_rgb2y_u8(const uint8_t* rgb, size_t npix, double* y, void* str
   return check_launch("rgb2y_kernel");
 }
 
+// geometry of one pair inside a launch that aims at `blocks_wanted` blocks for it: bands of 32 columns x chunks of
+// rows (chunks of at least 26 window rows on a small image); a chunk is walked in steps of 8 pixel rows (chunk + 6
+// halo rows)
+static void score_geometry(int h, int w, int crop, int blocks_wanted, int* bands, int* chunks, int* chunk_rows, int* steps) {
+  const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;
+  *bands = (cw_ + kBW - 1) / kBW;
+  int nch = (blocks_wanted + *bands / 2) / *bands;
+  const int max_chunks = (ch_ + 25) / 26;
+  if (nch > max_chunks) nch = max_chunks;
+  if (nch < 1) nch = 1;
+  int rows = (ch_ + nch - 1) / nch;
+  *steps = (rows + kWin - 1 + kRS - 1) / kRS;
+  *chunk_rows = *steps * kRS - (kWin - 1);
+  *chunks = (ch_ + *chunk_rows - 1) / *chunk_rows;
+}
+
+extern "C" int sr_score_batch_u8(const sr_score_item* items, int n, int crop, sr_score_result* results, void* stream) {
+  if (n < 0 || (n > 0 && (!items || !results))) return set_error(SR_ERR_INVALID, "sr_score_batch_u8: null pointer");
+  for (int i = 0; i < n; ++i) {
+    if (!items[i].a || !items[i].b) return set_error(SR_ERR_INVALID, "sr_score_batch_u8: null image pointer");
+    if (crop < 0 || items[i].h - 2 * crop < kWin || items[i].w - 2 * crop < kWin)
+      return set_error(SR_ERR_INVALID, "sr_score_pair_u8: image smaller than the 7x7 SSIM window after cropping");
+  }
+  for (int i0 = 0; i0 < n; i0 += kScoreBatch) {
+    const int m = n - i0 < kScoreBatch ? n - i0 : kScoreBatch;
+    // about one resident wave of blocks (SR_SCORE_BLOCKS_PER_SM per SM) over the whole launch
+    const int per_item = (148 * SR_SCORE_BLOCKS_PER_SM + m - 1) / m;
+    ScoreBatchParams B = {};
+    unsigned gx = 1, gy = 1;
+    for (int i = 0; i < m; ++i) {
+      B.item[i] = items[i0 + i];
+      score_geometry(items[i0 + i].h, items[i0 + i].w, crop, per_item, &B.bands[i], &B.chunks[i], &B.chunk_rows[i], &B.steps[i]);
+      if ((unsigned)B.bands[i] > gx) gx = (unsigned)B.bands[i];
+      if ((unsigned)B.chunks[i] > gy) gy = (unsigned)B.chunks[i];
+    }
+    if (gy > 65535u) return set_error(SR_ERR_UNSUPPORTED, "sr_score_pair_u8: image taller than 1.7 M rows");
+    score_pair_kernel<<<dim3(gx, gy, (unsigned)m), kScoreThreads, 0, as_stream(stream)>>>(B, crop, results + i0);
+    if (int rc = check_launch("score_pair_kernel")) return rc;
+  }
+  return SR_OK;
+}
+
 extern "C" int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w, int crop,
                                 sr_score_result* result, void* stream) {
   if (!a || !b || !result) return set_error(SR_ERR_INVALID, "sr_score_pair_u8: null pointer");
-  if (crop < 0 || h - 2 * crop < 7 || w - 2 * crop < 7)
-    return set_error(SR_ERR_INVALID, "sr_score_pair_u8: image smaller than the 7x7 SSIM window after cropping");
-  const int ch_ = h - 2 * crop, cw_ = w - 2 * crop;
-  // bands of 32 columns x chunks of rows: about one resident wave of blocks (4 per SM) on a large image, chunks of
-  // at least 26 window rows on a small one; a chunk is processed in steps of 8 pixel rows (chunk + 6 halo rows)
-  const int bands = (cw_ + kBW - 1) / kBW;
-  int chunks = (148 * SR_SCORE_BLOCKS_PER_SM + bands / 2) / bands;
-  const int max_chunks = (ch_ + 25) / 26;
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  int chunk_rows = (ch_ + chunks - 1) / chunks;
-  const int steps = (chunk_rows + kWin - 1 + kRS - 1) / kRS;
-  chunk_rows = steps * kRS - (kWin - 1);
-  chunks = (ch_ + chunk_rows - 1) / chunk_rows;
-  dim3 grid(bands, chunks);
-  if (grid.y > 65535u) return set_error(SR_ERR_UNSUPPORTED, "sr_score_pair_u8: image taller than 1.7 M rows");
-  score_pair_kernel<<<grid, kScoreThreads, 0, as_stream(stream)>>>(a, b, h, w, crop, chunk_rows, steps, result);
-  return check_launch("score_pair_kernel");
+  const sr_score_item item = {a, b, h, w};
+  return sr_score_batch_u8(&item, 1, crop, result, stream);
 }

@@ -87,28 +87,39 @@ def score_pair(im1, im2, cropval=10):
     return r["psnr_y"], r["ssim_rgb"], r["ssim_y"]
 
 
+def score_pairs(pairs, cropval=10):
+    """score_pair for a list of (im1, im2) pairs (shapes may differ from pair to pair): one launch and one
+    read-back for the whole list.  Returns a list of (psnrNITRE on Y, SSIM on RGB, SSIM on Y)."""
+    import torch
+    from sr100 import ops
+    dev = [(ops.to_device(np.asarray(a), torch.uint8), ops.to_device(np.asarray(b), torch.uint8)) for a, b in pairs]
+    return [(r["psnr_y"], r["ssim_rgb"], r["ssim_y"]) for r in ops.score_pairs(dev, crop=cropval)]
+
+
 def main(path_dir=DEFAULT_PATH_DIR, suffix='scaled', scale_factor=1):
     """scorpath.py:76-258: pair every file without `suffix` in its name with
-    '<stem>_<suffix>(<scale_factor>x)<ext>', score, print means."""
+    '<stem>_<suffix>(<scale_factor>x)<ext>', score, print means.  The pairs of the directory are scored in one
+    batched launch; the per-file prints keep the reference's order and wording."""
     scorlist, scorssimy, scorski = [], [], []
+    names, pairs = [], []
     for file in os.listdir(path_dir):
         pathfile = path_dir + file
         path = os.path.splitext(pathfile)
         if suffix not in pathfile:
             fileOrig = path[0] + path[1]
-            print(fileOrig)
             filenameNitre = path[0] + "_" + suffix + "(%dx)" % (scale_factor) + path[1]
-            print(filenameNitre)
-            im1 = _imread_rgb(fileOrig)
-            im2 = _imread_rgb(filenameNitre)
-            scor, ski, ski_y = score_pair(im1, im2, 10)
-            print("SCORs psnr_ski")
-            print(scor)
-            scorlist.append(scor)
-            scorski.append(ski)
-            scorssimy.append(ski_y)
-            print("SCORs SSIM Y")
-            print(ski_y)
+            names.append((fileOrig, filenameNitre))
+            pairs.append((_imread_rgb(fileOrig), _imread_rgb(filenameNitre)))
+    for (fileOrig, filenameNitre), (scor, ski, ski_y) in zip(names, score_pairs(pairs, 10)):
+        print(fileOrig)
+        print(filenameNitre)
+        print("SCORs psnr_ski")
+        print(scor)
+        scorlist.append(scor)
+        scorski.append(ski)
+        scorssimy.append(ski_y)
+        print("SCORs SSIM Y")
+        print(ski_y)
     meanPNSR = sum(scorlist) / float(len(scorlist))
     meanSKI = sum(scorski) / float(len(scorski))
     meanY = sum(scorssimy) / float(len(scorssimy))

@@ -104,6 +104,10 @@ class ScoreResult(C.Structure):
     ]
 
 
+class ScoreItem(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("h", C.c_int), ("w", C.c_int)]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [("precision", C.c_int), ("stream_lr_fp32", C.c_int), ("stream_hr_fp32", C.c_int),
                 ("a_mode", C.c_int), ("nacc", C.c_int), ("pair", C.c_int), ("use_graphs", C.c_int),
@@ -183,6 +187,7 @@ SIGNATURES = {
     "sr_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sr_rgb2y_u8": (_i, [_vp, _sz, _vp, _vp]),
     "sr_score_pair_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "sr_score_batch_u8": (_i, [_vp, _i, _i, _vp, _vp]),
     "sr_sum_sq_diff_f64": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "sr_mse_loss_grad": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
     "sr_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
@@ -253,7 +258,7 @@ def load():
         fn.restype = res
         fn.argtypes = args
     for which, struct in enumerate((ConvDesc, ConvPlanInfo, PackItem, WgradDesc, WgradPlanInfo, ScoreResult, ModelConfig,
-                                    ForwardDesc, TrainDesc, ModelRunInfo, StitchTile)):
+                                    ForwardDesc, TrainDesc, ModelRunInfo, StitchTile, ScoreItem)):
         if lib.sr_abi_struct_size(which) != C.sizeof(struct):
             raise SrError(-1, "%s: ctypes layout (%d bytes) does not match libsr100.so (%d bytes); rebuild the "
                               "library or update sr100/_lib.py" % (struct.__name__, C.sizeof(struct),

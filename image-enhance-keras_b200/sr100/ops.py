@@ -222,6 +222,38 @@ def rgb2y(img_u8):
     return y
 
 
+def _score_dict(r):
+    n = float(r.n_pix)
+    # psnrNITRE (PSNR.py:54-84): inputs > 1 are divided by 255, psnr = 10*log10(N / sum(diff^2))
+    sum_sq = r.sum_sq_y / (255.0 * 255.0)
+    psnr = 10.0 * np.log10(n / sum_sq) if sum_sq > 0 else float("inf")
+    ssim_y = r.ssim_y_sum / r.n_win
+    ssim_rgb = sum(r.ssim_rgb_sum[i] / r.n_win for i in range(3)) / 3.0
+    return dict(psnr_y=float(psnr), ssim_y=float(ssim_y), ssim_rgb=float(ssim_rgb), sum_sq_y=r.sum_sq_y,
+                n_pix=r.n_pix, n_win=r.n_win)
+
+
+def score_pairs(pairs, crop=10):
+    """Y-PSNR (psnrNITRE), Y-SSIM and RGB-SSIM of a list of (a, b) pairs of same-shaped uint8 RGB device images
+    after a `crop`-pixel border crop (the loop of scorpath.py:92-228): one launch per 32 pairs and ONE read-back
+    for all of them.  The pairs may differ in shape.  Returns a list of dicts of python floats."""
+    lib = L.require_device()
+    pairs = list(pairs)
+    if not pairs:
+        return []
+    items = (L.ScoreItem * len(pairs))()
+    for i, (a_u8, b_u8) in enumerate(pairs):
+        if a_u8.shape != b_u8.shape:
+            raise ValueError("images must have the same shape, got %s and %s" % (tuple(a_u8.shape), tuple(b_u8.shape)))
+        items[i].a, items[i].b = L.ptr(a_u8), L.ptr(b_u8)
+        items[i].h, items[i].w = int(a_u8.shape[0]), int(a_u8.shape[1])
+    size = C.sizeof(L.ScoreResult)
+    res = torch.zeros(len(pairs) * size, dtype=torch.uint8, device=pairs[0][0].device)
+    L.check(lib.sr_score_batch_u8(C.cast(items, C.c_void_p), len(pairs), crop, L.ptr(res), L.stream_ptr()))
+    raw = res.cpu().numpy().tobytes()
+    return [_score_dict(L.ScoreResult.from_buffer_copy(raw[i * size:(i + 1) * size])) for i in range(len(pairs))]
+
+
 def score_pair(a_u8, b_u8, crop=10):
     """Y-PSNR (psnrNITRE), Y-SSIM and RGB-SSIM of two same-shaped uint8 RGB device images after a
     `crop`-pixel border crop (scorpath.py:174-228).  Returns dict of python floats."""
@@ -231,15 +263,7 @@ def score_pair(a_u8, b_u8, crop=10):
     h, w, _ = a_u8.shape
     res = torch.zeros(C.sizeof(L.ScoreResult), dtype=torch.uint8, device=a_u8.device)
     L.check(lib.sr_score_pair_u8(L.ptr(a_u8), L.ptr(b_u8), h, w, crop, L.ptr(res), L.stream_ptr()))
-    r = L.ScoreResult.from_buffer_copy(res.cpu().numpy().tobytes())
-    n = float(r.n_pix)
-    # psnrNITRE (PSNR.py:54-84): inputs > 1 are divided by 255, psnr = 10*log10(N / sum(diff^2))
-    sum_sq = r.sum_sq_y / (255.0 * 255.0)
-    psnr = 10.0 * np.log10(n / sum_sq) if sum_sq > 0 else float("inf")
-    ssim_y = r.ssim_y_sum / r.n_win
-    ssim_rgb = sum(r.ssim_rgb_sum[i] / r.n_win for i in range(3)) / 3.0
-    return dict(psnr_y=float(psnr), ssim_y=float(ssim_y), ssim_rgb=float(ssim_rgb), sum_sq_y=r.sum_sq_y,
-                n_pix=r.n_pix, n_win=r.n_win)
+    return _score_dict(L.ScoreResult.from_buffer_copy(res.cpu().numpy().tobytes()))
 
 
 def sum_sq_diff(a, b):

@@ -46,7 +46,7 @@ int sr_dev_set_timeline(void* buf);
 /* sizeof of the ABI structs as compiled into the library, for bindings to check their own declarations against:
  * 0 sr_conv_desc, 1 sr_conv_plan_info_t, 2 sr_pack_item, 3 sr_wgrad_desc, 4 sr_wgrad_plan_info_t,
  * 5 sr_score_result, 6 sr_model_config, 7 sr_forward_desc, 8 sr_train_desc, 9 sr_model_run_info,
- * 10 sr_stitch_tile; 0 for anything else. */
+ * 10 sr_stitch_tile, 11 sr_score_item; 0 for anything else. */
 size_t sr_abi_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -366,6 +366,15 @@ typedef struct sr_score_result {
  * device pointer to one sr_score_result (112 bytes) which must be zeroed by the caller before the call. */
 int sr_score_pair_u8(const uint8_t* a, const uint8_t* b, int h, int w, int crop,
                      sr_score_result* result, void* stream);
+/* The same for n pairs (any mix of shapes) in one launch per 32 pairs -- the loop over a directory of
+ * scorpath.py:92-228 with one launch and one read-back instead of one per pair.  `items` is a HOST array (device
+ * image pointers inside), `results` a device array of n zeroed sr_score_result. */
+typedef struct sr_score_item {
+  const uint8_t* a;
+  const uint8_t* b;
+  int h, w;
+} sr_score_item;
+int sr_score_batch_u8(const sr_score_item* items, int n, int crop, sr_score_result* results, void* stream);
 
 /* *out += sum (a[i]-b[i])^2 in fp64 (device accumulator, zero it first): the reduction inside
  * PSNR.psnrVDSR / PSNRTorch / psnrSVLAB / psnrNITRE (PSNR.py:7-84) and models.psnr* (models.py:71-90). */

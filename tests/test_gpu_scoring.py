@@ -160,3 +160,27 @@ def test_scoring_band_and_chunk_geometry():
         va.copy_(torch.from_numpy(a))
         vb.copy_(torch.from_numpy(b))
         assert ops.score_pair(va, vb, crop=4) == want
+
+
+def test_batched_scoring_equals_per_pair_scoring():
+    """sr_score_batch_u8: any mix of shapes in one launch per 32 pairs (40 pairs here: two launches), one read-back;
+    every result is bit-identical to the pair scored on its own (the sums are integers, so the different chunking of a
+    batched launch cannot show).  scorpath.main scores a directory through this entry point
+    (test_scorpath_main_on_directory)."""
+    from sr100 import ops
+    rng = np.random.default_rng(33)
+    shapes = [(27, 27), (64, 48), (90, 33), (45, 200), (130, 71)] * 8
+    pairs = []
+    for h, w in shapes:
+        a = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-15, 16, size=a.shape), 0, 255).astype(np.uint8)
+        pairs.append((torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+    got = ops.score_pairs(pairs, crop=10)
+    want = [ops.score_pair(a, b, crop=10) for a, b in pairs]
+    assert got == want
+    assert ops.score_pairs([], crop=10) == []
+    with pytest.raises(ValueError):
+        ops.score_pairs([(pairs[0][0], pairs[1][0])], crop=10)
+    from sr100 import _lib as L
+    with pytest.raises(L.SrError):
+        ops.score_pairs([pairs[0], (pairs[0][0][:20].contiguous(), pairs[0][1][:20].contiguous())], crop=10)

@@ -57,6 +57,30 @@ def main():
     recs = [dict(kernel="score_pair_kernel", shape=[H, W], ms=round(tot / a.iters, 4),
                  gbs=round(2 * H * W * 3 / (tot / a.iters) / 1e6, 1))]
     print(json.dumps(recs[0]), flush=True)
+    # the config-3 batch: 64 pairs of 1356x2040 in two launches of 32 (1.06 GB of input: nothing stays in L2)
+    from sr100 import ops
+    import ctypes as C
+    n = 64
+    big_a = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device=dev)
+    big_b = torch.clamp(big_a.to(torch.int16) + torch.randint(-8, 9, big_a.shape, dtype=torch.int16, device=dev), 0, 255).to(torch.uint8)
+    items = (L.ScoreItem * n)()
+    for i in range(n):
+        items[i].a, items[i].b, items[i].h, items[i].w = L.ptr(big_a[i]), L.ptr(big_b[i]), H, W
+    resn = torch.zeros(n * C.sizeof(L.ScoreResult), dtype=torch.uint8, device=dev)
+    tot = 0.0
+    for _ in range(5):
+        resn.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.sr_score_batch_u8(C.cast(items, C.c_void_p), n, 10, L.ptr(resn), st()))
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    rec = dict(kernel="score_pair_kernel (64 pairs, sr_score_batch_u8)", shape=[n, H, W], ms=round(tot / 5, 4),
+               ms_per_pair=round(tot / 5 / n, 4), gbs=round(n * 2 * H * W * 3 / (tot / 5) / 1e6, 1))
+    recs.append(rec)
+    print(json.dumps(rec), flush=True)
+    del big_a, big_b
     # agreement with the oracle: SR-like noise, heavy noise, unrelated images; small and large
     from oracle import scoring as osc
     for (h, w, noise, smooth) in ((40, 37, 6, 5), (64, 48, 6, 5), (300, 200, 6, 5), (300, 200, 40, 1),

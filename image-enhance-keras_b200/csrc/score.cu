@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const __grid_
   // is index ctid + 96 k of the step's 8 x 38 pixels.  The three bytes of a pixel come from the one or two aligned
   // 32-bit words that hold them (funnel shift); a step advances every pointer by 8 rows = 24 w bytes, a multiple
   // of four, so the alignment of a pixel is the same in every step.
-  constexpr int kConvThreads = 96, kPixPerThread = (kRS * kPC + kConvThreads - 1) / kConvThreads;   // 4 (the 4th: 16 threads)
+  constexpr int kCvtThreads = 96, kPixPerThread = (kRS * kPC + kCvtThreads - 1) / kCvtThreads;   // 4 (the 4th: 16 threads)
   const int ctid = role * 32 + lane;                   // only used when role < 3
   uint32_t p_wa[kPixPerThread], p_wb[kPixPerThread];   // byte offset of the pixel's first aligned word from base_a / base_b
   uint32_t p_inf[kPixPerThread];                       // shift of a | shift of b << 8 | row in the step (255: none) << 16 | owned column << 24
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const __grid_
   const uint8_t* base_b = blk_b - db;
 #pragma unroll
   for (int k = 0; k < kPixPerThread; ++k) {
-    const int idx = ctid + k * kConvThreads;
+    const int idx = ctid + k * kCvtThreads;
     const int r = idx / kPC, c = idx - r * kPC;
     const bool on = role < 3 && r < kRS && bx0 + c < cw_;        // columns right of the image stay zero
     const uint32_t oa = da + (uint32_t)(r * w + c) * 3u, ob = db + (uint32_t)(r * w + c) * 3u;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_pair_kernel(const __grid_
   auto convert = [&](int step) {
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-      if (k < kPixPerThread - 1 || ctid < kRS * kPC - (kPixPerThread - 1) * kConvThreads) {
+      if (k < kPixPerThread - 1 || ctid < kRS * kPC - (kPixPerThread - 1) * kCvtThreads) {
         const uint32_t va = __funnelshift_r(raw[k][0], raw[k][1], p_inf[k] & 31u) & 0xffffffu;   // r | g << 8 | b << 16
         const uint32_t vb = __funnelshift_r(raw[k][2], raw[k][3], (p_inf[k] >> 8) & 31u) & 0xffffffu;
         const uint32_t ar = va & 0xffu, ag = (va >> 8) & 0xffu, ab = va >> 16;

@@ -63,13 +63,22 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// The timer is read once per 65536 failed polls, not once per poll: %globaltimer is a chip-wide resource, and with
+// every waiting thread of 148 SMs reading it between two try_waits a waiter noticed its barrier flip late -- in
+// tools/microbench/mma_vs_tma.cu that alone cost an MMA issue loop 22 % of its rate (1708 vs 2181 TFLOP/s chip-wide)
+// and a TMA ring 25 % of its bandwidth.
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  const uint64_t t0 = global_timer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > SR_MBAR_TIMEOUT_NS) {
-      printf("sr100: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
-             (int)threadIdx.x);
-      __trap();
+  uint64_t t0 = 0;
+  for (uint32_t n = 1;; ++n) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((n & 0xffffu) == 0u) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) {
+        t0 = t;
+      } else if (t - t0 > SR_MBAR_TIMEOUT_NS) {
+        printf("sr100: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }

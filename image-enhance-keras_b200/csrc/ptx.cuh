@@ -54,39 +54,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The wait is
+// FULLY INLINE -- no call, no printf, no timer: a failed try_wait already sleeps in hardware until the barrier's phase
+// flips (or ~10 ms pass), so the loop body runs a handful of times at most, and the bound is a poll count.  The
+// earlier version fell into a __noinline__ slow path that read %globaltimer; a call inside the MMA issue loop makes
+// the compiler rebuild the loop's uniform-register state (descriptors, R2UR) around it, which alone cost an issue
+// loop 25 % of its rate in tools/microbench/mma_vs_tma.cu (1635 vs 2181 TFLOP/s chip-wide for N = 128).
+#ifndef SR_MBAR_MAX_POLLS
+#define SR_MBAR_MAX_POLLS 0x10000000u
+#endif
 #ifndef SR_MBAR_TIMEOUT_NS
-#define SR_MBAR_TIMEOUT_NS 4000000000ull
+#define SR_MBAR_TIMEOUT_NS 4000000000ull   // the grid-barrier waits of the chain kernel are bounded in time
 #endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// The timer is read once per 65536 failed polls, not once per poll: %globaltimer is a chip-wide resource, and with
-// every waiting thread of 148 SMs reading it between two try_waits a waiter noticed its barrier flip late -- in
-// tools/microbench/mma_vs_tma.cu that alone cost an MMA issue loop 22 % of its rate (1708 vs 2181 TFLOP/s chip-wide)
-// and a TMA ring 25 % of its bandwidth.
-static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  uint64_t t0 = 0;
-  for (uint32_t n = 1;; ++n) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((n & 0xffffu) == 0u) {
-      const uint64_t t = global_timer_ns();
-      if (t0 == 0) {
-        t0 = t;
-      } else if (t - t0 > SR_MBAR_TIMEOUT_NS) {
-        printf("sr100: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-        __trap();
-      }
-    }
-  }
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-  for (int i = 0; i < 64; ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n == SR_MBAR_MAX_POLLS) __trap();
+  }
 }
 
 // ---------------------------------------------------------------- TMA

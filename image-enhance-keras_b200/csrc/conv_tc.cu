@@ -1128,17 +1128,12 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Spin until *counter >= target.  The poll itself is one acquire load (an L2 round trip); the bounded-wait check
-// (a protocol bug traps instead of hanging the GPU) reads the global timer only every 2048 polls.
-static __device__ __noinline__ void chain_wait_counter(const unsigned* counter, unsigned target) {
-  if (ld_acquire_gpu(counter) >= target) return;
-  const uint64_t t0 = global_timer_ns();
-  for (unsigned spins = 1;; ++spins) {
-    if (ld_acquire_gpu(counter) >= target) return;
-    if ((spins & 2047u) == 0 && global_timer_ns() - t0 > SR_MBAR_TIMEOUT_NS) {
-      printf("sr100: chain grid barrier timed out (block %d)\n", (int)blockIdx.x);
-      __trap();
-    }
+// Spin until *counter >= target.  The poll is one acquire load (an L2 round trip); inline and bounded by a poll count
+// like mbar_wait (a protocol bug traps instead of hanging the GPU; no call inside the role loops).
+__device__ __forceinline__ void chain_wait_counter(const unsigned* counter, unsigned target) {
+  unsigned spins = 0;
+  while (ld_acquire_gpu(counter) < target) {
+    if (++spins == 0x04000000u) __trap();
   }
 }
 

@@ -1128,12 +1128,13 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Spin until *counter >= target.  The poll is one acquire load (an L2 round trip); inline and bounded by a poll count
+// Spin until *counter >= target.  The poll is one acquire load (an L2 round trip); inline and bounded by the SM clock
 // like mbar_wait (a protocol bug traps instead of hanging the GPU; no call inside the role loops).
 __device__ __forceinline__ void chain_wait_counter(const unsigned* counter, unsigned target) {
-  unsigned spins = 0;
+  if (ld_acquire_gpu(counter) >= target) return;
+  const long long t0 = clock64();
   while (ld_acquire_gpu(counter) < target) {
-    if (++spins == 0x04000000u) __trap();
+    if (clock64() - t0 > SR_MBAR_TIMEOUT_CLK) __trap();
   }
 }
 

@@ -55,16 +55,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The wait is
-// FULLY INLINE -- no call, no printf, no timer: a failed try_wait already sleeps in hardware until the barrier's phase
-// flips (or ~10 ms pass), so the loop body runs a handful of times at most, and the bound is a poll count.  The
-// earlier version fell into a __noinline__ slow path that read %globaltimer; a call inside the MMA issue loop makes
-// the compiler rebuild the loop's uniform-register state (descriptors, R2UR) around it, which alone cost an issue
-// loop 25 % of its rate in tools/microbench/mma_vs_tma.cu (1635 vs 2181 TFLOP/s chip-wide for N = 128).
-#ifndef SR_MBAR_MAX_POLLS
-#define SR_MBAR_MAX_POLLS 0x10000000u
+// FULLY INLINE -- no call, no printf, no chip-wide timer: the bound is the SM's own clock (one CS2R per failed poll).
+// The earlier version fell into a __noinline__ slow path that read %globaltimer and could printf; a call inside the
+// MMA issue loop makes the compiler keep the loop's state in thread registers and rebuild the uniform registers of
+// the UTCHMMA operands around it (six R2UR per tap), which held the conv kernels at 0.73 of the tensor peak
+// (tools/microbench/mma_vs_tma.cu: 1635 vs 1924-2181 TFLOP/s chip-wide for an N = 128 issue loop).
+#ifndef SR_MBAR_TIMEOUT_CLK
+#define SR_MBAR_TIMEOUT_CLK (1ll << 33)    // ~4.4 s at 1.965 GHz
 #endif
 #ifndef SR_MBAR_TIMEOUT_NS
-#define SR_MBAR_TIMEOUT_NS 4000000000ull   // the grid-barrier waits of the chain kernel are bounded in time
+#define SR_MBAR_TIMEOUT_NS 4000000000ull   // waits on global memory (chain kernel's grid barrier, peer exchange) are bounded in time
 #endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
@@ -72,9 +72,10 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t n = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++n == SR_MBAR_MAX_POLLS) __trap();
+    if (clock64() - t0 > SR_MBAR_TIMEOUT_CLK) __trap();
   }
 }
 

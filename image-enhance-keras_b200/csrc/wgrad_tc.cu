@@ -189,7 +189,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (warp-convergent, elected lane issues)
-    if (has_work) {
+    // No `if (has_work)` around the issue loop (a CTA without units simply runs zero iterations): under that branch
+    // ptxas treated the whole loop as possibly divergent and kept ring positions, descriptors and trip counts in
+    // thread registers -- 102 R2UR between the first and the last UTCHMMA, 64 registers; without it the loop lives in
+    // uniform registers like the conv kernels' (no R2UR, 45 registers; tests/test_sass_guard.py).
+    {
       const bool leader = elect_one();
       // MN-major SW128 descriptors: LBO = bytes between the two 64-channel halves, SBO = 8 pixel rows
       const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SR_LAYOUT_SW128 << 29);
@@ -275,10 +279,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (++base == nring) base = 0;
         }
       }
-      if (leader) umma_commit(&bars->acc_full);
-      // wait for the accumulators here (one polling warp), then release the drain warps from their
-      // hardware barrier: they sleep instead of polling an mbarrier for the whole kernel
-      mbar_wait(&bars->acc_full, 0);
+      if (has_work) {
+        if (leader) umma_commit(&bars->acc_full);
+        // wait for the accumulators here (one polling warp), then release the drain warps from their
+        // hardware barrier: they sleep instead of polling an mbarrier for the whole kernel
+        mbar_wait(&bars->acc_full, 0);
+      }
     }
     __syncwarp();
     asm volatile("bar.sync 1, 160;" ::: "memory");

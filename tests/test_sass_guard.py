@@ -51,6 +51,20 @@ def test_conv_mma_issue_loops_have_no_call_and_no_r2ur(sass_functions):
     assert checked >= 25       # every conv_tc_kernel / conv_tc_pair_kernel / chain instantiation of the library
 
 
+def test_wgrad_mma_issue_loop_has_no_call_and_no_r2ur(sass_functions):
+    """Same property for the filter-gradient kernel: an `if (has_work)` around its issue loop made ptxas treat the loop as
+    possibly divergent (102 R2UR in the MMA span, 64 registers); without the branch the loop is uniform (0 R2UR, 45
+    registers) and the kernel is 3-11 % faster, bit-identical (profiles/r02_ab_wgrad_uniform_issue_loop.json)."""
+    names = [n for n in sass_functions if "wgrad_tc_kernel" in n]
+    assert names
+    for name in names:
+        span = _mma_span(sass_functions[name])
+        assert span, "no UTCHMMA in " + name
+        assert sum("CALL" in l for l in span) == 0, name
+        assert sum("R2UR" in l for l in span) == 0, "%d R2UR inside the MMA issue loop of %s" % (
+            sum("R2UR" in l for l in span), name)
+
+
 def test_waits_are_inline(sass_functions):
     """mbar_wait is __forceinline__ and nothing in ptx.cuh is __noinline__; no tensor-core kernel references vprintf (the old
     slow path printed before trapping)."""

@@ -402,6 +402,7 @@ struct WgradPlan {
 };
 
 static constexpr size_t kWgSmemBudget = 227 * 1024;
+static constexpr double kWgCostFloor = 0.0;   // see the CTA split in sr_wgrad_plan_create
 
 }  // namespace sr
 
@@ -556,9 +557,14 @@ extern "C" int sr_wgrad_plan_create(const sr_wgrad_desc* d, sr_wgrad_plan** out)
   {
     const char* e = dev_getenv("SR100_WGRAD_PCOST");
     const double pair_cost = e ? atof(e) : 1.5;    // cost of a pair item in single-tap units (measured optimum)
+    // every group streams the same X and G rows whatever its tap count: a floor on the cost is the part of a group's
+    // time that is operand ingest rather than MMA work (floor >= the largest group cost: equal CTAs per group)
+    const char* ef = dev_getenv("SR100_WGRAD_COSTFLOOR");
+    const double cost_floor = ef ? atof(ef) : kWgCostFloor;
     for (int g = 0; g < P.ngroups; ++g) {
       cost[g] = 0;
       for (int j = 0; j < P.g_nitems[g]; ++j) cost[g] += P.it_w[g][j] == 2 ? pair_cost : 1.0;
+      cost[g] = std::max(cost[g], cost_floor);
       total_cost += cost[g];
     }
   }

@@ -19,8 +19,9 @@
 //     the N side: two vertically adjacent taps (ky, kx), (ky+1, kx) read ring rows r and r+1 at the same column
 //     shift, and in the ring those are exactly one "64-channel half" stride apart four times over (half 0 / half 1
 //     of row r, half 0 / half 1 of row r+1 -- the descriptor's N-atom stride), so ONE tcgen05.mma of N = 256
-//     accumulates both taps: 12 KB of shared-memory operand reads per 2 taps instead of 16 (the kernel is bound by
-//     exactly that).  A group holds items of 1 or 2 taps; the drain transposes back.
+//     accumulates both taps: 12 KB of shared-memory operand reads per 2 taps instead of 16, and a paired tap was
+//     measured to cost 0.75 of a single one.  A group holds items of 1 or 2 taps; the drain transposes
+//     back.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

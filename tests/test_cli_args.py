@@ -60,3 +60,29 @@ def test_every_directory_entry_goes_through_upscale_step_patch(cli, tmp_path, mo
     assert calls[0] == ("init", 2)
     want_kw = dict(save_intermediate=True, scalemulti=4, patch_size=96, suffix="up")
     assert sorted(calls[1:]) == sorted([(d + "a.png", want_kw), (d + "b.bmp", want_kw)])
+
+
+def test_learn_script_builds_the_model_and_fits_180_epochs(monkeypatch):
+    """learn.py:11-22: DifvdsrDouble(1).create_model(); fit(nb_epochs=180)."""
+    spec = importlib.util.spec_from_file_location("sr_learn_under_test",
+                                                  os.path.join(ROOT, "image-enhance-keras_b200", "learn.py"))
+    learn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(learn)
+    calls = []
+
+    class FakeModel:
+        def __init__(self, scale):
+            calls.append(("init", scale))
+
+        def create_model(self):
+            calls.append(("create_model",))
+
+        def fit(self, **kw):
+            calls.append(("fit", kw))
+
+    monkeypatch.setitem(sys.modules, "models", types.SimpleNamespace(DifvdsrDouble=FakeModel))
+    learn.main([])
+    assert calls == [("init", 1), ("create_model",), ("fit", dict(nb_epochs=180))]
+    del calls[:]
+    learn.main(["3"])
+    assert calls[-1] == ("fit", dict(nb_epochs=3))

@@ -137,27 +137,24 @@ def _imread_rgb(path):
 
 
 def _index_generator(N, batch_size=32, shuffle=True, seed=None):
-    """img_utils.py:374-398: reshuffle at each epoch start, last batch short; yields
-    (index_array, current_index, current_batch_size)."""
-    batch_index = 0
-    total_batches_seen = 0
-    while 1:
+    """img_utils.py:374-398 (the Keras-1 index generator).  Yields (indices, start, count) forever.  The order is a
+    contract (batches must be bit-identical to the reference's for a given seed), so its quirks are kept:
+      * the global numpy RNG is re-seeded with seed + <batches yielded so far> before EVERY batch;
+      * a new order (permutation or arange) is drawn only when the pass counter is 0, and the counter is reset only by
+        a SHORT batch -- with N a multiple of batch_size the first order is reused for ever;
+      * a batch that would run past N is cut short (start + batch_size > N) and ends the pass.
+    Pinned to the reference's own function by tests/test_data_pipeline.py (tests/golden/generator_ref.npz)."""
+    order, in_pass, yielded = None, 0, 0
+    while True:
         if seed is not None:
-            np.random.seed(seed + total_batches_seen)
-        if batch_index == 0:
-            index_array = np.arange(N)
-            if shuffle:
-                index_array = np.random.permutation(N)
-        current_index = (batch_index * batch_size) % N
-        if N >= current_index + batch_size:
-            current_batch_size = batch_size
-            batch_index += 1
-        else:
-            current_batch_size = N - current_index
-            batch_index = 0
-        total_batches_seen += 1
-        yield (index_array[current_index: current_index + current_batch_size],
-               current_index, current_batch_size)
+            np.random.seed(seed + yielded)
+        if in_pass == 0:
+            order = np.random.permutation(N) if shuffle else np.arange(N)
+        start = (in_pass * batch_size) % N
+        count = batch_size if start + batch_size <= N else N - start
+        in_pass = in_pass + 1 if count == batch_size else 0
+        yielded += 1
+        yield order[start:start + count], start, count
 
 
 def image_generator(directory, scale_factor=2, target_shape=None, channels=3, small_train_images=False,

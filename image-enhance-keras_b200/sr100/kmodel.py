@@ -8,8 +8,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib as L
-from .engine import Engine, layer_specs
+from .engine import Engine
 
 
 class Layer:

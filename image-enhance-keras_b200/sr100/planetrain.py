@@ -22,8 +22,6 @@ LeakyReLU keeps the sign of its input, so its saved OUTPUT is the mask (sr_conv_
 gradient.  Operands bf16, accumulation fp32, master weights / gradients / Adam state fp32."""
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 

@@ -24,8 +24,6 @@ stubs (oracle/refgen_dataprep.py -> tests/golden/dataprep_ref.npz).
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 
 from . import pil_resample as pr

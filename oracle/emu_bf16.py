@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .model import NUMK, bilinear_x4_tf1, layer_specs
+from .model import bilinear_x4_tf1, layer_specs
 
 
 def _bf16(t):
